@@ -1,0 +1,132 @@
+/*
+ * lrperm.h - C ABI of the B200 permutation-null engine for ligand-receptor scoring.
+ *
+ * Drop-in boundary for the hot path of saezlab/liana-py (reference paths relative to
+ * /root/reference):
+ *
+ *   liana/method/sc/_liana_pipe.py:402-425        _run_method: cube -> gather -> score
+ *   liana/method/_pipe_utils/_get_mean_perms.py   _get_means_perms / _generate_perms_cube /
+ *                                                 _permute_and_aggregate / _calculate_pvals
+ *   liana/method/sc/_cellphonedb.py:9-30          _cpdb_score   (null side)
+ *   liana/method/sc/_geometric_mean.py:6-25       _gmean_score  (null side)
+ *   liana/method/sc/_liana_pipe.py:285-302        per-cluster observed means / props
+ *
+ * The reference is pure Python, so "the FFI a maintainer would bind" is ctypes; the stub is
+ * in INTEGRATION.md.  All entry points take plain pointers and sizes.  Every function
+ * returns an int status (LRPERM_OK == 0); nothing aborts or throws across the boundary.
+ * `lrperm_last_error` returns a human-readable message for the last non-zero status.
+ *
+ * Pointers flagged `*_on_device != 0` are CUDA device pointers in the engine's device
+ * (e.g. `torch.Tensor.data_ptr()`); otherwise they are host pointers and the engine does
+ * the copies on its stream.  One engine = one device + one stream; not thread-safe.
+ */
+#ifndef LRPERM_H
+#define LRPERM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRPERM_ABI_VERSION 1
+
+/* status codes */
+#define LRPERM_OK              0
+#define LRPERM_ERR_INVALID     1   /* bad argument / call order */
+#define LRPERM_ERR_CUDA        2   /* CUDA runtime error        */
+#define LRPERM_ERR_OOM         3   /* device allocation failed  */
+#define LRPERM_ERR_UNSUPPORTED 4   /* shape outside engine limits */
+
+/* where the permutations come from (replaces `rng.permutation(idx)`, _get_mean_perms.py:79) */
+#define LRPERM_PERMS_INDEX   0   /* caller supplies the reference's own index array perm_idx[P][N] */
+#define LRPERM_PERMS_PHILOX  1   /* engine generates them on device from (seed, global perm id)    */
+
+/* summation order of the per-(perm, cluster, gene) means (replaces _permute_and_aggregate :61-64) */
+#define LRPERM_ORDER_EXACT   0   /* the reference's order: float32, sequential in position order -> bit-identical cube */
+#define LRPERM_ORDER_FAST    1   /* float32, sequential in cell order per gene (<= 1e-5 rel. from the reference)      */
+
+/* which null scores to count (bitmask) */
+#define LRPERM_SCORE_CPDB    1   /* (a + b) / 2 >= lr_means        (_cellphonedb.py:25-28)    */
+#define LRPERM_SCORE_GMEAN   2   /* gmean(a, b) >= lr_gmeans       (_geometric_mean.py:22-23) */
+
+/* how the geometric-mean comparison is evaluated */
+#define LRPERM_GMEAN_PRODUCT 0   /* a*b >= g*g in float64 (exact for float32 inputs)          */
+#define LRPERM_GMEAN_LITERAL 1   /* exp((log a + log b)/2) >= g in float64, as scipy.stats.gmean */
+
+typedef struct lrperm_engine lrperm_engine;
+
+int         lrperm_abi_version(void);
+const char *lrperm_last_error(const lrperm_engine *h);   /* h may be NULL: error of the last failed create */
+
+/* Create / destroy an engine bound to CUDA device `device`. */
+int  lrperm_create(int device, lrperm_engine **out);
+void lrperm_destroy(lrperm_engine *h);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*; NULL = the engine's own stream). */
+int lrperm_set_stream(lrperm_engine *h, void *cuda_stream);
+
+/*
+ * The expression matrix the hot path sees: CSR float32, N cells x G genes, already subset to
+ * the resource's genes (input contract: _pipe_utils/_pre.py:65-169, _liana_pipe.py:161-164).
+ * indptr has N+1 entries of int32 (indptr_is_64 == 0) or int64; nnz must be < 2^31, G <= 65535.
+ */
+int lrperm_set_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes,
+                          const void *indptr, int indptr_is_64,
+                          const int32_t *indices, const float *data, int on_device);
+
+/* Cluster code per cell (codes of obs['@label'] in .cat.categories order, _get_mean_perms.py:47-52). */
+int lrperm_set_labels(lrperm_engine *h, const int32_t *labels, int32_t n_clusters, int on_device);
+
+/*
+ * The T rows of lr_res that reach the score function, as produced by _get_mat_idx
+ * (_get_mean_perms.py:103-113): gene column of the resolved ligand / receptor subunit and
+ * cluster index of source / target, plus the observed scores the null is compared against
+ * (float32, widened to float64 in the comparison like np.greater_equal does).  Either
+ * threshold pointer may be NULL if that score is not requested.
+ */
+int lrperm_set_triples(lrperm_engine *h, int64_t n_triples,
+                       const int32_t *ligand_idx, const int32_t *receptor_idx,
+                       const int32_t *source_idx, const int32_t *target_idx,
+                       const float *obs_cpdb, const float *obs_gmean, int on_device);
+
+/*
+ * Observed per-cluster statistics (_liana_pipe.py:285-302, _common.py:41-42):
+ * means[c*G+g] (float32, the same arithmetic as the cube with the identity permutation) and
+ * stored_counts[c*G+g] (number of stored CSR entries, explicit zeros included) ; cluster
+ * sizes n_c[c].  Any output pointer may be NULL.
+ */
+int lrperm_observed(lrperm_engine *h, float *means, int32_t *stored_counts, int32_t *cluster_sizes,
+                    int out_on_device);
+
+/*
+ * Run `n_perms` permutations and accumulate exceedance counts.
+ *   perm_source  LRPERM_PERMS_INDEX : perm_idx[p*N + j] = cell placed at position j in
+ *                                     permutation p (int32 or int64), p = 0..n_perms-1
+ *                LRPERM_PERMS_PHILOX: permutation p uses global id perm_offset + p and `seed`
+ *   counts_*[t]  number of permutations whose null score >= observed score (uint32, T entries),
+ *                OVERWRITTEN (not accumulated); NULL if that score is not requested
+ *   cube_out     optional float32 [n_perms][L][G] (the reference's `perms` cube layout), or NULL
+ */
+int lrperm_run(lrperm_engine *h, int64_t n_perms, int64_t perm_offset, uint64_t seed,
+               int perm_source, const void *perm_idx, int perm_idx_is_64, int perm_idx_on_device,
+               int order_mode, int scores, int gmean_mode,
+               uint32_t *counts_cpdb, uint32_t *counts_gmean, int counts_on_device,
+               float *cube_out, int cube_on_device);
+
+/* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32). */
+int lrperm_philox_perms(lrperm_engine *h, int64_t n_cells, int64_t n_perms, int64_t perm_offset,
+                        uint64_t seed, int32_t *out, int out_on_device);
+
+/* Device time (ms, CUDA events on the engine's stream) of the stages of the last lrperm_run:
+ * out[0] label/permutation setup, out[1] per-cluster means, out[2] score+count, out[3] total.
+ * Also number of kernel launches of the last run in out[4]. */
+int lrperm_last_timings(lrperm_engine *h, float *out5);
+
+/* Tuning knobs (0 = engine default): perms per label slab batch in FAST mode, nnz per gene chunk. */
+int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_chunk_nnz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRPERM_H */

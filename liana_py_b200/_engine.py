@@ -1,0 +1,246 @@
+"""ctypes binding of the C ABI in include/lrperm.h (the library built from csrc/lrperm_api.cu).
+
+This is the only way the Python layer reaches the GPU: there is no CPU fallback.  If the
+shared library is missing or no CUDA device is present, construction raises loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "_lib", "liblrperm.so")
+
+PERMS_INDEX, PERMS_PHILOX = 0, 1
+ORDER_EXACT, ORDER_FAST = 0, 1
+SCORE_CPDB, SCORE_GMEAN = 1, 2
+GMEAN_PRODUCT, GMEAN_LITERAL = 0, 1
+
+# every symbol include/lrperm.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = (
+    "lrperm_abi_version", "lrperm_last_error", "lrperm_create", "lrperm_destroy", "lrperm_set_stream",
+    "lrperm_set_matrix_csr", "lrperm_set_labels", "lrperm_set_triples", "lrperm_observed", "lrperm_run",
+    "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning",
+)
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load liblrperm.so (built in-tree by ``__graft_entry__.build()`` / ``liana_py_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"CUDA extension not built: {LIB_PATH} is missing. Run `python -m liana_py_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback for the permutation engine.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    lib.lrperm_abi_version.restype = C.c_int
+    lib.lrperm_last_error.restype = C.c_char_p
+    lib.lrperm_last_error.argtypes = [vp]
+    lib.lrperm_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.lrperm_destroy.argtypes = [vp]
+    lib.lrperm_destroy.restype = None
+    lib.lrperm_set_stream.argtypes = [vp, vp]
+    lib.lrperm_set_tuning.argtypes = [vp, i32, i32]
+    lib.lrperm_set_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int]
+    lib.lrperm_set_labels.argtypes = [vp, vp, i32, C.c_int]
+    lib.lrperm_set_triples.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_int]
+    lib.lrperm_observed.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.lrperm_run.argtypes = [vp, i64, i64, u64, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               vp, vp, C.c_int, vp, C.c_int]
+    lib.lrperm_philox_perms.argtypes = [vp, i64, i64, i64, u64, vp, C.c_int]
+    lib.lrperm_last_timings.argtypes = [vp, vp]
+    _lib = lib
+    return lib
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _ptr(x):
+    """(address, on_device, keepalive) for a numpy array / torch tensor / None."""
+    if x is None:
+        return None, 0, None
+    if _is_torch(x):
+        if not x.is_contiguous():
+            x = x.contiguous()
+        return C.c_void_p(x.data_ptr()), int(x.is_cuda), x
+    return C.c_void_p(x.ctypes.data), 0, x
+
+
+class Engine:
+    """One engine = one CUDA device + one stream (see include/lrperm.h)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.lrperm_create(int(device), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.lrperm_last_error(None).decode()
+            self._h = None
+            raise EngineError(f"lrperm_create failed (status {rc}): {msg}")
+        self.device = int(device)
+        self.N = self.G = self.L = self.T = 0
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.lrperm_last_error(self._h).decode()
+            if rc == 1:
+                raise ValueError(msg)
+            raise EngineError(f"status {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lrperm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        self._check(self._lib.lrperm_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_tuning(self, fast_perm_batch: int = 0, fast_chunk_nnz: int = 0):
+        self._check(self._lib.lrperm_set_tuning(self._h, int(fast_perm_batch), int(fast_chunk_nnz)))
+
+    # -- inputs ----------------------------------------------------------------------------
+    def set_matrix_csr(self, indptr, indices, data, n_cells: int, n_genes: int):
+        """CSR float32 N x G.  numpy (host) or torch CUDA tensors (device) - all three alike."""
+        if _is_torch(indptr):
+            import torch
+            is64 = indptr.dtype == torch.int64
+            assert indptr.dtype in (torch.int32, torch.int64) and indices.dtype == torch.int32 and data.dtype == torch.float32
+            assert indptr.is_cuda == indices.is_cuda == data.is_cuda
+        else:
+            indptr = np.ascontiguousarray(indptr)
+            if indptr.dtype not in (np.int32, np.int64):
+                indptr = indptr.astype(np.int64)
+            is64 = indptr.dtype == np.int64
+            indices = np.ascontiguousarray(indices, dtype=np.int32)
+            data = np.ascontiguousarray(data, dtype=np.float32)
+        p0, dev, k0 = _ptr(indptr)
+        p1, _, k1 = _ptr(indices)
+        p2, _, k2 = _ptr(data)
+        self._check(self._lib.lrperm_set_matrix_csr(self._h, int(n_cells), int(n_genes), p0, int(is64), p1, p2, dev))
+        self.N, self.G = int(n_cells), int(n_genes)
+
+    def set_matrix(self, X):
+        """SciPy CSR matrix (canonical format: sorted, no duplicate entries per row)."""
+        from scipy import sparse
+        if not sparse.isspmatrix_csr(X):
+            X = sparse.csr_matrix(X)
+        if not X.has_canonical_format:
+            X = X.copy()
+            X.sum_duplicates()
+        self.set_matrix_csr(X.indptr, X.indices, X.data, X.shape[0], X.shape[1])
+
+    def set_labels(self, labels, n_clusters: int):
+        if not _is_torch(labels):
+            labels = np.ascontiguousarray(labels, dtype=np.int32)
+        p, dev, _k = _ptr(labels)
+        self._check(self._lib.lrperm_set_labels(self._h, p, int(n_clusters), dev))
+        self.L = int(n_clusters)
+
+    def set_triples(self, ligand_idx, receptor_idx, source_idx, target_idx, obs_cpdb=None, obs_gmean=None):
+        arrs = [ligand_idx, receptor_idx, source_idx, target_idx]
+        if not _is_torch(ligand_idx):
+            arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in arrs]
+            obs_cpdb = None if obs_cpdb is None else np.ascontiguousarray(obs_cpdb, dtype=np.float32)
+            obs_gmean = None if obs_gmean is None else np.ascontiguousarray(obs_gmean, dtype=np.float32)
+        T = int(arrs[0].shape[0])
+        ptrs = [_ptr(a) for a in arrs]
+        pc, _, kc = _ptr(obs_cpdb)
+        pg, _, kg = _ptr(obs_gmean)
+        self._check(self._lib.lrperm_set_triples(self._h, T, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], pc, pg,
+                                                 ptrs[0][1]))
+        self.T = T
+
+    # -- outputs ---------------------------------------------------------------------------
+    def observed(self):
+        """(means float32 [L,G], stored_counts int32 [L,G], cluster_sizes int32 [L])."""
+        means = np.empty((self.L, self.G), dtype=np.float32)
+        stored = np.empty((self.L, self.G), dtype=np.int32)
+        sizes = np.empty(self.L, dtype=np.int32)
+        self._check(self._lib.lrperm_observed(self._h, C.c_void_p(means.ctypes.data), C.c_void_p(stored.ctypes.data),
+                                              C.c_void_p(sizes.ctypes.data), 0))
+        return means, stored, sizes
+
+    def run(self, n_perms: int, *, seed: int = 1337, perm_offset: int = 0, perm_idx=None, order: int = ORDER_EXACT,
+            scores: int = SCORE_CPDB, gmean_mode: int = GMEAN_PRODUCT, return_cube: bool = False,
+            counts_out=None):
+        """Run the permutation null.  perm_idx given -> the reference's own index array
+        (LRPERM_PERMS_INDEX); None -> Philox on device.  Returns dict with 'cpdb' / 'gmean' uint32
+        count vectors (numpy, or the torch CUDA tensors passed in counts_out) and optionally 'cube'."""
+        P = int(n_perms)
+        if perm_idx is not None:
+            src = PERMS_INDEX
+            if not _is_torch(perm_idx):
+                perm_idx = np.ascontiguousarray(perm_idx)
+                if perm_idx.dtype not in (np.int32, np.int64):
+                    perm_idx = perm_idx.astype(np.int64)
+                is64 = perm_idx.dtype == np.int64
+            else:
+                import torch
+                is64 = perm_idx.dtype == torch.int64
+            if tuple(perm_idx.shape) != (P, self.N):
+                raise ValueError(f"perm_idx must have shape ({P}, {self.N}), got {tuple(perm_idx.shape)}")
+        else:
+            src, is64 = PERMS_PHILOX, 0
+        pp, pdev, _kp = _ptr(perm_idx)
+        out = {}
+        on_dev = 0
+        cc = cg = None
+        if counts_out is not None:
+            cc, cg = counts_out
+            on_dev = 1
+        else:
+            if scores & SCORE_CPDB:
+                cc = np.zeros(self.T, dtype=np.uint32)
+            if scores & SCORE_GMEAN:
+                cg = np.zeros(self.T, dtype=np.uint32)
+        pc, _, _kc = _ptr(cc if scores & SCORE_CPDB else None)
+        pg, _, _kg = _ptr(cg if scores & SCORE_GMEAN else None)
+        cube = np.empty((P, self.L, self.G), dtype=np.float32) if return_cube else None
+        pcube, _, _kcube = _ptr(cube)
+        self._check(self._lib.lrperm_run(self._h, P, int(perm_offset), C.c_uint64(int(seed) & (2 ** 64 - 1)), src,
+                                         pp, int(is64), pdev, int(order), int(scores), int(gmean_mode),
+                                         pc, pg, on_dev, pcube, 0))
+        if scores & SCORE_CPDB:
+            out["cpdb"] = cc
+        if scores & SCORE_GMEAN:
+            out["gmean"] = cg
+        if return_cube:
+            out["cube"] = cube
+        return out
+
+    def philox_perms(self, n_cells: int, n_perms: int, seed: int = 1337, perm_offset: int = 0) -> np.ndarray:
+        out = np.empty((int(n_perms), int(n_cells)), dtype=np.int32)
+        self._check(self._lib.lrperm_philox_perms(self._h, int(n_cells), int(n_perms), int(perm_offset),
+                                                  C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def timings(self) -> dict:
+        buf = (C.c_float * 5)()
+        self._check(self._lib.lrperm_last_timings(self._h, C.cast(buf, C.c_void_p)))
+        return {"setup_ms": buf[0], "means_ms": buf[1], "score_ms": buf[2], "total_ms": buf[3], "launches": int(buf[4])}

@@ -1,0 +1,726 @@
+// lrperm_api.cu - host side of the C ABI declared in include/lrperm.h.
+//
+// One engine = one CUDA device + one stream.  The engine owns device copies of the matrix
+// (CSR pairs; a CSC copy is built lazily for FAST mode), the label tables, the triple tables
+// and the work buffers (label slab, partial sums, cube batch, counters).  `lrperm_run` loops
+// over permutation batches:   labels/permutation setup -> per-cluster means -> score+count.
+//
+// Replaces liana/method/sc/_liana_pipe.py:402-425 + liana/method/_pipe_utils/_get_mean_perms.py
+// as one fused call that never materialises `perms` (P x L x G float64) or `perm_stats`
+// (2 x P x T float64).
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "lrperm.h"
+#include "lrperm_kernels.cuh"
+
+using namespace lrperm;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct lrperm_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // matrix
+    int64_t N = 0, G = 0, nnz = 0;
+    DevBuf indptr, csr_pairs, csc_pairs, err_flag;
+    bool have_matrix = false, csc_ready = false;
+    std::vector<int32_t> h_csc_ptr;   // [G+1]
+
+    // labels
+    int32_t L = 0;
+    bool have_labels = false;
+    DevBuf labels32, labels8, order, cl_start, inv_n;
+    std::vector<int32_t> h_cl_start;
+
+    // triples
+    int64_t T = 0;
+    bool have_triples = false, have_thr_c = false, have_thr_g = false;
+    DevBuf rowA, rowB, thr_c, thr_g, counts_c, counts_g;
+
+    // FAST-mode chunk tables
+    int32_t fast_perm_batch = 0, fast_chunk_nnz = 0;   // 0 = auto
+    int32_t chunk_table_nnz = -1;                       // chunk size the tables were built for
+    int32_t n_chunks = 0, n_slots = 0;
+    DevBuf chunks, gene_slot_ptr;
+
+    // work buffers
+    DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out;
+
+    // timings of the last run
+    float t_setup = 0, t_means = 0, t_score = 0, t_total = 0;
+    int64_t launches = 0;
+    std::vector<cudaEvent_t> events;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(expr)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return h->fail(_e == cudaErrorMemoryAllocation ? LRPERM_ERR_OOM : LRPERM_ERR_CUDA,    \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define CK_LAUNCH()                                                                               \
+    do {                                                                                          \
+        h->launches++;                                                                            \
+        CK(cudaGetLastError());                                                                   \
+    } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int grid_for(int64_t n, int threads, int cap = 148 * 16) {
+    int64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+// copy `bytes` from a host-or-device source into a device buffer on the engine stream
+int upload(lrperm_engine* h, DevBuf& dst, const void* src, size_t bytes, int on_device) {
+    CK(dst.ensure(bytes));
+    if (bytes == 0) return LRPERM_OK;
+    CK(cudaMemcpyAsync(dst.p, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    return LRPERM_OK;
+}
+
+int download(lrperm_engine* h, void* dst, const void* src_dev, size_t bytes, int on_device) {
+    if (bytes == 0 || dst == nullptr) return LRPERM_OK;
+    CK(cudaMemcpyAsync(dst, src_dev, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    return LRPERM_OK;
+}
+
+int check_err_flag(lrperm_engine* h, const char* what) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) {
+        CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+        return h->fail(LRPERM_ERR_INVALID, "%s: invalid input (flag=%d: 1=column out of range, 2=indptr overflow, "
+                       "4=indptr not monotone, 8=triple index out of range)", what, flag);
+    }
+    return LRPERM_OK;
+}
+
+// ---- CSC copy + chunk tables for FAST mode -------------------------------------------------
+int build_csc(lrperm_engine* h) {
+    if (h->csc_ready) return LRPERM_OK;
+    const int64_t nnz = h->nnz;
+    const int32_t G = (int32_t)h->G;
+    CK(h->tmp_a.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nnz, 1)));   // column keys
+    CK(h->tmp_b.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));    // iota
+    CK(h->tmp_c.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nnz, 1)));   // sorted keys
+    CK(h->tmp_d.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));    // sorted source index
+    CK(h->stage_out.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));  // row ids
+    DevBuf col_count;
+    CK(col_count.ensure(sizeof(int32_t) * (size_t)(G + 1)));
+    CK(cudaMemsetAsync(col_count.p, 0, sizeof(int32_t) * (size_t)(G + 1), h->stream));
+    CK(h->csc_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
+    h->h_csc_ptr.assign((size_t)G + 1, 0);
+    if (nnz > 0) {
+        expand_rows_kernel<<<grid_for(h->N * 32, 256), 256, 0, h->stream>>>(h->indptr.as<int32_t>(), (int32_t)h->N,
+                                                                            h->stage_out.as<int32_t>());
+        CK_LAUNCH();
+        extract_cols_kernel<<<grid_for(nnz, 256), 256, 0, h->stream>>>(h->csr_pairs.as<int2>(), nnz, h->tmp_a.as<uint32_t>(),
+                                                                       h->tmp_b.as<int32_t>(), col_count.as<int32_t>());
+        CK_LAUNCH();
+        int end_bit = 1;
+        while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->tmp_a.as<uint32_t>(), h->tmp_c.as<uint32_t>(),
+                                           h->tmp_b.as<int32_t>(), h->tmp_d.as<int32_t>(), (int)nnz, 0, end_bit, h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<uint32_t>(), h->tmp_c.as<uint32_t>(),
+                                           h->tmp_b.as<int32_t>(), h->tmp_d.as<int32_t>(), (int)nnz, 0, end_bit, h->stream));
+        h->launches += 4;
+        gather_csc_kernel<<<grid_for(nnz, 256), 256, 0, h->stream>>>(h->tmp_d.as<int32_t>(), h->stage_out.as<int32_t>(),
+                                                                     h->csr_pairs.as<int2>(), nnz, h->csc_pairs.as<int2>());
+        CK_LAUNCH();
+        std::vector<int32_t> cnt((size_t)G + 1, 0);
+        CK(cudaMemcpyAsync(cnt.data(), col_count.p, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int32_t g = 0; g < G; ++g) h->h_csc_ptr[(size_t)g + 1] = h->h_csc_ptr[(size_t)g] + cnt[(size_t)g];
+    } else {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    col_count.release();
+    // the sort scratch is large (several x nnz); give it back
+    h->tmp_a.release(); h->tmp_b.release(); h->tmp_c.release(); h->tmp_d.release();
+    h->stage_out.release(); h->sort_tmp.release();
+    h->csc_ready = true;
+    h->chunk_table_nnz = -1;
+    return LRPERM_OK;
+}
+
+int build_chunks(lrperm_engine* h, int32_t chunk_nnz) {
+    if (h->chunk_table_nnz == chunk_nnz) return LRPERM_OK;
+    const int32_t G = (int32_t)h->G;
+    std::vector<FastChunk> chunks;
+    std::vector<int32_t> slot_ptr((size_t)G + 1, 0);
+    int32_t slot = 0;
+    for (int32_t g = 0; g < G; ++g) {
+        slot_ptr[(size_t)g] = slot;
+        const int32_t b = h->h_csc_ptr[(size_t)g], e = h->h_csc_ptr[(size_t)g + 1];
+        for (int32_t s = b; s < e; s += chunk_nnz) {
+            FastChunk c;
+            c.gene = g; c.begin = s; c.end = std::min(e, s + chunk_nnz); c.slot = slot++;
+            chunks.push_back(c);
+        }
+    }
+    slot_ptr[(size_t)G] = slot;
+    // longest chunks first (they are launched first -> short ones fill the tail)
+    std::stable_sort(chunks.begin(), chunks.end(), [](const FastChunk& a, const FastChunk& b) {
+        return (a.end - a.begin) > (b.end - b.begin);
+    });
+    h->n_chunks = (int32_t)chunks.size();
+    h->n_slots = slot;
+    CK(h->chunks.ensure(sizeof(FastChunk) * std::max<size_t>(chunks.size(), 1)));
+    CK(h->gene_slot_ptr.ensure(sizeof(int32_t) * ((size_t)G + 1)));
+    if (!chunks.empty())
+        CK(cudaMemcpyAsync(h->chunks.p, chunks.data(), sizeof(FastChunk) * chunks.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->gene_slot_ptr.p, slot_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+    h->chunk_table_nnz = chunk_nnz;
+    return LRPERM_OK;
+}
+
+int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube, int32_t PP) {
+    const int32_t G = (int32_t)h->G, L = h->L;
+    const int Gpad = (G + 31) & ~31;
+    const size_t smem = (size_t)kExactWarps * Gpad * sizeof(float);
+    if (smem > h->smem_optin)
+        return h->fail(LRPERM_ERR_UNSUPPORTED, "EXACT mode needs %zu B shared memory per CTA (G=%d); limit %zu", smem, G, h->smem_optin);
+    CK(cudaFuncSetAttribute(exact_means_kernel<kExactWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = (int64_t)pb * L;
+    const int64_t grid = (items + kExactWarps - 1) / kExactWarps;
+    if (grid > 0) {
+        exact_means_kernel<kExactWarps><<<(unsigned)grid, kExactWarps * 32, smem, h->stream>>>(
+            h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), h->order.as<int32_t>(), h->cl_start.as<int32_t>(),
+            h->inv_n.as<float>(), ps, (int32_t)h->N, G, L, pb, cube, PP);
+        CK_LAUNCH();
+    }
+    return LRPERM_OK;
+}
+
+template <int Q>
+int launch_fast_q(lrperm_engine* h, int32_t PB, float* partials) {
+    const int32_t L = h->L;
+    const size_t smem = (size_t)kFastWarps * L * Q * 32 * sizeof(float);
+    CK(cudaFuncSetAttribute(fast_means_kernel<Q, kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int32_t groups = PB / (32 * Q);
+    const int64_t items = (int64_t)h->n_chunks * groups;
+    const int64_t grid = (items + kFastWarps - 1) / kFastWarps;
+    if (grid > 0) {
+        fast_means_kernel<Q, kFastWarps><<<(unsigned)grid, kFastWarps * 32, smem, h->stream>>>(
+            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, h->slab.as<uint8_t>(), PB, L, groups, partials);
+        CK_LAUNCH();
+    }
+    return LRPERM_OK;
+}
+
+int pick_q(const lrperm_engine* h) {
+    // keep >= 1 CTA of kFastWarps warps resident: bins = warps * L * Q * 128 B
+    const size_t budget = h->smem_optin;
+    for (int q : {4, 2, 1}) {
+        const size_t smem = (size_t)kFastWarps * h->L * q * 32 * sizeof(float);
+        if (smem <= budget) return q;
+    }
+    return 0;
+}
+
+template <bool LIT>
+int launch_score_t(lrperm_engine* h, int scores, const float* cube, int32_t PP, int32_t pb) {
+    const int64_t T = h->T;
+    if (T == 0) return LRPERM_OK;
+    const unsigned grid = (unsigned)((T + kScoreTile - 1) / kScoreTile);
+    const bool c = scores & LRPERM_SCORE_CPDB, g = scores & LRPERM_SCORE_GMEAN;
+#define LAUNCH_SCORE(C, Gm)                                                                                   \
+    score_count_kernel<C, Gm, LIT><<<grid, kScoreThreads, 0, h->stream>>>(                                    \
+        cube, PP, pb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_c.as<float>(), h->thr_g.as<float>(), T, \
+        h->counts_c.as<uint32_t>(), h->counts_g.as<uint32_t>())
+    if (c && g) LAUNCH_SCORE(true, true);
+    else if (c) LAUNCH_SCORE(true, false);
+    else if (g) LAUNCH_SCORE(false, true);
+    else return LRPERM_OK;
+#undef LAUNCH_SCORE
+    CK_LAUNCH();
+    return LRPERM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int lrperm_abi_version(void) { return LRPERM_ABI_VERSION; }
+
+const char* lrperm_last_error(const lrperm_engine* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lrperm_create(int device, lrperm_engine** out) {
+    if (!out) { g_create_error = "lrperm_create: out is NULL"; return LRPERM_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("lrperm_create: no CUDA device available (") + cudaGetErrorString(e) + ")";
+        return LRPERM_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "lrperm_create: device index out of range"; return LRPERM_ERR_INVALID; }
+    lrperm_engine* h = new (std::nothrow) lrperm_engine();
+    if (!h) { g_create_error = "lrperm_create: host allocation failed"; return LRPERM_ERR_OOM; }
+    h->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = h->err_flag.ensure(sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->err_flag.p, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        g_create_error = std::string("lrperm_create: ") + cudaGetErrorString(e);
+        delete h;
+        return LRPERM_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = h;
+    return LRPERM_OK;
+}
+
+void lrperm_destroy(lrperm_engine* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->labels32, &h->labels8, &h->order,
+                      &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
+                      &h->chunks, &h->gene_slot_ptr, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
+                      &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out})
+        b->release();
+    for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int lrperm_set_stream(lrperm_engine* h, void* cuda_stream) {
+    if (!h) return LRPERM_ERR_INVALID;
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return LRPERM_OK;
+}
+
+int lrperm_set_tuning(lrperm_engine* h, int32_t fast_perm_batch, int32_t fast_chunk_nnz) {
+    if (!h) return LRPERM_ERR_INVALID;
+    if (fast_perm_batch < 0 || fast_chunk_nnz < 0 || (fast_perm_batch % 128) != 0)
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_tuning: fast_perm_batch must be a non-negative multiple of 128");
+    h->fast_perm_batch = fast_perm_batch;
+    h->fast_chunk_nnz = fast_chunk_nnz;
+    return LRPERM_OK;
+}
+
+int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, const void* indptr, int indptr_is_64,
+                          const int32_t* indices, const float* data, int on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    h->have_matrix = false; h->csc_ready = false; h->have_triples = false; h->have_labels = false;
+    if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr: bad shape or NULL indptr");
+    if (n_cells >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_set_matrix_csr: n_cells must be < 2^31");
+    if (n_genes > 65535) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_set_matrix_csr: n_genes must be <= 65535 (subset to resource genes first)");
+    // total stored entries = indptr[N]
+    int64_t nnz = 0;
+    const size_t isz = indptr_is_64 ? 8 : 4;
+    {
+        unsigned char last[8] = {0};
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(indptr) + isz * (size_t)n_cells;
+        if (on_device) { CK(cudaMemcpyAsync(last, src, isz, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+        else memcpy(last, src, isz);
+        if (indptr_is_64) { int64_t v; memcpy(&v, last, 8); nnz = v; } else { int32_t v; memcpy(&v, last, 4); nnz = v; }
+    }
+    if (nnz < 0 || nnz >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_set_matrix_csr: nnz=%lld must be in [0, 2^31)", (long long)nnz);
+    if (nnz > 0 && (!indices || !data)) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr: NULL indices/data");
+    h->N = n_cells; h->G = n_genes; h->nnz = nnz;
+
+    CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    if (indptr_is_64) {
+        int rc = upload(h, h->tmp_a, indptr, 8 * (size_t)(n_cells + 1), on_device);
+        if (rc) return rc;
+        narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(
+            h->tmp_a.as<int64_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag.as<int>());
+        CK_LAUNCH();
+    } else {
+        int rc = upload(h, h->tmp_a, indptr, 4 * (size_t)(n_cells + 1), on_device);
+        if (rc) return rc;
+        narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(
+            h->tmp_a.as<int32_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag.as<int>());
+        CK_LAUNCH();
+    }
+    CK(h->csr_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
+    if (nnz > 0) {
+        const int32_t* d_idx = indices;
+        const float* d_val = data;
+        if (!on_device) {
+            int rc = upload(h, h->tmp_b, indices, sizeof(int32_t) * (size_t)nnz, 0);
+            if (rc) return rc;
+            rc = upload(h, h->tmp_c, data, sizeof(float) * (size_t)nnz, 0);
+            if (rc) return rc;
+            d_idx = h->tmp_b.as<int32_t>();
+            d_val = h->tmp_c.as<float>();
+        }
+        pack_csr_kernel<<<grid_for(nnz, 256), 256, 0, h->stream>>>(d_idx, d_val, nnz, (int32_t)n_genes,
+                                                                   h->csr_pairs.as<int2>(), h->err_flag.as<int>());
+        CK_LAUNCH();
+    }
+    int rc = check_err_flag(h, "lrperm_set_matrix_csr");
+    if (rc) return rc;
+    h->tmp_a.release(); h->tmp_b.release(); h->tmp_c.release();
+    h->have_matrix = true;
+    return LRPERM_OK;
+}
+
+int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_clusters, int on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    h->have_labels = false;
+    if (!h->have_matrix) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: call lrperm_set_matrix_csr first");
+    if (!labels || n_clusters <= 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: NULL labels or n_clusters <= 0");
+    const int64_t N = h->N;
+    std::vector<int32_t> lab((size_t)N);
+    if (on_device) {
+        CK(cudaMemcpyAsync(lab.data(), labels, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else if (N > 0) {
+        memcpy(lab.data(), labels, sizeof(int32_t) * (size_t)N);
+    }
+    // positions grouped by cluster, ascending within a cluster (the reference's labels_mask order,
+    // _get_mean_perms.py:47-52 + boolean row selection at :63)
+    std::vector<int32_t> start((size_t)n_clusters + 1, 0);
+    for (int64_t j = 0; j < N; ++j) {
+        const int32_t c = lab[(size_t)j];
+        if (c < 0 || c >= n_clusters) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: label %d at cell %lld outside [0,%d)", c, (long long)j, n_clusters);
+        start[(size_t)c + 1]++;
+    }
+    for (int32_t c = 0; c < n_clusters; ++c) {
+        if (start[(size_t)c + 1] == 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: cluster %d has no cells (drop unused categories first)", c);
+        start[(size_t)c + 1] += start[(size_t)c];
+    }
+    std::vector<int32_t> order((size_t)N), fill(start.begin(), start.end() - 1);
+    for (int64_t j = 0; j < N; ++j) order[(size_t)fill[(size_t)lab[(size_t)j]]++] = (int32_t)j;
+    std::vector<float> inv((size_t)n_clusters);
+    for (int32_t c = 0; c < n_clusters; ++c) inv[(size_t)c] = (float)(1.0 / (double)(start[(size_t)c + 1] - start[(size_t)c]));
+    std::vector<uint8_t> lab8((size_t)N);
+    for (int64_t j = 0; j < N; ++j) lab8[(size_t)j] = (uint8_t)(lab[(size_t)j] & 0xff);
+
+    h->L = n_clusters;
+    h->h_cl_start = start;
+    int rc;
+    if ((rc = upload(h, h->labels32, lab.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
+    if ((rc = upload(h, h->labels8, lab8.data(), (size_t)N, 0))) return rc;
+    if ((rc = upload(h, h->order, order.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
+    if ((rc = upload(h, h->cl_start, start.data(), sizeof(int32_t) * ((size_t)n_clusters + 1), 0))) return rc;
+    if ((rc = upload(h, h->inv_n, inv.data(), sizeof(float) * (size_t)n_clusters, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_labels = true;
+    h->have_triples = false;
+    return LRPERM_OK;
+}
+
+int lrperm_set_triples(lrperm_engine* h, int64_t n_triples, const int32_t* ligand_idx, const int32_t* receptor_idx,
+                       const int32_t* source_idx, const int32_t* target_idx, const float* obs_cpdb, const float* obs_gmean,
+                       int on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    h->have_triples = false;
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_triples: set the matrix and labels first");
+    if (n_triples < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_triples: n_triples < 0");
+    if (n_triples > 0 && (!ligand_idx || !receptor_idx || !source_idx || !target_idx))
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_triples: NULL index array");
+    const size_t T = (size_t)n_triples;
+    int rc;
+    CK(h->rowA.ensure(sizeof(int32_t) * std::max<size_t>(T, 1)));
+    CK(h->rowB.ensure(sizeof(int32_t) * std::max<size_t>(T, 1)));
+    CK(h->counts_c.ensure(sizeof(uint32_t) * std::max<size_t>(T, 1)));
+    CK(h->counts_g.ensure(sizeof(uint32_t) * std::max<size_t>(T, 1)));
+    CK(h->thr_c.ensure(sizeof(float) * std::max<size_t>(T, 1)));
+    CK(h->thr_g.ensure(sizeof(float) * std::max<size_t>(T, 1)));
+    if (T > 0) {
+        const int32_t *dl = ligand_idx, *dr = receptor_idx, *dsrc = source_idx, *dt = target_idx;
+        if (!on_device) {
+            CK(h->tmp_a.ensure(sizeof(int32_t) * T * 4));
+            int32_t* base = h->tmp_a.as<int32_t>();
+            CK(cudaMemcpyAsync(base, ligand_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(base + T, receptor_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(base + 2 * T, source_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(base + 3 * T, target_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
+            dl = base; dr = base + T; dsrc = base + 2 * T; dt = base + 3 * T;
+        }
+        build_rows_kernel<<<grid_for((int64_t)T, 256, 1 << 30), 256, 0, h->stream>>>(
+            dl, dr, dsrc, dt, (int64_t)T, (int32_t)h->G, h->L, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->err_flag.as<int>());
+        CK_LAUNCH();
+        if (obs_cpdb && (rc = upload(h, h->thr_c, obs_cpdb, sizeof(float) * T, on_device))) return rc;
+        if (obs_gmean && (rc = upload(h, h->thr_g, obs_gmean, sizeof(float) * T, on_device))) return rc;
+    }
+    rc = check_err_flag(h, "lrperm_set_triples");
+    if (rc) return rc;
+    h->tmp_a.release();
+    h->T = n_triples;
+    h->have_thr_c = obs_cpdb != nullptr;
+    h->have_thr_g = obs_gmean != nullptr;
+    h->have_triples = true;
+    return LRPERM_OK;
+}
+
+int lrperm_observed(lrperm_engine* h, float* means, int32_t* stored_counts, int32_t* cluster_sizes, int out_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_observed: set the matrix and labels first");
+    const int32_t G = (int32_t)h->G, L = h->L;
+    const size_t LG = (size_t)L * G;
+    int rc;
+    if (means) {
+        // identity permutation through the exact-order kernel: cube[g][c][0]
+        CK(h->cube.ensure(sizeof(float) * LG));
+        CK(h->stage_out.ensure(sizeof(float) * LG));
+        PermSource ps{}; ps.identity = 1;
+        if ((rc = launch_exact(h, ps, 1, h->cube.as<float>(), 1))) return rc;
+        dim3 blk(32, 8), grd((G + 31) / 32, 1, L);
+        cube_export_kernel<<<grd, blk, 0, h->stream>>>(h->cube.as<float>(), G, L, 1, 1, h->stage_out.as<float>());
+        CK_LAUNCH();
+        if ((rc = download(h, means, h->stage_out.p, sizeof(float) * LG, out_on_device))) return rc;
+    }
+    if (stored_counts) {
+        CK(h->tmp_a.ensure(sizeof(int32_t) * LG));
+        CK(cudaMemsetAsync(h->tmp_a.p, 0, sizeof(int32_t) * LG, h->stream));
+        if (h->nnz > 0) {
+            stored_counts_kernel<<<grid_for(h->N * 32, 256), 256, 0, h->stream>>>(
+                h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), h->labels32.as<int32_t>(), (int32_t)h->N, G, h->tmp_a.as<int32_t>());
+            CK_LAUNCH();
+        }
+        if ((rc = download(h, stored_counts, h->tmp_a.p, sizeof(int32_t) * LG, out_on_device))) return rc;
+    }
+    if (cluster_sizes) {
+        std::vector<int32_t> sz((size_t)L);
+        for (int32_t c = 0; c < L; ++c) sz[(size_t)c] = h->h_cl_start[(size_t)c + 1] - h->h_cl_start[(size_t)c];
+        if (out_on_device) CK(cudaMemcpyAsync(cluster_sizes, sz.data(), sizeof(int32_t) * (size_t)L, cudaMemcpyHostToDevice, h->stream));
+        else memcpy(cluster_sizes, sz.data(), sizeof(int32_t) * (size_t)L);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
+int lrperm_philox_perms(lrperm_engine* h, int64_t n_cells, int64_t n_perms, int64_t perm_offset, uint64_t seed,
+                        int32_t* out, int out_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (n_cells <= 0 || n_cells >= 0x7fffffffLL || n_perms < 0 || !out) return h->fail(LRPERM_ERR_INVALID, "lrperm_philox_perms: bad arguments");
+    if (n_perms == 0) return LRPERM_OK;
+    if (n_perms > 65535) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_philox_perms: at most 65535 permutations per call");
+    const size_t bytes = sizeof(int32_t) * (size_t)n_cells * (size_t)n_perms;
+    int32_t* dst = out;
+    if (!out_on_device) { CK(h->stage_out.ensure(bytes)); dst = h->stage_out.as<int32_t>(); }
+    dim3 grd(grid_for(n_cells, 256, 1024), (unsigned)n_perms);
+    philox_perms_kernel<<<grd, 256, 0, h->stream>>>(seed, perm_offset, (int32_t)n_cells, (int32_t)n_perms, dst);
+    CK_LAUNCH();
+    if (!out_on_device) CK(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
+int lrperm_last_timings(lrperm_engine* h, float* out5) {
+    if (!h || !out5) return LRPERM_ERR_INVALID;
+    out5[0] = h->t_setup; out5[1] = h->t_means; out5[2] = h->t_score; out5[3] = h->t_total; out5[4] = (float)h->launches;
+    return LRPERM_OK;
+}
+
+int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t seed, int perm_source,
+               const void* perm_idx, int perm_idx_is_64, int perm_idx_on_device, int order_mode, int scores, int gmean_mode,
+               uint32_t* counts_cpdb, uint32_t* counts_gmean, int counts_on_device, float* cube_out, int cube_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: set the matrix and labels first");
+    if (n_perms < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: n_perms < 0");
+    if (perm_source != LRPERM_PERMS_INDEX && perm_source != LRPERM_PERMS_PHILOX) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: unknown perm_source %d", perm_source);
+    if (order_mode != LRPERM_ORDER_EXACT && order_mode != LRPERM_ORDER_FAST) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: unknown order_mode %d", order_mode);
+    if (perm_source == LRPERM_PERMS_INDEX && n_perms > 0 && !perm_idx) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: perm_idx is NULL");
+    if (scores & ~(LRPERM_SCORE_CPDB | LRPERM_SCORE_GMEAN)) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: unknown score bits %d", scores);
+    if (scores && !h->have_triples) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: scores requested but no triples set");
+    if ((scores & LRPERM_SCORE_CPDB) && (!h->have_thr_c || !counts_cpdb)) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: CPDB requested without obs_cpdb / counts_cpdb");
+    if ((scores & LRPERM_SCORE_GMEAN) && (!h->have_thr_g || !counts_gmean)) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: GMEAN requested without obs_gmean / counts_gmean");
+    if (gmean_mode != LRPERM_GMEAN_PRODUCT && gmean_mode != LRPERM_GMEAN_LITERAL) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: unknown gmean_mode %d", gmean_mode);
+
+    const int64_t N = h->N;
+    const int32_t G = (int32_t)h->G, L = h->L;
+    const int64_t T = h->T;
+    h->launches = 0;
+    int rc;
+
+    // ---- batch geometry ----
+    int32_t PB;   // permutations per batch (cube row stride PP == PB)
+    int Q = 0;
+    if (order_mode == LRPERM_ORDER_FAST) {
+        if (L > 255) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode supports at most 255 clusters (got %d); use EXACT", L);
+        Q = pick_q(h);
+        if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: %d clusters do not fit the shared-memory bins", L);
+        if ((rc = build_csc(h))) return rc;
+        PB = h->fast_perm_batch;
+        if (PB == 0) {
+            // label slab N x PB bytes should stay L2 resident (~48 MB budget), PB in {128, 256, 512}
+            PB = 512;
+            while (PB > 128 && (int64_t)PB * N > (48LL << 20)) PB >>= 1;
+        }
+        int32_t chunk_nnz = h->fast_chunk_nnz ? h->fast_chunk_nnz : 4096;
+        if ((rc = build_chunks(h, chunk_nnz))) return rc;
+    } else {
+        // enough (perm, cluster) warps for several waves, cube batch <= ~256 MB
+        PB = 512;
+        while (PB > 128 && (int64_t)PB * L * G * 4 > (256LL << 20)) PB >>= 1;
+    }
+    if (n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((n_perms + 127) / 128) * 128);
+    const int32_t PP = PB;
+    CK(h->cube.ensure(sizeof(float) * (size_t)G * L * PP));
+    if (order_mode == LRPERM_ORDER_FAST) {
+        CK(h->slab.ensure((size_t)N * PB));
+        CK(h->partials.ensure(sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB));
+    }
+    if (scores & LRPERM_SCORE_CPDB) CK(cudaMemsetAsync(h->counts_c.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
+    if (scores & LRPERM_SCORE_GMEAN) CK(cudaMemsetAsync(h->counts_g.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
+
+    const int64_t n_batches = (n_perms + PB - 1) / PB;
+    const size_t n_events = (size_t)n_batches * 4 + 2;
+    while (h->events.size() < n_events) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        h->events.push_back(ev);
+    }
+    size_t evi = 0;
+    CK(cudaEventRecord(h->events[evi++], h->stream));   // run start
+
+    const size_t idx_elem = perm_idx_is_64 ? 8 : 4;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int64_t p0 = b * PB;
+        const int32_t pb = (int32_t)std::min<int64_t>(PB, n_perms - p0);
+        CK(cudaEventRecord(h->events[evi++], h->stream));
+        // ---- stage 1: permutation source for this batch ----
+        PermSource ps{};
+        ps.is64 = perm_idx_is_64;
+        ps.seed = seed;
+        ps.perm_id0 = perm_offset + p0;
+        ps.philox = perm_source == LRPERM_PERMS_PHILOX;
+        if (!ps.philox) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
+            if (perm_idx_on_device) ps.idx = src;
+            else {
+                if ((rc = upload(h, h->perm_dev, src, idx_elem * (size_t)pb * (size_t)N, 0))) return rc;
+                ps.idx = h->perm_dev.p;
+            }
+        }
+        if (order_mode == LRPERM_ORDER_FAST) {
+            if (pb < PB) CK(cudaMemsetAsync(h->slab.p, 0, (size_t)N * PB, h->stream));
+            if (ps.philox) {
+                const int cells_per_block = 128;
+                dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
+                slab_philox_kernel<<<grd, 128, 0, h->stream>>>(ps, h->labels8.as<uint8_t>(), (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
+            } else {
+                dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
+                slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, h->labels8.as<uint8_t>(), (int32_t)N, pb, h->slab.as<uint8_t>(), PB);
+            }
+            CK_LAUNCH();
+        }
+        CK(cudaEventRecord(h->events[evi++], h->stream));
+        // ---- stage 2: per-(gene, cluster, permutation) means ----
+        if (order_mode == LRPERM_ORDER_FAST) {
+            if (Q == 4) rc = launch_fast_q<4>(h, PB, h->partials.as<float>());
+            else if (Q == 2) rc = launch_fast_q<2>(h, PB, h->partials.as<float>());
+            else rc = launch_fast_q<1>(h, PB, h->partials.as<float>());
+            if (rc) return rc;
+            fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, h->stream>>>(
+                h->partials.as<float>(), h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
+            CK_LAUNCH();
+        } else {
+            if ((rc = launch_exact(h, ps, pb, h->cube.as<float>(), PP))) return rc;
+        }
+        CK(cudaEventRecord(h->events[evi++], h->stream));
+        // ---- stage 3: score + compare + count ----
+        if (scores) {
+            if (gmean_mode == LRPERM_GMEAN_LITERAL) rc = launch_score_t<true>(h, scores, h->cube.as<float>(), PP, pb);
+            else rc = launch_score_t<false>(h, scores, h->cube.as<float>(), PP, pb);
+            if (rc) return rc;
+        }
+        if (cube_out) {
+            float* dst = cube_out + (size_t)p0 * L * G;
+            float* dev_dst = dst;
+            if (!cube_on_device) { CK(h->stage_out.ensure(sizeof(float) * (size_t)pb * L * G)); dev_dst = h->stage_out.as<float>(); }
+            dim3 blk(32, 8), grd((G + 31) / 32, (pb + 31) / 32, L);
+            cube_export_kernel<<<grd, blk, 0, h->stream>>>(h->cube.as<float>(), G, L, PP, pb, dev_dst);
+            CK_LAUNCH();
+            if (!cube_on_device) {
+                CK(cudaMemcpyAsync(dst, dev_dst, sizeof(float) * (size_t)pb * L * G, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));   // staging buffer is reused by the next batch
+            }
+        }
+        CK(cudaEventRecord(h->events[evi++], h->stream));
+    }
+    CK(cudaEventRecord(h->events[evi++], h->stream));   // run end (before result copies)
+    if (scores & LRPERM_SCORE_CPDB) if ((rc = download(h, counts_cpdb, h->counts_c.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
+    if (scores & LRPERM_SCORE_GMEAN) if ((rc = download(h, counts_gmean, h->counts_g.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+
+    h->t_setup = h->t_means = h->t_score = 0.f;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        float ms;
+        const size_t base = 1 + (size_t)b * 4;
+        CK(cudaEventElapsedTime(&ms, h->events[base], h->events[base + 1])); h->t_setup += ms;
+        CK(cudaEventElapsedTime(&ms, h->events[base + 1], h->events[base + 2])); h->t_means += ms;
+        CK(cudaEventElapsedTime(&ms, h->events[base + 2], h->events[base + 3])); h->t_score += ms;
+    }
+    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[evi - 1]));
+    return LRPERM_OK;
+}
+
+}  // extern "C"

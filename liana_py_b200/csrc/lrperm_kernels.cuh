@@ -1,0 +1,452 @@
+// lrperm_kernels.cuh - sm_100a kernels of the permutation-null engine.
+//
+// Data layout in HBM:
+//   csr_pairs[nnz]  int2 {column, float bits}      row-major (CSR) copy of X, 8 B per stored entry
+//   csc_pairs[nnz]  int2 {cell,   float bits}      gene-major (CSC) copy, cells ascending per gene
+//   order[N]        positions j sorted by cluster (stable), cl_start[L+1]
+//   slab[N][PB]     uint8 permuted label of cell i under permutation p (FAST mode, L2 resident)
+//   cube[G][L][PP]  float32 per-(gene, cluster) permuted means, permutation-minor (PP = padded batch)
+//   counts[T]       uint32 exceedance counters
+//
+// Reference arithmetic being reproduced: SURVEY.md Appendix B /
+// liana/method/_pipe_utils/_get_mean_perms.py:61-87 (cube), :117-142 (p-values),
+// liana/method/sc/_cellphonedb.py:25-28, liana/method/sc/_geometric_mean.py:22-23.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lrperm_philox.h"
+
+namespace lrperm {
+
+constexpr int kExactWarps = 8;       // warps per CTA in the exact-order kernel
+constexpr int kFastWarps = 8;        // warps per CTA in the fast kernel
+constexpr int kScoreThreads = 256;   // threads per CTA in the score kernel
+constexpr int kScoreTile = 256;      // triples per CTA in the score kernel
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ------------------------------------------------------------------------------------------
+// CSR packing + validation
+// ------------------------------------------------------------------------------------------
+__global__ void pack_csr_kernel(const int32_t* __restrict__ indices, const float* __restrict__ data,
+                                int64_t nnz, int32_t G, int2* __restrict__ pairs, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) {
+        int32_t c = indices[i];
+        if (c < 0 || c >= G) { atomicOr(err, 1); c = 0; }
+        pairs[i] = make_int2(c, __float_as_int(data[i]));
+    }
+}
+
+template <typename T>
+__global__ void narrow_indptr_kernel(const T* __restrict__ in, int64_t n, int32_t* __restrict__ out,
+                                     int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        T v = in[i];
+        if (v < 0 || (int64_t)v > 0x7fffffffLL) atomicOr(err, 2);
+        if (i > 0 && in[i - 1] > v) atomicOr(err, 4);
+        out[i] = (int32_t)v;
+    }
+}
+
+// row id of every stored entry (for the CSR -> CSC transpose)
+__global__ void expand_rows_kernel(const int32_t* __restrict__ indptr, int32_t N, int32_t* __restrict__ rows) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < N; r += nwarps) {
+        const int s = indptr[r], e = indptr[r + 1];
+        for (int o = s + lane_id(); o < e; o += 32) rows[o] = r;
+    }
+}
+
+__global__ void extract_cols_kernel(const int2* __restrict__ pairs, int64_t nnz, uint32_t* __restrict__ cols,
+                                    int32_t* __restrict__ iota, int32_t* __restrict__ col_count) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) {
+        const int c = pairs[i].x;
+        cols[i] = (uint32_t)c;
+        iota[i] = (int32_t)i;
+        atomicAdd(&col_count[c], 1);
+    }
+}
+
+__global__ void gather_csc_kernel(const int32_t* __restrict__ sorted_src, const int32_t* __restrict__ rows,
+                                  const int2* __restrict__ csr_pairs, int64_t nnz, int2* __restrict__ csc_pairs) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) {
+        const int32_t s = sorted_src[i];
+        csc_pairs[i] = make_int2(rows[s], csr_pairs[s].y);
+    }
+}
+
+// stored-entry counts per (cluster, gene): props = count / n_c  (_common.py:41-42)
+__global__ void stored_counts_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
+                                     const int32_t* __restrict__ labels, int32_t N, int32_t G,
+                                     int32_t* __restrict__ counts /*[L*G]*/) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < N; r += nwarps) {
+        const int s = indptr[r], e = indptr[r + 1];
+        const int c = labels[r];
+        for (int o = s + lane_id(); o < e; o += 32) atomicAdd(&counts[(int64_t)c * G + pairs[o].x], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Permutation sources
+// ------------------------------------------------------------------------------------------
+struct PermSource {
+    const void* idx;      // INDEX mode: perm_idx of this batch, [pb][N]
+    int is64;
+    int philox;           // 1 = PHILOX
+    uint64_t seed;
+    int64_t perm_id0;     // global id of the first permutation of the batch
+    int identity;         // 1 = identity permutation (observed statistics)
+};
+
+__device__ __forceinline__ int32_t perm_lookup(const PermSource& ps, int p_local, int64_t N, int32_t j) {
+    if (ps.is64) return (int32_t)((const int64_t*)ps.idx)[(int64_t)p_local * N + j];
+    return ((const int32_t*)ps.idx)[(int64_t)p_local * N + j];
+}
+
+// ------------------------------------------------------------------------------------------
+// EXACT mode: one warp per (permutation, cluster).  The warp walks the cluster's positions in
+// ascending order (the reference's order), fetches the CSR row of the cell the permutation put
+// there, and adds fl32(x * inv_n) into a G-float accumulator row in shared memory with separate
+// multiply and add roundings - bit-identical to scipy's (X * (1/n)).sum(0) on the permuted rows.
+// Lanes are spread over the stored entries of one row (distinct columns -> no intra-row hazard).
+// ------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
+                   const int32_t* __restrict__ order, const int32_t* __restrict__ cl_start,
+                   const float* __restrict__ inv_n, PermSource ps,
+                   int32_t N, int32_t G, int32_t L, int32_t n_perms_batch,
+                   float* __restrict__ cube, int32_t PP) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // items ordered cluster-major so the warps of one CTA have equal work
+    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    if (item >= (int64_t)n_perms_batch * L) return;
+    const int c = (int)(item / n_perms_batch);
+    const int p = (int)(item - (int64_t)c * n_perms_batch);
+    const int Gpad = (G + 31) & ~31;
+    float* acc = smem + (size_t)warp * Gpad;
+    for (int g = lane; g < Gpad; g += 32) acc[g] = 0.0f;
+    __syncwarp();
+
+    const float inv = inv_n[c];
+    const int k_begin = cl_start[c], k_end = cl_start[c + 1];
+    lrperm_bij_t bij;
+    if (ps.philox) bij = lrperm_bij_init(ps.seed, (uint64_t)(ps.perm_id0 + p), (uint32_t)N);
+
+    auto fetch_meta = [&](int k, int& rs, int& re) {
+        rs = 0; re = 0;
+        if (k < k_end) {
+            const int j = order[k];
+            int cell;
+            if (ps.identity) cell = j;
+            else if (ps.philox) cell = (int)lrperm_bij_forward(&bij, (uint32_t)j);
+            else cell = perm_lookup(ps, p, N, j);
+            rs = indptr[cell];
+            re = indptr[cell + 1];
+        }
+    };
+
+    int rs_n, re_n;
+    fetch_meta(k_begin + lane, rs_n, re_n);
+    for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+        const int rs_c = rs_n, re_c = re_n;
+        fetch_meta(k0 + 32 + lane, rs_n, re_n);   // prefetch the next 32 rows' extents
+        const int nrows = min(32, k_end - k0);
+        for (int r = 0; r < nrows; ++r) {
+            const int s = __shfl_sync(0xffffffffu, rs_c, r);
+            const int e = __shfl_sync(0xffffffffu, re_c, r);
+            int o = s + lane;
+            // four 32-entry chunks in flight per row
+            for (; o + 96 < e; o += 128) {
+                const int2 q0 = pairs[o], q1 = pairs[o + 32], q2 = pairs[o + 64], q3 = pairs[o + 96];
+                acc[q0.x] = __fadd_rn(acc[q0.x], __fmul_rn(__int_as_float(q0.y), inv));
+                acc[q1.x] = __fadd_rn(acc[q1.x], __fmul_rn(__int_as_float(q1.y), inv));
+                acc[q2.x] = __fadd_rn(acc[q2.x], __fmul_rn(__int_as_float(q2.y), inv));
+                acc[q3.x] = __fadd_rn(acc[q3.x], __fmul_rn(__int_as_float(q3.y), inv));
+            }
+            {
+                // tail: up to four predicated chunks, loads issued together
+                int2 q[4];
+                bool v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = (o + 32 * u) < e;
+                    q[u] = v[u] ? pairs[o + 32 * u] : make_int2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (v[u]) acc[q[u].x] = __fadd_rn(acc[q[u].x], __fmul_rn(__int_as_float(q[u].y), inv));
+            }
+            __syncwarp();   // next row may touch the same columns from other lanes
+        }
+    }
+    // flush: cube[g][c][p]
+    for (int g = lane; g < G; g += 32) cube[((int64_t)g * L + c) * PP + p] = acc[g];
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST mode, step 1: label slab.  slab[i*PB + p] = label of the position cell i lands on.
+// ------------------------------------------------------------------------------------------
+__global__ void slab_from_index_kernel(PermSource ps, const uint8_t* __restrict__ labels8, int32_t N,
+                                       int32_t n_perms_batch, uint8_t* __restrict__ slab, int32_t PB) {
+    // thread per (p, j): reads of perm_idx coalesce along j, byte writes scatter into the slab
+    const int p = blockIdx.y;
+    if (p >= n_perms_batch) return;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const int cell = perm_lookup(ps, p, N, j);
+        slab[(int64_t)cell * PB + p] = labels8[j];
+    }
+}
+
+__global__ void slab_philox_kernel(PermSource ps, const uint8_t* __restrict__ labels8, int32_t N,
+                                   int32_t n_perms_batch, uint8_t* __restrict__ slab, int32_t PB,
+                                   int32_t cells_per_block) {
+    // thread = one permutation of the batch (key derived once); loop over a tile of cells.
+    const int p = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = p < n_perms_batch;
+    lrperm_bij_t bij = lrperm_bij_init(ps.seed, (uint64_t)(ps.perm_id0 + (active ? p : 0)), (uint32_t)N);
+    const int i0 = blockIdx.x * cells_per_block;
+    const int i1 = min(N, i0 + cells_per_block);
+    if (!active) return;
+    for (int i = i0; i < i1; ++i) {
+        const uint32_t j = lrperm_bij_inverse(&bij, (uint32_t)i);
+        slab[(int64_t)i * PB + p] = labels8[j];
+    }
+}
+
+__global__ void philox_perms_kernel(uint64_t seed, int64_t perm_id0, int32_t N, int32_t n_perms,
+                                    int32_t* __restrict__ out) {
+    const int p = blockIdx.y;
+    if (p >= n_perms) return;
+    lrperm_bij_t bij = lrperm_bij_init(seed, (uint64_t)(perm_id0 + p), (uint32_t)N);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
+        out[(int64_t)p * N + j] = (int32_t)lrperm_bij_forward(&bij, (uint32_t)j);
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST mode, step 2: per-gene private histograms.
+// One warp = one chunk of one gene's stored entries x 32*Q permutations (lane owns Q of them).
+// Every lane keeps its own L x Q float bins in shared memory, laid out [c][q][lane] so that a
+// warp-wide access always hits 32 distinct banks: no atomics, no conflicts, deterministic order
+// (ascending cell within the gene).  The only per-entry global traffic is Q label bytes per lane
+// from the L2-resident slab; the {cell, value} pair is a warp-uniform (broadcast) load.
+// ------------------------------------------------------------------------------------------
+template <int Q> struct LabelWord;
+template <> struct LabelWord<1> { using type = uint8_t; };
+template <> struct LabelWord<2> { using type = uint16_t; };
+template <> struct LabelWord<4> { using type = uint32_t; };
+
+struct FastChunk { int32_t gene, begin, end, slot; };   // slot = index of the partial-sum row block
+
+template <int Q, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+fast_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restrict__ chunks, int32_t n_chunks,
+                  const uint8_t* __restrict__ slab, int32_t PB, int32_t L, int32_t groups_per_batch,
+                  float* __restrict__ partials /*[slot][L][PB]*/) {
+    extern __shared__ float smem[];
+    using LW = typename LabelWord<Q>::type;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * WARPS + warp;
+    if (item >= (int64_t)n_chunks * groups_per_batch) return;
+    // consecutive warps share the chunk (different permutation groups) -> pair loads hit L1
+    const int chunk_id = (int)(item / groups_per_batch);
+    const int group = (int)(item - (int64_t)chunk_id * groups_per_batch);
+    const FastChunk ch = chunks[chunk_id];
+    float* bins = smem + (size_t)warp * (L * Q * 32);
+    for (int i = lane; i < L * Q * 32; i += 32) bins[i] = 0.0f;
+    __syncwarp();
+
+    const LW* __restrict__ slab_w = reinterpret_cast<const LW*>(slab);
+    const int row_words = PB / Q;                  // label words per slab row
+    const int col_word = group * 32 + lane;        // this lane's word within the row
+    float* mybins = bins + lane;
+
+    constexpr int U = 8;
+    int k = ch.begin;
+    for (; k + U <= ch.end; k += U) {
+        int2 pr[U];
+        LW lw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pr[u] = __ldg(&csc_pairs[k + u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) lw[u] = __ldg(&slab_w[(int64_t)pr[u].x * row_words + col_word]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float v = __int_as_float(pr[u].y);
+            float* b[Q];
+            float x[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int c = (int)((lw[u] >> (8 * q)) & 0xff);
+                b[q] = mybins + (c * Q + q) * 32;
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) x[q] = *b[q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) *b[q] = x[q] + v;
+        }
+    }
+    for (; k < ch.end; ++k) {
+        const int2 pr = __ldg(&csc_pairs[k]);
+        const LW lw = __ldg(&slab_w[(int64_t)pr.x * row_words + col_word]);
+        const float v = __int_as_float(pr.y);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int c = (int)((lw >> (8 * q)) & 0xff);
+            float* b = mybins + (c * Q + q) * 32;
+            *b = *b + v;
+        }
+    }
+    __syncwarp();
+    // partial sums out: partials[(slot*L + c)*PB + group*32*Q + lane*Q + q]
+    float* out = partials + (int64_t)ch.slot * L * PB + group * 32 * Q + lane * Q;
+    for (int c = 0; c < L; ++c) {
+        float vals[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) vals[q] = mybins[(c * Q + q) * 32];
+        float* dst = out + (int64_t)c * PB;
+        if (Q == 4) {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(vals[0], vals[Q > 1 ? 1 : 0], vals[Q > 2 ? 2 : 0], vals[Q > 3 ? 3 : 0]));
+        } else if (Q == 2) {
+            __stcs(reinterpret_cast<float2*>(dst), make_float2(vals[0], vals[Q > 1 ? 1 : 0]));
+        } else {
+            __stcs(dst, vals[0]);
+        }
+    }
+}
+
+// FAST mode, step 3: combine a gene's chunk partials in fixed order, scale by 1/n_c, write cube.
+__global__ void fast_finalize_kernel(const float* __restrict__ partials, const int32_t* __restrict__ gene_slot_ptr /*[G+1]*/,
+                                     const float* __restrict__ inv_n, int32_t G, int32_t L, int32_t PB,
+                                     float* __restrict__ cube, int32_t PP, int32_t p_off) {
+    // thread per (g, c, p) with p fastest
+    const int64_t total = (int64_t)G * L * PB;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % PB);
+        const int64_t gc = i / PB;
+        const int c = (int)(gc % L);
+        const int g = (int)(gc / L);
+        float s = 0.0f;
+        const int s0 = gene_slot_ptr[g], s1 = gene_slot_ptr[g + 1];
+        for (int sl = s0; sl < s1; ++sl) s = __fadd_rn(s, __ldcs(&partials[((int64_t)sl * L + c) * PB + p]));
+        cube[((int64_t)g * L + c) * PP + p_off + p] = __fmul_rn(s, inv_n[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Score + compare + count (never materialises the reference's perm_stats[2,P,T]).
+// Lanes run over 32 consecutive permutations (coalesced 128 B reads of the permutation-minor
+// cube), each warp sweeps the CTA's tile of triples; ballots turn 32 comparisons into one popc.
+//   CellPhoneDB : (a + b)/2 >= m      in float64 (exact for float32 a, b)   _cellphonedb.py:28
+//   gmean       : a*b >= g*g          in float64 (exact products)           _geometric_mean.py:23
+//                 or exp((log a + log b)/2) >= g (LITERAL)
+// ------------------------------------------------------------------------------------------
+template <bool CPDB, bool GMEAN, bool LITERAL>
+__global__ void __launch_bounds__(kScoreThreads)
+score_count_kernel(const float* __restrict__ cube, int32_t PP, int32_t n_perms_batch,
+                   const int32_t* __restrict__ rowA, const int32_t* __restrict__ rowB,
+                   const float* __restrict__ thr_c, const float* __restrict__ thr_g, int64_t T,
+                   uint32_t* __restrict__ counts_c, uint32_t* __restrict__ counts_g) {
+    __shared__ int32_t s_ra[kScoreTile], s_rb[kScoreTile];
+    __shared__ float s_tc[kScoreTile], s_tg[kScoreTile];
+    __shared__ uint32_t s_cc[kScoreTile], s_cg[kScoreTile];
+    const int64_t t0 = (int64_t)blockIdx.x * kScoreTile;
+    const int nt = (int)min((int64_t)kScoreTile, T - t0);
+    for (int i = threadIdx.x; i < kScoreTile; i += blockDim.x) {
+        const bool ok = i < nt;
+        s_ra[i] = ok ? rowA[t0 + i] : 0;
+        s_rb[i] = ok ? rowB[t0 + i] : 0;
+        s_tc[i] = (CPDB && ok) ? thr_c[t0 + i] : 0.0f;
+        s_tg[i] = (GMEAN && ok) ? thr_g[t0 + i] : 0.0f;
+        s_cc[i] = 0; s_cg[i] = 0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = kScoreThreads / 32;
+    const int n_groups = (n_perms_batch + 31) >> 5;
+    for (int pg = warp; pg < n_groups; pg += NW) {
+        const int p = pg * 32 + lane;
+        const bool valid = p < n_perms_batch;
+        for (int tb = 0; tb < nt; tb += 32) {
+            uint32_t my_c = 0, my_g = 0;
+            const int tn = min(32, nt - tb);
+            for (int u = 0; u < tn; ++u) {
+                const int t = tb + u;
+                const float a = __ldg(&cube[(int64_t)s_ra[t] * PP + p]);
+                const float b = __ldg(&cube[(int64_t)s_rb[t] * PP + p]);
+                if (CPDB) {
+                    const bool ge = valid && (((double)a + (double)b) * 0.5 >= (double)s_tc[t]);
+                    const uint32_t m = __ballot_sync(0xffffffffu, ge);
+                    if (lane == u) my_c = __popc(m);
+                }
+                if (GMEAN) {
+                    bool ge;
+                    const double g = (double)s_tg[t];
+                    if (LITERAL) {
+                        ge = exp((log((double)a) + log((double)b)) * 0.5) >= g;
+                    } else {
+                        // sqrt(ab) >= g  <=>  ab >= g^2 for a, b, g >= 0 ; negatives -> NaN in the reference -> false
+                        ge = (a >= 0.0f) && (b >= 0.0f) && ((g <= 0.0) || ((double)a * (double)b >= g * g));
+                    }
+                    ge = ge && valid;
+                    const uint32_t m = __ballot_sync(0xffffffffu, ge);
+                    if (lane == u) my_g = __popc(m);
+                }
+            }
+            if (lane < tn) {
+                if (CPDB) atomicAdd(&s_cc[tb + lane], my_c);
+                if (GMEAN) atomicAdd(&s_cg[tb + lane], my_g);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        if (CPDB) counts_c[t0 + i] += s_cc[i];
+        if (GMEAN) counts_g[t0 + i] += s_cg[i];
+    }
+}
+
+// cube[g][c][PP] (perm-minor) -> out[p][c][g] (the reference's layout)
+__global__ void cube_export_kernel(const float* __restrict__ cube, int32_t G, int32_t L, int32_t PP,
+                                   int32_t n_perms_batch, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    // grid: x over gene tiles, y over perm tiles, z over clusters
+    const int g0 = blockIdx.x * 32, p0 = blockIdx.y * 32, c = blockIdx.z;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int g = g0 + r, p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (g < G && p < n_perms_batch) ? cube[((int64_t)g * L + c) * PP + p] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, g = g0 + threadIdx.x;
+        if (g < G && p < n_perms_batch) out[((int64_t)p * L + c) * G + g] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void build_rows_kernel(const int32_t* __restrict__ lig, const int32_t* __restrict__ rec,
+                                  const int32_t* __restrict__ src, const int32_t* __restrict__ tgt,
+                                  int64_t T, int32_t G, int32_t L, int32_t* __restrict__ rowA,
+                                  int32_t* __restrict__ rowB, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < T) {
+        const int l = lig[i], r = rec[i], s = src[i], t = tgt[i];
+        if (l < 0 || l >= G || r < 0 || r >= G || s < 0 || s >= L || t < 0 || t >= L) { atomicOr(err, 8); rowA[i] = 0; rowB[i] = 0; return; }
+        rowA[i] = l * L + s;
+        rowB[i] = r * L + t;
+    }
+}
+
+}  // namespace lrperm

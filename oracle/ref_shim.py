@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE ONLY - loads the *unmodified* reference modules from /root/reference.
+
+Only usable in the build container (``/root/reference`` does not exist on the GPU box).
+It is used by ``scripts/make_golden.py`` to generate the committed fixtures under
+``tests/golden/`` and by container-only differential tests.  Nothing in the product
+package imports this file.
+
+Recipe: the heavy package ``__init__`` files pull in scanpy /
+plotnine / mudata, which are not installed.  We pre-register bare package modules whose
+``__path__`` points into the reference tree, stub the four missing third-party modules,
+and then import the hot-path modules themselves unchanged:
+
+  liana/method/_pipe_utils/_get_mean_perms.py   (_get_means_perms, _calculate_pvals, ...)
+  liana/method/sc/_liana_pipe.py                (liana_pipe, _run_method, _get_lr)
+  liana/method/sc/_cellphonedb.py, _geometric_mean.py, _Method.py, _rank_aggregate.py
+  liana/method/_pipe_utils/_aggregate.py, _pre.py, _common.py
+  liana/resource/_reassemble_complexes.py, select_resource.py
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("LIANA_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "liana", "method", "sc"))
+
+
+class _DocstringProcessor:
+    def __init__(self, *a, **k):
+        self.params = {}
+
+    def dedent(self, f):
+        return f
+
+    def __getattr__(self, name):  # any other decorator-like attribute is a pass-through
+        def passthrough(*a, **k):
+            if len(a) == 1 and callable(a[0]) and not k:
+                return a[0]
+            return lambda f: f
+        return passthrough
+
+
+_loaded = None
+
+
+def load_reference():
+    """Return a namespace with the reference's own functions (imported unmodified)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if repo_root not in sys.path:
+        sys.path.insert(0, repo_root)
+    from liana_py_b200.testing._anndata_lite import AnnDataLite
+
+    lroot = os.path.join(REFERENCE_ROOT, "liana")
+
+    def bare_pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        m.__package__ = name
+        sys.modules[name] = m
+        return m
+
+    bare_pkg("liana", lroot)
+    bare_pkg("liana.method", os.path.join(lroot, "method"))
+    bare_pkg("liana.method.sc", os.path.join(lroot, "method", "sc"))
+    bare_pkg("liana.utils", os.path.join(lroot, "utils"))
+    bare_pkg("liana.resource", os.path.join(lroot, "resource"))
+
+    # third-party stubs
+    an = types.ModuleType("anndata")
+    an.AnnData = AnnDataLite
+    sys.modules.setdefault("anndata", an)
+    sc = types.ModuleType("scanpy")
+    sc.AnnData = AnnDataLite
+    sys.modules.setdefault("scanpy", sc)
+    mu = types.ModuleType("mudata")
+
+    class MuData:  # only used in isinstance checks (`_liana_pipe.py:126`)
+        pass
+    mu.MuData = MuData
+    sys.modules.setdefault("mudata", mu)
+    dr = types.ModuleType("docrep")
+    dr.DocstringProcessor = _DocstringProcessor
+    sys.modules.setdefault("docrep", dr)
+
+    # names `_liana_pipe.py` imports from packages whose __init__ we skipped
+    sys.modules["liana.utils"].mdata_to_anndata = lambda *a, **k: (_ for _ in ()).throw(
+        NotImplementedError("MuData input is out of scope"))
+    rc = importlib.import_module("liana.resource._reassemble_complexes")
+    sys.modules["liana.resource"].explode_complexes = rc.explode_complexes
+    sys.modules["liana.resource"].filter_reassemble_complexes = rc.filter_reassemble_complexes
+
+    ns = types.SimpleNamespace()
+    ns.AnnData = AnnDataLite
+    ns.reassemble = rc
+    ns.select_resource = importlib.import_module("liana.resource.select_resource")
+    ns.pipe_utils = importlib.import_module("liana.method._pipe_utils")
+    ns.pre = importlib.import_module("liana.method._pipe_utils._pre")
+    ns.common = importlib.import_module("liana.method._pipe_utils._common")
+    ns.get_mean_perms = importlib.import_module("liana.method._pipe_utils._get_mean_perms")
+    ns.aggregate = importlib.import_module("liana.method._pipe_utils._aggregate")
+    ns.liana_pipe = importlib.import_module("liana.method.sc._liana_pipe")
+    ns.Method = importlib.import_module("liana.method.sc._Method")
+    ns.cellphonedb_mod = importlib.import_module("liana.method.sc._cellphonedb")
+    ns.geometric_mean_mod = importlib.import_module("liana.method.sc._geometric_mean")
+    ns.rank_aggregate_mod = importlib.import_module("liana.method.sc._rank_aggregate")
+    ns.cellphonedb = ns.cellphonedb_mod.cellphonedb
+    ns.geometric_mean = ns.geometric_mean_mod.geometric_mean
+    ns.constants = importlib.import_module("liana._constants")
+    _loaded = ns
+    return ns

@@ -1,0 +1,152 @@
+"""Container-only: generate tests/golden/*.npz by running the UNMODIFIED reference code
+(/root/reference, loaded through oracle/ref_shim.py) on small synthetic inputs.
+
+For each case we record the inputs the reference's hot path actually saw (the CSR matrix after
+prep_check_adata + gene subsetting, label codes), the permutation cube it produced
+(`_get_means_perms`, liana/method/_pipe_utils/_get_mean_perms.py:9-57), the index arrays of
+`_get_mat_idx` (:103-113) and the final li.mt.cellphonedb / li.mt.geometric_mean frames.
+
+Run:  python scripts/make_golden.py          (needs /root/reference; not runnable on the GPU box)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+from scipy import sparse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_shim import load_reference  # noqa: E402
+from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
+from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def capture_run(ref, method, adata, **kw):
+    """Run one reference method, capturing what the hot path saw and produced."""
+    cap = {}
+    pipe = ref.liana_pipe
+    orig_perms, orig_idx = pipe._get_means_perms, pipe._get_mat_idx
+
+    def wrap_perms(adata, n_perms, seed, agg_fun, norm_factor, n_jobs, verbose):
+        cap["X"] = adata.X.copy().tocsr()
+        cap["var_names"] = np.array(adata.var_names)
+        cap["labels_cat"] = np.array(adata.obs['@label'].cat.categories)
+        cap["labels"] = np.asarray(adata.obs['@label'].cat.codes, dtype=np.int32)
+        cube = orig_perms(adata=adata, n_perms=n_perms, seed=seed, agg_fun=agg_fun, norm_factor=norm_factor,
+                          n_jobs=n_jobs, verbose=verbose)
+        cap["cube"] = cube
+        return cube
+
+    def wrap_idx(adata, lr_res):
+        out = orig_idx(adata, lr_res)
+        cap["lr_res_in"] = lr_res.copy()
+        cap["idx"] = [np.asarray(o, dtype=np.int32) for o in out]
+        return out
+
+    pipe._get_means_perms, pipe._get_mat_idx = wrap_perms, wrap_idx
+    try:
+        res = method(adata, inplace=False, **kw)
+    finally:
+        pipe._get_means_perms, pipe._get_mat_idx = orig_perms, orig_idx
+    cap["res"] = res
+    return cap
+
+
+def save_case(name, adata, groupby, n_perms, seed, expr_prop, ref, keep_cube_perms=None):
+    kw = dict(groupby=groupby, use_raw=False, n_perms=n_perms, seed=seed, expr_prop=expr_prop, verbose=False)
+    cp = capture_run(ref, ref.cellphonedb, adata.copy(), **kw)
+    gm = capture_run(ref, ref.geometric_mean, adata.copy(), **kw)
+    assert np.array_equal(cp["cube"], gm["cube"]), "both methods must see the same cube"
+    X = cp["X"]
+    X.sort_indices()
+    N = X.shape[0]
+    rng = np.random.default_rng(seed)
+    perm_idx = np.stack([rng.permutation(np.arange(N)) for _ in range(n_perms)])
+    cube = cp["cube"]
+    assert np.array_equal(cube.astype(np.float32).astype(np.float64), cube), "cube holds float32 values"
+    kc = n_perms if keep_cube_perms is None else min(keep_cube_perms, n_perms)
+    lr_in = cp["lr_res_in"]
+    lig, rec, src, tgt = cp["idx"]
+    full = adata.X.tocsr()
+    full.sort_indices()
+    arrays = dict(
+        # the full input (before the pipeline touches it) for drop-in tests
+        in_indptr=full.indptr.astype(np.int64), in_indices=full.indices.astype(np.int32),
+        in_data=full.data.astype(np.float32), in_shape=np.array(full.shape, dtype=np.int64),
+        in_var_names=np.array(adata.var_names, dtype=str), in_labels=np.array([str(v) for v in adata.obs[groupby]], dtype=str),
+        # what the hot path saw
+        indptr=X.indptr.astype(np.int64), indices=X.indices.astype(np.int32), data=X.data.astype(np.float32),
+        shape=np.array(X.shape, dtype=np.int64), var_names=cp["var_names"].astype(str),
+        labels=cp["labels"], labels_cat=cp["labels_cat"].astype(str),
+        perm_idx=perm_idx.astype(np.int32), cube=cube[:kc].astype(np.float32),
+        cube_cluster_sums=cube.sum(axis=(0, 2)),     # like liana/tests/test_get_mean_perms.py:27-35
+        ligand_idx=lig, receptor_idx=rec, source_idx=src, target_idx=tgt,
+        ligand_means=lr_in["ligand_means"].values.astype(np.float32),
+        receptor_means=lr_in["receptor_means"].values.astype(np.float32),
+        n_perms=np.int64(n_perms), seed=np.int64(seed), expr_prop=np.float64(expr_prop),
+    )
+    # final frames, aligned to the order of lr_res_in (the rows the score function saw)
+    key = ["source", "target", "ligand_complex", "receptor_complex"]
+    for tag, cap_, mag, spec in (("cpdb", cp, "lr_means", "cellphone_pvals"), ("gmean", gm, "lr_gmeans", "gmean_pvals")):
+        res = cap_["res"]
+        merged = lr_in[key].merge(res[key + [mag, spec]], on=key, how="left")
+        assert len(merged) == len(lr_in) and not merged[spec].isna().any()
+        arrays[f"{tag}_magnitude"] = merged[mag].values.astype(np.float32)
+        arrays[f"{tag}_pvals"] = merged[spec].values.astype(np.float64)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
+    cp["res"].to_csv(os.path.join(OUT, f"{name}_cellphonedb.csv.gz"), index=False)
+    gm["res"].to_csv(os.path.join(OUT, f"{name}_geometric_mean.csv.gz"), index=False)
+    print(f"{name}: N={N} G={X.shape[1]} L={len(cp['labels_cat'])} P={n_perms} T={len(lig)} "
+          f"mean cpdb pval={arrays['cpdb_pvals'].mean():.6f} mean gmean pval={arrays['gmean_pvals'].mean():.6f}")
+
+
+def ragged_case():
+    """Tiny input with empty cells, explicit stored zeros, unequal clusters and a sub-min_cells cluster."""
+    rng = np.random.default_rng(7)
+    from liana_py_b200.testing._synth import consensus_genes
+    genes = consensus_genes()
+    # pick genes that take part in complexes so min-subunit logic is exercised
+    res = pd.read_csv(os.path.join(ROOT, "liana_py_b200", "resource", "consensus.csv"))
+    cplx = res[res["ligand"].str.contains("_") | res["receptor"].str.contains("_")].head(40)
+    chosen = set()
+    for col in ("ligand", "receptor"):
+        for e in cplx[col]:
+            chosen.update(e.split("_"))
+    simple = res[~(res["ligand"].str.contains("_") | res["receptor"].str.contains("_"))].head(30)
+    chosen.update(simple["ligand"]); chosen.update(simple["receptor"])
+    chosen = np.array(sorted(chosen))
+    n, g = 90, len(chosen)
+    dense = (rng.random((n, g)) < 0.25) * np.log1p(rng.gamma(1.5, 2.0, size=(n, g)))
+    dense[5] = 0; dense[40] = 0                     # empty cells (kept by the reference, _pre.py:130-133)
+    X = sparse.csr_matrix(dense.astype(np.float32))
+    # add explicit stored zeros: they count towards props (getnnz) but not means
+    X = X.tolil(); X = X.tocsr()
+    X.data[::17] = 0.0
+    labels = np.array(["a"] * 40 + ["b"] * 25 + ["c"] * 22 + ["tiny"] * 3)   # 'tiny' < min_cells=5 -> dropped
+    perm = rng.permutation(n)
+    X = X[perm]; labels = labels[perm]
+    order = rng.permutation(g)
+    obs = pd.DataFrame({"cluster": pd.Categorical(labels)}, index=[f"c{i}" for i in range(n)])
+    var = pd.DataFrame(index=pd.Index(chosen[order]))
+    return AnnDataLite(X=X[:, order].tocsr(), obs=obs, var=var)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    # config 1 stand-in (BASELINE.json configs[0]): 700 cells x 765 genes, 10 clusters, P=100
+    save_case("toy700", make_synthetic_adata(700, 765, 10, density=0.10), "cluster", 100, 1337, 0.1, ref,
+              keep_cube_perms=8)
+    save_case("small300", make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12),
+              "cluster", 32, 42, 0.1, ref)
+    save_case("ragged90", ragged_case(), "cluster", 16, 5, 0.05, ref)
+
+
+if __name__ == "__main__":
+    main()

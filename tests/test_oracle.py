@@ -1,0 +1,101 @@
+"""CPU: pin the oracle (oracle/lrperm_oracle.c + oracle/numpy_port.py) against fixtures produced
+by the reference's own code (scripts/make_golden.py; liana/method/_pipe_utils/_get_mean_perms.py,
+liana/method/sc/_cellphonedb.py, _geometric_mean.py executed unmodified)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, numpy_port
+
+
+def test_perm_indices_match_reference_draws(golden):
+    # the reference draws rng.permutation(idx) P times from default_rng(seed) (_get_mean_perms.py:69,79)
+    P, N = int(golden["n_perms"]), golden["X"].shape[0]
+    assert np.array_equal(numpy_port.perm_indices(N, P, int(golden["seed"])), golden["perm_idx"])
+
+
+def test_c_cube_bit_exact_vs_reference(golden):
+    kc = golden["cube"].shape[0]
+    cube = c_oracle.cube(golden["X"], golden["labels"], golden["L"], golden["perm_idx"][:kc])
+    assert cube.dtype == np.float32
+    assert np.array_equal(cube, golden["cube"])      # bit-for-bit
+
+
+def test_c_cube_cluster_sums(golden):
+    # the quantity liana/tests/test_get_mean_perms.py:27-35 pins (sum over perms and genes per cluster)
+    cube = c_oracle.cube(golden["X"], golden["labels"], golden["L"], golden["perm_idx"])
+    np.testing.assert_allclose(cube.astype(np.float64).sum(axis=(0, 2)), golden["cube_cluster_sums"], rtol=0, atol=1e-9)
+
+
+def test_numpy_port_cube_bit_exact(golden):
+    kc = min(4, golden["cube"].shape[0])
+    cube = numpy_port.get_means_perms(golden["X"], golden["labels"], golden["L"], kc, int(golden["seed"]))
+    assert np.array_equal(cube.astype(np.float32), golden["cube"][:kc])
+
+
+def test_observed_means_match_reference(golden):
+    means, stored, sizes = c_oracle.observed(golden["X"], golden["labels"], golden["L"])
+    lm = means[golden["source_idx"], golden["ligand_idx"]]
+    rm = means[golden["target_idx"], golden["receptor_idx"]]
+    assert np.array_equal(lm, golden["ligand_means"])
+    assert np.array_equal(rm, golden["receptor_means"])
+    p_means, p_props = numpy_port.observed_stats(golden["X"], golden["labels"], golden["L"])
+    assert np.array_equal(p_means, means)
+    assert np.array_equal(p_props, stored / sizes[:, None])
+
+
+def test_scores_and_pvals_match_reference(golden):
+    g = golden
+    cube = c_oracle.cube(g["X"], g["labels"], g["L"], g["perm_idx"])
+    P = cube.shape[0]
+    idx = (g["ligand_idx"], g["receptor_idx"], g["source_idx"], g["target_idx"])
+    obs_c = numpy_port.cpdb_observed(g["ligand_means"].copy(), g["receptor_means"].copy())
+    obs_g = numpy_port.gmean_observed(g["ligand_means"], g["receptor_means"])
+    assert np.array_equal(obs_c, g["cpdb_magnitude"])
+    assert np.array_equal(obs_g.astype(np.float32), g["gmean_magnitude"])
+    cnt_c = numpy_port.counts_from_cube(cube, *idx, obs_c, "cellphonedb")
+    cnt_g = numpy_port.counts_from_cube(cube, *idx, obs_g, "gmean")
+    assert np.array_equal(cnt_c / P, g["cpdb_pvals"])
+    assert np.array_equal(cnt_g / P, g["gmean_pvals"])
+    # C restatement of the CellPhoneDB count
+    assert np.array_equal(c_oracle.counts_cpdb(cube, *idx, obs_c).astype(np.int64), cnt_c)
+    # zero-masked rows: every null mean >= 0 -> p == 1 exactly
+    assert np.all(cnt_c[obs_c == 0] == P)
+
+
+def test_run_method_block_port(golden):
+    g = golden
+    P = min(6, int(g["n_perms"]))
+    lr_means, pv = numpy_port.run_method_block(
+        g["X"], g["labels"], g["L"], P, int(g["seed"]), g["ligand_idx"], g["receptor_idx"], g["source_idx"],
+        g["target_idx"], g["ligand_means"].copy(), g["receptor_means"].copy(), "cellphonedb")
+    cube = c_oracle.cube(g["X"], g["labels"], g["L"], g["perm_idx"][:P])
+    cnt = c_oracle.counts_cpdb(cube, g["ligand_idx"], g["receptor_idx"], g["source_idx"], g["target_idx"], lr_means)
+    assert np.array_equal(pv, cnt / P)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 700, 1000, 4097])
+def test_philox_bijection_is_a_permutation(n):
+    perms = c_oracle.philox_perms(n, 5, 3, 1337)
+    for p in range(5):
+        assert np.array_equal(np.sort(perms[p]), np.arange(n))
+        inv = c_oracle.philox_inverse(n, 3 + p, 1337)
+        assert np.array_equal(inv[perms[p]], np.arange(n))
+    if n > 3:
+        assert not np.array_equal(perms[0], perms[1])
+    assert np.array_equal(perms[2], c_oracle.philox_perms(n, 1, 5, 1337)[0])   # keyed by global perm id
+
+
+def test_philox_positions_are_uniform():
+    # each cell should land on each position ~uniformly over permutations (chi-square on a coarse grid)
+    n, P, bins = 200, 4000, 10
+    perms = c_oracle.philox_perms(n, P, 0, 99)
+    # position of cell 0..4 across permutations
+    for cell in range(5):
+        pos = np.argmax(perms == cell, axis=1)
+        hist = np.bincount(pos * bins // n, minlength=bins)
+        chi2 = ((hist - P / bins) ** 2 / (P / bins)).sum()
+        assert chi2 < 40.0, (cell, chi2)       # 9 dof, p ~ 1e-5
+    # adjacent cells stay adjacent no more often than chance (~2/n)
+    inv = np.argsort(perms, axis=1)
+    adj = (np.abs(inv[:, 0] - inv[:, 1]) == 1).mean()
+    assert adj < 4.0 / n + 0.02
