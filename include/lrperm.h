@@ -123,8 +123,9 @@ int lrperm_philox_perms(lrperm_engine *h, int64_t n_cells, int64_t n_perms, int6
  * Also number of kernel launches of the last run in out[4]. */
 int lrperm_last_timings(lrperm_engine *h, float *out5);
 
-/* Tuning knobs (0 = engine default): perms per label slab batch in FAST mode, nnz per gene chunk. */
-int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_chunk_nnz);
+/* Tuning knobs of FAST mode (0 = engine default): permutations per batch (multiple of 128), stored
+ * entries per gene chunk, and MiB of label slab one cell tile may span (kept L2 resident). */
+int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_chunk_nnz, int32_t fast_tile_mib);
 
 #ifdef __cplusplus
 }

@@ -51,7 +51,7 @@ def load_library():
     lib.lrperm_destroy.argtypes = [vp]
     lib.lrperm_destroy.restype = None
     lib.lrperm_set_stream.argtypes = [vp, vp]
-    lib.lrperm_set_tuning.argtypes = [vp, i32, i32]
+    lib.lrperm_set_tuning.argtypes = [vp, i32, i32, i32]
     lib.lrperm_set_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int]
     lib.lrperm_set_labels.argtypes = [vp, vp, i32, C.c_int]
     lib.lrperm_set_triples.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_int]
@@ -121,8 +121,8 @@ class Engine:
     def set_stream(self, cuda_stream_ptr: Optional[int]):
         self._check(self._lib.lrperm_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
-    def set_tuning(self, fast_perm_batch: int = 0, fast_chunk_nnz: int = 0):
-        self._check(self._lib.lrperm_set_tuning(self._h, int(fast_perm_batch), int(fast_chunk_nnz)))
+    def set_tuning(self, fast_perm_batch: int = 0, fast_chunk_nnz: int = 0, fast_tile_mib: int = 0):
+        self._check(self._lib.lrperm_set_tuning(self._h, int(fast_perm_batch), int(fast_chunk_nnz), int(fast_tile_mib)))
 
     # -- inputs ----------------------------------------------------------------------------
     def set_matrix_csr(self, indptr, indices, data, n_cells: int, n_genes: int):

@@ -73,7 +73,8 @@ struct lrperm_engine {
 
     // FAST-mode chunk tables
     int32_t fast_perm_batch = 0, fast_chunk_nnz = 0;   // 0 = auto
-    int32_t chunk_table_nnz = -1;                       // chunk size the tables were built for
+    int32_t chunk_table_nnz = -1, chunk_table_tile = -1;   // parameters the chunk tables were built for
+    int32_t fast_tile_bytes = 0;                        // label-slab bytes one cell tile may span (0 = auto)
     int32_t n_chunks = 0, n_slots = 0;
     DevBuf chunks, gene_slot_ptr;
 
@@ -201,26 +202,49 @@ int build_csc(lrperm_engine* h) {
     return LRPERM_OK;
 }
 
-int build_chunks(lrperm_engine* h, int32_t chunk_nnz) {
-    if (h->chunk_table_nnz == chunk_nnz) return LRPERM_OK;
+int build_chunks(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
+    if (h->chunk_table_nnz == chunk_nnz && h->chunk_table_tile == tile_cells) return LRPERM_OK;
     const int32_t G = (int32_t)h->G;
-    std::vector<FastChunk> chunks;
+    // Split every gene's entry list at cell-tile boundaries (so that the chunks scheduled at any one
+    // time only touch one tile of the label slab, which then stays L2 resident) and at chunk_nnz.
+    const int32_t n_tiles = (int32_t)std::max<int64_t>(1, (h->N + tile_cells - 1) / tile_cells);
+    std::vector<int32_t> bounds((size_t)G * (n_tiles + 1));
+    {
+        DevBuf d_ptr, d_bounds;
+        CK(d_ptr.ensure(sizeof(int32_t) * ((size_t)G + 1)));
+        CK(d_bounds.ensure(sizeof(int32_t) * bounds.size()));
+        CK(cudaMemcpyAsync(d_ptr.p, h->h_csc_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
+        tile_bounds_kernel<<<grid_for((int64_t)bounds.size(), 256, 1 << 30), 256, 0, h->stream>>>(
+            h->csc_pairs.as<int2>(), d_ptr.as<int32_t>(), G, n_tiles, tile_cells, d_bounds.as<int32_t>());
+        CK_LAUNCH();
+        CK(cudaMemcpyAsync(bounds.data(), d_bounds.p, sizeof(int32_t) * bounds.size(), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        d_ptr.release(); d_bounds.release();
+    }
+    struct Tagged { FastChunk c; int32_t tile; };
+    std::vector<Tagged> tagged;
     std::vector<int32_t> slot_ptr((size_t)G + 1, 0);
     int32_t slot = 0;
     for (int32_t g = 0; g < G; ++g) {
         slot_ptr[(size_t)g] = slot;
-        const int32_t b = h->h_csc_ptr[(size_t)g], e = h->h_csc_ptr[(size_t)g + 1];
-        for (int32_t s = b; s < e; s += chunk_nnz) {
-            FastChunk c;
-            c.gene = g; c.begin = s; c.end = std::min(e, s + chunk_nnz); c.slot = slot++;
-            chunks.push_back(c);
+        for (int32_t t = 0; t < n_tiles; ++t) {
+            const int32_t b = bounds[(size_t)g * (n_tiles + 1) + t], e = bounds[(size_t)g * (n_tiles + 1) + t + 1];
+            for (int32_t s = b; s < e; s += chunk_nnz) {
+                Tagged x;
+                x.c.gene = g; x.c.begin = s; x.c.end = std::min(e, s + chunk_nnz); x.c.slot = slot++;
+                x.tile = t;
+                tagged.push_back(x);
+            }
         }
     }
     slot_ptr[(size_t)G] = slot;
-    // longest chunks first (they are launched first -> short ones fill the tail)
-    std::stable_sort(chunks.begin(), chunks.end(), [](const FastChunk& a, const FastChunk& b) {
-        return (a.end - a.begin) > (b.end - b.begin);
+    // tile-major; inside a tile the longest chunks first (short ones fill the tail)
+    std::stable_sort(tagged.begin(), tagged.end(), [](const Tagged& a, const Tagged& b) {
+        if (a.tile != b.tile) return a.tile < b.tile;
+        return (a.c.end - a.c.begin) > (b.c.end - b.c.begin);
     });
+    std::vector<FastChunk> chunks(tagged.size());
+    for (size_t i = 0; i < tagged.size(); ++i) chunks[i] = tagged[i].c;
     h->n_chunks = (int32_t)chunks.size();
     h->n_slots = slot;
     CK(h->chunks.ensure(sizeof(FastChunk) * std::max<size_t>(chunks.size(), 1)));
@@ -230,6 +254,7 @@ int build_chunks(lrperm_engine* h, int32_t chunk_nnz) {
     CK(cudaMemcpyAsync(h->gene_slot_ptr.p, slot_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
     h->chunk_table_nnz = chunk_nnz;
+    h->chunk_table_tile = tile_cells;
     return LRPERM_OK;
 }
 
@@ -356,12 +381,13 @@ int lrperm_set_stream(lrperm_engine* h, void* cuda_stream) {
     return LRPERM_OK;
 }
 
-int lrperm_set_tuning(lrperm_engine* h, int32_t fast_perm_batch, int32_t fast_chunk_nnz) {
+int lrperm_set_tuning(lrperm_engine* h, int32_t fast_perm_batch, int32_t fast_chunk_nnz, int32_t fast_tile_mib) {
     if (!h) return LRPERM_ERR_INVALID;
-    if (fast_perm_batch < 0 || fast_chunk_nnz < 0 || (fast_perm_batch % 128) != 0)
+    if (fast_perm_batch < 0 || fast_chunk_nnz < 0 || fast_tile_mib < 0 || fast_tile_mib > 1024 || (fast_perm_batch % 128) != 0)
         return h->fail(LRPERM_ERR_INVALID, "lrperm_set_tuning: fast_perm_batch must be a non-negative multiple of 128");
     h->fast_perm_batch = fast_perm_batch;
     h->fast_chunk_nnz = fast_chunk_nnz;
+    h->fast_tile_bytes = fast_tile_mib << 20;
     return LRPERM_OK;
 }
 
@@ -608,14 +634,13 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         Q = pick_q(h);
         if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: %d clusters do not fit the shared-memory bins", L);
         if ((rc = build_csc(h))) return rc;
-        PB = h->fast_perm_batch;
-        if (PB == 0) {
-            // label slab N x PB bytes should stay L2 resident (~48 MB budget), PB in {128, 256, 512}
-            PB = 512;
-            while (PB > 128 && (int64_t)PB * N > (48LL << 20)) PB >>= 1;
-        }
-        int32_t chunk_nnz = h->fast_chunk_nnz ? h->fast_chunk_nnz : 4096;
-        if ((rc = build_chunks(h, chunk_nnz))) return rc;
+        PB = h->fast_perm_batch ? h->fast_perm_batch : 512;
+        if (n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((n_perms + 127) / 128) * 128);
+        // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
+        const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (16LL << 20);
+        const int32_t tile_cells = (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / PB, 1024), std::max<int64_t>(N, 1));
+        const int32_t chunk_nnz = h->fast_chunk_nnz ? h->fast_chunk_nnz : 4096;
+        if ((rc = build_chunks(h, chunk_nnz, tile_cells))) return rc;
     } else {
         // enough (perm, cluster) warps for several waves, cube batch <= ~256 MB
         PB = 512;

@@ -85,6 +85,21 @@ __global__ void gather_csc_kernel(const int32_t* __restrict__ sorted_src, const 
     }
 }
 
+// first stored entry of gene g whose cell id is >= t * tile_cells (CSC cells ascend within a gene)
+__global__ void tile_bounds_kernel(const int2* __restrict__ csc_pairs, const int32_t* __restrict__ csc_ptr, int32_t G,
+                                   int32_t n_tiles, int32_t tile_cells, int32_t* __restrict__ bounds /*[G][n_tiles+1]*/) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)G * (n_tiles + 1)) return;
+    const int g = (int)(i / (n_tiles + 1)), t = (int)(i % (n_tiles + 1));
+    int lo = csc_ptr[g], hi = csc_ptr[g + 1];
+    const int64_t key = (int64_t)t * tile_cells;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if ((int64_t)csc_pairs[mid].x < key) lo = mid + 1; else hi = mid;
+    }
+    bounds[i] = lo;
+}
+
 // stored-entry counts per (cluster, gene): props = count / n_c  (_common.py:41-42)
 __global__ void stored_counts_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
                                      const int32_t* __restrict__ labels, int32_t N, int32_t G,
@@ -251,8 +266,20 @@ template <> struct LabelWord<4> { using type = uint32_t; };
 
 struct FastChunk { int32_t gene, begin, end, slot; };   // slot = index of the partial-sum row block
 
+template <int Q>
+__device__ __forceinline__ void fast_update(float* mybins, uint32_t lw, float v) {
+    float* b[Q];
+    float x[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) b[q] = mybins + (((lw >> (8 * q)) & 0xffu) * Q + q) * 32;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) x[q] = *b[q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) *b[q] = x[q] + v;
+}
+
 template <int Q, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 1)
 fast_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restrict__ chunks, int32_t n_chunks,
                   const uint8_t* __restrict__ slab, int32_t PB, int32_t L, int32_t groups_per_batch,
                   float* __restrict__ partials /*[slot][L][PB]*/) {
@@ -269,45 +296,39 @@ fast_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restric
     for (int i = lane; i < L * Q * 32; i += 32) bins[i] = 0.0f;
     __syncwarp();
 
-    const LW* __restrict__ slab_w = reinterpret_cast<const LW*>(slab);
-    const int row_words = PB / Q;                  // label words per slab row
-    const int col_word = group * 32 + lane;        // this lane's word within the row
+    const LW* __restrict__ slab_w = reinterpret_cast<const LW*>(slab) + (group * 32 + lane);
+    const int64_t row_words = PB / Q;              // label words per slab row
     float* mybins = bins + lane;
 
-    constexpr int U = 8;
-    int k = ch.begin;
-    for (; k + U <= ch.end; k += U) {
-        int2 pr[U];
-        LW lw[U];
+    // Software pipeline over blocks of 32 stored entries: lane l holds entry k+l; cell ids are
+    // broadcast by shuffle so that the 32 label-word loads of the NEXT block are all in flight
+    // (L2 latency) while the current block's 32 x Q bin updates run out of shared memory.
+    constexpr int B = 32;
+    const int first_cell = __ldg(&csc_pairs[ch.begin]).x;
+    auto load_pair = [&](int k) -> int2 {
+        return (k + lane < ch.end) ? __ldg(&csc_pairs[k + lane]) : make_int2(first_cell, 0);   // tail: adds +0.0f
+    };
+    LW lw_cur[B], lw_nxt[B];
+    int2 pr_cur = load_pair(ch.begin);
 #pragma unroll
-        for (int u = 0; u < U; ++u) pr[u] = __ldg(&csc_pairs[k + u]);
+    for (int u = 0; u < B; ++u) lw_cur[u] = __ldg(slab_w + (int64_t)__shfl_sync(0xffffffffu, pr_cur.x, u) * row_words);
+    for (int k = ch.begin; k < ch.end; k += B) {
+        const bool more = k + B < ch.end;
+        int2 pr_nxt = make_int2(first_cell, 0);
+        if (more) {
+            pr_nxt = load_pair(k + B);
 #pragma unroll
-        for (int u = 0; u < U; ++u) lw[u] = __ldg(&slab_w[(int64_t)pr[u].x * row_words + col_word]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float v = __int_as_float(pr[u].y);
-            float* b[Q];
-            float x[Q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const int c = (int)((lw[u] >> (8 * q)) & 0xff);
-                b[q] = mybins + (c * Q + q) * 32;
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) x[q] = *b[q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) *b[q] = x[q] + v;
+            for (int u = 0; u < B; ++u) lw_nxt[u] = __ldg(slab_w + (int64_t)__shfl_sync(0xffffffffu, pr_nxt.x, u) * row_words);
         }
-    }
-    for (; k < ch.end; ++k) {
-        const int2 pr = __ldg(&csc_pairs[k]);
-        const LW lw = __ldg(&slab_w[(int64_t)pr.x * row_words + col_word]);
-        const float v = __int_as_float(pr.y);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int c = (int)((lw >> (8 * q)) & 0xff);
-            float* b = mybins + (c * Q + q) * 32;
-            *b = *b + v;
+        for (int u = 0; u < B; ++u) {
+            const float v = __int_as_float(__shfl_sync(0xffffffffu, pr_cur.y, u));
+            fast_update<Q>(mybins, (uint32_t)lw_cur[u], v);
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < B; ++u) lw_cur[u] = lw_nxt[u];
+            pr_cur = pr_nxt;
         }
     }
     __syncwarp();
