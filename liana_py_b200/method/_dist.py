@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+The permutation null shards naturally: rank r runs permutations
+[P*r/R, P*(r+1)/R) against replicated inputs and only the uint32 exceedance counters are
+combined - one integer all-reduce, so results are bit-identical for any number of GPUs.
+`by_sample` shards whole samples and needs no collective (results are gathered as objects).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class DistContext:
+    def __init__(self, rank: int = 0, world_size: int = 1, device=None, group=None):
+        self.rank, self.world_size, self.device, self.group = rank, world_size, device, group
+
+    @classmethod
+    def from_torch(cls, group=None):
+        """Context of the already-initialised default process group (or a single-rank context)."""
+        try:
+            import torch.distributed as dist
+        except Exception:     # pragma: no cover
+            return cls()
+        if not (dist.is_available() and dist.is_initialized()):
+            return cls()
+        import torch
+        backend = dist.get_backend(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        return cls(dist.get_rank(group), dist.get_world_size(group), device, group)
+
+    def perm_range(self, n_perms: int):
+        """Contiguous block of global permutation ids owned by this rank."""
+        return (n_perms * self.rank) // self.world_size, (n_perms * (self.rank + 1)) // self.world_size
+
+    def all_reduce_sum_u32(self, counts: np.ndarray) -> np.ndarray:
+        """Sum a host uint32 vector over ranks (counts <= n_perms, so int32 transport is exact)."""
+        if self.world_size == 1:
+            return counts
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(counts.astype(np.int32, copy=True)).to(self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy().astype(np.uint32)
+
+    def all_reduce_sum_(self, tensor):
+        """In-place sum of a device int32 tensor (the bench's HBM-resident path)."""
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+        return tensor
+
+    def sample_shard(self, sizes):
+        """Longest-first greedy assignment of samples to ranks; returns indices owned by this rank."""
+        order = np.argsort(-np.asarray(sizes), kind="stable")
+        load = np.zeros(self.world_size)
+        owner = np.empty(len(sizes), dtype=np.int64)
+        for i in order:
+            r = int(np.argmin(load))
+            owner[i] = r
+            load[r] += sizes[i]
+        return [int(i) for i in np.flatnonzero(owner == self.rank)]
+
+    def all_gather_objects(self, obj):
+        if self.world_size == 1:
+            return [obj]
+        import torch.distributed as dist
+        out = [None] * self.world_size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out

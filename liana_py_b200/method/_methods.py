@@ -1,0 +1,214 @@
+"""Drop-in `li.mt.cellphonedb` / `li.mt.geometric_mean` (+ `.by_sample`) backed by the CUDA engine.
+
+Same call signatures, defaults, result columns, dtypes and sort order as the reference's
+`Method.__call__` / `MethodMeta.by_sample` (`liana/method/sc/_Method.py:92-267`).  Engine-only
+options are keyword-only with defaults:
+
+  perm_source  'philox'    (default) permutations generated on device from (seed, perm id)
+               'reference' the reference's own NumPy PCG64 draws -> results identical to liana
+  order        None (auto: 'exact' with perm_source='reference', 'fast' with 'philox') | 'exact' | 'fast'
+  gmean_mode   'product' (exact comparison) | 'literal' (float64 exp/log like scipy.stats.gmean)
+  device       CUDA device index;  dist: a DistContext to shard permutations / samples over ranks
+`n_jobs` is accepted and ignored (parallelism is on the GPU).
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+
+from .. import _constants as K
+from . import _pipeline as PL
+from . import _tables
+from ._dist import DistContext
+
+V = K.DefaultValues
+
+
+class NullCounts:
+    """What the engine hands a score function instead of the reference's perm_stats[2,P,T] cube:
+    exceedance counts per row and the number of permutations."""
+
+    def __init__(self, counts: np.ndarray, n_perms: int):
+        self.counts, self.n_perms = counts, n_perms
+
+    def pvals(self) -> np.ndarray:
+        return self.counts / self.n_perms          # float64, `_get_mean_perms.py:137`
+
+
+class MethodMeta:
+    """Method metadata record; same fields as `liana/method/sc/_Method.py:16-69`."""
+    instances = []
+
+    def __init__(self, method_name, complex_cols, add_cols, fun, magnitude, magnitude_ascending,
+                 specificity, specificity_ascending, permute, reference, engine_score=None):
+        self.__class__.instances.append(weakref.proxy(self))
+        self.method_name = method_name
+        self.complex_cols = complex_cols
+        self.add_cols = add_cols
+        self.fun = fun
+        self.magnitude = magnitude
+        self.magnitude_ascending = magnitude_ascending
+        self.specificity = specificity
+        self.specificity_ascending = specificity_ascending
+        self.permute = permute
+        self.reference = reference
+        self.engine_score = engine_score        # 'cpdb' | 'gmean' | None: which null the engine counts
+
+    def describe(self):
+        print(f"{self.method_name} uses `{self.magnitude}` and `{self.specificity}`"
+              f" as measures of expression strength and interaction specificity, respectively")
+
+    def get_meta(self):
+        return pd.DataFrame([{"Method Name": self.method_name, "Magnitude Score": self.magnitude,
+                              "Specificity Score": self.specificity, "Reference": self.reference}])
+
+    # ------------------------------------------------------------------------------------
+    def by_sample(self, adata, sample_key: str, key_added: str = K.Keys.uns_key, inplace: bool = V.inplace,
+                  verbose=V.verbose, **kwargs):
+        """Run the method per sample (`_Method.py:92-159`).  Samples are independent; with a
+        DistContext (kwarg `dist`) whole samples are sharded over ranks, longest first, and the
+        per-sample frames are gathered - no data-path collective."""
+        if sample_key not in adata.obs:
+            raise ValueError(f"{sample_key} was not found in `adata.obs`.")
+        if not isinstance(adata.obs[sample_key].dtype, pd.CategoricalDtype):
+            adata.obs[sample_key] = adata.obs[sample_key].astype("category")
+        full_verbose = verbose == 'full'
+        samples = list(adata.obs[sample_key].cat.categories)
+        dist: Optional[DistContext] = kwargs.pop("dist", None)
+        sample_col = np.asarray(adata.obs[sample_key])
+        sizes = [int((sample_col == s).sum()) for s in samples]
+        mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
+        results = {}
+        for i in mine:
+            temp = adata[sample_col == samples[i]].copy()
+            results[samples[i]] = self.__call__(temp, inplace=False, verbose=full_verbose, **kwargs)
+        if dist is not None and dist.world_size > 1:
+            merged = {}
+            for part in dist.all_gather_objects(results):
+                merged.update(part)
+            results = merged
+        frames = []
+        for s in samples:                      # sample-category order, like the reference's concat
+            df = results[s].copy()
+            df.insert(0, sample_key, s)
+            frames.append(df)
+        liana_res = pd.concat(frames, ignore_index=True)
+        if inplace:
+            adata.uns[key_added] = liana_res
+        return None if inplace else liana_res
+
+
+class Method(MethodMeta):
+    def __init__(self, _method: MethodMeta):
+        super().__init__(method_name=_method.method_name, complex_cols=_method.complex_cols,
+                         add_cols=_method.add_cols, fun=_method.fun, magnitude=_method.magnitude,
+                         magnitude_ascending=_method.magnitude_ascending, specificity=_method.specificity,
+                         specificity_ascending=_method.specificity_ascending, permute=_method.permute,
+                         reference=_method.reference, engine_score=_method.engine_score)
+        self._method = _method
+
+    def __call__(self, adata, groupby: str, resource_name: str = V.resource_name, expr_prop: float = V.expr_prop,
+                 min_cells: int = V.min_cells, groupby_pairs: Optional[pd.DataFrame] = V.groupby_pairs,
+                 base: float = V.logbase, supp_columns: Optional[list] = V.supp_columns,
+                 return_all_lrs: bool = V.return_all_lrs, key_added: str = K.Keys.uns_key,
+                 use_raw: Optional[bool] = V.use_raw, layer: Optional[str] = V.layer, de_method: str = V.de_method,
+                 n_perms: Optional[int] = V.n_perms, seed: int = V.seed, n_jobs: int = 1,
+                 resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
+                 mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
+                 *, perm_source: str = "philox", order: Optional[str] = None, gmean_mode: str = "product",
+                 device: int = 0, dist: Optional[DistContext] = None):
+        if supp_columns:
+            raise NotImplementedError("supp_columns are outside the scope of the permutation engine")
+        state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
+                           use_raw, layer, verbose, device=device)
+        liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
+                               perm_source, order, gmean_mode, dist)
+        liana_res = liana_res.sort_values(by=self.magnitude, ascending=self.magnitude_ascending)
+        if inplace:
+            adata.uns[key_added] = liana_res
+        return None if inplace else liana_res
+
+
+def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_lrs, perm_source, order,
+               gmean_mode, dist, aggregate_flag=False, null_cache=None) -> pd.DataFrame:
+    """`_run_method` (`_liana_pipe.py:363-452`) for one method on a prepared PipelineState."""
+    tri = _tables.resolve_triples(state.tables, state.means, state.props, expr_prop, state.pair_mask, return_all_lrs)
+    lr_res = PL.base_frame(state, tri)
+    kept = tri.keep
+    x = lr_res[kept] if return_all_lrs else lr_res
+    null = None
+    if method.permute and n_perms is not None:
+        sub = tri if not return_all_lrs else _subset(tri, kept)
+        key = (method.engine_score, n_perms, seed, perm_source, order, gmean_mode, expr_prop, return_all_lrs)
+        if null_cache is not None and key in null_cache:
+            null = null_cache[key]
+        else:
+            both = null_cache is not None      # rank_aggregate: one pass counts both nulls from one cube
+            oc = PL.observed_cpdb(sub.ligand_means, sub.receptor_means) if (both or method.engine_score == "cpdb") else None
+            og = PL.observed_gmean(sub.ligand_means, sub.receptor_means) if (both or method.engine_score == "gmean") else None
+            out = PL.permutation_counts(state, sub, oc, og, n_perms, seed, perm_source, order, gmean_mode, dist)
+            if null_cache is not None:
+                for name in ("cpdb", "gmean"):
+                    if name in out:
+                        null_cache[(name,) + key[1:]] = NullCounts(out[name], n_perms)
+            null = NullCounts(out[method.engine_score], n_perms)
+    magnitude, specificity = method.fun(x, null) if method.permute else method.fun(x)
+    spec_name = method.specificity if (not method.permute or n_perms is not None) else None
+    lr_res = lr_res.copy()
+    if method.magnitude is not None:
+        lr_res[method.magnitude] = _scatter(magnitude, kept, return_all_lrs)
+    if spec_name is not None:
+        lr_res[spec_name] = _scatter(specificity, kept, return_all_lrs)
+    if return_all_lrs:
+        lr_res[K.LRS_TO_KEEP] = kept
+        # rows that failed expr_prop get the worst kept value (`_liana_pipe.py:433-443`)
+        for col, asc in ((method.magnitude, method.magnitude_ascending), (spec_name, method.specificity_ascending)):
+            if col is not None:
+                vals = lr_res[col]
+                lr_res.loc[~kept, col] = vals.max() if asc else vals.min()
+    if aggregate_flag:
+        cols = K.PRIMARY + [c for c in (method.magnitude, spec_name) if c is not None]
+        lr_res = lr_res[cols]
+    return lr_res
+
+
+def _scatter(values, kept, return_all_lrs):
+    if not return_all_lrs:
+        return values
+    out = np.full(kept.shape[0], np.nan, dtype=np.asarray(values).dtype if np.asarray(values).dtype.kind == 'f' else np.float64)
+    out[kept] = values
+    return out
+
+
+def _subset(tri, mask):
+    return _tables.ResolvedTriples(**{k: getattr(tri, k)[mask] for k in tri.__dataclass_fields__})
+
+
+# ---- the two permutation score functions ------------------------------------------------------
+def _cpdb_score(x: pd.DataFrame, perm_stats: Optional[NullCounts]):
+    """CellPhoneDB-like lr_means and p-values (`liana/method/sc/_cellphonedb.py:9-30`)."""
+    lr_means = PL.observed_cpdb(x[K.LIGAND_MEANS].values, x[K.RECEPTOR_MEANS].values)
+    return lr_means, (perm_stats.pvals() if perm_stats is not None else None)
+
+
+def _gmean_score(x: pd.DataFrame, perm_stats: Optional[NullCounts]):
+    """Geometric-mean magnitude and p-values (`liana/method/sc/_geometric_mean.py:6-25`)."""
+    lr_gmeans = PL.observed_gmean(x[K.LIGAND_MEANS].values, x[K.RECEPTOR_MEANS].values)
+    return lr_gmeans, (perm_stats.pvals() if perm_stats is not None else None)
+
+
+_cellphonedb = MethodMeta(method_name="CellPhoneDB", complex_cols=[K.LIGAND_MEANS, K.RECEPTOR_MEANS], add_cols=[],
+                          fun=_cpdb_score, magnitude="lr_means", magnitude_ascending=False,
+                          specificity="cellphone_pvals", specificity_ascending=True, permute=True,
+                          reference="Efremova et al., 2020. Nature protocols 15(4).", engine_score="cpdb")
+_geometric_mean = MethodMeta(method_name="Geometric Mean", complex_cols=[K.LIGAND_MEANS, K.RECEPTOR_MEANS], add_cols=[],
+                             fun=_gmean_score, magnitude="lr_gmeans", magnitude_ascending=False,
+                             specificity="gmean_pvals", specificity_ascending=True, permute=True,
+                             reference="CellPhoneDBv2's permutation approach applied to the geometric means.",
+                             engine_score="gmean")
+
+cellphonedb = Method(_method=_cellphonedb)
+geometric_mean = Method(_method=_geometric_mean)

@@ -1,0 +1,141 @@
+"""Host side of the drop-in: the equivalent of `liana_pipe` + `_run_method`
+(`liana/method/sc/_liana_pipe.py:23-252, 363-452`) for the permutation methods, with the block
+`:402-425` (cube -> gather -> score -> p-values) replaced by ONE call into the CUDA engine.
+
+No CPU fallback: the per-cluster statistics and the permutation null always run on the GPU
+through the C ABI (`liana_py_b200._engine`).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+from scipy.stats import gmean as _scipy_gmean
+
+from .. import _constants as K
+from .. import _engine as E
+from ..resource import handle_resource
+from . import _pre, _tables
+from ._dist import DistContext
+
+_ENGINES = {}
+
+
+def get_engine(device: int = 0) -> E.Engine:
+    """One cached engine per CUDA device (raises EngineError if the library / GPU is missing)."""
+    eng = _ENGINES.get(device)
+    if eng is None or eng._h is None:
+        eng = E.Engine(device)
+        _ENGINES[device] = eng
+    return eng
+
+
+def observed_cpdb(ligand_means: np.ndarray, receptor_means: np.ndarray) -> np.ndarray:
+    """float32 mean of the pair, zero where either side is zero (`_cellphonedb.py:25-27`)."""
+    zero = (ligand_means == 0) | (receptor_means == 0)
+    out = np.mean((ligand_means, receptor_means), axis=0)
+    out[zero] = 0
+    return out
+
+
+def observed_gmean(ligand_means: np.ndarray, receptor_means: np.ndarray) -> np.ndarray:
+    """scipy.stats.gmean of the pair in float32 (`_geometric_mean.py:22`); host side so that the
+    threshold is bit-identical to the reference's NumPy math."""
+    with np.errstate(divide="ignore"):
+        return _scipy_gmean((ligand_means, receptor_means), axis=0)
+
+
+def reference_perm_indices(n_cells: int, n_perms: int, seed: int) -> np.ndarray:
+    """The reference's own draws: ONE default_rng(seed), `rng.permutation(arange(N))` P times in
+    order (`_get_mean_perms.py:69-72,79`).  Used when perm_source='reference' (validation mode)."""
+    rng = np.random.default_rng(seed=seed)
+    idx = np.arange(n_cells)
+    out = np.empty((n_perms, n_cells), dtype=np.int32 if n_cells < 2 ** 31 else np.int64)
+    for p in range(n_perms):
+        out[p] = rng.permutation(idx)
+    return out
+
+
+class PipelineState:
+    """Everything computed before any method-specific scoring (shared by rank_aggregate methods)."""
+
+    def __init__(self, prep, tables, engine, means, props, sizes, pair_mask):
+        self.prep, self.tables, self.engine = prep, tables, engine
+        self.means, self.props, self.sizes, self.pair_mask = means, props, sizes, pair_mask
+
+
+def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells, use_raw, layer,
+            verbose, device=0) -> PipelineState:
+    res = handle_resource(interactions=interactions, resource=resource, resource_name=resource_name, verbose=verbose)
+    groupby_subset = None
+    if groupby_pairs is not None:
+        if not (K.SOURCE in groupby_pairs.columns) | (K.TARGET in groupby_pairs.columns):
+            raise AssertionError(f"{K.SOURCE} and {K.TARGET} must be in groupby_pairs")
+        groupby_subset = np.union1d(groupby_pairs[K.SOURCE].unique(), groupby_pairs[K.TARGET].unique())
+    prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, groupby_subset=groupby_subset,
+                              use_raw=use_raw, layer=layer, verbose=verbose)
+    _pre.assert_covered(_tables.resource_entities(res), prep.var_names, verbose=verbose)
+    tables = _tables.build_resource_tables(res, prep.var_names)
+    # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`)
+    cols = np.searchsorted(prep.var_names, tables.entities)
+    X = prep.X[:, cols].tocsr()
+    X.sort_indices()
+    prep.X, prep.var_names = X, tables.entities
+    if verbose:
+        print(f"Generating ligand-receptor stats for {X.shape[0]} samples and {X.shape[1]} features")
+    L = len(prep.categories)
+    eng = get_engine(device)
+    eng.set_matrix(X)
+    eng.set_labels(prep.labels, L)
+    means, stored, sizes = eng.observed()
+    props = stored / sizes[:, None].astype(np.float64)
+    pair_mask = None
+    if groupby_pairs is not None:
+        pos = {c: i for i, c in enumerate(prep.categories)}
+        pair_mask = np.zeros((L, L), dtype=bool)
+        for s, t in zip(groupby_pairs[K.SOURCE], groupby_pairs[K.TARGET]):
+            if s in pos and t in pos:
+                pair_mask[pos[s], pos[t]] = True
+    return PipelineState(prep, tables, eng, means, props, sizes, pair_mask)
+
+
+def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFrame:
+    """lr_res with the reference's column names / dtypes / order for the kept rows."""
+    names, cats, tb = state.prep.var_names, state.prep.categories, state.tables
+    return pd.DataFrame({
+        K.LIGAND: names[tri.lig_gene], K.LIGAND_COMPLEX: tb.ligand_complex[tri.inter],
+        K.LIGAND_MEANS: tri.ligand_means, K.LIGAND_PROPS: tri.ligand_props,
+        K.RECEPTOR: names[tri.rec_gene], K.RECEPTOR_COMPLEX: tb.receptor_complex[tri.inter],
+        K.RECEPTOR_MEANS: tri.receptor_means, K.RECEPTOR_PROPS: tri.receptor_props,
+        K.SOURCE: np.asarray(cats)[tri.src], K.TARGET: np.asarray(cats)[tri.tgt],
+    })
+
+
+def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, seed, perm_source, order,
+                       gmean_mode, dist: DistContext | None = None):
+    """Exceedance counts for the kept rows.  Permutations are sharded over ranks when a
+    DistContext with world_size > 1 is given; the uint32 count vectors are summed with one
+    all-reduce (integer -> identical for any GPU count)."""
+    eng = state.engine
+    scores = (E.SCORE_CPDB if obs_cpdb is not None else 0) | (E.SCORE_GMEAN if obs_gmean is not None else 0)
+    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs_cpdb, obs_gmean)
+    rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
+    lo = (n_perms * rank) // world
+    hi = (n_perms * (rank + 1)) // world
+    if perm_source == "reference":
+        perm_idx = reference_perm_indices(state.prep.X.shape[0], n_perms, seed)[lo:hi]
+        if order is None:
+            order = "exact"
+    elif perm_source == "philox":
+        perm_idx = None
+        if order is None:
+            order = "fast"
+    else:
+        raise ValueError("perm_source must be 'philox' or 'reference'")
+    if order not in ("exact", "fast"):
+        raise ValueError("order must be 'exact', 'fast' or None")
+    out = eng.run(hi - lo, seed=seed, perm_offset=lo, perm_idx=perm_idx,
+                  order=E.ORDER_EXACT if order == "exact" else E.ORDER_FAST, scores=scores,
+                  gmean_mode=E.GMEAN_LITERAL if gmean_mode == "literal" else E.GMEAN_PRODUCT)
+    if dist is not None and world > 1:
+        out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
+    return out

@@ -1,0 +1,125 @@
+"""Vectorised construction of the tables the permutation kernels consume.
+
+Replaces, with identical results, the reference's pandas pipeline between the per-cluster
+statistics and the score function:
+
+  explode_complexes              liana/resource/_reassemble_complexes.py:104-134
+  filter_resource                liana/method/_pipe_utils/_pre.py:188-224
+  _join_stats (L^2 merges)       liana/method/_pipe_utils/_common.py:5-39, _liana_pipe.py:310-321
+  filter_reassemble_complexes    liana/resource/_reassemble_complexes.py:11-101
+  _get_positions / _get_mat_idx  liana/method/_pipe_utils/_get_mean_perms.py:90-113  (O(T*G) there)
+
+Key facts used: for a row (source s, target t, ligand complex LC, receptor
+complex RC) the kept ligand subunit is the FIRST subunit (in the complex's '_' order) whose
+mean in s is minimal, the receptor subunit likewise in t; the row survives if
+min(all ligand-subunit props in s, all receptor-subunit props in t) >= expr_prop.
+So everything factorises into [n_interactions, L] tables.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import pandas as pd
+
+
+@dataclass
+class ResourceTables:
+    ligand_complex: np.ndarray     # [n_int] str
+    receptor_complex: np.ndarray   # [n_int] str
+    lig_sub: np.ndarray            # [n_int, max_l] gene index, -1 padded
+    rec_sub: np.ndarray            # [n_int, max_r]
+    entities: np.ndarray           # sorted gene names used by the kept interactions
+
+
+def resource_entities(resource: pd.DataFrame, sep: str = "_") -> np.ndarray:
+    """All subunit symbols named by the resource (np.union1d of exploded ligand / receptor)."""
+    genes = set()
+    for col in ("ligand", "receptor"):
+        for entry in resource[col].astype(str):
+            genes.update(entry.split(sep))
+    return np.array(sorted(genes), dtype=str)
+
+
+def build_resource_tables(resource: pd.DataFrame, var_names: np.ndarray, sep: str = "_"):
+    """Drop interactions with any subunit missing from `var_names` (filter_resource), then index
+    the remaining subunits into the gene-subset column space (sorted intersection of resource
+    entities and var_names, `_liana_pipe.py:161-164`).  Returns (tables, entities)."""
+    present = set(map(str, var_names))
+    lig_lists, rec_lists, lc, rc = [], [], [], []
+    for lig, rec in zip(resource["ligand"].astype(str), resource["receptor"].astype(str)):
+        ls, rs = lig.split(sep), rec.split(sep)
+        if all(x in present for x in ls) and all(x in present for x in rs):
+            lig_lists.append(ls); rec_lists.append(rs); lc.append(lig); rc.append(rec)
+    ents = sorted({g for lst in lig_lists for g in lst} | {g for lst in rec_lists for g in lst})
+    entities = np.array(ents, dtype=str)
+    pos = {g: i for i, g in enumerate(ents)}
+    n = len(lc)
+    max_l = max((len(x) for x in lig_lists), default=1)
+    max_r = max((len(x) for x in rec_lists), default=1)
+    lig_sub = np.full((n, max_l), -1, dtype=np.int32)
+    rec_sub = np.full((n, max_r), -1, dtype=np.int32)
+    for i, (ls, rs) in enumerate(zip(lig_lists, rec_lists)):
+        lig_sub[i, :len(ls)] = [pos[g] for g in ls]
+        rec_sub[i, :len(rs)] = [pos[g] for g in rs]
+    return ResourceTables(np.array(lc, dtype=str), np.array(rc, dtype=str), lig_sub, rec_sub, entities)
+
+
+def _resolve_side(sub: np.ndarray, means: np.ndarray, props: np.ndarray, first_subunit: bool):
+    """For every (interaction, cluster): chosen subunit gene, its mean / prop, and the minimal prop
+    over all subunits.  `means`, `props` are [L, G]."""
+    n, m = sub.shape
+    L = means.shape[0]
+    pad = sub < 0
+    safe = np.where(pad, 0, sub)
+    mm = means[:, safe]                      # [L, n, m]
+    pp = props[:, safe]
+    mm = np.where(pad[None], np.inf, mm)
+    pp = np.where(pad[None], np.inf, pp)
+    if first_subunit:
+        arg = np.zeros((L, n), dtype=np.int64)
+    else:
+        arg = np.argmin(mm, axis=2)          # first minimal subunit in '_' order
+    ii = np.arange(n)[None, :]
+    gene = safe[ii, arg]                     # [L, n]
+    cl = np.arange(L)[:, None]
+    return (gene.T.astype(np.int32), means[cl, gene].T, props[cl, gene].T, pp.min(axis=2).T)
+
+
+@dataclass
+class ResolvedTriples:
+    inter: np.ndarray        # [T] interaction index
+    src: np.ndarray          # [T] cluster index
+    tgt: np.ndarray          # [T]
+    lig_gene: np.ndarray     # [T] gene column of the resolved ligand subunit
+    rec_gene: np.ndarray     # [T]
+    ligand_means: np.ndarray     # [T] float32
+    receptor_means: np.ndarray   # [T] float32
+    ligand_props: np.ndarray     # [T] float64
+    receptor_props: np.ndarray   # [T] float64
+    keep: np.ndarray         # [T] bool (all True unless return_all_lrs)
+
+
+def resolve_triples(tables: ResourceTables, means: np.ndarray, props: np.ndarray, expr_prop: float,
+                    pair_mask: np.ndarray | None = None, return_all_lrs: bool = False) -> ResolvedTriples:
+    """means float32 [L,G], props float64 [L,G] in the gene-subset column space.
+    pair_mask [L,L] bool restricts (source, target) pairs (groupby_pairs)."""
+    L = means.shape[0]
+    # with return_all_lrs the reference de-duplicates subunit rows BEFORE the min-subunit step
+    # (`_reassemble_complexes.py:52-57`), i.e. every complex is represented by its first subunits
+    lg, lm, lp, lpmin = _resolve_side(tables.lig_sub, means, props, first_subunit=return_all_lrs)
+    rg, rm, rp, rpmin = _resolve_side(tables.rec_sub, means, props, first_subunit=return_all_lrs)
+    n = lg.shape[0]
+    prop_min = np.minimum(lpmin[:, :, None], rpmin[:, None, :])        # [n, s, t]
+    expressed = prop_min >= expr_prop
+    valid = np.ones((n, L, L), dtype=bool) if pair_mask is None else np.broadcast_to(pair_mask[None], (n, L, L))
+    sel = valid if return_all_lrs else (valid & expressed)
+    # row order: source-major, then target, then interaction (the reference concatenates per pair)
+    s_idx, t_idx, i_idx = np.nonzero(np.transpose(sel, (1, 2, 0)))
+    keep = expressed[i_idx, s_idx, t_idx]
+    return ResolvedTriples(
+        inter=i_idx.astype(np.int32), src=s_idx.astype(np.int32), tgt=t_idx.astype(np.int32),
+        lig_gene=lg[i_idx, s_idx], rec_gene=rg[i_idx, t_idx],
+        ligand_means=lm[i_idx, s_idx].astype(np.float32), receptor_means=rm[i_idx, t_idx].astype(np.float32),
+        ligand_props=lp[i_idx, s_idx].astype(np.float64), receptor_props=rp[i_idx, t_idx].astype(np.float64),
+        keep=keep)

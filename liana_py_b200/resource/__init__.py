@@ -1,0 +1,46 @@
+"""Ligand-receptor resources.
+
+Only the `consensus` table is bundled (``consensus.csv``: the `resource == 'consensus'` rows of the
+reference's ``liana/resource/omni_resource.csv`` reduced to gene symbols, derived by
+``scripts/extract_resource.py``).  Other resources are passed as a DataFrame via ``resource=``
+or as ``interactions=[(ligand, receptor), ...]`` - same contract as
+``liana/resource/select_resource.py:57-82``.
+"""
+from __future__ import annotations
+
+import os
+
+import pandas as pd
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def show_resources():
+    return sorted(f[:-4] for f in os.listdir(_DIR) if f.endswith(".csv"))
+
+
+def select_resource(resource_name: str = "consensus") -> pd.DataFrame:
+    """DataFrame with ['ligand', 'receptor'] columns (complexes as 'A_B')."""
+    name = str(resource_name).lower()
+    path = os.path.join(_DIR, f"{name}.csv")
+    if not os.path.exists(path):
+        raise ValueError(f"Resource {name} not found. Please choose from {show_resources()} "
+                         "or pass a DataFrame via `resource=`.")
+    return pd.read_csv(path, index_col=False)
+
+
+def handle_resource(interactions=None, resource=None, resource_name=None, verbose=False) -> pd.DataFrame:
+    """Precedence interactions > resource > resource_name, validation as the reference."""
+    if interactions is not None:
+        if not isinstance(interactions, list) or any(len(item) != 2 for item in interactions):
+            raise ValueError("'interactions' should be a list of tuples in the format [(x1, y1), (x2, y2), ...].")
+        return pd.DataFrame(list(dict.fromkeys(map(tuple, interactions))), columns=["ligand", "receptor"])
+    if resource is not None:
+        if not isinstance(resource, pd.DataFrame) or "ligand" not in resource.columns or "receptor" not in resource.columns:
+            raise ValueError("If 'interactions' is None, 'resource' must be a valid DataFrame "
+                             "with columns 'ligand' and 'receptor'.")
+        out = resource[["ligand", "receptor"]].dropna(subset=["ligand", "receptor"]).drop_duplicates()
+        return out.reset_index(drop=True)
+    if resource_name is None:
+        raise ValueError("If 'interactions' and 'resource' are both None, 'resource_name' must be provided.")
+    return select_resource(resource_name)

@@ -1,0 +1,92 @@
+"""GPU: the drop-in li.mt.cellphonedb / geometric_mean frames against frames produced by the
+reference's own code on the same input (tests/golden/*_cellphonedb.csv.gz, scripts/make_golden.py)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy import sparse
+
+import liana_py_b200 as li
+from liana_py_b200.testing._anndata_lite import AnnDataLite
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KEY = ["source", "target", "ligand_complex", "receptor_complex"]
+
+
+def load_input(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    X = sparse.csr_matrix((z["in_data"], z["in_indices"], z["in_indptr"]), shape=tuple(z["in_shape"]))
+    obs = pd.DataFrame({"cluster": pd.Categorical(z["in_labels"])}, index=[f"cell{i}" for i in range(X.shape[0])])
+    var = pd.DataFrame(index=pd.Index(z["in_var_names"]))
+    return AnnDataLite(X=X, obs=obs, var=var), int(z["n_perms"]), int(z["seed"]), float(z["expr_prop"])
+
+
+def compare(res, gold, mag, spec):
+    assert list(res.columns) == list(gold.columns)
+    a = res.sort_values(KEY).reset_index(drop=True)
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in KEY + ["ligand", "receptor"]:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+    for c in ["ligand_means", "receptor_means", mag]:
+        assert a[c].dtype == np.float32
+        assert np.array_equal(a[c].values, b[c].values.astype(np.float32)), c     # bit-identical float32
+    for c in ["ligand_props", "receptor_props", spec]:
+        assert a[c].dtype == np.float64
+        assert np.array_equal(a[c].values, b[c].values), c
+    # same sort key as the reference: magnitude descending
+    assert np.all(np.diff(res[mag].values) <= 0)
+
+
+@pytest.mark.parametrize("name", ["toy700", "small300", "ragged90"])
+def test_cellphonedb_frame_identical_to_reference(name):
+    adata, P, seed, ep = load_input(name)
+    res = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                            inplace=False, perm_source="reference")
+    gold = pd.read_csv(os.path.join(GOLDEN, f"{name}_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")
+    # inplace contract
+    li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                      perm_source="reference")
+    assert adata.uns["liana_res"].shape == res.shape
+
+
+@pytest.mark.parametrize("name", ["toy700", "small300", "ragged90"])
+def test_geometric_mean_frame_identical_to_reference(name):
+    adata, P, seed, ep = load_input(name)
+    res = li.mt.geometric_mean(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                               inplace=False, perm_source="reference")
+    gold = pd.read_csv(os.path.join(GOLDEN, f"{name}_geometric_mean.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_gmeans", "gmean_pvals")
+
+
+def test_n_perms_none_and_philox_default():
+    adata, P, seed, ep = load_input("small300")
+    res = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=None, inplace=False)
+    assert "cellphone_pvals" not in res.columns and "lr_means" in res.columns
+    ph = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=200, inplace=False)   # Philox, fast
+    ex = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=200, inplace=False, order="exact")
+    a = ph.sort_values(KEY)["cellphone_pvals"].values
+    b = ex.sort_values(KEY)["cellphone_pvals"].values
+    assert np.abs(a - b).max() <= 1.0 / 200 + 1e-12          # same permutations, summation order differs
+    gold = pd.read_csv(os.path.join(GOLDEN, "small300_cellphonedb.csv.gz"), float_precision="round_trip").sort_values(KEY)
+    # a different RNG gives statistically equivalent p-values
+    assert abs(a.mean() - gold["cellphone_pvals"].values.mean()) < 0.05
+
+
+def test_error_conventions():
+    adata, P, seed, ep = load_input("ragged90")
+    with pytest.raises(ValueError, match="not found"):
+        li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, resource_name="nope", n_perms=2)
+    with pytest.raises(ValueError, match="raw"):
+        li.mt.cellphonedb(adata, groupby="cluster", use_raw=True, n_perms=2)
+    with pytest.raises(ValueError, match="layer"):
+        li.mt.cellphonedb(adata, groupby="cluster", use_raw=True, layer="x", n_perms=2)
+    with pytest.raises(AssertionError):
+        li.mt.cellphonedb(adata, groupby="nope", use_raw=False, n_perms=2)
+    bad = adata.copy()
+    bad.var_names = [f"X{i}" for i in range(bad.shape[1])]
+    with pytest.raises(ValueError, match="Too few features"):
+        li.mt.cellphonedb(bad, groupby="cluster", use_raw=False, n_perms=2)
