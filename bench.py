@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the permutation-null hot path (metric of BASELINE.json:
+permutations x LR-triples per second for cellphonedb, n_perms=1000).
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload c3|c2|c4|c5] [--order fast|exact]
+  python bench.py --impl reference ...      # CPU port of the reference on the box's host cores
+
+A "step" = one full pass of the hot path (label shuffles -> per-cluster means -> score ->
+exceedance counts for all P permutations and all T kept triples) over one synthetic input.
+`value` is measured with the inputs resident in HBM; `e2e` goes through the C ABI with HOST
+buffers (H2D of the CSR matrix / labels / triple tables and D2H of the counts inside the timed
+region).  Multi-GPU: one process per GPU (torchrun), permutations sharded by global id, one
+NCCL all-reduce of the uint32 counters per step (strong scaling: total work fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (cells, genes nominal, clusters, description)
+    "c2": (50_000, 20_000, 20, "configs[1]: 50k cells x 20k genes CSR 8%, 20 clusters, consensus, n_perms=1000"),
+    "c3": (500_000, 30_000, 50, "configs[2]: 500k cells x 30k genes CSR 8%, 50 clusters, consensus, n_perms=1000"),
+    "c4": (200_000, 30_000, 40, "configs[3] shape: 200k cells, 40 clusters, n_perms=1000"),
+    "c5": (10_000, 30_000, 30, "configs[4] one sample: 10k cells, 30 clusters, n_perms=1000"),
+    "tiny": (3_000, 2_000, 8, "smoke-size workload for CI: 3k cells, 8 clusters"),
+}
+METRIC = "permutations x LR-triples per second (cellphonedb, n_perms=1000)"
+UNIT = "perm*triples/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) == bit and "None" not in name and "All" not in name:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_workload(name, device, seed_data=1337, seed_labels=1338, use_engine=True):
+    """Synthetic CSR over the resource's genes only (the hot path never sees the background genes;
+    SURVEY.md 8d) + triple tables from the real consensus resource with expr_prop=0.1."""
+    import torch
+    from liana_py_b200 import _engine as E
+    from liana_py_b200.method import _pipeline as PL, _tables
+    from liana_py_b200.resource import select_resource
+    from liana_py_b200.testing._synth import consensus_genes
+    from liana_py_b200.testing._synth_gpu import synthetic_csr_torch
+
+    N, G_nominal, L, desc = WORKLOADS[name]
+    genes = consensus_genes()
+    G = len(genes)
+    indptr, indices, data, labels = synthetic_csr_torch(N, G, L, 0.08, seed_data, seed_labels, device=device)
+    if use_engine:
+        eng = E.Engine(device.index)
+        eng.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        eng.set_matrix_csr(indptr, indices, data, N, G)
+        eng.set_labels(labels, L)
+        means, stored, sizes = eng.observed()
+    else:       # reference arm: no engine anywhere on the path (observed stats from the CPU checker)
+        from scipy import sparse
+        from oracle import c_oracle
+        eng = None
+        Xh = sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(N, G))
+        means, stored, sizes = c_oracle.observed(Xh, labels.cpu().numpy(), L)
+    props = stored / sizes[:, None].astype(np.float64)
+    tables = _tables.build_resource_tables(select_resource("consensus"), genes)
+    assert np.array_equal(tables.entities, genes)
+    tri = _tables.resolve_triples(tables, means, props, 0.1)
+    obs = PL.observed_cpdb(tri.ligand_means, tri.receptor_means)
+    wl = dict(name=name, desc=desc, N=N, G=G, G_nominal=G_nominal, L=L, nnz=int(indices.numel()), T=int(len(obs)),
+              T_max=int(tables.lig_sub.shape[0]) * L * L, indptr=indptr, indices=indices, data=data, labels=labels,
+              tri=tri, obs=obs)
+    return eng, wl
+
+
+def model_bytes(wl, P):
+    """one streaming pass over X_sub per permutation."""
+    per_perm = 8 * wl["nnz"] + 4 * (wl["N"] + 1) + 4 * wl["N"] + 8 * wl["L"] * wl["G"]
+    return per_perm, P * per_perm + 24 * wl["T"]
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from liana_py_b200 import _engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun (--nproc-per-node N) for --gpus N > 1")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    P = args.n_perms
+    order = E.ORDER_FAST if args.order == "fast" else E.ORDER_EXACT
+    eng, wl = build_workload(args.workload, device)
+    T = wl["T"]
+    lo, hi = (P * rank) // world, (P * (rank + 1)) // world
+    tri, obs = wl["tri"], wl["obs"]
+    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
+    counts = torch.zeros(max(T, 1), dtype=torch.int32, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > L2 (126 MB)
+
+    def step_resident():
+        eng.run(hi - lo, seed=1337, perm_offset=lo, order=order, scores=E.SCORE_CPDB, counts_out=(counts, None))
+        if world > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+
+    def timed(fn, steps, warmup, flush_l2=True):
+        for _ in range(warmup):
+            fn()
+        per, launches, kern_ms, kern_n = [], 0, 0.0, 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for _ in range(steps):
+            if flush_l2:
+                flush.fill_(1)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            per.append(e0.elapsed_time(e1))
+            tm = eng.timings()
+            launches += tm["launches"]
+            kern_ms += tm["main_kernel_ms"]
+            kern_n += tm["main_kernel_launches"]
+        t = torch.tensor([sum(per)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, kern_ms, kern_n, eng.timings()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_ms, launches, kern_ms, kern_n, tm = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = P * T / (ms_per_step * 1e-3)
+    result_counts = counts.clone()
+
+    # ---- end to end through the C ABI with host buffers (pinned), same metric ----
+    host = {k: wl[k].cpu().pin_memory() for k in ("indptr", "indices", "data", "labels")}
+    h_idx = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).pin_memory()
+             for a in (tri.lig_gene, tri.rec_gene, tri.src, tri.tgt)]
+    h_obs = torch.from_numpy(np.ascontiguousarray(obs, dtype=np.float32)).pin_memory()
+    h_counts = torch.zeros(max(T, 1), dtype=torch.int32).pin_memory()
+    h2d = sum(int(t.numel() * t.element_size()) for t in list(host.values()) + h_idx + [h_obs])
+    d2h = int(h_counts.numel() * 4)
+
+    def step_e2e():
+        eng.set_matrix_csr(host["indptr"], host["indices"], host["data"], wl["N"], wl["G"])
+        eng.set_labels(host["labels"], wl["L"])
+        eng.set_triples(h_idx[0], h_idx[1], h_idx[2], h_idx[3], h_obs, None)
+        out = eng.run(hi - lo, seed=1337, perm_offset=lo, order=order, scores=E.SCORE_CPDB, counts_out=(counts, None))
+        if world > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        h_counts.copy_(counts, non_blocking=False)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(1):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = P * T / float(e2e_s.item())
+    assert torch.equal(h_counts.to(device), result_counts), "e2e counts differ from the resident run"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak_gbs, peak_src = peaks()
+    per_perm_bytes, total_bytes = model_bytes(wl, P)
+    pb = tm["perm_batch"]
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    perms_per_launch = (hi - lo) / max(tm["main_kernel_launches"], 1)
+    achieved = per_perm_bytes * perms_per_launch / (kern_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{args.workload}_{args.order}")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 sums / f64 compare", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "cells": wl["N"], "genes_nominal": wl["G_nominal"],
+                   "genes_in_resource": wl["G"], "clusters": wl["L"], "nnz": wl["nnz"], "n_perms": P,
+                   "triples_kept": T, "triples_max": wl["T_max"], "expr_prop": 0.1, "order": args.order,
+                   "perm_source": "philox", "parallelism": f"perm-shard x{world}",
+                   "l2": "L2 flushed (256 MB write) before every timed step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(e2e_s.item()) * 1e3},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "stages_ms": {k: tm[k] for k in ("setup_ms", "means_ms", "score_ms", "total_ms")},
+        "roofline": {"bound": "hbm", "kernel": "fast_means_kernel" if args.order == "fast" else "exact_means_kernel",
+                     "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                     "peak_source": peak_src, "traffic": traffic,
+                     "algorithmic_bytes_per_perm": per_perm_bytes, "perms_per_launch": perms_per_launch,
+                     "kernel_ms_per_launch": kern_avg_ms,
+                     "note": "streaming model of SURVEY.md 8(d); the fast kernel reuses L2-resident label tiles "
+                             "across permutations, so achieved may exceed the DRAM peak (see DESIGN.md)"},
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(wl, P, T, n_jobs=1, budget_s=args.cpu_budget)
+        if args.order == "fast" and not args.no_exact:
+            ex_ms, _, ex_kern, ex_n, _ = timed(lambda: eng.run(P, seed=1337, order=E.ORDER_EXACT, scores=E.SCORE_CPDB,
+                                                             counts_out=(counts, None)), 2, 1)
+            ex_ms /= 2
+            line["exact_order_mode"] = {"ms_per_step": ex_ms, "value": P * T / (ex_ms * 1e-3),
+                                        "roofline_frac": per_perm_bytes * P / (ex_kern / 2 * 1e-3) / 1e9 / peak_gbs,
+                                        "note": "bit-identical-to-reference summation order (validation mode)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_inputs(wl):
+    from scipy import sparse
+    X = sparse.csr_matrix((wl["data"].cpu().numpy(), wl["indices"].cpu().numpy(), wl["indptr"].cpu().numpy()),
+                          shape=(wl["N"], wl["G"]))
+    return X, wl["labels"].cpu().numpy()
+
+
+def cpu_baseline(wl, P, T, n_jobs=1, budget_s=20.0):
+    """The reference's hot path (NumPy/SciPy port, oracle/numpy_port.py) on a bounded sample of the
+    same workload: a chunk of permutations, extrapolated linearly in P (every stage is linear in P)."""
+    from oracle import numpy_port
+    X, labels = cpu_inputs(wl)
+    tri, obs = wl["tri"], wl["obs"]
+    # size the sample from one timed permutation
+    t0 = time.perf_counter()
+    numpy_port.get_means_perms(X, labels, wl["L"], 1, 1337, 1)
+    one = time.perf_counter() - t0
+    p_s = int(max(n_jobs, min(P, budget_s / max(one, 1e-3) * max(n_jobs, 1) * (0.6 if n_jobs > 1 else 1.0))))
+    p_s = max(1, (p_s // n_jobs) * n_jobs)
+    t0 = time.perf_counter()
+    numpy_port.run_method_block(X, labels, wl["L"], p_s, 1337, tri.lig_gene, tri.rec_gene, tri.src, tri.tgt,
+                                tri.ligand_means.copy(), tri.receptor_means.copy(), "cellphonedb", n_jobs=n_jobs)
+    dt = time.perf_counter() - t0
+    return {"value": p_s * T / dt, "unit": UNIT, "cores": n_jobs, "kind": "port",
+            "sample": f"{p_s} of {P} permutations of the same workload in {dt:.1f} s "
+                      f"(NumPy/SciPy restatement of _get_means_perms + gather + _cpdb_score, n_jobs={n_jobs}); "
+                      f"extrapolated full run: {dt / p_s * P:.0f} s",
+            "host_cpu_count": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (port) with all host threads it can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    # same synthetic generator as the engine arm (torch CUDA RNG when a GPU is present)
+    device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    _, wl = build_workload(args.workload, device, use_engine=False)
+    P, T = args.n_perms, wl["T"]
+    n_jobs = max(1, min(os.cpu_count() or 1, 16))
+    budget = max(5.0, min(args.cpu_budget, 60.0))
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline(wl, P, T, n_jobs=n_jobs, budget_s=budget)
+        if i >= args.warmup:
+            vals.append(last["value"])
+        if i == 0 and args.warmup + args.steps > 2:
+            budget = max(5.0, budget / 2)
+    value = float(np.mean(vals))
+    last["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": P * T / value * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 sums / f64 compare", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "cells": wl["N"], "genes_in_resource": wl["G"],
+                       "clusters": wl["L"], "nnz": wl["nnz"], "n_perms": P, "triples_kept": T, "expr_prop": 0.1},
+            "cpu_baseline": last,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--order", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--n-perms", type=int, default=1000)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-exact", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        args.warmup = 3        # timing rule: at least 3 warm-up steps
+    os.environ["PYTHONPATH"] = ROOT + os.pathsep + os.environ.get("PYTHONPATH", "")   # joblib workers import oracle/
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,9 +119,10 @@ int lrperm_philox_perms(lrperm_engine *h, int64_t n_cells, int64_t n_perms, int6
                         uint64_t seed, int32_t *out, int out_on_device);
 
 /* Device time (ms, CUDA events on the engine's stream) of the stages of the last lrperm_run:
- * out[0] label/permutation setup, out[1] per-cluster means, out[2] score+count, out[3] total.
- * Also number of kernel launches of the last run in out[4]. */
-int lrperm_last_timings(lrperm_engine *h, float *out5);
+ * out[0] label/permutation setup, out[1] per-cluster means (all kernels), out[2] score+count,
+ * out[3] total, out[4] number of kernel launches, out[5] time of the dominant means kernel alone
+ * (summed over batches), out[6] its launch count, out[7] permutations per batch. */
+int lrperm_last_timings(lrperm_engine *h, float *out8);
 
 /* Tuning knobs of FAST mode (0 = engine default): permutations per batch (multiple of 128), stored
  * entries per gene chunk, and MiB of label slab one cell tile may span (kept L2 resident). */

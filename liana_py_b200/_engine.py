@@ -241,6 +241,7 @@ class Engine:
         return out
 
     def timings(self) -> dict:
-        buf = (C.c_float * 5)()
+        buf = (C.c_float * 8)()
         self._check(self._lib.lrperm_last_timings(self._h, C.cast(buf, C.c_void_p)))
-        return {"setup_ms": buf[0], "means_ms": buf[1], "score_ms": buf[2], "total_ms": buf[3], "launches": int(buf[4])}
+        return {"setup_ms": buf[0], "means_ms": buf[1], "score_ms": buf[2], "total_ms": buf[3], "launches": int(buf[4]),
+                "main_kernel_ms": buf[5], "main_kernel_launches": int(buf[6]), "perm_batch": int(buf[7])}

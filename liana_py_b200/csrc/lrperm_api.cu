@@ -82,7 +82,8 @@ struct lrperm_engine {
     DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out;
 
     // timings of the last run
-    float t_setup = 0, t_means = 0, t_score = 0, t_total = 0;
+    float t_setup = 0, t_means = 0, t_score = 0, t_total = 0, t_main = 0;
+    int32_t n_main_launches = 0, last_pb = 0;
     int64_t launches = 0;
     std::vector<cudaEvent_t> events;
 
@@ -598,9 +599,10 @@ int lrperm_philox_perms(lrperm_engine* h, int64_t n_cells, int64_t n_perms, int6
     return LRPERM_OK;
 }
 
-int lrperm_last_timings(lrperm_engine* h, float* out5) {
-    if (!h || !out5) return LRPERM_ERR_INVALID;
-    out5[0] = h->t_setup; out5[1] = h->t_means; out5[2] = h->t_score; out5[3] = h->t_total; out5[4] = (float)h->launches;
+int lrperm_last_timings(lrperm_engine* h, float* out8) {
+    if (!h || !out8) return LRPERM_ERR_INVALID;
+    out8[0] = h->t_setup; out8[1] = h->t_means; out8[2] = h->t_score; out8[3] = h->t_total; out8[4] = (float)h->launches;
+    out8[5] = h->t_main; out8[6] = (float)h->n_main_launches; out8[7] = (float)h->last_pb;
     return LRPERM_OK;
 }
 
@@ -648,6 +650,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     }
     if (n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((n_perms + 127) / 128) * 128);
     const int32_t PP = PB;
+    h->last_pb = PB;
     CK(h->cube.ensure(sizeof(float) * (size_t)G * L * PP));
     if (order_mode == LRPERM_ORDER_FAST) {
         CK(h->slab.ensure((size_t)N * PB));
@@ -657,7 +660,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     if (scores & LRPERM_SCORE_GMEAN) CK(cudaMemsetAsync(h->counts_g.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
 
     const int64_t n_batches = (n_perms + PB - 1) / PB;
-    const size_t n_events = (size_t)n_batches * 4 + 2;
+    const size_t n_events = (size_t)n_batches * 5 + 2;
     while (h->events.size() < n_events) {
         cudaEvent_t ev;
         CK(cudaEventCreate(&ev));
@@ -704,11 +707,13 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
             else if (Q == 2) rc = launch_fast_q<2>(h, PB, h->partials.as<float>());
             else rc = launch_fast_q<1>(h, PB, h->partials.as<float>());
             if (rc) return rc;
+            CK(cudaEventRecord(h->events[evi++], h->stream));   // main kernel done
             fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, h->stream>>>(
                 h->partials.as<float>(), h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
             CK_LAUNCH();
         } else {
             if ((rc = launch_exact(h, ps, pb, h->cube.as<float>(), PP))) return rc;
+            CK(cudaEventRecord(h->events[evi++], h->stream));   // main kernel done
         }
         CK(cudaEventRecord(h->events[evi++], h->stream));
         // ---- stage 3: score + compare + count ----
@@ -736,13 +741,15 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     if (scores & LRPERM_SCORE_GMEAN) if ((rc = download(h, counts_gmean, h->counts_g.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
     CK(cudaStreamSynchronize(h->stream));
 
-    h->t_setup = h->t_means = h->t_score = 0.f;
+    h->t_setup = h->t_means = h->t_score = h->t_main = 0.f;
+    h->n_main_launches = (int32_t)n_batches;
     for (int64_t b = 0; b < n_batches; ++b) {
         float ms;
-        const size_t base = 1 + (size_t)b * 4;
+        const size_t base = 1 + (size_t)b * 5;
         CK(cudaEventElapsedTime(&ms, h->events[base], h->events[base + 1])); h->t_setup += ms;
-        CK(cudaEventElapsedTime(&ms, h->events[base + 1], h->events[base + 2])); h->t_means += ms;
-        CK(cudaEventElapsedTime(&ms, h->events[base + 2], h->events[base + 3])); h->t_score += ms;
+        CK(cudaEventElapsedTime(&ms, h->events[base + 1], h->events[base + 2])); h->t_main += ms;
+        CK(cudaEventElapsedTime(&ms, h->events[base + 1], h->events[base + 3])); h->t_means += ms;
+        CK(cudaEventElapsedTime(&ms, h->events[base + 3], h->events[base + 4])); h->t_score += ms;
     }
     CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[evi - 1]));
     return LRPERM_OK;
