@@ -214,8 +214,8 @@ def run_gpu(args):
             dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         h_counts.copy_(counts, non_blocking=False)
 
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(1):
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(max(3, args.warmup)):
         step_e2e()
     if world > 1:
         dist.barrier()

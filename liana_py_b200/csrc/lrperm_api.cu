@@ -79,7 +79,7 @@ struct lrperm_engine {
     DevBuf chunks, gene_slot_ptr;
 
     // work buffers
-    DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out;
+    DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out, small_a, small_b;
 
     // timings of the last run
     float t_setup = 0, t_means = 0, t_score = 0, t_total = 0, t_main = 0;
@@ -163,7 +163,7 @@ int build_csc(lrperm_engine* h) {
     CK(h->tmp_c.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nnz, 1)));   // sorted keys
     CK(h->tmp_d.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));    // sorted source index
     CK(h->stage_out.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));  // row ids
-    DevBuf col_count;
+    DevBuf& col_count = h->small_a;
     CK(col_count.ensure(sizeof(int32_t) * (size_t)(G + 1)));
     CK(cudaMemsetAsync(col_count.p, 0, sizeof(int32_t) * (size_t)(G + 1), h->stream));
     CK(h->csc_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
@@ -194,10 +194,8 @@ int build_csc(lrperm_engine* h) {
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }
-    col_count.release();
-    // the sort scratch is large (several x nnz); give it back
-    h->tmp_a.release(); h->tmp_b.release(); h->tmp_c.release(); h->tmp_d.release();
-    h->stage_out.release(); h->sort_tmp.release();
+    // scratch buffers stay allocated: repeated set_matrix / run cycles (by_sample, e2e serving) would
+    // otherwise pay cudaMalloc/cudaFree (device-synchronising) on every call
     h->csc_ready = true;
     h->chunk_table_nnz = -1;
     return LRPERM_OK;
@@ -211,7 +209,7 @@ int build_chunks(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
     const int32_t n_tiles = (int32_t)std::max<int64_t>(1, (h->N + tile_cells - 1) / tile_cells);
     std::vector<int32_t> bounds((size_t)G * (n_tiles + 1));
     {
-        DevBuf d_ptr, d_bounds;
+        DevBuf &d_ptr = h->small_a, &d_bounds = h->small_b;
         CK(d_ptr.ensure(sizeof(int32_t) * ((size_t)G + 1)));
         CK(d_bounds.ensure(sizeof(int32_t) * bounds.size()));
         CK(cudaMemcpyAsync(d_ptr.p, h->h_csc_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
@@ -220,7 +218,6 @@ int build_chunks(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
         CK_LAUNCH();
         CK(cudaMemcpyAsync(bounds.data(), d_bounds.p, sizeof(int32_t) * bounds.size(), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        d_ptr.release(); d_bounds.release();
     }
     struct Tagged { FastChunk c; int32_t tile; };
     std::vector<Tagged> tagged;
@@ -369,7 +366,7 @@ void lrperm_destroy(lrperm_engine* h) {
     for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->labels32, &h->labels8, &h->order,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
                       &h->chunks, &h->gene_slot_ptr, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
-                      &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out})
+                      &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -446,7 +443,6 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     }
     int rc = check_err_flag(h, "lrperm_set_matrix_csr");
     if (rc) return rc;
-    h->tmp_a.release(); h->tmp_b.release(); h->tmp_c.release();
     h->have_matrix = true;
     return LRPERM_OK;
 }
@@ -535,7 +531,6 @@ int lrperm_set_triples(lrperm_engine* h, int64_t n_triples, const int32_t* ligan
     }
     rc = check_err_flag(h, "lrperm_set_triples");
     if (rc) return rc;
-    h->tmp_a.release();
     h->T = n_triples;
     h->have_thr_c = obs_cpdb != nullptr;
     h->have_thr_g = obs_gmean != nullptr;

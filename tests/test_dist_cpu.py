@@ -1,0 +1,82 @@
+"""CPU (gloo, world_size 2): the host-side multi-rank logic - permutation sharding by global id,
+the integer all-reduce of exceedance counts, sample sharding and frame gathering for by_sample.
+The per-rank compute is stood in by the CPU oracle (the engine itself needs a GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from liana_py_b200.method._dist import DistContext
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from conftest import load_golden
+        from oracle import c_oracle, numpy_port
+        ctx = DistContext.from_torch()
+        assert (ctx.rank, ctx.world_size) == (rank, world)
+        g = load_golden("small300")
+        P = int(g["n_perms"])
+        lo, hi = ctx.perm_range(P)
+        cube = c_oracle.cube(g["X"], g["labels"], g["L"], g["perm_idx"][lo:hi])
+        idx = (g["ligand_idx"], g["receptor_idx"], g["source_idx"], g["target_idx"])
+        obs = numpy_port.cpdb_observed(g["ligand_means"].copy(), g["receptor_means"].copy())
+        local = numpy_port.counts_from_cube(cube, *idx, obs, "cellphonedb").astype(np.uint32)
+        total = ctx.all_reduce_sum_u32(local)
+        assert np.array_equal(total / P, g["cpdb_pvals"])          # identical to the single-process reference
+        # by_sample: whole samples per rank, gathered as objects
+        sizes = [50, 400, 30, 220, 90, 10, 300]
+        mine = ctx.sample_shard(sizes)
+        parts = ctx.all_gather_objects({i: sizes[i] * 2 for i in mine})
+        merged = {}
+        for p in parts:
+            assert not (set(p) & set(merged))
+            merged.update(p)
+        assert merged == {i: s * 2 for i, s in enumerate(sizes)}
+        loads = [sum(sizes[i] for i in q) for q in (ctx.all_gather_objects(mine))]
+        assert max(loads) - min(loads) <= max(sizes)
+        t = torch.full((4,), rank + 1, dtype=torch.int32)
+        ctx.all_reduce_sum_(t)
+        assert t.tolist() == [sum(range(1, world + 1))] * 4
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo(tmp_path):
+    world = 2
+    here = os.path.dirname(os.path.abspath(__file__))
+    os.environ["PYTHONPATH"] = here + os.pathsep + os.path.dirname(here) + os.pathsep + os.environ.get("PYTHONPATH", "")
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_perm_ranges_partition():
+    for P in (1, 7, 1000, 1001):
+        for W in (1, 2, 3, 8):
+            seen = []
+            for r in range(W):
+                lo, hi = DistContext(r, W).perm_range(P)
+                seen.extend(range(lo, hi))
+            assert seen == list(range(P))
+
+
+def test_single_rank_context_is_identity():
+    ctx = DistContext.from_torch()
+    assert ctx.world_size == 1
+    a = np.arange(5, dtype=np.uint32)
+    assert ctx.all_reduce_sum_u32(a) is a
+    assert ctx.sample_shard([3, 1, 2]) == [0, 1, 2]

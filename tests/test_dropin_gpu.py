@@ -90,3 +90,27 @@ def test_error_conventions():
     bad.var_names = [f"X{i}" for i in range(bad.shape[1])]
     with pytest.raises(ValueError, match="Too few features"):
         li.mt.cellphonedb(bad, groupby="cluster", use_raw=False, n_perms=2)
+
+
+def test_by_sample_matches_per_sample_calls():
+    adata, P, seed, ep = load_input("toy700")
+    rng = np.random.default_rng(0)
+    adata.obs["sample"] = rng.choice(["A", "B", "C"], size=adata.shape[0])     # not categorical yet
+    kw = dict(groupby="cluster", use_raw=False, n_perms=20, seed=seed, expr_prop=ep, perm_source="reference")
+    res = li.mt.cellphonedb.by_sample(adata, "sample", inplace=False, **kw)
+    assert res.columns[0] == "sample" and list(res.columns[1:]) == [
+        "ligand", "ligand_complex", "ligand_means", "ligand_props", "receptor", "receptor_complex",
+        "receptor_means", "receptor_props", "source", "target", "lr_means", "cellphone_pvals"]
+    assert list(dict.fromkeys(res["sample"])) == ["A", "B", "C"]
+    for s in ["A", "B", "C"]:
+        sub = adata[np.asarray(adata.obs["sample"] == s)].copy()
+        one = li.mt.cellphonedb(sub, inplace=False, **kw)
+        got = res[res["sample"] == s].drop(columns="sample")
+        a = got.sort_values(KEY).reset_index(drop=True)
+        b = one.sort_values(KEY).reset_index(drop=True)
+        assert np.array_equal(a["lr_means"].values, b["lr_means"].values)
+        assert np.array_equal(a["cellphone_pvals"].values, b["cellphone_pvals"].values)
+    with pytest.raises(ValueError, match="was not found"):
+        li.mt.cellphonedb.by_sample(adata, "nope", **kw)
+    li.mt.cellphonedb.by_sample(adata, "sample", key_added="by_s", **kw)
+    assert adata.uns["by_s"].shape == res.shape
