@@ -256,22 +256,52 @@ int build_chunks(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
     return LRPERM_OK;
 }
 
-int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube, int32_t PP) {
+template <int W>
+int launch_exact_w(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube, int32_t PP, size_t smem) {
     const int32_t G = (int32_t)h->G, L = h->L;
-    const int Gpad = (G + 31) & ~31;
-    const size_t smem = (size_t)kExactWarps * Gpad * sizeof(float);
-    if (smem > h->smem_optin)
-        return h->fail(LRPERM_ERR_UNSUPPORTED, "EXACT mode needs %zu B shared memory per CTA (G=%d); limit %zu", smem, G, h->smem_optin);
-    CK(cudaFuncSetAttribute(exact_means_kernel<kExactWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(exact_means_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t items = (int64_t)pb * L;
-    const int64_t grid = (items + kExactWarps - 1) / kExactWarps;
+    const int64_t grid = (items + W - 1) / W;
     if (grid > 0) {
-        exact_means_kernel<kExactWarps><<<(unsigned)grid, kExactWarps * 32, smem, h->stream>>>(
+        exact_means_kernel<W><<<(unsigned)grid, W * 32, smem, h->stream>>>(
             h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), h->order.as<int32_t>(), h->cl_start.as<int32_t>(),
             h->inv_n.as<float>(), ps, (int32_t)h->N, G, L, pb, cube, PP);
         CK_LAUNCH();
     }
     return LRPERM_OK;
+}
+
+int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube, int32_t PP) {
+    const int32_t G = (int32_t)h->G;
+    const int Gpad = (G + 31) & ~31;
+    const size_t per_warp = (size_t)Gpad * sizeof(float);
+    // warps per CTA: maximise resident warps per SM under the shared-memory budget
+    // (1 KB per CTA is reserved by the driver) and the 2048-thread limit
+    const size_t sm_budget = 227 * 1024;
+    int best_w = 0, best_res = 0;
+    for (int w : {16, 12, 10, 9, 8, 7, 6, 4, 2, 1}) {
+        const size_t cta = per_warp * w + 1024;
+        if (per_warp * w > h->smem_optin) continue;
+        int ctas = (int)std::min<size_t>(sm_budget / cta, 32);
+        ctas = std::min(ctas, 2048 / (w * 32));
+        const int res = std::min(ctas * w, 48);       // ~60 registers/thread caps residency near 32-40 warps
+        if (res > best_res) { best_res = res; best_w = w; }
+    }
+    if (best_w == 0)
+        return h->fail(LRPERM_ERR_UNSUPPORTED, "EXACT mode needs %zu B shared memory per warp (G=%d); limit %zu", per_warp, G, h->smem_optin);
+    const size_t smem = per_warp * best_w;
+    switch (best_w) {
+        case 16: return launch_exact_w<16>(h, ps, pb, cube, PP, smem);
+        case 12: return launch_exact_w<12>(h, ps, pb, cube, PP, smem);
+        case 10: return launch_exact_w<10>(h, ps, pb, cube, PP, smem);
+        case 9: return launch_exact_w<9>(h, ps, pb, cube, PP, smem);
+        case 8: return launch_exact_w<8>(h, ps, pb, cube, PP, smem);
+        case 7: return launch_exact_w<7>(h, ps, pb, cube, PP, smem);
+        case 6: return launch_exact_w<6>(h, ps, pb, cube, PP, smem);
+        case 4: return launch_exact_w<4>(h, ps, pb, cube, PP, smem);
+        case 2: return launch_exact_w<2>(h, ps, pb, cube, PP, smem);
+        default: return launch_exact_w<1>(h, ps, pb, cube, PP, smem);
+    }
 }
 
 template <int Q>
@@ -437,8 +467,8 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
             d_idx = h->tmp_b.as<int32_t>();
             d_val = h->tmp_c.as<float>();
         }
-        pack_csr_kernel<<<grid_for(nnz, 256), 256, 0, h->stream>>>(d_idx, d_val, nnz, (int32_t)n_genes,
-                                                                   h->csr_pairs.as<int2>(), h->err_flag.as<int>());
+        pack_csr_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+            h->indptr.as<int32_t>(), d_idx, d_val, (int32_t)n_cells, (int32_t)n_genes, h->csr_pairs.as<int2>(), h->err_flag.as<int>());
         CK_LAUNCH();
     }
     int rc = check_err_flag(h, "lrperm_set_matrix_csr");

@@ -30,14 +30,68 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // ------------------------------------------------------------------------------------------
 // CSR packing + validation
 // ------------------------------------------------------------------------------------------
-__global__ void pack_csr_kernel(const int32_t* __restrict__ indices, const float* __restrict__ data,
-                                int64_t nnz, int32_t G, int2* __restrict__ pairs, int* __restrict__ err) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nnz; i += stride) {
-        int32_t c = indices[i];
-        if (c < 0 || c >= G) { atomicOr(err, 1); c = 0; }
-        pairs[i] = make_int2(c, __float_as_int(data[i]));
+// One warp per row.  Besides packing {column, value}, the row's entries are re-ordered so that every
+// group of 32 consecutive entries (one warp-wide accumulate in exact_means_kernel) spreads over the
+// shared-memory banks (column & 31) as evenly as possible: entries are ranked in bank-sorted order
+// and dealt round-robin over the row's 32-entry groups, so a bank with c entries appears at most
+// ceil(c / groups) (+1) times per group instead of ~3.4 times for random columns.  The order of the
+// stored entries inside a row is irrelevant for the arithmetic (one entry per column and row).
+__global__ void pack_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                const float* __restrict__ data, int32_t N, int32_t G,
+                                int2* __restrict__ pairs, int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int r = warp; r < N; r += nwarps) {
+        const int s = indptr[r], e = indptr[r + 1];
+        const int n = e - s;
+        if (n <= 0) continue;
+        // pass 1: entries per bank (lane b holds the count of bank b)
+        int cnt = 0;
+        for (int o = s; o < e; o += 32) {
+            const bool valid = o + lane < e;
+            int c = valid ? indices[o + lane] : 0;
+            if (valid && (c < 0 || c >= G)) { atomicOr(err, 1); c = 0; }
+            const int bank = c & 31;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const unsigned m = __ballot_sync(0xffffffffu, valid && bank == b);
+                if (lane == b) cnt += __popc(m);
+            }
+        }
+        // exclusive prefix over banks -> first bank-sorted index of every bank
+        int start = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, start, d);
+            if (lane >= d) start += t;
+        }
+        start -= cnt;
+        const int nfull = n >> 5, rem = n & 31;
+        const int ngroups = nfull + (rem ? 1 : 0);
+        const int phase1 = rem * ngroups;       // entries dealt while the partial (last) group fills up
+        // pass 2: place
+        int run = 0;                            // entries of bank `lane` seen in earlier chunks
+        for (int o = s; o < e; o += 32) {
+            const bool valid = o + lane < e;
+            int c = valid ? indices[o + lane] : 0;
+            if (c < 0 || c >= G) c = 0;
+            const float v = valid ? data[o + lane] : 0.0f;
+            const int bank = c & 31;
+            const unsigned peers = __match_any_sync(0xffffffffu, valid ? bank : (32 + lane));
+            const int rank = __shfl_sync(0xffffffffu, run, bank) + __popc(peers & lt_mask);
+            const int i = __shfl_sync(0xffffffffu, start, bank) + rank;      // bank-sorted index
+            int grp, col;
+            if (i < phase1) { grp = i % ngroups; col = i / ngroups; }
+            else { const int j = i - phase1; grp = j % nfull; col = rem + j / nfull; }
+            if (valid) pairs[s + grp * 32 + col] = make_int2(c, __float_as_int(v));
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const unsigned m = __ballot_sync(0xffffffffu, valid && bank == b);
+                if (lane == b) run += __popc(m);
+            }
+        }
     }
 }
 
@@ -130,6 +184,12 @@ __device__ __forceinline__ int32_t perm_lookup(const PermSource& ps, int p_local
     return ((const int32_t*)ps.idx)[(int64_t)p_local * N + j];
 }
 
+__device__ __forceinline__ int2 ld_stream_int2(const int2* p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // EXACT mode: one warp per (permutation, cluster).  The warp walks the cluster's positions in
 // ascending order (the reference's order), fetches the CSR row of the cell the permutation put
@@ -174,38 +234,57 @@ exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ 
         }
     };
 
+    // Row pipeline: the first U*32 stored entries of row r+1 are loaded into registers while row r is
+    // being accumulated, so every warp keeps ~1.3 KB of gathered row data in flight (HBM latency).
+    constexpr int U = 8;
+    auto prefetch = [&](int s, int e, int2 (&q)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int o = s + lane + 32 * u;
+            q[u] = (o < e) ? ld_stream_int2(pairs + o) : make_int2(-1, 0);
+        }
+    };
+    auto apply = [&](int s, int e, const int2 (&q)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (q[u].x >= 0) acc[q[u].x] = __fadd_rn(acc[q[u].x], __fmul_rn(__int_as_float(q[u].y), inv));
+        for (int o = s + lane + 32 * U; o < e; o += 128) {     // rows longer than U*32 entries
+            int2 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = (o + 32 * u < e) ? ld_stream_int2(pairs + o + 32 * u) : make_int2(-1, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t[u].x >= 0) acc[t[u].x] = __fadd_rn(acc[t[u].x], __fmul_rn(__int_as_float(t[u].y), inv));
+        }
+        __syncwarp();   // the next row may touch the same columns from other lanes
+    };
+
     int rs_n, re_n;
     fetch_meta(k_begin + lane, rs_n, re_n);
+    int2 qa[U], qb[U];      // ping-pong row buffers (no register moves between rows)
+    int sa = __shfl_sync(0xffffffffu, rs_n, 0), ea = __shfl_sync(0xffffffffu, re_n, 0), sb, eb;
+    prefetch(sa, ea, qa);
     for (int k0 = k_begin; k0 < k_end; k0 += 32) {
         const int rs_c = rs_n, re_c = re_n;
-        fetch_meta(k0 + 32 + lane, rs_n, re_n);   // prefetch the next 32 rows' extents
+        fetch_meta(k0 + 32 + lane, rs_n, re_n);   // extents of the next 32 rows ((0,0) past the end)
         const int nrows = min(32, k_end - k0);
-        for (int r = 0; r < nrows; ++r) {
-            const int s = __shfl_sync(0xffffffffu, rs_c, r);
-            const int e = __shfl_sync(0xffffffffu, re_c, r);
-            int o = s + lane;
-            // four 32-entry chunks in flight per row
-            for (; o + 96 < e; o += 128) {
-                const int2 q0 = pairs[o], q1 = pairs[o + 32], q2 = pairs[o + 64], q3 = pairs[o + 96];
-                acc[q0.x] = __fadd_rn(acc[q0.x], __fmul_rn(__int_as_float(q0.y), inv));
-                acc[q1.x] = __fadd_rn(acc[q1.x], __fmul_rn(__int_as_float(q1.y), inv));
-                acc[q2.x] = __fadd_rn(acc[q2.x], __fmul_rn(__int_as_float(q2.y), inv));
-                acc[q3.x] = __fadd_rn(acc[q3.x], __fmul_rn(__int_as_float(q3.y), inv));
+        for (int r = 0; r < nrows; r += 2) {
+            // row r is in qa; fetch row r+1 into qb, then row r+2 into qa
+            sb = __shfl_sync(0xffffffffu, rs_c, (r + 1) & 31);
+            eb = __shfl_sync(0xffffffffu, re_c, (r + 1) & 31);
+            if (r + 1 >= nrows) { sb = 0; eb = 0; }          // nrows is odd only in the last block
+            prefetch(sb, eb, qb);
+            apply(sa, ea, qa);
+            if (r + 2 < 32) {
+                sa = __shfl_sync(0xffffffffu, rs_c, (r + 2) & 31);
+                ea = __shfl_sync(0xffffffffu, re_c, (r + 2) & 31);
+                if (r + 2 >= nrows) { sa = 0; ea = 0; }
+            } else {
+                sa = __shfl_sync(0xffffffffu, rs_n, 0);
+                ea = __shfl_sync(0xffffffffu, re_n, 0);
             }
-            {
-                // tail: up to four predicated chunks, loads issued together
-                int2 q[4];
-                bool v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = (o + 32 * u) < e;
-                    q[u] = v[u] ? pairs[o + 32 * u] : make_int2(0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (v[u]) acc[q[u].x] = __fadd_rn(acc[q[u].x], __fmul_rn(__int_as_float(q[u].y), inv));
-            }
-            __syncwarp();   // next row may touch the same columns from other lanes
+            prefetch(sa, ea, qa);
+            apply(sb, eb, qb);
         }
     }
     // flush: cube[g][c][p]
@@ -310,13 +389,13 @@ fast_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restric
     };
     LW lw_cur[B], lw_nxt[B];
     int2 pr_cur = load_pair(ch.begin);
+    int2 pr_nxt = load_pair(ch.begin + B);          // entry pairs run two blocks ahead of the updates
 #pragma unroll
     for (int u = 0; u < B; ++u) lw_cur[u] = __ldg(slab_w + (int64_t)__shfl_sync(0xffffffffu, pr_cur.x, u) * row_words);
     for (int k = ch.begin; k < ch.end; k += B) {
         const bool more = k + B < ch.end;
-        int2 pr_nxt = make_int2(first_cell, 0);
+        const int2 pr_nxt2 = load_pair(k + 2 * B);
         if (more) {
-            pr_nxt = load_pair(k + B);
 #pragma unroll
             for (int u = 0; u < B; ++u) lw_nxt[u] = __ldg(slab_w + (int64_t)__shfl_sync(0xffffffffu, pr_nxt.x, u) * row_words);
         }
@@ -328,8 +407,9 @@ fast_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restric
         if (more) {
 #pragma unroll
             for (int u = 0; u < B; ++u) lw_cur[u] = lw_nxt[u];
-            pr_cur = pr_nxt;
         }
+        pr_cur = pr_nxt;
+        pr_nxt = pr_nxt2;
     }
     __syncwarp();
     // partial sums out: partials[(slot*L + c)*PB + group*32*Q + lane*Q + q]
