@@ -128,6 +128,11 @@ int lrperm_last_timings(lrperm_engine *h, float *out8);
  * entries per gene chunk, and MiB of label slab one cell tile may span (kept L2 resident). */
 int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_chunk_nnz, int32_t fast_tile_mib);
 
+/* Named engine options (experiments / A-B measurements; defaults are the production settings):
+ *   "fast_variant"  2 (default) = fast2_means_kernel, 1 = fast_means_kernel (round-1 first version)
+ *   "fast_q"        permutations per lane in FAST mode: 0 = auto, 2, 4 or 8                      */
+int lrperm_set_option(lrperm_engine *h, const char *name, int64_t value);
+
 #ifdef __cplusplus
 }
 #endif

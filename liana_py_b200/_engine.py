@@ -23,7 +23,7 @@ GMEAN_PRODUCT, GMEAN_LITERAL = 0, 1
 ABI_SYMBOLS = (
     "lrperm_abi_version", "lrperm_last_error", "lrperm_create", "lrperm_destroy", "lrperm_set_stream",
     "lrperm_set_matrix_csr", "lrperm_set_labels", "lrperm_set_triples", "lrperm_observed", "lrperm_run",
-    "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning",
+    "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
 )
 
 _lib = None
@@ -52,6 +52,7 @@ def load_library():
     lib.lrperm_destroy.restype = None
     lib.lrperm_set_stream.argtypes = [vp, vp]
     lib.lrperm_set_tuning.argtypes = [vp, i32, i32, i32]
+    lib.lrperm_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.lrperm_set_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int]
     lib.lrperm_set_labels.argtypes = [vp, vp, i32, C.c_int]
     lib.lrperm_set_triples.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_int]
@@ -120,6 +121,9 @@ class Engine:
 
     def set_stream(self, cuda_stream_ptr: Optional[int]):
         self._check(self._lib.lrperm_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.lrperm_set_option(self._h, name.encode(), int(value)))
 
     def set_tuning(self, fast_perm_batch: int = 0, fast_chunk_nnz: int = 0, fast_tile_mib: int = 0):
         self._check(self._lib.lrperm_set_tuning(self._h, int(fast_perm_batch), int(fast_chunk_nnz), int(fast_tile_mib)))

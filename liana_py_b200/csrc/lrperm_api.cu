@@ -63,7 +63,8 @@ struct lrperm_engine {
     // labels
     int32_t L = 0;
     bool have_labels = false;
-    DevBuf labels32, labels8, order, cl_start, inv_n;
+    DevBuf labels32, labels8, labels8s, order, cl_start, inv_n;
+    int32_t labels8s_scale = 0;          // scale the labels8s table currently holds (0 = stale)
     std::vector<int32_t> h_cl_start;
 
     // triples
@@ -75,6 +76,8 @@ struct lrperm_engine {
     int32_t fast_perm_batch = 0, fast_chunk_nnz = 0;   // 0 = auto
     int32_t chunk_table_nnz = -1, chunk_table_tile = -1;   // parameters the chunk tables were built for
     int32_t fast_tile_bytes = 0;                        // label-slab bytes one cell tile may span (0 = auto)
+    int32_t fast_variant = 2;                           // 1 = fast_means_kernel, 2 = fast2_means_kernel
+    int32_t fast_q = 0;                                 // permutations per lane (0 = auto)
     int32_t n_chunks = 0, n_slots = 0;
     DevBuf chunks, gene_slot_ptr;
 
@@ -320,6 +323,38 @@ int launch_fast_q(lrperm_engine* h, int32_t PB, float* partials) {
     return LRPERM_OK;
 }
 
+template <int Q, int B>
+int launch_fast2_q(lrperm_engine* h, int32_t PB, float* partials) {
+    const int32_t L = h->L;
+    const size_t smem = (size_t)L * Q * 128 + 16 * B;
+    CK(cudaFuncSetAttribute(fast2_means_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int32_t groups = PB / (32 * Q);
+    const int64_t grid = (int64_t)h->n_chunks * groups;
+    if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: too many chunks (%lld CTAs)", (long long)grid);
+    if (grid > 0) {
+        fast2_means_kernel<Q, B><<<(unsigned)grid, 32, smem, h->stream>>>(
+            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, h->slab.as<uint8_t>(), PB, L, groups, partials);
+        CK_LAUNCH();
+    }
+    return LRPERM_OK;
+}
+
+// v2 kernel: permutations per lane.  The slab byte is label*Q/2 (must fit 8 bits) and the bins take
+// L*Q*128 B of shared memory per warp; more, smaller CTAs hide the LDS->FADD->STS chain better.
+int pick_q2(const lrperm_engine* h) {
+    const size_t budget = h->smem_optin;
+    if (h->fast_q) {
+        const int q = h->fast_q;
+        if ((q == 2 || q == 4 || q == 8) && (h->L - 1) * q / 2 <= 255 && (size_t)h->L * q * 128 + 512 <= budget) return q;
+        return 0;
+    }
+    for (int q : {4, 2}) {
+        if ((h->L - 1) * q / 2 > 255) continue;
+        if ((size_t)h->L * q * 128 + 512 <= budget) return q;
+    }
+    return 0;
+}
+
 int pick_q(const lrperm_engine* h) {
     // keep >= 1 CTA of kFastWarps warps resident: bins = warps * L * Q * 128 B
     const size_t budget = h->smem_optin;
@@ -393,7 +428,7 @@ void lrperm_destroy(lrperm_engine* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->labels32, &h->labels8, &h->order,
+    for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->labels32, &h->labels8, &h->labels8s, &h->order,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
                       &h->chunks, &h->gene_slot_ptr, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b})
@@ -416,6 +451,21 @@ int lrperm_set_tuning(lrperm_engine* h, int32_t fast_perm_batch, int32_t fast_ch
     h->fast_perm_batch = fast_perm_batch;
     h->fast_chunk_nnz = fast_chunk_nnz;
     h->fast_tile_bytes = fast_tile_mib << 20;
+    return LRPERM_OK;
+}
+
+int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
+    if (!h || !name) return LRPERM_ERR_INVALID;
+    const std::string key(name);
+    if (key == "fast_variant") {
+        if (value != 1 && value != 2) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_variant must be 1 or 2");
+        h->fast_variant = (int32_t)value;
+    } else if (key == "fast_q") {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_q must be 0, 1, 2, 4 or 8");
+        h->fast_q = (int32_t)value;
+    } else {
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: unknown option '%s'", name);
+    }
     return LRPERM_OK;
 }
 
@@ -511,6 +561,7 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
     for (int64_t j = 0; j < N; ++j) lab8[(size_t)j] = (uint8_t)(lab[(size_t)j] & 0xff);
 
     h->L = n_clusters;
+    h->labels8s_scale = 0;
     h->h_cl_start = start;
     int rc;
     if ((rc = upload(h, h->labels32, lab.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
@@ -658,11 +709,13 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     int Q = 0;
     if (order_mode == LRPERM_ORDER_FAST) {
         if (L > 255) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode supports at most 255 clusters (got %d); use EXACT", L);
-        Q = pick_q(h);
+        Q = h->fast_variant == 2 ? pick_q2(h) : pick_q(h);
         if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: %d clusters do not fit the shared-memory bins", L);
         if ((rc = build_csc(h))) return rc;
         PB = h->fast_perm_batch ? h->fast_perm_batch : 512;
-        if (n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((n_perms + 127) / 128) * 128);
+        const int32_t gran = std::max(128, 32 * Q);        // a warp covers 32*Q permutations
+        if (n_perms < PB) PB = (int32_t)std::max<int64_t>(gran, ((n_perms + gran - 1) / gran) * gran);
+        PB = ((PB + gran - 1) / gran) * gran;
         // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
         const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (16LL << 20);
         const int32_t tile_cells = (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / PB, 1024), std::max<int64_t>(N, 1));
@@ -673,7 +726,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         PB = 512;
         while (PB > 128 && (int64_t)PB * L * G * 4 > (256LL << 20)) PB >>= 1;
     }
-    if (n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((n_perms + 127) / 128) * 128);
+    if (order_mode != LRPERM_ORDER_FAST && n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((n_perms + 127) / 128) * 128);
     const int32_t PP = PB;
     h->last_pb = PB;
     CK(h->cube.ensure(sizeof(float) * (size_t)G * L * PP));
@@ -684,6 +737,19 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     if (scores & LRPERM_SCORE_CPDB) CK(cudaMemsetAsync(h->counts_c.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
     if (scores & LRPERM_SCORE_GMEAN) CK(cudaMemsetAsync(h->counts_g.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
 
+    const uint8_t* slab_labels = h->labels8.as<uint8_t>();
+    if (order_mode == LRPERM_ORDER_FAST && h->fast_variant == 2) {
+        const int32_t scale = Q / 2;
+        if (h->labels8s_scale != scale) {
+            CK(h->labels8s.ensure((size_t)std::max<int64_t>(N, 1)));
+            if (N > 0) {
+                scale_labels_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels8.as<uint8_t>(), (int32_t)N, scale, h->labels8s.as<uint8_t>());
+                CK_LAUNCH();
+            }
+            h->labels8s_scale = scale;
+        }
+        slab_labels = h->labels8s.as<uint8_t>();
+    }
     const int64_t n_batches = (n_perms + PB - 1) / PB;
     const size_t n_events = (size_t)n_batches * 5 + 2;
     while (h->events.size() < n_events) {
@@ -718,17 +784,21 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
             if (ps.philox) {
                 const int cells_per_block = 128;
                 dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
-                slab_philox_kernel<<<grd, 128, 0, h->stream>>>(ps, h->labels8.as<uint8_t>(), (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
+                slab_philox_kernel<<<grd, 128, 0, h->stream>>>(ps, slab_labels, (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
             } else {
                 dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
-                slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, h->labels8.as<uint8_t>(), (int32_t)N, pb, h->slab.as<uint8_t>(), PB);
+                slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, slab_labels, (int32_t)N, pb, h->slab.as<uint8_t>(), PB);
             }
             CK_LAUNCH();
         }
         CK(cudaEventRecord(h->events[evi++], h->stream));
         // ---- stage 2: per-(gene, cluster, permutation) means ----
         if (order_mode == LRPERM_ORDER_FAST) {
-            if (Q == 4) rc = launch_fast_q<4>(h, PB, h->partials.as<float>());
+            if (h->fast_variant == 2) {
+                if (Q == 8) rc = launch_fast2_q<8, 16>(h, PB, h->partials.as<float>());
+                else if (Q == 4) rc = launch_fast2_q<4, 32>(h, PB, h->partials.as<float>());
+                else rc = launch_fast2_q<2, 32>(h, PB, h->partials.as<float>());
+            } else if (Q == 4) rc = launch_fast_q<4>(h, PB, h->partials.as<float>());
             else if (Q == 2) rc = launch_fast_q<2>(h, PB, h->partials.as<float>());
             else rc = launch_fast_q<1>(h, PB, h->partials.as<float>());
             if (rc) return rc;

@@ -321,6 +321,12 @@ __global__ void slab_philox_kernel(PermSource ps, const uint8_t* __restrict__ la
     }
 }
 
+// slab label bytes for the v2 fast kernel: label * Q/2 (so that byte << 8 == label * Q * 128)
+__global__ void scale_labels_kernel(const uint8_t* __restrict__ labels8, int32_t N, int32_t scale, uint8_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = (uint8_t)(labels8[i] * scale);
+}
+
 __global__ void philox_perms_kernel(uint64_t seed, int64_t perm_id0, int32_t N, int32_t n_perms,
                                     int32_t* __restrict__ out) {
     const int p = blockIdx.y;
@@ -425,6 +431,135 @@ fast_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restric
             __stcs(reinterpret_cast<float2*>(dst), make_float2(vals[0], vals[Q > 1 ? 1 : 0]));
         } else {
             __stcs(dst, vals[0]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST mode, step 2 (v2): same decomposition as fast_means_kernel (one warp = one chunk of one gene's
+// stored entries x 32*Q permutations, private per-lane bins, deterministic ascending-cell order),
+// restructured around the shared-memory pipe, which is what bounds it:
+//   * one warp per CTA, bins at the start of dynamic shared memory, so a bin address is ONE PRMT:
+//     byte 0 = lane*4, byte 1 = the label byte (the slab stores label * Q/2, i.e. label*Q*128 >> 8),
+//     and the q*128 plane offset is an immediate of the LDS/STS -> 4 instructions per update
+//     (PRMT, LDS, FADD, STS) instead of ~9;
+//   * the {cell, value} pairs of a block of B entries are staged in shared memory once and read back
+//     as 128-bit broadcasts (0.5 wavefronts per entry) instead of two shuffles per entry (2 wavefronts);
+//   * label words of block b+1 are in flight while block b updates (registers ping-pong, no moves).
+// ------------------------------------------------------------------------------------------
+template <int Q> struct LabelVec;
+template <> struct LabelVec<2> { using type = uint16_t; };
+template <> struct LabelVec<4> { using type = uint32_t; };
+template <> struct LabelVec<8> { using type = uint2; };
+
+template <int Q> __device__ __forceinline__ uint32_t label_word(const typename LabelVec<Q>::type& w, int q);
+template <> __device__ __forceinline__ uint32_t label_word<2>(const uint16_t& w, int) { return (uint32_t)w; }
+template <> __device__ __forceinline__ uint32_t label_word<4>(const uint32_t& w, int) { return w; }
+template <> __device__ __forceinline__ uint32_t label_word<8>(const uint2& w, int q) { return q < 4 ? w.x : w.y; }
+
+template <int Q>
+__device__ __forceinline__ void fast2_update(unsigned char* bins, uint32_t lane4, const typename LabelVec<Q>::type& lw, float v) {
+    float* b[Q];
+    float x[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        // {byte1 = label byte q, byte0 = lane*4}: offset of bin [label][q=0][lane]
+        const uint32_t off = __byte_perm(label_word<Q>(lw, q), lane4, 0x5504u | ((uint32_t)(q & 3) << 4));
+        b[q] = reinterpret_cast<float*>(bins + off + q * 128);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) x[q] = *b[q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) *b[q] = x[q] + v;
+}
+
+template <int Q, int B>
+__global__ void __launch_bounds__(32)
+fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restrict__ chunks, int32_t n_chunks,
+                   const uint8_t* __restrict__ slab, int32_t PB, int32_t L, int32_t groups_per_batch,
+                   float* __restrict__ partials /*[slot][L][PB]*/) {
+    extern __shared__ __align__(16) unsigned char smem2[];
+    using LV = typename LabelVec<Q>::type;
+    static_assert(B % 4 == 0 && B <= 32, "block of staged entries");
+    const int lane = threadIdx.x;
+    const int chunk_id = (int)(blockIdx.x / (unsigned)groups_per_batch);
+    const int group = (int)(blockIdx.x - (unsigned)chunk_id * (unsigned)groups_per_batch);
+    const FastChunk ch = chunks[chunk_id];
+    const int bins_bytes = L * Q * 128;
+    unsigned char* bins = smem2;
+    int* st_cell = reinterpret_cast<int*>(smem2 + bins_bytes);                 // [2][B]
+    float* st_val = reinterpret_cast<float*>(smem2 + bins_bytes + 2 * B * 4);  // [2][B]
+    {
+        float4* z = reinterpret_cast<float4*>(bins);
+        for (int i = lane; i < L * Q * 8; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const LV* __restrict__ slab_w = reinterpret_cast<const LV*>(slab) + (group * 32 + lane);
+    const int64_t row_words = PB / Q;              // label words per slab row
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const int first_cell = __ldg(&csc_pairs[ch.begin]).x;
+
+    auto load_pair = [&](int k) -> int2 {          // tail entries add +0.0f to a valid bin
+        return (lane < B && k + lane < ch.end) ? __ldg(&csc_pairs[k + lane]) : make_int2(first_cell, 0);
+    };
+    auto stage = [&](int buf, int2 pr) {
+        __syncwarp();                              // earlier broadcasts of this buffer are done
+        if (lane < B) { st_cell[buf * B + lane] = pr.x; st_val[buf * B + lane] = __int_as_float(pr.y); }
+        __syncwarp();
+    };
+    auto fetch_labels = [&](int buf, LV (&lw)[B]) {
+#pragma unroll
+        for (int u = 0; u < B; u += 4) {
+            const int4 c4 = *reinterpret_cast<const int4*>(st_cell + buf * B + u);
+            lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
+            lw[u + 1] = __ldg(slab_w + (int64_t)c4.y * row_words);
+            lw[u + 2] = __ldg(slab_w + (int64_t)c4.z * row_words);
+            lw[u + 3] = __ldg(slab_w + (int64_t)c4.w * row_words);
+        }
+    };
+    auto update = [&](int buf, const LV (&lw)[B]) {
+#pragma unroll
+        for (int u = 0; u < B; u += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(st_val + buf * B + u);
+            fast2_update<Q>(bins, lane4, lw[u + 0], v4.x);
+            fast2_update<Q>(bins, lane4, lw[u + 1], v4.y);
+            fast2_update<Q>(bins, lane4, lw[u + 2], v4.z);
+            fast2_update<Q>(bins, lane4, lw[u + 3], v4.w);
+        }
+    };
+
+    LV lwA[B], lwB[B];
+    int2 pr = load_pair(ch.begin);
+    stage(0, pr);
+    fetch_labels(0, lwA);
+    pr = load_pair(ch.begin + B);
+    for (int k = ch.begin; k < ch.end; k += 2 * B) {
+        // block k: buffer 0 / lwA ; block k+B: buffer 1 / lwB
+        stage(1, pr);
+        pr = load_pair(k + 2 * B);
+        const bool more1 = k + B < ch.end;
+        if (more1) fetch_labels(1, lwB);
+        update(0, lwA);
+        if (!more1) break;
+        stage(0, pr);
+        pr = load_pair(k + 3 * B);
+        if (k + 2 * B < ch.end) fetch_labels(0, lwA);
+        update(1, lwB);
+    }
+    __syncwarp();
+    // partial sums out: partials[(slot*L + c)*PB + group*32*Q + lane*Q + q]
+    const float* mybins = reinterpret_cast<const float*>(bins) + lane;
+    float* out = partials + (int64_t)ch.slot * L * PB + group * 32 * Q + lane * Q;
+    for (int c = 0; c < L; ++c) {
+        float vals[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) vals[q] = mybins[(c * Q + q) * 32];
+        float* dst = out + (int64_t)c * PB;
+        if (Q == 2) {
+            __stcs(reinterpret_cast<float2*>(dst), make_float2(vals[0], vals[1]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; q += 4)
+                __stcs(reinterpret_cast<float4*>(dst + q), make_float4(vals[q], vals[(q + 1) % Q], vals[(q + 2) % Q], vals[(q + 3) % Q]));
         }
     }
 }

@@ -1,0 +1,55 @@
+"""A/B of the FAST-mode kernel variants (device time, CUDA events inside the engine) + bitwise check
+that every variant produces the same cube (same chunking -> same summation order)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from liana_py_b200 import _engine as E
+from liana_py_b200.testing._synth_gpu import synthetic_csr_torch
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+P = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["1:0", "2:4", "2:2", "2:8"]
+N, G, L = {"c2": (50000, 1877, 20), "c3": (500000, 1877, 50), "c4": (200000, 1877, 40), "c5": (10000, 1877, 30),
+           "small": (20000, 500, 12)}[cfg]
+indptr, indices, data, labels = synthetic_csr_torch(N, G, L, 0.08)
+nnz = indices.numel()
+eng = E.Engine(0)
+eng.set_matrix_csr(indptr, indices, data, N, G)
+eng.set_labels(labels, L)
+rng = np.random.default_rng(0)
+T = 200000
+lig, rec, src, tgt = rng.integers(0, G, T), rng.integers(0, G, T), rng.integers(0, L, T), rng.integers(0, L, T)
+means, _, _ = eng.observed()
+obs = ((means[src, lig] + means[tgt, rec]) / 2).astype(np.float32)
+eng.set_triples(lig, rec, src, tgt, obs, None)
+ref_counts = None
+ref_cube = None
+for v in variants:
+    var, q = (int(x) for x in v.split(":"))
+    if var == 2 and q and (L - 1) * q // 2 > 255:
+        continue
+    eng.set_option("fast_variant", var)
+    eng.set_option("fast_q", q)
+    try:
+        small = eng.run(128, seed=5, order=E.ORDER_FAST, scores=E.SCORE_CPDB, return_cube=(N * 0 + G * L * 128 * 4 < (1 << 30)))
+    except E.EngineError as e:
+        print(f"{cfg} variant {v}: {e}")
+        continue
+    if "cube" in small:
+        if ref_cube is None:
+            ref_cube = small["cube"]
+        else:
+            print(f"{cfg} variant {v}: cube bitwise equal to first variant: {np.array_equal(ref_cube, small['cube'])}")
+    best = None
+    for _ in range(4):
+        out = eng.run(P, seed=1337, order=E.ORDER_FAST, scores=E.SCORE_CPDB)
+        tm = eng.timings()
+        if best is None or tm["total_ms"] < best["total_ms"]:
+            best = tm
+    if ref_counts is None:
+        ref_counts = out["cpdb"]
+    same = np.array_equal(ref_counts, out["cpdb"])
+    upd = P * nnz / (best["main_kernel_ms"] * 1e-3)
+    print(f"{cfg} variant {v}: total {best['total_ms']:.2f} ms  setup {best['setup_ms']:.2f}  means {best['means_ms']:.2f} "
+          f"(main {best['main_kernel_ms']:.2f})  score {best['score_ms']:.2f}  upd/s {upd:.3e}  "
+          f"upd/clk/SM {upd / 148 / 1.965e9:.2f}  counts equal: {same}", flush=True)

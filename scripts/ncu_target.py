@@ -13,7 +13,7 @@ eng = E.Engine(0); eng.set_matrix_csr(indptr, indices, data, N, G); eng.set_labe
 rng = np.random.default_rng(0); T = 1_000_000
 lig, rec, src, tgt = rng.integers(0, G, T), rng.integers(0, G, T), rng.integers(0, L, T), rng.integers(0, L, T)
 eng.set_triples(lig, rec, src, tgt, np.ones(T, np.float32), None)
-for _ in range(2):
+for _ in range(2 if Pf else 0):
     eng.run(Pf, seed=1, order=E.ORDER_FAST, scores=E.SCORE_CPDB); print("fast", eng.timings())
-for _ in range(2):
+for _ in range(2 if Pe else 0):
     eng.run(Pe, seed=1, order=E.ORDER_EXACT, scores=E.SCORE_CPDB); print("exact", eng.timings())
