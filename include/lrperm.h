@@ -100,6 +100,16 @@ int lrperm_observed(lrperm_engine *h, float *means, int32_t *stored_counts, int3
                     int out_on_device);
 
 /*
+ * Per-(cluster, gene) float64 moments of the observed matrix, inputs of the non-permutation scores
+ * that rank_aggregate ranks next to the permutation p-values (_liana_pipe.py:259-273 z-scores via
+ * sc.pp.scale, :341-360 1-vs-rest log2FC on `logbase`^x - 1):  sum_x[c*G+g], sum_sq[c*G+g] = sum x^2,
+ * sum_expm1[c*G+g] = sum (logbase^x - 1) over the stored entries of cluster c.  Deterministic
+ * (fixed-order segment partials).  Any output pointer may be NULL.
+ */
+int lrperm_cluster_moments(lrperm_engine *h, double logbase, double *sum_x, double *sum_sq, double *sum_expm1,
+                           int out_on_device);
+
+/*
  * Run `n_perms` permutations and accumulate exceedance counts.
  *   perm_source  LRPERM_PERMS_INDEX : perm_idx[p*N + j] = cell placed at position j in
  *                                     permutation p (int32 or int64), p = 0..n_perms-1

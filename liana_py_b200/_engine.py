@@ -24,6 +24,7 @@ ABI_SYMBOLS = (
     "lrperm_abi_version", "lrperm_last_error", "lrperm_create", "lrperm_destroy", "lrperm_set_stream",
     "lrperm_set_matrix_csr", "lrperm_set_labels", "lrperm_set_triples", "lrperm_observed", "lrperm_run",
     "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
+    "lrperm_cluster_moments",
 )
 
 _lib = None
@@ -53,6 +54,7 @@ def load_library():
     lib.lrperm_set_stream.argtypes = [vp, vp]
     lib.lrperm_set_tuning.argtypes = [vp, i32, i32, i32]
     lib.lrperm_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.lrperm_cluster_moments.argtypes = [vp, C.c_double, vp, vp, vp, C.c_int]
     lib.lrperm_set_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int]
     lib.lrperm_set_labels.argtypes = [vp, vp, i32, C.c_int]
     lib.lrperm_set_triples.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_int]
@@ -189,6 +191,12 @@ class Engine:
         self._check(self._lib.lrperm_observed(self._h, C.c_void_p(means.ctypes.data), C.c_void_p(stored.ctypes.data),
                                               C.c_void_p(sizes.ctypes.data), 0))
         return means, stored, sizes
+
+    def cluster_moments(self, logbase: float = float(np.e)):
+        """(sum_x, sum_sq, sum_expm1) float64 [L,G]: per-cluster sums of x, x^2 and logbase^x - 1."""
+        outs = [np.empty((self.L, self.G), dtype=np.float64) for _ in range(3)]
+        self._check(self._lib.lrperm_cluster_moments(self._h, float(logbase), *(C.c_void_p(o.ctypes.data) for o in outs), 0))
+        return tuple(outs)
 
     def run(self, n_perms: int, *, seed: int = 1337, perm_offset: int = 0, perm_idx=None, order: int = ORDER_EXACT,
             scores: int = SCORE_CPDB, gmean_mode: int = GMEAN_PRODUCT, return_cube: bool = False,

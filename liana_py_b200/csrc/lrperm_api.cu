@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -50,6 +51,8 @@ struct lrperm_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;    // FAST mode: label slabs / finalize / score run here, overlapped with the main kernel
+    int32_t overlap = 1;
     std::string err;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -82,6 +85,7 @@ struct lrperm_engine {
     DevBuf chunks, gene_slot_ptr;
 
     // work buffers
+    DevBuf slab2, partials2;              // second halves of the double buffers of the pipelined FAST path
     DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out, small_a, small_b;
 
     // timings of the last run
@@ -308,7 +312,7 @@ int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube
 }
 
 template <int Q>
-int launch_fast_q(lrperm_engine* h, int32_t PB, float* partials) {
+int launch_fast_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials) {
     const int32_t L = h->L;
     const size_t smem = (size_t)kFastWarps * L * Q * 32 * sizeof(float);
     CK(cudaFuncSetAttribute(fast_means_kernel<Q, kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -317,14 +321,14 @@ int launch_fast_q(lrperm_engine* h, int32_t PB, float* partials) {
     const int64_t grid = (items + kFastWarps - 1) / kFastWarps;
     if (grid > 0) {
         fast_means_kernel<Q, kFastWarps><<<(unsigned)grid, kFastWarps * 32, smem, h->stream>>>(
-            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, h->slab.as<uint8_t>(), PB, L, groups, partials);
+            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, slab, PB, L, groups, partials);
         CK_LAUNCH();
     }
     return LRPERM_OK;
 }
 
 template <int Q, int B>
-int launch_fast2_q(lrperm_engine* h, int32_t PB, float* partials) {
+int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials) {
     const int32_t L = h->L;
     const size_t smem = (size_t)L * Q * 128 + 16 * B;
     CK(cudaFuncSetAttribute(fast2_means_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -333,7 +337,7 @@ int launch_fast2_q(lrperm_engine* h, int32_t PB, float* partials) {
     if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: too many chunks (%lld CTAs)", (long long)grid);
     if (grid > 0) {
         fast2_means_kernel<Q, B><<<(unsigned)grid, 32, smem, h->stream>>>(
-            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, h->slab.as<uint8_t>(), PB, L, groups, partials);
+            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, slab, PB, L, groups, partials);
         CK_LAUNCH();
     }
     return LRPERM_OK;
@@ -384,6 +388,154 @@ int launch_score_t(lrperm_engine* h, int scores, const float* cube, int32_t PP, 
     return LRPERM_OK;
 }
 
+
+int launch_fast_any(lrperm_engine* h, int Q, int32_t PB, const uint8_t* slab, float* partials) {
+    if (h->fast_variant == 2) {
+        if (Q == 8) return launch_fast2_q<8, 16>(h, PB, slab, partials);
+        if (Q == 4) return launch_fast2_q<4, 32>(h, PB, slab, partials);
+        return launch_fast2_q<2, 32>(h, PB, slab, partials);
+    }
+    if (Q == 4) return launch_fast_q<4>(h, PB, slab, partials);
+    if (Q == 2) return launch_fast_q<2>(h, PB, slab, partials);
+    return launch_fast_q<1>(h, PB, slab, partials);
+}
+
+struct RunArgs {
+    int64_t n_perms, perm_offset;
+    uint64_t seed;
+    int perm_source;
+    const void* perm_idx;
+    int perm_idx_is_64, perm_idx_on_device, scores, gmean_mode;
+    float* cube_out;
+    int cube_on_device;
+};
+
+// FAST mode, pipelined over two streams.  Stream A (the engine stream) runs only the main kernel;
+// stream B runs everything around it: the label slab of batch b+1 while main(b) runs, and
+// finalize(b) + score(b) while main(b+1) runs.  Slab and partial-sum buffers are double-buffered.
+//   B: slab(0) | slab(1)         | wait m0, finalize(0), score(0), slab(2) | wait m1, finalize(1), ...
+//   A: wait s0, main(0), rec m0  | wait s1, main(1), rec m1                | wait s2, wait f0, main(2) ...
+int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, const uint8_t* slab_labels) {
+    const int64_t N = h->N;
+    const int32_t G = (int32_t)h->G, L = h->L;
+    const int32_t PP = PB;
+    const int64_t n_batches = (a.n_perms + PB - 1) / PB;
+    int rc;
+    cudaStream_t sA = h->stream, sB = h->aux_stream;
+    const size_t slab_bytes = (size_t)N * PB;
+    const size_t part_bytes = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB;
+    const bool dbl = n_batches > 1;
+    if (dbl) { CK(h->slab2.ensure(slab_bytes)); CK(h->partials2.ensure(part_bytes)); }
+    uint8_t* slabs[2] = {h->slab.as<uint8_t>(), dbl ? h->slab2.as<uint8_t>() : h->slab.as<uint8_t>()};
+    float* parts[2] = {h->partials.as<float>(), dbl ? h->partials2.as<float>() : h->partials.as<float>()};
+
+    // events: [0] start, [1] end, then per batch: s0 s1 (slab), m0 m1 (main), f0 f1 (finalize), c1 (score end)
+    const size_t n_events = 2 + (size_t)n_batches * 7 + 1;
+    while (h->events.size() < n_events) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        h->events.push_back(ev);
+    }
+    auto EV = [&](int64_t b, int k) { return h->events[2 + (size_t)b * 7 + k]; };
+    cudaEvent_t ev_fork = h->events[2 + (size_t)n_batches * 7];
+    CK(cudaEventRecord(h->events[0], sA));       // run start (after the counter memsets on A)
+    CK(cudaEventRecord(ev_fork, sA));
+    CK(cudaStreamWaitEvent(sB, ev_fork, 0));     // B starts after everything already queued on A
+
+    const size_t idx_elem = a.perm_idx_is_64 ? 8 : 4;
+    auto enqueue_slab = [&](int64_t b) -> int {
+        const int64_t p0 = b * PB;
+        const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+        uint8_t* slab = slabs[b & 1];
+        PermSource ps{};
+        ps.is64 = a.perm_idx_is_64;
+        ps.seed = a.seed;
+        ps.perm_id0 = a.perm_offset + p0;
+        ps.philox = a.perm_source == LRPERM_PERMS_PHILOX;
+        CK(cudaEventRecord(EV(b, 0), sB));
+        if (pb < PB) CK(cudaMemsetAsync(slab, 0, slab_bytes, sB));
+        if (ps.philox) {
+            const int cells_per_block = 128;
+            dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
+            slab_philox_kernel<<<grd, 128, 0, sB>>>(ps, slab_labels, (int32_t)N, pb, slab, PB, cells_per_block);
+        } else {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
+            if (a.perm_idx_on_device) ps.idx = src;
+            else {
+                // the staging buffer is reused by every batch: slab(b) is queued on B after slab(b-1), in order
+                CK(h->perm_dev.ensure(idx_elem * (size_t)pb * (size_t)N));
+                CK(cudaMemcpyAsync(h->perm_dev.p, src, idx_elem * (size_t)pb * (size_t)N, cudaMemcpyHostToDevice, sB));
+                ps.idx = h->perm_dev.p;
+            }
+            dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
+            slab_from_index_kernel<<<grd, 256, 0, sB>>>(ps, slab_labels, (int32_t)N, pb, slab, PB);
+        }
+        CK_LAUNCH();
+        CK(cudaEventRecord(EV(b, 1), sB));
+        return LRPERM_OK;
+    };
+
+    if ((rc = enqueue_slab(0))) return rc;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int64_t p0 = b * PB;
+        const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+        if (b + 1 < n_batches && (rc = enqueue_slab(b + 1))) return rc;
+        // ---- A: main kernel ----
+        CK(cudaStreamWaitEvent(sA, EV(b, 1), 0));
+        if (b >= 2) CK(cudaStreamWaitEvent(sA, EV(b - 2, 5), 0));     // partials[b&1] consumed by finalize(b-2)
+        CK(cudaEventRecord(EV(b, 2), sA));
+        if ((rc = launch_fast_any(h, Q, PB, slabs[b & 1], parts[b & 1]))) return rc;
+        CK(cudaEventRecord(EV(b, 3), sA));
+        // ---- B: finalize + score (+ optional cube export) ----
+        CK(cudaStreamWaitEvent(sB, EV(b, 3), 0));
+        CK(cudaEventRecord(EV(b, 4), sB));
+        fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, sB>>>(
+            parts[b & 1], h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
+        CK_LAUNCH();
+        CK(cudaEventRecord(EV(b, 5), sB));
+        if (a.scores) {
+            cudaStream_t saved = h->stream;
+            h->stream = sB;
+            if (a.gmean_mode == LRPERM_GMEAN_LITERAL) rc = launch_score_t<true>(h, a.scores, h->cube.as<float>(), PP, pb);
+            else rc = launch_score_t<false>(h, a.scores, h->cube.as<float>(), PP, pb);
+            h->stream = saved;
+            if (rc) return rc;
+        }
+        if (a.cube_out) {
+            float* dst = a.cube_out + (size_t)p0 * L * G;
+            float* dev_dst = dst;
+            if (!a.cube_on_device) { CK(h->stage_out.ensure(sizeof(float) * (size_t)pb * L * G)); dev_dst = h->stage_out.as<float>(); }
+            dim3 blk(32, 8), grd((G + 31) / 32, (pb + 31) / 32, L);
+            cube_export_kernel<<<grd, blk, 0, sB>>>(h->cube.as<float>(), G, L, PP, pb, dev_dst);
+            CK_LAUNCH();
+            if (!a.cube_on_device) {
+                CK(cudaMemcpyAsync(dst, dev_dst, sizeof(float) * (size_t)pb * L * G, cudaMemcpyDeviceToHost, sB));
+                CK(cudaStreamSynchronize(sB));   // staging buffer is reused by the next batch
+            }
+        }
+        CK(cudaEventRecord(EV(b, 6), sB));
+    }
+    // join: A continues (result copies) after the last score on B
+    CK(cudaStreamWaitEvent(sA, EV(n_batches - 1, 6), 0));
+    CK(cudaEventRecord(h->events[1], sA));
+    return LRPERM_OK;
+}
+
+int collect_pipelined_timings(lrperm_engine* h, int64_t n_batches) {
+    auto EV = [&](int64_t b, int k) { return h->events[2 + (size_t)b * 7 + k]; };
+    h->t_setup = h->t_means = h->t_score = h->t_main = 0.f;
+    h->n_main_launches = (int32_t)n_batches;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        float ms;
+        CK(cudaEventElapsedTime(&ms, EV(b, 0), EV(b, 1))); h->t_setup += ms;
+        CK(cudaEventElapsedTime(&ms, EV(b, 2), EV(b, 3))); h->t_main += ms; h->t_means += ms;
+        CK(cudaEventElapsedTime(&ms, EV(b, 4), EV(b, 5))); h->t_means += ms;
+        CK(cudaEventElapsedTime(&ms, EV(b, 5), EV(b, 6))); h->t_score += ms;
+    }
+    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[1]));
+    return LRPERM_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -410,6 +562,13 @@ int lrperm_create(int device, lrperm_engine** out) {
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // highest priority: the CTA dispatcher otherwise drains the main kernel's whole grid before it
+        // starts a kernel of another stream, and the overlap would only happen at the tail
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = h->err_flag.ensure(sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->err_flag.p, 0, sizeof(int));
     if (e != cudaSuccess) {
@@ -430,11 +589,12 @@ void lrperm_destroy(lrperm_engine* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->labels32, &h->labels8, &h->labels8s, &h->order,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
-                      &h->chunks, &h->gene_slot_ptr, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
+                      &h->chunks, &h->gene_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     delete h;
 }
 
@@ -460,6 +620,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     if (key == "fast_variant") {
         if (value != 1 && value != 2) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_variant must be 1 or 2");
         h->fast_variant = (int32_t)value;
+    } else if (key == "overlap") {
+        if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: overlap must be 0 or 1");
+        h->overlap = (int32_t)value;
     } else if (key == "fast_q") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_q must be 0, 1, 2, 4 or 8");
         h->fast_q = (int32_t)value;
@@ -657,6 +820,33 @@ int lrperm_observed(lrperm_engine* h, float* means, int32_t* stored_counts, int3
     return LRPERM_OK;
 }
 
+int lrperm_cluster_moments(lrperm_engine* h, double logbase, double* sum_x, double* sum_sq, double* sum_expm1, int out_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_cluster_moments: set the matrix and labels first");
+    if (!(logbase > 0.0)) return h->fail(LRPERM_ERR_INVALID, "lrperm_cluster_moments: logbase must be > 0");
+    const int32_t G = (int32_t)h->G, L = h->L;
+    const size_t LG = (size_t)L * G;
+    const int32_t n_seg = 16;
+    CK(h->tmp_a.ensure(sizeof(double) * 3 * LG * n_seg));
+    CK(h->tmp_b.ensure(sizeof(double) * 3 * LG));
+    const size_t smem = sizeof(double) * 3 * kMomentTile;
+    CK(cudaFuncSetAttribute(cluster_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grd((unsigned)n_seg, (unsigned)L, (unsigned)((G + kMomentTile - 1) / kMomentTile));
+    cluster_moments_kernel<<<grd, 32, smem, h->stream>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), h->order.as<int32_t>(),
+                                                         h->cl_start.as<int32_t>(), G, n_seg, std::log(logbase), h->tmp_a.as<double>(), L);
+    CK_LAUNCH();
+    moments_reduce_kernel<<<grid_for((int64_t)3 * LG, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<double>(), G, L, n_seg, h->tmp_b.as<double>());
+    CK_LAUNCH();
+    int rc;
+    const double* base = h->tmp_b.as<double>();
+    if ((rc = download(h, sum_x, base, sizeof(double) * LG, out_on_device))) return rc;
+    if ((rc = download(h, sum_sq, base + LG, sizeof(double) * LG, out_on_device))) return rc;
+    if ((rc = download(h, sum_expm1, base + 2 * LG, sizeof(double) * LG, out_on_device))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
 int lrperm_philox_perms(lrperm_engine* h, int64_t n_cells, int64_t n_perms, int64_t perm_offset, uint64_t seed,
                         int32_t* out, int out_on_device) {
     if (!h) return LRPERM_ERR_INVALID;
@@ -751,6 +941,15 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         slab_labels = h->labels8s.as<uint8_t>();
     }
     const int64_t n_batches = (n_perms + PB - 1) / PB;
+    if (order_mode == LRPERM_ORDER_FAST && h->overlap && n_batches > 0) {
+        RunArgs ra{n_perms, perm_offset, seed, perm_source, perm_idx, perm_idx_is_64, perm_idx_on_device, scores, gmean_mode,
+                   cube_out, cube_on_device};
+        if ((rc = run_fast_pipelined(h, ra, Q, PB, slab_labels))) { cudaStreamSynchronize(h->aux_stream); cudaStreamSynchronize(h->stream); return rc; }
+        if (scores & LRPERM_SCORE_CPDB) if ((rc = download(h, counts_cpdb, h->counts_c.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
+        if (scores & LRPERM_SCORE_GMEAN) if ((rc = download(h, counts_gmean, h->counts_g.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        return collect_pipelined_timings(h, n_batches);
+    }
     const size_t n_events = (size_t)n_batches * 5 + 2;
     while (h->events.size() < n_events) {
         cudaEvent_t ev;
@@ -794,13 +993,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         CK(cudaEventRecord(h->events[evi++], h->stream));
         // ---- stage 2: per-(gene, cluster, permutation) means ----
         if (order_mode == LRPERM_ORDER_FAST) {
-            if (h->fast_variant == 2) {
-                if (Q == 8) rc = launch_fast2_q<8, 16>(h, PB, h->partials.as<float>());
-                else if (Q == 4) rc = launch_fast2_q<4, 32>(h, PB, h->partials.as<float>());
-                else rc = launch_fast2_q<2, 32>(h, PB, h->partials.as<float>());
-            } else if (Q == 4) rc = launch_fast_q<4>(h, PB, h->partials.as<float>());
-            else if (Q == 2) rc = launch_fast_q<2>(h, PB, h->partials.as<float>());
-            else rc = launch_fast_q<1>(h, PB, h->partials.as<float>());
+            rc = launch_fast_any(h, Q, PB, h->slab.as<uint8_t>(), h->partials.as<float>());
             if (rc) return rc;
             CK(cudaEventRecord(h->events[evi++], h->stream));   // main kernel done
             fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, h->stream>>>(

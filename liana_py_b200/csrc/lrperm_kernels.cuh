@@ -167,6 +167,60 @@ __global__ void stored_counts_kernel(const int32_t* __restrict__ indptr, const i
     }
 }
 
+// Per-(cluster, gene) float64 moments of the observed matrix, for the non-permutation scores that
+// rank_aggregate combines with the permutation p-values (liana/method/sc/_liana_pipe.py:259-273,
+// 341-360): sum x (cluster means, z-scores), sum x^2 (sc.pp.scale's per-gene variance) and
+// sum (base^x - 1) (the 1-vs-rest log2FC).  One warp per (segment of a cluster's cells, gene tile);
+// the warp owns its shared-memory accumulators (lanes cover one row's distinct columns), segment
+// partials are combined in fixed order by moments_reduce_kernel -> deterministic.
+constexpr int kMomentTile = 4096;     // genes per tile: 3 x 4096 x 8 B = 96 KB of shared memory
+
+__global__ void __launch_bounds__(32)
+cluster_moments_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
+                       const int32_t* __restrict__ order, const int32_t* __restrict__ cl_start,
+                       int32_t G, int32_t n_seg, double ln_base, double* __restrict__ partial /*[3][L][n_seg][G]*/,
+                       int32_t L) {
+    extern __shared__ double macc[];
+    const int lane = threadIdx.x, seg = blockIdx.x, c = blockIdx.y, g0 = blockIdx.z * kMomentTile;
+    const int gt = min(kMomentTile, G - g0);
+    double* s1 = macc; double* s2 = macc + kMomentTile; double* s3 = macc + 2 * kMomentTile;
+    for (int g = lane; g < gt; g += 32) { s1[g] = 0.0; s2[g] = 0.0; s3[g] = 0.0; }
+    __syncwarp();
+    const int kb = cl_start[c], ke = cl_start[c + 1];
+    const int64_t len = ke - kb;
+    const int k0 = kb + (int)(len * seg / n_seg), k1 = kb + (int)(len * (seg + 1) / n_seg);
+    for (int k = k0; k < k1; ++k) {
+        const int cell = order[k];
+        const int rs = indptr[cell], re = indptr[cell + 1];
+        for (int o = rs + lane; o < re; o += 32) {
+            const int2 pr = pairs[o];
+            const int g = pr.x - g0;
+            if (g >= 0 && g < gt) {
+                const double x = (double)__int_as_float(pr.y);
+                s1[g] += x;
+                s2[g] += x * x;
+                s3[g] += expm1(x * ln_base);
+            }
+        }
+        __syncwarp();
+    }
+    const size_t plane = (size_t)L * n_seg * G;
+    double* out = partial + ((size_t)c * n_seg + seg) * G + g0;
+    for (int g = lane; g < gt; g += 32) { out[g] = s1[g]; out[plane + g] = s2[g]; out[2 * plane + g] = s3[g]; }
+}
+
+__global__ void moments_reduce_kernel(const double* __restrict__ partial, int32_t G, int32_t L, int32_t n_seg,
+                                      double* __restrict__ out /*[3][L][G]*/) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)3 * L * G;
+    if (i >= total) return;
+    const int g = (int)(i % G);
+    const int64_t mc = i / G;                 // moment * L + cluster
+    double s = 0.0;
+    for (int seg = 0; seg < n_seg; ++seg) s += partial[(mc * n_seg + seg) * G + g];
+    out[i] = s;
+}
+
 // ------------------------------------------------------------------------------------------
 // Permutation sources
 // ------------------------------------------------------------------------------------------

@@ -123,20 +123,28 @@ class Method(MethodMeta):
         if supp_columns:
             raise NotImplementedError("supp_columns are outside the scope of the permutation engine")
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
-                           use_raw, layer, verbose, device=device)
+                           use_raw, layer, verbose, device=device, base=base)
         liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
                                perm_source, order, gmean_mode, dist)
-        liana_res = liana_res.sort_values(by=self.magnitude, ascending=self.magnitude_ascending)
+        orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
+            else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
+        liana_res = liana_res.sort_values(by=orderby, ascending=ascending)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
 
 
 def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_lrs, perm_source, order,
-               gmean_mode, dist, aggregate_flag=False, null_cache=None) -> pd.DataFrame:
-    """`_run_method` (`_liana_pipe.py:363-452`) for one method on a prepared PipelineState."""
+               gmean_mode, dist, aggregate_flag=False, null_cache=None, permuting_methods=None) -> pd.DataFrame:
+    """`_run_method` (`_liana_pipe.py:363-452`) for one method on a prepared PipelineState.
+
+    In a consensus (`null_cache` given) every permutation method named in `permuting_methods` is counted
+    from ONE pass over the permutations, and the counts are cached for the methods that follow."""
     tri = _tables.resolve_triples(state.tables, state.means, state.props, expr_prop, state.pair_mask, return_all_lrs)
     lr_res = PL.base_frame(state, tri)
+    if method.add_cols:
+        lr_res = PL.add_method_columns(state, tri, lr_res, method.add_cols)
+        lr_res = lr_res[sorted(lr_res.columns)]            # `np.union1d` of the column sets (`_liana_pipe.py:385`)
     kept = tri.keep
     x = lr_res[kept] if return_all_lrs else lr_res
     null = None
@@ -146,9 +154,11 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
         if null_cache is not None and key in null_cache:
             null = null_cache[key]
         else:
-            both = null_cache is not None      # rank_aggregate: one pass counts both nulls from one cube
-            oc = PL.observed_cpdb(sub.ligand_means, sub.receptor_means) if (both or method.engine_score == "cpdb") else None
-            og = PL.observed_gmean(sub.ligand_means, sub.receptor_means) if (both or method.engine_score == "gmean") else None
+            wanted = {method.engine_score}
+            if null_cache is not None and permuting_methods:
+                wanted |= {m.engine_score for m in permuting_methods if m.permute and m.engine_score}
+            oc = PL.observed_cpdb(sub.ligand_means, sub.receptor_means) if "cpdb" in wanted else None
+            og = PL.observed_gmean(sub.ligand_means, sub.receptor_means) if "gmean" in wanted else None
             out = PL.permutation_counts(state, sub, oc, og, n_perms, seed, perm_source, order, gmean_mode, dist)
             if null_cache is not None:
                 for name in ("cpdb", "gmean"):
@@ -158,12 +168,13 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
     magnitude, specificity = method.fun(x, null) if method.permute else method.fun(x)
     spec_name = method.specificity if (not method.permute or n_perms is not None) else None
     lr_res = lr_res.copy()
+    if return_all_lrs:
+        lr_res[K.LRS_TO_KEEP] = kept
     if method.magnitude is not None:
         lr_res[method.magnitude] = _scatter(magnitude, kept, return_all_lrs)
     if spec_name is not None:
         lr_res[spec_name] = _scatter(specificity, kept, return_all_lrs)
     if return_all_lrs:
-        lr_res[K.LRS_TO_KEEP] = kept
         # rows that failed expr_prop get the worst kept value (`_liana_pipe.py:433-443`)
         for col, asc in ((method.magnitude, method.magnitude_ascending), (spec_name, method.specificity_ascending)):
             if col is not None:

@@ -56,15 +56,77 @@ def reference_perm_indices(n_cells: int, n_perms: int, seed: int) -> np.ndarray:
 
 
 class PipelineState:
-    """Everything computed before any method-specific scoring (shared by rank_aggregate methods)."""
+    """Everything computed before any method-specific scoring (shared by rank_aggregate methods).
 
-    def __init__(self, prep, tables, engine, means, props, sizes, pair_mask):
+    means float32 [L,G], props float64 [L,G], sizes int32 [L] come from the engine's observed pass;
+    the statistics only the non-permutation methods need are computed lazily from the engine's
+    float64 per-(cluster, gene) moments (`lrperm_cluster_moments`)."""
+
+    def __init__(self, prep, tables, engine, means, props, sizes, pair_mask, base=float(np.e)):
         self.prep, self.tables, self.engine = prep, tables, engine
         self.means, self.props, self.sizes, self.pair_mask = means, props, sizes, pair_mask
+        self.base = float(base)
+        self._moments = None
+        self._cache = {}
+
+    def _get_moments(self):
+        if self._moments is None:
+            self._moments = self.engine.cluster_moments(self.base)
+        return self._moments
+
+    def zscores(self) -> np.ndarray:
+        """Cluster means of the per-gene z-scored matrix, float32 [L,G] (`_liana_pipe.py:259-262, 303-304`:
+        sc.pp.scale = (x - mean_g) / std_g with the unbiased variance, std 0 -> 1; the mean over a
+        cluster's cells is (cluster mean - mean_g) / std_g)."""
+        if "z" not in self._cache:
+            sum_x, sum_sq, _ = self._get_moments()
+            n = float(self.sizes.sum())
+            mean = sum_x.sum(axis=0) / n
+            var = (sum_sq.sum(axis=0) / n - mean ** 2) * (n / (n - 1.0))
+            std = np.sqrt(np.maximum(var, 0.0))
+            std[std == 0] = 1.0
+            cl_mean = sum_x / self.sizes[:, None].astype(np.float64)
+            self._cache["z"] = ((cl_mean - mean[None, :]) / std[None, :]).astype(np.float32)
+        return self._cache["z"]
+
+    def logfc(self) -> np.ndarray:
+        """1-vs-rest log2FC of base^x - 1 ("normcounts"), float32 [L,G] (`_liana_pipe.py:341-360`)."""
+        if "fc" not in self._cache:
+            _, _, sum_e = self._get_moments()
+            n_c = self.sizes.astype(np.float64)[:, None]
+            n = float(self.sizes.sum())
+            subj = sum_e / n_c
+            with np.errstate(invalid="ignore", divide="ignore"):
+                rest = (sum_e.sum(axis=0)[None, :] - sum_e) / (n - n_c)
+            self._cache["fc"] = (np.log2(subj + 1.0) - np.log2(rest + 1.0)).astype(np.float32)
+        return self._cache["fc"]
+
+    def means_sums(self, side: str) -> np.ndarray:
+        """NATMI denominators (`_liana_pipe.py:185-190, 337-338`): for a ligand row (target t, gene g) the sum
+        of the gene's cluster means over all sources paired with t; for a receptor row (source s, gene g) the
+        sum over all targets paired with s.  float32 [L,G], accumulated in cluster order with the
+        compensated float32 summation pandas' groupby-sum uses."""
+        key = "sum_" + side
+        if key not in self._cache:
+            L = self.means.shape[0]
+            mask = np.ones((L, L), dtype=bool) if self.pair_mask is None else self.pair_mask   # [source, target]
+            if side == "receptor":
+                mask = mask.T                                                                   # [target, source]
+            out = np.zeros_like(self.means)
+            comp = np.zeros_like(self.means)
+            for j in range(L):                 # j = the cluster being added; rows of `out` = the fixed side
+                sel = mask[j]                  # ligand: mask[source j, target t]; receptor: mask.T[target j, source s]
+                y = self.means[j][None, :] - comp
+                t = out + y
+                new_comp = (t - out) - y
+                out = np.where(sel[:, None], t, out)
+                comp = np.where(sel[:, None], new_comp, comp)
+            self._cache[key] = out
+        return self._cache[key]
 
 
 def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells, use_raw, layer,
-            verbose, device=0) -> PipelineState:
+            verbose, device=0, base=float(np.e)) -> PipelineState:
     res = handle_resource(interactions=interactions, resource=resource, resource_name=resource_name, verbose=verbose)
     groupby_subset = None
     if groupby_pairs is not None:
@@ -95,7 +157,7 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
         for s, t in zip(groupby_pairs[K.SOURCE], groupby_pairs[K.TARGET]):
             if s in pos and t in pos:
                 pair_mask[pos[s], pos[t]] = True
-    return PipelineState(prep, tables, eng, means, props, sizes, pair_mask)
+    return PipelineState(prep, tables, eng, means, props, sizes, pair_mask, base=base)
 
 
 def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFrame:
@@ -108,6 +170,30 @@ def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFra
         K.RECEPTOR_MEANS: tri.receptor_means, K.RECEPTOR_PROPS: tri.receptor_props,
         K.SOURCE: np.asarray(cats)[tri.src], K.TARGET: np.asarray(cats)[tri.tgt],
     })
+
+
+def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame: pd.DataFrame, add_cols) -> pd.DataFrame:
+    """Method-specific statistic columns of the rows in `tri` (the resolved min-subunit gene of every row
+    carries its own statistics through `filter_reassemble_complexes`, `_reassemble_complexes.py:60-66`)."""
+    frame = frame.copy()
+    for col in add_cols:
+        if col == "ligand_zscores":
+            frame[col] = state.zscores()[tri.src, tri.lig_gene]
+        elif col == "receptor_zscores":
+            frame[col] = state.zscores()[tri.tgt, tri.rec_gene]
+        elif col == "ligand_logfc":
+            frame[col] = state.logfc()[tri.src, tri.lig_gene]
+        elif col == "receptor_logfc":
+            frame[col] = state.logfc()[tri.tgt, tri.rec_gene]
+        elif col == "ligand_means_sums":
+            frame[col] = state.means_sums("ligand")[tri.tgt, tri.lig_gene]
+        elif col == "receptor_means_sums":
+            frame[col] = state.means_sums("receptor")[tri.src, tri.rec_gene]
+        elif col == "mat_mean":
+            frame[col] = np.float32(state.prep.mat_mean)
+        else:
+            raise NotImplementedError(f"column `{col}` is outside the scope of the permutation engine")
+    return frame
 
 
 def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, seed, perm_source, order,

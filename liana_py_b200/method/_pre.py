@@ -30,6 +30,7 @@ class PreparedInput:
     labels: np.ndarray            # int32 cluster code per cell
     categories: np.ndarray        # cluster names, code order
     obs_index: pd.Index           # cell names kept
+    mat_mean: float = 0.0         # mean over ALL entries of the prepared matrix (SingleCellSignalR, `_liana_pipe.py:139-140`)
 
 
 def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False):
@@ -140,8 +141,10 @@ def prepare_input(adata, groupby, min_cells, groupby_subset=None, use_raw=False,
         names = names[order]
     X = sparse.csr_matrix(X)
     X.sort_indices()
+    n_all = X.shape[0] * X.shape[1]
+    mat_mean = float(X.data.sum(dtype=np.float64) / n_all) if n_all else 0.0
     return PreparedInput(X=X, var_names=names, labels=np.asarray(lab_sub.cat.codes, dtype=np.int32),
-                         categories=np.asarray(lab_sub.cat.categories), obs_index=obs.index[rows])
+                         categories=np.asarray(lab_sub.cat.categories), obs_index=obs.index[rows], mat_mean=mat_mean)
 
 
 def assert_covered(subset, superset, prop_missing_allowed=0.98, verbose=False):

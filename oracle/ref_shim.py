@@ -45,6 +45,48 @@ class _DocstringProcessor:
         return passthrough
 
 
+def _scanpy_scale(adata, zero_center=True, max_value=None, copy=False, layer=None, obsm=None):
+    """Restatement of scanpy.pp.scale (third-party dependency, pinned scanpy 1.9.8 `poetry.lock:3475`, not
+    vendored under /root/reference) for the one call the reference makes: `sc.pp.scale(adata, copy=True).X`
+    (`liana/method/sc/_liana_pipe.py:262`).  Published algorithm (scanpy/preprocessing/_simple.py
+    `scale_sparse` -> `scale_array`, `_utils._get_mean_var`): densify, mean and E[x^2] per gene in float64
+    (the square taken in the matrix dtype), unbiased variance, std 0 -> 1, then in-place `X -= mean; X /= std`
+    on the float32 matrix."""
+    import numpy as np
+    from scipy import sparse
+    assert zero_center and max_value is None and layer is None and obsm is None
+    X = adata.X.toarray() if sparse.issparse(adata.X) else np.array(adata.X)
+    mean = np.mean(X, axis=0, dtype=np.float64)
+    mean_sq = np.multiply(X, X).mean(axis=0, dtype=np.float64)
+    var = mean_sq - mean ** 2
+    var *= X.shape[0] / (X.shape[0] - 1)
+    std = np.sqrt(var)
+    std[std == 0] = 1
+    X -= mean
+    X /= std
+    out = adata.copy() if copy else adata
+    out.X = X
+    return out if copy else None
+
+
+def _install_pandas_compat():
+    """Container drift, not a change of the reference: `_run_method` ends with `lr_res.drop([None], axis=1)`
+    (`_liana_pipe.py:449-450`) to remove the column a method without a magnitude / specificity score wrote
+    under the label None.  pandas 2.0.3 (pinned, `poetry.lock:2402`) keeps None as a label; pandas 3 turns it
+    into NaN and then cannot find None.  Make that one call mean what it meant under the pinned pandas."""
+    import pandas as pd
+    if getattr(pd.DataFrame.drop, "_lrperm_compat", False):
+        return
+    orig = pd.DataFrame.drop
+
+    def drop(self, labels=None, *args, **kwargs):
+        if isinstance(labels, list) and len(labels) == 1 and labels[0] is None and kwargs.get("axis") == 1:
+            return self.loc[:, ~self.columns.isna()]
+        return orig(self, labels, *args, **kwargs)
+    drop._lrperm_compat = True
+    pd.DataFrame.drop = drop
+
+
 _loaded = None
 
 
@@ -82,6 +124,7 @@ def load_reference():
     sys.modules.setdefault("anndata", an)
     sc = types.ModuleType("scanpy")
     sc.AnnData = AnnDataLite
+    sc.pp = types.SimpleNamespace(scale=_scanpy_scale)
     sys.modules.setdefault("scanpy", sc)
     mu = types.ModuleType("mudata")
 
@@ -100,6 +143,7 @@ def load_reference():
     sys.modules["liana.resource"].explode_complexes = rc.explode_complexes
     sys.modules["liana.resource"].filter_reassemble_complexes = rc.filter_reassemble_complexes
 
+    _install_pandas_compat()
     ns = types.SimpleNamespace()
     ns.AnnData = AnnDataLite
     ns.reassemble = rc
@@ -114,6 +158,15 @@ def load_reference():
     ns.cellphonedb_mod = importlib.import_module("liana.method.sc._cellphonedb")
     ns.geometric_mean_mod = importlib.import_module("liana.method.sc._geometric_mean")
     ns.rank_aggregate_mod = importlib.import_module("liana.method.sc._rank_aggregate")
+    ns.connectome_mod = importlib.import_module("liana.method.sc._connectome")
+    ns.logfc_mod = importlib.import_module("liana.method.sc._logfc")
+    ns.natmi_mod = importlib.import_module("liana.method.sc._natmi")
+    ns.sca_mod = importlib.import_module("liana.method.sc._singlecellsignalr")
+    # the default consensus of `liana/method/__init__.py:13-14` (that __init__ pulls in the spatial stack)
+    ns.default_methods = [ns.cellphonedb_mod.cellphonedb, ns.connectome_mod.connectome, ns.logfc_mod.logfc,
+                          ns.natmi_mod.natmi, ns.sca_mod.singlecellsignalr]
+    ns.rank_aggregate = ns.rank_aggregate_mod.AggregateClass(ns.rank_aggregate_mod._rank_aggregate_meta,
+                                                             methods=ns.default_methods)
     ns.cellphonedb = ns.cellphonedb_mod.cellphonedb
     ns.geometric_mean = ns.geometric_mean_mod.geometric_mean
     ns.constants = importlib.import_module("liana._constants")

@@ -8,7 +8,7 @@ from liana_py_b200.testing._synth_gpu import synthetic_csr_torch
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["1:0", "2:4", "2:2", "2:8"]
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["2:4:0:512", "2:4:1:512", "2:4:1:256", "2:4:1:128", "2:4:1:1024"]
 N, G, L = {"c2": (50000, 1877, 20), "c3": (500000, 1877, 50), "c4": (200000, 1877, 40), "c5": (10000, 1877, 30),
            "small": (20000, 500, 12)}[cfg]
 indptr, indices, data, labels = synthetic_csr_torch(N, G, L, 0.08)
@@ -25,7 +25,10 @@ eng.set_triples(lig, rec, src, tgt, obs, None)
 ref_counts = None
 ref_cube = None
 for v in variants:
-    var, q = (int(x) for x in v.split(":"))
+    parts = [int(x) for x in v.split(":")] + [1, 0]
+    var, q, ov, pbt = parts[0], parts[1], parts[2], parts[3]
+    eng.set_option("overlap", ov)
+    eng.set_tuning(pbt, 0, 0)
     if var == 2 and q and (L - 1) * q // 2 > 255:
         continue
     eng.set_option("fast_variant", var)

@@ -137,9 +137,43 @@ def ragged_case():
     return AnnDataLite(X=X[:, order].tocsr(), obs=obs, var=var)
 
 
+def save_rank_aggregate(name, adata, groupby, n_perms, seed, expr_prop, ref, **extra):
+    """li.mt.rank_aggregate of the reference (default consensus: cellphonedb, connectome, logfc, natmi,
+    singlecellsignalr; `liana/method/__init__.py:13-14`) -> final frame as CSV.  `sc.pp.scale` is the only
+    scanpy call on this path and is restated in oracle/ref_shim.py."""
+    tag = "".join(f"_{k}-{v}" for k, v in sorted(extra.items())) + ("_noperms" if n_perms is None else "")
+    res = ref.rank_aggregate(adata.copy(), groupby=groupby, use_raw=False, n_perms=n_perms, seed=seed,
+                             expr_prop=expr_prop, inplace=False, verbose=False, **extra)
+    res.to_csv(os.path.join(OUT, f"{name}_rank_aggregate{tag}.csv.gz"), index=False)
+    print(f"{name} rank_aggregate{tag}: {res.shape}, columns {list(res.columns)[4:]}")
+
+
+def save_reference_csv_fixture():
+    """The reference's own golden frame for rank_aggregate (liana/tests/data/aggregate_rank_rest.csv, produced
+    by its authors on pbmc68k_reduced with n_perms=2; asserted by liana/tests/test_rank_aggregate.py:41-47).
+    The dataset is not available offline, but the frame pins the consensus step: recomputing both rank columns
+    from its score columns must reproduce them."""
+    from oracle.ref_shim import REFERENCE_ROOT
+    src = os.path.join(REFERENCE_ROOT, "liana", "tests", "data", "aggregate_rank_rest.csv")
+    df = pd.read_csv(src, index_col=0)
+    df.to_csv(os.path.join(OUT, "ref_aggregate_rank_rest.csv.gz"), index=False)
+    print("ref_aggregate_rank_rest:", df.shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    save_reference_csv_fixture()
+    save_rank_aggregate("toy700", make_synthetic_adata(700, 765, 10, density=0.10), "cluster", 100, 1337, 0.1, ref)
+    small = make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12)
+    save_rank_aggregate("small300", small, "cluster", 32, 42, 0.1, ref)
+    save_rank_aggregate("small300", small, "cluster", 32, 42, 0.1, ref, aggregate_method="mean")
+    save_rank_aggregate("ragged90", ragged_case(), "cluster", 16, 5, 0.05, ref)
+    # LAST: with n_perms=None the reference sets `cellphonedb.specificity = None` on the shared method object
+    # (`_liana_pipe.py:420-422`) and every later permutation call in the same process would fail
+    save_rank_aggregate("small300", small, "cluster", None, 42, 0.1, ref)
+    if "--rank-only" in sys.argv:
+        return
     # config 1 stand-in (BASELINE.json configs[0]): 700 cells x 765 genes, 10 clusters, P=100
     save_case("toy700", make_synthetic_adata(700, 765, 10, density=0.10), "cluster", 100, 1337, 0.1, ref,
               keep_cube_perms=8)

@@ -1,0 +1,89 @@
+"""CPU: the consensus step (average ranks + RobustRankAggregate / mean rank) against known answers.
+
+* `ref_aggregate_rank_rest.csv.gz` is the reference's OWN golden frame
+  (liana/tests/data/aggregate_rank_rest.csv, asserted by liana/tests/test_rank_aggregate.py:41-47):
+  recomputing both rank columns from its score columns must reproduce the stored ranks.
+* `*_rank_aggregate*.csv.gz` were produced in the build container by the unmodified reference
+  (scripts/make_golden.py) on the synthetic fixtures.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import liana_py_b200 as li
+from liana_py_b200.method._aggregate import aggregate, rank_aggregate_scores, robust_rank_aggregate
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KEY = ["source", "target", "ligand_complex", "receptor_complex"]
+
+
+def _read(name):
+    return pd.read_csv(os.path.join(GOLDEN, name), float_precision="round_trip")
+
+
+def test_specs_match_reference():
+    # liana/tests/test_rank_aggregate.py:24-38
+    ra = li.mt.rank_aggregate
+    assert ra.specificity_specs == {"CellPhoneDB": ("cellphone_pvals", True), "Connectome": ("scaled_weight", False),
+                                    "log2FC": ("lr_logfc", False), "NATMI": ("spec_weight", False)}
+    assert ra.magnitude_specs == {"CellPhoneDB": ("lr_means", False), "Connectome": ("expr_prod", False),
+                                  "NATMI": ("expr_prod", False), "SingleCellSignalR": ("lrscore", False)}
+    assert ra.magnitude == "magnitude_rank" and ra.specificity == "specificity_rank"
+    assert ra.method_name == "Rank_Aggregate"
+
+
+# The reference's own CSV was written under its pinned scipy (float64 ranks) -> reproduced to 1e-12.  The frames
+# generated in this container ran the same reference code on scipy 1.18, whose rankdata keeps float32 for
+# float32 scores, so their stored ranks carry ~1e-7 of float32 rounding (oracle caveat).
+@pytest.mark.parametrize("fname,method,rtol", [
+    ("ref_aggregate_rank_rest.csv.gz", "rra", 1e-12), ("toy700_rank_aggregate.csv.gz", "rra", 1e-6),
+    ("small300_rank_aggregate.csv.gz", "rra", 1e-6), ("ragged90_rank_aggregate.csv.gz", "rra", 1e-6),
+    ("small300_rank_aggregate_aggregate_method-mean.csv.gz", "mean", 1e-6)])
+def test_ranks_reproduce_reference_frames(fname, method, rtol):
+    gold = _read(fname)
+    scores = gold.drop(columns=["specificity_rank", "magnitude_rank"]).copy()
+    out = aggregate(scores, consensus=li.mt.rank_aggregate, aggregate_method=method)
+    out = out.sort_values(KEY).reset_index(drop=True)
+    exp = gold.sort_values(KEY).reset_index(drop=True)
+    # the reference's own golden CSV stores its float32 scores with 8 digits -> rank ties are preserved
+    np.testing.assert_allclose(out["specificity_rank"].values, exp["specificity_rank"].values, rtol=rtol, atol=0)
+    np.testing.assert_allclose(out["magnitude_rank"].values, exp["magnitude_rank"].values, rtol=rtol, atol=0)
+    # float32 score columns (what the pipeline produces) give the same ranks as their float64 read-back
+    f32 = scores.copy()
+    for c in f32.columns:
+        if f32[c].dtype == np.float64 and c not in ("cellphone_pvals",):
+            f32[c] = f32[c].astype(np.float32)
+    out32 = aggregate(f32, consensus=li.mt.rank_aggregate, aggregate_method=method).sort_values(KEY).reset_index(drop=True)
+    np.testing.assert_allclose(out32["magnitude_rank"].values, exp["magnitude_rank"].values, rtol=max(rtol, 1e-9), atol=0)
+    assert np.all(np.diff(aggregate(scores, li.mt.rank_aggregate, method)["magnitude_rank"].values) >= 0)
+
+
+def test_noperms_frame_only_has_magnitude():
+    gold = _read("small300_rank_aggregate_noperms.csv.gz")
+    assert "specificity_rank" not in gold.columns and "cellphone_pvals" not in gold.columns
+    scores = gold.drop(columns=["magnitude_rank"]).copy()
+    out = aggregate(scores, li.mt.rank_aggregate, "rra", consensus_opts="Magnitude")
+    assert "specificity_rank" not in out.columns
+    a = out.sort_values(KEY)["magnitude_rank"].values
+    b = gold.sort_values(KEY)["magnitude_rank"].values
+    np.testing.assert_allclose(a, b, rtol=1e-6)
+
+
+def test_rra_properties():
+    rng = np.random.default_rng(0)
+    n, m = 500, 4
+    rmat = np.stack([rng.permutation(n) + 1.0 for _ in range(m)], axis=1)
+    rho = robust_rank_aggregate(rmat)
+    assert rho.shape == (n,) and np.all((rho >= 0) & (rho <= 1))
+    # a row ranked first by every method gets the smallest score; column order is irrelevant
+    rmat[0] = 1.0
+    rho = robust_rank_aggregate(rmat)
+    assert rho.argmin() == 0
+    assert np.allclose(rho, robust_rank_aggregate(rmat[:, ::-1]))
+    # expr_prod is named by two methods and therefore ranked twice (reference quirk, kept on purpose)
+    df = pd.DataFrame({"expr_prod": [3.0, 1.0, 2.0]})
+    once = rank_aggregate_scores(df, {"A": ("expr_prod", False)}, "mean")
+    twice = rank_aggregate_scores(df, {"A": ("expr_prod", False), "B": ("expr_prod", False)}, "mean")
+    assert np.array_equal(np.argsort(once), np.argsort(twice)[::-1])

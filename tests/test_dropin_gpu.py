@@ -114,3 +114,96 @@ def test_by_sample_matches_per_sample_calls():
         li.mt.cellphonedb.by_sample(adata, "nope", **kw)
     li.mt.cellphonedb.by_sample(adata, "sample", key_added="by_s", **kw)
     assert adata.uns["by_s"].shape == res.shape
+
+
+# ---- rank_aggregate (default consensus) against frames produced by the reference's own code ----------------
+SCORES = ["lr_means", "cellphone_pvals", "expr_prod", "scaled_weight", "lr_logfc", "spec_weight", "lrscore"]
+
+
+def compare_aggregate(res, gold, rank_cols):
+    assert list(res.columns) == list(gold.columns)
+    a = res.sort_values(KEY).reset_index(drop=True)
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in KEY:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+    for c in [c for c in SCORES if c in gold.columns]:
+        if c in ("lr_means",):
+            assert np.array_equal(a[c].values, b[c].values.astype(np.float32)), c           # bit-identical
+        elif c == "cellphone_pvals":
+            assert np.array_equal(a[c].values, b[c].values), c                              # bit-identical
+        else:
+            # float32 statistics computed by a different (float64-accumulating) route than the reference's
+            # float32 NumPy/SciPy one: same tolerance as the reference's own frame test (rtol 1e-4,
+            # liana/tests/test_rank_aggregate.py:41-47), observed ~1e-6
+            assert a[c].dtype == np.float32, c
+            np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-4, atol=2e-6, err_msg=c)
+    for c in rank_cols:
+        # The consensus is a function of the RANKS of the float32 scores.  A pair of scores the reference's
+        # float32 arithmetic separates by ~1 ulp can come out in the other order here (the statistics are
+        # accumulated in float64), which moves two ranks by one and the aggregate of those rows by ~1/n.
+        # So: (nearly) all rows to the reference's own test tolerance, the rest within a one-rank shift.
+        rel = np.abs(a[c].values - b[c].values) / np.maximum(np.abs(b[c].values), 1e-12)
+        assert (rel <= 1e-4).mean() >= 0.999, (c, float((rel <= 1e-4).mean()))
+        assert rel.max() <= 2e-2, (c, float(rel.max()))
+        # rank ORDER identical except among rows whose aggregate ranks are numerically tied
+        oa, ob = np.argsort(a[c].values, kind="stable"), np.argsort(b[c].values, kind="stable")
+        moved = oa != ob
+        if moved.any():
+            assert np.allclose(b[c].values[oa][moved], b[c].values[ob][moved], rtol=2e-2, atol=1e-9), c
+    assert np.all(np.diff(res[rank_cols[-1]].values) >= 0)            # sorted by magnitude_rank ascending
+
+
+@pytest.mark.parametrize("name", ["toy700", "small300", "ragged90"])
+def test_rank_aggregate_frame_matches_reference(name):
+    adata, P, seed, ep = load_input(name)
+    res = li.mt.rank_aggregate(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                               inplace=False, perm_source="reference")
+    gold = pd.read_csv(os.path.join(GOLDEN, f"{name}_rank_aggregate.csv.gz"), float_precision="round_trip")
+    compare_aggregate(res, gold, ["specificity_rank", "magnitude_rank"])
+
+
+def test_rank_aggregate_mean_and_noperms():
+    adata, P, seed, ep = load_input("small300")
+    res = li.mt.rank_aggregate(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                               inplace=False, perm_source="reference", aggregate_method="mean")
+    gold = pd.read_csv(os.path.join(GOLDEN, "small300_rank_aggregate_aggregate_method-mean.csv.gz"),
+                       float_precision="round_trip")
+    compare_aggregate(res, gold, ["specificity_rank", "magnitude_rank"])
+    res = li.mt.rank_aggregate(adata, groupby="cluster", use_raw=False, n_perms=None, seed=seed, expr_prop=ep,
+                               inplace=False)
+    gold = pd.read_csv(os.path.join(GOLDEN, "small300_rank_aggregate_noperms.csv.gz"), float_precision="round_trip")
+    compare_aggregate(res, gold, ["magnitude_rank"])
+    # the method objects are not mutated by an n_perms=None call (the reference sets specificity=None for good)
+    assert li.mt.cellphonedb.specificity == "cellphone_pvals"
+
+
+def test_custom_consensus_counts_both_nulls_in_one_pass():
+    """BASELINE.json configs[3]: cellphonedb + geometric_mean permutation nulls plus non-permutation scores in
+    one AggregateClass; both nulls come from the same permutations and must equal the single-method runs."""
+    adata, P, seed, ep = load_input("small300")
+    methods = [li.mt.cellphonedb, li.mt.geometric_mean, li.mt.connectome, li.mt.logfc, li.mt.natmi,
+               li.mt.singlecellsignalr]
+    custom = li.mt.AggregateClass(li.mt.aggregate_meta, methods=methods)
+    res = custom(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep, inplace=False,
+                 perm_source="reference")
+    assert {"lr_means", "cellphone_pvals", "lr_gmeans", "gmean_pvals", "specificity_rank", "magnitude_rank"} <= set(res.columns)
+    cp = pd.read_csv(os.path.join(GOLDEN, "small300_cellphonedb.csv.gz"), float_precision="round_trip")
+    gm = pd.read_csv(os.path.join(GOLDEN, "small300_geometric_mean.csv.gz"), float_precision="round_trip")
+    m = res.merge(cp[KEY + ["cellphone_pvals"]], on=KEY, suffixes=("", "_ref")).merge(
+        gm[KEY + ["gmean_pvals"]], on=KEY, suffixes=("", "_ref"))
+    assert len(m) == len(res) == len(cp)
+    assert np.array_equal(m["cellphone_pvals"].values, m["cellphone_pvals_ref"].values)
+    assert np.array_equal(m["gmean_pvals"].values, m["gmean_pvals_ref"].values)
+
+
+def test_single_non_permutation_methods_run():
+    adata, P, seed, ep = load_input("small300")
+    gold = pd.read_csv(os.path.join(GOLDEN, "small300_rank_aggregate.csv.gz"), float_precision="round_trip")
+    for method, cols in ((li.mt.connectome, ["expr_prod", "scaled_weight"]), (li.mt.logfc, ["lr_logfc"]),
+                         (li.mt.natmi, ["expr_prod", "spec_weight"]), (li.mt.singlecellsignalr, ["lrscore"])):
+        res = method(adata, groupby="cluster", use_raw=False, expr_prop=ep, inplace=False)
+        m = res.merge(gold[KEY + cols], on=KEY, suffixes=("", "_ref"))
+        assert len(m) == len(gold)
+        for c in cols:
+            np.testing.assert_allclose(m[c].values, m[c + "_ref"].values, rtol=1e-4, atol=2e-6)
