@@ -75,6 +75,26 @@ int lrperm_set_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes,
                           const void *indptr, int indptr_is_64,
                           const int32_t *indices, const float *data, int on_device);
 
+/*
+ * Input contract on device - replaces the matrix work of prep_check_adata
+ * (liana/method/_pipe_utils/_pre.py:112-142: float32 CSR, empty-feature / empty-sample / non-finite
+ * checks, the min_cells row filter :153-162, the alphabetical gene order :168) and the gene subset of
+ * liana_pipe (liana/method/sc/_liana_pipe.py:161-164), which the reference does with SciPy copies.
+ *
+ * lrperm_stage_matrix_csr uploads the caller's FULL matrix (n_cells x n_genes, any column order within a
+ * row, nnz < 2^31) and returns, over that matrix: col_sums[g] (float64, all rows; a gene is "empty" when
+ * it is 0), the total over the rows flagged in row_keep (NULL = all rows; for mat_mean), the number of
+ * non-finite stored values and of all-zero rows.  The outputs are HOST pointers (any may be NULL);
+ * indptr / indices / data / row_keep follow `on_device`.
+ * lrperm_commit_matrix then makes the staged matrix the engine's matrix, keeping the rows flagged in
+ * row_keep and the columns with col_map[g] >= 0 renamed to col_map[g] in [0, n_genes_out) (host array,
+ * at most one source per output column); it is equivalent to lrperm_set_matrix_csr on the filtered copy.
+ */
+int lrperm_stage_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes, const void *indptr, int indptr_is_64,
+                            const int32_t *indices, const float *data, int on_device, const uint8_t *row_keep,
+                            double *col_sums, double *kept_total, int64_t *n_nonfinite, int64_t *n_empty_rows);
+int lrperm_commit_matrix(lrperm_engine *h, const int32_t *col_map, int64_t n_genes_out);
+
 /* Cluster code per cell (codes of obs['@label'] in .cat.categories order, _get_mean_perms.py:47-52). */
 int lrperm_set_labels(lrperm_engine *h, const int32_t *labels, int32_t n_clusters, int on_device);
 

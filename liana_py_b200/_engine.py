@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "lrperm_abi_version", "lrperm_last_error", "lrperm_create", "lrperm_destroy", "lrperm_set_stream",
     "lrperm_set_matrix_csr", "lrperm_set_labels", "lrperm_set_triples", "lrperm_observed", "lrperm_run",
     "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
-    "lrperm_cluster_moments",
+    "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
 )
 
 _lib = None
@@ -55,6 +55,8 @@ def load_library():
     lib.lrperm_set_tuning.argtypes = [vp, i32, i32, i32]
     lib.lrperm_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.lrperm_cluster_moments.argtypes = [vp, C.c_double, vp, vp, vp, C.c_int]
+    lib.lrperm_stage_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.lrperm_commit_matrix.argtypes = [vp, vp, i64]
     lib.lrperm_set_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int]
     lib.lrperm_set_labels.argtypes = [vp, vp, i32, C.c_int]
     lib.lrperm_set_triples.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_int]
@@ -160,6 +162,31 @@ class Engine:
             X = X.copy()
             X.sum_duplicates()
         self.set_matrix_csr(X.indptr, X.indices, X.data, X.shape[0], X.shape[1])
+
+    def stage_matrix(self, X, row_keep=None):
+        """Upload the caller's FULL SciPy CSR matrix (float32) and return its statistics:
+        dict(col_sums float64 [G], kept_total, n_nonfinite, n_empty_rows).  Follow with commit_matrix."""
+        indptr = np.ascontiguousarray(X.indptr)
+        if indptr.dtype not in (np.int32, np.int64):
+            indptr = indptr.astype(np.int64)
+        indices = np.ascontiguousarray(X.indices, dtype=np.int32)
+        data = np.ascontiguousarray(X.data, dtype=np.float32)
+        keep = None if row_keep is None else np.ascontiguousarray(row_keep, dtype=np.uint8)
+        n, g = X.shape
+        col_sums = np.zeros(g, dtype=np.float64)
+        total, bad, empty = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.lrperm_stage_matrix_csr(
+            self._h, int(n), int(g), C.c_void_p(indptr.ctypes.data), int(indptr.dtype == np.int64),
+            C.c_void_p(indices.ctypes.data), C.c_void_p(data.ctypes.data), 0,
+            None if keep is None else C.c_void_p(keep.ctypes.data), C.c_void_p(col_sums.ctypes.data),
+            C.byref(total), C.byref(bad), C.byref(empty)))
+        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+
+    def commit_matrix(self, col_map, n_genes_out: int, n_cells_out: int):
+        """Make the staged matrix the engine's matrix: rows flagged in row_keep, columns with col_map >= 0."""
+        col_map = np.ascontiguousarray(col_map, dtype=np.int32)
+        self._check(self._lib.lrperm_commit_matrix(self._h, C.c_void_p(col_map.ctypes.data), int(n_genes_out)))
+        self.N, self.G = int(n_cells_out), int(n_genes_out)
 
     def set_labels(self, labels, n_clusters: int):
         if not _is_torch(labels):

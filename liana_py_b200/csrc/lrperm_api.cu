@@ -10,11 +10,14 @@
 // (2 x P x T float64).
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -29,6 +32,21 @@ using namespace lrperm;
 namespace {
 
 std::string g_create_error;
+
+// LRPERM_DEBUG_TIMING=1: wall-clock of the host-side stages on stderr (development aid)
+struct StageTimer {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit StageTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {
+        static const bool enabled = std::getenv("LRPERM_DEBUG_TIMING") != nullptr;
+        on = enabled;
+    }
+    ~StageTimer() {
+        if (on) fprintf(stderr, "[lrperm] %-18s %8.3f ms\n", name,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -62,6 +80,12 @@ struct lrperm_engine {
     DevBuf indptr, csr_pairs, csc_pairs, err_flag;
     bool have_matrix = false, csc_ready = false;
     std::vector<int32_t> h_csc_ptr;   // [G+1]
+
+    // staged (caller's full) matrix, between lrperm_stage_matrix_csr and lrperm_commit_matrix
+    bool staged = false;
+    int64_t st_N = 0, st_G = 0, st_nnz = 0;
+    bool st_has_keep = false;
+    DevBuf st_indptr, st_indices, st_data, st_row_keep, st_small;
 
     // labels
     int32_t L = 0;
@@ -163,6 +187,7 @@ int check_err_flag(lrperm_engine* h, const char* what) {
 // ---- CSC copy + chunk tables for FAST mode -------------------------------------------------
 int build_csc(lrperm_engine* h) {
     if (h->csc_ready) return LRPERM_OK;
+    StageTimer timer("build_csc");
     const int64_t nnz = h->nnz;
     const int32_t G = (int32_t)h->G;
     CK(h->tmp_a.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nnz, 1)));   // column keys
@@ -210,6 +235,7 @@ int build_csc(lrperm_engine* h) {
 
 int build_chunks(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
     if (h->chunk_table_nnz == chunk_nnz && h->chunk_table_tile == tile_cells) return LRPERM_OK;
+    StageTimer timer("build_chunks");
     const int32_t G = (int32_t)h->G;
     // Split every gene's entry list at cell-tile boundaries (so that the chunks scheduled at any one
     // time only touch one tile of the label slab, which then stays L2 resident) and at chunk_nnz.
@@ -587,7 +613,8 @@ void lrperm_destroy(lrperm_engine* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->labels32, &h->labels8, &h->labels8s, &h->order,
+    for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->st_indptr, &h->st_indices, &h->st_data, &h->st_row_keep, &h->st_small,
+                      &h->labels32, &h->labels8, &h->labels8s, &h->order,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
                       &h->chunks, &h->gene_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b})
@@ -635,6 +662,7 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
 int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, const void* indptr, int indptr_is_64,
                           const int32_t* indices, const float* data, int on_device) {
     if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("set_matrix_csr");
     DeviceGuard guard(h->device);
     h->have_matrix = false; h->csc_ready = false; h->have_triples = false; h->have_labels = false;
     if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr: bad shape or NULL indptr");
@@ -690,8 +718,148 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     return LRPERM_OK;
 }
 
+int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, const void* indptr, int indptr_is_64,
+                            const int32_t* indices, const float* data, int on_device, const uint8_t* row_keep,
+                            double* col_sums, double* kept_total, int64_t* n_nonfinite, int64_t* n_empty_rows) {
+    if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("stage_matrix_csr");
+    DeviceGuard guard(h->device);
+    h->staged = false;
+    if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: bad shape or NULL indptr");
+    if (n_cells >= 0x7fffffffLL || n_genes >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: n_cells and n_genes must be < 2^31");
+    int64_t nnz = 0;
+    const size_t isz = indptr_is_64 ? 8 : 4;
+    {
+        unsigned char last[8] = {0};
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(indptr) + isz * (size_t)n_cells;
+        if (on_device) { CK(cudaMemcpyAsync(last, src, isz, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+        else memcpy(last, src, isz);
+        if (indptr_is_64) { int64_t v; memcpy(&v, last, 8); nnz = v; } else { int32_t v; memcpy(&v, last, 4); nnz = v; }
+    }
+    if (nnz < 0 || nnz >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: nnz=%lld must be in [0, 2^31)", (long long)nnz);
+    if (nnz > 0 && (!indices || !data)) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: NULL indices/data");
+    int rc;
+    CK(h->st_indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    if ((rc = upload(h, h->tmp_a, indptr, isz * (size_t)(n_cells + 1), on_device))) return rc;
+    if (indptr_is_64)
+        narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int64_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
+    else
+        narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int32_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
+    CK_LAUNCH();
+    if ((rc = upload(h, h->st_indices, indices, sizeof(int32_t) * (size_t)nnz, on_device))) return rc;
+    if ((rc = upload(h, h->st_data, data, sizeof(float) * (size_t)nnz, on_device))) return rc;
+    h->st_has_keep = row_keep != nullptr;
+    if (row_keep && (rc = upload(h, h->st_row_keep, row_keep, (size_t)n_cells, on_device))) return rc;
+    // [G doubles col sums][kept_total][n_nonfinite][n_empty_rows]
+    const size_t small_bytes = sizeof(double) * ((size_t)n_genes + 3);
+    CK(h->st_small.ensure(small_bytes));
+    CK(cudaMemsetAsync(h->st_small.p, 0, small_bytes, h->stream));
+    double* d_small = h->st_small.as<double>();
+    if (n_cells > 0) {
+        stage_stats_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+            h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(),
+            row_keep ? h->st_row_keep.as<uint8_t>() : nullptr, (int32_t)n_cells, (int32_t)n_genes, d_small,
+            d_small + n_genes, reinterpret_cast<unsigned long long*>(d_small + n_genes + 1),
+            reinterpret_cast<unsigned long long*>(d_small + n_genes + 2), h->err_flag.as<int>());
+        CK_LAUNCH();
+    }
+    std::vector<double> host((size_t)n_genes + 3);
+    CK(cudaMemcpyAsync(host.data(), d_small, small_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = check_err_flag(h, "lrperm_stage_matrix_csr"))) return rc;     // synchronises the stream
+    if (col_sums) memcpy(col_sums, host.data(), sizeof(double) * (size_t)n_genes);
+    if (kept_total) *kept_total = host[(size_t)n_genes];
+    unsigned long long u;
+    memcpy(&u, &host[(size_t)n_genes + 1], 8); if (n_nonfinite) *n_nonfinite = (int64_t)u;
+    memcpy(&u, &host[(size_t)n_genes + 2], 8); if (n_empty_rows) *n_empty_rows = (int64_t)u;
+    h->st_N = n_cells; h->st_G = n_genes; h->st_nnz = nnz;
+    h->staged = true;
+    return LRPERM_OK;
+}
+
+int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_genes_out) {
+    if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("commit_matrix");
+    DeviceGuard guard(h->device);
+    if (!h->staged) return h->fail(LRPERM_ERR_INVALID, "lrperm_commit_matrix: call lrperm_stage_matrix_csr first");
+    if (!col_map || n_genes_out <= 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_commit_matrix: NULL col_map or n_genes_out <= 0");
+    if (n_genes_out > 65535) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_commit_matrix: n_genes_out must be <= 65535");
+    const int64_t N = h->st_N, Gin = h->st_G;
+    {   // every output column has at most one source column (distinct columns per row is an engine invariant)
+        std::vector<uint8_t> seen((size_t)n_genes_out, 0);
+        for (int64_t g = 0; g < Gin; ++g) {
+            const int32_t m = col_map[g];
+            if (m < -1 || m >= n_genes_out) return h->fail(LRPERM_ERR_INVALID, "lrperm_commit_matrix: col_map[%lld]=%d outside [-1,%lld)", (long long)g, m, (long long)n_genes_out);
+            if (m >= 0) {
+                if (seen[(size_t)m]) return h->fail(LRPERM_ERR_INVALID, "lrperm_commit_matrix: output column %d has two source columns", m);
+                seen[(size_t)m] = 1;
+            }
+        }
+    }
+    h->have_matrix = false; h->csc_ready = false; h->have_triples = false; h->have_labels = false;
+    int rc;
+    DevBuf &d_map = h->small_a, &d_flag = h->tmp_a, &d_excl = h->tmp_d, &d_newrow = h->stage_out;
+    if ((rc = upload(h, d_map, col_map, sizeof(int32_t) * (size_t)Gin, 0))) return rc;
+    CK(d_flag.ensure(sizeof(int32_t) * (size_t)(N + 1)));
+    CK(d_excl.ensure(sizeof(int32_t) * (size_t)(N + 1)));
+    CK(d_newrow.ensure(sizeof(int32_t) * (size_t)(N + 1)));
+    int64_t N_out = N;
+    if (N > 0) {
+        row_keep_to_flag_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->st_has_keep ? h->st_row_keep.as<uint8_t>() : nullptr, (int32_t)N, d_flag.as<int32_t>());
+        CK_LAUNCH();
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag.as<int32_t>(), d_excl.as<int32_t>(), (int)N, h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(h->sort_tmp.p, tmp_bytes, d_flag.as<int32_t>(), d_excl.as<int32_t>(), (int)N, h->stream));
+        new_row_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(d_flag.as<int32_t>(), d_excl.as<int32_t>(), (int32_t)N, d_newrow.as<int32_t>());
+        CK_LAUNCH();
+        int32_t last_excl = 0, last_flag = 0;
+        CK(cudaMemcpyAsync(&last_excl, d_excl.as<int32_t>() + (N - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&last_flag, d_flag.as<int32_t>() + (N - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        N_out = (int64_t)last_excl + last_flag;
+    }
+    // per-row counts of surviving entries -> exclusive scan -> indptr of the engine matrix
+    DevBuf& d_counts = h->tmp_b;
+    CK(d_counts.ensure(sizeof(int32_t) * (size_t)(N_out + 1)));
+    CK(cudaMemsetAsync(d_counts.p, 0, sizeof(int32_t) * (size_t)(N_out + 1), h->stream));
+    CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(N_out + 1)));
+    int64_t nnz_out = 0;
+    if (N > 0) {
+        mapped_count_kernel<<<grid_for(N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+            h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), d_map.as<int32_t>(), d_newrow.as<int32_t>(), (int32_t)N, d_counts.as<int32_t>());
+        CK_LAUNCH();
+    }
+    {
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts.as<int32_t>(), h->indptr.as<int32_t>(), (int)(N_out + 1), h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(h->sort_tmp.p, tmp_bytes, d_counts.as<int32_t>(), h->indptr.as<int32_t>(), (int)(N_out + 1), h->stream));
+        int32_t total = 0;
+        CK(cudaMemcpyAsync(&total, h->indptr.as<int32_t>() + N_out, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        nnz_out = total;
+    }
+    CK(h->tmp_c.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz_out, 1)));
+    CK(h->tmp_d.ensure(sizeof(float) * (size_t)std::max<int64_t>(nnz_out, 1)));     // d_excl is dead from here on
+    CK(h->csr_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz_out, 1)));
+    if (N > 0 && nnz_out > 0) {
+        mapped_scatter_kernel<<<grid_for(N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+            h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), d_map.as<int32_t>(), d_newrow.as<int32_t>(),
+            (int32_t)N, h->indptr.as<int32_t>(), h->tmp_c.as<int32_t>(), h->tmp_d.as<float>());
+        CK_LAUNCH();
+        pack_csr_kernel<<<grid_for(N_out * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+            h->indptr.as<int32_t>(), h->tmp_c.as<int32_t>(), h->tmp_d.as<float>(), (int32_t)N_out, (int32_t)n_genes_out, h->csr_pairs.as<int2>(), h->err_flag.as<int>());
+        CK_LAUNCH();
+    }
+    if ((rc = check_err_flag(h, "lrperm_commit_matrix"))) return rc;
+    h->N = N_out; h->G = n_genes_out; h->nnz = nnz_out;
+    h->have_matrix = true;
+    return LRPERM_OK;
+}
+
 int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_clusters, int on_device) {
     if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("set_labels");
     DeviceGuard guard(h->device);
     h->have_labels = false;
     if (!h->have_matrix) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: call lrperm_set_matrix_csr first");
@@ -742,6 +910,7 @@ int lrperm_set_triples(lrperm_engine* h, int64_t n_triples, const int32_t* ligan
                        const int32_t* source_idx, const int32_t* target_idx, const float* obs_cpdb, const float* obs_gmean,
                        int on_device) {
     if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("set_triples");
     DeviceGuard guard(h->device);
     h->have_triples = false;
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_triples: set the matrix and labels first");
@@ -876,6 +1045,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
                const void* perm_idx, int perm_idx_is_64, int perm_idx_on_device, int order_mode, int scores, int gmean_mode,
                uint32_t* counts_cpdb, uint32_t* counts_gmean, int counts_on_device, float* cube_out, int cube_on_device) {
     if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("run");
     DeviceGuard guard(h->device);
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: set the matrix and labels first");
     if (n_perms < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_run: n_perms < 0");

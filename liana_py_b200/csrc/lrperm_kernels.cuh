@@ -95,6 +95,107 @@ __global__ void pack_csr_kernel(const int32_t* __restrict__ indptr, const int32_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Input contract on device (replaces the matrix work of prep_check_adata,
+// liana/method/_pipe_utils/_pre.py:112-142,168, and the gene subset of liana_pipe,
+// liana/method/sc/_liana_pipe.py:161-164): the caller's FULL matrix is staged once, statistics are
+// taken over it, then it is filtered to kept rows / mapped to the resource's gene columns.
+// ------------------------------------------------------------------------------------------
+// One warp per row of the staged matrix: per-column sums over ALL rows (float64 atomics; used only for
+// the "gene is empty" test and the matrix mean), number of non-finite values, number of empty rows,
+// total over the kept rows.
+__global__ void stage_stats_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                   const float* __restrict__ data, const uint8_t* __restrict__ row_keep, int32_t N, int32_t G,
+                                   double* __restrict__ col_sums, double* __restrict__ kept_total,
+                                   unsigned long long* __restrict__ n_nonfinite, unsigned long long* __restrict__ n_empty_rows,
+                                   int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double block_total = 0.0;
+    unsigned long long bad = 0, empty = 0;
+    for (int r = warp; r < N; r += nwarps) {
+        const int s = indptr[r], e = indptr[r + 1];
+        double row = 0.0;
+        for (int o = s + lane; o < e; o += 32) {
+            const int c = indices[o];
+            const float v = data[o];
+            if (c < 0 || c >= G) { atomicOr(err, 1); continue; }
+            if (!isfinite(v)) { ++bad; continue; }
+            if (v != 0.0f) atomicAdd(&col_sums[c], (double)v);
+            row += (double)v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) row += __shfl_xor_sync(0xffffffffu, row, d);
+        if (lane == 0) {
+            if (row == 0.0) ++empty;
+            if (!row_keep || row_keep[r]) block_total += row;
+        }
+    }
+    if (bad) atomicAdd(n_nonfinite, bad);
+    if (lane == 0) {
+        if (empty) atomicAdd(n_empty_rows, empty);
+        if (block_total != 0.0) atomicAdd(kept_total, block_total);
+    }
+}
+
+// entries of every KEPT row that survive the column map -> counts[new_row]
+__global__ void mapped_count_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                    const int32_t* __restrict__ col_map, const int32_t* __restrict__ new_row /*[N], -1 = dropped*/,
+                                    int32_t N, int32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < N; r += nwarps) {
+        const int nr = new_row[r];
+        if (nr < 0) continue;
+        const int s = indptr[r], e = indptr[r + 1];
+        int n = 0;
+        for (int o = s + lane; o < e; o += 32) n += col_map[indices[o]] >= 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+        if (lane == 0) counts[nr] = n;
+    }
+}
+
+// order-preserving compaction of the kept entries into (out_indices, out_data) at out_indptr[new_row]
+__global__ void mapped_scatter_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                      const float* __restrict__ data, const int32_t* __restrict__ col_map,
+                                      const int32_t* __restrict__ new_row, int32_t N, const int32_t* __restrict__ out_indptr,
+                                      int32_t* __restrict__ out_indices, float* __restrict__ out_data) {
+    const int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int r = warp; r < N; r += nwarps) {
+        const int nr = new_row[r];
+        if (nr < 0) continue;
+        const int s = indptr[r], e = indptr[r + 1];
+        int w = out_indptr[nr];
+        for (int o = s; o < e; o += 32) {
+            const bool in = o + lane < e;
+            const int c = in ? col_map[indices[o + lane]] : -1;
+            const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
+            if (c >= 0) {
+                const int dst = w + __popc(m & lt_mask);
+                out_indices[dst] = c;
+                out_data[dst] = data[o + lane];
+            }
+            w += __popc(m);
+        }
+    }
+}
+
+__global__ void row_keep_to_flag_kernel(const uint8_t* __restrict__ row_keep, int32_t N, int32_t* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) flag[i] = row_keep ? (row_keep[i] != 0) : 1;
+}
+
+__global__ void new_row_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ excl, int32_t N, int32_t* __restrict__ new_row) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) new_row[i] = flag[i] ? excl[i] : -1;
+}
+
 template <typename T>
 __global__ void narrow_indptr_kernel(const T* __restrict__ in, int64_t n, int32_t* __restrict__ out,
                                      int* __restrict__ err) {

@@ -133,20 +133,21 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
         if not (K.SOURCE in groupby_pairs.columns) | (K.TARGET in groupby_pairs.columns):
             raise AssertionError(f"{K.SOURCE} and {K.TARGET} must be in groupby_pairs")
         groupby_subset = np.union1d(groupby_pairs[K.SOURCE].unique(), groupby_pairs[K.TARGET].unique())
-    prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, groupby_subset=groupby_subset,
+    eng = get_engine(device)
+    prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, engine=eng, groupby_subset=groupby_subset,
                               use_raw=use_raw, layer=layer, verbose=verbose)
     _pre.assert_covered(_tables.resource_entities(res), prep.var_names, verbose=verbose)
     tables = _tables.build_resource_tables(res, prep.var_names)
-    # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`)
-    cols = np.searchsorted(prep.var_names, tables.entities)
-    X = prep.X[:, cols].tocsr()
-    X.sort_indices()
-    prep.X, prep.var_names = X, tables.entities
+    # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`): a column map for the
+    # staged matrix instead of SciPy fancy indexing + index sorting
+    pos = np.searchsorted(prep.var_names, tables.entities)
+    col_map = np.full(prep.n_genes_in, -1, dtype=np.int32)
+    col_map[prep.var_cols[pos]] = np.arange(len(tables.entities), dtype=np.int32)
     if verbose:
-        print(f"Generating ligand-receptor stats for {X.shape[0]} samples and {X.shape[1]} features")
+        print(f"Generating ligand-receptor stats for {prep.n_cells} samples and {len(tables.entities)} features")
     L = len(prep.categories)
-    eng = get_engine(device)
-    eng.set_matrix(X)
+    eng.commit_matrix(col_map, len(tables.entities), prep.n_cells)
+    prep.var_names = tables.entities
     eng.set_labels(prep.labels, L)
     means, stored, sizes = eng.observed()
     props = stored / sizes[:, None].astype(np.float64)
@@ -160,15 +161,22 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
     return PipelineState(prep, tables, eng, means, props, sizes, pair_mask, base=base)
 
 
+def _take_names(names, codes):
+    """names[codes] as a pandas string array: one vectorised take on the Index's backing array (10x faster
+    than fancy-indexing a NumPy unicode array and letting pandas re-infer every string)."""
+    idx = names if isinstance(names, pd.Index) else pd.Index(np.asarray(names))
+    return idx.array.take(np.asarray(codes, dtype=np.int64))
+
+
 def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFrame:
     """lr_res with the reference's column names / dtypes / order for the kept rows."""
     names, cats, tb = state.prep.var_names, state.prep.categories, state.tables
     return pd.DataFrame({
-        K.LIGAND: names[tri.lig_gene], K.LIGAND_COMPLEX: tb.ligand_complex[tri.inter],
+        K.LIGAND: _take_names(names, tri.lig_gene), K.LIGAND_COMPLEX: _take_names(tb.ligand_complex, tri.inter),
         K.LIGAND_MEANS: tri.ligand_means, K.LIGAND_PROPS: tri.ligand_props,
-        K.RECEPTOR: names[tri.rec_gene], K.RECEPTOR_COMPLEX: tb.receptor_complex[tri.inter],
+        K.RECEPTOR: _take_names(names, tri.rec_gene), K.RECEPTOR_COMPLEX: _take_names(tb.receptor_complex, tri.inter),
         K.RECEPTOR_MEANS: tri.receptor_means, K.RECEPTOR_PROPS: tri.receptor_props,
-        K.SOURCE: np.asarray(cats)[tri.src], K.TARGET: np.asarray(cats)[tri.tgt],
+        K.SOURCE: _take_names(cats, tri.src), K.TARGET: _take_names(cats, tri.tgt),
     })
 
 
@@ -208,7 +216,7 @@ def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, 
     lo = (n_perms * rank) // world
     hi = (n_perms * (rank + 1)) // world
     if perm_source == "reference":
-        perm_idx = reference_perm_indices(state.prep.X.shape[0], n_perms, seed)[lo:hi]
+        perm_idx = reference_perm_indices(state.prep.n_cells, n_perms, seed)[lo:hi]
         if order is None:
             order = "exact"
     elif perm_source == "philox":

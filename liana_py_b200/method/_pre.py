@@ -25,11 +25,15 @@ def _logg(msg, level="info", verbose=False):
 
 @dataclass
 class PreparedInput:
-    X: sparse.csr_matrix          # cells x genes, float32, canonical CSR
-    var_names: np.ndarray         # sorted gene names (str)
-    labels: np.ndarray            # int32 cluster code per cell
+    """What `prep_check_adata` hands on, without the matrix copies: the caller's matrix stays staged on the
+    device (`Engine.stage_matrix`) until `_pipeline.prepare` commits it with the resource's column map."""
+    var_names: np.ndarray         # sorted (alphabetical) names of the non-empty genes (str)
+    var_cols: np.ndarray          # column of the staged matrix holding each of var_names
+    n_genes_in: int               # columns of the staged matrix
+    labels: np.ndarray            # int32 cluster code per KEPT cell
     categories: np.ndarray        # cluster names, code order
     obs_index: pd.Index           # cell names kept
+    n_cells: int                  # kept cells
     mat_mean: float = 0.0         # mean over ALL entries of the prepared matrix (SingleCellSignalR, `_liana_pipe.py:139-140`)
 
 
@@ -74,8 +78,10 @@ def _make_unique(names: pd.Index) -> pd.Index:
     return pd.Index(out)
 
 
-def prepare_input(adata, groupby, min_cells, groupby_subset=None, use_raw=False, layer=None,
+def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_raw=False, layer=None,
                   complex_sep="_", verbose=False) -> PreparedInput:
+    """Same checks, order and exception types as `prep_check_adata` (`_pre.py:65-169`); the passes over the
+    matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU."""
     if hasattr(adata, "mod"):
         raise NotImplementedError("MuData input is outside the scope of the B200 permutation engine; "
                                   "convert to AnnData first.")
@@ -84,30 +90,15 @@ def prepare_input(adata, groupby, min_cells, groupby_subset=None, use_raw=False,
         var_names = pd.Index(adata.raw.var_names)
     else:
         var_names = pd.Index(adata.var_names)
-    X = X.astype(np.float32)
-    if not X.has_canonical_format:
+    if X.dtype != np.float32:
+        X = X.astype(np.float32)
+    if not X.has_canonical_format:          # duplicate entries would break "one entry per (cell, gene)"
         X = X.copy()
         X.sum_duplicates()
     var_names = _make_unique(var_names)
     obs = adata.obs
 
-    # empty features are removed (sum == 0), empty cells only reported (`_pre.py:122-133`)
-    col_sums = np.asarray(X.sum(axis=0)).ravel()
-    empty = col_sums == 0
-    if empty.any():
-        _logg(f"{int(empty.sum())} features of mat are empty, they will be removed.", level="warn", verbose=verbose)
-        keep = np.flatnonzero(~empty)
-        X = X[:, keep]
-        var_names = var_names[keep]
-    n_empty_cells = int((np.asarray(X.sum(axis=1)).ravel() == 0).sum())
-    if n_empty_cells:
-        _logg(f"{n_empty_cells} samples of mat are empty, they will be removed.", level="warn", verbose=verbose)
-    head = float(np.sum(X.data[:100]))
-    if head == np.floor(head):
-        _logg("Make sure that normalized counts are passed!", level="warn", verbose=verbose)
-    if np.any(~np.isfinite(X.data)):
-        raise ValueError("mat contains non finite values (nan or inf), please set them to 0 or remove them.")
-
+    # labels first (no matrix needed): which cells survive groupby_subset / min_cells (`_pre.py:143-162`)
     if groupby not in obs.columns:
         raise AssertionError(f"`{groupby}` not found in `adata.obs.columns`.")
     lab = obs[groupby]
@@ -125,26 +116,38 @@ def prepare_input(adata, groupby, min_cells, groupby_subset=None, use_raw=False,
         keep_mask = ~np.asarray(lab_sub.isin(low))
         rows = rows[keep_mask]
         lab_sub = lab_sub[keep_mask].cat.remove_unused_categories()
+    row_keep = None
+    if len(rows) != X.shape[0]:
+        row_keep = np.zeros(X.shape[0], dtype=np.uint8)
+        row_keep[rows] = 1
+
+    stats = engine.stage_matrix(X, row_keep)
+    # empty features are removed (sum == 0 over ALL cells), empty cells only reported (`_pre.py:122-133`)
+    empty = stats["col_sums"] == 0
+    if empty.any():
+        _logg(f"{int(empty.sum())} features of mat are empty, they will be removed.", level="warn", verbose=verbose)
+    if stats["n_empty_rows"]:
+        _logg(f"{stats['n_empty_rows']} samples of mat are empty, they will be removed.", level="warn", verbose=verbose)
+    head = float(np.sum(X.data[:100]))
+    if head == np.floor(head):
+        _logg("Make sure that normalized counts are passed!", level="warn", verbose=verbose)
+    if stats["n_nonfinite"]:
+        raise ValueError("mat contains non finite values (nan or inf), please set them to 0 or remove them.")
+    if low:
         _logg("The following cell identities were excluded: {0}".format(", ".join(map(str, low))),
               level="warn", verbose=verbose)
-    if len(rows) != X.shape[0]:
-        X = X[rows]
+    keep_cols = np.flatnonzero(~empty)
+    names = np.asarray(var_names, dtype=str)[keep_cols]
     if complex_sep is not None and verbose:
-        issues = [n for n in var_names if complex_sep in n]
+        issues = [n for n in names if complex_sep in n]
         if issues:
             _logg(f"{issues} contain `{complex_sep}`. Consider replacing those!", level="warn", verbose=True)
-    # genes in alphabetical order (`_pre.py:168`)
-    names = np.asarray(var_names, dtype=str)
-    order = np.argsort(names, kind="stable")
-    if not np.array_equal(order, np.arange(len(order))):
-        X = X[:, order]
-        names = names[order]
-    X = sparse.csr_matrix(X)
-    X.sort_indices()
-    n_all = X.shape[0] * X.shape[1]
-    mat_mean = float(X.data.sum(dtype=np.float64) / n_all) if n_all else 0.0
-    return PreparedInput(X=X, var_names=names, labels=np.asarray(lab_sub.cat.codes, dtype=np.int32),
-                         categories=np.asarray(lab_sub.cat.categories), obs_index=obs.index[rows], mat_mean=mat_mean)
+    order = np.argsort(names, kind="stable")            # genes in alphabetical order (`_pre.py:168`)
+    n_all = len(rows) * len(keep_cols)
+    return PreparedInput(var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
+                         labels=np.asarray(lab_sub.cat.codes, dtype=np.int32),
+                         categories=np.asarray(lab_sub.cat.categories), obs_index=obs.index[rows], n_cells=len(rows),
+                         mat_mean=float(stats["kept_total"] / n_all) if n_all else 0.0)
 
 
 def assert_covered(subset, superset, prop_missing_allowed=0.98, verbose=False):
