@@ -190,35 +190,34 @@ int build_csc(lrperm_engine* h) {
     StageTimer timer("build_csc");
     const int64_t nnz = h->nnz;
     const int32_t G = (int32_t)h->G;
-    CK(h->tmp_a.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nnz, 1)));   // column keys
-    CK(h->tmp_b.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));    // iota
-    CK(h->tmp_c.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(nnz, 1)));   // sorted keys
-    CK(h->tmp_d.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));    // sorted source index
-    CK(h->stage_out.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));  // row ids
+    const size_t n1 = (size_t)std::max<int64_t>(nnz, 1);
+    CK(h->tmp_a.ensure(sizeof(uint32_t) * n1));              // column keys
+    CK(h->tmp_c.ensure(sizeof(uint32_t) * n1));              // sorted keys (discarded)
+    CK(h->tmp_b.ensure(sizeof(unsigned long long) * n1));    // payload {cell, value bits}
     DevBuf& col_count = h->small_a;
     CK(col_count.ensure(sizeof(int32_t) * (size_t)(G + 1)));
     CK(cudaMemsetAsync(col_count.p, 0, sizeof(int32_t) * (size_t)(G + 1), h->stream));
-    CK(h->csc_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
+    CK(h->csc_pairs.ensure(sizeof(int2) * n1));
     h->h_csc_ptr.assign((size_t)G + 1, 0);
     if (nnz > 0) {
-        expand_rows_kernel<<<grid_for(h->N * 32, 256), 256, 0, h->stream>>>(h->indptr.as<int32_t>(), (int32_t)h->N,
-                                                                            h->stage_out.as<int32_t>());
-        CK_LAUNCH();
-        extract_cols_kernel<<<grid_for(nnz, 256), 256, 0, h->stream>>>(h->csr_pairs.as<int2>(), nnz, h->tmp_a.as<uint32_t>(),
-                                                                       h->tmp_b.as<int32_t>(), col_count.as<int32_t>());
+        size_t smem = sizeof(int32_t) * (size_t)G;
+        const int use_shared = smem <= 96 * 1024;
+        if (!use_shared) smem = 0;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(csc_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        csc_keys_kernel<<<h->sm_count * 4, 512, smem, h->stream>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), (int32_t)h->N, G,
+                                                                  h->tmp_a.as<uint32_t>(), h->tmp_b.as<unsigned long long>(), col_count.as<int32_t>(), use_shared);
         CK_LAUNCH();
         int end_bit = 1;
         while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
+        // stable LSD radix sort by column: cells stay ascending inside a gene; the sorted payload is csc_pairs
         size_t tmp_bytes = 0;
+        unsigned long long* sorted = reinterpret_cast<unsigned long long*>(h->csc_pairs.p);
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->tmp_a.as<uint32_t>(), h->tmp_c.as<uint32_t>(),
-                                           h->tmp_b.as<int32_t>(), h->tmp_d.as<int32_t>(), (int)nnz, 0, end_bit, h->stream));
+                                           h->tmp_b.as<unsigned long long>(), sorted, (int)nnz, 0, end_bit, h->stream));
         CK(h->sort_tmp.ensure(tmp_bytes));
         CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<uint32_t>(), h->tmp_c.as<uint32_t>(),
-                                           h->tmp_b.as<int32_t>(), h->tmp_d.as<int32_t>(), (int)nnz, 0, end_bit, h->stream));
+                                           h->tmp_b.as<unsigned long long>(), sorted, (int)nnz, 0, end_bit, h->stream));
         h->launches += 4;
-        gather_csc_kernel<<<grid_for(nnz, 256), 256, 0, h->stream>>>(h->tmp_d.as<int32_t>(), h->stage_out.as<int32_t>(),
-                                                                     h->csr_pairs.as<int2>(), nnz, h->csc_pairs.as<int2>());
-        CK_LAUNCH();
         std::vector<int32_t> cnt((size_t)G + 1, 0);
         CK(cudaMemcpyAsync(cnt.data(), col_count.p, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1077,9 +1076,19 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         if (n_perms < PB) PB = (int32_t)std::max<int64_t>(gran, ((n_perms + gran - 1) / gran) * gran);
         PB = ((PB + gran - 1) / gran) * gran;
         // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
-        const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (16LL << 20);
+        // (measured on B200, scripts/perf_tune.py: 32 MiB tiles beat 16 MiB by 2-3% on configs[1] and [2])
+        const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (32LL << 20);
         const int32_t tile_cells = (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / PB, 1024), std::max<int64_t>(N, 1));
-        const int32_t chunk_nnz = h->fast_chunk_nnz ? h->fast_chunk_nnz : 4096;
+        // entries per chunk: long chunks amortise the bin zeroing / partial-sum write-out, but the grid should
+        // still hold ~16 waves of (chunk x permutation group) warps; 4096 for configs[1], 16384 for configs[2]
+        int32_t chunk_nnz = h->fast_chunk_nnz;
+        if (!chunk_nnz) {
+            const int64_t groups = PB / (32 * Q);
+            const int64_t target_items = (int64_t)h->sm_count * 8 * 16;
+            int64_t c = h->nnz * groups / std::max<int64_t>(target_items, 1);
+            c = std::min<int64_t>(std::max<int64_t>(c, 4096), 16384);
+            chunk_nnz = (int32_t)((c + 1023) / 1024 * 1024);
+        }
         if ((rc = build_chunks(h, chunk_nnz, tile_cells))) return rc;
     } else {
         // enough (perm, cluster) warps for several waves, cube batch <= ~256 MB

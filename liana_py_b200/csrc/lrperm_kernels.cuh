@@ -208,36 +208,32 @@ __global__ void narrow_indptr_kernel(const T* __restrict__ in, int64_t n, int32_
     }
 }
 
-// row id of every stored entry (for the CSR -> CSC transpose)
-__global__ void expand_rows_kernel(const int32_t* __restrict__ indptr, int32_t N, int32_t* __restrict__ rows) {
+// CSR -> CSC transpose, step 1: per stored entry the sort key (column) and the payload {cell, value bits}
+// packed so that the sorted payload array IS the csc_pairs array; column histogram privatised in shared
+// memory (one global atomic per (CTA, column) instead of one per entry).
+__global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs, int32_t N, int32_t G,
+                                uint32_t* __restrict__ keys, unsigned long long* __restrict__ payload,
+                                int32_t* __restrict__ col_count, int use_shared) {
+    extern __shared__ int32_t hist_smem[];
+    int32_t* hist = use_shared ? hist_smem : col_count;      // G too large for shared memory: global atomics
+    if (use_shared) for (int g = threadIdx.x; g < G; g += blockDim.x) hist[g] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp; r < N; r += nwarps) {
         const int s = indptr[r], e = indptr[r + 1];
-        for (int o = s + lane_id(); o < e; o += 32) rows[o] = r;
+        for (int o = s + lane; o < e; o += 32) {
+            const int2 pr = pairs[o];
+            keys[o] = (uint32_t)pr.x;
+            payload[o] = ((unsigned long long)(uint32_t)pr.y << 32) | (uint32_t)r;
+            atomicAdd(&hist[pr.x], 1);
+        }
     }
-}
-
-__global__ void extract_cols_kernel(const int2* __restrict__ pairs, int64_t nnz, uint32_t* __restrict__ cols,
-                                    int32_t* __restrict__ iota, int32_t* __restrict__ col_count) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nnz; i += stride) {
-        const int c = pairs[i].x;
-        cols[i] = (uint32_t)c;
-        iota[i] = (int32_t)i;
-        atomicAdd(&col_count[c], 1);
-    }
-}
-
-__global__ void gather_csc_kernel(const int32_t* __restrict__ sorted_src, const int32_t* __restrict__ rows,
-                                  const int2* __restrict__ csr_pairs, int64_t nnz, int2* __restrict__ csc_pairs) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < nnz; i += stride) {
-        const int32_t s = sorted_src[i];
-        csc_pairs[i] = make_int2(rows[s], csr_pairs[s].y);
-    }
+    __syncthreads();
+    if (use_shared)
+        for (int g = threadIdx.x; g < G; g += blockDim.x)
+            if (hist[g]) atomicAdd(&col_count[g], hist[g]);
 }
 
 // first stored entry of gene g whose cell id is >= t * tile_cells (CSC cells ascend within a gene)
