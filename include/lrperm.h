@@ -144,7 +144,12 @@ int lrperm_run(lrperm_engine *h, int64_t n_perms, int64_t perm_offset, uint64_t 
                uint32_t *counts_cpdb, uint32_t *counts_gmean, int counts_on_device,
                float *cube_out, int cube_on_device);
 
-/* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32). */
+/* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32), i.e. the array
+ * that reproduces a PHILOX run when passed back as LRPERM_PERMS_INDEX.  The device bijection rho_p (keyed by
+ * seed and global permutation id, include/lrperm_philox.h) acts on CLUSTER-SORTED positions: position
+ * order[k] (k-th position in stable label order) receives cell rho_p(k), so the label of a cell follows from
+ * k = rho_p^-1(cell) and the cluster boundaries alone.  Requires the labels to be set; n_cells must equal
+ * the engine's cell count. */
 int lrperm_philox_perms(lrperm_engine *h, int64_t n_cells, int64_t n_perms, int64_t perm_offset,
                         uint64_t seed, int32_t *out, int out_on_device);
 

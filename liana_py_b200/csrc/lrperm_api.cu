@@ -90,7 +90,8 @@ struct lrperm_engine {
     // labels
     int32_t L = 0;
     bool have_labels = false;
-    DevBuf labels32, labels8, labels8s, order, cl_start, inv_n;
+    DevBuf labels32, labels8, labels8s, order, rank, bucket_cluster, cl_start, inv_n;
+    int32_t n_buckets = 0, bucket_shift = 0;      // coarse position -> cluster table of slab_philox_kernel
     int32_t labels8s_scale = 0;          // scale the labels8s table currently holds (0 = stale)
     std::vector<int32_t> h_cl_start;
 
@@ -442,6 +443,7 @@ struct RunArgs {
 //   A: wait s0, main(0), rec m0  | wait s1, main(1), rec m1                | wait s2, wait f0, main(2) ...
 int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, const uint8_t* slab_labels) {
     const int64_t N = h->N;
+    const int32_t label_scale = h->fast_variant == 2 ? Q / 2 : 1;
     const int32_t G = (int32_t)h->G, L = h->L;
     const int32_t PP = PB;
     const int64_t n_batches = (a.n_perms + PB - 1) / PB;
@@ -482,7 +484,9 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         if (ps.philox) {
             const int cells_per_block = 128;
             dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
-            slab_philox_kernel<<<grd, 128, 0, sB>>>(ps, slab_labels, (int32_t)N, pb, slab, PB, cells_per_block);
+            const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
+            slab_philox_kernel<<<grd, 128, tab_smem, sB>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
+                                                           h->bucket_shift, L, label_scale, (int32_t)N, pb, slab, PB, cells_per_block);
         } else {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
             if (a.perm_idx_on_device) ps.idx = src;
@@ -613,7 +617,7 @@ void lrperm_destroy(lrperm_engine* h) {
     DeviceGuard guard(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->st_indptr, &h->st_indices, &h->st_data, &h->st_row_keep, &h->st_small,
-                      &h->labels32, &h->labels8, &h->labels8s, &h->order,
+                      &h->labels32, &h->labels8, &h->labels8s, &h->order, &h->rank, &h->bucket_cluster,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
                       &h->chunks, &h->gene_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b})
@@ -889,6 +893,22 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
     for (int32_t c = 0; c < n_clusters; ++c) inv[(size_t)c] = (float)(1.0 / (double)(start[(size_t)c + 1] - start[(size_t)c]));
     std::vector<uint8_t> lab8((size_t)N);
     for (int64_t j = 0; j < N; ++j) lab8[(size_t)j] = (uint8_t)(lab[(size_t)j] & 0xff);
+    // PHILOX permutations live on cluster-sorted positions: rank[j] = index of position j in `order`, and a
+    // coarse table (<= 4096 buckets of 2^shift sorted positions) gives the cluster of a sorted position
+    std::vector<int32_t> rank((size_t)N);
+    for (int64_t k = 0; k < N; ++k) rank[(size_t)order[(size_t)k]] = (int32_t)k;
+    int32_t shift = 0;
+    while (((N - 1) >> shift) >= 4096) ++shift;
+    const int32_t n_buckets = (int32_t)(((N > 0 ? N - 1 : 0) >> shift) + 1);
+    std::vector<uint8_t> bucket((size_t)n_buckets);
+    {
+        int32_t c = 0;
+        for (int32_t b = 0; b < n_buckets; ++b) {
+            const int64_t k0 = (int64_t)b << shift;
+            while (c + 1 < n_clusters && k0 >= start[(size_t)c + 1]) ++c;
+            bucket[(size_t)b] = (uint8_t)(c & 0xff);
+        }
+    }
 
     h->L = n_clusters;
     h->labels8s_scale = 0;
@@ -897,6 +917,10 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
     if ((rc = upload(h, h->labels32, lab.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
     if ((rc = upload(h, h->labels8, lab8.data(), (size_t)N, 0))) return rc;
     if ((rc = upload(h, h->order, order.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
+    if ((rc = upload(h, h->rank, rank.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
+    if ((rc = upload(h, h->bucket_cluster, bucket.data(), (size_t)n_buckets, 0))) return rc;
+    h->n_buckets = n_buckets;
+    h->bucket_shift = shift;
     if ((rc = upload(h, h->cl_start, start.data(), sizeof(int32_t) * ((size_t)n_clusters + 1), 0))) return rc;
     if ((rc = upload(h, h->inv_n, inv.data(), sizeof(float) * (size_t)n_clusters, 0))) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -1020,13 +1044,16 @@ int lrperm_philox_perms(lrperm_engine* h, int64_t n_cells, int64_t n_perms, int6
     if (!h) return LRPERM_ERR_INVALID;
     DeviceGuard guard(h->device);
     if (n_cells <= 0 || n_cells >= 0x7fffffffLL || n_perms < 0 || !out) return h->fail(LRPERM_ERR_INVALID, "lrperm_philox_perms: bad arguments");
+    if (!h->have_labels || n_cells != h->N)
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_philox_perms: set the matrix and labels first (the permutations are defined on "
+                       "cluster-sorted positions) and pass n_cells == the engine's cell count");
     if (n_perms == 0) return LRPERM_OK;
     if (n_perms > 65535) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_philox_perms: at most 65535 permutations per call");
     const size_t bytes = sizeof(int32_t) * (size_t)n_cells * (size_t)n_perms;
     int32_t* dst = out;
     if (!out_on_device) { CK(h->stage_out.ensure(bytes)); dst = h->stage_out.as<int32_t>(); }
     dim3 grd(grid_for(n_cells, 256, 1024), (unsigned)n_perms);
-    philox_perms_kernel<<<grd, 256, 0, h->stream>>>(seed, perm_offset, (int32_t)n_cells, (int32_t)n_perms, dst);
+    philox_perms_kernel<<<grd, 256, 0, h->stream>>>(seed, perm_offset, (int32_t)n_cells, (int32_t)n_perms, h->rank.as<int32_t>(), dst);
     CK_LAUNCH();
     if (!out_on_device) CK(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1107,6 +1134,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     if (scores & LRPERM_SCORE_GMEAN) CK(cudaMemsetAsync(h->counts_g.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
 
     const uint8_t* slab_labels = h->labels8.as<uint8_t>();
+    const int32_t label_scale = (order_mode == LRPERM_ORDER_FAST && h->fast_variant == 2) ? Q / 2 : 1;
     if (order_mode == LRPERM_ORDER_FAST && h->fast_variant == 2) {
         const int32_t scale = Q / 2;
         if (h->labels8s_scale != scale) {
@@ -1162,7 +1190,9 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
             if (ps.philox) {
                 const int cells_per_block = 128;
                 dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
-                slab_philox_kernel<<<grd, 128, 0, h->stream>>>(ps, slab_labels, (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
+                const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
+                slab_philox_kernel<<<grd, 128, tab_smem, h->stream>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
+                                                                      h->bucket_shift, L, label_scale, (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
             } else {
                 dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
                 slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, slab_labels, (int32_t)N, pb, h->slab.as<uint8_t>(), PB);

@@ -375,11 +375,14 @@ exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ 
     auto fetch_meta = [&](int k, int& rs, int& re) {
         rs = 0; re = 0;
         if (k < k_end) {
-            const int j = order[k];
             int cell;
-            if (ps.identity) cell = j;
-            else if (ps.philox) cell = (int)lrperm_bij_forward(&bij, (uint32_t)j);
-            else cell = perm_lookup(ps, p, N, j);
+            // PHILOX: the bijection is defined on cluster-sorted positions (position order[k] holds cell
+            // rho_p(k)), so neither `order` nor a label gather is needed; see slab_philox_kernel
+            if (ps.philox) cell = (int)lrperm_bij_forward(&bij, (uint32_t)k);
+            else {
+                const int j = order[k];
+                cell = ps.identity ? j : perm_lookup(ps, p, N, j);
+            }
             rs = indptr[cell];
             re = indptr[cell + 1];
         }
@@ -456,10 +459,20 @@ __global__ void slab_from_index_kernel(PermSource ps, const uint8_t* __restrict_
     }
 }
 
-__global__ void slab_philox_kernel(PermSource ps, const uint8_t* __restrict__ labels8, int32_t N,
-                                   int32_t n_perms_batch, uint8_t* __restrict__ slab, int32_t PB,
-                                   int32_t cells_per_block) {
+__global__ void slab_philox_kernel(PermSource ps, const int32_t* __restrict__ cl_start, const uint8_t* __restrict__ bucket_cluster,
+                                   int32_t n_buckets, int32_t bucket_shift, int32_t L, int32_t label_scale, int32_t N,
+                                   int32_t n_perms_batch, uint8_t* __restrict__ slab, int32_t PB, int32_t cells_per_block) {
     // thread = one permutation of the batch (key derived once); loop over a tile of cells.
+    // PHILOX permutations are defined on CLUSTER-SORTED positions: pi_p(order[k]) = rho_p(k).  The label of
+    // cell i is therefore the cluster whose range [cl_start[c], cl_start[c+1]) holds k = rho_p^-1(i): a
+    // lookup in two small shared-memory tables instead of a random gather from the N-entry label array
+    // (32 L1 wavefronts per warp, which also competed with the shared-memory-bound main kernel it overlaps).
+    extern __shared__ int32_t s_tab[];
+    int32_t* s_start = s_tab;                                             // [L + 1]
+    uint8_t* s_bucket = reinterpret_cast<uint8_t*>(s_tab + L + 1);        // [n_buckets]
+    for (int i = threadIdx.x; i <= L; i += blockDim.x) s_start[i] = cl_start[i];
+    for (int i = threadIdx.x; i < n_buckets; i += blockDim.x) s_bucket[i] = bucket_cluster[i];
+    __syncthreads();
     const int p = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = p < n_perms_batch;
     lrperm_bij_t bij = lrperm_bij_init(ps.seed, (uint64_t)(ps.perm_id0 + (active ? p : 0)), (uint32_t)N);
@@ -467,24 +480,27 @@ __global__ void slab_philox_kernel(PermSource ps, const uint8_t* __restrict__ la
     const int i1 = min(N, i0 + cells_per_block);
     if (!active) return;
     for (int i = i0; i < i1; ++i) {
-        const uint32_t j = lrperm_bij_inverse(&bij, (uint32_t)i);
-        slab[(int64_t)i * PB + p] = labels8[j];
+        const int k = (int)lrperm_bij_inverse(&bij, (uint32_t)i);
+        int c = s_bucket[k >> bucket_shift];                              // cluster of the bucket's first position
+        while (k >= s_start[c + 1]) ++c;                                  // a bucket rarely spans a boundary
+        slab[(int64_t)i * PB + p] = (uint8_t)(c * label_scale);
     }
+}
+
+__global__ void philox_perms_kernel(uint64_t seed, int64_t perm_id0, int32_t N, int32_t n_perms,
+                                    const int32_t* __restrict__ rank, int32_t* __restrict__ out) {
+    // out[p][j] = cell placed at position j = rho_p(rank[j]), rank[j] = index of j in cluster-sorted order
+    const int p = blockIdx.y;
+    if (p >= n_perms) return;
+    lrperm_bij_t bij = lrperm_bij_init(seed, (uint64_t)(perm_id0 + p), (uint32_t)N);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
+        out[(int64_t)p * N + j] = (int32_t)lrperm_bij_forward(&bij, (uint32_t)rank[j]);
 }
 
 // slab label bytes for the v2 fast kernel: label * Q/2 (so that byte << 8 == label * Q * 128)
 __global__ void scale_labels_kernel(const uint8_t* __restrict__ labels8, int32_t N, int32_t scale, uint8_t* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) out[i] = (uint8_t)(labels8[i] * scale);
-}
-
-__global__ void philox_perms_kernel(uint64_t seed, int64_t perm_id0, int32_t N, int32_t n_perms,
-                                    int32_t* __restrict__ out) {
-    const int p = blockIdx.y;
-    if (p >= n_perms) return;
-    lrperm_bij_t bij = lrperm_bij_init(seed, (uint64_t)(perm_id0 + p), (uint32_t)N);
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
-        out[(int64_t)p * N + j] = (int32_t)lrperm_bij_forward(&bij, (uint32_t)j);
 }
 
 // ------------------------------------------------------------------------------------------

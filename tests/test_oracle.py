@@ -99,3 +99,55 @@ def test_philox_positions_are_uniform():
     inv = np.argsort(perms, axis=1)
     adj = (np.abs(inv[:, 0] - inv[:, 1]) == 1).mean()
     assert adj < 4.0 / n + 0.02
+
+
+def test_philox_small_domain_pairs_are_uniform():
+    # N = 6: the joint position of any two cells is uniform over the 30 ordered pairs of distinct positions.
+    # (A Feistel network only reaches even permutations of its power-of-two domain, so the distribution over
+    # ALL n! permutations of a tiny domain is not uniform; the permutation null only needs the label-level,
+    # i.e. low-order, statistics tested here and in test_philox_label_mixing_matches_hypergeometric.)
+    n, P = 6, 30 * 1000
+    perms = c_oracle.philox_perms(n, P, 0, 2024)
+    inv = np.argsort(perms, axis=1)                         # inv[p][cell] = position
+    for a_, b_ in ((0, 1), (2, 5), (4, 3)):
+        table = np.zeros((n, n))
+        np.add.at(table, (inv[:, a_], inv[:, b_]), 1)
+        off = table[~np.eye(n, dtype=bool)]
+        assert np.all(np.diag(table) == 0)
+        chi2 = ((off - P / 30) ** 2 / (P / 30)).sum()
+        assert chi2 < 75.0, (a_, b_, chi2)                  # 29 dof, mean 29, sd 7.6 -> 6 sd
+
+
+def test_philox_consecutive_ids_are_independent():
+    # where cell 0 sits under permutation id p vs id p+1 (and under seed s vs s+1): 7 x 7 contingency tables
+    n, P = 7, 49 * 400
+    a = c_oracle.philox_perms(n, P + 1, 0, 7)
+    pos = np.argmax(a == 0, axis=1)
+    table = np.zeros((n, n))
+    np.add.at(table, (pos[:-1], pos[1:]), 1)
+    chi2 = ((table - P / 49) ** 2 / (P / 49)).sum()
+    assert chi2 < 110.0, chi2                   # 48 dof (36 for independence + margins), mean ~48, sd ~10
+    b = c_oracle.philox_perms(n, P, 0, 8)
+    posb = np.argmax(b == 0, axis=1)
+    table = np.zeros((n, n))
+    np.add.at(table, (pos[:P], posb), 1)
+    chi2 = ((table - P / 49) ** 2 / (P / 49)).sum()
+    assert chi2 < 110.0, chi2
+
+
+def test_philox_label_mixing_matches_hypergeometric():
+    # N cells in 3 clusters of unequal size: the number of cluster-a cells that receive label b under a random
+    # permutation is hypergeometric; check mean and variance over many permutations at a non-power-of-two N
+    for n, sizes, P in ((3001, [1700, 1000, 301], 1500), (64, [30, 20, 14], 4000), (17, [6, 6, 5], 4000)):
+        sizes = np.array(sizes)
+        lab = np.repeat(np.arange(3), sizes)
+        perms = c_oracle.philox_perms(n, P, 5, 31337)            # perms[p][j] = cell at position j
+        for a in range(3):
+            for b in range(3):
+                # cells of original cluster a sitting on positions labelled b
+                x = (lab[perms][:, lab == b] == a).sum(axis=1)
+                K, m = sizes[a], sizes[b]
+                mean = m * K / n
+                var = m * (K / n) * (1 - K / n) * (n - m) / (n - 1)
+                assert abs(x.mean() - mean) < 5 * np.sqrt(var / P), (n, a, b, x.mean(), mean)
+                assert 0.85 < x.var() / var < 1.18, (n, a, b, x.var(), var)
