@@ -128,7 +128,7 @@ class Method(MethodMeta):
                                perm_source, order, gmean_mode, dist)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
-        liana_res = liana_res.sort_values(by=orderby, ascending=ascending)
+        liana_res = PL.materialise_names(state, liana_res.sort_values(by=orderby, ascending=ascending))
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
@@ -140,8 +140,7 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
 
     In a consensus (`null_cache` given) every permutation method named in `permuting_methods` is counted
     from ONE pass over the permutations, and the counts are cached for the methods that follow."""
-    tri = _tables.resolve_triples(state.tables, state.means, state.props, expr_prop, state.pair_mask, return_all_lrs)
-    lr_res = PL.base_frame(state, tri)
+    tri, lr_res = state.resolved(expr_prop, return_all_lrs)       # shared by the methods of a consensus
     if method.add_cols:
         lr_res = PL.add_method_columns(state, tri, lr_res, method.add_cols)
         lr_res = lr_res[sorted(lr_res.columns)]            # `np.union1d` of the column sets (`_liana_pipe.py:385`)
@@ -167,7 +166,7 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
             null = NullCounts(out[method.engine_score], n_perms)
     magnitude, specificity = method.fun(x, null) if method.permute else method.fun(x)
     spec_name = method.specificity if (not method.permute or n_perms is not None) else None
-    lr_res = lr_res.copy()
+    lr_res = (lr_res[K.PRIMARY] if aggregate_flag else lr_res).copy()     # the cached base frame stays untouched
     if return_all_lrs:
         lr_res[K.LRS_TO_KEEP] = kept
     if method.magnitude is not None:

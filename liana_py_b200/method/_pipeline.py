@@ -55,6 +55,23 @@ def reference_perm_indices(n_cells: int, n_perms: int, seed: int) -> np.ndarray:
     return out
 
 
+_TABLE_CACHE = {}
+
+
+def _cached_tables(res: pd.DataFrame, var_names: np.ndarray):
+    """(ResourceTables, all resource entities) memoised on (resource content, gene names): `by_sample` and
+    repeated calls on the same AnnData rebuild nothing (4.6k interactions of Python string handling otherwise)."""
+    key = (int(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).sum()),
+           len(var_names), hash(np.asarray(var_names, dtype=str).tobytes()))
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        if len(_TABLE_CACHE) >= 8:
+            _TABLE_CACHE.pop(next(iter(_TABLE_CACHE)))
+        hit = (_tables.build_resource_tables(res, var_names), _tables.resource_entities(res))
+        _TABLE_CACHE[key] = hit
+    return hit
+
+
 class PipelineState:
     """Everything computed before any method-specific scoring (shared by rank_aggregate methods).
 
@@ -68,6 +85,16 @@ class PipelineState:
         self.base = float(base)
         self._moments = None
         self._cache = {}
+
+    def resolved(self, expr_prop, return_all_lrs):
+        """(ResolvedTriples, base lr_res frame) for one filter setting; every method of a consensus filters with
+        the same `complex_cols` and `expr_prop`, so the tables are built once (the reference re-runs
+        `filter_reassemble_complexes` per method, `_liana_pipe.py:378-382`).  Callers must not mutate the frame."""
+        key = ("tri", float(expr_prop), bool(return_all_lrs))
+        if key not in self._cache:
+            tri = _tables.resolve_triples(self.tables, self.means, self.props, expr_prop, self.pair_mask, return_all_lrs)
+            self._cache[key] = (tri, base_frame(self, tri))
+        return self._cache[key]
 
     def _get_moments(self):
         if self._moments is None:
@@ -136,8 +163,8 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
     eng = get_engine(device)
     prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, engine=eng, groupby_subset=groupby_subset,
                               use_raw=use_raw, layer=layer, verbose=verbose)
-    _pre.assert_covered(_tables.resource_entities(res), prep.var_names, verbose=verbose)
-    tables = _tables.build_resource_tables(res, prep.var_names)
+    tables, all_entities = _cached_tables(res, prep.var_names)
+    _pre.assert_covered(all_entities, prep.var_names, verbose=verbose)
     # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`): a column map for the
     # staged matrix instead of SciPy fancy indexing + index sorting
     pos = np.searchsorted(prep.var_names, tables.entities)
@@ -169,15 +196,27 @@ def _take_names(names, codes):
 
 
 def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFrame:
-    """lr_res with the reference's column names / dtypes / order for the kept rows."""
-    names, cats, tb = state.prep.var_names, state.prep.categories, state.tables
+    """lr_res with the reference's column names / dtypes / order for the kept rows.  The six name columns hold
+    int32 CODES until `materialise_names` runs on the final (filtered, sorted) frame: selecting, sorting and
+    concatenating integer columns is several times cheaper than moving strings around."""
     return pd.DataFrame({
-        K.LIGAND: _take_names(names, tri.lig_gene), K.LIGAND_COMPLEX: _take_names(tb.ligand_complex, tri.inter),
+        K.LIGAND: tri.lig_gene, K.LIGAND_COMPLEX: tri.inter,
         K.LIGAND_MEANS: tri.ligand_means, K.LIGAND_PROPS: tri.ligand_props,
-        K.RECEPTOR: _take_names(names, tri.rec_gene), K.RECEPTOR_COMPLEX: _take_names(tb.receptor_complex, tri.inter),
+        K.RECEPTOR: tri.rec_gene, K.RECEPTOR_COMPLEX: tri.inter,
         K.RECEPTOR_MEANS: tri.receptor_means, K.RECEPTOR_PROPS: tri.receptor_props,
-        K.SOURCE: _take_names(cats, tri.src), K.TARGET: _take_names(cats, tri.tgt),
+        K.SOURCE: tri.src, K.TARGET: tri.tgt,
     })
+
+
+def materialise_names(state: PipelineState, frame: pd.DataFrame) -> pd.DataFrame:
+    """Replace the code columns of `base_frame` by the gene / complex / cluster names (in place, same order)."""
+    names, cats, tb = state.prep.var_names, state.prep.categories, state.tables
+    lookup = {K.LIGAND: names, K.RECEPTOR: names, K.LIGAND_COMPLEX: tb.ligand_complex,
+              K.RECEPTOR_COMPLEX: tb.receptor_complex, K.SOURCE: cats, K.TARGET: cats}
+    for col, table in lookup.items():
+        if col in frame.columns:
+            frame[col] = _take_names(table, frame[col].values)
+    return frame
 
 
 def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame: pd.DataFrame, add_cols) -> pd.DataFrame:

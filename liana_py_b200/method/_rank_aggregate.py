@@ -67,8 +67,8 @@ class AggregateClass(MethodMeta):
             lrs[method.method_name] = run_method(state, meta, expr_prop, n_perms, seed, return_all_lrs, perm_source,
                                                  order, gmean_mode, dist, aggregate_flag=True, null_cache=null_cache,
                                                  permuting_methods=[getattr(m, "_method", m) for m in self.methods])
-        if consensus_opts is False:
-            return lrs                                          # per-method results as they are (`:220-221`)
+        if consensus_opts is False:                             # per-method results as they are (`:220-221`)
+            return {k: PL.materialise_names(state, v) for k, v in lrs.items()}
         # the reference outer-merges the per-method frames on the key columns (`_aggregate.py:39-49`);
         # they all hold the same rows in the same order here, so the join is a column concatenation
         frames = list(lrs.values())
@@ -81,6 +81,7 @@ class AggregateClass(MethodMeta):
         orderby = self.magnitude if self.magnitude in lr_res.columns else self.specificity
         if orderby in lr_res.columns:
             lr_res = lr_res.sort_values(by=orderby, ascending=True)   # `_liana_pipe.py:246-250`
+        lr_res = PL.materialise_names(state, lr_res)
         if inplace:
             adata.uns[key_added] = lr_res
         return None if inplace else lr_res
