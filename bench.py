@@ -385,6 +385,8 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: NCCL's "NCCL version ..." banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
