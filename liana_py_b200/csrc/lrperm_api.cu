@@ -306,7 +306,7 @@ int launch_exact_w(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cu
 
 int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube, int32_t PP) {
     const int32_t G = (int32_t)h->G;
-    const int Gpad = (G + 31) & ~31;
+    const int Gpad = ((G + 31) & ~31) + 32;      // + one dummy slot per lane (see exact_means_kernel)
     const size_t per_warp = (size_t)Gpad * sizeof(float);
     // warps per CTA: maximise resident warps per SM under the shared-memory budget
     // (1 KB per CTA is reserved by the driver) and the 2048-thread limit
@@ -317,7 +317,7 @@ int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube
         if (per_warp * w > h->smem_optin) continue;
         int ctas = (int)std::min<size_t>(sm_budget / cta, 32);
         ctas = std::min(ctas, 2048 / (w * 32));
-        const int res = std::min(ctas * w, 48);       // ~60 registers/thread caps residency near 32-40 warps
+        const int res = std::min(ctas * w, 28);       // 72 registers/thread (launch bounds) cap residency at 28 warps
         if (res > best_res) { best_res = res; best_w = w; }
     }
     if (best_w == 0)

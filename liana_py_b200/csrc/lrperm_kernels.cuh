@@ -348,8 +348,10 @@ __device__ __forceinline__ int2 ld_stream_int2(const int2* p) {
 // multiply and add roundings - bit-identical to scipy's (X * (1/n)).sum(0) on the permuted rows.
 // Lanes are spread over the stored entries of one row (distinct columns -> no intra-row hazard).
 // ------------------------------------------------------------------------------------------
+// (min CTAs per SM so that ~28 warps stay resident: the register allocator must not trade occupancy -
+// rows in flight - for a few registers)
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (28 / WARPS) > 0 ? (28 / WARPS) : 1)
 exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
                    const int32_t* __restrict__ order, const int32_t* __restrict__ cl_start,
                    const float* __restrict__ inv_n, PermSource ps,
@@ -362,10 +364,13 @@ exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ 
     if (item >= (int64_t)n_perms_batch * L) return;
     const int c = (int)(item / n_perms_batch);
     const int p = (int)(item - (int64_t)c * n_perms_batch);
-    const int Gpad = (G + 31) & ~31;
+    // accumulator row of the warp: G columns (padded to 32) + 32 dummy slots, one per lane, that absorb the
+    // "+ 0.0f" of lanes past the end of a row, so the accumulate step has no divergent branch
+    const int Gpad = ((G + 31) & ~31) + 32;
     float* acc = smem + (size_t)warp * Gpad;
     for (int g = lane; g < Gpad; g += 32) acc[g] = 0.0f;
     __syncwarp();
+    const int dummy_col = Gpad - 32 + lane;
 
     const float inv = inv_n[c];
     const int k_begin = cl_start[c], k_end = cl_start[c + 1];
@@ -390,25 +395,40 @@ exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ 
 
     // Row pipeline: the first U*32 stored entries of row r+1 are loaded into registers while row r is
     // being accumulated, so every warp keeps ~1.3 KB of gathered row data in flight (HBM latency).
-    constexpr int U = 8;
+    constexpr int U = 6;
     auto prefetch = [&](int s, int e, int2 (&q)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int o = s + lane + 32 * u;
-            q[u] = (o < e) ? ld_stream_int2(pairs + o) : make_int2(-1, 0);
+            q[u] = (o < e) ? ld_stream_int2(pairs + o) : make_int2(dummy_col, 0);
         }
     };
+    // Accumulate one row.  The columns of a row are distinct, so its U groups of 32 entries are independent:
+    // all loads first, then the adds, then the stores - one shared-memory round trip per row, not per group.
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
+    auto lds = [](uint32_t a) { float x; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a)); return x; };
+    auto sts = [](uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); };
     auto apply = [&](int s, int e, const int2 (&q)[U]) {
+        const int n = e - s;                                   // warp-uniform
+        float x[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (q[u].x >= 0) acc[q[u].x] = __fadd_rn(acc[q[u].x], __fmul_rn(__int_as_float(q[u].y), inv));
-        for (int o = s + lane + 32 * U; o < e; o += 128) {     // rows longer than U*32 entries
+            if (u * 32 < n) x[u] = lds(acc_s + (uint32_t)q[u].x * 4u);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (u * 32 < n) x[u] = __fadd_rn(x[u], __fmul_rn(__int_as_float(q[u].y), inv));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (u * 32 < n) sts(acc_s + (uint32_t)q[u].x * 4u, x[u]);
+        for (int o = s + 32 * U; o < e; o += 128) {            // rows longer than U*32 entries (uniform loop)
             int2 t[4];
+            float y[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) t[u] = (o + 32 * u < e) ? ld_stream_int2(pairs + o + 32 * u) : make_int2(-1, 0);
+            for (int u = 0; u < 4; ++u) t[u] = (o + lane + 32 * u < e) ? ld_stream_int2(pairs + o + lane + 32 * u) : make_int2(dummy_col, 0);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (t[u].x >= 0) acc[t[u].x] = __fadd_rn(acc[t[u].x], __fmul_rn(__int_as_float(t[u].y), inv));
+            for (int u = 0; u < 4; ++u) y[u] = lds(acc_s + (uint32_t)t[u].x * 4u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sts(acc_s + (uint32_t)t[u].x * 4u, __fadd_rn(y[u], __fmul_rn(__int_as_float(t[u].y), inv)));
         }
         __syncwarp();   // the next row may touch the same columns from other lanes
     };
