@@ -82,17 +82,20 @@ class MethodMeta:
         sizes = [int((sample_col == s).sum()) for s in samples]
         mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
         results = {}
+        sharded = dist is not None and dist.world_size > 1
         for i in mine:
             temp = adata[sample_col == samples[i]].copy()
-            results[samples[i]] = self.__call__(temp, inplace=False, verbose=full_verbose, **kwargs)
-        if dist is not None and dist.world_size > 1:
+            # across ranks the frames travel with integer code columns + their small name tables (a third of
+            # the bytes of the string frames) and are turned into names after the gather
+            results[samples[i]] = self.__call__(temp, inplace=False, verbose=full_verbose, _names=not sharded, **kwargs)
+        if sharded:
             merged = {}
             for part in dist.all_gather_objects(results):
                 merged.update(part)
-            results = merged
+            results = {s: PL.materialise_names(tables, frame) for s, (frame, tables) in merged.items()}
         frames = []
         for s in samples:                      # sample-category order, like the reference's concat
-            df = results[s].copy()
+            df = results[s]
             df.insert(0, sample_key, s)
             frames.append(df)
         liana_res = pd.concat(frames, ignore_index=True)
@@ -119,7 +122,7 @@ class Method(MethodMeta):
                  resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
                  *, perm_source: str = "philox", order: Optional[str] = None, gmean_mode: str = "product",
-                 device: int = 0, dist: Optional[DistContext] = None):
+                 device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
         if supp_columns:
             raise NotImplementedError("supp_columns are outside the scope of the permutation engine")
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
@@ -128,7 +131,10 @@ class Method(MethodMeta):
                                perm_source, order, gmean_mode, dist)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
-        liana_res = PL.materialise_names(state, liana_res.sort_values(by=orderby, ascending=ascending))
+        liana_res = liana_res.sort_values(by=orderby, ascending=ascending)
+        if not _names:                          # by_sample across ranks: (code frame, name tables), see by_sample
+            return liana_res, PL.name_tables(state)
+        liana_res = PL.materialise_names(state, liana_res)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res

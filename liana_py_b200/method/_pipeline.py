@@ -208,11 +208,16 @@ def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFra
     })
 
 
-def materialise_names(state: PipelineState, frame: pd.DataFrame) -> pd.DataFrame:
-    """Replace the code columns of `base_frame` by the gene / complex / cluster names (in place, same order)."""
+def name_tables(state: PipelineState) -> dict:
+    """The small lookup tables `materialise_names` needs (what travels with a code frame between ranks)."""
     names, cats, tb = state.prep.var_names, state.prep.categories, state.tables
-    lookup = {K.LIGAND: names, K.RECEPTOR: names, K.LIGAND_COMPLEX: tb.ligand_complex,
-              K.RECEPTOR_COMPLEX: tb.receptor_complex, K.SOURCE: cats, K.TARGET: cats}
+    return {K.LIGAND: names, K.RECEPTOR: names, K.LIGAND_COMPLEX: tb.ligand_complex,
+            K.RECEPTOR_COMPLEX: tb.receptor_complex, K.SOURCE: cats, K.TARGET: cats}
+
+
+def materialise_names(state_or_tables, frame: pd.DataFrame) -> pd.DataFrame:
+    """Replace the code columns of `base_frame` by the gene / complex / cluster names (in place, same order)."""
+    lookup = state_or_tables if isinstance(state_or_tables, dict) else name_tables(state_or_tables)
     for col, table in lookup.items():
         if col in frame.columns:
             frame[col] = _take_names(table, frame[col].values)

@@ -53,7 +53,7 @@ class AggregateClass(MethodMeta):
                  resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
                  *, perm_source: str = "philox", order: Optional[str] = None, gmean_mode: str = "product",
-                 device: int = 0, dist: Optional[DistContext] = None):
+                 device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
         if n_perms is None:
             consensus_opts = "Magnitude"                       # `_liana_pipe.py:108-109`
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
@@ -81,6 +81,8 @@ class AggregateClass(MethodMeta):
         orderby = self.magnitude if self.magnitude in lr_res.columns else self.specificity
         if orderby in lr_res.columns:
             lr_res = lr_res.sort_values(by=orderby, ascending=True)   # `_liana_pipe.py:246-250`
+        if not _names:                          # by_sample across ranks: (code frame, name tables)
+            return lr_res, PL.name_tables(state)
         lr_res = PL.materialise_names(state, lr_res)
         if inplace:
             adata.uns[key_added] = lr_res
