@@ -296,7 +296,7 @@ def run_gpu(args):
             line["exact_order_mode"] = {"ms_per_step": ex_ms, "value": P * T / (ex_ms * 1e-3),
                                         "roofline_frac": per_perm_bytes * P / (ex_kern / 2 * 1e-3) / 1e9 / peak_gbs,
                                         "note": "bit-identical-to-reference summation order (validation mode)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -381,12 +381,25 @@ def run_reference(args):
                        "clusters": wl["L"], "nnz": wl["nnz"], "n_perms": P, "triples_kept": T, "expr_prop": 0.1},
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
-    # stdout carries exactly ONE JSON line: NCCL's "NCCL version ..." banner goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line: everything any library prints to file descriptor 1 (NCCL's
+    # "NCCL version ..." banner, torchrun notices) is sent to stderr, and the line is written to the saved fd
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
