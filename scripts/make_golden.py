@@ -23,6 +23,8 @@ sys.path.insert(0, ROOT)
 from oracle.ref_shim import load_reference  # noqa: E402
 from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
 from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from variants import variant_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -160,9 +162,22 @@ def save_reference_csv_fixture():
     print("ref_aggregate_rank_rest:", df.shape)
 
 
+def save_variants(ref):
+    adata, variants = variant_inputs()
+    for name, kw in variants.items():
+        res = ref.cellphonedb(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+                              verbose=False, **kw)
+        res.to_csv(os.path.join(OUT, f"variant_{name}_cellphonedb.csv.gz"), index=False)
+        print(f"variant {name}: {res.shape}, mean pval {res['cellphone_pvals'].mean():.4f}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    if "--variants-only" in sys.argv:
+        save_variants(ref)
+        return
+    save_variants(ref)
     save_reference_csv_fixture()
     save_rank_aggregate("toy700", make_synthetic_adata(700, 765, 10, density=0.10), "cluster", 100, 1337, 0.1, ref)
     small = make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12)

@@ -207,3 +207,40 @@ def test_single_non_permutation_methods_run():
         assert len(m) == len(gold)
         for c in cols:
             np.testing.assert_allclose(m[c].values, m[c + "_ref"].values, rtol=1e-4, atol=2e-6)
+
+
+# ---- the optional arguments of the call signature, against the reference's frames ---------------------------
+@pytest.mark.parametrize("name", ["pairs", "interactions", "resource", "raw", "layer"])
+def test_call_signature_variants_identical_to_reference(name):
+    from variants import variant_inputs
+    adata, variants = variant_inputs()
+    res = li.mt.cellphonedb(adata, groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+                            perm_source="reference", **variants[name])
+    gold = pd.read_csv(os.path.join(GOLDEN, f"variant_{name}_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")
+
+
+def test_return_all_lrs_contract():
+    """`return_all_lrs=True` (liana/tests/test_sc_methods.py:166-190: every (pair, interaction) row comes back, the
+    rows that fail expr_prop get the worst magnitude / specificity of the kept ones).  The reference itself cannot
+    run this option under pandas 3 (chained `fillna(inplace=True)`, `_reassemble_complexes.py:56-57`), so the
+    contract is checked directly."""
+    adata, P, seed, ep = load_input("small300")
+    kept = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                             inplace=False, perm_source="reference")
+    full = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                             inplace=False, perm_source="reference", return_all_lrs=True)
+    assert "lrs_to_keep" in full.columns and len(full) > len(kept)
+    n_pairs = adata.obs["cluster"].nunique() ** 2
+    assert len(full) % n_pairs == 0                                   # every interaction for every cluster pair
+    assert int(full["lrs_to_keep"].sum()) == len(kept)
+    rest = full[~full["lrs_to_keep"]]
+    assert np.all(rest["lr_means"] == full.loc[full["lrs_to_keep"], "lr_means"].min())
+    assert np.all(rest["cellphone_pvals"] == full.loc[full["lrs_to_keep"], "cellphone_pvals"].max())
+    # the kept rows carry the same p-values as the filtered call (for simple, non-complex interactions the
+    # resolved subunits are identical too)
+    m = kept.merge(full[full["lrs_to_keep"]], on=KEY, suffixes=("", "_all"))
+    assert len(m) == len(kept)
+    simple = ~(m["ligand_complex"].str.contains("_") | m["receptor_complex"].str.contains("_"))
+    assert np.array_equal(m.loc[simple, "cellphone_pvals"].values, m.loc[simple, "cellphone_pvals_all"].values)
+    assert np.array_equal(m.loc[simple, "lr_means"].values, m.loc[simple, "lr_means_all"].values)

@@ -1,0 +1,38 @@
+"""Inputs of the call-signature variants shared by scripts/make_golden.py (which runs the reference on them in
+the build container) and tests/test_dropin_gpu.py (which runs the drop-in on them on the GPU box)."""
+import os
+
+import numpy as np
+import pandas as pd
+
+from liana_py_b200.testing._synth import make_synthetic_adata
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def variant_inputs():
+    """small300 with the optional arguments of the call signature exercised (liana/tests/test_sc_methods.py,
+    test_pre.py use the same knobs on pbmc68k): groupby_pairs, interactions=, resource=, .raw, layers."""
+    adata = make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12)
+    cats = list(adata.obs["cluster"].cat.categories)
+    pairs = pd.DataFrame({"source": [cats[0], cats[0], cats[2], cats[3]], "target": [cats[1], cats[0], cats[3], cats[0]]})
+    res = pd.read_csv(os.path.join(ROOT, "liana_py_b200", "resource", "consensus.csv"))
+    present = set(adata.var_names)
+    ok = res[[all(g in present for g in (l + "_" + r).split("_")) for l, r in zip(res["ligand"], res["receptor"])]]
+    interactions = list(zip(ok["ligand"].head(40), ok["receptor"].head(40)))
+    custom = ok.iloc[40:140][["ligand", "receptor"]].reset_index(drop=True)
+    # .raw holds log1p(2x) of X, a layer holds sqrt(X): three different matrices in one object
+    X = adata.X.tocsr()
+    raw = X.copy(); raw.data = np.log1p(2.0 * raw.data).astype(np.float32)
+    lay = X.copy(); lay.data = np.sqrt(lay.data).astype(np.float32)
+    adata.raw = type("Raw", (), {"X": raw, "var_names": adata.var_names, "var": adata.var})()
+    adata.layers["sqrt"] = lay
+    return adata, dict(
+        pairs=dict(groupby_pairs=pairs, use_raw=False),
+        interactions=dict(interactions=interactions, use_raw=False),
+        resource=dict(resource=custom, use_raw=False),
+        raw=dict(use_raw=True),
+        layer=dict(layer="sqrt", use_raw=False),
+    )
+
+
