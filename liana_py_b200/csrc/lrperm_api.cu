@@ -104,6 +104,7 @@ struct lrperm_engine {
     int32_t fast_perm_batch = 0, fast_chunk_nnz = 0;   // 0 = auto
     int32_t chunk_table_nnz = -1, chunk_table_tile = -1;   // parameters the chunk tables were built for
     int32_t fast_tile_bytes = 0;                        // label-slab bytes one cell tile may span (0 = auto)
+    int32_t n_sched = 0;                                // batches of the last pipelined run
     int32_t fast_variant = 2;                           // 1 = fast_means_kernel, 2 = fast2_means_kernel
     int32_t fast_q = 0;                                 // permutations per lane (0 = auto)
     int32_t n_chunks = 0, n_slots = 0;
@@ -436,6 +437,17 @@ struct RunArgs {
     int cube_on_device;
 };
 
+// Batch schedule of the pipelined FAST path, in permutations: batches of PB, the last one rounded up to `gran`
+// (the permutations one warp group covers) only.  A schedule with one-group first / last batches (to shorten
+// the slab prologue and the finalize + score epilogue that nothing overlaps) was measured and dropped: small
+// batches leave the main kernel with too few CTAs per wave (configs[1]: 4.8 ms instead of 3.8 ms).
+std::vector<int32_t> batch_schedule(int64_t n_perms, int32_t PB, int32_t gran) {
+    std::vector<int32_t> out;
+    for (int64_t left = n_perms; left > 0; left -= PB)
+        out.push_back((int32_t)(left >= PB ? PB : (left + gran - 1) / gran * gran));
+    return out;
+}
+
 // FAST mode, pipelined over two streams.  Stream A (the engine stream) runs only the main kernel;
 // stream B runs everything around it: the label slab of batch b+1 while main(b) runs, and
 // finalize(b) + score(b) while main(b+1) runs.  Slab and partial-sum buffers are double-buffered.
@@ -445,14 +457,22 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     const int64_t N = h->N;
     const int32_t label_scale = h->fast_variant == 2 ? Q / 2 : 1;
     const int32_t G = (int32_t)h->G, L = h->L;
-    const int32_t PP = PB;
-    const int64_t n_batches = (a.n_perms + PB - 1) / PB;
+    const int32_t gran = std::max(128, 32 * Q);
+    const std::vector<int32_t> sched = batch_schedule(a.n_perms, PB, gran);
+    const int64_t n_batches = (int64_t)sched.size();
+    std::vector<int64_t> first(sched.size() + 1, 0);
+    int32_t pb_max = gran;
+    for (size_t i = 0; i < sched.size(); ++i) { first[i + 1] = first[i] + sched[i]; pb_max = std::max(pb_max, sched[i]); }
+    h->n_sched = (int32_t)n_batches;
     int rc;
     cudaStream_t sA = h->stream, sB = h->aux_stream;
-    const size_t slab_bytes = (size_t)N * PB;
-    const size_t part_bytes = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB;
+    const size_t slab_max = (size_t)N * pb_max;
+    const size_t part_max = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * pb_max;
     const bool dbl = n_batches > 1;
-    if (dbl) { CK(h->slab2.ensure(slab_bytes)); CK(h->partials2.ensure(part_bytes)); }
+    CK(h->slab.ensure(slab_max));
+    CK(h->partials.ensure(part_max));
+    CK(h->cube.ensure(sizeof(float) * (size_t)G * L * pb_max));
+    if (dbl) { CK(h->slab2.ensure(slab_max)); CK(h->partials2.ensure(part_max)); }
     uint8_t* slabs[2] = {h->slab.as<uint8_t>(), dbl ? h->slab2.as<uint8_t>() : h->slab.as<uint8_t>()};
     float* parts[2] = {h->partials.as<float>(), dbl ? h->partials2.as<float>() : h->partials.as<float>()};
 
@@ -471,8 +491,9 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
 
     const size_t idx_elem = a.perm_idx_is_64 ? 8 : 4;
     auto enqueue_slab = [&](int64_t b) -> int {
-        const int64_t p0 = b * PB;
-        const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+        const int64_t p0 = first[(size_t)b];
+        const int32_t PBb = sched[(size_t)b];
+        const int32_t pb = (int32_t)std::min<int64_t>(PBb, a.n_perms - p0);
         uint8_t* slab = slabs[b & 1];
         PermSource ps{};
         ps.is64 = a.perm_idx_is_64;
@@ -480,24 +501,24 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         ps.perm_id0 = a.perm_offset + p0;
         ps.philox = a.perm_source == LRPERM_PERMS_PHILOX;
         CK(cudaEventRecord(EV(b, 0), sB));
-        if (pb < PB) CK(cudaMemsetAsync(slab, 0, slab_bytes, sB));
+        if (pb < PBb) CK(cudaMemsetAsync(slab, 0, (size_t)N * PBb, sB));
         if (ps.philox) {
             const int cells_per_block = 128;
             dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
             const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
             slab_philox_kernel<<<grd, 128, tab_smem, sB>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
-                                                           h->bucket_shift, L, label_scale, (int32_t)N, pb, slab, PB, cells_per_block);
+                                                           h->bucket_shift, L, label_scale, (int32_t)N, pb, slab, PBb, cells_per_block);
         } else {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
             if (a.perm_idx_on_device) ps.idx = src;
             else {
                 // the staging buffer is reused by every batch: slab(b) is queued on B after slab(b-1), in order
-                CK(h->perm_dev.ensure(idx_elem * (size_t)pb * (size_t)N));
+                CK(h->perm_dev.ensure(idx_elem * (size_t)pb_max * (size_t)N));
                 CK(cudaMemcpyAsync(h->perm_dev.p, src, idx_elem * (size_t)pb * (size_t)N, cudaMemcpyHostToDevice, sB));
                 ps.idx = h->perm_dev.p;
             }
             dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
-            slab_from_index_kernel<<<grd, 256, 0, sB>>>(ps, slab_labels, (int32_t)N, pb, slab, PB);
+            slab_from_index_kernel<<<grd, 256, 0, sB>>>(ps, slab_labels, (int32_t)N, pb, slab, PBb);
         }
         CK_LAUNCH();
         CK(cudaEventRecord(EV(b, 1), sB));
@@ -506,36 +527,37 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
 
     if ((rc = enqueue_slab(0))) return rc;
     for (int64_t b = 0; b < n_batches; ++b) {
-        const int64_t p0 = b * PB;
-        const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+        const int64_t p0 = first[(size_t)b];
+        const int32_t PBb = sched[(size_t)b];
+        const int32_t pb = (int32_t)std::min<int64_t>(PBb, a.n_perms - p0);
         if (b + 1 < n_batches && (rc = enqueue_slab(b + 1))) return rc;
         // ---- A: main kernel ----
         CK(cudaStreamWaitEvent(sA, EV(b, 1), 0));
         if (b >= 2) CK(cudaStreamWaitEvent(sA, EV(b - 2, 5), 0));     // partials[b&1] consumed by finalize(b-2)
         CK(cudaEventRecord(EV(b, 2), sA));
-        if ((rc = launch_fast_any(h, Q, PB, slabs[b & 1], parts[b & 1]))) return rc;
+        if ((rc = launch_fast_any(h, Q, PBb, slabs[b & 1], parts[b & 1]))) return rc;
         CK(cudaEventRecord(EV(b, 3), sA));
         // ---- B: finalize + score (+ optional cube export) ----
         CK(cudaStreamWaitEvent(sB, EV(b, 3), 0));
         CK(cudaEventRecord(EV(b, 4), sB));
-        fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, sB>>>(
-            parts[b & 1], h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
+        fast_finalize_kernel<<<grid_for((int64_t)G * L * PBb, 256, h->sm_count * 8), 256, 0, sB>>>(
+            parts[b & 1], h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PBb, h->cube.as<float>(), PBb, 0);
         CK_LAUNCH();
         CK(cudaEventRecord(EV(b, 5), sB));
         if (a.scores) {
             cudaStream_t saved = h->stream;
             h->stream = sB;
-            if (a.gmean_mode == LRPERM_GMEAN_LITERAL) rc = launch_score_t<true>(h, a.scores, h->cube.as<float>(), PP, pb);
-            else rc = launch_score_t<false>(h, a.scores, h->cube.as<float>(), PP, pb);
+            if (a.gmean_mode == LRPERM_GMEAN_LITERAL) rc = launch_score_t<true>(h, a.scores, h->cube.as<float>(), PBb, pb);
+            else rc = launch_score_t<false>(h, a.scores, h->cube.as<float>(), PBb, pb);
             h->stream = saved;
             if (rc) return rc;
         }
         if (a.cube_out) {
             float* dst = a.cube_out + (size_t)p0 * L * G;
             float* dev_dst = dst;
-            if (!a.cube_on_device) { CK(h->stage_out.ensure(sizeof(float) * (size_t)pb * L * G)); dev_dst = h->stage_out.as<float>(); }
+            if (!a.cube_on_device) { CK(h->stage_out.ensure(sizeof(float) * (size_t)pb_max * L * G)); dev_dst = h->stage_out.as<float>(); }
             dim3 blk(32, 8), grd((G + 31) / 32, (pb + 31) / 32, L);
-            cube_export_kernel<<<grd, blk, 0, sB>>>(h->cube.as<float>(), G, L, PP, pb, dev_dst);
+            cube_export_kernel<<<grd, blk, 0, sB>>>(h->cube.as<float>(), G, L, PBb, pb, dev_dst);
             CK_LAUNCH();
             if (!a.cube_on_device) {
                 CK(cudaMemcpyAsync(dst, dev_dst, sizeof(float) * (size_t)pb * L * G, cudaMemcpyDeviceToHost, sB));
@@ -1103,14 +1125,18 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         if (n_perms < PB) PB = (int32_t)std::max<int64_t>(gran, ((n_perms + gran - 1) / gran) * gran);
         PB = ((PB + gran - 1) / gran) * gran;
         // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
-        // (measured on B200, scripts/perf_tune.py: 32 MiB tiles beat 16 MiB by 2-3% on configs[1] and [2])
-        const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (32LL << 20);
-        const int32_t tile_cells = (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / PB, 1024), std::max<int64_t>(N, 1));
+        // (measured on B200, scripts/perf_tune.py: 131,072-cell tiles - 64 MiB of slab at 512 permutations, 16 MiB
+        // at the 125 permutations one of 8 GPUs runs - beat 32 MiB by 1% / 6% and 16 MiB by 3% on configs[2])
+        const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (64LL << 20);
+        // The tile (and with it the chunk table, i.e. the summation order of FAST mode) is defined for the
+        // nominal batch of 512 permutations whatever batch sizes are run: FAST results do not depend on the
+        // batch schedule, so they are bit-identical for any number of GPUs / permutation shards.
+        const int32_t tile_cells = (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / 512, 1024), std::max<int64_t>(N, 1));
         // entries per chunk: long chunks amortise the bin zeroing / partial-sum write-out, but the grid should
         // still hold ~16 waves of (chunk x permutation group) warps; 4096 for configs[1], 16384 for configs[2]
         int32_t chunk_nnz = h->fast_chunk_nnz;
         if (!chunk_nnz) {
-            const int64_t groups = PB / (32 * Q);
+            const int64_t groups = 512 / (32 * Q);
             const int64_t target_items = (int64_t)h->sm_count * 8 * 16;
             int64_t c = h->nnz * groups / std::max<int64_t>(target_items, 1);
             c = std::min<int64_t>(std::max<int64_t>(c, 4096), 16384);
@@ -1155,7 +1181,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         if (scores & LRPERM_SCORE_CPDB) if ((rc = download(h, counts_cpdb, h->counts_c.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
         if (scores & LRPERM_SCORE_GMEAN) if ((rc = download(h, counts_gmean, h->counts_g.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
         CK(cudaStreamSynchronize(h->stream));
-        return collect_pipelined_timings(h, n_batches);
+        return collect_pipelined_timings(h, h->n_sched);
     }
     const size_t n_events = (size_t)n_batches * 5 + 2;
     while (h->events.size() < n_events) {
