@@ -100,3 +100,44 @@ def philox_inverse(n_cells, perm_id, seed) -> np.ndarray:
     out = np.empty(n_cells, dtype=np.int32)
     lib().oracle_philox_inverse(C.c_int64(n_cells), C.c_int64(perm_id), C.c_uint64(seed), _p(out, C.c_int32))
     return out
+
+
+def trimean_cube(X, labels, n_clusters, perm_idx, mat_max, threads: int | None = None) -> np.ndarray:
+    """float64 trimean cube [P, L, G].  perm_idx int64 [P, N]: the null (float32 values x * fl32(1/mat_max));
+    perm_idx None: the observed statistic [1, L, G] (float64 values x * (1/mat_max)).  The reciprocal is
+    evaluated here with NumPy scalar semantics, like SciPy does inside the reference's two divisions."""
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    N, G = X.shape
+    indptr, indices, data = _csr_parts(X)
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    recip = 1.0 / np.float32(mat_max)
+    if perm_idx is None:
+        P, pp, observed = 1, None, 1
+    else:
+        perm_idx = np.ascontiguousarray(perm_idx, dtype=np.int64)
+        P, pp, observed = perm_idx.shape[0], _p(perm_idx, C.c_int64), 0
+        assert perm_idx.shape == (P, N)
+    out = np.empty((P, n_clusters, G), dtype=np.float64)
+    rc = lib().oracle_trimean_cube(C.c_int64(N), C.c_int64(G), _p(indptr, C.c_int64), _p(indices, C.c_int32),
+                                   _p(data, C.c_float), _p(labels, C.c_int32), C.c_int32(n_clusters), C.c_int64(P),
+                                   pp, C.c_int(observed), C.c_float(float(np.float32(recip))), C.c_double(float(recip)),
+                                   _p(out, C.c_double))
+    if rc:
+        raise RuntimeError(f"oracle_trimean_cube failed rc={rc}")
+    return out
+
+
+def counts_cellchat(cube_f64, lig, rec, src, tgt, obs, kh=0.5) -> np.ndarray:
+    P, L, G = cube_f64.shape
+    cube_f64 = np.ascontiguousarray(cube_f64, dtype=np.float64)
+    lig, rec, src, tgt = (np.ascontiguousarray(a, dtype=np.int32) for a in (lig, rec, src, tgt))
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    T = len(lig)
+    out = np.zeros(T, dtype=np.uint32)
+    rc = lib().oracle_counts_cellchat(C.c_int64(P), C.c_int32(L), C.c_int64(G), _p(cube_f64, C.c_double), C.c_int64(T),
+                                      _p(lig, C.c_int32), _p(rec, C.c_int32), _p(src, C.c_int32), _p(tgt, C.c_int32),
+                                      _p(obs, C.c_double), C.c_double(kh), _p(out, C.c_uint32))
+    if rc:
+        raise RuntimeError(f"oracle_counts_cellchat failed rc={rc}")
+    return out

@@ -12,7 +12,7 @@ and then import the hot-path modules themselves unchanged:
 
   liana/method/_pipe_utils/_get_mean_perms.py   (_get_means_perms, _calculate_pvals, ...)
   liana/method/sc/_liana_pipe.py                (liana_pipe, _run_method, _get_lr)
-  liana/method/sc/_cellphonedb.py, _geometric_mean.py, _Method.py, _rank_aggregate.py
+  liana/method/sc/_cellphonedb.py, _geometric_mean.py, _cellchat.py, _Method.py, _rank_aggregate.py
   liana/method/_pipe_utils/_aggregate.py, _pre.py, _common.py
   liana/resource/_reassemble_complexes.py, select_resource.py
 """
@@ -87,6 +87,14 @@ def _install_pandas_compat():
     pd.DataFrame.drop = drop
 
 
+def _install_numpy_compat():
+    """Container drift, not a change of the reference: `_lr_probability` calls `np.product`
+    (`liana/method/sc/_cellchat.py:8`), an alias of `np.prod` that NumPy 2 removed (pinned: 1.24.4)."""
+    import numpy as np
+    if not hasattr(np, "product"):
+        np.product = np.prod
+
+
 _loaded = None
 
 
@@ -144,6 +152,7 @@ def load_reference():
     sys.modules["liana.resource"].filter_reassemble_complexes = rc.filter_reassemble_complexes
 
     _install_pandas_compat()
+    _install_numpy_compat()
     ns = types.SimpleNamespace()
     ns.AnnData = AnnDataLite
     ns.reassemble = rc
@@ -162,6 +171,8 @@ def load_reference():
     ns.logfc_mod = importlib.import_module("liana.method.sc._logfc")
     ns.natmi_mod = importlib.import_module("liana.method.sc._natmi")
     ns.sca_mod = importlib.import_module("liana.method.sc._singlecellsignalr")
+    ns.cellchat_mod = importlib.import_module("liana.method.sc._cellchat")
+    ns.cellchat = ns.cellchat_mod.cellchat
     # the default consensus of `liana/method/__init__.py:13-14` (that __init__ pulls in the spatial stack)
     ns.default_methods = [ns.cellphonedb_mod.cellphonedb, ns.connectome_mod.connectome, ns.logfc_mod.logfc,
                           ns.natmi_mod.natmi, ns.sca_mod.singlecellsignalr]

@@ -108,6 +108,44 @@ def save_case(name, adata, groupby, n_perms, seed, expr_prop, ref, keep_cube_per
           f"mean cpdb pval={arrays['cpdb_pvals'].mean():.6f} mean gmean pval={arrays['gmean_pvals'].mean():.6f}")
 
 
+def save_cellchat_case(name, adata, groupby, n_perms, seed, expr_prop, ref):
+    """li.mt.cellchat of the reference: what `_get_means_perms` saw (the matrix BEFORE its in-place division,
+    `_get_mean_perms.py:43-44`), the float64 trimean cube, the rows / indices / observed trimeans that reached
+    `_cellchat_score`, and the final frame."""
+    kw = dict(groupby=groupby, use_raw=False, n_perms=n_perms, seed=seed, expr_prop=expr_prop, verbose=False)
+    cc = capture_run(ref, ref.cellchat, adata.copy(), **kw)
+    X = cc["X"]
+    X.sort_indices()
+    lr_in = cc["lr_res_in"]
+    lig, rec, src, tgt = cc["idx"]
+    res = cc["res"]
+    key = ["source", "target", "ligand_complex", "receptor_complex"]
+    merged = lr_in[key].merge(res[key + ["lr_probs", "cellchat_pvals"]], on=key, how="left")
+    assert len(merged) == len(lr_in) and not merged["cellchat_pvals"].isna().any()
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}_cellchat.npz"),
+        indptr=X.indptr.astype(np.int64), indices=X.indices.astype(np.int32), data=X.data.astype(np.float32),
+        shape=np.array(X.shape, dtype=np.int64), labels=cc["labels"], mat_max=np.float32(lr_in["mat_max"].values[0]),
+        cube=cc["cube"].astype(np.float64), ligand_idx=lig, receptor_idx=rec, source_idx=src, target_idx=tgt,
+        ligand_trimean=lr_in["ligand_trimean"].values.astype(np.float64),
+        receptor_trimean=lr_in["receptor_trimean"].values.astype(np.float64),
+        lr_probs=merged["lr_probs"].values.astype(np.float64), pvals=merged["cellchat_pvals"].values.astype(np.float64),
+        n_perms=np.int64(n_perms), seed=np.int64(seed), expr_prop=np.float64(expr_prop))
+    res.to_csv(os.path.join(OUT, f"{name}_cellchat.csv.gz"), index=False)
+    print(f"{name} cellchat: N={X.shape[0]} G={X.shape[1]} P={n_perms} T={len(lig)} nonzero cube {np.mean(cc['cube'] != 0):.3f} "
+          f"nonzero lr_probs {np.mean(res['lr_probs'] > 0):.3f} mean pval={res['cellchat_pvals'].mean():.6f}")
+
+
+def dense_case():
+    """700 cells x 300 genes, 6 unequal clusters, high density (many non-zero quartiles), a few negative values
+    and explicit zeros: exercises every branch of the sparse order-statistic logic."""
+    ad = make_synthetic_adata(700, 300, 6, density=0.45, seed_data=21, seed_labels=22)
+    X = ad.X.tocsr().copy()
+    X.data[::11] = 0.0
+    X.data[5::29] *= -1.0
+    return AnnDataLite(X=X, obs=ad.obs, var=ad.var)
+
+
 def ragged_case():
     """Tiny input with empty cells, explicit stored zeros, unequal clusters and a sub-min_cells cluster."""
     rng = np.random.default_rng(7)
@@ -171,13 +209,24 @@ def save_variants(ref):
         print(f"variant {name}: {res.shape}, mean pval {res['cellphone_pvals'].mean():.4f}")
 
 
+def save_cellchat(ref):
+    save_cellchat_case("small300", make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12),
+                       "cluster", 32, 42, 0.1, ref)
+    save_cellchat_case("dense700", dense_case(), "cluster", 24, 9, 0.1, ref)
+    save_cellchat_case("ragged90", ragged_case(), "cluster", 16, 5, 0.05, ref)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     if "--variants-only" in sys.argv:
         save_variants(ref)
         return
+    if "--cellchat-only" in sys.argv:
+        save_cellchat(ref)
+        return
     save_variants(ref)
+    save_cellchat(ref)
     save_reference_csv_fixture()
     save_rank_aggregate("toy700", make_synthetic_adata(700, 765, 10, density=0.10), "cluster", 100, 1337, 0.1, ref)
     small = make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12)

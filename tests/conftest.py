@@ -29,6 +29,21 @@ def golden(request):
     return load_golden(request.param)
 
 
+def load_golden_cellchat(name):
+    from scipy import sparse
+    z = np.load(os.path.join(GOLDEN, f"{name}_cellchat.npz"))
+    d = {k: z[k] for k in z.files}
+    d["X"] = sparse.csr_matrix((d["data"], d["indices"], d["indptr"]), shape=tuple(d["shape"]))
+    d["L"] = int(d["labels"].max()) + 1
+    d["name"] = name
+    return d
+
+
+@pytest.fixture(scope="session", params=["small300", "dense700", "ragged90"])
+def golden_cc(request):
+    return load_golden_cellchat(request.param)
+
+
 @pytest.fixture(scope="session")
 def engine():
     from liana_py_b200 import _engine
