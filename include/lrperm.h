@@ -10,6 +10,8 @@
  *   liana/method/sc/_cellphonedb.py:9-30          _cpdb_score   (null side)
  *   liana/method/sc/_geometric_mean.py:6-25       _gmean_score  (null side)
  *   liana/method/sc/_liana_pipe.py:285-302        per-cluster observed means / props
+ *   liana/method/sc/_cellchat.py:7-32, _liana_pipe.py:307-308, 394-397, 462-465
+ *                                                 CellChat: trimean null + _lr_probability
  *
  * The reference is pure Python, so "the FFI a maintainer would bind" is ctypes; the stub is
  * in INTEGRATION.md.  All entry points take plain pointers and sizes.  Every function
@@ -144,6 +146,36 @@ int lrperm_run(lrperm_engine *h, int64_t n_perms, int64_t perm_offset, uint64_t 
                uint32_t *counts_cpdb, uint32_t *counts_gmean, int counts_on_device,
                float *cube_out, int cube_on_device);
 
+/*
+ * CellChat null (liana/method/sc/_cellchat.py:7-32): the per-(permutation, cluster, gene) statistic is the
+ * TRIMEAN (q25 + 2 median + q75) / 4 of the cluster's dense column of X / mat_max (_trimean,
+ * _liana_pipe.py:462-465, called through _get_means_perms with norm_factor, :394-397 and
+ * _get_mean_perms.py:43-44) and the null score is prod / (kh + prod) of the ligand and receptor trimeans,
+ * compared with >= in float64.  The engine selects the six order statistics a trimean needs from the stored
+ * entries (zeros accounted for arithmetically) and applies numpy's interpolation arithmetic: results are
+ * bit-identical to the reference for identical permutations (no summation order is involved).
+ *
+ * SciPy evaluates the reference's two divisions differently, and both are followed:
+ *   null      `adata.X /= norm_factor`  is  data *= (1.0 / norm_factor) in float32  -> pass recip32 = float32(1 / mat_max)
+ *   observed  `temp.X / mat_max`        is  X.astype(float64) * (1 / mat_max)       -> pass recip    = (double)(1 / mat_max)
+ * (`1 / np.float32` is a float32 under NumPy >= 2 and a float64 before: the caller evaluates it, see _engine.py).
+ *
+ * lrperm_run_trimean: permutations as in lrperm_run; the triples' index arrays come from lrperm_set_triples
+ * (its thresholds may be NULL); obs_prob[T] = the observed lr_probs (float64); counts[T] (uint32, overwritten) =
+ * number of permutations with null score >= observed, or NULL (then obs_prob may be NULL and no triples are
+ * needed); cube_out = optional float64 [n_perms][L][G] trimean cube (the reference's `perms` layout).
+ * lrperm_observed_trimean: trimean[c*G + g] (float64) of the unpermuted clusters (_liana_pipe.py:307-308).
+ * Limits: n_cells < 2^28, at most 255 clusters.
+ */
+int lrperm_run_trimean(lrperm_engine *h, int64_t n_perms, int64_t perm_offset, uint64_t seed,
+                       int perm_source, const void *perm_idx, int perm_idx_is_64, int perm_idx_on_device,
+                       float recip32, double kh, const double *obs_prob, int obs_on_device,
+                       uint32_t *counts, int counts_on_device, double *cube_out, int cube_on_device);
+int lrperm_observed_trimean(lrperm_engine *h, double recip, double *trimean, int out_on_device);
+/* Device time (ms) of the stages of the last trimean run, summed over batches: out[0] entry counting
+ * (the dominant kernel), out[1] prefix, out[2] rank selection, out[3] interpolation. */
+int lrperm_trimean_timings(lrperm_engine *h, float *out4);
+
 /* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32), i.e. the array
  * that reproduces a PHILOX run when passed back as LRPERM_PERMS_INDEX.  The device bijection rho_p (keyed by
  * seed and global permutation id, include/lrperm_philox.h) acts on CLUSTER-SORTED positions: position
@@ -165,7 +197,9 @@ int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_ch
 
 /* Named engine options (experiments / A-B measurements; defaults are the production settings):
  *   "fast_variant"  2 (default) = fast2_means_kernel, 1 = fast_means_kernel (round-1 first version)
- *   "fast_q"        permutations per lane in FAST mode: 0 = auto, 2, 4 or 8                      */
+ *   "fast_q"        permutations per lane in FAST mode: 0 = auto, 2, 4 or 8
+ *   "trimean_chunk_nnz"   stored entries per chunk of the trimean path (0 = auto; multiple of 1024)
+ *   "trimean_perm_batch"  permutations per batch of the trimean path (0 = auto; multiple of 128)  */
 int lrperm_set_option(lrperm_engine *h, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -25,6 +25,7 @@ ABI_SYMBOLS = (
     "lrperm_set_matrix_csr", "lrperm_set_labels", "lrperm_set_triples", "lrperm_observed", "lrperm_run",
     "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
+    "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings",
 )
 
 _lib = None
@@ -65,6 +66,10 @@ def load_library():
                                vp, vp, C.c_int, vp, C.c_int]
     lib.lrperm_philox_perms.argtypes = [vp, i64, i64, i64, u64, vp, C.c_int]
     lib.lrperm_last_timings.argtypes = [vp, vp]
+    lib.lrperm_run_trimean.argtypes = [vp, i64, i64, u64, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_double,
+                                       vp, C.c_int, vp, C.c_int, vp, C.c_int]
+    lib.lrperm_observed_trimean.argtypes = [vp, C.c_double, vp, C.c_int]
+    lib.lrperm_trimean_timings.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -272,6 +277,63 @@ class Engine:
         if return_cube:
             out["cube"] = cube
         return out
+
+    # -- CellChat: trimean null -------------------------------------------------------------
+    @staticmethod
+    def trimean_reciprocals(mat_max):
+        """(recip32, recip) the way SciPy evaluates the reference's two divisions by the float32 `mat_max`
+        (`adata.X /= norm_factor` -> `data *= 1.0 / norm`, float32; `temp.X / mat_max` -> float64 matrix times
+        `1 / mat_max`): NumPy scalar semantics decide whether `1 / np.float32` is float32 (NumPy >= 2) or float64."""
+        recip = 1.0 / np.float32(mat_max)
+        return float(np.float32(recip)), float(recip)
+
+    def observed_trimean(self, mat_max) -> np.ndarray:
+        """float64 [L,G]: `_trimean(temp.X / mat_max)` per cluster (`_liana_pipe.py:307-308`)."""
+        out = np.empty((self.L, self.G), dtype=np.float64)
+        _, recip = self.trimean_reciprocals(mat_max)
+        self._check(self._lib.lrperm_observed_trimean(self._h, recip, C.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def run_trimean(self, n_perms: int, mat_max, *, obs_prob=None, kh: float = 0.5, seed: int = 1337, perm_offset: int = 0,
+                    perm_idx=None, return_cube: bool = False):
+        """CellChat null.  Returns dict with 'cellchat' uint32 counts (if obs_prob is given; needs set_triples)
+        and optionally 'cube' float64 [P,L,G]."""
+        P = int(n_perms)
+        if perm_idx is not None:
+            src = PERMS_INDEX
+            perm_idx = np.ascontiguousarray(perm_idx)
+            if perm_idx.dtype not in (np.int32, np.int64):
+                perm_idx = perm_idx.astype(np.int64)
+            is64 = perm_idx.dtype == np.int64
+            if tuple(perm_idx.shape) != (P, self.N):
+                raise ValueError(f"perm_idx must have shape ({P}, {self.N}), got {tuple(perm_idx.shape)}")
+        else:
+            src, is64 = PERMS_PHILOX, 0
+        pp, pdev, _kp = _ptr(perm_idx)
+        recip32, _ = self.trimean_reciprocals(mat_max)
+        counts = None
+        if obs_prob is not None:
+            obs_prob = np.ascontiguousarray(obs_prob, dtype=np.float64)
+            if obs_prob.shape != (self.T,):
+                raise ValueError(f"obs_prob must have shape ({self.T},)")
+            counts = np.zeros(self.T, dtype=np.uint32)
+        po, _, _ko = _ptr(obs_prob)
+        pc, _, _kc = _ptr(counts)
+        cube = np.empty((P, self.L, self.G), dtype=np.float64) if return_cube else None
+        pcube, _, _kcube = _ptr(cube)
+        self._check(self._lib.lrperm_run_trimean(self._h, P, int(perm_offset), C.c_uint64(int(seed) & (2 ** 64 - 1)), src,
+                                                 pp, int(is64), pdev, C.c_float(recip32), float(kh), po, 0, pc, 0, pcube, 0))
+        out = {}
+        if counts is not None:
+            out["cellchat"] = counts
+        if return_cube:
+            out["cube"] = cube
+        return out
+
+    def trimean_timings(self) -> dict:
+        buf = (C.c_float * 4)()
+        self._check(self._lib.lrperm_trimean_timings(self._h, C.cast(buf, C.c_void_p)))
+        return {"count_ms": buf[0], "prefix_ms": buf[1], "select_ms": buf[2], "finalize_ms": buf[3]}
 
     def philox_perms(self, n_cells: int, n_perms: int, seed: int = 1337, perm_offset: int = 0) -> np.ndarray:
         out = np.empty((int(n_perms), int(n_cells)), dtype=np.int32)

@@ -14,7 +14,8 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SOURCES = [os.path.join(_PKG, "csrc", "lrperm_api.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "lrperm_kernels.cuh"), os.path.join(_ROOT, "include", "lrperm.h"),
+HEADERS = [os.path.join(_PKG, "csrc", "lrperm_kernels.cuh"), os.path.join(_PKG, "csrc", "lrperm_trimean.cuh"),
+           os.path.join(_ROOT, "include", "lrperm.h"),
            os.path.join(_ROOT, "include", "lrperm_philox.h")]
 OUT = os.path.join(_PKG, "_lib", "liblrperm.so")
 

@@ -26,6 +26,7 @@
 
 #include "lrperm.h"
 #include "lrperm_kernels.cuh"
+#include "lrperm_trimean.cuh"
 
 using namespace lrperm;
 
@@ -113,6 +114,14 @@ struct lrperm_engine {
     // work buffers
     DevBuf slab2, partials2;              // second halves of the double buffers of the pipelined FAST path
     DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out, small_a, small_b;
+
+    // CellChat trimean path (lrperm_trimean.cuh)
+    DevBuf vsc_pairs, tm_chunks, tm_region_ptr, tm_counts, tm_prefix, tm_planes, tm_cube, tm_tgt, tm_roles, thr_d, counts_t;
+    bool vsc_ready = false, tm_tables_ready = false;
+    int32_t tm_chunk_nnz = 0, tm_perm_batch = 0;        // tuning (0 = auto)
+    int32_t tm_table_nnz = -1;                           // chunk size the trimean chunk table was built for
+    int32_t tm_n_chunks = 0, tm_n_slots = 0, tm_n_regions = 0;
+    float tm_ms[5] = {0, 0, 0, 0, 0};                    // count, prefix, select, finalize, select-warps-that-walked (n/a)
 
     // timings of the last run
     float t_setup = 0, t_means = 0, t_score = 0, t_total = 0, t_main = 0;
@@ -587,6 +596,333 @@ int collect_pipelined_timings(lrperm_engine* h, int64_t n_batches) {
     return LRPERM_OK;
 }
 
+
+// ---- CellChat trimean path: value-sorted CSC, chunk / rank tables -------------------------------------
+int build_vsc(lrperm_engine* h) {
+    if (h->vsc_ready) return LRPERM_OK;
+    StageTimer timer("build_vsc");
+    const int64_t nnz = h->nnz;
+    const int32_t G = (int32_t)h->G;
+    const size_t n1 = (size_t)std::max<int64_t>(nnz, 1);
+    CK(h->tmp_a.ensure(sizeof(unsigned long long) * n1));    // keys {column, value key}
+    CK(h->tmp_c.ensure(sizeof(unsigned long long) * n1));    // sorted keys (discarded)
+    CK(h->tmp_b.ensure(sizeof(unsigned long long) * n1));    // payload {value bits, cell}
+    DevBuf& col_count = h->small_a;
+    CK(col_count.ensure(sizeof(int32_t) * (size_t)(G + 1)));
+    CK(cudaMemsetAsync(col_count.p, 0, sizeof(int32_t) * (size_t)(G + 1), h->stream));
+    CK(h->vsc_pairs.ensure(sizeof(int2) * n1));
+    h->h_csc_ptr.assign((size_t)G + 1, 0);
+    if (nnz > 0) {
+        vsc_keys_kernel<<<h->sm_count * 4, 512, 0, h->stream>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), (int32_t)h->N, G,
+                                                               h->tmp_a.as<unsigned long long>(), h->tmp_b.as<unsigned long long>(), col_count.as<int32_t>());
+        CK_LAUNCH();
+        int end_bit = 1;
+        while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
+        end_bit += 32;
+        size_t tmp_bytes = 0;
+        unsigned long long* sorted = reinterpret_cast<unsigned long long*>(h->vsc_pairs.p);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->tmp_a.as<unsigned long long>(), h->tmp_c.as<unsigned long long>(),
+                                           h->tmp_b.as<unsigned long long>(), sorted, (int)nnz, 0, end_bit, h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<unsigned long long>(), h->tmp_c.as<unsigned long long>(),
+                                           h->tmp_b.as<unsigned long long>(), sorted, (int)nnz, 0, end_bit, h->stream));
+        h->launches += 8;
+        std::vector<int32_t> cnt((size_t)G + 1, 0);
+        CK(cudaMemcpyAsync(cnt.data(), col_count.p, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int32_t g = 0; g < G; ++g) h->h_csc_ptr[(size_t)g + 1] = h->h_csc_ptr[(size_t)g] + cnt[(size_t)g];
+    } else {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->vsc_ready = true;
+    h->tm_table_nnz = -1;
+    return LRPERM_OK;
+}
+
+// chunk table of the trimean path: every gene's positive region and negative region (the explicit zeros between
+// them need no walk), cut every chunk_nnz entries; slots are consecutive inside a region; longest chunks first
+int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz) {
+    if (h->tm_table_nnz == chunk_nnz) return LRPERM_OK;
+    StageTimer timer("build_tm_chunks");
+    const int32_t G = (int32_t)h->G;
+    std::vector<int32_t> pos_end((size_t)G), neg_begin((size_t)G);
+    {
+        DevBuf &d_ptr = h->small_a, &d_b = h->small_b;
+        CK(d_ptr.ensure(sizeof(int32_t) * ((size_t)G + 1)));
+        CK(d_b.ensure(sizeof(int32_t) * 2 * (size_t)G));
+        CK(cudaMemcpyAsync(d_ptr.p, h->h_csc_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
+        tm_bounds_kernel<<<grid_for(G, 128, 1 << 30), 128, 0, h->stream>>>(h->vsc_pairs.as<int2>(), d_ptr.as<int32_t>(), G,
+                                                                         d_b.as<int32_t>(), d_b.as<int32_t>() + G);
+        CK_LAUNCH();
+        CK(cudaMemcpyAsync(pos_end.data(), d_b.p, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(neg_begin.data(), d_b.as<int32_t>() + G, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    std::vector<FastChunk> chunks;
+    std::vector<int32_t> region_ptr(1, 0);
+    int32_t slot = 0;
+    for (int32_t g = 0; g < G; ++g) {
+        const int32_t b[2] = {h->h_csc_ptr[(size_t)g], neg_begin[(size_t)g]};
+        const int32_t e[2] = {pos_end[(size_t)g], h->h_csc_ptr[(size_t)g + 1]};
+        for (int dir = 0; dir < 2; ++dir) {
+            if (e[dir] <= b[dir]) continue;
+            for (int32_t s0 = b[dir]; s0 < e[dir]; s0 += chunk_nnz) {
+                FastChunk c;
+                c.gene = g | (dir << kTmDirBit); c.begin = s0; c.end = std::min(e[dir], s0 + chunk_nnz); c.slot = slot++;
+                chunks.push_back(c);
+            }
+            region_ptr.push_back(slot);
+        }
+    }
+    std::stable_sort(chunks.begin(), chunks.end(), [](const FastChunk& a, const FastChunk& b) { return (a.end - a.begin) > (b.end - b.begin); });
+    h->tm_n_chunks = (int32_t)chunks.size();
+    h->tm_n_slots = slot;
+    h->tm_n_regions = (int32_t)region_ptr.size() - 1;
+    CK(h->tm_chunks.ensure(sizeof(FastChunk) * std::max<size_t>(chunks.size(), 1)));
+    CK(h->tm_region_ptr.ensure(sizeof(int32_t) * region_ptr.size()));
+    if (!chunks.empty())
+        CK(cudaMemcpyAsync(h->tm_chunks.p, chunks.data(), sizeof(FastChunk) * chunks.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tm_region_ptr.p, region_ptr.data(), sizeof(int32_t) * region_ptr.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm_table_nnz = chunk_nnz;
+    return LRPERM_OK;
+}
+
+// Which order statistics a trimean of n values needs (numpy: np.quantile method 'linear' = Hyndman & Fan 7,
+// virtual index (n - 1) q, neighbours floor / floor + 1; np.median = mean of the middle one / two), as ranks to
+// count down to while walking the positives from the top (dir 0) or the negatives from the bottom (dir 1).
+int build_tm_tables(lrperm_engine* h) {
+    if (h->tm_tables_ready) return LRPERM_OK;
+    const int32_t L = h->L;
+    std::vector<int32_t> tgt((size_t)2 * L * 8, 0);
+    std::vector<TmRoles> roles((size_t)L);
+    for (int32_t c = 0; c < L; ++c) {
+        const int64_t n = h->h_cl_start[(size_t)c + 1] - h->h_cl_start[(size_t)c];
+        int64_t want[6];
+        const double v25 = (double)(n - 1) * 0.25, v75 = (double)(n - 1) * 0.75;
+        auto neighbours = [&](double virt, int64_t& lo, int64_t& hi) {
+            lo = (int64_t)std::floor(virt); hi = lo + 1;
+            if (virt >= (double)(n - 1)) { lo = n - 1; hi = n - 1; }
+        };
+        neighbours(v25, want[0], want[1]);
+        want[2] = (n & 1) ? n / 2 : n / 2 - 1;
+        want[3] = n / 2;
+        neighbours(v75, want[4], want[5]);
+        std::vector<int64_t> uniq(want, want + 6);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        const int m = (int)uniq.size();
+        for (int j = 0; j < 6; ++j) roles[(size_t)c].plane[j] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), want[j]) - uniq.begin());
+        roles[(size_t)c].g25 = (float)(v25 - std::floor(v25));
+        roles[(size_t)c].g75 = (float)(v75 - std::floor(v75));
+        for (int k = 0; k < m; ++k) {
+            tgt[((size_t)0 * L + c) * 8 + k] = (int32_t)(n - uniq[(size_t)(m - 1 - k)]);     // rank from the top, ascending
+            tgt[((size_t)1 * L + c) * 8 + k] = (int32_t)(uniq[(size_t)k] + 1);               // rank from the bottom, ascending
+        }
+        tgt[((size_t)0 * L + c) * 8 + 6] = m;
+        tgt[((size_t)1 * L + c) * 8 + 6] = m;
+    }
+    int rc;
+    if ((rc = upload(h, h->tm_tgt, tgt.data(), sizeof(int32_t) * tgt.size(), 0))) return rc;
+    if ((rc = upload(h, h->tm_roles, roles.data(), sizeof(TmRoles) * roles.size(), 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm_tables_ready = true;
+    return LRPERM_OK;
+}
+
+template <int Q>
+int launch_tm_count_select(lrperm_engine* h, int32_t PB, const uint8_t* slab, cudaEvent_t* ev /*[4]*/) {
+    constexpr int B = 32;
+    const int32_t L = h->L, G = (int32_t)h->G;
+    const int32_t groups = PB / (32 * Q);
+    const int64_t grid = (int64_t)h->tm_n_chunks * groups;
+    if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "trimean: too many chunks (%lld CTAs)", (long long)grid);
+    const size_t smem_count = (size_t)L * Q * 128 + 16 * B;
+    const size_t smem_sel = smem_count + sizeof(int32_t) * 8 * (size_t)L;
+    CK(cudaFuncSetAttribute(fast2_means_kernel<Q, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+    CK(cudaFuncSetAttribute(tm_select_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+    const int64_t plane_stride = (int64_t)G * L * PB;
+    CK(cudaEventRecord(ev[0], h->stream));
+    if (grid > 0) {
+        fast2_means_kernel<Q, B, true><<<(unsigned)grid, 32, smem_count, h->stream>>>(
+            h->vsc_pairs.as<int2>(), h->tm_chunks.as<FastChunk>(), h->tm_n_chunks, slab, PB, L, groups, h->tm_counts.as<float>());
+        CK_LAUNCH();
+    }
+    CK(cudaEventRecord(ev[1], h->stream));
+    if (h->tm_n_regions > 0) {
+        tm_prefix_kernel<<<grid_for((int64_t)h->tm_n_regions * L * PB, 256, h->sm_count * 16), 256, 0, h->stream>>>(
+            h->tm_counts.as<float>(), h->tm_region_ptr.as<int32_t>(), h->tm_n_regions, L, PB, h->tm_prefix.as<uint32_t>());
+        CK_LAUNCH();
+    }
+    CK(cudaEventRecord(ev[2], h->stream));
+    if (grid > 0) {
+        tm_select_kernel<Q, B><<<(unsigned)grid, 32, smem_sel, h->stream>>>(
+            h->vsc_pairs.as<int2>(), h->tm_chunks.as<FastChunk>(), slab, PB, L, groups, h->tm_counts.as<float>(),
+            h->tm_prefix.as<uint32_t>(), h->tm_tgt.as<int32_t>(), h->tm_planes.as<float>(), plane_stride);
+        CK_LAUNCH();
+    }
+    CK(cudaEventRecord(ev[3], h->stream));
+    return LRPERM_OK;
+}
+
+struct TrimeanArgs {
+    int64_t n_perms, perm_offset;
+    uint64_t seed;
+    int perm_source;            // LRPERM_PERMS_INDEX / LRPERM_PERMS_PHILOX, or -1 = identity (observed statistic)
+    const void* perm_idx;
+    int perm_idx_is_64, perm_idx_on_device;
+    float r32;
+    double r64, kh;
+    bool score;
+    double* cube_out;           // [n_perms][L][G] or NULL
+    int cube_on_device;
+};
+
+// batches of permutations: slab -> count -> prefix -> select -> finalize -> (score) (-> export)
+int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
+    const int64_t N = h->N;
+    const int32_t G = (int32_t)h->G, L = h->L;
+    const int64_t T = h->T;
+    int rc;
+    if (L > 255) return h->fail(LRPERM_ERR_UNSUPPORTED, "trimean: at most 255 clusters (got %d)", L);
+    if (N >= (1LL << 28)) return h->fail(LRPERM_ERR_UNSUPPORTED, "trimean: n_cells must be < 2^28");
+    int Q = 0;
+    for (int q : {4, 2}) {
+        if ((L - 1) * q / 2 > 255) continue;
+        if ((size_t)L * q * 128 + 512 + 32 * (size_t)L <= h->smem_optin) { Q = q; break; }
+    }
+    if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "trimean: %d clusters do not fit the shared-memory bins", L);
+    if ((rc = build_vsc(h))) return rc;
+    // entries per chunk: the select pass re-walks whole chunks, so they are shorter than FAST mode's
+    const int32_t chunk_nnz = h->tm_chunk_nnz ? h->tm_chunk_nnz : 8192;
+    if ((rc = build_tm_chunks(h, chunk_nnz))) return rc;
+    if ((rc = build_tm_tables(h))) return rc;
+    // permutations per batch: the walk visits cells in VALUE order, so the whole label slab (N x PB bytes)
+    // should sit in L2: <= 64 MiB
+    int32_t PB = h->tm_perm_batch;
+    if (!PB) PB = (int32_t)std::min<int64_t>(512, std::max<int64_t>(128, ((64LL << 20) / std::max<int64_t>(N, 1)) / 128 * 128));
+    if (a.n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((a.n_perms + 127) / 128) * 128);
+    h->last_pb = PB;
+    const size_t slot_elems = (size_t)std::max(h->tm_n_slots, 1) * L * PB;
+    const size_t plane_elems = (size_t)G * L * PB;
+    CK(h->slab.ensure((size_t)std::max<int64_t>(N, 1) * PB));
+    CK(h->tm_counts.ensure(sizeof(float) * slot_elems));
+    CK(h->tm_prefix.ensure(sizeof(uint32_t) * slot_elems));
+    CK(h->tm_planes.ensure(sizeof(float) * kTmPlanes * plane_elems));
+    CK(h->tm_cube.ensure(sizeof(double) * plane_elems));
+    // label bytes pre-scaled by Q/2 (see fast2_means_kernel)
+    const int32_t scale = Q / 2;
+    if (h->labels8s_scale != scale) {
+        CK(h->labels8s.ensure((size_t)std::max<int64_t>(N, 1)));
+        if (N > 0) {
+            scale_labels_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels8.as<uint8_t>(), (int32_t)N, scale, h->labels8s.as<uint8_t>());
+            CK_LAUNCH();
+        }
+        h->labels8s_scale = scale;
+    }
+    const int64_t n_batches = (a.n_perms + PB - 1) / PB;
+    const size_t n_events = (size_t)n_batches * 8 + 2;
+    while (h->events.size() < n_events) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        h->events.push_back(ev);
+    }
+    CK(cudaEventRecord(h->events[0], h->stream));
+    const size_t idx_elem = a.perm_idx_is_64 ? 8 : 4;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        cudaEvent_t* ev = &h->events[1 + (size_t)b * 8];
+        const int64_t p0 = b * PB;
+        const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+        CK(cudaEventRecord(ev[0], h->stream));
+        // ---- label slab ----
+        if (pb < PB) CK(cudaMemsetAsync(h->slab.p, 0, (size_t)N * PB, h->stream));
+        if (a.perm_source < 0) {
+            slab_identity_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels8s.as<uint8_t>(), (int32_t)N, h->slab.as<uint8_t>(), PB);
+        } else {
+            PermSource ps{};
+            ps.is64 = a.perm_idx_is_64;
+            ps.seed = a.seed;
+            ps.perm_id0 = a.perm_offset + p0;
+            ps.philox = a.perm_source == LRPERM_PERMS_PHILOX;
+            if (ps.philox) {
+                const int cells_per_block = 128;
+                dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
+                const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
+                slab_philox_kernel<<<grd, 128, tab_smem, h->stream>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
+                                                                      h->bucket_shift, L, scale, (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
+            } else {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
+                if (a.perm_idx_on_device) ps.idx = src;
+                else {
+                    if ((rc = upload(h, h->perm_dev, src, idx_elem * (size_t)pb * (size_t)N, 0))) return rc;
+                    ps.idx = h->perm_dev.p;
+                }
+                dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
+                slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, h->labels8s.as<uint8_t>(), (int32_t)N, pb, h->slab.as<uint8_t>(), PB);
+            }
+        }
+        CK_LAUNCH();
+        CK(cudaMemsetAsync(h->tm_planes.p, 0, sizeof(float) * kTmPlanes * plane_elems, h->stream));
+        // ---- count, prefix, select ----
+        if (Q == 4) rc = launch_tm_count_select<4>(h, PB, h->slab.as<uint8_t>(), ev + 1);
+        else rc = launch_tm_count_select<2>(h, PB, h->slab.as<uint8_t>(), ev + 1);
+        if (rc) return rc;
+        // ---- numpy's interpolation arithmetic -> float64 cube ----
+        {
+            const int grid = grid_for((int64_t)plane_elems, 256, h->sm_count * 16);
+            if (a.perm_source < 0)
+                tm_finalize_kernel<true><<<grid, 256, 0, h->stream>>>(h->tm_planes.as<float>(), (int64_t)plane_elems, h->tm_roles.as<TmRoles>(),
+                                                                      G, L, PB, a.r32, a.r64, h->tm_cube.as<double>(), PB);
+            else
+                tm_finalize_kernel<false><<<grid, 256, 0, h->stream>>>(h->tm_planes.as<float>(), (int64_t)plane_elems, h->tm_roles.as<TmRoles>(),
+                                                                       G, L, PB, a.r32, a.r64, h->tm_cube.as<double>(), PB);
+            CK_LAUNCH();
+        }
+        CK(cudaEventRecord(ev[5], h->stream));
+        if (a.score && T > 0) {
+            score_count_cellchat_kernel<<<(unsigned)((T + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, h->stream>>>(
+                h->tm_cube.as<double>(), PB, pb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_d.as<double>(), a.kh, T,
+                h->counts_t.as<uint32_t>());
+            CK_LAUNCH();
+        }
+        CK(cudaEventRecord(ev[6], h->stream));
+        if (a.cube_out) {
+            double* dst = a.cube_out + (size_t)p0 * L * G;
+            double* dev_dst = dst;
+            if (!a.cube_on_device) { CK(h->stage_out.ensure(sizeof(double) * (size_t)pb * L * G)); dev_dst = h->stage_out.as<double>(); }
+            dim3 blk(32, 8), grd((G + 31) / 32, (pb + 31) / 32, L);
+            cube_export_f64_kernel<<<grd, blk, 0, h->stream>>>(h->tm_cube.as<double>(), G, L, PB, pb, dev_dst);
+            CK_LAUNCH();
+            if (!a.cube_on_device) {
+                CK(cudaMemcpyAsync(dst, dev_dst, sizeof(double) * (size_t)pb * L * G, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
+        }
+        CK(cudaEventRecord(ev[7], h->stream));
+    }
+    CK(cudaEventRecord(h->events[1 + (size_t)n_batches * 8], h->stream));
+    return LRPERM_OK;
+}
+
+int collect_trimean_timings(lrperm_engine* h, int64_t n_batches) {
+    h->t_setup = h->t_means = h->t_score = h->t_main = 0.f;
+    for (float& v : h->tm_ms) v = 0.f;
+    h->n_main_launches = (int32_t)n_batches;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        cudaEvent_t* ev = &h->events[1 + (size_t)b * 8];
+        float ms;
+        CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); h->t_setup += ms;
+        CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); h->tm_ms[0] += ms; h->t_main += ms;
+        CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); h->tm_ms[1] += ms;
+        CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); h->tm_ms[2] += ms;
+        CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); h->tm_ms[3] += ms;
+        CK(cudaEventElapsedTime(&ms, ev[1], ev[5])); h->t_means += ms;
+        CK(cudaEventElapsedTime(&ms, ev[5], ev[6])); h->t_score += ms;
+    }
+    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[1 + (size_t)n_batches * 8]));
+    return LRPERM_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -642,7 +978,9 @@ void lrperm_destroy(lrperm_engine* h) {
                       &h->labels32, &h->labels8, &h->labels8s, &h->order, &h->rank, &h->bucket_cluster,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
                       &h->chunks, &h->gene_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
-                      &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b})
+                      &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b,
+                      &h->vsc_pairs, &h->tm_chunks, &h->tm_region_ptr, &h->tm_counts, &h->tm_prefix, &h->tm_planes, &h->tm_cube,
+                      &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -675,6 +1013,12 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "overlap") {
         if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: overlap must be 0 or 1");
         h->overlap = (int32_t)value;
+    } else if (key == "trimean_chunk_nnz") {
+        if (value < 0 || value > (1 << 22) || (value % 1024) != 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: trimean_chunk_nnz must be a multiple of 1024 in [0, 2^22]");
+        h->tm_chunk_nnz = (int32_t)value;
+    } else if (key == "trimean_perm_batch") {
+        if (value < 0 || value > 4096 || (value % 128) != 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: trimean_perm_batch must be a multiple of 128 in [0, 4096]");
+        h->tm_perm_batch = (int32_t)value;
     } else if (key == "fast_q") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_q must be 0, 1, 2, 4 or 8");
         h->fast_q = (int32_t)value;
@@ -689,7 +1033,7 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     if (!h) return LRPERM_ERR_INVALID;
     StageTimer timer("set_matrix_csr");
     DeviceGuard guard(h->device);
-    h->have_matrix = false; h->csc_ready = false; h->have_triples = false; h->have_labels = false;
+    h->have_matrix = false; h->csc_ready = false; h->vsc_ready = false; h->have_triples = false; h->have_labels = false;
     if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr: bad shape or NULL indptr");
     if (n_cells >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_set_matrix_csr: n_cells must be < 2^31");
     if (n_genes > 65535) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_set_matrix_csr: n_genes must be <= 65535 (subset to resource genes first)");
@@ -820,7 +1164,7 @@ int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_gen
             }
         }
     }
-    h->have_matrix = false; h->csc_ready = false; h->have_triples = false; h->have_labels = false;
+    h->have_matrix = false; h->csc_ready = false; h->vsc_ready = false; h->have_triples = false; h->have_labels = false;
     int rc;
     DevBuf &d_map = h->small_a, &d_flag = h->tmp_a, &d_excl = h->tmp_d, &d_newrow = h->stage_out;
     if ((rc = upload(h, d_map, col_map, sizeof(int32_t) * (size_t)Gin, 0))) return rc;
@@ -933,6 +1277,7 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
     }
 
     h->L = n_clusters;
+    h->tm_tables_ready = false;
     h->labels8s_scale = 0;
     h->h_cl_start = start;
     int rc;
@@ -1275,6 +1620,60 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         CK(cudaEventElapsedTime(&ms, h->events[base + 3], h->events[base + 4])); h->t_score += ms;
     }
     CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[evi - 1]));
+    return LRPERM_OK;
+}
+
+int lrperm_run_trimean(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t seed, int perm_source,
+                       const void* perm_idx, int perm_idx_is_64, int perm_idx_on_device, float recip32, double kh,
+                       const double* obs_prob, int obs_on_device, uint32_t* counts, int counts_on_device,
+                       double* cube_out, int cube_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("run_trimean");
+    DeviceGuard guard(h->device);
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: set the matrix and labels first");
+    if (n_perms < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: n_perms < 0");
+    if (perm_source != LRPERM_PERMS_INDEX && perm_source != LRPERM_PERMS_PHILOX) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: unknown perm_source %d", perm_source);
+    if (perm_source == LRPERM_PERMS_INDEX && n_perms > 0 && !perm_idx) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: perm_idx is NULL");
+    if (!(recip32 > 0.0f) || !std::isfinite(recip32)) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: recip32 must be positive and finite");
+    const bool score = counts != nullptr;
+    if (score && (!h->have_triples || !obs_prob)) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: counts requested without triples / obs_prob");
+    const int64_t T = h->T;
+    h->launches = 0;
+    int rc;
+    if (score) {
+        if ((rc = upload(h, h->thr_d, obs_prob, sizeof(double) * (size_t)T, obs_on_device))) return rc;
+        CK(h->counts_t.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1)));
+        CK(cudaMemsetAsync(h->counts_t.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
+    }
+    TrimeanArgs a{n_perms, perm_offset, seed, perm_source, perm_idx, perm_idx_is_64, perm_idx_on_device, recip32, (double)recip32, kh,
+                  score, cube_out, cube_on_device};
+    if ((rc = run_trimean_batches(h, a))) { cudaStreamSynchronize(h->stream); return rc; }
+    if (score && (rc = download(h, counts, h->counts_t.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return collect_trimean_timings(h, (n_perms + h->last_pb - 1) / std::max(h->last_pb, 1));
+}
+
+int lrperm_observed_trimean(lrperm_engine* h, double recip, double* trimean, int out_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_observed_trimean: set the matrix and labels first");
+    if (!(recip > 0.0) || !std::isfinite(recip) || !trimean) return h->fail(LRPERM_ERR_INVALID, "lrperm_observed_trimean: recip must be positive and finite, trimean non-NULL");
+    const int32_t G = (int32_t)h->G, L = h->L;
+    h->launches = 0;
+    int rc;
+    // one identity "permutation" through the same kernels; the batch is exported as [1][L][G]
+    double* dev_dst = trimean;
+    if (!out_on_device) { CK(h->tmp_d.ensure(sizeof(double) * (size_t)L * G)); dev_dst = h->tmp_d.as<double>(); }
+    TrimeanArgs a{1, 0, 0, -1, nullptr, 0, 0, (float)recip, recip, 0.0, false, dev_dst, 1};
+    if ((rc = run_trimean_batches(h, a))) { cudaStreamSynchronize(h->stream); return rc; }
+    if (!out_on_device) CK(cudaMemcpyAsync(trimean, dev_dst, sizeof(double) * (size_t)L * G, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return collect_trimean_timings(h, 1);
+}
+
+int lrperm_trimean_timings(lrperm_engine* h, float* out4) {
+    if (!h || !out4) return LRPERM_ERR_INVALID;
+    for (int i = 0; i < 4; ++i) out4[i] = h->tm_ms[i];
     return LRPERM_OK;
 }
 

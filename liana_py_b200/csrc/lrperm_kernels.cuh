@@ -660,7 +660,9 @@ __device__ __forceinline__ void fast2_update(unsigned char* bins, uint32_t lane4
     for (int q = 0; q < Q; ++q) *b[q] = x[q] + v;
 }
 
-template <int Q, int B>
+// COUNT = true: every stored entry contributes 1.0f instead of its value (per-(chunk, cluster, permutation)
+// entry counts of the trimean path, lrperm_trimean.cuh; exact in float32: a chunk holds < 2^24 entries).
+template <int Q, int B, bool COUNT = false>
 __global__ void __launch_bounds__(32)
 fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restrict__ chunks, int32_t n_chunks,
                    const uint8_t* __restrict__ slab, int32_t PB, int32_t L, int32_t groups_per_batch,
@@ -688,6 +690,10 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
     auto load_pair = [&](int k) -> int2 {          // tail entries add +0.0f to a valid bin
         return (lane < B && k + lane < ch.end) ? __ldg(&csc_pairs[k + lane]) : make_int2(first_cell, 0);
     };
+    auto load_pair_count = [&](int k) -> int2 {    // COUNT: 1.0f per real entry, +0.0f for the tail
+        const bool in = lane < B && k + lane < ch.end;
+        return make_int2(in ? __ldg(&csc_pairs[k + lane]).x : first_cell, in ? 0x3f800000 : 0);
+    };
     auto stage = [&](int buf, int2 pr) {
         __syncwarp();                              // earlier broadcasts of this buffer are done
         if (lane < B) { st_cell[buf * B + lane] = pr.x; st_val[buf * B + lane] = __int_as_float(pr.y); }
@@ -714,21 +720,22 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
         }
     };
 
+    auto next_pair = [&](int k) -> int2 { return COUNT ? load_pair_count(k) : load_pair(k); };
     LV lwA[B], lwB[B];
-    int2 pr = load_pair(ch.begin);
+    int2 pr = next_pair(ch.begin);
     stage(0, pr);
     fetch_labels(0, lwA);
-    pr = load_pair(ch.begin + B);
+    pr = next_pair(ch.begin + B);
     for (int k = ch.begin; k < ch.end; k += 2 * B) {
         // block k: buffer 0 / lwA ; block k+B: buffer 1 / lwB
         stage(1, pr);
-        pr = load_pair(k + 2 * B);
+        pr = next_pair(k + 2 * B);
         const bool more1 = k + B < ch.end;
         if (more1) fetch_labels(1, lwB);
         update(0, lwA);
         if (!more1) break;
         stage(0, pr);
-        pr = load_pair(k + 3 * B);
+        pr = next_pair(k + 3 * B);
         if (k + 2 * B < ch.end) fetch_labels(0, lwA);
         update(1, lwB);
     }

@@ -1,0 +1,120 @@
+"""GPU parity tests of the CellChat trimean null (lrperm_run_trimean / lrperm_observed_trimean, through the
+C ABI) against the fixtures produced by the reference's own li.mt.cellchat and against the C oracle.
+Order statistics are selected, not summed: every comparison here is BIT-EXACT."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from liana_py_b200 import _engine as E
+from oracle import c_oracle, numpy_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _idx(g):
+    return g["ligand_idx"], g["receptor_idx"], g["source_idx"], g["target_idx"]
+
+
+def _perm_idx(g):
+    return numpy_port.perm_indices(g["X"].shape[0], int(g["n_perms"]), int(g["seed"]))
+
+
+def test_trimean_cube_and_counts_match_reference_golden(engine, golden_cc):
+    g = golden_cc
+    P = int(g["n_perms"])
+    engine.set_matrix(g["X"])
+    engine.set_labels(g["labels"], g["L"])
+    engine.set_triples(*_idx(g))
+    out = engine.run_trimean(P, g["mat_max"], obs_prob=g["lr_probs"], perm_idx=_perm_idx(g), return_cube=True)
+    assert out["cube"].dtype == np.float64
+    assert np.array_equal(out["cube"], g["cube"])                       # bit-identical float64 cube
+    assert np.array_equal(out["cellchat"] / P, g["pvals"])              # p-values bit-identical
+
+
+def test_observed_trimean_matches_reference_golden(engine, golden_cc):
+    g = golden_cc
+    engine.set_matrix(g["X"])
+    engine.set_labels(g["labels"], g["L"])
+    obs = engine.observed_trimean(g["mat_max"])
+    assert np.array_equal(obs, c_oracle.trimean_cube(g["X"], g["labels"], g["L"], None, g["mat_max"])[0])
+    assert np.array_equal(obs[g["source_idx"], g["ligand_idx"]], g["ligand_trimean"])
+    assert np.array_equal(obs[g["target_idx"], g["receptor_idx"]], g["receptor_trimean"])
+
+
+def _random_case(seed, N, G, L, negatives=False, explicit_zeros=False, skew=False):
+    rng = np.random.default_rng(seed)
+    dens = rng.beta(0.8, 1.2, size=G)
+    dense = (rng.random((N, G)) < dens[None, :]) * np.log1p(rng.gamma(1.5, 2.0, (N, G)))
+    if negatives:
+        dense *= np.where(rng.random((N, G)) < 0.3, -1.0, 1.0)
+    X = sparse.csr_matrix(dense.astype(np.float32))
+    if explicit_zeros:
+        X.data[::13] = 0.0
+    if skew:
+        p = rng.dirichlet(np.full(L, 0.5))
+        labels = rng.choice(L, size=N, p=p).astype(np.int32)
+    else:
+        labels = rng.integers(0, L, N).astype(np.int32)
+    labels[:L] = np.arange(L)
+    return X, labels
+
+
+@pytest.mark.parametrize("case", [
+    dict(seed=1, N=20000, G=24, L=7, chunk=1024),                                   # many chunks per gene: prefix + select
+    dict(seed=2, N=9000, G=40, L=50, chunk=1024, skew=True),                        # 50 unequal clusters (tiny ones too)
+    dict(seed=3, N=6000, G=30, L=5, chunk=2048, negatives=True, explicit_zeros=True),
+    dict(seed=4, N=3000, G=16, L=130, chunk=1024, skew=True),                       # > 128 clusters: 2 permutations per lane
+    dict(seed=5, N=50, G=12, L=3, chunk=0),                                          # tiny clusters, odd / even sizes
+])
+def test_trimean_cube_matches_oracle_multichunk(engine, case):
+    X, labels = _random_case(case["seed"], case["N"], case["G"], case["L"], case.get("negatives", False),
+                             case.get("explicit_zeros", False), case.get("skew", False))
+    L = case["L"]
+    mat_max = np.float32(X.max())
+    P = 6
+    perm_idx = numpy_port.perm_indices(X.shape[0], P, 11)
+    engine.set_option("trimean_chunk_nnz", case["chunk"])
+    try:
+        engine.set_matrix(X)
+        engine.set_labels(labels, L)
+        out = engine.run_trimean(P, mat_max, perm_idx=perm_idx, return_cube=True)
+        ref = c_oracle.trimean_cube(X, labels, L, perm_idx, mat_max)
+        assert np.array_equal(out["cube"], ref)
+        assert np.mean(ref != 0) > 0.1
+        obs = engine.observed_trimean(mat_max)
+        assert np.array_equal(obs, c_oracle.trimean_cube(X, labels, L, None, mat_max)[0])
+    finally:
+        engine.set_option("trimean_chunk_nnz", 0)
+
+
+def test_trimean_philox_equals_index_mode_and_shards_add_up(engine):
+    X, labels = _random_case(9, 12000, 20, 6)
+    L = 6
+    mat_max = np.float32(X.max())
+    engine.set_option("trimean_chunk_nnz", 2048)
+    try:
+        engine.set_matrix(X)
+        engine.set_labels(labels, L)
+        rng = np.random.default_rng(0)
+        T = 500
+        lig, rec = rng.integers(0, X.shape[1], T), rng.integers(0, X.shape[1], T)
+        src, tgt = rng.integers(0, L, T), rng.integers(0, L, T)
+        engine.set_triples(lig, rec, src, tgt)
+        obs_tm = engine.observed_trimean(mat_max)
+        obs = numpy_port.lr_probability((obs_tm[src, lig], obs_tm[tgt, rec]))
+        P = 200                                                      # two batches of 128
+        engine.set_option("trimean_perm_batch", 128)
+        ph = engine.run_trimean(P, mat_max, obs_prob=obs, seed=5, return_cube=True)
+        perms = engine.philox_perms(X.shape[0], P, seed=5)
+        ix = engine.run_trimean(P, mat_max, obs_prob=obs, perm_idx=perms, return_cube=True)
+        assert np.array_equal(ph["cube"], ix["cube"]) and np.array_equal(ph["cellchat"], ix["cellchat"])
+        # counts against the oracle's score on the engine's own cube (the cube itself is checked above)
+        assert np.array_equal(ph["cellchat"].astype(np.int64), numpy_port.counts_cellchat(ph["cube"], lig, rec, src, tgt, obs))
+        a = engine.run_trimean(90, mat_max, obs_prob=obs, seed=5, perm_offset=0)["cellchat"]
+        b = engine.run_trimean(110, mat_max, obs_prob=obs, seed=5, perm_offset=90)["cellchat"]
+        assert np.array_equal(a + b, ph["cellchat"])
+        ref = c_oracle.trimean_cube(X, labels, L, perms[:8].astype(np.int64), mat_max)
+        assert np.array_equal(ph["cube"][:8], ref)
+    finally:
+        engine.set_option("trimean_chunk_nnz", 0)
+        engine.set_option("trimean_perm_batch", 0)
