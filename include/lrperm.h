@@ -96,6 +96,10 @@ int lrperm_stage_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes, 
                             const int32_t *indices, const float *data, int on_device, const uint8_t *row_keep,
                             double *col_sums, double *kept_total, int64_t *n_nonfinite, int64_t *n_empty_rows);
 int lrperm_commit_matrix(lrperm_engine *h, const int32_t *col_map, int64_t n_genes_out);
+/* Largest STORED value over the kept rows of the staged matrix (-inf if none) and the number of stored entries
+ * in those rows: the inputs of CellChat's `mat_max = adata.X.max()` (liana/method/sc/_liana_pipe.py:143-146;
+ * the implicit zeros take part in that maximum, the caller adds them).  Valid between stage and the next stage. */
+int lrperm_staged_max(lrperm_engine *h, float *max_stored, int64_t *n_stored);
 
 /* Cluster code per cell (codes of obs['@label'] in .cat.categories order, _get_mean_perms.py:47-52). */
 int lrperm_set_labels(lrperm_engine *h, const int32_t *labels, int32_t n_clusters, int on_device);

@@ -35,3 +35,5 @@ LIGAND_MEANS, RECEPTOR_MEANS = 'ligand_means', 'receptor_means'
 LIGAND_PROPS, RECEPTOR_PROPS = 'ligand_props', 'receptor_props'
 LRS_TO_KEEP = 'lrs_to_keep'
 LABEL = '@label'
+LIGAND_TRIMEAN, RECEPTOR_TRIMEAN = 'ligand_trimean', 'receptor_trimean'
+MAT_MAX = 'mat_max'

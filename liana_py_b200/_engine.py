@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "lrperm_set_matrix_csr", "lrperm_set_labels", "lrperm_set_triples", "lrperm_observed", "lrperm_run",
     "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
-    "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings",
+    "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
 )
 
 _lib = None
@@ -70,6 +70,7 @@ def load_library():
                                        vp, C.c_int, vp, C.c_int, vp, C.c_int]
     lib.lrperm_observed_trimean.argtypes = [vp, C.c_double, vp, C.c_int]
     lib.lrperm_trimean_timings.argtypes = [vp, vp]
+    lib.lrperm_staged_max.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 
@@ -186,6 +187,12 @@ class Engine:
             None if keep is None else C.c_void_p(keep.ctypes.data), C.c_void_p(col_sums.ctypes.data),
             C.byref(total), C.byref(bad), C.byref(empty)))
         return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+
+    def staged_max(self):
+        """(largest stored value over the kept rows of the staged matrix as np.float32, stored entries in them)."""
+        mx, cnt = C.c_float(0.0), C.c_int64(0)
+        self._check(self._lib.lrperm_staged_max(self._h, C.byref(mx), C.byref(cnt)))
+        return np.float32(mx.value), int(cnt.value)
 
     def commit_matrix(self, col_map, n_genes_out: int, n_cells_out: int):
         """Make the staged matrix the engine's matrix: rows flagged in row_keep, columns with col_map >= 0."""

@@ -1145,6 +1145,32 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
     return LRPERM_OK;
 }
 
+int lrperm_staged_max(lrperm_engine* h, float* max_stored, int64_t* n_stored) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->staged) return h->fail(LRPERM_ERR_INVALID, "lrperm_staged_max: call lrperm_stage_matrix_csr first");
+    // [uint32 max key][pad][uint64 stored entries]
+    CK(h->small_b.ensure(16));
+    CK(cudaMemsetAsync(h->small_b.p, 0, 16, h->stream));
+    if (h->st_N > 0 && h->st_nnz > 0) {
+        stage_max_kernel<<<grid_for(h->st_N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+            h->st_indptr.as<int32_t>(), h->st_data.as<float>(), h->st_has_keep ? h->st_row_keep.as<uint8_t>() : nullptr,
+            (int32_t)h->st_N, h->small_b.as<uint32_t>(), reinterpret_cast<unsigned long long*>(h->small_b.as<unsigned char>() + 8));
+        CK_LAUNCH();
+    }
+    unsigned char host[16];
+    CK(cudaMemcpyAsync(host, h->small_b.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    uint32_t key; unsigned long long cnt;
+    memcpy(&key, host, 4); memcpy(&cnt, host + 8, 8);
+    if (max_stored) {
+        if (key == 0) *max_stored = -INFINITY;           // no stored entry in the kept rows
+        else { const uint32_t b = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key; memcpy(max_stored, &b, 4); }
+    }
+    if (n_stored) *n_stored = (int64_t)cnt;
+    return LRPERM_OK;
+}
+
 int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_genes_out) {
     if (!h) return LRPERM_ERR_INVALID;
     StageTimer timer("commit_matrix");

@@ -139,6 +139,35 @@ __global__ void stage_stats_kernel(const int32_t* __restrict__ indptr, const int
     }
 }
 
+// largest stored value over the kept rows of the staged matrix (CellChat's `mat_max = adata.X.max()`,
+// liana/method/sc/_liana_pipe.py:143-146), as an order-preserving unsigned key so that atomicMax applies
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+    const uint32_t b = (uint32_t)__float_as_int(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void stage_max_kernel(const int32_t* __restrict__ indptr, const float* __restrict__ data,
+                                 const uint8_t* __restrict__ row_keep, int32_t N, uint32_t* __restrict__ max_key,
+                                 unsigned long long* __restrict__ n_stored) {
+    const int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t best = 0;
+    unsigned long long stored = 0;
+    for (int r = warp; r < N; r += nwarps) {
+        if (row_keep && !row_keep[r]) continue;
+        const int s = indptr[r], e = indptr[r + 1];
+        for (int o = s + lane; o < e; o += 32) best = max(best, float_order_key(data[o]));
+        if (lane == 0) stored += (unsigned long long)(e - s);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 0) {
+        if (best) atomicMax(max_key, best);
+        if (stored) atomicAdd(n_stored, stored);
+    }
+}
+
 // entries of every KEPT row that survive the column map -> counts[new_row]
 __global__ void mapped_count_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                     const int32_t* __restrict__ col_map, const int32_t* __restrict__ new_row /*[N], -1 = dropped*/,

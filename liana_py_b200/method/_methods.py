@@ -1,4 +1,4 @@
-"""Drop-in `li.mt.cellphonedb` / `li.mt.geometric_mean` (+ `.by_sample`) backed by the CUDA engine.
+"""Drop-in `li.mt.cellphonedb` / `li.mt.geometric_mean` / `li.mt.cellchat` (+ `.by_sample`) backed by the CUDA engine.
 
 Same call signatures, defaults, result columns, dtypes and sort order as the reference's
 `Method.__call__` / `MethodMeta.by_sample` (`liana/method/sc/_Method.py:92-267`).  Engine-only
@@ -126,7 +126,7 @@ class Method(MethodMeta):
         if supp_columns:
             raise NotImplementedError("supp_columns are outside the scope of the permutation engine")
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
-                           use_raw, layer, verbose, device=device, base=base)
+                           use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in self.add_cols)
         liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
                                perm_source, order, gmean_mode, dist)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
@@ -146,7 +146,8 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
 
     In a consensus (`null_cache` given) every permutation method named in `permuting_methods` is counted
     from ONE pass over the permutations, and the counts are cached for the methods that follow."""
-    tri, lr_res = state.resolved(expr_prop, return_all_lrs)       # shared by the methods of a consensus
+    stat = "trimean" if K.LIGAND_TRIMEAN in method.complex_cols else "means"
+    tri, lr_res = state.resolved(expr_prop, return_all_lrs, stat)       # shared by the methods of a consensus
     if method.add_cols:
         lr_res = PL.add_method_columns(state, tri, lr_res, method.add_cols)
         lr_res = lr_res[sorted(lr_res.columns)]            # `np.union1d` of the column sets (`_liana_pipe.py:385`)
@@ -158,10 +159,16 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
         key = (method.engine_score, n_perms, seed, perm_source, order, gmean_mode, expr_prop, return_all_lrs)
         if null_cache is not None and key in null_cache:
             null = null_cache[key]
+        elif method.engine_score == "cellchat":
+            obs = PL.observed_cellchat(sub.ligand_means, sub.receptor_means, cellchat._kh)
+            out = PL.permutation_counts_trimean(state, sub, obs, n_perms, seed, perm_source, cellchat._kh, dist)
+            null = NullCounts(out["cellchat"], n_perms)
+            if null_cache is not None:
+                null_cache[key] = null
         else:
             wanted = {method.engine_score}
             if null_cache is not None and permuting_methods:
-                wanted |= {m.engine_score for m in permuting_methods if m.permute and m.engine_score}
+                wanted |= {m.engine_score for m in permuting_methods if m.permute and m.engine_score in ("cpdb", "gmean")}
             oc = PL.observed_cpdb(sub.ligand_means, sub.receptor_means) if "cpdb" in wanted else None
             og = PL.observed_gmean(sub.ligand_means, sub.receptor_means) if "gmean" in wanted else None
             out = PL.permutation_counts(state, sub, oc, og, n_perms, seed, perm_source, order, gmean_mode, dist)
@@ -216,6 +223,12 @@ def _gmean_score(x: pd.DataFrame, perm_stats: Optional[NullCounts]):
     return lr_gmeans, (perm_stats.pvals() if perm_stats is not None else None)
 
 
+def _cellchat_score(x: pd.DataFrame, perm_stats: Optional[NullCounts]):
+    """CellChat-like lr_probs and p-values (`liana/method/sc/_cellchat.py:13-32`)."""
+    lr_prob = PL.observed_cellchat(x[K.LIGAND_TRIMEAN].values, x[K.RECEPTOR_TRIMEAN].values, cellchat._kh)
+    return lr_prob, (perm_stats.pvals() if perm_stats is not None else None)
+
+
 _cellphonedb = MethodMeta(method_name="CellPhoneDB", complex_cols=[K.LIGAND_MEANS, K.RECEPTOR_MEANS], add_cols=[],
                           fun=_cpdb_score, magnitude="lr_means", magnitude_ascending=False,
                           specificity="cellphone_pvals", specificity_ascending=True, permute=True,
@@ -226,5 +239,12 @@ _geometric_mean = MethodMeta(method_name="Geometric Mean", complex_cols=[K.LIGAN
                              reference="CellPhoneDBv2's permutation approach applied to the geometric means.",
                              engine_score="gmean")
 
+_cellchat = MethodMeta(method_name="CellChat", complex_cols=[K.LIGAND_TRIMEAN, K.RECEPTOR_TRIMEAN], add_cols=[K.MAT_MAX],
+                       fun=_cellchat_score, magnitude="lr_probs", magnitude_ascending=False,
+                       specificity="cellchat_pvals", specificity_ascending=True, permute=True,
+                       reference="Jin et al., 2021. Nature communications 12(1).", engine_score="cellchat")
+
 cellphonedb = Method(_method=_cellphonedb)
 geometric_mean = Method(_method=_geometric_mean)
+cellchat = Method(_method=_cellchat)
+cellchat._kh = 0.5               # `_cellchat.py:53`: a module-level knob in the reference too

@@ -86,15 +86,25 @@ class PipelineState:
         self._moments = None
         self._cache = {}
 
-    def resolved(self, expr_prop, return_all_lrs):
-        """(ResolvedTriples, base lr_res frame) for one filter setting; every method of a consensus filters with
-        the same `complex_cols` and `expr_prop`, so the tables are built once (the reference re-runs
-        `filter_reassemble_complexes` per method, `_liana_pipe.py:378-382`).  Callers must not mutate the frame."""
-        key = ("tri", float(expr_prop), bool(return_all_lrs))
+    def resolved(self, expr_prop, return_all_lrs, stat="means"):
+        """(ResolvedTriples, base lr_res frame) for one filter setting; the methods of a consensus that share
+        `complex_cols` and `expr_prop` share the tables (the reference re-runs `filter_reassemble_complexes` per
+        method, `_liana_pipe.py:378-382`).  `stat` names the statistic the complexes are resolved by: 'means'
+        (ligand_means / receptor_means) or 'trimean' (CellChat's complex_cols).  Callers must not mutate the frame."""
+        key = ("tri", float(expr_prop), bool(return_all_lrs), stat)
         if key not in self._cache:
-            tri = _tables.resolve_triples(self.tables, self.means, self.props, expr_prop, self.pair_mask, return_all_lrs)
-            self._cache[key] = (tri, base_frame(self, tri))
+            by = self.means if stat == "means" else self.trimean()
+            tri = _tables.resolve_triples(self.tables, by, self.props, expr_prop, self.pair_mask, return_all_lrs)
+            self._cache[key] = (tri, base_frame(self, tri, stat))
         return self._cache[key]
+
+    def trimean(self) -> np.ndarray:
+        """Observed cluster trimeans of X / mat_max, float64 [L,G] (`_liana_pipe.py:307-308, 462-465`)."""
+        if "trimean" not in self._cache:
+            if self.prep.mat_max is None:
+                raise RuntimeError("the input was prepared without mat_max (internal error)")
+            self._cache["trimean"] = self.engine.observed_trimean(self.prep.mat_max)
+        return self._cache["trimean"]
 
     def _get_moments(self):
         if self._moments is None:
@@ -153,7 +163,7 @@ class PipelineState:
 
 
 def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells, use_raw, layer,
-            verbose, device=0, base=float(np.e)) -> PipelineState:
+            verbose, device=0, base=float(np.e), want_max=False) -> PipelineState:
     res = handle_resource(interactions=interactions, resource=resource, resource_name=resource_name, verbose=verbose)
     groupby_subset = None
     if groupby_pairs is not None:
@@ -162,7 +172,7 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
         groupby_subset = np.union1d(groupby_pairs[K.SOURCE].unique(), groupby_pairs[K.TARGET].unique())
     eng = get_engine(device)
     prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, engine=eng, groupby_subset=groupby_subset,
-                              use_raw=use_raw, layer=layer, verbose=verbose)
+                              use_raw=use_raw, layer=layer, verbose=verbose, want_max=want_max)
     tables, all_entities = _cached_tables(res, prep.var_names)
     _pre.assert_covered(all_entities, prep.var_names, verbose=verbose)
     # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`): a column map for the
@@ -195,15 +205,16 @@ def _take_names(names, codes):
     return idx.array.take(np.asarray(codes, dtype=np.int64))
 
 
-def base_frame(state: PipelineState, tri: _tables.ResolvedTriples) -> pd.DataFrame:
+def base_frame(state: PipelineState, tri: _tables.ResolvedTriples, stat: str = "means") -> pd.DataFrame:
     """lr_res with the reference's column names / dtypes / order for the kept rows.  The six name columns hold
     int32 CODES until `materialise_names` runs on the final (filtered, sorted) frame: selecting, sorting and
     concatenating integer columns is several times cheaper than moving strings around."""
+    lig_stat, rec_stat = (K.LIGAND_MEANS, K.RECEPTOR_MEANS) if stat == "means" else (K.LIGAND_TRIMEAN, K.RECEPTOR_TRIMEAN)
     return pd.DataFrame({
         K.LIGAND: tri.lig_gene, K.LIGAND_COMPLEX: tri.inter,
-        K.LIGAND_MEANS: tri.ligand_means, K.LIGAND_PROPS: tri.ligand_props,
+        lig_stat: tri.ligand_means, K.LIGAND_PROPS: tri.ligand_props,
         K.RECEPTOR: tri.rec_gene, K.RECEPTOR_COMPLEX: tri.inter,
-        K.RECEPTOR_MEANS: tri.receptor_means, K.RECEPTOR_PROPS: tri.receptor_props,
+        rec_stat: tri.receptor_means, K.RECEPTOR_PROPS: tri.receptor_props,
         K.SOURCE: tri.src, K.TARGET: tri.tgt,
     })
 
@@ -243,6 +254,8 @@ def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame
             frame[col] = state.means_sums("receptor")[tri.src, tri.rec_gene]
         elif col == "mat_mean":
             frame[col] = np.float32(state.prep.mat_mean)
+        elif col == K.MAT_MAX:
+            frame[col] = np.float32(state.prep.mat_max)
         else:
             raise NotImplementedError(f"column `{col}` is outside the scope of the permutation engine")
     return frame
@@ -274,6 +287,37 @@ def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, 
     out = eng.run(hi - lo, seed=seed, perm_offset=lo, perm_idx=perm_idx,
                   order=E.ORDER_EXACT if order == "exact" else E.ORDER_FAST, scores=scores,
                   gmean_mode=E.GMEAN_LITERAL if gmean_mode == "literal" else E.GMEAN_PRODUCT)
+    if dist is not None and world > 1:
+        out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
+    return out
+
+
+KH = 0.5          # `cellchat._kh` (`liana/method/sc/_cellchat.py:53`)
+
+
+def observed_cellchat(ligand_trimean: np.ndarray, receptor_trimean: np.ndarray, kh: float = KH) -> np.ndarray:
+    """`_lr_probability` of the observed trimeans, float64 (`_cellchat.py:7-10, 29`); host side so that the
+    threshold is bit-identical to the reference's NumPy math."""
+    lr_prob = np.prod((ligand_trimean, receptor_trimean), axis=0)
+    return lr_prob / (kh + lr_prob)
+
+
+def permutation_counts_trimean(state: PipelineState, tri, obs_prob, n_perms, seed, perm_source, kh=KH,
+                               dist: DistContext | None = None):
+    """CellChat exceedance counts for the kept rows (selection, not summation: no `order` applies).  Sharded over
+    ranks like `permutation_counts`."""
+    eng = state.engine
+    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt)
+    rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
+    lo = (n_perms * rank) // world
+    hi = (n_perms * (rank + 1)) // world
+    if perm_source == "reference":
+        perm_idx = reference_perm_indices(state.prep.n_cells, n_perms, seed)[lo:hi]
+    elif perm_source == "philox":
+        perm_idx = None
+    else:
+        raise ValueError("perm_source must be 'philox' or 'reference'")
+    out = eng.run_trimean(hi - lo, state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_offset=lo, perm_idx=perm_idx)
     if dist is not None and world > 1:
         out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
     return out

@@ -35,6 +35,7 @@ class PreparedInput:
     obs_index: pd.Index           # cell names kept
     n_cells: int                  # kept cells
     mat_mean: float = 0.0         # mean over ALL entries of the prepared matrix (SingleCellSignalR, `_liana_pipe.py:139-140`)
+    mat_max: np.float32 | None = None   # `adata.X.max()` of the prepared matrix (CellChat, `_liana_pipe.py:143-146`)
 
 
 def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False):
@@ -79,7 +80,7 @@ def _make_unique(names: pd.Index) -> pd.Index:
 
 
 def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_raw=False, layer=None,
-                  complex_sep="_", verbose=False) -> PreparedInput:
+                  complex_sep="_", verbose=False, want_max=False) -> PreparedInput:
     """Same checks, order and exception types as `prep_check_adata` (`_pre.py:65-169`); the passes over the
     matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU."""
     if hasattr(adata, "mod"):
@@ -144,7 +145,12 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
             _logg(f"{issues} contain `{complex_sep}`. Consider replacing those!", level="warn", verbose=True)
     order = np.argsort(names, kind="stable")            # genes in alphabetical order (`_pre.py:168`)
     n_all = len(rows) * len(keep_cols)
-    return PreparedInput(var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
+    mat_max = None
+    if want_max:
+        # scipy's sparse .max(): the implicit zeros take part (any prepared matrix that is not fully dense has one)
+        stored_max, n_stored = engine.staged_max()
+        mat_max = stored_max if (n_stored >= n_all and n_stored > 0) else np.float32(max(stored_max, np.float32(0)))
+    return PreparedInput(mat_max=mat_max, var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
                          labels=np.asarray(lab_sub.cat.codes, dtype=np.int32),
                          categories=np.asarray(lab_sub.cat.categories), obs_index=obs.index[rows], n_cells=len(rows),
                          mat_mean=float(stats["kept_total"] / n_all) if n_all else 0.0)

@@ -93,8 +93,8 @@ class ResolvedTriples:
     tgt: np.ndarray          # [T]
     lig_gene: np.ndarray     # [T] gene column of the resolved ligand subunit
     rec_gene: np.ndarray     # [T]
-    ligand_means: np.ndarray     # [T] float32
-    receptor_means: np.ndarray   # [T] float32
+    ligand_means: np.ndarray     # [T] the complex-resolving statistic of the ligand subunit: cluster means
+    receptor_means: np.ndarray   # [T] (float32) or, for CellChat, cluster trimeans (float64)
     ligand_props: np.ndarray     # [T] float64
     receptor_props: np.ndarray   # [T] float64
     keep: np.ndarray         # [T] bool (all True unless return_all_lrs)
@@ -102,7 +102,8 @@ class ResolvedTriples:
 
 def resolve_triples(tables: ResourceTables, means: np.ndarray, props: np.ndarray, expr_prop: float,
                     pair_mask: np.ndarray | None = None, return_all_lrs: bool = False) -> ResolvedTriples:
-    """means float32 [L,G], props float64 [L,G] in the gene-subset column space.
+    """means [L,G] = the statistic named by the method's `complex_cols` (float32 cluster means; float64 cluster
+    trimeans for CellChat), props float64 [L,G], in the gene-subset column space.
     pair_mask [L,L] bool restricts (source, target) pairs (groupby_pairs)."""
     L = means.shape[0]
     # with return_all_lrs the reference de-duplicates subunit rows BEFORE the min-subunit step
@@ -120,6 +121,6 @@ def resolve_triples(tables: ResourceTables, means: np.ndarray, props: np.ndarray
     return ResolvedTriples(
         inter=i_idx.astype(np.int32), src=s_idx.astype(np.int32), tgt=t_idx.astype(np.int32),
         lig_gene=lg[i_idx, s_idx], rec_gene=rg[i_idx, t_idx],
-        ligand_means=lm[i_idx, s_idx].astype(np.float32), receptor_means=rm[i_idx, t_idx].astype(np.float32),
+        ligand_means=lm[i_idx, s_idx].astype(means.dtype), receptor_means=rm[i_idx, t_idx].astype(means.dtype),
         ligand_props=lp[i_idx, s_idx].astype(np.float64), receptor_props=rp[i_idx, t_idx].astype(np.float64),
         keep=keep)

@@ -122,8 +122,13 @@ def save_cellchat_case(name, adata, groupby, n_perms, seed, expr_prop, ref):
     key = ["source", "target", "ligand_complex", "receptor_complex"]
     merged = lr_in[key].merge(res[key + ["lr_probs", "cellchat_pvals"]], on=key, how="left")
     assert len(merged) == len(lr_in) and not merged["cellchat_pvals"].isna().any()
+    full = adata.X.tocsr()
+    full.sort_indices()
     np.savez_compressed(
         os.path.join(OUT, f"{name}_cellchat.npz"),
+        in_indptr=full.indptr.astype(np.int64), in_indices=full.indices.astype(np.int32),
+        in_data=full.data.astype(np.float32), in_shape=np.array(full.shape, dtype=np.int64),
+        in_var_names=np.array(adata.var_names, dtype=str), in_labels=np.array([str(v) for v in adata.obs[groupby]], dtype=str),
         indptr=X.indptr.astype(np.int64), indices=X.indices.astype(np.int32), data=X.data.astype(np.float32),
         shape=np.array(X.shape, dtype=np.int64), labels=cc["labels"], mat_max=np.float32(lr_in["mat_max"].values[0]),
         cube=cc["cube"].astype(np.float64), ligand_idx=lig, receptor_idx=rec, source_idx=src, target_idx=tgt,

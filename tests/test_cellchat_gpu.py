@@ -118,3 +118,57 @@ def test_trimean_philox_equals_index_mode_and_shards_add_up(engine):
     finally:
         engine.set_option("trimean_chunk_nnz", 0)
         engine.set_option("trimean_perm_batch", 0)
+
+
+# ---- the drop-in li.mt.cellchat against frames produced by the reference's own code --------------------------
+import os  # noqa: E402
+
+import pandas as pd  # noqa: E402
+
+import liana_py_b200 as li  # noqa: E402
+from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KEY = ["source", "target", "ligand_complex", "receptor_complex"]
+
+
+def _load_input(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}_cellchat.npz"))
+    X = sparse.csr_matrix((z["in_data"], z["in_indices"], z["in_indptr"]), shape=tuple(z["in_shape"]))
+    obs = pd.DataFrame({"cluster": pd.Categorical(z["in_labels"])}, index=[f"cell{i}" for i in range(X.shape[0])])
+    var = pd.DataFrame(index=pd.Index(z["in_var_names"]))
+    return AnnDataLite(X=X, obs=obs, var=var), int(z["n_perms"]), int(z["seed"]), float(z["expr_prop"])
+
+
+@pytest.mark.parametrize("name", ["small300", "dense700", "ragged90"])
+def test_cellchat_frame_identical_to_reference(name):
+    adata, P, seed, ep = _load_input(name)
+    res = li.mt.cellchat(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep, inplace=False,
+                         perm_source="reference")
+    gold = pd.read_csv(os.path.join(GOLDEN, f"{name}_cellchat.csv.gz"), float_precision="round_trip")
+    assert list(res.columns) == list(gold.columns)
+    a = res.sort_values(KEY).reset_index(drop=True)
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in KEY + ["ligand", "receptor"]:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+    assert a["mat_max"].dtype == np.float32 and np.array_equal(a["mat_max"].values, b["mat_max"].values.astype(np.float32))
+    for c in ["ligand_trimean", "receptor_trimean", "ligand_props", "receptor_props", "lr_probs", "cellchat_pvals"]:
+        assert a[c].dtype == np.float64
+        assert np.array_equal(a[c].values, b[c].values), c                  # bit-identical float64
+    assert np.all(np.diff(res["lr_probs"].values) <= 0)                     # sorted by magnitude, descending
+
+
+def test_cellchat_philox_default_and_no_perms():
+    adata, P, seed, ep = _load_input("dense700")
+    res = li.mt.cellchat(adata, groupby="cluster", use_raw=False, n_perms=None, inplace=False)
+    assert "cellchat_pvals" not in res.columns and "lr_probs" in res.columns
+    ph = li.mt.cellchat(adata, groupby="cluster", use_raw=False, n_perms=300, inplace=False)    # Philox permutations
+    gold = pd.read_csv(os.path.join(GOLDEN, "dense700_cellchat.csv.gz"), float_precision="round_trip")
+    a, b = ph.sort_values(KEY), gold.sort_values(KEY)
+    assert np.array_equal(a["lr_probs"].values, b["lr_probs"].values)
+    assert abs(a["cellchat_pvals"].values.mean() - b["cellchat_pvals"].values.mean()) < 0.03   # another RNG, same null
+    # a custom consensus with CellChat in it
+    agg = li.mt.AggregateClass(li.mt.aggregate_meta, methods=[li.mt.cellphonedb, li.mt.cellchat])
+    out = agg(adata, groupby="cluster", use_raw=False, n_perms=50, inplace=False)
+    assert {"lr_means", "cellphone_pvals", "lr_probs", "cellchat_pvals", "magnitude_rank", "specificity_rank"} <= set(out.columns)
