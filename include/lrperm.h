@@ -177,8 +177,9 @@ int lrperm_run_trimean(lrperm_engine *h, int64_t n_perms, int64_t perm_offset, u
                        uint32_t *counts, int counts_on_device, double *cube_out, int cube_on_device);
 int lrperm_observed_trimean(lrperm_engine *h, double recip, double *trimean, int out_on_device);
 /* Device time (ms) of the stages of the last trimean run, summed over batches: out[0] entry counting
- * (the dominant kernel), out[1] prefix, out[2] rank selection, out[3] interpolation. */
-int lrperm_trimean_timings(lrperm_engine *h, float *out4);
+ * (the dominant kernel), out[1] prefix, out[2] rank selection, out[3] interpolation; out[4] the number of
+ * (chunk, permutation group) warps of the selection pass that had to re-walk their chunk, out[5] all of them. */
+int lrperm_trimean_timings(lrperm_engine *h, float *out6);
 
 /* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32), i.e. the array
  * that reproduces a PHILOX run when passed back as LRPERM_PERMS_INDEX.  The device bijection rho_p (keyed by

@@ -338,9 +338,10 @@ class Engine:
         return out
 
     def trimean_timings(self) -> dict:
-        buf = (C.c_float * 4)()
+        buf = (C.c_float * 6)()
         self._check(self._lib.lrperm_trimean_timings(self._h, C.cast(buf, C.c_void_p)))
-        return {"count_ms": buf[0], "prefix_ms": buf[1], "select_ms": buf[2], "finalize_ms": buf[3]}
+        return {"count_ms": buf[0], "prefix_ms": buf[1], "select_ms": buf[2], "finalize_ms": buf[3],
+                "walked_warps": int(buf[4]), "select_warps": int(buf[5])}
 
     def philox_perms(self, n_cells: int, n_perms: int, seed: int = 1337, perm_offset: int = 0) -> np.ndarray:
         out = np.empty((int(n_perms), int(n_cells)), dtype=np.int32)

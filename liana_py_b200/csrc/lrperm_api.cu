@@ -116,6 +116,9 @@ struct lrperm_engine {
     DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out, small_a, small_b;
 
     // CellChat trimean path (lrperm_trimean.cuh)
+    DevBuf tm_diag, tm_chunk_of_slot, tm_region_dir, tm_walk_flag, tm_walk_list;
+    int64_t tm_select_warps = 0, tm_walked_warps = 0;
+    int32_t tm_n_batches = 0, tm_n_super = 0;
     DevBuf vsc_pairs, tm_chunks, tm_region_ptr, tm_counts, tm_prefix, tm_planes, tm_cube, tm_tgt, tm_roles, thr_d, counts_t;
     bool vsc_ready = false, tm_tables_ready = false;
     int32_t tm_chunk_nnz = 0, tm_perm_batch = 0;        // tuning (0 = auto)
@@ -660,12 +663,14 @@ int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz) {
     }
     std::vector<FastChunk> chunks;
     std::vector<int32_t> region_ptr(1, 0);
+    std::vector<uint8_t> region_dir;
     int32_t slot = 0;
     for (int32_t g = 0; g < G; ++g) {
         const int32_t b[2] = {h->h_csc_ptr[(size_t)g], neg_begin[(size_t)g]};
         const int32_t e[2] = {pos_end[(size_t)g], h->h_csc_ptr[(size_t)g + 1]};
         for (int dir = 0; dir < 2; ++dir) {
             if (e[dir] <= b[dir]) continue;
+            region_dir.push_back((uint8_t)dir);
             for (int32_t s0 = b[dir]; s0 < e[dir]; s0 += chunk_nnz) {
                 FastChunk c;
                 c.gene = g | (dir << kTmDirBit); c.begin = s0; c.end = std::min(e[dir], s0 + chunk_nnz); c.slot = slot++;
@@ -678,6 +683,12 @@ int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz) {
     h->tm_n_chunks = (int32_t)chunks.size();
     h->tm_n_slots = slot;
     h->tm_n_regions = (int32_t)region_ptr.size() - 1;
+    std::vector<int32_t> chunk_of_slot((size_t)std::max(slot, 1), 0);
+    for (size_t i = 0; i < chunks.size(); ++i) chunk_of_slot[(size_t)chunks[i].slot] = (int32_t)i;
+    int rc;
+    if ((rc = upload(h, h->tm_chunk_of_slot, chunk_of_slot.data(), sizeof(int32_t) * chunk_of_slot.size(), 0))) return rc;
+    if (region_dir.empty()) region_dir.push_back(0);
+    if ((rc = upload(h, h->tm_region_dir, region_dir.data(), region_dir.size(), 0))) return rc;
     CK(h->tm_chunks.ensure(sizeof(FastChunk) * std::max<size_t>(chunks.size(), 1)));
     CK(h->tm_region_ptr.ensure(sizeof(int32_t) * region_ptr.size()));
     if (!chunks.empty())
@@ -731,37 +742,55 @@ int build_tm_tables(lrperm_engine* h) {
 }
 
 template <int Q>
-int launch_tm_count_select(lrperm_engine* h, int32_t PB, const uint8_t* slab, cudaEvent_t* ev /*[4]*/) {
+int launch_tm_count(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* counts, uint32_t* prefix, int32_t n_valid, int32_t batch_in_super,
+                    cudaEvent_t* ev /*[3]*/) {
     constexpr int B = 32;
-    const int32_t L = h->L, G = (int32_t)h->G;
+    const int32_t L = h->L;
     const int32_t groups = PB / (32 * Q);
     const int64_t grid = (int64_t)h->tm_n_chunks * groups;
     if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "trimean: too many chunks (%lld CTAs)", (long long)grid);
     const size_t smem_count = (size_t)L * Q * 128 + 16 * B;
-    const size_t smem_sel = smem_count + sizeof(int32_t) * 8 * (size_t)L;
     CK(cudaFuncSetAttribute(fast2_means_kernel<Q, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
-    CK(cudaFuncSetAttribute(tm_select_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
-    const int64_t plane_stride = (int64_t)G * L * PB;
     CK(cudaEventRecord(ev[0], h->stream));
     if (grid > 0) {
         fast2_means_kernel<Q, B, true><<<(unsigned)grid, 32, smem_count, h->stream>>>(
-            h->vsc_pairs.as<int2>(), h->tm_chunks.as<FastChunk>(), h->tm_n_chunks, slab, PB, L, groups, h->tm_counts.as<float>());
+            h->vsc_pairs.as<int2>(), h->tm_chunks.as<FastChunk>(), h->tm_n_chunks, slab, PB, L, groups, counts);
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ev[1], h->stream));
     if (h->tm_n_regions > 0) {
+        uint32_t* wl = h->tm_walk_list.as<uint32_t>();           // [0] item count, [1] cursor, [2..] items
         tm_prefix_kernel<<<grid_for((int64_t)h->tm_n_regions * L * PB, 256, h->sm_count * 16), 256, 0, h->stream>>>(
-            h->tm_counts.as<float>(), h->tm_region_ptr.as<int32_t>(), h->tm_n_regions, L, PB, h->tm_prefix.as<uint32_t>());
+            counts, h->tm_region_ptr.as<int32_t>(), h->tm_region_dir.as<uint8_t>(), h->tm_tgt.as<int32_t>(), h->tm_n_regions, L, PB,
+            32 * Q, n_valid, (uint32_t)batch_in_super * (uint32_t)h->tm_n_slots * (uint32_t)groups, prefix,
+            h->tm_walk_flag.as<uint32_t>(), wl + 2, wl);
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ev[2], h->stream));
-    if (grid > 0) {
-        tm_select_kernel<Q, B><<<(unsigned)grid, 32, smem_sel, h->stream>>>(
-            h->vsc_pairs.as<int2>(), h->tm_chunks.as<FastChunk>(), slab, PB, L, groups, h->tm_counts.as<float>(),
-            h->tm_prefix.as<uint32_t>(), h->tm_tgt.as<int32_t>(), h->tm_planes.as<float>(), plane_stride);
+    return LRPERM_OK;
+}
+
+template <int Q>
+int launch_tm_select(lrperm_engine* h, int32_t PB, int32_t nb, int32_t n_perms_super, size_t slot_elems, size_t plane_elems) {
+    constexpr int B = 32;
+    const int32_t L = h->L;
+    const int32_t groups = PB / (32 * Q);
+    const size_t smem_sel = (size_t)L * Q * 128 + 16 * B + sizeof(int32_t) * 8 * (size_t)L;
+    CK(cudaFuncSetAttribute(tm_select_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+    if (h->tm_n_chunks > 0) {
+        // persistent: as many one-warp CTAs as stay resident (shared memory bound), they pull items off the list
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tm_select_kernel<Q, B>, 32, smem_sel));
+        const unsigned grid = (unsigned)std::max(1, per_sm) * (unsigned)h->sm_count;
+        uint32_t* wl = h->tm_walk_list.as<uint32_t>();
+        tm_select_kernel<Q, B><<<grid, 32, smem_sel, h->stream>>>(
+            h->vsc_pairs.as<int2>(), h->tm_chunks.as<FastChunk>(), h->tm_chunk_of_slot.as<int32_t>(), h->slab.as<uint8_t>(), PB, L, groups,
+            h->tm_n_slots, h->tm_counts.as<float>(), h->tm_prefix.as<uint32_t>(), h->tm_tgt.as<int32_t>(), h->tm_planes.as<float>(),
+            (int64_t)nb * (int64_t)plane_elems, (int64_t)h->N * PB, (int64_t)slot_elems, (int64_t)plane_elems, n_perms_super,
+            wl + 2, wl, wl + 1, h->tm_diag.as<unsigned long long>());
         CK_LAUNCH();
+        h->tm_select_warps += (int64_t)h->tm_n_chunks * groups * nb;
     }
-    CK(cudaEventRecord(ev[3], h->stream));
     return LRPERM_OK;
 }
 
@@ -778,7 +807,9 @@ struct TrimeanArgs {
     int cube_on_device;
 };
 
-// batches of permutations: slab -> count -> prefix -> select -> finalize -> (score) (-> export)
+// Super-batches of nb batches of PB permutations.  Per batch: slab -> count -> prefix (the slab of ONE batch is what
+// should sit in L2 during the count pass).  Per super-batch: ONE select launch over all its batches, one finalize,
+// then per batch score (-> export).
 int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
     const int64_t N = h->N;
     const int32_t G = (int32_t)h->G, L = h->L;
@@ -797,19 +828,28 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
     const int32_t chunk_nnz = h->tm_chunk_nnz ? h->tm_chunk_nnz : 8192;
     if ((rc = build_tm_chunks(h, chunk_nnz))) return rc;
     if ((rc = build_tm_tables(h))) return rc;
-    // permutations per batch: the walk visits cells in VALUE order, so the whole label slab (N x PB bytes)
-    // should sit in L2: <= 64 MiB
+    // permutations per batch: the walk visits cells in VALUE order, so the whole label slab of a batch (N x PB
+    // bytes) should sit in L2: <= 64 MiB
     int32_t PB = h->tm_perm_batch;
     if (!PB) PB = (int32_t)std::min<int64_t>(512, std::max<int64_t>(128, ((64LL << 20) / std::max<int64_t>(N, 1)) / 128 * 128));
     if (a.n_perms < PB) PB = (int32_t)std::max<int64_t>(128, ((a.n_perms + 127) / 128) * 128);
     h->last_pb = PB;
     const size_t slot_elems = (size_t)std::max(h->tm_n_slots, 1) * L * PB;
     const size_t plane_elems = (size_t)G * L * PB;
-    CK(h->slab.ensure((size_t)std::max<int64_t>(N, 1) * PB));
-    CK(h->tm_counts.ensure(sizeof(float) * slot_elems));
-    CK(h->tm_prefix.ensure(sizeof(uint32_t) * slot_elems));
-    CK(h->tm_planes.ensure(sizeof(float) * kTmPlanes * plane_elems));
-    CK(h->tm_cube.ensure(sizeof(double) * plane_elems));
+    const size_t slab_elems = (size_t)std::max<int64_t>(N, 1) * PB;
+    // batches per super-batch: everything of a super-batch stays resident (<= ~12 GiB)
+    const size_t per_batch = slab_elems + 8 * slot_elems + (4 * kTmPlanes + 8) * plane_elems;
+    const int64_t n_batches = (a.n_perms + PB - 1) / PB;
+    const int32_t NB = (int32_t)std::max<int64_t>(1, std::min<int64_t>(n_batches, (int64_t)((12ULL << 30) / std::max<size_t>(per_batch, 1))));
+    CK(h->slab.ensure(slab_elems * NB));
+    CK(h->tm_counts.ensure(sizeof(float) * slot_elems * NB));
+    CK(h->tm_prefix.ensure(sizeof(uint32_t) * slot_elems * NB));
+    CK(h->tm_planes.ensure(sizeof(float) * kTmPlanes * plane_elems * NB));
+    CK(h->tm_cube.ensure(sizeof(double) * plane_elems * NB));
+    const size_t n_items_max = (size_t)std::max(h->tm_n_slots, 1) * (size_t)(PB / (32 * Q)) * (size_t)NB;
+    if (n_items_max >= 0xffffffffULL) return h->fail(LRPERM_ERR_UNSUPPORTED, "trimean: too many (chunk, group) items per super-batch");
+    CK(h->tm_walk_flag.ensure(sizeof(uint32_t) * n_items_max));
+    CK(h->tm_walk_list.ensure(sizeof(uint32_t) * (n_items_max + 2)));
     // label bytes pre-scaled by Q/2 (see fast2_means_kernel)
     const int32_t scale = Q / 2;
     if (h->labels8s_scale != scale) {
@@ -820,106 +860,146 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
         }
         h->labels8s_scale = scale;
     }
-    const int64_t n_batches = (a.n_perms + PB - 1) / PB;
-    const size_t n_events = (size_t)n_batches * 8 + 2;
+    const int64_t n_super = (n_batches + NB - 1) / NB;
+    // events: [0] start; per batch 4 (slab start, count start, count end, prefix end) + 2 (score start, score end);
+    // per super-batch 3 (select start, select end, finalize end); last = end
+    const size_t n_events = 2 + (size_t)n_batches * 6 + (size_t)n_super * 3;
     while (h->events.size() < n_events) {
         cudaEvent_t ev;
         CK(cudaEventCreate(&ev));
         h->events.push_back(ev);
     }
+    CK(h->tm_diag.ensure(8));
+    CK(cudaMemsetAsync(h->tm_diag.p, 0, 8, h->stream));
+    h->tm_select_warps = 0;
+    h->tm_n_batches = (int32_t)n_batches;
+    h->tm_n_super = (int32_t)n_super;
     CK(cudaEventRecord(h->events[0], h->stream));
     const size_t idx_elem = a.perm_idx_is_64 ? 8 : 4;
-    for (int64_t b = 0; b < n_batches; ++b) {
-        cudaEvent_t* ev = &h->events[1 + (size_t)b * 8];
-        const int64_t p0 = b * PB;
-        const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
-        CK(cudaEventRecord(ev[0], h->stream));
-        // ---- label slab ----
-        if (pb < PB) CK(cudaMemsetAsync(h->slab.p, 0, (size_t)N * PB, h->stream));
-        if (a.perm_source < 0) {
-            slab_identity_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels8s.as<uint8_t>(), (int32_t)N, h->slab.as<uint8_t>(), PB);
-        } else {
-            PermSource ps{};
-            ps.is64 = a.perm_idx_is_64;
-            ps.seed = a.seed;
-            ps.perm_id0 = a.perm_offset + p0;
-            ps.philox = a.perm_source == LRPERM_PERMS_PHILOX;
-            if (ps.philox) {
-                const int cells_per_block = 128;
-                dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
-                const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
-                slab_philox_kernel<<<grd, 128, tab_smem, h->stream>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
-                                                                      h->bucket_shift, L, scale, (int32_t)N, pb, h->slab.as<uint8_t>(), PB, cells_per_block);
+    for (int64_t sb = 0; sb < n_super; ++sb) {
+        const int64_t b0 = sb * NB;
+        const int32_t nb = (int32_t)std::min<int64_t>(NB, n_batches - b0);
+        const int32_t n_perms_super = (int32_t)std::min<int64_t>((int64_t)nb * PB, a.n_perms - b0 * PB);
+        CK(cudaMemsetAsync(h->tm_planes.p, 0, sizeof(float) * kTmPlanes * plane_elems * nb, h->stream));
+        CK(cudaMemsetAsync(h->tm_walk_flag.p, 0, sizeof(uint32_t) * n_items_max, h->stream));
+        CK(cudaMemsetAsync(h->tm_walk_list.p, 0, 2 * sizeof(uint32_t), h->stream));
+        for (int32_t bi = 0; bi < nb; ++bi) {
+            const int64_t b = b0 + bi;
+            cudaEvent_t* ev = &h->events[1 + (size_t)b * 6];
+            const int64_t p0 = b * PB;
+            const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+            uint8_t* slab = h->slab.as<uint8_t>() + slab_elems * bi;
+            CK(cudaEventRecord(ev[0], h->stream));
+            // ---- label slab ----
+            if (pb < PB) CK(cudaMemsetAsync(slab, 0, slab_elems, h->stream));
+            if (a.perm_source < 0) {
+                slab_identity_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels8s.as<uint8_t>(), (int32_t)N, slab, PB);
             } else {
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
-                if (a.perm_idx_on_device) ps.idx = src;
-                else {
-                    if ((rc = upload(h, h->perm_dev, src, idx_elem * (size_t)pb * (size_t)N, 0))) return rc;
-                    ps.idx = h->perm_dev.p;
+                PermSource ps{};
+                ps.is64 = a.perm_idx_is_64;
+                ps.seed = a.seed;
+                ps.perm_id0 = a.perm_offset + p0;
+                ps.philox = a.perm_source == LRPERM_PERMS_PHILOX;
+                if (ps.philox) {
+                    const int cells_per_block = 128;
+                    dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
+                    const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
+                    slab_philox_kernel<<<grd, 128, tab_smem, h->stream>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
+                                                                          h->bucket_shift, L, scale, (int32_t)N, pb, slab, PB, cells_per_block);
+                } else {
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
+                    if (a.perm_idx_on_device) ps.idx = src;
+                    else {
+                        if ((rc = upload(h, h->perm_dev, src, idx_elem * (size_t)pb * (size_t)N, 0))) return rc;
+                        ps.idx = h->perm_dev.p;
+                    }
+                    dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
+                    slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, h->labels8s.as<uint8_t>(), (int32_t)N, pb, slab, PB);
                 }
-                dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
-                slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, h->labels8s.as<uint8_t>(), (int32_t)N, pb, h->slab.as<uint8_t>(), PB);
             }
+            CK_LAUNCH();
+            // ---- count, prefix ----
+            float* counts = h->tm_counts.as<float>() + slot_elems * bi;
+            uint32_t* prefix = h->tm_prefix.as<uint32_t>() + slot_elems * bi;
+            if (Q == 4) rc = launch_tm_count<4>(h, PB, slab, counts, prefix, pb, bi, ev + 1);
+            else rc = launch_tm_count<2>(h, PB, slab, counts, prefix, pb, bi, ev + 1);
+            if (rc) return rc;
         }
-        CK_LAUNCH();
-        CK(cudaMemsetAsync(h->tm_planes.p, 0, sizeof(float) * kTmPlanes * plane_elems, h->stream));
-        // ---- count, prefix, select ----
-        if (Q == 4) rc = launch_tm_count_select<4>(h, PB, h->slab.as<uint8_t>(), ev + 1);
-        else rc = launch_tm_count_select<2>(h, PB, h->slab.as<uint8_t>(), ev + 1);
+        cudaEvent_t* sev = &h->events[1 + (size_t)n_batches * 6 + (size_t)sb * 3];
+        // ---- select: one launch over the batches of the super-batch ----
+        CK(cudaEventRecord(sev[0], h->stream));
+        if (Q == 4) rc = launch_tm_select<4>(h, PB, nb, n_perms_super, slot_elems, plane_elems);
+        else rc = launch_tm_select<2>(h, PB, nb, n_perms_super, slot_elems, plane_elems);
         if (rc) return rc;
-        // ---- numpy's interpolation arithmetic -> float64 cube ----
+        CK(cudaEventRecord(sev[1], h->stream));
+        // ---- numpy's interpolation arithmetic -> float64 cube [batch][G][L][PB] ----
         {
-            const int grid = grid_for((int64_t)plane_elems, 256, h->sm_count * 16);
+            const int64_t total = (int64_t)plane_elems * nb;
+            const int grid = grid_for(total, 256, h->sm_count * 16);
             if (a.perm_source < 0)
-                tm_finalize_kernel<true><<<grid, 256, 0, h->stream>>>(h->tm_planes.as<float>(), (int64_t)plane_elems, h->tm_roles.as<TmRoles>(),
-                                                                      G, L, PB, a.r32, a.r64, h->tm_cube.as<double>(), PB);
+                tm_finalize_kernel<true><<<grid, 256, 0, h->stream>>>(h->tm_planes.as<float>(), total, h->tm_roles.as<TmRoles>(),
+                                                                      G * nb, L, PB, a.r32, a.r64, h->tm_cube.as<double>(), PB);
             else
-                tm_finalize_kernel<false><<<grid, 256, 0, h->stream>>>(h->tm_planes.as<float>(), (int64_t)plane_elems, h->tm_roles.as<TmRoles>(),
-                                                                       G, L, PB, a.r32, a.r64, h->tm_cube.as<double>(), PB);
+                tm_finalize_kernel<false><<<grid, 256, 0, h->stream>>>(h->tm_planes.as<float>(), total, h->tm_roles.as<TmRoles>(),
+                                                                       G * nb, L, PB, a.r32, a.r64, h->tm_cube.as<double>(), PB);
             CK_LAUNCH();
         }
-        CK(cudaEventRecord(ev[5], h->stream));
-        if (a.score && T > 0) {
-            score_count_cellchat_kernel<<<(unsigned)((T + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, h->stream>>>(
-                h->tm_cube.as<double>(), PB, pb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_d.as<double>(), a.kh, T,
-                h->counts_t.as<uint32_t>());
-            CK_LAUNCH();
-        }
-        CK(cudaEventRecord(ev[6], h->stream));
-        if (a.cube_out) {
-            double* dst = a.cube_out + (size_t)p0 * L * G;
-            double* dev_dst = dst;
-            if (!a.cube_on_device) { CK(h->stage_out.ensure(sizeof(double) * (size_t)pb * L * G)); dev_dst = h->stage_out.as<double>(); }
-            dim3 blk(32, 8), grd((G + 31) / 32, (pb + 31) / 32, L);
-            cube_export_f64_kernel<<<grd, blk, 0, h->stream>>>(h->tm_cube.as<double>(), G, L, PB, pb, dev_dst);
-            CK_LAUNCH();
-            if (!a.cube_on_device) {
-                CK(cudaMemcpyAsync(dst, dev_dst, sizeof(double) * (size_t)pb * L * G, cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaStreamSynchronize(h->stream));
+        CK(cudaEventRecord(sev[2], h->stream));
+        for (int32_t bi = 0; bi < nb; ++bi) {
+            const int64_t b = b0 + bi;
+            cudaEvent_t* ev = &h->events[1 + (size_t)b * 6];
+            const int64_t p0 = b * PB;
+            const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
+            const double* cube = h->tm_cube.as<double>() + plane_elems * bi;
+            CK(cudaEventRecord(ev[4], h->stream));
+            if (a.score && T > 0) {
+                score_count_cellchat_kernel<<<(unsigned)((T + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, h->stream>>>(
+                    cube, PB, pb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_d.as<double>(), a.kh, T, h->counts_t.as<uint32_t>());
+                CK_LAUNCH();
+            }
+            CK(cudaEventRecord(ev[5], h->stream));
+            if (a.cube_out) {
+                double* dst = a.cube_out + (size_t)p0 * L * G;
+                double* dev_dst = dst;
+                if (!a.cube_on_device) { CK(h->stage_out.ensure(sizeof(double) * (size_t)pb * L * G)); dev_dst = h->stage_out.as<double>(); }
+                dim3 blk(32, 8), grd((G + 31) / 32, (pb + 31) / 32, L);
+                cube_export_f64_kernel<<<grd, blk, 0, h->stream>>>(cube, G, L, PB, pb, dev_dst);
+                CK_LAUNCH();
+                if (!a.cube_on_device) {
+                    CK(cudaMemcpyAsync(dst, dev_dst, sizeof(double) * (size_t)pb * L * G, cudaMemcpyDeviceToHost, h->stream));
+                    CK(cudaStreamSynchronize(h->stream));
+                }
             }
         }
-        CK(cudaEventRecord(ev[7], h->stream));
     }
-    CK(cudaEventRecord(h->events[1 + (size_t)n_batches * 8], h->stream));
+    CK(cudaEventRecord(h->events[n_events - 1], h->stream));
+    unsigned long long walked = 0;
+    CK(cudaMemcpyAsync(&walked, h->tm_diag.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->tm_walked_warps = (int64_t)walked;
     return LRPERM_OK;
 }
 
-int collect_trimean_timings(lrperm_engine* h, int64_t n_batches) {
+int collect_trimean_timings(lrperm_engine* h) {
+    const int64_t n_batches = h->tm_n_batches, n_super = h->tm_n_super;
     h->t_setup = h->t_means = h->t_score = h->t_main = 0.f;
     for (float& v : h->tm_ms) v = 0.f;
     h->n_main_launches = (int32_t)n_batches;
+    float ms;
     for (int64_t b = 0; b < n_batches; ++b) {
-        cudaEvent_t* ev = &h->events[1 + (size_t)b * 8];
-        float ms;
+        cudaEvent_t* ev = &h->events[1 + (size_t)b * 6];
         CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); h->t_setup += ms;
         CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); h->tm_ms[0] += ms; h->t_main += ms;
         CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); h->tm_ms[1] += ms;
-        CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); h->tm_ms[2] += ms;
-        CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); h->tm_ms[3] += ms;
-        CK(cudaEventElapsedTime(&ms, ev[1], ev[5])); h->t_means += ms;
-        CK(cudaEventElapsedTime(&ms, ev[5], ev[6])); h->t_score += ms;
+        CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); h->t_score += ms;
     }
-    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[1 + (size_t)n_batches * 8]));
+    for (int64_t sb = 0; sb < n_super; ++sb) {
+        cudaEvent_t* sev = &h->events[1 + (size_t)n_batches * 6 + (size_t)sb * 3];
+        CK(cudaEventElapsedTime(&ms, sev[0], sev[1])); h->tm_ms[2] += ms;
+        CK(cudaEventElapsedTime(&ms, sev[1], sev[2])); h->tm_ms[3] += ms;
+    }
+    h->t_means = h->tm_ms[0] + h->tm_ms[1] + h->tm_ms[2] + h->tm_ms[3];
+    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[1 + (size_t)n_batches * 6 + (size_t)n_super * 3]));
     return LRPERM_OK;
 }
 
@@ -980,7 +1060,8 @@ void lrperm_destroy(lrperm_engine* h) {
                       &h->chunks, &h->gene_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b,
                       &h->vsc_pairs, &h->tm_chunks, &h->tm_region_ptr, &h->tm_counts, &h->tm_prefix, &h->tm_planes, &h->tm_cube,
-                      &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t})
+                      &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t, &h->tm_diag, &h->tm_chunk_of_slot, &h->tm_region_dir,
+                      &h->tm_walk_flag, &h->tm_walk_list})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1676,7 +1757,7 @@ int lrperm_run_trimean(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, u
     if ((rc = run_trimean_batches(h, a))) { cudaStreamSynchronize(h->stream); return rc; }
     if (score && (rc = download(h, counts, h->counts_t.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    return collect_trimean_timings(h, (n_perms + h->last_pb - 1) / std::max(h->last_pb, 1));
+    return collect_trimean_timings(h);
 }
 
 int lrperm_observed_trimean(lrperm_engine* h, double recip, double* trimean, int out_on_device) {
@@ -1694,12 +1775,14 @@ int lrperm_observed_trimean(lrperm_engine* h, double recip, double* trimean, int
     if ((rc = run_trimean_batches(h, a))) { cudaStreamSynchronize(h->stream); return rc; }
     if (!out_on_device) CK(cudaMemcpyAsync(trimean, dev_dst, sizeof(double) * (size_t)L * G, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return collect_trimean_timings(h, 1);
+    return collect_trimean_timings(h);
 }
 
-int lrperm_trimean_timings(lrperm_engine* h, float* out4) {
-    if (!h || !out4) return LRPERM_ERR_INVALID;
-    for (int i = 0; i < 4; ++i) out4[i] = h->tm_ms[i];
+int lrperm_trimean_timings(lrperm_engine* h, float* out6) {
+    if (!h || !out6) return LRPERM_ERR_INVALID;
+    for (int i = 0; i < 4; ++i) out6[i] = h->tm_ms[i];
+    out6[4] = (float)h->tm_walked_warps;
+    out6[5] = (float)h->tm_select_warps;
     return LRPERM_OK;
 }
 

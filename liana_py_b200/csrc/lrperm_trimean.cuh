@@ -18,9 +18,10 @@
 //
 // Per batch of permutations (label slab as in FAST mode):
 //   1. count   fast2_means_kernel<COUNT>: entries per (chunk, cluster, permutation)            - the heavy pass
-//   2. prefix  tm_prefix_kernel: exclusive prefix of the counts over the chunks of a (gene, sign) region
-//   3. select  tm_select_kernel: only the (chunk, permutation group) warps in which a wanted rank falls
-//              re-walk their chunk with a per-(cluster, permutation) countdown and store the value met at 0
+//   2. prefix  tm_prefix_kernel: exclusive prefix of the counts over the chunks of a (gene, sign) region; lists the
+//              (chunk, permutation group) items in which a wanted rank falls (a few % of all)
+//   3. select  tm_select_kernel: persistent warps re-walk the listed chunks with a per-(cluster, permutation)
+//              countdown and store the value met at 0
 //   4. final   tm_finalize_kernel: numpy's interpolation arithmetic on the selected values -> float64 cube
 //   5. score   score_count_cellchat_kernel
 #pragma once
@@ -80,19 +81,37 @@ __global__ void slab_identity_kernel(const uint8_t* __restrict__ labels8s, int32
     if (i < N) slab[(int64_t)i * PB] = labels8s[i];
 }
 
-// exclusive prefix of the per-chunk counts over the chunks (slots) of one region, per (cluster, permutation)
+// exclusive prefix of the per-chunk counts over the chunks (slots) of one region, per (cluster, permutation); and,
+// while the running count passes a wanted rank of the cluster, the (slot, permutation group) pair is appended ONCE to
+// the work list of the select pass (walk_flag de-duplicates; the list order is arbitrary, every item writes its
+// own outputs).  item = (batch * n_slots + slot) * groups + group.
 __global__ void tm_prefix_kernel(const float* __restrict__ counts /*[slot][L][PB]*/, const int32_t* __restrict__ region_ptr /*[R+1]*/,
-                                 int32_t R, int32_t L, int32_t PB, uint32_t* __restrict__ prefix /*[slot][L][PB]*/) {
+                                 const uint8_t* __restrict__ region_dir /*[R]*/, const int32_t* __restrict__ tm_tgt /*[2][L][8]*/,
+                                 int32_t R, int32_t L, int32_t PB, int32_t perms_per_group, int32_t n_valid,
+                                 uint32_t item_base /* batch * n_slots * groups */, uint32_t* __restrict__ prefix /*[slot][L][PB]*/,
+                                 uint32_t* __restrict__ walk_flag, uint32_t* __restrict__ walk_list, uint32_t* __restrict__ walk_count) {
     const int64_t total = (int64_t)R * L * PB;
+    const int groups = PB / perms_per_group;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t cp = i % ((int64_t)L * PB);
         const int r = (int)(i / ((int64_t)L * PB));
+        const int c = (int)(cp / PB), p = (int)(cp % PB);
+        const int32_t* tgt = tm_tgt + ((int)region_dir[r] * L + c) * 8;
+        const int m = (p < n_valid) ? __ldg(tgt + 6) : 0;
+        int k = 0;
+        uint32_t next = m ? (uint32_t)__ldg(tgt) : 0xffffffffu;       // smallest wanted rank above the running count
         uint32_t run = 0;
         const int s0 = region_ptr[r], s1 = region_ptr[r + 1];
+        const int group = p / perms_per_group;
         for (int sl = s0; sl < s1; ++sl) {
             const int64_t at = (int64_t)sl * L * PB + cp;
             prefix[at] = run;
             run += (uint32_t)__ldcs(&counts[at]);
+            if (run >= next) {                                         // a wanted rank falls inside slot sl
+                const uint32_t item = item_base + (uint32_t)sl * (uint32_t)groups + (uint32_t)group;
+                if (walk_flag[item] == 0 && atomicExch(&walk_flag[item], 1u) == 0) walk_list[atomicAdd(walk_count, 1u)] = item;
+                do { ++k; next = (k < m) ? (uint32_t)__ldg(tgt + k) : 0xffffffffu; } while (run >= next);
+            }
         }
     }
 }
@@ -106,149 +125,186 @@ __device__ __forceinline__ uint32_t tm_label_byte(const typename LabelVec<Q>::ty
     return (label_word<Q>(lw, q) >> (8 * (q & 3))) & 0xffu;
 }
 
+// A countdown reached zero: the value of this entry is the wanted order statistic k of (cluster, permutation);
+// store it and re-arm the state with the distance to the cluster's next wanted rank.  Out of line (the caller is
+// unrolled 2*B times); the Q states are re-read together, the rare body runs only in the lanes that hit.
+template <int Q>
+__device__ __noinline__ void tm_hit(unsigned char* bins, const int32_t* tgt_s, float* out_base, int64_t plane_stride, int32_t PB,
+                                    uint32_t lane4, uint32_t lw, float v, int dir) {
+    uint32_t* b[Q];
+    uint32_t st[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) b[q] = reinterpret_cast<uint32_t*>(bins + __byte_perm(lw, lane4, 0x5504u | ((uint32_t)q << 4)) + q * 128);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) st[q] = *b[q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        if (st[q] < 8u) {
+            const int k = (int)st[q];
+            const int c = (int)(((lw >> (8 * q)) & 0xffu) / (Q / 2));
+            const int4 t4 = *reinterpret_cast<const int4*>(tgt_s + c * 8 + (k & 4));      // ranks k&4 .. k&4+3
+            const int m = tgt_s[c * 8 + 6];
+            const int plane = dir ? k : m - 1 - k;
+            out_base[(int64_t)plane * plane_stride + (int64_t)c * PB + q] = v;
+            const int cur = (k & 3) == 0 ? t4.x : (k & 3) == 1 ? t4.y : (k & 3) == 2 ? t4.z : t4.w;
+            const int nxt = (k & 3) == 0 ? t4.y : (k & 3) == 1 ? t4.z : (k & 3) == 2 ? t4.w : tgt_s[c * 8 + 4];
+            *b[q] = (k + 1 < m) ? ((uint32_t)(nxt - cur) << 3) | (uint32_t)(k + 1) : kTmNever;
+        }
+    }
+}
+
 template <int Q, int B>
 __global__ void __launch_bounds__(32)
-tm_select_kernel(const int2* __restrict__ vsc_pairs, const FastChunk* __restrict__ chunks, const uint8_t* __restrict__ slab,
-                 int32_t PB, int32_t L, int32_t groups_per_batch, const float* __restrict__ counts, const uint32_t* __restrict__ prefix,
+tm_select_kernel(const int2* __restrict__ vsc_pairs, const FastChunk* __restrict__ chunks, const int32_t* __restrict__ chunk_of_slot,
+                 const uint8_t* __restrict__ slab_all, int32_t PB, int32_t L, int32_t groups_per_batch, int32_t n_slots,
+                 const float* __restrict__ counts_all, const uint32_t* __restrict__ prefix_all,
                  const int32_t* __restrict__ tm_tgt /*[2][L][8]: ranks k<6 ascending, [6] = number of ranks*/,
-                 float* __restrict__ planes /*[6][G][L][PB]*/, int64_t plane_stride) {
+                 float* __restrict__ planes_all /*[6][batch][G][L][PB]*/, int64_t plane_stride,
+                 int64_t slab_batch_stride, int64_t slot_batch_stride, int64_t plane_batch_stride, int32_t n_perms_total,
+                 const uint32_t* __restrict__ walk_list, const uint32_t* __restrict__ walk_count, uint32_t* __restrict__ cursor,
+                 unsigned long long* __restrict__ n_walked) {
     extern __shared__ __align__(16) unsigned char smem2[];
     using LV = typename LabelVec<Q>::type;
     static_assert(Q == 2 || Q == 4, "label byte = cluster * Q/2");
     const int lane = threadIdx.x;
-    const int chunk_id = (int)(blockIdx.x / (unsigned)groups_per_batch);
-    const int group = (int)(blockIdx.x - (unsigned)chunk_id * (unsigned)groups_per_batch);
-    const FastChunk ch = chunks[chunk_id];
-    const int dir = (ch.gene >> kTmDirBit) & 1;
-    const int gene = ch.gene & ((1 << kTmDirBit) - 1);
     const int bins_bytes = L * Q * 128;
     unsigned char* bins = smem2;
     int* st_cell = reinterpret_cast<int*>(smem2 + bins_bytes);                 // [2][B]
     float* st_val = reinterpret_cast<float*>(smem2 + bins_bytes + 2 * B * 4);  // [2][B]
     int32_t* tgt_s = reinterpret_cast<int32_t*>(smem2 + bins_bytes + 4 * B * 4);   // [L][8]
-    for (int i = lane; i < L * 8; i += 32) tgt_s[i] = tm_tgt[dir * L * 8 + i];
-    __syncwarp();
-
-    // ---- initial states from the prefix counts; leave if no wanted rank falls inside this chunk ----
-    const int p_first = group * 32 * Q + lane * Q;
-    bool any = false;
-    {
-        const int64_t base = (int64_t)ch.slot * L * PB + p_first;
-        uint32_t* st = reinterpret_cast<uint32_t*>(bins) + lane;
-        for (int c = 0; c < L; ++c) {
-            uint32_t pre[Q];
-            float cnt[Q];
-            if (Q == 4) {
-                const uint4 a = *reinterpret_cast<const uint4*>(prefix + base + (int64_t)c * PB);
-                const float4 b = *reinterpret_cast<const float4*>(counts + base + (int64_t)c * PB);
-                pre[0] = a.x; pre[1] = a.y; pre[Q > 2 ? 2 : 0] = a.z; pre[Q > 2 ? 3 : 0] = a.w;
-                cnt[0] = b.x; cnt[1] = b.y; cnt[Q > 2 ? 2 : 0] = b.z; cnt[Q > 2 ? 3 : 0] = b.w;
-            } else {
-                const uint2 a = *reinterpret_cast<const uint2*>(prefix + base + (int64_t)c * PB);
-                const float2 b = *reinterpret_cast<const float2*>(counts + base + (int64_t)c * PB);
-                pre[0] = a.x; pre[1] = a.y; cnt[0] = b.x; cnt[1] = b.y;
-            }
-            const int m = tgt_s[c * 8 + 6];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                int k = 0;
-                while (k < m && (uint32_t)tgt_s[c * 8 + k] <= pre[q]) ++k;
-                uint32_t state = kTmNever;
-                if (k < m) {
-                    const uint32_t cd = (uint32_t)tgt_s[c * 8 + k] - pre[q];
-                    state = (cd << 3) | (uint32_t)k;
-                    any |= cd <= (uint32_t)cnt[q];
-                }
-                st[(c * Q + q) * 32] = state;
-            }
-        }
-    }
-    if (!__any_sync(0xffffffffu, any)) return;
-    __syncwarp();
-
-    const LV* __restrict__ slab_w = reinterpret_cast<const LV*>(slab) + (group * 32 + lane);
-    const int64_t row_words = PB / Q;
     const uint32_t lane4 = (uint32_t)lane * 4u;
-    const int first_cell = __ldg(&vsc_pairs[ch.begin]).x;
-    float* const out_base = planes + ((int64_t)gene * L) * PB + p_first;
+    const uint32_t n_items = *walk_count;
+    if (blockIdx.x == 0 && lane == 0) atomicAdd(n_walked, (unsigned long long)n_items);     // diagnostic
+    int tgt_dir = -1;
 
-    auto load_pair = [&](int k) -> int2 {
-        return (lane < B && k + lane < ch.end) ? __ldg(&vsc_pairs[k + lane]) : make_int2(first_cell, 0);
-    };
-    auto stage = [&](int buf, int2 pr) {
+    // Persistent warp: the work list holds only the (batch, chunk, permutation group) items in which a wanted rank
+    // falls (a few % of all); a lone walking warp is latency-bound, so every SM keeps as many of them resident as
+    // its shared memory allows and they pull items until the list is empty.
+    for (;;) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(cursor, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
+        const uint32_t item = walk_list[it];
+        const int group = (int)(item % (uint32_t)groups_per_batch);
+        const uint32_t bs = item / (uint32_t)groups_per_batch;
+        const int slot = (int)(bs % (uint32_t)n_slots);
+        const int batch = (int)(bs / (uint32_t)n_slots);
+        const FastChunk ch = chunks[chunk_of_slot[slot]];
+        const int dir = (ch.gene >> kTmDirBit) & 1;
+        const int gene = ch.gene & ((1 << kTmDirBit) - 1);
+        const uint8_t* slab = slab_all + batch * slab_batch_stride;
+        const float* counts = counts_all + batch * slot_batch_stride;
+        const uint32_t* prefix = prefix_all + batch * slot_batch_stride;
+        float* planes = planes_all + batch * plane_batch_stride;
+        const int n_valid = min(PB, n_perms_total - batch * PB);     // permutations of this batch that exist
         __syncwarp();
-        if (lane < B) { st_cell[buf * B + lane] = pr.x; st_val[buf * B + lane] = __int_as_float(pr.y); }
+        if (dir != tgt_dir) {
+            for (int i = lane; i < L * 8; i += 32) tgt_s[i] = tm_tgt[dir * L * 8 + i];
+            tgt_dir = dir;
+        }
         __syncwarp();
-    };
-    auto fetch_labels = [&](int buf, LV (&lw)[B]) {
+
+        // ---- initial states from the prefix counts ----
+        const int p_first = group * 32 * Q + lane * Q;
+        {
+            const int64_t base = (int64_t)slot * L * PB + p_first;
+            uint32_t* st = reinterpret_cast<uint32_t*>(bins) + lane;
+#pragma unroll 2
+            for (int c = 0; c < L; ++c) {
+                uint32_t pre[Q];
+                if (Q == 4) {
+                    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(prefix + base + (int64_t)c * PB));
+                    pre[0] = a.x; pre[1] = a.y; pre[Q > 2 ? 2 : 0] = a.z; pre[Q > 2 ? 3 : 0] = a.w;
+                } else {
+                    const uint2 a = __ldcs(reinterpret_cast<const uint2*>(prefix + base + (int64_t)c * PB));
+                    pre[0] = a.x; pre[1] = a.y;
+                }
+                const int m = tgt_s[c * 8 + 6];
 #pragma unroll
-        for (int u = 0; u < B; u += 4) {
-            const int4 c4 = *reinterpret_cast<const int4*>(st_cell + buf * B + u);
-            lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
-            lw[u + 1] = __ldg(slab_w + (int64_t)c4.y * row_words);
-            lw[u + 2] = __ldg(slab_w + (int64_t)c4.z * row_words);
-            lw[u + 3] = __ldg(slab_w + (int64_t)c4.w * row_words);
-        }
-    };
-    // one entry: decrement the Q states; rarely (<= 6 times per cluster and permutation) a countdown hits zero
-    auto entry = [&](const LV& lw, float v, uint32_t dec) {
-        uint32_t* b[Q];
-        uint32_t s[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t off = __byte_perm(label_word<Q>(lw, q), lane4, 0x5504u | ((uint32_t)(q & 3) << 4));
-            b[q] = reinterpret_cast<uint32_t*>(bins + off + q * 128);
-        }
-#pragma unroll
-        for (int q = 0; q < Q; ++q) s[q] = *b[q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) s[q] -= dec;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) *b[q] = s[q];
-        uint32_t mn = s[0];
-#pragma unroll
-        for (int q = 1; q < Q; ++q) mn = min(mn, s[q]);
-        if (mn < 8u && dec) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                if (s[q] < 8u) {
-                    const int k = (int)s[q];
-                    const int c = (int)(tm_label_byte<Q>(lw, q) / (Q / 2));
-                    const int m = tgt_s[c * 8 + 6];
-                    const int plane = dir ? k : m - 1 - k;
-                    out_base[(int64_t)plane * plane_stride + (int64_t)c * PB + q] = v;
-                    *b[q] = (k + 1 < m) ? ((uint32_t)(tgt_s[c * 8 + k + 1] - tgt_s[c * 8 + k]) << 3) | (uint32_t)(k + 1) : kTmNever;
+                for (int q = 0; q < Q; ++q) {
+                    int k = 0;
+                    while (k < m && (uint32_t)tgt_s[c * 8 + k] <= pre[q]) ++k;
+                    uint32_t state = kTmNever;
+                    if (k < m && p_first + q < n_valid) state = (((uint32_t)tgt_s[c * 8 + k] - pre[q]) << 3) | (uint32_t)k;
+                    st[(c * Q + q) * 32] = state;
                 }
             }
         }
-    };
-    auto update = [&](int buf, const LV (&lw)[B], int k0) {
-#pragma unroll
-        for (int u = 0; u < B; u += 4) {
-            const float4 v4 = *reinterpret_cast<const float4*>(st_val + buf * B + u);
-            entry(lw[u + 0], v4.x, (k0 + u + 0 < ch.end) ? 8u : 0u);
-            entry(lw[u + 1], v4.y, (k0 + u + 1 < ch.end) ? 8u : 0u);
-            entry(lw[u + 2], v4.z, (k0 + u + 2 < ch.end) ? 8u : 0u);
-            entry(lw[u + 3], v4.w, (k0 + u + 3 < ch.end) ? 8u : 0u);
-        }
-    };
+        __syncwarp();
 
-    LV lwA[B], lwB[B];
-    int2 pr = load_pair(ch.begin);
-    stage(0, pr);
-    fetch_labels(0, lwA);
-    pr = load_pair(ch.begin + B);
-    for (int k = ch.begin; k < ch.end; k += 2 * B) {
-        stage(1, pr);
-        pr = load_pair(k + 2 * B);
-        const bool more1 = k + B < ch.end;
-        if (more1) fetch_labels(1, lwB);
-        update(0, lwA, k);
-        if (!more1) break;
+        const LV* __restrict__ slab_w = reinterpret_cast<const LV*>(slab) + (group * 32 + lane);
+        const int64_t row_words = PB / Q;
+        const int first_cell = __ldg(&vsc_pairs[ch.begin]).x;
+        float* const out_base = planes + ((int64_t)gene * L) * PB + p_first;
+
+        auto load_pair = [&](int k) -> int2 {
+            return (lane < B && k + lane < ch.end) ? __ldg(&vsc_pairs[k + lane]) : make_int2(first_cell, 0);
+        };
+        auto stage = [&](int buf, int2 pr) {
+            __syncwarp();
+            if (lane < B) { st_cell[buf * B + lane] = pr.x; st_val[buf * B + lane] = __int_as_float(pr.y); }
+            __syncwarp();
+        };
+        auto fetch_labels = [&](int buf, LV (&lw)[B]) {
+#pragma unroll
+            for (int u = 0; u < B; u += 4) {
+                const int4 c4 = *reinterpret_cast<const int4*>(st_cell + buf * B + u);
+                lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
+                lw[u + 1] = __ldg(slab_w + (int64_t)c4.y * row_words);
+                lw[u + 2] = __ldg(slab_w + (int64_t)c4.z * row_words);
+                lw[u + 3] = __ldg(slab_w + (int64_t)c4.w * row_words);
+            }
+        };
+        // one entry: decrement the Q states; rarely (<= 6 times per cluster and permutation) a countdown hits zero
+        auto entry = [&](const LV& lw, float v, uint32_t dec) {
+            uint32_t* b[Q];
+            uint32_t s[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const uint32_t off = __byte_perm(label_word<Q>(lw, q), lane4, 0x5504u | ((uint32_t)(q & 3) << 4));
+                b[q] = reinterpret_cast<uint32_t*>(bins + off + q * 128);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) s[q] = *b[q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) s[q] -= dec;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) *b[q] = s[q];
+            uint32_t mn = s[0];
+#pragma unroll
+            for (int q = 1; q < Q; ++q) mn = min(mn, s[q]);
+            // out of line: this lambda is unrolled 2*B times and the kernel must stay inside the instruction cache
+            if (mn < 8u) tm_hit<Q>(bins, tgt_s, out_base, plane_stride, PB, lane4, (uint32_t)label_word<Q>(lw, 0), v, dir);
+        };
+        auto update = [&](int buf, const LV (&lw)[B], int k0) {
+#pragma unroll
+            for (int u = 0; u < B; u += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(st_val + buf * B + u);
+                entry(lw[u + 0], v4.x, (k0 + u + 0 < ch.end) ? 8u : 0u);
+                entry(lw[u + 1], v4.y, (k0 + u + 1 < ch.end) ? 8u : 0u);
+                entry(lw[u + 2], v4.z, (k0 + u + 2 < ch.end) ? 8u : 0u);
+                entry(lw[u + 3], v4.w, (k0 + u + 3 < ch.end) ? 8u : 0u);
+            }
+        };
+
+        LV lwA[B], lwB[B];
+        int2 pr = load_pair(ch.begin);
         stage(0, pr);
-        pr = load_pair(k + 3 * B);
-        if (k + 2 * B < ch.end) fetch_labels(0, lwA);
-        update(1, lwB, k + B);
+        fetch_labels(0, lwA);
+        pr = load_pair(ch.begin + B);
+        for (int k = ch.begin; k < ch.end; k += 2 * B) {
+            stage(1, pr);
+            pr = load_pair(k + 2 * B);
+            const bool more1 = k + B < ch.end;
+            if (more1) fetch_labels(1, lwB);
+            update(0, lwA, k);
+            if (!more1) break;
+            stage(0, pr);
+            pr = load_pair(k + 3 * B);
+            if (k + 2 * B < ch.end) fetch_labels(0, lwA);
+            update(1, lwB, k + B);
+        }
     }
 }
 
