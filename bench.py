@@ -285,6 +285,9 @@ def run_gpu(args):
         "stages_ms": {k: tm[k] for k in ("setup_ms", "means_ms", "score_ms", "total_ms")},
         "roofline": roofline,
     }
+    if world == 1 and not args.no_cellchat:
+        line["cellchat_null"] = cellchat_null(eng, wl, P, timed, cpu=not args.no_cpu)
+        eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
     if world == 1 and not args.no_dropin:
         line["dropin_call"] = dropin_call(wl, P)
     if world == 1 and not args.no_cpu:
@@ -299,6 +302,51 @@ def run_gpu(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cellchat_null(eng, wl, P, timed, cpu=True):
+    """Secondary number: the CellChat null on the same matrix - per-(permutation, cluster, gene)
+    TRIMEANS (three quantiles of the dense column, selected exactly from the stored entries) instead of means,
+    prod / (kh + prod) score, same metric.  Device time with resident inputs, L2 flushed between steps."""
+    from liana_py_b200.method import _pipeline as PL, _tables
+    from liana_py_b200.resource import select_resource
+    from liana_py_b200.testing._synth import consensus_genes
+    mat_max = np.float32(wl["data"].max().item())
+    obs_tm = eng.observed_trimean(mat_max)
+    _, stored, sizes = eng.observed()
+    props = stored / sizes[:, None].astype(np.float64)
+    tables = _tables.build_resource_tables(select_resource("consensus"), consensus_genes())
+    tri = _tables.resolve_triples(tables, obs_tm, props, 0.1)
+    obs = PL.observed_cellchat(tri.ligand_means, tri.receptor_means)
+    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt)
+    T = len(obs)
+    keep = {}
+
+    def step():
+        keep["out"] = eng.run_trimean(P, mat_max, obs_prob=obs, seed=1337)
+
+    total_ms, launches, kern_ms, kern_n, tm = timed(step, 2, 3)
+    ms = total_ms / 2
+    tt = eng.trimean_timings()
+    out = {"ms_per_step": ms, "value": P * T / (ms * 1e-3), "unit": UNIT, "triples_kept": T,
+           "nonzero_observed_trimeans": float(np.mean(obs_tm != 0)), "perm_batch": tm["perm_batch"],
+           "stages_ms": {"slab_ms": tm["setup_ms"], "count_ms": tt["count_ms"], "prefix_ms": tt["prefix_ms"],
+                         "select_ms": tt["select_ms"], "finalize_ms": tt["finalize_ms"], "score_ms": tm["score_ms"]},
+           "rewalked_items": [tt["walked_warps"], tt["select_warps"]],
+           "count_kernel_updates_per_s": P * wl["nnz"] / (tt["count_ms"] * 1e-3),
+           "mean_pvalue": float(keep["out"]["cellchat"].mean() / P),
+           "note": "lrperm_run_trimean: count (fast2_means_kernel<COUNT>, shared-memory-pipe bound like the cellphonedb "
+                   "kernel) + prefix + select + finalize + score; bit-identical to the reference for identical permutations"}
+    if cpu:
+        from oracle import numpy_port
+        X, labels = cpu_inputs(wl)
+        t0 = time.perf_counter()
+        numpy_port.get_trimean_perms(X, labels, wl["L"], 1, 1337, mat_max)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": T / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"1 of {P} permutations in {dt:.1f} s (NumPy restatement of _get_means_perms with "
+                                         f"agg_fun=_trimean: dense np.quantile / np.median per cluster); extrapolated full run: {dt * P:.0f} s"}
+    return out
 
 
 def dropin_call(wl, P):
@@ -412,6 +460,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--no-cellchat", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3        # timing rule: at least 3 warm-up steps

@@ -861,9 +861,12 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
         h->labels8s_scale = scale;
     }
     const int64_t n_super = (n_batches + NB - 1) / NB;
-    // events: [0] start; per batch 4 (slab start, count start, count end, prefix end) + 2 (score start, score end);
-    // per super-batch 3 (select start, select end, finalize end); last = end
-    const size_t n_events = 2 + (size_t)n_batches * 6 + (size_t)n_super * 3;
+    // events: [0] start; per batch 4 (slab start, count start, count end, prefix end) + 2 (score start, score end)
+    // + 1 (slab end, on the aux stream); per super-batch 3 (select start, select end, finalize end); last = end
+    const size_t n_events = 2 + (size_t)n_batches * 7 + (size_t)n_super * 3;
+    // the label slabs are generated on the aux stream, ahead of and concurrently with the counting of earlier batches
+    // (ALU-bound Feistel rounds next to a shared-memory-bound kernel); every batch of a super-batch has its own slab
+    cudaStream_t sM = h->stream, sS = h->overlap ? h->aux_stream : h->stream;
     while (h->events.size() < n_events) {
         cudaEvent_t ev;
         CK(cudaEventCreate(&ev));
@@ -875,9 +878,12 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
     h->tm_n_batches = (int32_t)n_batches;
     h->tm_n_super = (int32_t)n_super;
     CK(cudaEventRecord(h->events[0], h->stream));
+    if (sS != sM) CK(cudaStreamWaitEvent(sS, h->events[0], 0));       // the aux stream starts after everything queued so far
     const size_t idx_elem = a.perm_idx_is_64 ? 8 : 4;
     for (int64_t sb = 0; sb < n_super; ++sb) {
         const int64_t b0 = sb * NB;
+        // the slabs of this super-batch overwrite those the previous select pass reads
+        if (sb > 0 && sS != sM) CK(cudaStreamWaitEvent(sS, h->events[1 + (size_t)n_batches * 7 + (size_t)(sb - 1) * 3 + 1], 0));
         const int32_t nb = (int32_t)std::min<int64_t>(NB, n_batches - b0);
         const int32_t n_perms_super = (int32_t)std::min<int64_t>((int64_t)nb * PB, a.n_perms - b0 * PB);
         CK(cudaMemsetAsync(h->tm_planes.p, 0, sizeof(float) * kTmPlanes * plane_elems * nb, h->stream));
@@ -885,15 +891,15 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
         CK(cudaMemsetAsync(h->tm_walk_list.p, 0, 2 * sizeof(uint32_t), h->stream));
         for (int32_t bi = 0; bi < nb; ++bi) {
             const int64_t b = b0 + bi;
-            cudaEvent_t* ev = &h->events[1 + (size_t)b * 6];
+            cudaEvent_t* ev = &h->events[1 + (size_t)b * 7];
             const int64_t p0 = b * PB;
             const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
             uint8_t* slab = h->slab.as<uint8_t>() + slab_elems * bi;
-            CK(cudaEventRecord(ev[0], h->stream));
-            // ---- label slab ----
-            if (pb < PB) CK(cudaMemsetAsync(slab, 0, slab_elems, h->stream));
+            CK(cudaEventRecord(ev[0], sS));
+            // ---- label slab (aux stream) ----
+            if (pb < PB) CK(cudaMemsetAsync(slab, 0, slab_elems, sS));
             if (a.perm_source < 0) {
-                slab_identity_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels8s.as<uint8_t>(), (int32_t)N, slab, PB);
+                slab_identity_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, sS>>>(h->labels8s.as<uint8_t>(), (int32_t)N, slab, PB);
             } else {
                 PermSource ps{};
                 ps.is64 = a.perm_idx_is_64;
@@ -904,20 +910,24 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
                     const int cells_per_block = 128;
                     dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
                     const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
-                    slab_philox_kernel<<<grd, 128, tab_smem, h->stream>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
-                                                                          h->bucket_shift, L, scale, (int32_t)N, pb, slab, PB, cells_per_block);
+                    slab_philox_kernel<<<grd, 128, tab_smem, sS>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
+                                                                   h->bucket_shift, L, scale, (int32_t)N, pb, slab, PB, cells_per_block);
                 } else {
                     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
                     if (a.perm_idx_on_device) ps.idx = src;
                     else {
-                        if ((rc = upload(h, h->perm_dev, src, idx_elem * (size_t)pb * (size_t)N, 0))) return rc;
+                        // one staging buffer, reused batch after batch: uploads and slab kernels are ordered on the aux stream
+                        CK(h->perm_dev.ensure(idx_elem * (size_t)PB * (size_t)N));
+                        CK(cudaMemcpyAsync(h->perm_dev.p, src, idx_elem * (size_t)pb * (size_t)N, cudaMemcpyHostToDevice, sS));
                         ps.idx = h->perm_dev.p;
                     }
                     dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
-                    slab_from_index_kernel<<<grd, 256, 0, h->stream>>>(ps, h->labels8s.as<uint8_t>(), (int32_t)N, pb, slab, PB);
+                    slab_from_index_kernel<<<grd, 256, 0, sS>>>(ps, h->labels8s.as<uint8_t>(), (int32_t)N, pb, slab, PB);
                 }
             }
             CK_LAUNCH();
+            CK(cudaEventRecord(ev[6], sS));
+            if (sS != sM) CK(cudaStreamWaitEvent(sM, ev[6], 0));
             // ---- count, prefix ----
             float* counts = h->tm_counts.as<float>() + slot_elems * bi;
             uint32_t* prefix = h->tm_prefix.as<uint32_t>() + slot_elems * bi;
@@ -925,7 +935,7 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
             else rc = launch_tm_count<2>(h, PB, slab, counts, prefix, pb, bi, ev + 1);
             if (rc) return rc;
         }
-        cudaEvent_t* sev = &h->events[1 + (size_t)n_batches * 6 + (size_t)sb * 3];
+        cudaEvent_t* sev = &h->events[1 + (size_t)n_batches * 7 + (size_t)sb * 3];
         // ---- select: one launch over the batches of the super-batch ----
         CK(cudaEventRecord(sev[0], h->stream));
         if (Q == 4) rc = launch_tm_select<4>(h, PB, nb, n_perms_super, slot_elems, plane_elems);
@@ -947,7 +957,7 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
         CK(cudaEventRecord(sev[2], h->stream));
         for (int32_t bi = 0; bi < nb; ++bi) {
             const int64_t b = b0 + bi;
-            cudaEvent_t* ev = &h->events[1 + (size_t)b * 6];
+            cudaEvent_t* ev = &h->events[1 + (size_t)b * 7];
             const int64_t p0 = b * PB;
             const int32_t pb = (int32_t)std::min<int64_t>(PB, a.n_perms - p0);
             const double* cube = h->tm_cube.as<double>() + plane_elems * bi;
@@ -987,19 +997,19 @@ int collect_trimean_timings(lrperm_engine* h) {
     h->n_main_launches = (int32_t)n_batches;
     float ms;
     for (int64_t b = 0; b < n_batches; ++b) {
-        cudaEvent_t* ev = &h->events[1 + (size_t)b * 6];
-        CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); h->t_setup += ms;
+        cudaEvent_t* ev = &h->events[1 + (size_t)b * 7];
+        CK(cudaEventElapsedTime(&ms, ev[0], ev[6])); h->t_setup += ms;
         CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); h->tm_ms[0] += ms; h->t_main += ms;
         CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); h->tm_ms[1] += ms;
         CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); h->t_score += ms;
     }
     for (int64_t sb = 0; sb < n_super; ++sb) {
-        cudaEvent_t* sev = &h->events[1 + (size_t)n_batches * 6 + (size_t)sb * 3];
+        cudaEvent_t* sev = &h->events[1 + (size_t)n_batches * 7 + (size_t)sb * 3];
         CK(cudaEventElapsedTime(&ms, sev[0], sev[1])); h->tm_ms[2] += ms;
         CK(cudaEventElapsedTime(&ms, sev[1], sev[2])); h->tm_ms[3] += ms;
     }
     h->t_means = h->tm_ms[0] + h->tm_ms[1] + h->tm_ms[2] + h->tm_ms[3];
-    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[1 + (size_t)n_batches * 6 + (size_t)n_super * 3]));
+    CK(cudaEventElapsedTime(&h->t_total, h->events[0], h->events[1 + (size_t)n_batches * 7 + (size_t)n_super * 3]));
     return LRPERM_OK;
 }
 
