@@ -285,6 +285,9 @@ def run_gpu(args):
         "stages_ms": {k: tm[k] for k in ("setup_ms", "means_ms", "score_ms", "total_ms")},
         "roofline": roofline,
     }
+    if world == 1 and not args.no_stress:
+        line["stress_expr_prop0"] = stress_variant(eng, wl, P, order, counts, timed)
+        eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
     if world == 1 and not args.no_cellchat:
         line["cellchat_null"] = cellchat_null(eng, wl, P, timed, cpu=not args.no_cpu)
         eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
@@ -302,6 +305,29 @@ def run_gpu(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stress_variant(eng, wl, P, order, counts, timed):
+    """the same workload with expr_prop=0, i.e. every (source, target, interaction) row reaches the
+    score function (T = T_max): the means cube is unchanged, the score + count stage grows ~15x."""
+    import torch
+    from liana_py_b200 import _engine as E
+    from liana_py_b200.method import _pipeline as PL, _tables
+    from liana_py_b200.resource import select_resource
+    from liana_py_b200.testing._synth import consensus_genes
+    means, stored, sizes = eng.observed()
+    props = stored / sizes[:, None].astype(np.float64)
+    tables = _tables.build_resource_tables(select_resource("consensus"), consensus_genes())
+    tri = _tables.resolve_triples(tables, means, props, 0.0)
+    obs = PL.observed_cpdb(tri.ligand_means, tri.receptor_means)
+    T = len(obs)
+    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
+    big = torch.zeros(max(T, 1), dtype=torch.int32, device=counts.device)
+    total_ms, _, _, _, tm = timed(lambda: eng.run(P, seed=1337, order=order, scores=E.SCORE_CPDB, counts_out=(big, None)), 2, 3)
+    ms = total_ms / 2
+    return {"triples": T, "ms_per_step": ms, "value": P * T / (ms * 1e-3), "unit": UNIT,
+            "stages_ms": {k: tm[k] for k in ("setup_ms", "means_ms", "score_ms", "total_ms")},
+            "note": "expr_prop=0: all T_max rows scored; resident inputs, L2 flushed between steps"}
 
 
 def cellchat_null(eng, wl, P, timed, cpu=True):
@@ -461,6 +487,7 @@ def main():
     ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--no-cellchat", action="store_true")
+    ap.add_argument("--no-stress", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3        # timing rule: at least 3 warm-up steps

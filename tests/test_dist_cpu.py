@@ -37,6 +37,16 @@ def _worker(rank, world, port, out_dir):
         local = numpy_port.counts_from_cube(cube, *idx, obs, "cellphonedb").astype(np.uint32)
         total = ctx.all_reduce_sum_u32(local)
         assert np.array_equal(total / P, g["cpdb_pvals"])          # identical to the single-process reference
+        # CellChat null: same sharding, the oracle's trimean cube per rank, integer all-reduce
+        from conftest import load_golden_cellchat
+        gc = load_golden_cellchat("ragged90")
+        Pc = int(gc["n_perms"])
+        lo, hi = ctx.perm_range(Pc)
+        perms = numpy_port.perm_indices(gc["X"].shape[0], Pc, int(gc["seed"]))[lo:hi]
+        tm_cube = c_oracle.trimean_cube(gc["X"], gc["labels"], gc["L"], perms, gc["mat_max"])
+        idx_c = (gc["ligand_idx"], gc["receptor_idx"], gc["source_idx"], gc["target_idx"])
+        local_c = numpy_port.counts_cellchat(tm_cube, *idx_c, gc["lr_probs"]).astype(np.uint32)
+        assert np.array_equal(ctx.all_reduce_sum_u32(local_c) / Pc, gc["pvals"])
         # by_sample: whole samples per rank, gathered as objects
         sizes = [50, 400, 30, 220, 90, 10, 300]
         mine = ctx.sample_shard(sizes)
