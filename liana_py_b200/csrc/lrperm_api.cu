@@ -71,6 +71,10 @@ struct lrperm_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t aux_stream = nullptr;    // FAST mode: label slabs / finalize / score run here, overlapped with the main kernel
+    cudaStream_t copy_stream = nullptr;   // matrix uploads from pinned host memory (lrperm_set_matrix_csr) run here, unwaited
+    cudaEvent_t ev_matrix = nullptr;      // recorded on copy_stream after the upload + packing
+    bool matrix_pending = false;          // the engine stream has not waited for ev_matrix yet (validation deferred too)
+    DevBuf err_flag_m;                    // validation flags of the pending matrix
     int32_t overlap = 1;
     std::string err;
     int sm_count = 148;
@@ -196,6 +200,32 @@ int check_err_flag(lrperm_engine* h, const char* what) {
                        "4=indptr not monotone, 8=triple index out of range)", what, flag);
     }
     return LRPERM_OK;
+}
+
+// A matrix uploaded from pinned host memory is still in flight on the copy stream (lrperm_set_matrix_csr returned
+// without waiting): make the engine stream wait for it and surface the deferred validation result.  Everything
+// that reads the matrix on the device calls this first; what does not need it (labels, triples, the label slabs of
+// the first batches) proceeds while the upload runs.
+int wait_matrix(lrperm_engine* h) {
+    if (!h->matrix_pending) return LRPERM_OK;
+    h->matrix_pending = false;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_matrix, 0));
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->err_flag_m.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) {
+        CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream));
+        h->have_matrix = false;
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr (deferred check): invalid input (flag=%d: 1=column out of range, "
+                       "2=indptr overflow, 4=indptr not monotone)", flag);
+    }
+    return LRPERM_OK;
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 // ---- CSC copy + chunk tables for FAST mode -------------------------------------------------
@@ -465,7 +495,8 @@ std::vector<int32_t> batch_schedule(int64_t n_perms, int32_t PB, int32_t gran) {
 // finalize(b) + score(b) while main(b+1) runs.  Slab and partial-sum buffers are double-buffered.
 //   B: slab(0) | slab(1)         | wait m0, finalize(0), score(0), slab(2) | wait m1, finalize(1), ...
 //   A: wait s0, main(0), rec m0  | wait s1, main(1), rec m1                | wait s2, wait f0, main(2) ...
-int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, const uint8_t* slab_labels) {
+int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, const uint8_t* slab_labels,
+                       int32_t chunk_nnz, int32_t tile_cells) {
     const int64_t N = h->N;
     const int32_t label_scale = h->fast_variant == 2 ? Q / 2 : 1;
     const int32_t G = (int32_t)h->G, L = h->L;
@@ -479,14 +510,11 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     int rc;
     cudaStream_t sA = h->stream, sB = h->aux_stream;
     const size_t slab_max = (size_t)N * pb_max;
-    const size_t part_max = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * pb_max;
     const bool dbl = n_batches > 1;
     CK(h->slab.ensure(slab_max));
-    CK(h->partials.ensure(part_max));
     CK(h->cube.ensure(sizeof(float) * (size_t)G * L * pb_max));
-    if (dbl) { CK(h->slab2.ensure(slab_max)); CK(h->partials2.ensure(part_max)); }
+    if (dbl) CK(h->slab2.ensure(slab_max));
     uint8_t* slabs[2] = {h->slab.as<uint8_t>(), dbl ? h->slab2.as<uint8_t>() : h->slab.as<uint8_t>()};
-    float* parts[2] = {h->partials.as<float>(), dbl ? h->partials2.as<float>() : h->partials.as<float>()};
 
     // events: [0] start, [1] end, then per batch: s0 s1 (slab), m0 m1 (main), f0 f1 (finalize), c1 (score end)
     const size_t n_events = 2 + (size_t)n_batches * 7 + 1;
@@ -537,12 +565,23 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         return LRPERM_OK;
     };
 
+    // The label slabs of the first two batches need the labels only: they are queued BEFORE the engine stream waits
+    // for a matrix upload still in flight (lrperm_set_matrix_csr from pinned memory) and before the host blocks in
+    // the CSC / chunk-table builds, so they run while the matrix crosses PCIe.
     if ((rc = enqueue_slab(0))) return rc;
+    if (n_batches > 1 && (rc = enqueue_slab(1))) return rc;
+    if ((rc = wait_matrix(h))) return rc;
+    if ((rc = build_csc(h))) return rc;
+    if ((rc = build_chunks(h, chunk_nnz, tile_cells))) return rc;
+    const size_t part_max = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * pb_max;
+    CK(h->partials.ensure(part_max));
+    if (dbl) CK(h->partials2.ensure(part_max));
+    float* parts[2] = {h->partials.as<float>(), dbl ? h->partials2.as<float>() : h->partials.as<float>()};
     for (int64_t b = 0; b < n_batches; ++b) {
         const int64_t p0 = first[(size_t)b];
         const int32_t PBb = sched[(size_t)b];
         const int32_t pb = (int32_t)std::min<int64_t>(PBb, a.n_perms - p0);
-        if (b + 1 < n_batches && (rc = enqueue_slab(b + 1))) return rc;
+        if (b >= 1 && b + 1 < n_batches && (rc = enqueue_slab(b + 1))) return rc;
         // ---- A: main kernel ----
         CK(cudaStreamWaitEvent(sA, EV(b, 1), 0));
         if (b >= 2) CK(cudaStreamWaitEvent(sA, EV(b - 2, 5), 0));     // partials[b&1] consumed by finalize(b-2)
@@ -1046,8 +1085,12 @@ int lrperm_create(int device, lrperm_engine** out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         e = cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi);
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_matrix, cudaEventDisableTiming);
     if (e == cudaSuccess) e = h->err_flag.ensure(sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->err_flag.p, 0, sizeof(int));
+    if (e == cudaSuccess) e = h->err_flag_m.ensure(sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->err_flag_m.p, 0, sizeof(int));
     if (e != cudaSuccess) {
         g_create_error = std::string("lrperm_create: ") + cudaGetErrorString(e);
         delete h;
@@ -1064,6 +1107,8 @@ void lrperm_destroy(lrperm_engine* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    h->err_flag_m.release();
     for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->st_indptr, &h->st_indices, &h->st_data, &h->st_row_keep, &h->st_small,
                       &h->labels32, &h->labels8, &h->labels8s, &h->order, &h->rank, &h->bucket_cluster,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
@@ -1076,6 +1121,8 @@ void lrperm_destroy(lrperm_engine* h) {
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_matrix) cudaEventDestroy(h->ev_matrix);
     delete h;
 }
 
@@ -1140,7 +1187,42 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     }
     if (nnz < 0 || nnz >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_set_matrix_csr: nnz=%lld must be in [0, 2^31)", (long long)nnz);
     if (nnz > 0 && (!indices || !data)) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr: NULL indices/data");
+    // an earlier pending upload must not race with this one
+    if (h->matrix_pending) { CK(cudaStreamSynchronize(h->copy_stream)); h->matrix_pending = false; CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream)); }
     h->N = n_cells; h->G = n_genes; h->nnz = nnz;
+
+    if (!on_device && nnz > 0 && is_pinned_host(indptr) && is_pinned_host(indices) && is_pinned_host(data)) {
+        // Pinned host buffers: copies + packing go to the copy stream and the call returns without waiting, so the
+        // caller's next calls (labels, triples, the first label slabs of lrperm_run) overlap the PCIe transfer.
+        // Staging buffers of their own: tmp_* are used by those calls.  Validation is reported by the first call
+        // that needs the matrix (wait_matrix).
+        cudaStream_t sC = h->copy_stream;
+        h->staged = false;
+        CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+        CK(h->st_indptr.ensure(isz * (size_t)(n_cells + 1)));
+        CK(h->st_indices.ensure(sizeof(int32_t) * (size_t)nnz));
+        CK(h->st_data.ensure(sizeof(float) * (size_t)nnz));
+        CK(h->csr_pairs.ensure(sizeof(int2) * (size_t)nnz));
+        CK(cudaStreamSynchronize(h->stream));          // earlier work on the engine stream may still read the old matrix
+        CK(cudaMemcpyAsync(h->st_indptr.p, indptr, isz * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, sC));
+        if (indptr_is_64)
+            narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, sC>>>(h->st_indptr.as<int64_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag_m.as<int>());
+        else
+            narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, sC>>>(h->st_indptr.as<int32_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag_m.as<int>());
+        CK_LAUNCH();
+        // (the copy engine serves H2D copies of all streams in submission order: the small uploads of the calls that
+        // follow queue behind this transfer, but the host is not blocked and kernels - the label slabs - are not either)
+        CK(cudaMemcpyAsync(h->st_indices.p, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, sC));
+        CK(cudaMemcpyAsync(h->st_data.p, data, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, sC));
+        pack_csr_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, sC>>>(
+            h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), (int32_t)n_cells, (int32_t)n_genes,
+            h->csr_pairs.as<int2>(), h->err_flag_m.as<int>());
+        CK_LAUNCH();
+        CK(cudaEventRecord(h->ev_matrix, sC));
+        h->matrix_pending = true;
+        h->have_matrix = true;
+        return LRPERM_OK;
+    }
 
     CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
     if (indptr_is_64) {
@@ -1184,6 +1266,7 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
     if (!h) return LRPERM_ERR_INVALID;
     StageTimer timer("stage_matrix_csr");
     DeviceGuard guard(h->device);
+    if (h->matrix_pending) { CK(cudaStreamSynchronize(h->copy_stream)); h->matrix_pending = false; CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream)); }
     h->staged = false;
     if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: bad shape or NULL indptr");
     if (n_cells >= 0x7fffffffLL || n_genes >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: n_cells and n_genes must be < 2^31");
@@ -1462,6 +1545,7 @@ int lrperm_observed(lrperm_engine* h, float* means, int32_t* stored_counts, int3
     if (!h) return LRPERM_ERR_INVALID;
     DeviceGuard guard(h->device);
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_observed: set the matrix and labels first");
+    { const int rcw = wait_matrix(h); if (rcw) return rcw; }
     const int32_t G = (int32_t)h->G, L = h->L;
     const size_t LG = (size_t)L * G;
     int rc;
@@ -1500,6 +1584,7 @@ int lrperm_cluster_moments(lrperm_engine* h, double logbase, double* sum_x, doub
     if (!h) return LRPERM_ERR_INVALID;
     DeviceGuard guard(h->device);
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_cluster_moments: set the matrix and labels first");
+    { const int rcw = wait_matrix(h); if (rcw) return rcw; }
     if (!(logbase > 0.0)) return h->fail(LRPERM_ERR_INVALID, "lrperm_cluster_moments: logbase must be > 0");
     const int32_t G = (int32_t)h->G, L = h->L;
     const size_t LG = (size_t)L * G;
@@ -1577,11 +1662,11 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     // ---- batch geometry ----
     int32_t PB;   // permutations per batch (cube row stride PP == PB)
     int Q = 0;
+    int32_t fast_chunk = 0, fast_tile = 0;
     if (order_mode == LRPERM_ORDER_FAST) {
         if (L > 255) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode supports at most 255 clusters (got %d); use EXACT", L);
         Q = h->fast_variant == 2 ? pick_q2(h) : pick_q(h);
         if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: %d clusters do not fit the shared-memory bins", L);
-        if ((rc = build_csc(h))) return rc;
         PB = h->fast_perm_batch ? h->fast_perm_batch : 512;
         const int32_t gran = std::max(128, 32 * Q);        // a warp covers 32*Q permutations
         if (n_perms < PB) PB = (int32_t)std::max<int64_t>(gran, ((n_perms + gran - 1) / gran) * gran);
@@ -1604,8 +1689,10 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
             c = std::min<int64_t>(std::max<int64_t>(c, 4096), 16384);
             chunk_nnz = (int32_t)((c + 1023) / 1024 * 1024);
         }
-        if ((rc = build_chunks(h, chunk_nnz, tile_cells))) return rc;
+        fast_chunk = chunk_nnz;
+        fast_tile = tile_cells;
     } else {
+        if ((rc = wait_matrix(h))) return rc;
         // enough (perm, cluster) warps for several waves, cube batch <= ~256 MB
         PB = 512;
         while (PB > 128 && (int64_t)PB * L * G * 4 > (256LL << 20)) PB >>= 1;
@@ -1614,7 +1701,12 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     const int32_t PP = PB;
     h->last_pb = PB;
     CK(h->cube.ensure(sizeof(float) * (size_t)G * L * PP));
-    if (order_mode == LRPERM_ORDER_FAST) {
+    const int64_t n_batches = (n_perms + PB - 1) / PB;
+    const bool pipelined = order_mode == LRPERM_ORDER_FAST && h->overlap && n_batches > 0;
+    if (order_mode == LRPERM_ORDER_FAST && !pipelined) {
+        if ((rc = wait_matrix(h))) return rc;
+        if ((rc = build_csc(h))) return rc;
+        if ((rc = build_chunks(h, fast_chunk, fast_tile))) return rc;
         CK(h->slab.ensure((size_t)N * PB));
         CK(h->partials.ensure(sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB));
     }
@@ -1635,11 +1727,10 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         }
         slab_labels = h->labels8s.as<uint8_t>();
     }
-    const int64_t n_batches = (n_perms + PB - 1) / PB;
-    if (order_mode == LRPERM_ORDER_FAST && h->overlap && n_batches > 0) {
+    if (pipelined) {
         RunArgs ra{n_perms, perm_offset, seed, perm_source, perm_idx, perm_idx_is_64, perm_idx_on_device, scores, gmean_mode,
                    cube_out, cube_on_device};
-        if ((rc = run_fast_pipelined(h, ra, Q, PB, slab_labels))) { cudaStreamSynchronize(h->aux_stream); cudaStreamSynchronize(h->stream); return rc; }
+        if ((rc = run_fast_pipelined(h, ra, Q, PB, slab_labels, fast_chunk, fast_tile))) { cudaStreamSynchronize(h->aux_stream); cudaStreamSynchronize(h->stream); return rc; }
         if (scores & LRPERM_SCORE_CPDB) if ((rc = download(h, counts_cpdb, h->counts_c.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
         if (scores & LRPERM_SCORE_GMEAN) if ((rc = download(h, counts_gmean, h->counts_g.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
         CK(cudaStreamSynchronize(h->stream));
@@ -1748,6 +1839,7 @@ int lrperm_run_trimean(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, u
     StageTimer timer("run_trimean");
     DeviceGuard guard(h->device);
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: set the matrix and labels first");
+    { const int rcw = wait_matrix(h); if (rcw) return rcw; }
     if (n_perms < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: n_perms < 0");
     if (perm_source != LRPERM_PERMS_INDEX && perm_source != LRPERM_PERMS_PHILOX) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: unknown perm_source %d", perm_source);
     if (perm_source == LRPERM_PERMS_INDEX && n_perms > 0 && !perm_idx) return h->fail(LRPERM_ERR_INVALID, "lrperm_run_trimean: perm_idx is NULL");
@@ -1774,6 +1866,7 @@ int lrperm_observed_trimean(lrperm_engine* h, double recip, double* trimean, int
     if (!h) return LRPERM_ERR_INVALID;
     DeviceGuard guard(h->device);
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_observed_trimean: set the matrix and labels first");
+    { const int rcw = wait_matrix(h); if (rcw) return rcw; }
     if (!(recip > 0.0) || !std::isfinite(recip) || !trimean) return h->fail(LRPERM_ERR_INVALID, "lrperm_observed_trimean: recip must be positive and finite, trimean non-NULL");
     const int32_t G = (int32_t)h->G, L = h->L;
     h->launches = 0;

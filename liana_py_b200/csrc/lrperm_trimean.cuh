@@ -194,7 +194,6 @@ tm_select_kernel(const int2* __restrict__ vsc_pairs, const FastChunk* __restrict
         const int dir = (ch.gene >> kTmDirBit) & 1;
         const int gene = ch.gene & ((1 << kTmDirBit) - 1);
         const uint8_t* slab = slab_all + batch * slab_batch_stride;
-        const float* counts = counts_all + batch * slot_batch_stride;
         const uint32_t* prefix = prefix_all + batch * slot_batch_stride;
         float* planes = planes_all + batch * plane_batch_stride;
         const int n_valid = min(PB, n_perms_total - batch * PB);     // permutations of this batch that exist

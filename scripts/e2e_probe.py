@@ -25,3 +25,12 @@ for it in range(4):
     hc.copy_(counts); sync(); ts.append(time.perf_counter())
     d = np.diff(ts) * 1e3
     print(f"{cfg} it{it}: set_matrix {d[0]:.1f}  set_labels {d[1]:.1f}  set_triples {d[2]:.1f}  run {d[3]:.1f} (dev {eng.timings()['total_ms']:.1f})  d2h {d[4]:.2f}  total {d.sum():.1f} ms")
+# the same sequence without synchronising between the calls (what bench.py's e2e leg times)
+for it in range(4):
+    sync(); t0 = time.perf_counter()
+    eng.set_matrix_csr(host[0], host[1], host[2], N, G)
+    eng.set_labels(host[3], L)
+    eng.set_triples(tri[0], tri[1], tri[2], tri[3], obs, None)
+    eng.run(P, seed=1, order=E.ORDER_FAST, scores=E.SCORE_CPDB, counts_out=(counts, None))
+    hc.copy_(counts); sync()
+    print(f"{cfg} it{it}: unsynchronised sequence total {(time.perf_counter()-t0)*1e3:.1f} ms (run dev {eng.timings()['total_ms']:.1f})")
