@@ -19,9 +19,12 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lrperm.h"
@@ -64,6 +67,56 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Host-side helper of pageable uploads: a few persistent threads that memcpy slices of one piece into a pinned
+// staging buffer in parallel (one thread moves ~10 GB/s, PCIe takes ~50 GB/s).
+class ParallelCopier {
+public:
+    explicit ParallelCopier(int n) : n_(n) {
+        for (int i = 0; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+    }
+    ~ParallelCopier() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = static_cast<unsigned char*>(dst); src_ = static_cast<const unsigned char*>(src); bytes_ = bytes;
+            pending_ = n_; ++gen_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void loop(int i) {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            const size_t slice = ((bytes_ + n_ - 1) / n_ + 63) & ~(size_t)63;
+            const size_t b = std::min(bytes_, slice * i), e = std::min(bytes_, slice * (i + 1));
+            unsigned char* d = dst_; const unsigned char* s = src_;
+            lk.unlock();
+            if (e > b) memcpy(d + b, s + b, e - b);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+    unsigned char* dst_ = nullptr; const unsigned char* src_ = nullptr; size_t bytes_ = 0;
+    int pending_ = 0;
+};
+
 }  // namespace
 
 struct lrperm_engine {
@@ -75,6 +128,11 @@ struct lrperm_engine {
     cudaEvent_t ev_matrix = nullptr;      // recorded on copy_stream after the upload + packing
     bool matrix_pending = false;          // the engine stream has not waited for ev_matrix yet (validation deferred too)
     DevBuf err_flag_m;                    // validation flags of the pending matrix
+    // pageable uploads: two pinned staging pieces filled by a few host threads while the other one is in flight
+    ParallelCopier* copier = nullptr;
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    static constexpr size_t kPinPiece = 16u << 20;
     int32_t overlap = 1;
     std::string err;
     int sm_count = 148;
@@ -176,10 +234,45 @@ int grid_for(int64_t n, int threads, int cap = 148 * 16) {
     return (int)g;
 }
 
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Large upload from PAGEABLE host memory (a NumPy array): the driver's own staging moves ~10 GB/s; here host threads
+// fill one pinned piece while the previous one is on the wire.
+int upload_pageable(lrperm_engine* h, void* dst, const void* src, size_t bytes) {
+    if (!h->copier) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        h->copier = new (std::nothrow) ParallelCopier((int)std::max(2u, std::min(6u, hw ? hw / 2 : 2u)));
+        if (!h->copier) return h->fail(LRPERM_ERR_OOM, "host allocation failed");
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaHostAlloc(&h->pin[i], lrperm_engine::kPinPiece, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&h->pin_ev[i], cudaEventDisableTiming));
+        }
+    }
+    const unsigned char* s = static_cast<const unsigned char*>(src);
+    unsigned char* d = static_cast<unsigned char*>(dst);
+    int k = 0;
+    for (size_t o = 0; o < bytes; o += lrperm_engine::kPinPiece, ++k) {
+        const size_t n = std::min(lrperm_engine::kPinPiece, bytes - o);
+        const int b = k & 1;
+        if (k >= 2) CK(cudaEventSynchronize(h->pin_ev[b]));      // the DMA that read this piece two rounds ago is done
+        h->copier->copy(h->pin[b], s + o, n);
+        CK(cudaMemcpyAsync(d + o, h->pin[b], n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->pin_ev[b], h->stream));
+    }
+    // the staging pieces are reused by the next upload: leave none in flight
+    for (int b = 0; b < 2 && b < k; ++b) CK(cudaEventSynchronize(h->pin_ev[b]));
+    return LRPERM_OK;
+}
+
 // copy `bytes` from a host-or-device source into a device buffer on the engine stream
 int upload(lrperm_engine* h, DevBuf& dst, const void* src, size_t bytes, int on_device) {
     CK(dst.ensure(bytes));
     if (bytes == 0) return LRPERM_OK;
+    if (!on_device && bytes >= (32u << 20) && !is_pinned_host(src)) return upload_pageable(h, dst.p, src, bytes);
     CK(cudaMemcpyAsync(dst.p, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     return LRPERM_OK;
 }
@@ -220,12 +313,6 @@ int wait_matrix(lrperm_engine* h) {
                        "2=indptr overflow, 4=indptr not monotone)", flag);
     }
     return LRPERM_OK;
-}
-
-bool is_pinned_host(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
 }
 
 // ---- CSC copy + chunk tables for FAST mode -------------------------------------------------
@@ -1123,6 +1210,8 @@ void lrperm_destroy(lrperm_engine* h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_matrix) cudaEventDestroy(h->ev_matrix);
+    delete h->copier;
+    for (int i = 0; i < 2; ++i) { if (h->pin[i]) cudaFreeHost(h->pin[i]); if (h->pin_ev[i]) cudaEventDestroy(h->pin_ev[i]); }
     delete h;
 }
 

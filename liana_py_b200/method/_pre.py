@@ -107,20 +107,27 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
         _logg(f"Converting `{groupby}` to categorical!", level="warn", verbose=verbose)
         lab = lab.astype("category")
         obs[groupby] = lab       # the reference converts in place too (`_pre.py:269-271`)
-    rows = np.arange(X.shape[0])
+    # on the category CODES (one bincount) instead of pandas categorical ops over every cell
+    codes = np.asarray(lab.cat.codes, dtype=np.int64)
+    cats = lab.cat.categories
+    keep = np.ones(X.shape[0], dtype=bool)
     if groupby_subset is not None:
-        rows = rows[np.asarray(lab.isin(groupby_subset))]
-    lab_sub = lab.iloc[rows].cat.remove_unused_categories()
-    counts = lab_sub.value_counts(sort=False)
-    low = [c for c in lab_sub.cat.categories if counts[c] < min_cells]
+        in_subset = np.append(np.asarray(cats.isin(groupby_subset)), False)     # code -1 (missing label) -> False
+        keep &= in_subset[codes]
+    counts = np.bincount(codes[keep & (codes >= 0)], minlength=len(cats))
+    low_mask = (counts > 0) & (counts < min_cells)
+    low = [c for c, m in zip(cats, low_mask) if m]
     if low:
-        keep_mask = ~np.asarray(lab_sub.isin(low))
-        rows = rows[keep_mask]
-        lab_sub = lab_sub[keep_mask].cat.remove_unused_categories()
+        keep &= ~np.append(low_mask, False)[codes]
+    rows = np.flatnonzero(keep)
+    used = (counts > 0) & ~low_mask
+    remap = np.cumsum(used) - 1                                                  # old code -> code among the kept categories
+    kept_codes = codes[rows]
+    new_codes = np.where(kept_codes >= 0, remap[np.maximum(kept_codes, 0)], -1).astype(np.int32)
+    kept_categories = np.asarray(cats[used])
     row_keep = None
     if len(rows) != X.shape[0]:
-        row_keep = np.zeros(X.shape[0], dtype=np.uint8)
-        row_keep[rows] = 1
+        row_keep = keep.astype(np.uint8)
 
     stats = engine.stage_matrix(X, row_keep)
     # empty features are removed (sum == 0 over ALL cells), empty cells only reported (`_pre.py:122-133`)
@@ -151,8 +158,7 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
         stored_max, n_stored = engine.staged_max()
         mat_max = stored_max if (n_stored >= n_all and n_stored > 0) else np.float32(max(stored_max, np.float32(0)))
     return PreparedInput(mat_max=mat_max, var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
-                         labels=np.asarray(lab_sub.cat.codes, dtype=np.int32),
-                         categories=np.asarray(lab_sub.cat.categories), obs_index=obs.index[rows], n_cells=len(rows),
+                         labels=new_codes, categories=kept_categories, obs_index=obs.index[rows], n_cells=len(rows),
                          mat_mean=float(stats["kept_total"] / n_all) if n_all else 0.0)
 
 

@@ -111,16 +111,28 @@ def resolve_triples(tables: ResourceTables, means: np.ndarray, props: np.ndarray
     lg, lm, lp, lpmin = _resolve_side(tables.lig_sub, means, props, first_subunit=return_all_lrs)
     rg, rm, rp, rpmin = _resolve_side(tables.rec_sub, means, props, first_subunit=return_all_lrs)
     n = lg.shape[0]
-    prop_min = np.minimum(lpmin[:, :, None], rpmin[:, None, :])        # [n, s, t]
-    expressed = prop_min >= expr_prop
-    valid = np.ones((n, L, L), dtype=bool) if pair_mask is None else np.broadcast_to(pair_mask[None], (n, L, L))
-    sel = valid if return_all_lrs else (valid & expressed)
-    # row order: source-major, then target, then interaction (the reference concatenates per pair)
-    s_idx, t_idx, i_idx = np.nonzero(np.transpose(sel, (1, 2, 0)))
-    keep = expressed[i_idx, s_idx, t_idx]
+    # min(all subunit props) >= expr_prop  <=>  both sides pass: two [n, L] masks instead of an [n, L, L] float cube;
+    # the row order (source-major, then target, then interaction: the reference concatenates per pair) is the
+    # C order of an [L, L, n] mask, so one flatnonzero gives the rows already in place
+    l_ok = np.ascontiguousarray((lpmin >= expr_prop).T)                   # [s, i]
+    r_ok = np.ascontiguousarray((rpmin >= expr_prop).T)                   # [t, i]
+    expressed = l_ok[:, None, :] & r_ok[None, :, :]                       # [s, t, i]
+    if return_all_lrs:
+        sel = np.ones((L, L, n), dtype=bool) if pair_mask is None else np.broadcast_to(pair_mask[:, :, None], (L, L, n))
+    else:
+        sel = expressed if pair_mask is None else expressed & pair_mask[:, :, None]
+    flat = np.flatnonzero(sel)
+    keep = expressed.ravel()[flat] if return_all_lrs else np.ones(flat.shape[0], dtype=bool)
+    st, i_idx = np.divmod(flat, n)
+    s_idx, t_idx = np.divmod(st, L)
+    li, ri = i_idx * L + s_idx, i_idx * L + t_idx                         # flat positions in the [n, L] side tables
+
+    def side(a, pos, dtype):
+        return np.take(np.ascontiguousarray(a).reshape(-1), pos).astype(dtype, copy=False)
+
     return ResolvedTriples(
         inter=i_idx.astype(np.int32), src=s_idx.astype(np.int32), tgt=t_idx.astype(np.int32),
-        lig_gene=lg[i_idx, s_idx], rec_gene=rg[i_idx, t_idx],
-        ligand_means=lm[i_idx, s_idx].astype(means.dtype), receptor_means=rm[i_idx, t_idx].astype(means.dtype),
-        ligand_props=lp[i_idx, s_idx].astype(np.float64), receptor_props=rp[i_idx, t_idx].astype(np.float64),
+        lig_gene=side(lg, li, np.int32), rec_gene=side(rg, ri, np.int32),
+        ligand_means=side(lm, li, means.dtype), receptor_means=side(rm, ri, means.dtype),
+        ligand_props=side(lp, li, np.float64), receptor_props=side(rp, ri, np.float64),
         keep=keep)
