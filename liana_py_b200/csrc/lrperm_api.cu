@@ -170,6 +170,7 @@ struct lrperm_engine {
     int32_t n_sched = 0;                                // batches of the last pipelined run
     int32_t fast_variant = 2;                           // 1 = fast_means_kernel, 2 = fast2_means_kernel
     int32_t fast_q = 0;                                 // permutations per lane (0 = auto)
+    int32_t fast_first_batch = 0;                       // permutations of a short first batch (0 = none; A/B only)
     int32_t n_chunks = 0, n_slots = 0;
     DevBuf chunks, gene_slot_ptr;
 
@@ -570,9 +571,11 @@ struct RunArgs {
 // (the permutations one warp group covers) only.  A schedule with one-group first / last batches (to shorten
 // the slab prologue and the finalize + score epilogue that nothing overlaps) was measured and dropped: small
 // batches leave the main kernel with too few CTAs per wave (configs[1]: 4.8 ms instead of 3.8 ms).
-std::vector<int32_t> batch_schedule(int64_t n_perms, int32_t PB, int32_t gran) {
+std::vector<int32_t> batch_schedule(int64_t n_perms, int32_t PB, int32_t gran, int32_t first_batch) {
     std::vector<int32_t> out;
-    for (int64_t left = n_perms; left > 0; left -= PB)
+    int64_t left = n_perms;
+    if (first_batch > 0 && first_batch < PB && left > first_batch) { out.push_back(first_batch); left -= first_batch; }
+    for (; left > 0; left -= PB)
         out.push_back((int32_t)(left >= PB ? PB : (left + gran - 1) / gran * gran));
     return out;
 }
@@ -588,7 +591,11 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     const int32_t label_scale = h->fast_variant == 2 ? Q / 2 : 1;
     const int32_t G = (int32_t)h->G, L = h->L;
     const int32_t gran = std::max(128, 32 * Q);
-    const std::vector<int32_t> sched = batch_schedule(a.n_perms, PB, gran);
+    // option "fast_first_batch": a short first batch would shorten the slab prologue that nothing overlaps.  Measured
+    // (scripts/first_batch_ab.py, n_perms=1000): 128 / 256 permutations first -> configs[1] 3.79 -> 4.22 / 4.14 ms,
+    // configs[3] shape 14.44 -> 14.60 / 14.44, configs[2] 32.71 -> 33.06 / 32.89: never a gain, default off.
+    const int32_t first_batch = std::max(h->fast_first_batch, 0);
+    const std::vector<int32_t> sched = batch_schedule(a.n_perms, PB, gran, first_batch / gran * gran);
     const int64_t n_batches = (int64_t)sched.size();
     std::vector<int64_t> first(sched.size() + 1, 0);
     int32_t pb_max = gran;
@@ -1246,6 +1253,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "trimean_perm_batch") {
         if (value < 0 || value > 4096 || (value % 128) != 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: trimean_perm_batch must be a multiple of 128 in [0, 4096]");
         h->tm_perm_batch = (int32_t)value;
+    } else if (key == "fast_first_batch") {
+        if (value < 0 || value > 4096) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_first_batch must be in [0, 4096]");
+        h->fast_first_batch = (int32_t)value;
     } else if (key == "fast_q") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_q must be 0, 1, 2, 4 or 8");
         h->fast_q = (int32_t)value;
