@@ -142,7 +142,17 @@ struct lrperm_engine {
     int64_t N = 0, G = 0, nnz = 0;
     DevBuf indptr, csr_pairs, csc_pairs, err_flag;
     bool have_matrix = false, csc_ready = false;
-    std::vector<int32_t> h_csc_ptr;   // [G+1]
+    std::vector<int32_t> h_csc_ptr;   // [G+1] gene pointers of the value-sorted CSC (trimean path)
+    // FAST mode: the CSC copy is built cell tile by cell tile (the entries of a tile's rows are contiguous in CSR
+    // order and the tile's gene-major copy occupies the same index range), so a tile can be sorted - and its chunks
+    // run - while later tiles are still being uploaded
+    int32_t csc_tile_cells = 0, n_tiles = 0, tiles_enqueued = 0, tiles_tabled = 0;
+    int32_t* hist_pin = nullptr;          // pinned host [n_tiles][G] column counts per tile
+    size_t hist_pin_cap = 0;
+    DevBuf csc_keys, csc_keys2, csc_payload, tile_hist, tile_slot_ptr;
+    std::vector<cudaEvent_t> ev_tile;     // tile t: CSC sorted and histogram on the host
+    std::vector<FastChunk> h_chunks;      // tile-major; inside a tile longest first
+    std::vector<int32_t> h_tile_chunk_ptr, h_tile_slot_ptr, h_tile_entry0;
 
     // staged (caller's full) matrix, between lrperm_stage_matrix_csr and lrperm_commit_matrix
     bool staged = false;
@@ -172,7 +182,7 @@ struct lrperm_engine {
     int32_t fast_q = 0;                                 // permutations per lane (0 = auto)
     int32_t fast_first_batch = 0;                       // permutations of a short first batch (0 = none; A/B only)
     int32_t n_chunks = 0, n_slots = 0;
-    DevBuf chunks, gene_slot_ptr;
+    DevBuf chunks;
 
     // work buffers
     DevBuf slab2, partials2;              // second halves of the double buffers of the pipelined FAST path
@@ -316,107 +326,157 @@ int wait_matrix(lrperm_engine* h) {
     return LRPERM_OK;
 }
 
-// ---- CSC copy + chunk tables for FAST mode -------------------------------------------------
-int build_csc(lrperm_engine* h) {
-    if (h->csc_ready) return LRPERM_OK;
-    StageTimer timer("build_csc");
-    const int64_t nnz = h->nnz;
+// ---- CSC copy + chunk tables for FAST mode, one cell tile at a time ---------------------------
+int32_t fast_tile_cells(const lrperm_engine* h) {
+    // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
+    // (measured on B200, scripts/perf_tune.py: 131,072-cell tiles - 64 MiB of slab at 512 permutations, 16 MiB
+    // at the 125 permutations one of 8 GPUs runs - beat 32 MiB by 1% / 6% and 16 MiB by 3% on configs[2])
+    const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (64LL << 20);
+    // The tile (and with it the chunk table, i.e. the summation order of FAST mode) is defined for the
+    // nominal batch of 512 permutations whatever batch sizes are run: FAST results do not depend on the
+    // batch schedule, so they are bit-identical for any number of GPUs / permutation shards.
+    return (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / 512, 1024), std::max<int64_t>(h->N, 1));
+}
+
+// (re)start the tile-wise CSC build for `tile_cells`: buffers, per-tile events, pinned histogram
+int csc_begin(lrperm_engine* h, int32_t tile_cells) {
+    if (h->csc_ready && h->csc_tile_cells == tile_cells) return LRPERM_OK;
     const int32_t G = (int32_t)h->G;
-    const size_t n1 = (size_t)std::max<int64_t>(nnz, 1);
-    CK(h->tmp_a.ensure(sizeof(uint32_t) * n1));              // column keys
-    CK(h->tmp_c.ensure(sizeof(uint32_t) * n1));              // sorted keys (discarded)
-    CK(h->tmp_b.ensure(sizeof(unsigned long long) * n1));    // payload {cell, value bits}
-    DevBuf& col_count = h->small_a;
-    CK(col_count.ensure(sizeof(int32_t) * (size_t)(G + 1)));
-    CK(cudaMemsetAsync(col_count.p, 0, sizeof(int32_t) * (size_t)(G + 1), h->stream));
+    const size_t n1 = (size_t)std::max<int64_t>(h->nnz, 1);
+    h->csc_tile_cells = tile_cells;
+    h->n_tiles = (int32_t)std::max<int64_t>(1, (h->N + tile_cells - 1) / tile_cells);
+    h->tiles_enqueued = 0;
+    h->tiles_tabled = 0;
+    h->chunk_table_nnz = -1;
+    CK(h->csc_keys.ensure(sizeof(uint32_t) * n1));                // column keys
+    CK(h->csc_keys2.ensure(sizeof(uint32_t) * n1));               // sorted keys (discarded)
+    CK(h->csc_payload.ensure(sizeof(unsigned long long) * n1));   // payload {cell, value bits}
     CK(h->csc_pairs.ensure(sizeof(int2) * n1));
-    h->h_csc_ptr.assign((size_t)G + 1, 0);
-    if (nnz > 0) {
+    const size_t hist_elems = (size_t)h->n_tiles * (size_t)G;
+    CK(h->tile_hist.ensure(sizeof(int32_t) * hist_elems));
+    if (hist_elems > h->hist_pin_cap) {
+        if (h->hist_pin) cudaFreeHost(h->hist_pin);
+        h->hist_pin = nullptr; h->hist_pin_cap = 0;
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&h->hist_pin), sizeof(int32_t) * hist_elems, cudaHostAllocDefault));
+        h->hist_pin_cap = hist_elems;
+    }
+    while (h->ev_tile.size() < (size_t)h->n_tiles) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->ev_tile.push_back(ev);
+    }
+    // one temp buffer for the largest tile's sort
+    size_t tmp_bytes = 0;
+    int end_bit = 1;
+    while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->csc_keys.as<uint32_t>(), h->csc_keys2.as<uint32_t>(),
+                                       h->csc_payload.as<unsigned long long>(), reinterpret_cast<unsigned long long*>(h->csc_pairs.p),
+                                       (int)std::min<int64_t>(h->nnz, 0x7fffffff), 0, end_bit, h->stream));
+    CK(h->sort_tmp.ensure(tmp_bytes));
+    h->csc_ready = true;
+    return LRPERM_OK;
+}
+
+// queue the CSC build of tile t on `st`: keys + histogram, stable radix sort by column (cells stay ascending inside a
+// gene), histogram to the pinned host buffer, event.  [e0, e1) = the tile's entry range (host-known).
+int csc_enqueue_tile(lrperm_engine* h, int32_t t, int64_t e0, int64_t e1, cudaStream_t st) {
+    const int32_t G = (int32_t)h->G;
+    const int32_t row0 = (int32_t)std::min<int64_t>((int64_t)t * h->csc_tile_cells, h->N);
+    const int32_t row1 = (int32_t)std::min<int64_t>((int64_t)(t + 1) * h->csc_tile_cells, h->N);
+    int32_t* d_hist = h->tile_hist.as<int32_t>() + (size_t)t * G;
+    CK(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * (size_t)G, st));
+    if (e1 > e0) {
         size_t smem = sizeof(int32_t) * (size_t)G;
         const int use_shared = smem <= 96 * 1024;
         if (!use_shared) smem = 0;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(csc_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        csc_keys_kernel<<<h->sm_count * 4, 512, smem, h->stream>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), (int32_t)h->N, G,
-                                                                  h->tmp_a.as<uint32_t>(), h->tmp_b.as<unsigned long long>(), col_count.as<int32_t>(), use_shared);
+        const int grid = (int)std::min<int64_t>((int64_t)h->sm_count * 4, std::max<int64_t>(1, ((int64_t)(row1 - row0) * 32 + 511) / 512));
+        csc_keys_kernel<<<grid, 512, smem, st>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), row0, row1, G,
+                                                 h->csc_keys.as<uint32_t>(), h->csc_payload.as<unsigned long long>(), d_hist, use_shared);
         CK_LAUNCH();
         int end_bit = 1;
         while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
-        // stable LSD radix sort by column: cells stay ascending inside a gene; the sorted payload is csc_pairs
-        size_t tmp_bytes = 0;
-        unsigned long long* sorted = reinterpret_cast<unsigned long long*>(h->csc_pairs.p);
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->tmp_a.as<uint32_t>(), h->tmp_c.as<uint32_t>(),
-                                           h->tmp_b.as<unsigned long long>(), sorted, (int)nnz, 0, end_bit, h->stream));
-        CK(h->sort_tmp.ensure(tmp_bytes));
-        CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<uint32_t>(), h->tmp_c.as<uint32_t>(),
-                                           h->tmp_b.as<unsigned long long>(), sorted, (int)nnz, 0, end_bit, h->stream));
+        size_t tmp_bytes = h->sort_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->csc_keys.as<uint32_t>() + e0, h->csc_keys2.as<uint32_t>() + e0,
+                                           h->csc_payload.as<unsigned long long>() + e0,
+                                           reinterpret_cast<unsigned long long*>(h->csc_pairs.p) + e0, (int)(e1 - e0), 0, end_bit, st));
         h->launches += 4;
-        std::vector<int32_t> cnt((size_t)G + 1, 0);
-        CK(cudaMemcpyAsync(cnt.data(), col_count.p, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        for (int32_t g = 0; g < G; ++g) h->h_csc_ptr[(size_t)g + 1] = h->h_csc_ptr[(size_t)g] + cnt[(size_t)g];
-    } else {
-        CK(cudaStreamSynchronize(h->stream));
     }
-    // scratch buffers stay allocated: repeated set_matrix / run cycles (by_sample, e2e serving) would
-    // otherwise pay cudaMalloc/cudaFree (device-synchronising) on every call
-    h->csc_ready = true;
-    h->chunk_table_nnz = -1;
+    CK(cudaMemcpyAsync(h->hist_pin + (size_t)t * G, d_hist, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev_tile[(size_t)t], st));
     return LRPERM_OK;
 }
 
-int build_chunks(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
-    if (h->chunk_table_nnz == chunk_nnz && h->chunk_table_tile == tile_cells) return LRPERM_OK;
-    StageTimer timer("build_chunks");
+// chunk table of tile t (host, after its histogram arrived): every gene's entries inside the tile, cut every
+// chunk_nnz; inside the tile the longest chunks first (short ones fill the tail); slots numbered tile by tile
+int chunks_append_tile(lrperm_engine* h, int32_t t, int32_t chunk_nnz, cudaStream_t st) {
     const int32_t G = (int32_t)h->G;
-    // Split every gene's entry list at cell-tile boundaries (so that the chunks scheduled at any one
-    // time only touch one tile of the label slab, which then stays L2 resident) and at chunk_nnz.
-    const int32_t n_tiles = (int32_t)std::max<int64_t>(1, (h->N + tile_cells - 1) / tile_cells);
-    std::vector<int32_t> bounds((size_t)G * (n_tiles + 1));
-    {
-        DevBuf &d_ptr = h->small_a, &d_bounds = h->small_b;
-        CK(d_ptr.ensure(sizeof(int32_t) * ((size_t)G + 1)));
-        CK(d_bounds.ensure(sizeof(int32_t) * bounds.size()));
-        CK(cudaMemcpyAsync(d_ptr.p, h->h_csc_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
-        tile_bounds_kernel<<<grid_for((int64_t)bounds.size(), 256, 1 << 30), 256, 0, h->stream>>>(
-            h->csc_pairs.as<int2>(), d_ptr.as<int32_t>(), G, n_tiles, tile_cells, d_bounds.as<int32_t>());
-        CK_LAUNCH();
-        CK(cudaMemcpyAsync(bounds.data(), d_bounds.p, sizeof(int32_t) * bounds.size(), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventSynchronize(h->ev_tile[(size_t)t]));
+    if (t == 0) {
+        h->h_chunks.clear();
+        h->h_tile_chunk_ptr.assign(1, 0);
+        h->h_tile_slot_ptr.assign((size_t)h->n_tiles * ((size_t)G + 1), 0);
+        h->h_tile_entry0.assign(1, 0);
+        h->n_slots = 0;
+        // device tables sized for any tiling of this matrix
+        const size_t max_chunks = (size_t)(h->nnz / std::max(chunk_nnz, 1)) + (size_t)G * (size_t)h->n_tiles + 1;
+        CK(h->chunks.ensure(sizeof(FastChunk) * max_chunks));
+        CK(h->tile_slot_ptr.ensure(sizeof(int32_t) * h->h_tile_slot_ptr.size()));
     }
-    struct Tagged { FastChunk c; int32_t tile; };
-    std::vector<Tagged> tagged;
-    std::vector<int32_t> slot_ptr((size_t)G + 1, 0);
-    int32_t slot = 0;
+    const int32_t* hist = h->hist_pin + (size_t)t * G;
+    int32_t pos = h->h_tile_entry0[(size_t)t];
+    int32_t slot = h->n_slots;
+    const size_t first = h->h_chunks.size();
+    int32_t* tsp = h->h_tile_slot_ptr.data() + (size_t)t * ((size_t)G + 1);
     for (int32_t g = 0; g < G; ++g) {
-        slot_ptr[(size_t)g] = slot;
-        for (int32_t t = 0; t < n_tiles; ++t) {
-            const int32_t b = bounds[(size_t)g * (n_tiles + 1) + t], e = bounds[(size_t)g * (n_tiles + 1) + t + 1];
-            for (int32_t s = b; s < e; s += chunk_nnz) {
-                Tagged x;
-                x.c.gene = g; x.c.begin = s; x.c.end = std::min(e, s + chunk_nnz); x.c.slot = slot++;
-                x.tile = t;
-                tagged.push_back(x);
-            }
+        tsp[g] = slot;
+        const int32_t e = pos + hist[g];
+        for (int32_t s0 = pos; s0 < e; s0 += chunk_nnz) {
+            FastChunk c;
+            c.gene = g; c.begin = s0; c.end = std::min(e, s0 + chunk_nnz); c.slot = slot++;
+            h->h_chunks.push_back(c);
         }
+        pos = e;
     }
-    slot_ptr[(size_t)G] = slot;
-    // tile-major; inside a tile the longest chunks first (short ones fill the tail)
-    std::stable_sort(tagged.begin(), tagged.end(), [](const Tagged& a, const Tagged& b) {
-        if (a.tile != b.tile) return a.tile < b.tile;
-        return (a.c.end - a.c.begin) > (b.c.end - b.c.begin);
-    });
-    std::vector<FastChunk> chunks(tagged.size());
-    for (size_t i = 0; i < tagged.size(); ++i) chunks[i] = tagged[i].c;
-    h->n_chunks = (int32_t)chunks.size();
+    tsp[G] = slot;
+    std::stable_sort(h->h_chunks.begin() + (std::ptrdiff_t)first, h->h_chunks.end(),
+                     [](const FastChunk& a, const FastChunk& b) { return (a.end - a.begin) > (b.end - b.begin); });
+    h->h_tile_entry0.push_back(pos);
+    h->h_tile_chunk_ptr.push_back((int32_t)h->h_chunks.size());
     h->n_slots = slot;
-    CK(h->chunks.ensure(sizeof(FastChunk) * std::max<size_t>(chunks.size(), 1)));
-    CK(h->gene_slot_ptr.ensure(sizeof(int32_t) * ((size_t)G + 1)));
-    if (!chunks.empty())
-        CK(cudaMemcpyAsync(h->chunks.p, chunks.data(), sizeof(FastChunk) * chunks.size(), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->gene_slot_ptr.p, slot_ptr.data(), sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
-    h->chunk_table_nnz = chunk_nnz;
-    h->chunk_table_tile = tile_cells;
+    h->n_chunks = (int32_t)h->h_chunks.size();
+    const size_t n_new = h->h_chunks.size() - first;
+    if (n_new)
+        CK(cudaMemcpyAsync(h->chunks.as<FastChunk>() + first, h->h_chunks.data() + first, sizeof(FastChunk) * n_new, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->tile_slot_ptr.as<int32_t>() + (size_t)t * ((size_t)G + 1), tsp, sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, st));
+    h->tiles_tabled = t + 1;
+    return LRPERM_OK;
+}
+
+// everything at once (matrix resident): CSC of all tiles, then all chunk tables
+int ensure_fast_tables(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
+    int rc;
+    if (!(h->csc_ready && h->csc_tile_cells == tile_cells)) {
+        StageTimer timer("build_csc");
+        if ((rc = csc_begin(h, tile_cells))) return rc;
+        // entry ranges of the tiles: indptr at the tile boundaries
+        std::vector<int32_t> e((size_t)h->n_tiles + 1, 0);
+        for (int32_t t = 0; t <= h->n_tiles; ++t) {
+            const int64_t row = std::min<int64_t>((int64_t)t * tile_cells, h->N);
+            CK(cudaMemcpyAsync(&e[(size_t)t], h->indptr.as<int32_t>() + row, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        for (int32_t t = 0; t < h->n_tiles; ++t)
+            if ((rc = csc_enqueue_tile(h, t, e[(size_t)t], e[(size_t)t + 1], h->stream))) return rc;
+        h->tiles_enqueued = h->n_tiles;
+    }
+    if (h->tiles_enqueued == h->n_tiles && (h->chunk_table_nnz != chunk_nnz || h->tiles_tabled < h->n_tiles)) {
+        StageTimer timer("build_chunks");
+        const int32_t from = h->chunk_table_nnz == chunk_nnz ? h->tiles_tabled : 0;
+        for (int32_t t = from; t < h->n_tiles; ++t)
+            if ((rc = chunks_append_tile(h, t, chunk_nnz, h->stream))) return rc;
+        h->chunk_table_nnz = chunk_nnz;
+    }
     return LRPERM_OK;
 }
 
@@ -469,32 +529,32 @@ int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube
 }
 
 template <int Q>
-int launch_fast_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials) {
+int launch_fast_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, int32_t c0, int32_t cn) {
     const int32_t L = h->L;
     const size_t smem = (size_t)kFastWarps * L * Q * 32 * sizeof(float);
     CK(cudaFuncSetAttribute(fast_means_kernel<Q, kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int32_t groups = PB / (32 * Q);
-    const int64_t items = (int64_t)h->n_chunks * groups;
+    const int64_t items = (int64_t)cn * groups;
     const int64_t grid = (items + kFastWarps - 1) / kFastWarps;
     if (grid > 0) {
         fast_means_kernel<Q, kFastWarps><<<(unsigned)grid, kFastWarps * 32, smem, h->stream>>>(
-            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, slab, PB, L, groups, partials);
+            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>() + c0, cn, slab, PB, L, groups, partials);
         CK_LAUNCH();
     }
     return LRPERM_OK;
 }
 
 template <int Q, int B>
-int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials) {
+int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, int32_t c0, int32_t cn) {
     const int32_t L = h->L;
     const size_t smem = (size_t)L * Q * 128 + 16 * B;
     CK(cudaFuncSetAttribute(fast2_means_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int32_t groups = PB / (32 * Q);
-    const int64_t grid = (int64_t)h->n_chunks * groups;
+    const int64_t grid = (int64_t)cn * groups;
     if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: too many chunks (%lld CTAs)", (long long)grid);
     if (grid > 0) {
         fast2_means_kernel<Q, B><<<(unsigned)grid, 32, smem, h->stream>>>(
-            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>(), h->n_chunks, slab, PB, L, groups, partials);
+            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>() + c0, cn, slab, PB, L, groups, partials);
         CK_LAUNCH();
     }
     return LRPERM_OK;
@@ -546,15 +606,17 @@ int launch_score_t(lrperm_engine* h, int scores, const float* cube, int32_t PP, 
 }
 
 
-int launch_fast_any(lrperm_engine* h, int Q, int32_t PB, const uint8_t* slab, float* partials) {
+// chunks [c0, c0 + cn) of the table (cn < 0: all)
+int launch_fast_any(lrperm_engine* h, int Q, int32_t PB, const uint8_t* slab, float* partials, int32_t c0 = 0, int32_t cn = -1) {
+    if (cn < 0) cn = h->n_chunks - c0;
     if (h->fast_variant == 2) {
-        if (Q == 8) return launch_fast2_q<8, 16>(h, PB, slab, partials);
-        if (Q == 4) return launch_fast2_q<4, 32>(h, PB, slab, partials);
-        return launch_fast2_q<2, 32>(h, PB, slab, partials);
+        if (Q == 8) return launch_fast2_q<8, 16>(h, PB, slab, partials, c0, cn);
+        if (Q == 4) return launch_fast2_q<4, 32>(h, PB, slab, partials, c0, cn);
+        return launch_fast2_q<2, 32>(h, PB, slab, partials, c0, cn);
     }
-    if (Q == 4) return launch_fast_q<4>(h, PB, slab, partials);
-    if (Q == 2) return launch_fast_q<2>(h, PB, slab, partials);
-    return launch_fast_q<1>(h, PB, slab, partials);
+    if (Q == 4) return launch_fast_q<4>(h, PB, slab, partials, c0, cn);
+    if (Q == 2) return launch_fast_q<2>(h, PB, slab, partials, c0, cn);
+    return launch_fast_q<1>(h, PB, slab, partials, c0, cn);
 }
 
 struct RunArgs {
@@ -665,8 +727,7 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     if ((rc = enqueue_slab(0))) return rc;
     if (n_batches > 1 && (rc = enqueue_slab(1))) return rc;
     if ((rc = wait_matrix(h))) return rc;
-    if ((rc = build_csc(h))) return rc;
-    if ((rc = build_chunks(h, chunk_nnz, tile_cells))) return rc;
+    if ((rc = ensure_fast_tables(h, chunk_nnz, tile_cells))) return rc;
     const size_t part_max = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * pb_max;
     CK(h->partials.ensure(part_max));
     if (dbl) CK(h->partials2.ensure(part_max));
@@ -686,7 +747,7 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         CK(cudaStreamWaitEvent(sB, EV(b, 3), 0));
         CK(cudaEventRecord(EV(b, 4), sB));
         fast_finalize_kernel<<<grid_for((int64_t)G * L * PBb, 256, h->sm_count * 8), 256, 0, sB>>>(
-            parts[b & 1], h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PBb, h->cube.as<float>(), PBb, 0);
+            parts[b & 1], h->tile_slot_ptr.as<int32_t>(), h->n_tiles, h->inv_n.as<float>(), G, L, PBb, h->cube.as<float>(), PBb, 0);
         CK_LAUNCH();
         CK(cudaEventRecord(EV(b, 5), sB));
         if (a.scores) {
@@ -1206,13 +1267,15 @@ void lrperm_destroy(lrperm_engine* h) {
     for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->st_indptr, &h->st_indices, &h->st_data, &h->st_row_keep, &h->st_small,
                       &h->labels32, &h->labels8, &h->labels8s, &h->order, &h->rank, &h->bucket_cluster,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
-                      &h->chunks, &h->gene_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
+                      &h->chunks, &h->csc_keys, &h->csc_keys2, &h->csc_payload, &h->tile_hist, &h->tile_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b,
                       &h->vsc_pairs, &h->tm_chunks, &h->tm_region_ptr, &h->tm_counts, &h->tm_prefix, &h->tm_planes, &h->tm_cube,
                       &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t, &h->tm_diag, &h->tm_chunk_of_slot, &h->tm_region_dir,
                       &h->tm_walk_flag, &h->tm_walk_list})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ev_tile) cudaEventDestroy(ev);
+    if (h->hist_pin) cudaFreeHost(h->hist_pin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1314,7 +1377,7 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
         CK(cudaMemcpyAsync(h->st_indices.p, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, sC));
         CK(cudaMemcpyAsync(h->st_data.p, data, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, sC));
         pack_csr_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, sC>>>(
-            h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), (int32_t)n_cells, (int32_t)n_genes,
+            h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), 0, (int32_t)n_cells, (int32_t)n_genes,
             h->csr_pairs.as<int2>(), h->err_flag_m.as<int>());
         CK_LAUNCH();
         CK(cudaEventRecord(h->ev_matrix, sC));
@@ -1350,7 +1413,7 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
             d_val = h->tmp_c.as<float>();
         }
         pack_csr_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
-            h->indptr.as<int32_t>(), d_idx, d_val, (int32_t)n_cells, (int32_t)n_genes, h->csr_pairs.as<int2>(), h->err_flag.as<int>());
+            h->indptr.as<int32_t>(), d_idx, d_val, 0, (int32_t)n_cells, (int32_t)n_genes, h->csr_pairs.as<int2>(), h->err_flag.as<int>());
         CK_LAUNCH();
     }
     int rc = check_err_flag(h, "lrperm_set_matrix_csr");
@@ -1516,7 +1579,7 @@ int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_gen
             (int32_t)N, h->indptr.as<int32_t>(), h->tmp_c.as<int32_t>(), h->tmp_d.as<float>());
         CK_LAUNCH();
         pack_csr_kernel<<<grid_for(N_out * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
-            h->indptr.as<int32_t>(), h->tmp_c.as<int32_t>(), h->tmp_d.as<float>(), (int32_t)N_out, (int32_t)n_genes_out, h->csr_pairs.as<int2>(), h->err_flag.as<int>());
+            h->indptr.as<int32_t>(), h->tmp_c.as<int32_t>(), h->tmp_d.as<float>(), 0, (int32_t)N_out, (int32_t)n_genes_out, h->csr_pairs.as<int2>(), h->err_flag.as<int>());
         CK_LAUNCH();
     }
     if ((rc = check_err_flag(h, "lrperm_commit_matrix"))) return rc;
@@ -1770,14 +1833,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         const int32_t gran = std::max(128, 32 * Q);        // a warp covers 32*Q permutations
         if (n_perms < PB) PB = (int32_t)std::max<int64_t>(gran, ((n_perms + gran - 1) / gran) * gran);
         PB = ((PB + gran - 1) / gran) * gran;
-        // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
-        // (measured on B200, scripts/perf_tune.py: 131,072-cell tiles - 64 MiB of slab at 512 permutations, 16 MiB
-        // at the 125 permutations one of 8 GPUs runs - beat 32 MiB by 1% / 6% and 16 MiB by 3% on configs[2])
-        const int64_t tile_bytes = h->fast_tile_bytes ? h->fast_tile_bytes : (64LL << 20);
-        // The tile (and with it the chunk table, i.e. the summation order of FAST mode) is defined for the
-        // nominal batch of 512 permutations whatever batch sizes are run: FAST results do not depend on the
-        // batch schedule, so they are bit-identical for any number of GPUs / permutation shards.
-        const int32_t tile_cells = (int32_t)std::min<int64_t>(std::max<int64_t>(tile_bytes / 512, 1024), std::max<int64_t>(N, 1));
+        const int32_t tile_cells = fast_tile_cells(h);
         // entries per chunk: long chunks amortise the bin zeroing / partial-sum write-out, but the grid should
         // still hold ~16 waves of (chunk x permutation group) warps; 4096 for configs[1], 16384 for configs[2]
         int32_t chunk_nnz = h->fast_chunk_nnz;
@@ -1804,8 +1860,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     const bool pipelined = order_mode == LRPERM_ORDER_FAST && h->overlap && n_batches > 0;
     if (order_mode == LRPERM_ORDER_FAST && !pipelined) {
         if ((rc = wait_matrix(h))) return rc;
-        if ((rc = build_csc(h))) return rc;
-        if ((rc = build_chunks(h, fast_chunk, fast_tile))) return rc;
+        if ((rc = ensure_fast_tables(h, fast_chunk, fast_tile))) return rc;
         CK(h->slab.ensure((size_t)N * PB));
         CK(h->partials.ensure(sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB));
     }
@@ -1884,7 +1939,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
             if (rc) return rc;
             CK(cudaEventRecord(h->events[evi++], h->stream));   // main kernel done
             fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, h->stream>>>(
-                h->partials.as<float>(), h->gene_slot_ptr.as<int32_t>(), h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
+                h->partials.as<float>(), h->tile_slot_ptr.as<int32_t>(), h->n_tiles, h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
             CK_LAUNCH();
         } else {
             if ((rc = launch_exact(h, ps, pb, h->cube.as<float>(), PP))) return rc;

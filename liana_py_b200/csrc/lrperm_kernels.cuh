@@ -37,13 +37,13 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // ceil(c / groups) (+1) times per group instead of ~3.4 times for random columns.  The order of the
 // stored entries inside a row is irrelevant for the arithmetic (one entry per column and row).
 __global__ void pack_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                const float* __restrict__ data, int32_t N, int32_t G,
+                                const float* __restrict__ data, int32_t row0, int32_t row1, int32_t G,
                                 int2* __restrict__ pairs, int* __restrict__ err) {
     const int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int r = warp; r < N; r += nwarps) {
+    for (int r = row0 + warp; r < row1; r += nwarps) {
         const int s = indptr[r], e = indptr[r + 1];
         const int n = e - s;
         if (n <= 0) continue;
@@ -237,10 +237,11 @@ __global__ void narrow_indptr_kernel(const T* __restrict__ in, int64_t n, int32_
     }
 }
 
-// CSR -> CSC transpose, step 1: per stored entry the sort key (column) and the payload {cell, value bits}
-// packed so that the sorted payload array IS the csc_pairs array; column histogram privatised in shared
-// memory (one global atomic per (CTA, column) instead of one per entry).
-__global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs, int32_t N, int32_t G,
+// CSR -> CSC transpose of ONE cell tile (rows [row0, row1)), step 1: per stored entry the sort key (column) and the
+// payload {cell, value bits} packed so that the sorted payload array IS the tile's csc_pairs range; column histogram of
+// the tile privatised in shared memory (one global atomic per (CTA, column) instead of one per entry).  The entries
+// of a tile's rows are contiguous in CSR order, and the tile's CSC occupies the same index range.
+__global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs, int32_t row0, int32_t row1, int32_t G,
                                 uint32_t* __restrict__ keys, unsigned long long* __restrict__ payload,
                                 int32_t* __restrict__ col_count, int use_shared) {
     extern __shared__ int32_t hist_smem[];
@@ -250,7 +251,7 @@ __global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* 
     const int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < N; r += nwarps) {
+    for (int r = row0 + warp; r < row1; r += nwarps) {
         const int s = indptr[r], e = indptr[r + 1];
         for (int o = s + lane; o < e; o += 32) {
             const int2 pr = pairs[o];
@@ -263,21 +264,6 @@ __global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* 
     if (use_shared)
         for (int g = threadIdx.x; g < G; g += blockDim.x)
             if (hist[g]) atomicAdd(&col_count[g], hist[g]);
-}
-
-// first stored entry of gene g whose cell id is >= t * tile_cells (CSC cells ascend within a gene)
-__global__ void tile_bounds_kernel(const int2* __restrict__ csc_pairs, const int32_t* __restrict__ csc_ptr, int32_t G,
-                                   int32_t n_tiles, int32_t tile_cells, int32_t* __restrict__ bounds /*[G][n_tiles+1]*/) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)G * (n_tiles + 1)) return;
-    const int g = (int)(i / (n_tiles + 1)), t = (int)(i % (n_tiles + 1));
-    int lo = csc_ptr[g], hi = csc_ptr[g + 1];
-    const int64_t key = (int64_t)t * tile_cells;
-    while (lo < hi) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if ((int64_t)csc_pairs[mid].x < key) lo = mid + 1; else hi = mid;
-    }
-    bounds[i] = lo;
 }
 
 // stored-entry counts per (cluster, gene): props = count / n_c  (_common.py:41-42)
@@ -787,9 +773,11 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
     }
 }
 
-// FAST mode, step 3: combine a gene's chunk partials in fixed order, scale by 1/n_c, write cube.
-__global__ void fast_finalize_kernel(const float* __restrict__ partials, const int32_t* __restrict__ gene_slot_ptr /*[G+1]*/,
-                                     const float* __restrict__ inv_n, int32_t G, int32_t L, int32_t PB,
+// FAST mode, step 3: combine a gene's chunk partials in fixed order (cell tiles ascending, chunks ascending inside a
+// tile: slots are numbered tile by tile, tile_slot_ptr[t][g] .. [t][g+1] are gene g's slots in tile t), scale by
+// 1/n_c, write cube.
+__global__ void fast_finalize_kernel(const float* __restrict__ partials, const int32_t* __restrict__ tile_slot_ptr /*[n_tiles][G+1]*/,
+                                     int32_t n_tiles, const float* __restrict__ inv_n, int32_t G, int32_t L, int32_t PB,
                                      float* __restrict__ cube, int32_t PP, int32_t p_off) {
     // thread per (g, c, p) with p fastest
     const int64_t total = (int64_t)G * L * PB;
@@ -799,8 +787,10 @@ __global__ void fast_finalize_kernel(const float* __restrict__ partials, const i
         const int c = (int)(gc % L);
         const int g = (int)(gc / L);
         float s = 0.0f;
-        const int s0 = gene_slot_ptr[g], s1 = gene_slot_ptr[g + 1];
-        for (int sl = s0; sl < s1; ++sl) s = __fadd_rn(s, __ldcs(&partials[((int64_t)sl * L + c) * PB + p]));
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s0 = tile_slot_ptr[(int64_t)t * (G + 1) + g], s1 = tile_slot_ptr[(int64_t)t * (G + 1) + g + 1];
+            for (int sl = s0; sl < s1; ++sl) s = __fadd_rn(s, __ldcs(&partials[((int64_t)sl * L + c) * PB + p]));
+        }
         cube[((int64_t)g * L + c) * PP + p_off + p] = __fmul_rn(s, inv_n[c]);
     }
 }
