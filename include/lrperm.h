@@ -72,6 +72,13 @@ int lrperm_set_stream(lrperm_engine *h, void *cuda_stream);
  * The expression matrix the hot path sees: CSR float32, N cells x G genes, already subset to
  * the resource's genes (input contract: _pipe_utils/_pre.py:65-169, _liana_pipe.py:161-164).
  * indptr has N+1 entries of int32 (indptr_is_64 == 0) or int64; nnz must be < 2^31, G <= 65535.
+ *
+ * Host buffers in PINNED memory (cudaHostAlloc / cudaHostRegister) are uploaded asynchronously, cell tile by cell tile,
+ * on a copy stream of the engine: the call returns at once, and the buffers must stay valid and unchanged until the
+ * first call that consumes the matrix (lrperm_run, lrperm_observed, ...) has returned - as with cudaMemcpyAsync.
+ * lrperm_run in FAST order then starts its first batch on the first tile while the others are still in flight.
+ * The row pointers are validated before the call returns; a column out of range is reported by the consuming call.
+ * Pageable host buffers and device buffers are consumed before the call returns.
  */
 int lrperm_set_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes,
                           const void *indptr, int indptr_is_64,

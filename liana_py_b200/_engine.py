@@ -157,6 +157,8 @@ class Engine:
         p1, _, k1 = _ptr(indices)
         p2, _, k2 = _ptr(data)
         self._check(self._lib.lrperm_set_matrix_csr(self._h, int(n_cells), int(n_genes), p0, int(is64), p1, p2, dev))
+        # pinned host buffers are uploaded asynchronously (include/lrperm.h): keep them alive until the next matrix
+        self._matrix_keepalive = (k0, k1, k2)
         self.N, self.G = int(n_cells), int(n_genes)
 
     def set_matrix(self, X):

@@ -67,6 +67,30 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Pinned host buffer that only grows.  Outgrown blocks are kept until the engine is destroyed: a copy kernel or an
+// asynchronous copy queued earlier may still be reading the old block.
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    std::vector<void*> retired;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) retired.push_back(p);
+        p = nullptr; cap = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, 1u << 16);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        for (void* q : retired) cudaFreeHost(q);
+        p = nullptr; cap = 0; retired.clear();
+        cudaGetLastError();
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // Host-side helper of pageable uploads: a few persistent threads that memcpy slices of one piece into a pinned
 // staging buffer in parallel (one thread moves ~10 GB/s, PCIe takes ~50 GB/s).
 class ParallelCopier {
@@ -127,6 +151,14 @@ struct lrperm_engine {
     cudaStream_t copy_stream = nullptr;   // matrix uploads from pinned host memory (lrperm_set_matrix_csr) run here, unwaited
     cudaEvent_t ev_matrix = nullptr;      // recorded on copy_stream after the upload + packing
     bool matrix_pending = false;          // the engine stream has not waited for ev_matrix yet (validation deferred too)
+    // tile-wise upload: lrperm_set_matrix_csr submits the first cell tile only; the remaining tiles are submitted by
+    // the first call that consumes the matrix (AFTER the small uploads of set_labels / set_triples: the copy engine
+    // serves H2D copies in submission order), each followed on the copy stream by its packing and CSC sort
+    const void* up_indices = nullptr;
+    const void* up_data = nullptr;
+    std::vector<int64_t> up_e;            // entry offset at every tile boundary [n_tiles + 1]
+    int32_t up_next_tile = 0;
+    bool check_matrix_flag = false;       // the gated first batch consumed a pending upload: read err_flag_m after the run
     DevBuf err_flag_m;                    // validation flags of the pending matrix
     // pageable uploads: two pinned staging pieces filled by a few host threads while the other one is in flight
     ParallelCopier* copier = nullptr;
@@ -147,8 +179,8 @@ struct lrperm_engine {
     // order and the tile's gene-major copy occupies the same index range), so a tile can be sorted - and its chunks
     // run - while later tiles are still being uploaded
     int32_t csc_tile_cells = 0, n_tiles = 0, tiles_enqueued = 0, tiles_tabled = 0;
-    int32_t* hist_pin = nullptr;          // pinned host [n_tiles][G] column counts per tile
-    size_t hist_pin_cap = 0;
+    PinnedBuf hist_pin;                   // pinned host [n_tiles][G] column counts per tile
+    PinnedBuf table_pin;                  // pinned host mirror of the chunk table + tile_slot_ptr rows (read by copy_words_kernel)
     DevBuf csc_keys, csc_keys2, csc_payload, tile_hist, tile_slot_ptr;
     std::vector<cudaEvent_t> ev_tile;     // tile t: CSC sorted and histogram on the host
     std::vector<FastChunk> h_chunks;      // tile-major; inside a tile longest first
@@ -306,26 +338,6 @@ int check_err_flag(lrperm_engine* h, const char* what) {
     return LRPERM_OK;
 }
 
-// A matrix uploaded from pinned host memory is still in flight on the copy stream (lrperm_set_matrix_csr returned
-// without waiting): make the engine stream wait for it and surface the deferred validation result.  Everything
-// that reads the matrix on the device calls this first; what does not need it (labels, triples, the label slabs of
-// the first batches) proceeds while the upload runs.
-int wait_matrix(lrperm_engine* h) {
-    if (!h->matrix_pending) return LRPERM_OK;
-    h->matrix_pending = false;
-    CK(cudaStreamWaitEvent(h->stream, h->ev_matrix, 0));
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, h->err_flag_m.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (flag) {
-        CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream));
-        h->have_matrix = false;
-        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr (deferred check): invalid input (flag=%d: 1=column out of range, "
-                       "2=indptr overflow, 4=indptr not monotone)", flag);
-    }
-    return LRPERM_OK;
-}
-
 // ---- CSC copy + chunk tables for FAST mode, one cell tile at a time ---------------------------
 int32_t fast_tile_cells(const lrperm_engine* h) {
     // cells per tile: the slab rows of one tile (tile_cells x PB bytes) should sit in L2
@@ -354,12 +366,7 @@ int csc_begin(lrperm_engine* h, int32_t tile_cells) {
     CK(h->csc_pairs.ensure(sizeof(int2) * n1));
     const size_t hist_elems = (size_t)h->n_tiles * (size_t)G;
     CK(h->tile_hist.ensure(sizeof(int32_t) * hist_elems));
-    if (hist_elems > h->hist_pin_cap) {
-        if (h->hist_pin) cudaFreeHost(h->hist_pin);
-        h->hist_pin = nullptr; h->hist_pin_cap = 0;
-        CK(cudaHostAlloc(reinterpret_cast<void**>(&h->hist_pin), sizeof(int32_t) * hist_elems, cudaHostAllocDefault));
-        h->hist_pin_cap = hist_elems;
-    }
+    CK(h->hist_pin.ensure(sizeof(int32_t) * hist_elems));
     while (h->ev_tile.size() < (size_t)h->n_tiles) {
         cudaEvent_t ev;
         CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -402,8 +409,56 @@ int csc_enqueue_tile(lrperm_engine* h, int32_t t, int64_t e0, int64_t e1, cudaSt
                                            reinterpret_cast<unsigned long long*>(h->csc_pairs.p) + e0, (int)(e1 - e0), 0, end_bit, st));
         h->launches += 4;
     }
-    CK(cudaMemcpyAsync(h->hist_pin + (size_t)t * G, d_hist, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->hist_pin.as<int32_t>() + (size_t)t * G, d_hist, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev_tile[(size_t)t], st));
+    return LRPERM_OK;
+}
+
+// submit the transfer + packing + CSC sort of the next `count` tiles of a pending pinned upload (count < 0: all that
+// are left) to the copy stream; after the last one ev_matrix marks "the whole matrix is on the device"
+int submit_tiles(lrperm_engine* h, int32_t count) {
+    cudaStream_t sC = h->copy_stream;
+    int rc;
+    const int32_t end = count < 0 ? h->n_tiles : std::min(h->n_tiles, h->up_next_tile + count);
+    for (int32_t t = h->up_next_tile; t < end; ++t) {
+        const int64_t e0 = h->up_e[(size_t)t], e1 = h->up_e[(size_t)t + 1];
+        const int32_t row0 = (int32_t)std::min<int64_t>((int64_t)t * h->csc_tile_cells, h->N);
+        const int32_t row1 = (int32_t)std::min<int64_t>((int64_t)(t + 1) * h->csc_tile_cells, h->N);
+        if (e1 > e0) {
+            CK(cudaMemcpyAsync(h->st_indices.as<int32_t>() + e0, static_cast<const int32_t*>(h->up_indices) + e0, sizeof(int32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, sC));
+            CK(cudaMemcpyAsync(h->st_data.as<float>() + e0, static_cast<const float*>(h->up_data) + e0, sizeof(float) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, sC));
+            pack_csr_kernel<<<grid_for((int64_t)(row1 - row0) * 32, 256, h->sm_count * 32), 256, 0, sC>>>(
+                h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), row0, row1, (int32_t)h->G,
+                h->csr_pairs.as<int2>(), h->err_flag_m.as<int>());
+            CK_LAUNCH();
+        }
+        if ((rc = csc_enqueue_tile(h, t, e0, e1, sC))) return rc;
+        h->tiles_enqueued = t + 1;
+    }
+    h->up_next_tile = end;
+    if (end == h->n_tiles) CK(cudaEventRecord(h->ev_matrix, sC));
+    return LRPERM_OK;
+}
+
+// A matrix uploaded from pinned host memory may still be in flight on the copy stream (lrperm_set_matrix_csr returned
+// without waiting): submit what is left of it, make the engine stream wait, surface the deferred validation result.
+// Everything that reads the whole matrix on the device calls this first; what does not need it (labels, triples,
+// the label slabs of the first batches) proceeds while the upload runs.
+int wait_matrix(lrperm_engine* h) {
+    if (!h->matrix_pending) return LRPERM_OK;
+    int rc;
+    if ((rc = submit_tiles(h, -1))) return rc;
+    h->matrix_pending = false;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_matrix, 0));
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->err_flag_m.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag) {
+        CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream));
+        h->have_matrix = false;
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr (deferred check): invalid input (flag=%d: 1=column out of range, "
+                       "2=indptr overflow, 4=indptr not monotone)", flag);
+    }
     return LRPERM_OK;
 }
 
@@ -422,8 +477,10 @@ int chunks_append_tile(lrperm_engine* h, int32_t t, int32_t chunk_nnz, cudaStrea
         const size_t max_chunks = (size_t)(h->nnz / std::max(chunk_nnz, 1)) + (size_t)G * (size_t)h->n_tiles + 1;
         CK(h->chunks.ensure(sizeof(FastChunk) * max_chunks));
         CK(h->tile_slot_ptr.ensure(sizeof(int32_t) * h->h_tile_slot_ptr.size()));
+        const size_t words = max_chunks * (sizeof(FastChunk) / 4) + h->h_tile_slot_ptr.size();
+        CK(h->table_pin.ensure(sizeof(uint32_t) * words));      // an outgrown mirror is retired, not freed: nothing in flight loses it
     }
-    const int32_t* hist = h->hist_pin + (size_t)t * G;
+    const int32_t* hist = h->hist_pin.as<int32_t>() + (size_t)t * G;
     int32_t pos = h->h_tile_entry0[(size_t)t];
     int32_t slot = h->n_slots;
     const size_t first = h->h_chunks.size();
@@ -445,10 +502,23 @@ int chunks_append_tile(lrperm_engine* h, int32_t t, int32_t chunk_nnz, cudaStrea
     h->h_tile_chunk_ptr.push_back((int32_t)h->h_chunks.size());
     h->n_slots = slot;
     h->n_chunks = (int32_t)h->h_chunks.size();
+    // to the device through the pinned mirror and a copy KERNEL (not the copy engine: see copy_words_kernel); the mirror
+    // has a distinct region per tile, so nothing in flight is overwritten
     const size_t n_new = h->h_chunks.size() - first;
-    if (n_new)
-        CK(cudaMemcpyAsync(h->chunks.as<FastChunk>() + first, h->h_chunks.data() + first, sizeof(FastChunk) * n_new, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->tile_slot_ptr.as<int32_t>() + (size_t)t * ((size_t)G + 1), tsp, sizeof(int32_t) * ((size_t)G + 1), cudaMemcpyHostToDevice, st));
+    const size_t cw = sizeof(FastChunk) / 4;
+    const size_t max_chunks = (size_t)(h->nnz / std::max(chunk_nnz, 1)) + (size_t)G * (size_t)h->n_tiles + 1;
+    if (n_new) {
+        uint32_t* pin = h->table_pin.as<uint32_t>() + first * cw;
+        memcpy(pin, h->h_chunks.data() + first, sizeof(FastChunk) * n_new);
+        copy_words_kernel<<<grid_for((int64_t)(n_new * cw), 256, 256), 256, 0, st>>>(pin, reinterpret_cast<uint32_t*>(h->chunks.as<FastChunk>() + first), (int64_t)(n_new * cw));
+        CK_LAUNCH();
+    }
+    {
+        uint32_t* pin = h->table_pin.as<uint32_t>() + max_chunks * cw + (size_t)t * ((size_t)G + 1);
+        memcpy(pin, tsp, sizeof(int32_t) * ((size_t)G + 1));
+        copy_words_kernel<<<grid_for((int64_t)G + 1, 256, 64), 256, 0, st>>>(pin, reinterpret_cast<uint32_t*>(h->tile_slot_ptr.as<int32_t>() + (size_t)t * ((size_t)G + 1)), (int64_t)G + 1);
+        CK_LAUNCH();
+    }
     h->tiles_tabled = t + 1;
     return LRPERM_OK;
 }
@@ -726,9 +796,22 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     // the CSC / chunk-table builds, so they run while the matrix crosses PCIe.
     if ((rc = enqueue_slab(0))) return rc;
     if (n_batches > 1 && (rc = enqueue_slab(1))) return rc;
-    if ((rc = wait_matrix(h))) return rc;
-    if ((rc = ensure_fast_tables(h, chunk_nnz, tile_cells))) return rc;
-    const size_t part_max = sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * pb_max;
+    // A pinned upload still in flight, tiled the way this run wants it: the first batch runs TILE BY TILE behind the
+    // transfer (chunks are scheduled tile-major anyway): the host waits for tile t's CSC sort, builds its chunk
+    // table, launches the tile's chunk warps; tiles t+1.. keep crossing PCIe and being sorted on the copy stream.
+    const bool gated = h->matrix_pending && h->csc_tile_cells == tile_cells;
+    size_t slots_cap;
+    if (gated) {
+        if ((rc = submit_tiles(h, -1))) return rc;           // behind the label / triple uploads in the copy engine's queue
+        h->chunk_table_nnz = -1;
+        h->tiles_tabled = 0;
+        slots_cap = (size_t)(h->nnz / std::max(chunk_nnz, 1)) + (size_t)G * (size_t)h->n_tiles + 1;
+    } else {
+        if ((rc = wait_matrix(h))) return rc;
+        if ((rc = ensure_fast_tables(h, chunk_nnz, tile_cells))) return rc;
+        slots_cap = (size_t)std::max(h->n_slots, 1);
+    }
+    const size_t part_max = sizeof(float) * slots_cap * L * pb_max;
     CK(h->partials.ensure(part_max));
     if (dbl) CK(h->partials2.ensure(part_max));
     float* parts[2] = {h->partials.as<float>(), dbl ? h->partials2.as<float>() : h->partials.as<float>()};
@@ -741,7 +824,18 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         CK(cudaStreamWaitEvent(sA, EV(b, 1), 0));
         if (b >= 2) CK(cudaStreamWaitEvent(sA, EV(b - 2, 5), 0));     // partials[b&1] consumed by finalize(b-2)
         CK(cudaEventRecord(EV(b, 2), sA));
-        if ((rc = launch_fast_any(h, Q, PBb, slabs[b & 1], parts[b & 1]))) return rc;
+        if (b == 0 && gated) {
+            for (int32_t t = 0; t < h->n_tiles; ++t) {
+                if ((rc = chunks_append_tile(h, t, chunk_nnz, sA))) return rc;      // host waits for tile t's CSC
+                const int32_t c0 = h->h_tile_chunk_ptr[(size_t)t], c1 = h->h_tile_chunk_ptr[(size_t)t + 1];
+                if (c1 > c0 && (rc = launch_fast_any(h, Q, PBb, slabs[0], parts[0], c0, c1 - c0))) return rc;
+            }
+            h->chunk_table_nnz = chunk_nnz;
+            // the whole matrix is resident now; its column-range validation is read back with the results
+            h->matrix_pending = false;
+            CK(cudaStreamWaitEvent(sA, h->ev_matrix, 0));
+            h->check_matrix_flag = true;
+        } else if ((rc = launch_fast_any(h, Q, PBb, slabs[b & 1], parts[b & 1]))) return rc;
         CK(cudaEventRecord(EV(b, 3), sA));
         // ---- B: finalize + score (+ optional cube export) ----
         CK(cudaStreamWaitEvent(sB, EV(b, 3), 0));
@@ -1275,7 +1369,8 @@ void lrperm_destroy(lrperm_engine* h) {
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_tile) cudaEventDestroy(ev);
-    if (h->hist_pin) cudaFreeHost(h->hist_pin);
+    h->hist_pin.release();
+    h->table_pin.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1354,36 +1449,45 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     h->N = n_cells; h->G = n_genes; h->nnz = nnz;
 
     if (!on_device && nnz > 0 && is_pinned_host(indptr) && is_pinned_host(indices) && is_pinned_host(data)) {
-        // Pinned host buffers: copies + packing go to the copy stream and the call returns without waiting, so the
-        // caller's next calls (labels, triples, the first label slabs of lrperm_run) overlap the PCIe transfer.
-        // Staging buffers of their own: tmp_* are used by those calls.  Validation is reported by the first call
-        // that needs the matrix (wait_matrix).
+        // Pinned host buffers: nothing waits here.  The row pointers and the FIRST cell tile go to the copy stream now,
+        // the other tiles when the matrix is first consumed (submit_pending_tiles); every tile is packed and its CSC
+        // copy sorted on the copy stream right behind its transfer, so lrperm_run can start the first batch on tile 0
+        // while tiles 1.. are still crossing PCIe.  The buffers must stay valid and unchanged until that call returns
+        // (as with cudaMemcpyAsync).  Column-range validation is reported by the consuming call.
         cudaStream_t sC = h->copy_stream;
         h->staged = false;
+        {   // row pointers are validated here, on the host: device code below indexes with them
+            int64_t prev = 0;
+            bool ok = true;
+            if (indptr_is_64) { const int64_t* ip = static_cast<const int64_t*>(indptr); ok = ip[0] == 0; for (int64_t r = 0; r <= n_cells && ok; ++r) { ok = ip[r] >= prev; prev = ip[r]; } }
+            else { const int32_t* ip = static_cast<const int32_t*>(indptr); ok = ip[0] == 0; for (int64_t r = 0; r <= n_cells && ok; ++r) { ok = ip[r] >= prev; prev = ip[r]; } }
+            if (!ok) { h->have_matrix = false; return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr: invalid input (indptr must start at 0 and be non-decreasing)"); }
+        }
         CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
         CK(h->st_indptr.ensure(isz * (size_t)(n_cells + 1)));
         CK(h->st_indices.ensure(sizeof(int32_t) * (size_t)nnz));
         CK(h->st_data.ensure(sizeof(float) * (size_t)nnz));
         CK(h->csr_pairs.ensure(sizeof(int2) * (size_t)nnz));
         CK(cudaStreamSynchronize(h->stream));          // earlier work on the engine stream may still read the old matrix
+        int rc;
+        const int32_t tile_cells = fast_tile_cells(h);
+        h->csc_ready = false;
+        if ((rc = csc_begin(h, tile_cells))) return rc;
+        h->up_e.assign((size_t)h->n_tiles + 1, 0);
+        for (int32_t t = 0; t <= h->n_tiles; ++t) {
+            const int64_t row = std::min<int64_t>((int64_t)t * tile_cells, n_cells);
+            h->up_e[(size_t)t] = indptr_is_64 ? static_cast<const int64_t*>(indptr)[row] : (int64_t)static_cast<const int32_t*>(indptr)[row];
+        }
+        h->up_indices = indices; h->up_data = data; h->up_next_tile = 0;
         CK(cudaMemcpyAsync(h->st_indptr.p, indptr, isz * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, sC));
         if (indptr_is_64)
             narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, sC>>>(h->st_indptr.as<int64_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag_m.as<int>());
         else
             narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, sC>>>(h->st_indptr.as<int32_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag_m.as<int>());
         CK_LAUNCH();
-        // (the copy engine serves H2D copies of all streams in submission order: the small uploads of the calls that
-        // follow queue behind this transfer, but the host is not blocked and kernels - the label slabs - are not either)
-        CK(cudaMemcpyAsync(h->st_indices.p, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, sC));
-        CK(cudaMemcpyAsync(h->st_data.p, data, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, sC));
-        pack_csr_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, sC>>>(
-            h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), 0, (int32_t)n_cells, (int32_t)n_genes,
-            h->csr_pairs.as<int2>(), h->err_flag_m.as<int>());
-        CK_LAUNCH();
-        CK(cudaEventRecord(h->ev_matrix, sC));
         h->matrix_pending = true;
         h->have_matrix = true;
-        return LRPERM_OK;
+        return submit_tiles(h, 1);                     // the first tile now
     }
 
     CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
@@ -1888,6 +1992,16 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         if (scores & LRPERM_SCORE_CPDB) if ((rc = download(h, counts_cpdb, h->counts_c.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
         if (scores & LRPERM_SCORE_GMEAN) if ((rc = download(h, counts_gmean, h->counts_g.p, sizeof(uint32_t) * (size_t)T, counts_on_device))) return rc;
         CK(cudaStreamSynchronize(h->stream));
+        if (h->check_matrix_flag) {
+            h->check_matrix_flag = false;
+            int flag = 0;
+            CK(cudaMemcpy(&flag, h->err_flag_m.p, sizeof(int), cudaMemcpyDeviceToHost));
+            if (flag) {
+                CK(cudaMemset(h->err_flag_m.p, 0, sizeof(int)));
+                h->have_matrix = false;
+                return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr (deferred check): invalid input (flag=%d: 1=column out of range)", flag);
+            }
+        }
         return collect_pipelined_timings(h, h->n_sched);
     }
     const size_t n_events = (size_t)n_batches * 5 + 2;

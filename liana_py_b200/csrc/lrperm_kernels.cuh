@@ -266,6 +266,13 @@ __global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* 
             if (hist[g]) atomicAdd(&col_count[g], hist[g]);
 }
 
+// small host -> device table copy that does NOT go through the copy engine: `src` is pinned host memory read by the
+// SMs over PCIe.  The copy engine serves H2D copies of all streams in submission order, so a few-KB table queued
+// behind hundreds of MB of matrix tiles would arrive only after them (see chunks_append_tile).
+__global__ void copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // stored-entry counts per (cluster, gene): props = count / n_c  (_common.py:41-42)
 __global__ void stored_counts_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
                                      const int32_t* __restrict__ labels, int32_t N, int32_t G,

@@ -22,6 +22,7 @@ for name, (N, G, L, P) in {"a": (50000, 1877, 20, 300), "b": (9000, 300, 50, 200
         eng.set_tuning(0, chunk, tile_mib)
         for overlap in (1, 0):
             eng.set_option("overlap", overlap)
+            print("run", name, tile_mib, chunk, overlap, flush=True)
             r = eng.run(P, seed=11, order=E.ORDER_FAST, scores=E.SCORE_CPDB | E.SCORE_GMEAN, return_cube=(N <= 50000 and P <= 200))
             key = f"{name}_t{tile_mib}_c{chunk}_o{overlap}"
             out[key + "_cpdb"] = r["cpdb"]; out[key + "_gmean"] = r["gmean"]
