@@ -158,7 +158,9 @@ struct lrperm_engine {
     const void* up_data = nullptr;
     std::vector<int64_t> up_e;            // entry offset at every tile boundary [n_tiles + 1]
     int32_t up_next_tile = 0;
-    bool check_matrix_flag = false;       // the gated first batch consumed a pending upload: read err_flag_m after the run
+    bool check_matrix_flag = false;
+    int32_t slab0_by_tile = 1;            // option: first batch's label slab generated / consumed cell tile by cell tile
+    std::vector<cudaEvent_t> ev_slab_tile;       // the gated first batch consumed a pending upload: read err_flag_m after the run
     DevBuf err_flag_m;                    // validation flags of the pending matrix
     // pageable uploads: two pinned staging pieces filled by a few host threads while the other one is in flight
     ParallelCopier* copier = nullptr;
@@ -756,6 +758,17 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     CK(cudaStreamWaitEvent(sB, ev_fork, 0));     // B starts after everything already queued on A
 
     const size_t idx_elem = a.perm_idx_is_64 ? 8 : 4;
+    // Batch 0 has nothing to hide its label slab behind.  With Philox labels the slab rows of one cell tile can be
+    // generated on their own, so the first batch's slab is made tile by tile and the tile's chunk warps start as soon
+    // as ITS rows exist (the chunk schedule is tile-major); later batches' slabs are hidden behind the previous batch.
+    const int32_t tile_rows = std::max(tile_cells, 1);
+    const int32_t n_tiles_run = (int32_t)std::max<int64_t>(1, (N + tile_rows - 1) / tile_rows);
+    const bool slab0_tiled = a.perm_source == LRPERM_PERMS_PHILOX && n_tiles_run > 1 && h->slab0_by_tile;
+    while (h->ev_slab_tile.size() < (size_t)n_tiles_run) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->ev_slab_tile.push_back(ev);
+    }
     auto enqueue_slab = [&](int64_t b) -> int {
         const int64_t p0 = first[(size_t)b];
         const int32_t PBb = sched[(size_t)b];
@@ -770,10 +783,17 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         if (pb < PBb) CK(cudaMemsetAsync(slab, 0, (size_t)N * PBb, sB));
         if (ps.philox) {
             const int cells_per_block = 128;
-            dim3 grd((unsigned)((N + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
             const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
-            slab_philox_kernel<<<grd, 128, tab_smem, sB>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
-                                                           h->bucket_shift, L, label_scale, (int32_t)N, pb, slab, PBb, cells_per_block);
+            const int32_t nt = (b == 0 && slab0_tiled) ? n_tiles_run : 1;
+            for (int32_t t = 0; t < nt; ++t) {
+                const int64_t c0 = nt == 1 ? 0 : (int64_t)t * tile_rows, c1 = nt == 1 ? N : std::min<int64_t>(N, c0 + tile_rows);
+                dim3 grd((unsigned)((c1 - c0 + cells_per_block - 1) / cells_per_block), (unsigned)((pb + 127) / 128));
+                slab_philox_kernel<<<grd, 128, tab_smem, sB>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
+                                                               h->bucket_shift, L, label_scale, (int32_t)N, pb, slab, PBb, cells_per_block,
+                                                               (int32_t)c0, (int32_t)c1);
+                CK_LAUNCH();
+                if (nt > 1) CK(cudaEventRecord(h->ev_slab_tile[(size_t)t], sB));
+            }
         } else {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.perm_idx) + idx_elem * (size_t)p0 * (size_t)N;
             if (a.perm_idx_on_device) ps.idx = src;
@@ -785,8 +805,8 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
             }
             dim3 grd(grid_for(N, 256, 1024), (unsigned)pb);
             slab_from_index_kernel<<<grd, 256, 0, sB>>>(ps, slab_labels, (int32_t)N, pb, slab, PBb);
+            CK_LAUNCH();
         }
-        CK_LAUNCH();
         CK(cudaEventRecord(EV(b, 1), sB));
         return LRPERM_OK;
     };
@@ -821,20 +841,24 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         const int32_t pb = (int32_t)std::min<int64_t>(PBb, a.n_perms - p0);
         if (b >= 1 && b + 1 < n_batches && (rc = enqueue_slab(b + 1))) return rc;
         // ---- A: main kernel ----
-        CK(cudaStreamWaitEvent(sA, EV(b, 1), 0));
+        const bool by_tile = b == 0 && slab0_tiled && h->n_tiles == n_tiles_run;
+        if (!by_tile) CK(cudaStreamWaitEvent(sA, EV(b, 1), 0));
         if (b >= 2) CK(cudaStreamWaitEvent(sA, EV(b - 2, 5), 0));     // partials[b&1] consumed by finalize(b-2)
         CK(cudaEventRecord(EV(b, 2), sA));
-        if (b == 0 && gated) {
+        if (b == 0 && (gated || by_tile)) {
             for (int32_t t = 0; t < h->n_tiles; ++t) {
-                if ((rc = chunks_append_tile(h, t, chunk_nnz, sA))) return rc;      // host waits for tile t's CSC
+                if (gated && (rc = chunks_append_tile(h, t, chunk_nnz, sA))) return rc;      // host waits for tile t's CSC
+                if (by_tile) CK(cudaStreamWaitEvent(sA, h->ev_slab_tile[(size_t)t], 0));   // the tile's slab rows exist
                 const int32_t c0 = h->h_tile_chunk_ptr[(size_t)t], c1 = h->h_tile_chunk_ptr[(size_t)t + 1];
                 if (c1 > c0 && (rc = launch_fast_any(h, Q, PBb, slabs[0], parts[0], c0, c1 - c0))) return rc;
             }
-            h->chunk_table_nnz = chunk_nnz;
-            // the whole matrix is resident now; its column-range validation is read back with the results
-            h->matrix_pending = false;
-            CK(cudaStreamWaitEvent(sA, h->ev_matrix, 0));
-            h->check_matrix_flag = true;
+            if (gated) {
+                h->chunk_table_nnz = chunk_nnz;
+                // the whole matrix is resident now; its column-range validation is read back with the results
+                h->matrix_pending = false;
+                CK(cudaStreamWaitEvent(sA, h->ev_matrix, 0));
+                h->check_matrix_flag = true;
+            }
         } else if ((rc = launch_fast_any(h, Q, PBb, slabs[b & 1], parts[b & 1]))) return rc;
         CK(cudaEventRecord(EV(b, 3), sA));
         // ---- B: finalize + score (+ optional cube export) ----
@@ -1369,6 +1393,7 @@ void lrperm_destroy(lrperm_engine* h) {
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_tile) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ev_slab_tile) cudaEventDestroy(ev);
     h->hist_pin.release();
     h->table_pin.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1411,6 +1436,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "trimean_perm_batch") {
         if (value < 0 || value > 4096 || (value % 128) != 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: trimean_perm_batch must be a multiple of 128 in [0, 4096]");
         h->tm_perm_batch = (int32_t)value;
+    } else if (key == "slab0_by_tile") {
+        if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: slab0_by_tile must be 0 or 1");
+        h->slab0_by_tile = (int32_t)value;
     } else if (key == "fast_first_batch") {
         if (value < 0 || value > 4096) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_first_batch must be in [0, 4096]");
         h->fast_first_batch = (int32_t)value;

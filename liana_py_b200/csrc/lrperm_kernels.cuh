@@ -503,7 +503,8 @@ __global__ void slab_from_index_kernel(PermSource ps, const uint8_t* __restrict_
 
 __global__ void slab_philox_kernel(PermSource ps, const int32_t* __restrict__ cl_start, const uint8_t* __restrict__ bucket_cluster,
                                    int32_t n_buckets, int32_t bucket_shift, int32_t L, int32_t label_scale, int32_t N,
-                                   int32_t n_perms_batch, uint8_t* __restrict__ slab, int32_t PB, int32_t cells_per_block) {
+                                   int32_t n_perms_batch, uint8_t* __restrict__ slab, int32_t PB, int32_t cells_per_block,
+                                   int32_t cell0 = 0, int32_t cell1 = 0x7fffffff /* rows [cell0, cell1) of the slab only */) {
     // thread = one permutation of the batch (key derived once); loop over a tile of cells.
     // PHILOX permutations are defined on CLUSTER-SORTED positions: pi_p(order[k]) = rho_p(k).  The label of
     // cell i is therefore the cluster whose range [cl_start[c], cl_start[c+1]) holds k = rho_p^-1(i): a
@@ -518,8 +519,8 @@ __global__ void slab_philox_kernel(PermSource ps, const int32_t* __restrict__ cl
     const int p = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = p < n_perms_batch;
     lrperm_bij_t bij = lrperm_bij_init(ps.seed, (uint64_t)(ps.perm_id0 + (active ? p : 0)), (uint32_t)N);
-    const int i0 = blockIdx.x * cells_per_block;
-    const int i1 = min(N, i0 + cells_per_block);
+    const int i0 = cell0 + blockIdx.x * cells_per_block;
+    const int i1 = min(min(N, cell1), i0 + cells_per_block);
     if (!active) return;
     for (int i = i0; i < i1; ++i) {
         const int k = (int)lrperm_bij_inverse(&bij, (uint32_t)i);
