@@ -209,7 +209,7 @@ struct lrperm_engine {
 
     // FAST-mode chunk tables
     int32_t fast_perm_batch = 0, fast_chunk_nnz = 0;   // 0 = auto
-    int32_t chunk_table_nnz = -1, chunk_table_tile = -1;   // parameters the chunk tables were built for
+    int32_t chunk_table_nnz = -1;                       // chunk length the chunk tables were built for
     int32_t fast_tile_bytes = 0;                        // label-slab bytes one cell tile may span (0 = auto)
     int32_t n_sched = 0;                                // batches of the last pipelined run
     int32_t fast_variant = 2;                           // 1 = fast_means_kernel, 2 = fast2_means_kernel
