@@ -188,6 +188,19 @@ int lrperm_observed_trimean(lrperm_engine *h, double recip, double *trimean, int
  * (chunk, permutation group) warps of the selection pass that had to re-walk their chunk, out[5] all of them. */
 int lrperm_trimean_timings(lrperm_engine *h, float *out6);
 
+/*
+ * Consensus of method scores (liana/method/_pipe_utils/_aggregate.py:70-181), the step that turns the permutation
+ * p-values and the other scores into `specificity_rank` / `magnitude_rank`:
+ *   lrperm_rank_average  ranks[i] = scipy.stats.rankdata(negate ? -values : values, method='average')[i]   (:91-98);
+ *                        float64, ties share the average rank, -0.0 ties with +0.0; values must not contain NaN
+ *   lrperm_rra           RobustRankAggregate of Kolde et al. 2012 (:110-181): rmat[row][col] are ranks (row-major,
+ *                        n_cols <= 16), col_max[col] their column maxima; rho[row] = min(1, n_cols * min_k
+ *                        I_{r_(k)}(k, n_cols - k + 1)) with r = sorted(rmat[row] / col_max)
+ * Host or device pointers (`on_device`), independent of the matrix / label state of the engine.
+ */
+int lrperm_rank_average(lrperm_engine *h, int64_t n, const double *values, int negate, double *ranks, int on_device);
+int lrperm_rra(lrperm_engine *h, int64_t n_rows, int32_t n_cols, const double *rmat, const double *col_max, double *rho, int on_device);
+
 /* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32), i.e. the array
  * that reproduces a PHILOX run when passed back as LRPERM_PERMS_INDEX.  The device bijection rho_p (keyed by
  * seed and global permutation id, include/lrperm_philox.h) acts on CLUSTER-SORTED positions: position

@@ -26,6 +26,7 @@ ABI_SYMBOLS = (
     "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
+    "lrperm_rank_average", "lrperm_rra",
 )
 
 _lib = None
@@ -71,6 +72,8 @@ def load_library():
     lib.lrperm_observed_trimean.argtypes = [vp, C.c_double, vp, C.c_int]
     lib.lrperm_trimean_timings.argtypes = [vp, vp]
     lib.lrperm_staged_max.argtypes = [vp, vp, vp]
+    lib.lrperm_rank_average.argtypes = [vp, i64, vp, C.c_int, vp, C.c_int]
+    lib.lrperm_rra.argtypes = [vp, i64, i32, vp, vp, vp, C.c_int]
     _lib = lib
     return lib
 
@@ -344,6 +347,24 @@ class Engine:
         self._check(self._lib.lrperm_trimean_timings(self._h, C.cast(buf, C.c_void_p)))
         return {"count_ms": buf[0], "prefix_ms": buf[1], "select_ms": buf[2], "finalize_ms": buf[3],
                 "walked_warps": int(buf[4]), "select_warps": int(buf[5])}
+
+    # -- consensus ---------------------------------------------------------------------------
+    def rank_average(self, values, negate: bool = False) -> np.ndarray:
+        """scipy.stats.rankdata(-values if negate else values, method='average') as float64 (no NaN in `values`)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = np.empty(v.shape[0], dtype=np.float64)
+        self._check(self._lib.lrperm_rank_average(self._h, int(v.shape[0]), C.c_void_p(v.ctypes.data), int(bool(negate)),
+                                                  C.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def rra(self, rmat) -> np.ndarray:
+        """RobustRankAggregate rho per row of a rank matrix [n_rows, n_cols] (`_aggregate.py:110-181`)."""
+        r = np.ascontiguousarray(rmat, dtype=np.float64)
+        col_max = np.ascontiguousarray(r.max(axis=0)) if r.shape[0] else np.ones(r.shape[1])
+        out = np.empty(r.shape[0], dtype=np.float64)
+        self._check(self._lib.lrperm_rra(self._h, int(r.shape[0]), int(r.shape[1]), C.c_void_p(r.ctypes.data),
+                                         C.c_void_p(col_max.ctypes.data), C.c_void_p(out.ctypes.data), 0))
+        return out
 
     def philox_perms(self, n_cells: int, n_perms: int, seed: int = 1337, perm_offset: int = 0) -> np.ndarray:
         out = np.empty((int(n_perms), int(n_cells)), dtype=np.int32)

@@ -2177,6 +2177,75 @@ int lrperm_observed_trimean(lrperm_engine* h, double recip, double* trimean, int
     return collect_trimean_timings(h);
 }
 
+int lrperm_rank_average(lrperm_engine* h, int64_t n, const double* values, int negate, double* ranks, int on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (n < 0 || n >= 0x7fffffffLL || (n > 0 && (!values || !ranks))) return h->fail(LRPERM_ERR_INVALID, "lrperm_rank_average: bad arguments");
+    if (n == 0) return LRPERM_OK;
+    int rc;
+    const size_t N = (size_t)n;
+    // tmp_a: values (host input) | ranks ; tmp_b: keys, tmp_c: sorted keys ; tmp_d: idx, sorted idx, flags, gid, starts
+    const double* d_vals = values;
+    if (!on_device) { if ((rc = upload(h, h->tmp_a, values, sizeof(double) * N, 0))) return rc; d_vals = h->tmp_a.as<double>(); }
+    CK(h->tmp_b.ensure(sizeof(unsigned long long) * N));
+    CK(h->tmp_c.ensure(sizeof(unsigned long long) * N));
+    CK(h->tmp_d.ensure(sizeof(int32_t) * N * 5));
+    CK(h->stage_out.ensure(sizeof(double) * N));
+    uint32_t* idx = h->tmp_d.as<uint32_t>();
+    uint32_t* idx_sorted = idx + N;
+    int32_t* flag = reinterpret_cast<int32_t*>(idx + 2 * N);
+    int32_t* gid = flag + N;
+    int32_t* starts = gid + N;
+    const int grid = grid_for(n, 256, 1 << 30);
+    rank_keys_kernel<<<grid, 256, 0, h->stream>>>(d_vals, n, negate, h->tmp_b.as<unsigned long long>(), idx);
+    CK_LAUNCH();
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->tmp_b.as<unsigned long long>(), h->tmp_c.as<unsigned long long>(), idx, idx_sorted, (int)n, 0, 64, h->stream));
+    size_t scan_bytes = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, flag, gid, (int)n, h->stream));
+    CK(h->sort_tmp.ensure(std::max(tmp_bytes, scan_bytes)));
+    tmp_bytes = h->sort_tmp.cap;
+    CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->tmp_b.as<unsigned long long>(), h->tmp_c.as<unsigned long long>(), idx, idx_sorted, (int)n, 0, 64, h->stream));
+    rank_flags_kernel<<<grid, 256, 0, h->stream>>>(h->tmp_c.as<unsigned long long>(), n, flag);
+    CK_LAUNCH();
+    scan_bytes = h->sort_tmp.cap;
+    CK(cub::DeviceScan::InclusiveSum(h->sort_tmp.p, scan_bytes, flag, gid, (int)n, h->stream));
+    rank_starts_kernel<<<grid, 256, 0, h->stream>>>(flag, gid, n, starts);
+    CK_LAUNCH();
+    int32_t n_groups = 0;
+    CK(cudaMemcpyAsync(&n_groups, gid + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double* d_ranks = on_device ? ranks : h->stage_out.as<double>();
+    rank_scatter_kernel<<<grid, 256, 0, h->stream>>>(gid, starts, idx_sorted, n, n_groups, d_ranks);
+    CK_LAUNCH();
+    if (!on_device) CK(cudaMemcpyAsync(ranks, d_ranks, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
+int lrperm_rra(lrperm_engine* h, int64_t n_rows, int32_t n_cols, const double* rmat, const double* col_max, double* rho, int on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (n_rows < 0 || n_cols <= 0 || n_cols > kRraMaxCols || (n_rows > 0 && (!rmat || !col_max || !rho)))
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_rra: bad arguments (at most %d score columns)", kRraMaxCols);
+    if (n_rows == 0) return LRPERM_OK;
+    int rc;
+    const size_t cells = (size_t)n_rows * (size_t)n_cols;
+    const double *d_r = rmat, *d_m = col_max;
+    if (!on_device) {
+        if ((rc = upload(h, h->tmp_a, rmat, sizeof(double) * cells, 0))) return rc;
+        if ((rc = upload(h, h->small_a, col_max, sizeof(double) * (size_t)n_cols, 0))) return rc;
+        d_r = h->tmp_a.as<double>(); d_m = h->small_a.as<double>();
+        CK(h->stage_out.ensure(sizeof(double) * (size_t)n_rows));
+    }
+    double* d_out = on_device ? rho : h->stage_out.as<double>();
+    rra_kernel<<<grid_for(n_rows, 128, 1 << 30), 128, 0, h->stream>>>(d_r, d_m, n_rows, n_cols, d_out);
+    CK_LAUNCH();
+    if (!on_device) CK(cudaMemcpyAsync(rho, d_out, sizeof(double) * (size_t)n_rows, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
 int lrperm_trimean_timings(lrperm_engine* h, float* out6) {
     if (!h || !out6) return LRPERM_ERR_INVALID;
     for (int i = 0; i < 4; ++i) out6[i] = h->tm_ms[i];

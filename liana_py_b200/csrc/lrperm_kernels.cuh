@@ -906,4 +906,81 @@ __global__ void build_rows_kernel(const int32_t* __restrict__ lig, const int32_t
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Consensus of method scores (liana/method/_pipe_utils/_aggregate.py:70-181): average-method ranks of a score
+// column (scipy.stats.rankdata(method='average'), :91-98) and the RobustRankAggregate rho of every row (:110-181).
+// ------------------------------------------------------------------------------------------
+// order-preserving 64-bit key of (sign * v); -0.0 and +0.0 share a key (they tie in rankdata)
+__global__ void rank_keys_kernel(const double* __restrict__ v, int64_t n, int negate, unsigned long long* __restrict__ keys,
+                                 uint32_t* __restrict__ idx) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = v[i];
+    if (negate) x = -x;
+    unsigned long long b = (x == 0.0) ? 0ull : (unsigned long long)__double_as_longlong(x);
+    keys[i] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    idx[i] = (uint32_t)i;
+}
+
+// flag[i] = 1 where a new tie group starts in the sorted key array
+__global__ void rank_flags_kernel(const unsigned long long* __restrict__ keys, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// group_start[g] = sorted position of the first member of tie group g (gid = inclusive sum of the flags, 1-based)
+__global__ void rank_starts_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ gid, int64_t n,
+                                   int32_t* __restrict__ group_start) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) group_start[gid[i] - 1] = (int32_t)i;
+}
+
+// average rank of the tie group [s, e] (0-based sorted positions) = (s + e) / 2 + 1, written at the original index
+__global__ void rank_scatter_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ group_start, const uint32_t* __restrict__ idx,
+                                    int64_t n, int32_t n_groups, double* __restrict__ ranks) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = gid[i] - 1;
+    const int64_t s = group_start[g];
+    const int64_t e = (g + 1 < n_groups ? (int64_t)group_start[g + 1] : n) - 1;
+    ranks[idx[i]] = (double)(s + e + 2) * 0.5;
+}
+
+// rho of one row: ranks / column maximum, sorted ascending, p_k = I_{r_(k)}(k, n - k + 1) (the regularized incomplete
+// beta function with integer shape parameters = a binomial tail: sum_{j >= k} C(n, j) x^j (1 - x)^(n - j)), row
+// minimum, Bonferroni over the n methods, clipped to [0, 1]
+constexpr int kRraMaxCols = 16;
+__global__ void rra_kernel(const double* __restrict__ rmat /*[n_rows][n_cols]*/, const double* __restrict__ col_max, int64_t n_rows,
+                           int32_t n, double* __restrict__ rho) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double r[kRraMaxCols];
+    bool has_nan = false;
+    for (int c = 0; c < n; ++c) { r[c] = rmat[row * n + c] / col_max[c]; has_nan |= isnan(r[c]); }
+    if (has_nan) { rho[row] = r[0] + r[n - 1] + nan(""); return; }      // beta.cdf(nan) -> np.min -> nan
+    for (int a = 1; a < n; ++a) {                       // insertion sort, n <= 16
+        const double x = r[a];
+        int b = a - 1;
+        while (b >= 0 && r[b] > x) { r[b + 1] = r[b]; --b; }
+        r[b + 1] = x;
+    }
+    double best = 1.0;
+    for (int k = 1; k <= n; ++k) {
+        const double x = r[k - 1], y = 1.0 - x;
+        // binomial tail, terms built incrementally from j = k: C(n,k) x^k y^(n-k), then * (n-j)/(j+1) * x/y
+        double p;
+        if (x <= 0.0) p = 0.0;
+        else if (x >= 1.0) p = 1.0;
+        else {
+            double coef = 1.0;
+            for (int j = 1; j <= k; ++j) coef = coef * (double)(n - k + j) / (double)j;       // C(n, k)
+            double term = coef * pow(x, (double)k) * pow(y, (double)(n - k));
+            p = term;
+            for (int j = k; j < n; ++j) { term = term * (double)(n - j) / (double)(j + 1) * (x / y); p += term; }
+        }
+        best = fmin(best, p);
+    }
+    rho[row] = fmin(fmax(best * (double)n, 0.0), 1.0);
+}
+
 }  // namespace lrperm

@@ -17,7 +17,17 @@ import pandas as pd
 from scipy.stats import beta, rankdata
 
 
-def rank_aggregate_scores(lr_res: pd.DataFrame, specs: dict, aggregate_method: str = "rra") -> np.ndarray:
+def _rank_average(values: np.ndarray, negate: bool, engine) -> np.ndarray:
+    """rankdata(method='average') of +-values: on the device (radix sort + tie groups, `lrperm_rank_average`) when an
+    engine is given - the product path always gives one - else SciPy (CPU tests of the host logic / checker)."""
+    if engine is None:
+        return rankdata(values * -1 if negate else values, method="average")
+    if np.isnan(values).any():                    # nan_policy='propagate': every rank is NaN
+        return np.full(values.shape[0], np.nan)
+    return engine.rank_average(values, negate)
+
+
+def rank_aggregate_scores(lr_res: pd.DataFrame, specs: dict, aggregate_method: str = "rra", engine=None) -> np.ndarray:
     """`_rank_aggregate` (`_aggregate.py:70-107`): specs = {method_name: (score_name, ascending)}."""
     assert aggregate_method in ["rra", "mean"]
     ranks = {}
@@ -27,12 +37,12 @@ def rank_aggregate_scores(lr_res: pd.DataFrame, specs: dict, aggregate_method: s
     for spec in specs:
         score_name, ascending = specs[spec]
         cur = ranks.get(score_name, cols[score_name])
-        ranks[score_name] = rankdata(cur if ascending else cur * -1, method="average")
+        ranks[score_name] = _rank_average(cur, not ascending, engine)
     # the reference iterates a *set* of names for the column order; RRA sorts every row and the mean
     # is symmetric, so the order of the columns does not change the result
     rmat = np.stack([ranks[name] for name in ranks], axis=1)
     if aggregate_method == "rra":
-        return robust_rank_aggregate(rmat)
+        return robust_rank_aggregate(rmat) if engine is None else engine.rra(rmat)
     return np.mean(rmat, axis=1) / rmat.shape[0]
 
 
@@ -47,16 +57,16 @@ def robust_rank_aggregate(rmat: np.ndarray) -> np.ndarray:
     return np.clip(np.min(p, axis=1) * n, a_min=0, a_max=1)
 
 
-def aggregate(lr_res: pd.DataFrame, consensus, aggregate_method: str = "rra", consensus_opts=None) -> pd.DataFrame:
+def aggregate(lr_res: pd.DataFrame, consensus, aggregate_method: str = "rra", consensus_opts=None, engine=None) -> pd.DataFrame:
     """`_aggregate` (`_aggregate.py:7-67`) on the already-joined frame (key columns + every method's
     score columns).  Adds `consensus.specificity` / `consensus.magnitude` and sorts by the last one."""
     if consensus_opts is None:
         consensus_opts = ["Magnitude", "Specificity"]
     order_col = ""
     if "Specificity" in consensus_opts:
-        lr_res[consensus.specificity] = rank_aggregate_scores(lr_res, consensus.specificity_specs, aggregate_method)
+        lr_res[consensus.specificity] = rank_aggregate_scores(lr_res, consensus.specificity_specs, aggregate_method, engine)
         order_col = consensus.specificity
     if "Magnitude" in consensus_opts:
-        lr_res[consensus.magnitude] = rank_aggregate_scores(lr_res, consensus.magnitude_specs, aggregate_method)
+        lr_res[consensus.magnitude] = rank_aggregate_scores(lr_res, consensus.magnitude_specs, aggregate_method, engine)
         order_col = consensus.magnitude
     return lr_res.sort_values(order_col)

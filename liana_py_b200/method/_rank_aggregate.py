@@ -77,7 +77,8 @@ class AggregateClass(MethodMeta):
             for col in f.columns:
                 if col not in lr_res.columns:                   # duplicated score names keep the first (`:47-49`)
                     lr_res[col] = f[col].values
-        lr_res = aggregate(lr_res, consensus=self, aggregate_method=aggregate_method, consensus_opts=consensus_opts)
+        lr_res = aggregate(lr_res, consensus=self, aggregate_method=aggregate_method, consensus_opts=consensus_opts,
+                           engine=state.engine)
         orderby = self.magnitude if self.magnitude in lr_res.columns else self.specificity
         if orderby in lr_res.columns:
             lr_res = lr_res.sort_values(by=orderby, ascending=True)   # `_liana_pipe.py:246-250`
