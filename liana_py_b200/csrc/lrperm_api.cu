@@ -159,6 +159,7 @@ struct lrperm_engine {
     std::vector<int64_t> up_e;            // entry offset at every tile boundary [n_tiles + 1]
     int32_t up_next_tile = 0;
     bool check_matrix_flag = false;
+    int32_t score_gpb = 0;                // option: 32-permutation groups per block of the score kernels (0 = auto: L2 fit)
     int32_t slab0_by_tile = 1;            // option: first batch's label slab generated / consumed cell tile by cell tile
     std::vector<cudaEvent_t> ev_slab_tile;       // the gated first batch consumed a pending upload: read err_flag_m after the run
     DevBuf err_flag_m;                    // validation flags of the pending matrix
@@ -658,15 +659,25 @@ int pick_q(const lrperm_engine* h) {
     return 0;
 }
 
+int32_t score_groups_per_block(const lrperm_engine* h, int32_t n_groups, size_t elem) {
+    if (h->score_gpb > 0) return std::min(h->score_gpb, std::max(n_groups, 1));
+    const size_t per_group = (size_t)h->G * (size_t)h->L * 32 * elem;
+    const size_t fit = (48u << 20) / std::max<size_t>(per_group, 1);
+    return (int32_t)std::max<size_t>(1, std::min<size_t>(fit, (size_t)std::max(n_groups, 1)));
+}
+
 template <bool LIT>
 int launch_score_t(lrperm_engine* h, int scores, const float* cube, int32_t PP, int32_t pb) {
     const int64_t T = h->T;
     if (T == 0) return LRPERM_OK;
-    const unsigned grid = (unsigned)((T + kScoreTile - 1) / kScoreTile);
     const bool c = scores & LRPERM_SCORE_CPDB, g = scores & LRPERM_SCORE_GMEAN;
+    // permutation groups per block: the gathered cube slice (G x L rows x 128 B per group) should fit L2 (~48 MiB)
+    const int32_t n_groups = (pb + 31) / 32;
+    const int32_t gpb = score_groups_per_block(h, n_groups, sizeof(float));
+    dim3 grid((unsigned)((T + kScoreTile - 1) / kScoreTile), (unsigned)((n_groups + gpb - 1) / gpb));
 #define LAUNCH_SCORE(C, Gm)                                                                                   \
     score_count_kernel<C, Gm, LIT><<<grid, kScoreThreads, 0, h->stream>>>(                                    \
-        cube, PP, pb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_c.as<float>(), h->thr_g.as<float>(), T, \
+        cube, PP, pb, gpb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_c.as<float>(), h->thr_g.as<float>(), T, \
         h->counts_c.as<uint32_t>(), h->counts_g.as<uint32_t>())
     if (c && g) LAUNCH_SCORE(true, true);
     else if (c) LAUNCH_SCORE(true, false);
@@ -1275,8 +1286,11 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
             const double* cube = h->tm_cube.as<double>() + plane_elems * bi;
             CK(cudaEventRecord(ev[4], h->stream));
             if (a.score && T > 0) {
-                score_count_cellchat_kernel<<<(unsigned)((T + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, h->stream>>>(
-                    cube, PB, pb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_d.as<double>(), a.kh, T, h->counts_t.as<uint32_t>());
+                const int32_t n_groups = (pb + 31) / 32;
+                const int32_t gpb = score_groups_per_block(h, n_groups, sizeof(double));
+                dim3 sgrid((unsigned)((T + kScoreTile - 1) / kScoreTile), (unsigned)((n_groups + gpb - 1) / gpb));
+                score_count_cellchat_kernel<<<sgrid, kScoreThreads, 0, h->stream>>>(
+                    cube, PB, pb, gpb, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->thr_d.as<double>(), a.kh, T, h->counts_t.as<uint32_t>());
                 CK_LAUNCH();
             }
             CK(cudaEventRecord(ev[5], h->stream));
@@ -1436,6 +1450,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "trimean_perm_batch") {
         if (value < 0 || value > 4096 || (value % 128) != 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: trimean_perm_batch must be a multiple of 128 in [0, 4096]");
         h->tm_perm_batch = (int32_t)value;
+    } else if (key == "score_groups_per_block") {
+        if (value < 0 || value > 1024) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: score_groups_per_block must be in [0, 1024]");
+        h->score_gpb = (int32_t)value;
     } else if (key == "slab0_by_tile") {
         if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: slab0_by_tile must be 0 or 1");
         h->slab0_by_tile = (int32_t)value;

@@ -811,9 +811,12 @@ __global__ void fast_finalize_kernel(const float* __restrict__ partials, const i
 //   gmean       : a*b >= g*g          in float64 (exact products)           _geometric_mean.py:23
 //                 or exp((log a + log b)/2) >= g (LITERAL)
 // ------------------------------------------------------------------------------------------
+// blockIdx.y = block of `groups_per_block` 32-permutation groups: the CTAs of one permutation block are scheduled
+// together and touch only that slice of every cube row, so the gathered slice (G x L x groups_per_block x 128 B) stays
+// L2 resident instead of streaming the whole cube batch from DRAM once per 256-triple tile.
 template <bool CPDB, bool GMEAN, bool LITERAL>
 __global__ void __launch_bounds__(kScoreThreads)
-score_count_kernel(const float* __restrict__ cube, int32_t PP, int32_t n_perms_batch,
+score_count_kernel(const float* __restrict__ cube, int32_t PP, int32_t n_perms_batch, int32_t groups_per_block,
                    const int32_t* __restrict__ rowA, const int32_t* __restrict__ rowB,
                    const float* __restrict__ thr_c, const float* __restrict__ thr_g, int64_t T,
                    uint32_t* __restrict__ counts_c, uint32_t* __restrict__ counts_g) {
@@ -834,10 +837,16 @@ score_count_kernel(const float* __restrict__ cube, int32_t PP, int32_t n_perms_b
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = kScoreThreads / 32;
     const int n_groups = (n_perms_batch + 31) >> 5;
-    for (int pg = warp; pg < n_groups; pg += NW) {
+    const int g_first = blockIdx.y * groups_per_block;
+    const int n_g = min(groups_per_block, n_groups - g_first);
+    const int n_tb = (nt + 31) >> 5;
+    // work items: (permutation group of this block, 32-triple sub-tile)
+    for (int item = warp; item < n_g * n_tb; item += NW) {
+        const int pg = g_first + item % n_g;
+        const int tb = (item / n_g) * 32;
         const int p = pg * 32 + lane;
         const bool valid = p < n_perms_batch;
-        for (int tb = 0; tb < nt; tb += 32) {
+        {
             uint32_t my_c = 0, my_g = 0;
             const int tn = min(32, nt - tb);
             for (int u = 0; u < tn; ++u) {
@@ -870,9 +879,10 @@ score_count_kernel(const float* __restrict__ cube, int32_t PP, int32_t n_perms_b
         }
     }
     __syncthreads();
+    // integer adds: several permutation blocks (and batches) accumulate into the same counters, in any order
     for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-        if (CPDB) counts_c[t0 + i] += s_cc[i];
-        if (GMEAN) counts_g[t0 + i] += s_cg[i];
+        if (CPDB && s_cc[i]) atomicAdd(&counts_c[t0 + i], s_cc[i]);
+        if (GMEAN && s_cg[i]) atomicAdd(&counts_g[t0 + i], s_cg[i]);
     }
 }
 

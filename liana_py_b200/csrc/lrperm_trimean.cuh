@@ -348,7 +348,7 @@ __global__ void tm_finalize_kernel(const float* __restrict__ planes, int64_t pla
 // CellChat null score + compare + count: prob = a*b / (kh + a*b) >= observed (float64 throughout,
 // liana/method/sc/_cellchat.py:7-10, _get_mean_perms.py:133-137).  Same decomposition as score_count_kernel.
 __global__ void __launch_bounds__(kScoreThreads)
-score_count_cellchat_kernel(const double* __restrict__ cube, int32_t PP, int32_t n_perms_batch,
+score_count_cellchat_kernel(const double* __restrict__ cube, int32_t PP, int32_t n_perms_batch, int32_t groups_per_block,
                             const int32_t* __restrict__ rowA, const int32_t* __restrict__ rowB,
                             const double* __restrict__ thr, double kh, int64_t T, uint32_t* __restrict__ counts) {
     __shared__ int32_t s_ra[kScoreTile], s_rb[kScoreTile];
@@ -367,10 +367,15 @@ score_count_cellchat_kernel(const double* __restrict__ cube, int32_t PP, int32_t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = kScoreThreads / 32;
     const int n_groups = (n_perms_batch + 31) >> 5;
-    for (int pg = warp; pg < n_groups; pg += NW) {
+    const int g_first = blockIdx.y * groups_per_block;           // permutation block: see score_count_kernel
+    const int n_g = min(groups_per_block, n_groups - g_first);
+    const int n_tb = (nt + 31) >> 5;
+    for (int item = warp; item < n_g * n_tb; item += NW) {
+        const int pg = g_first + item % n_g;
+        const int tb = (item / n_g) * 32;
         const int p = pg * 32 + lane;
         const bool valid = p < n_perms_batch;
-        for (int tb = 0; tb < nt; tb += 32) {
+        {
             uint32_t mine = 0;
             const int tn = min(32, nt - tb);
             for (int u = 0; u < tn; ++u) {
@@ -386,7 +391,7 @@ score_count_cellchat_kernel(const double* __restrict__ cube, int32_t PP, int32_t
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) counts[t0 + i] += s_c[i];
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) if (s_c[i]) atomicAdd(&counts[t0 + i], s_c[i]);
 }
 
 // cube[g][c][PP] (perm-minor, float64) -> out[p][c][g] (the reference's layout)
