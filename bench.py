@@ -204,9 +204,22 @@ def run_gpu(args):
     h_counts = torch.zeros(max(T, 1), dtype=torch.int32).pin_memory()
     h2d = sum(int(t.numel() * t.element_size()) for t in list(host.values()) + h_idx + [h_obs])
     d2h = int(h_counts.numel() * 4)
+    if world > 1:       # whole job: every rank uploads the small tables, the matrix arrays cross PCIe once in total
+        mat = sum(int(host[k].numel() * host[k].element_size()) for k in ("indices", "data"))
+        h2d = world * (h2d - mat) + mat
+        d2h *= world
+
+    from liana_py_b200.method._dist import DistContext
+    dctx = DistContext.from_torch() if world > 1 else None
 
     def step_e2e():
-        eng.set_matrix_csr(host["indptr"], host["indices"], host["data"], wl["N"], wl["G"])
+        if world > 1:
+            # every rank holds the same host matrix: each uploads 1/world of it from pinned memory and the slices are
+            # all-gathered over NVLink instead of 8 full transfers over 8 PCIe links fed by the same host memory
+            d_ip, d_ix, d_dt = dctx.upload_csr_sharded(host["indptr"], host["indices"], host["data"])
+            eng.set_matrix_csr(d_ip, d_ix, d_dt, wl["N"], wl["G"])
+        else:
+            eng.set_matrix_csr(host["indptr"], host["indices"], host["data"], wl["N"], wl["G"])
         eng.set_labels(host["labels"], wl["L"])
         eng.set_triples(h_idx[0], h_idx[1], h_idx[2], h_idx[3], h_obs, None)
         out = eng.run(hi - lo, seed=1337, perm_offset=lo, order=order, scores=E.SCORE_CPDB, counts_out=(counts, None))

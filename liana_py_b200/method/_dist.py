@@ -60,6 +60,45 @@ class DistContext:
             load[r] += sizes[i]
         return [int(i) for i in np.flatnonzero(owner == self.rank)]
 
+    def upload_csr_sharded(self, indptr, indices, data):
+        """Replicated host CSR -> replicated DEVICE CSR without every rank pulling the whole matrix over its own PCIe
+        link: rank r uploads the r-th 1/world slice of the flat `indices` / `data` arrays (pinned host tensors or
+        NumPy arrays) and the slices are all-gathered over NVLink (NCCL).  Returns torch CUDA tensors
+        (indptr, indices, data) to pass to `Engine.set_matrix_csr`.  With one rank it is a plain upload."""
+        import torch
+        import torch.distributed as dist
+
+        def as_tensor(a):
+            return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+
+        indptr, indices, data = as_tensor(indptr), as_tensor(indices), as_tensor(data)
+        dev = self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        d_indptr = indptr.to(dev, non_blocking=True)
+        if self.world_size == 1:
+            out = (d_indptr, indices.to(dev, non_blocking=True), data.to(dev, non_blocking=True))
+            if dev.type == "cuda":
+                torch.cuda.current_stream(dev).synchronize()
+            return out
+        nnz = int(indices.numel())
+        chunk = (nnz + self.world_size - 1) // self.world_size
+        lo, hi = min(nnz, self.rank * chunk), min(nnz, (self.rank + 1) * chunk)
+        outs = []
+        for arr in (indices, data):
+            local = torch.zeros(chunk, dtype=arr.dtype, device=dev)
+            local[:hi - lo].copy_(arr[lo:hi], non_blocking=True)
+            full = torch.empty(chunk * self.world_size, dtype=arr.dtype, device=dev)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(full, local, group=self.group)
+            else:
+                parts = [torch.empty_like(local) for _ in range(self.world_size)]
+                dist.all_gather(parts, local, group=self.group)
+                full = torch.cat(parts)
+            outs.append(full[:nnz])
+        if dev.type == "cuda":
+            # the engine works on its own non-blocking stream: hand the tensors over complete
+            torch.cuda.current_stream(dev).synchronize()
+        return d_indptr, outs[0], outs[1]
+
     def all_gather_objects(self, obj):
         if self.world_size == 1:
             return [obj]

@@ -47,6 +47,11 @@ def _worker(rank, world, port, out_dir):
         idx_c = (gc["ligand_idx"], gc["receptor_idx"], gc["source_idx"], gc["target_idx"])
         local_c = numpy_port.counts_cellchat(tm_cube, *idx_c, gc["lr_probs"]).astype(np.uint32)
         assert np.array_equal(ctx.all_reduce_sum_u32(local_c) / Pc, gc["pvals"])
+        # sharded upload: every rank contributes 1/world of the flat CSR arrays, the all-gather rebuilds them everywhere
+        cpu_ctx = DistContext(ctx.rank, ctx.world_size, torch.device("cpu"), None)
+        X = g["X"]
+        ip, ix, dt = cpu_ctx.upload_csr_sharded(X.indptr.astype(np.int32), X.indices.astype(np.int32), X.data.astype(np.float32))
+        assert np.array_equal(ip.numpy(), X.indptr) and np.array_equal(ix.numpy(), X.indices) and np.array_equal(dt.numpy(), X.data)
         # by_sample: whole samples per rank, gathered as objects
         sizes = [50, 400, 30, 220, 90, 10, 300]
         mine = ctx.sample_shard(sizes)
