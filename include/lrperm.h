@@ -223,6 +223,7 @@ int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_ch
 /* Named engine options (experiments / A-B measurements; defaults are the production settings):
  *   "fast_variant"  2 (default) = fast2_means_kernel, 1 = fast_means_kernel (round-1 first version)
  *   "fast_q"        permutations per lane in FAST mode: 0 = auto, 2, 4 or 8
+ *   "eager_csc"           1 (default) = lrperm_set_matrix_csr / lrperm_commit_matrix queue the CSC copy of FAST mode at once
  *   "score_groups_per_block"  32-permutation groups per block of the score kernels (0 = auto: the gathered cube slice fits L2)
  *   "slab0_by_tile"       1 (default) = the first batch's label slab is generated and consumed cell tile by cell tile
  *   "fast_first_batch"    permutations of a short first batch of the pipelined FAST path (0 = none, default)

@@ -159,6 +159,7 @@ struct lrperm_engine {
     std::vector<int64_t> up_e;            // entry offset at every tile boundary [n_tiles + 1]
     int32_t up_next_tile = 0;
     bool check_matrix_flag = false;
+    int32_t eager_csc = 1;                // option: queue the CSC build of FAST mode as soon as the matrix is set
     int32_t score_gpb = 0;                // option: 32-permutation groups per block of the score kernels (0 = auto: L2 fit)
     int32_t slab0_by_tile = 1;            // option: first batch's label slab generated / consumed cell tile by cell tile
     std::vector<cudaEvent_t> ev_slab_tile;       // the gated first batch consumed a pending upload: read err_flag_m after the run
@@ -185,6 +186,8 @@ struct lrperm_engine {
     PinnedBuf hist_pin;                   // pinned host [n_tiles][G] column counts per tile
     PinnedBuf table_pin;                  // pinned host mirror of the chunk table + tile_slot_ptr rows (read by copy_words_kernel)
     DevBuf csc_keys, csc_keys2, csc_payload, tile_hist, tile_slot_ptr;
+    DevBuf csc_tmp;                       // CUB temp storage of the CSC sorts: they may run on the copy stream while the
+                                          // engine stream sorts something else (labels) with sort_tmp
     std::vector<cudaEvent_t> ev_tile;     // tile t: CSC sorted and histogram on the host
     std::vector<FastChunk> h_chunks;      // tile-major; inside a tile longest first
     std::vector<int32_t> h_tile_chunk_ptr, h_tile_slot_ptr, h_tile_entry0;
@@ -382,7 +385,7 @@ int csc_begin(lrperm_engine* h, int32_t tile_cells) {
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->csc_keys.as<uint32_t>(), h->csc_keys2.as<uint32_t>(),
                                        h->csc_payload.as<unsigned long long>(), reinterpret_cast<unsigned long long*>(h->csc_pairs.p),
                                        (int)std::min<int64_t>(h->nnz, 0x7fffffff), 0, end_bit, h->stream));
-    CK(h->sort_tmp.ensure(tmp_bytes));
+    CK(h->csc_tmp.ensure(tmp_bytes));
     h->csc_ready = true;
     return LRPERM_OK;
 }
@@ -406,8 +409,8 @@ int csc_enqueue_tile(lrperm_engine* h, int32_t t, int64_t e0, int64_t e1, cudaSt
         CK_LAUNCH();
         int end_bit = 1;
         while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
-        size_t tmp_bytes = h->sort_tmp.cap;
-        CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->csc_keys.as<uint32_t>() + e0, h->csc_keys2.as<uint32_t>() + e0,
+        size_t tmp_bytes = h->csc_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(h->csc_tmp.p, tmp_bytes, h->csc_keys.as<uint32_t>() + e0, h->csc_keys2.as<uint32_t>() + e0,
                                            h->csc_payload.as<unsigned long long>() + e0,
                                            reinterpret_cast<unsigned long long*>(h->csc_pairs.p) + e0, (int)(e1 - e0), 0, end_bit, st));
         h->launches += 4;
@@ -527,22 +530,28 @@ int chunks_append_tile(lrperm_engine* h, int32_t t, int32_t chunk_nnz, cudaStrea
 }
 
 // everything at once (matrix resident): CSC of all tiles, then all chunk tables
+// queue the CSC build of every tile of the resident matrix on the engine stream (no wait for the result)
+int csc_enqueue_all(lrperm_engine* h, int32_t tile_cells) {
+    if (h->csc_ready && h->csc_tile_cells == tile_cells) return LRPERM_OK;
+    StageTimer timer("build_csc");
+    int rc;
+    if ((rc = csc_begin(h, tile_cells))) return rc;
+    // entry ranges of the tiles: indptr at the tile boundaries
+    std::vector<int32_t> e((size_t)h->n_tiles + 1, 0);
+    for (int32_t t = 0; t <= h->n_tiles; ++t) {
+        const int64_t row = std::min<int64_t>((int64_t)t * tile_cells, h->N);
+        CK(cudaMemcpyAsync(&e[(size_t)t], h->indptr.as<int32_t>() + row, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    for (int32_t t = 0; t < h->n_tiles; ++t)
+        if ((rc = csc_enqueue_tile(h, t, e[(size_t)t], e[(size_t)t + 1], h->stream))) return rc;
+    h->tiles_enqueued = h->n_tiles;
+    return LRPERM_OK;
+}
+
 int ensure_fast_tables(lrperm_engine* h, int32_t chunk_nnz, int32_t tile_cells) {
     int rc;
-    if (!(h->csc_ready && h->csc_tile_cells == tile_cells)) {
-        StageTimer timer("build_csc");
-        if ((rc = csc_begin(h, tile_cells))) return rc;
-        // entry ranges of the tiles: indptr at the tile boundaries
-        std::vector<int32_t> e((size_t)h->n_tiles + 1, 0);
-        for (int32_t t = 0; t <= h->n_tiles; ++t) {
-            const int64_t row = std::min<int64_t>((int64_t)t * tile_cells, h->N);
-            CK(cudaMemcpyAsync(&e[(size_t)t], h->indptr.as<int32_t>() + row, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        }
-        CK(cudaStreamSynchronize(h->stream));
-        for (int32_t t = 0; t < h->n_tiles; ++t)
-            if ((rc = csc_enqueue_tile(h, t, e[(size_t)t], e[(size_t)t + 1], h->stream))) return rc;
-        h->tiles_enqueued = h->n_tiles;
-    }
+    if ((rc = csc_enqueue_all(h, tile_cells))) return rc;
     if (h->tiles_enqueued == h->n_tiles && (h->chunk_table_nnz != chunk_nnz || h->tiles_tabled < h->n_tiles)) {
         StageTimer timer("build_chunks");
         const int32_t from = h->chunk_table_nnz == chunk_nnz ? h->tiles_tabled : 0;
@@ -1399,7 +1408,7 @@ void lrperm_destroy(lrperm_engine* h) {
     for (DevBuf* b : {&h->indptr, &h->csr_pairs, &h->csc_pairs, &h->err_flag, &h->st_indptr, &h->st_indices, &h->st_data, &h->st_row_keep, &h->st_small,
                       &h->labels32, &h->labels8, &h->labels8s, &h->order, &h->rank, &h->bucket_cluster,
                       &h->cl_start, &h->inv_n, &h->rowA, &h->rowB, &h->thr_c, &h->thr_g, &h->counts_c, &h->counts_g,
-                      &h->chunks, &h->csc_keys, &h->csc_keys2, &h->csc_payload, &h->tile_hist, &h->tile_slot_ptr, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
+                      &h->chunks, &h->csc_keys, &h->csc_keys2, &h->csc_payload, &h->tile_hist, &h->tile_slot_ptr, &h->csc_tmp, &h->slab2, &h->partials2, &h->perm_dev, &h->slab, &h->partials, &h->cube, &h->sort_tmp,
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b,
                       &h->vsc_pairs, &h->tm_chunks, &h->tm_region_ptr, &h->tm_counts, &h->tm_prefix, &h->tm_planes, &h->tm_cube,
                       &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t, &h->tm_diag, &h->tm_chunk_of_slot, &h->tm_region_dir,
@@ -1450,6 +1459,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "trimean_perm_batch") {
         if (value < 0 || value > 4096 || (value % 128) != 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: trimean_perm_batch must be a multiple of 128 in [0, 4096]");
         h->tm_perm_batch = (int32_t)value;
+    } else if (key == "eager_csc") {
+        if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: eager_csc must be 0 or 1");
+        h->eager_csc = (int32_t)value;
     } else if (key == "score_groups_per_block") {
         if (value < 0 || value > 1024) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: score_groups_per_block must be in [0, 1024]");
         h->score_gpb = (int32_t)value;
@@ -1568,6 +1580,8 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     int rc = check_err_flag(h, "lrperm_set_matrix_csr");
     if (rc) return rc;
     h->have_matrix = true;
+    // FAST mode is what normally follows: start the CSC copy now, it sorts while the caller prepares labels / triples
+    if (h->eager_csc && nnz > 0 && (rc = csc_enqueue_all(h, fast_tile_cells(h)))) return rc;
     return LRPERM_OK;
 }
 
@@ -1734,6 +1748,7 @@ int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_gen
     if ((rc = check_err_flag(h, "lrperm_commit_matrix"))) return rc;
     h->N = N_out; h->G = n_genes_out; h->nnz = nnz_out;
     h->have_matrix = true;
+    if (h->eager_csc && nnz_out > 0 && (rc = csc_enqueue_all(h, fast_tile_cells(h)))) return rc;
     return LRPERM_OK;
 }
 
@@ -1745,35 +1760,60 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
     if (!h->have_matrix) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: call lrperm_set_matrix_csr first");
     if (!labels || n_clusters <= 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: NULL labels or n_clusters <= 0");
     const int64_t N = h->N;
-    std::vector<int32_t> lab((size_t)N);
-    if (on_device) {
-        CK(cudaMemcpyAsync(lab.data(), labels, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    } else if (N > 0) {
-        memcpy(lab.data(), labels, sizeof(int32_t) * (size_t)N);
+    const size_t N1 = (size_t)std::max<int64_t>(N, 1);
+    int rc;
+    // Everything that scales with N runs on the device: cluster sizes (histogram), positions grouped by cluster,
+    // ascending within a cluster (stable radix sort of the labels: the reference's labels_mask order,
+    // _get_mean_perms.py:47-52 + boolean row selection at :63), their inverse, byte labels.  The host only sees the
+    // L cluster sizes.
+    if ((rc = upload(h, h->labels32, labels, sizeof(int32_t) * (size_t)N, on_device))) return rc;
+    CK(h->labels8.ensure(N1));
+    CK(h->order.ensure(sizeof(int32_t) * N1));
+    CK(h->rank.ensure(sizeof(int32_t) * N1));
+    DevBuf &d_small = h->small_b, &d_keys = h->tmp_a, &d_keys2 = h->tmp_c, &d_iota = h->tmp_d;
+    CK(d_small.ensure(sizeof(int32_t) * ((size_t)n_clusters + 1)));          // [L] counts, [L] first out-of-range cell
+    CK(d_keys.ensure(sizeof(uint32_t) * N1));
+    CK(d_keys2.ensure(sizeof(uint32_t) * N1));
+    CK(d_iota.ensure(sizeof(int32_t) * N1));
+    CK(cudaMemsetAsync(d_small.p, 0, sizeof(int32_t) * (size_t)n_clusters, h->stream));
+    CK(cudaMemsetAsync(d_small.as<int32_t>() + n_clusters, 0x7f, sizeof(int32_t), h->stream));
+    std::vector<int32_t> cnt((size_t)n_clusters + 1, 0);
+    if (N > 0) {
+        const size_t smem = n_clusters <= 4096 ? sizeof(int32_t) * (size_t)n_clusters : 0;
+        label_hist_kernel<<<grid_for(N, 256, h->sm_count * 8), 256, smem, h->stream>>>(
+            h->labels32.as<int32_t>(), (int32_t)N, n_clusters, d_small.as<int32_t>(), d_small.as<int32_t>() + n_clusters,
+            d_keys.as<uint32_t>(), d_iota.as<int32_t>());
+        CK_LAUNCH();
+        int end_bit = 1;
+        while ((1 << end_bit) < n_clusters && end_bit < 31) ++end_bit;
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_iota.as<int32_t>(),
+                                           h->order.as<int32_t>(), (int)N, 0, end_bit, h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        tmp_bytes = h->sort_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, d_keys.as<uint32_t>(), d_keys2.as<uint32_t>(), d_iota.as<int32_t>(),
+                                           h->order.as<int32_t>(), (int)N, 0, end_bit, h->stream));
+        label_tables_kernel<<<grid_for(N, 256, 1 << 30), 256, 0, h->stream>>>(h->labels32.as<int32_t>(), h->order.as<int32_t>(), (int32_t)N,
+                                                                            h->rank.as<int32_t>(), h->labels8.as<uint8_t>());
+        CK_LAUNCH();
     }
-    // positions grouped by cluster, ascending within a cluster (the reference's labels_mask order,
-    // _get_mean_perms.py:47-52 + boolean row selection at :63)
+    CK(cudaMemcpyAsync(cnt.data(), d_small.p, sizeof(int32_t) * ((size_t)n_clusters + 1), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (N > 0 && cnt[(size_t)n_clusters] < N) {
+        const int64_t j = cnt[(size_t)n_clusters];
+        int32_t c = 0;
+        CK(cudaMemcpy(&c, h->labels32.as<int32_t>() + j, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: label %d at cell %lld outside [0,%d)", c, (long long)j, n_clusters);
+    }
     std::vector<int32_t> start((size_t)n_clusters + 1, 0);
-    for (int64_t j = 0; j < N; ++j) {
-        const int32_t c = lab[(size_t)j];
-        if (c < 0 || c >= n_clusters) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: label %d at cell %lld outside [0,%d)", c, (long long)j, n_clusters);
-        start[(size_t)c + 1]++;
-    }
     for (int32_t c = 0; c < n_clusters; ++c) {
-        if (start[(size_t)c + 1] == 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: cluster %d has no cells (drop unused categories first)", c);
-        start[(size_t)c + 1] += start[(size_t)c];
+        if (cnt[(size_t)c] == 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: cluster %d has no cells (drop unused categories first)", c);
+        start[(size_t)c + 1] = start[(size_t)c] + cnt[(size_t)c];
     }
-    std::vector<int32_t> order((size_t)N), fill(start.begin(), start.end() - 1);
-    for (int64_t j = 0; j < N; ++j) order[(size_t)fill[(size_t)lab[(size_t)j]]++] = (int32_t)j;
     std::vector<float> inv((size_t)n_clusters);
     for (int32_t c = 0; c < n_clusters; ++c) inv[(size_t)c] = (float)(1.0 / (double)(start[(size_t)c + 1] - start[(size_t)c]));
-    std::vector<uint8_t> lab8((size_t)N);
-    for (int64_t j = 0; j < N; ++j) lab8[(size_t)j] = (uint8_t)(lab[(size_t)j] & 0xff);
-    // PHILOX permutations live on cluster-sorted positions: rank[j] = index of position j in `order`, and a
-    // coarse table (<= 4096 buckets of 2^shift sorted positions) gives the cluster of a sorted position
-    std::vector<int32_t> rank((size_t)N);
-    for (int64_t k = 0; k < N; ++k) rank[(size_t)order[(size_t)k]] = (int32_t)k;
+    // PHILOX permutations live on cluster-sorted positions: a coarse table (<= 4096 buckets of 2^shift sorted
+    // positions) gives the cluster of a sorted position
     int32_t shift = 0;
     while (((N - 1) >> shift) >= 4096) ++shift;
     const int32_t n_buckets = (int32_t)(((N > 0 ? N - 1 : 0) >> shift) + 1);
@@ -1786,16 +1826,10 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
             bucket[(size_t)b] = (uint8_t)(c & 0xff);
         }
     }
-
     h->L = n_clusters;
     h->tm_tables_ready = false;
     h->labels8s_scale = 0;
     h->h_cl_start = start;
-    int rc;
-    if ((rc = upload(h, h->labels32, lab.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
-    if ((rc = upload(h, h->labels8, lab8.data(), (size_t)N, 0))) return rc;
-    if ((rc = upload(h, h->order, order.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
-    if ((rc = upload(h, h->rank, rank.data(), sizeof(int32_t) * (size_t)N, 0))) return rc;
     if ((rc = upload(h, h->bucket_cluster, bucket.data(), (size_t)n_buckets, 0))) return rc;
     h->n_buckets = n_buckets;
     h->bucket_shift = shift;

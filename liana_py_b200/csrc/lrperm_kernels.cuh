@@ -341,6 +341,37 @@ __global__ void moments_reduce_kernel(const double* __restrict__ partial, int32_
 }
 
 // ------------------------------------------------------------------------------------------
+// Label tables (replaces the host passes of lrperm_set_labels): cluster sizes, first out-of-range cell, positions
+// grouped by cluster (stable: ascending inside a cluster = the reference's labels_mask order,
+// _get_mean_perms.py:47-52 + boolean row selection at :63), their inverse, byte labels.
+// ------------------------------------------------------------------------------------------
+__global__ void label_hist_kernel(const int32_t* __restrict__ labels, int32_t N, int32_t L, int32_t* __restrict__ counts,
+                                  int32_t* __restrict__ first_bad, uint32_t* __restrict__ keys, int32_t* __restrict__ iota) {
+    extern __shared__ int32_t lh_smem[];
+    const bool use_shared = L <= 4096;
+    if (use_shared) for (int c = threadIdx.x; c < L; c += blockDim.x) lh_smem[c] = 0;
+    __syncthreads();
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const int c = labels[j];
+        iota[j] = j;
+        if (c < 0 || c >= L) { atomicMin(first_bad, j); keys[j] = 0; continue; }
+        keys[j] = (uint32_t)c;
+        atomicAdd(use_shared ? &lh_smem[c] : &counts[c], 1);
+    }
+    __syncthreads();
+    if (use_shared) for (int c = threadIdx.x; c < L; c += blockDim.x) if (lh_smem[c]) atomicAdd(&counts[c], lh_smem[c]);
+}
+
+__global__ void label_tables_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ order, int32_t N,
+                                    int32_t* __restrict__ rank, uint8_t* __restrict__ labels8) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) {
+        rank[order[k]] = k;
+        labels8[k] = (uint8_t)(labels[k] & 0xff);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Permutation sources
 // ------------------------------------------------------------------------------------------
 struct PermSource {
