@@ -162,7 +162,9 @@ struct lrperm_engine {
     int32_t eager_csc = 1;                // option: queue the CSC build of FAST mode as soon as the matrix is set
     int32_t score_gpb = 0;                // option: 32-permutation groups per block of the score kernels (0 = auto: L2 fit)
     int32_t slab0_by_tile = 1;            // option: first batch's label slab generated / consumed cell tile by cell tile
-    std::vector<cudaEvent_t> ev_slab_tile;       // the gated first batch consumed a pending upload: read err_flag_m after the run
+    std::vector<cudaEvent_t> ev_slab_tile;
+    std::vector<cudaEvent_t> ev_main_tile;   // [2 * tile]: start / stop of the first batch's chunk warps of one tile (timing only)
+    int32_t main_tiles_timed = 0;            // tiles the first batch of the last run was launched by (0 = one launch)       // the gated first batch consumed a pending upload: read err_flag_m after the run
     DevBuf err_flag_m;                    // validation flags of the pending matrix
     // pageable uploads: two pinned staging pieces filled by a few host threads while the other one is in flight
     ParallelCopier* copier = nullptr;
@@ -789,6 +791,12 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         h->ev_slab_tile.push_back(ev);
     }
+    while (h->ev_main_tile.size() < 2 * (size_t)n_tiles_run) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        h->ev_main_tile.push_back(ev);
+    }
+    h->main_tiles_timed = 0;
     auto enqueue_slab = [&](int64_t b) -> int {
         const int64_t p0 = first[(size_t)b];
         const int32_t PBb = sched[(size_t)b];
@@ -870,8 +878,12 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
                 if (gated && (rc = chunks_append_tile(h, t, chunk_nnz, sA))) return rc;      // host waits for tile t's CSC
                 if (by_tile) CK(cudaStreamWaitEvent(sA, h->ev_slab_tile[(size_t)t], 0));   // the tile's slab rows exist
                 const int32_t c0 = h->h_tile_chunk_ptr[(size_t)t], c1 = h->h_tile_chunk_ptr[(size_t)t + 1];
+                // kernel time of the tile alone (the waits above - slab rows, CSC of an arriving tile - are not kernel time)
+                CK(cudaEventRecord(h->ev_main_tile[2 * (size_t)t], sA));
                 if (c1 > c0 && (rc = launch_fast_any(h, Q, PBb, slabs[0], parts[0], c0, c1 - c0))) return rc;
+                CK(cudaEventRecord(h->ev_main_tile[2 * (size_t)t + 1], sA));
             }
+            h->main_tiles_timed = h->n_tiles;
             if (gated) {
                 h->chunk_table_nnz = chunk_nnz;
                 // the whole matrix is resident now; its column-range validation is read back with the results
@@ -923,7 +935,13 @@ int collect_pipelined_timings(lrperm_engine* h, int64_t n_batches) {
     for (int64_t b = 0; b < n_batches; ++b) {
         float ms;
         CK(cudaEventElapsedTime(&ms, EV(b, 0), EV(b, 1))); h->t_setup += ms;
-        CK(cudaEventElapsedTime(&ms, EV(b, 2), EV(b, 3))); h->t_main += ms; h->t_means += ms;
+        CK(cudaEventElapsedTime(&ms, EV(b, 2), EV(b, 3))); h->t_means += ms;
+        if (b == 0 && h->main_tiles_timed > 0) {        // launched tile by tile: sum of the launches, without the gating waits
+            for (int32_t t = 0; t < h->main_tiles_timed; ++t) {
+                CK(cudaEventElapsedTime(&ms, h->ev_main_tile[2 * (size_t)t], h->ev_main_tile[2 * (size_t)t + 1]));
+                h->t_main += ms;
+            }
+        } else h->t_main += ms;
         CK(cudaEventElapsedTime(&ms, EV(b, 4), EV(b, 5))); h->t_means += ms;
         CK(cudaEventElapsedTime(&ms, EV(b, 5), EV(b, 6))); h->t_score += ms;
     }
@@ -1417,6 +1435,7 @@ void lrperm_destroy(lrperm_engine* h) {
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_tile) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_slab_tile) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ev_main_tile) cudaEventDestroy(ev);
     h->hist_pin.release();
     h->table_pin.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
