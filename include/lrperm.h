@@ -189,6 +189,29 @@ int lrperm_observed_trimean(lrperm_engine *h, double recip, double *trimean, int
 int lrperm_trimean_timings(lrperm_engine *h, float *out6);
 
 /*
+ * expr_prop filter, min-subunit resolution of the complexes and name -> index maps on the device
+ * (filter_reassemble_complexes, liana/resource/_reassemble_complexes.py:11-101; _get_mat_idx,
+ * liana/method/_pipe_utils/_get_mean_perms.py:90-113; _join_stats, _pipe_utils/_common.py:5-39), which the reference
+ * does with pandas merges over L^2 x 5,780 exploded rows and an O(T x G) Python dictionary comprehension.
+ *   lig_sub / rec_sub [n_inter][max_l | max_r]  gene column of every subunit of the ligand / receptor complex, in the
+ *                                               complex's '_' order, -1 padded (host)
+ *   stat [L][G]            the statistic named by the method's complex_cols: cluster means (float32) or CellChat's
+ *                          cluster trimeans (float64, stat_is_f64 = 1); props [L][G] float64; pair_mask [L][L] or NULL
+ *   first_subunit          1 = every complex is represented by its first subunit (return_all_lrs de-duplicates before
+ *                          the min-subunit step, :52-57), else the FIRST subunit with the minimal statistic
+ *   return_all             1 = rows that fail expr_prop are emitted too (keep = 0)
+ * Rows come out in the reference's order (source-major, then target, then interaction).  lrperm_resolve_triples returns
+ * the row count; lrperm_fetch_triples copies the columns to host arrays of that length (all required): interaction index, source / target cluster, resolved ligand / receptor gene column, their
+ * statistic (float32 or float64 like `stat`) and props, and the expr_prop flag.
+ */
+int lrperm_resolve_triples(lrperm_engine *h, int32_t n_inter, int32_t max_l, int32_t max_r,
+                           const int32_t *lig_sub, const int32_t *rec_sub, const void *stat, int stat_is_f64,
+                           const double *props, double expr_prop, const uint8_t *pair_mask, int first_subunit,
+                           int return_all, int64_t *n_rows);
+int lrperm_fetch_triples(lrperm_engine *h, int32_t *inter, int32_t *src, int32_t *tgt, int32_t *lig_gene, int32_t *rec_gene,
+                         void *lig_stat, void *rec_stat, double *lig_props, double *rec_props, uint8_t *keep);
+
+/*
  * Consensus of method scores (liana/method/_pipe_utils/_aggregate.py:70-181), the step that turns the permutation
  * p-values and the other scores into `specificity_rank` / `magnitude_rank`:
  *   lrperm_rank_average  ranks[i] = scipy.stats.rankdata(negate ? -values : values, method='average')[i]   (:91-98);

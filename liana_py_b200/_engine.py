@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "lrperm_philox_perms", "lrperm_last_timings", "lrperm_set_tuning", "lrperm_set_option",
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
-    "lrperm_rank_average", "lrperm_rra",
+    "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
 )
 
 _lib = None
@@ -74,6 +74,8 @@ def load_library():
     lib.lrperm_staged_max.argtypes = [vp, vp, vp]
     lib.lrperm_rank_average.argtypes = [vp, i64, vp, C.c_int, vp, C.c_int]
     lib.lrperm_rra.argtypes = [vp, i64, i32, vp, vp, vp, C.c_int]
+    lib.lrperm_resolve_triples.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.c_int, vp, C.c_double, vp, C.c_int, C.c_int, vp]
+    lib.lrperm_fetch_triples.argtypes = [vp] + [vp] * 10
     _lib = lib
     return lib
 
@@ -347,6 +349,36 @@ class Engine:
         self._check(self._lib.lrperm_trimean_timings(self._h, C.cast(buf, C.c_void_p)))
         return {"count_ms": buf[0], "prefix_ms": buf[1], "select_ms": buf[2], "finalize_ms": buf[3],
                 "walked_warps": int(buf[4]), "select_warps": int(buf[5])}
+
+    # -- complexes / expr_prop filter ---------------------------------------------------------
+    def resolve_triples(self, lig_sub, rec_sub, stat, props, expr_prop, pair_mask=None, first_subunit=False, return_all=False):
+        """Kept (source, target, interaction) rows with resolved subunits (include/lrperm.h).  Returns a dict of
+        host arrays: inter, src, tgt, lig_gene, rec_gene (int32), lig_stat, rec_stat (dtype of `stat`), lig_props,
+        rec_props (float64), keep (bool)."""
+        lig_sub = np.ascontiguousarray(lig_sub, dtype=np.int32)
+        rec_sub = np.ascontiguousarray(rec_sub, dtype=np.int32)
+        if stat.dtype not in (np.float32, np.float64):
+            stat = stat.astype(np.float64)
+        stat = np.ascontiguousarray(stat)
+        props = np.ascontiguousarray(props, dtype=np.float64)
+        assert stat.shape == (self.L, self.G) and props.shape == (self.L, self.G)
+        mask = None if pair_mask is None else np.ascontiguousarray(pair_mask, dtype=np.uint8)
+        n = C.c_int64(0)
+        self._check(self._lib.lrperm_resolve_triples(
+            self._h, int(lig_sub.shape[0]), int(lig_sub.shape[1]), int(rec_sub.shape[1]), C.c_void_p(lig_sub.ctypes.data),
+            C.c_void_p(rec_sub.ctypes.data), C.c_void_p(stat.ctypes.data), int(stat.dtype == np.float64),
+            C.c_void_p(props.ctypes.data), float(expr_prop), None if mask is None else C.c_void_p(mask.ctypes.data),
+            int(bool(first_subunit)), int(bool(return_all)), C.byref(n)))
+        T = int(n.value)
+        out = {k: np.empty(T, dtype=np.int32) for k in ("inter", "src", "tgt", "lig_gene", "rec_gene")}
+        out.update({k: np.empty(T, dtype=stat.dtype) for k in ("lig_stat", "rec_stat")})
+        out.update({k: np.empty(T, dtype=np.float64) for k in ("lig_props", "rec_props")})
+        keep = np.empty(T, dtype=np.uint8)
+        order = ("inter", "src", "tgt", "lig_gene", "rec_gene", "lig_stat", "rec_stat", "lig_props", "rec_props")
+        self._check(self._lib.lrperm_fetch_triples(self._h, *(C.c_void_p(out[k].ctypes.data) for k in order),
+                                                   C.c_void_p(keep.ctypes.data)))
+        out["keep"] = keep.astype(bool)
+        return out
 
     # -- consensus ---------------------------------------------------------------------------
     def rank_average(self, values, negate: bool = False) -> np.ndarray:

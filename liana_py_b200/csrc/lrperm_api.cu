@@ -229,6 +229,10 @@ struct lrperm_engine {
     DevBuf perm_dev, slab, partials, cube, sort_tmp, tmp_a, tmp_b, tmp_c, tmp_d, stage_out, small_a, small_b;
 
     // CellChat trimean path (lrperm_trimean.cuh)
+    // lrperm_resolve_triples: side tables and the resolved rows (kept until lrperm_fetch_triples)
+    DevBuf rs_side, rs_flag, rs_pos, rs_rows, rs_in;
+    int64_t rs_T = -1;
+    int32_t rs_f64 = 0;
     DevBuf tm_diag, tm_chunk_of_slot, tm_region_dir, tm_walk_flag, tm_walk_list;
     int64_t tm_select_warps = 0, tm_walked_warps = 0;
     int32_t tm_n_batches = 0, tm_n_super = 0;
@@ -1430,7 +1434,7 @@ void lrperm_destroy(lrperm_engine* h) {
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b,
                       &h->vsc_pairs, &h->tm_chunks, &h->tm_region_ptr, &h->tm_counts, &h->tm_prefix, &h->tm_planes, &h->tm_cube,
                       &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t, &h->tm_diag, &h->tm_chunk_of_slot, &h->tm_region_dir,
-                      &h->tm_walk_flag, &h->tm_walk_list})
+                      &h->tm_walk_flag, &h->tm_walk_list, &h->rs_side, &h->rs_flag, &h->rs_pos, &h->rs_rows, &h->rs_in})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_tile) cudaEventDestroy(ev);
@@ -2245,6 +2249,139 @@ int lrperm_observed_trimean(lrperm_engine* h, double recip, double* trimean, int
     if (!out_on_device) CK(cudaMemcpyAsync(trimean, dev_dst, sizeof(double) * (size_t)L * G, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return collect_trimean_timings(h);
+}
+
+extern "C++" {
+namespace {
+// byte layout of the resolved rows buffer: 5 int32 columns, 2 statistic columns (ST), 2 double columns, 1 byte column
+struct RowsLayout { size_t inter, src, tgt, lg, rg, ls, rs, lp, rp, keep, total; };
+RowsLayout rows_layout(size_t T, size_t st_size) {
+    RowsLayout l;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+    l.lp = take(8 * T); l.rp = take(8 * T); l.ls = take(st_size * T); l.rs = take(st_size * T);
+    l.inter = take(4 * T); l.src = take(4 * T); l.tgt = take(4 * T); l.lg = take(4 * T); l.rg = take(4 * T); l.keep = take(T);
+    l.total = o;
+    return l;
+}
+
+template <typename ST>
+int resolve_impl(lrperm_engine* h, int32_t n, int32_t max_l, int32_t max_r, const int32_t* d_lsub, const int32_t* d_rsub,
+                 const ST* d_stat, const double* d_props, double expr_prop, const uint8_t* d_mask, int first_subunit, int return_all,
+                 int64_t* n_rows) {
+    const int32_t L = h->L, G = (int32_t)h->G;
+    const size_t nl = (size_t)n * L;
+    // side tables: per side gene[nl] int32, stat[nl] ST, prop[nl] f64, pmin[nl] f64
+    const size_t side_bytes = ((nl * 8 + 255) & ~(size_t)255) * 3 + ((nl * 4 + 255) & ~(size_t)255);
+    CK(h->rs_side.ensure(2 * side_bytes));
+    auto side = [&](int which, int32_t*& gene, ST*& stv, double*& prop, double*& pmin) {
+        unsigned char* b = h->rs_side.as<unsigned char>() + (size_t)which * side_bytes;
+        const size_t a8 = (nl * 8 + 255) & ~(size_t)255;
+        prop = reinterpret_cast<double*>(b); pmin = reinterpret_cast<double*>(b + a8);
+        stv = reinterpret_cast<ST*>(b + 2 * a8); gene = reinterpret_cast<int32_t*>(b + 3 * a8);
+    };
+    int32_t *gl, *gr; ST *sl, *sr; double *pl, *pr, *ml, *mr;
+    side(0, gl, sl, pl, ml); side(1, gr, sr, pr, mr);
+    const int g1 = grid_for((int64_t)nl, 256, 1 << 30);
+    resolve_side_kernel<ST><<<g1, 256, 0, h->stream>>>(d_lsub, n, max_l, L, G, d_stat, d_props, first_subunit, gl, sl, pl, ml);
+    CK_LAUNCH();
+    resolve_side_kernel<ST><<<g1, 256, 0, h->stream>>>(d_rsub, n, max_r, L, G, d_stat, d_props, first_subunit, gr, sr, pr, mr);
+    CK_LAUNCH();
+    const int64_t F = (int64_t)L * L * n;
+    if (F >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_resolve_triples: L^2 x n_inter must be < 2^31");
+    CK(h->rs_flag.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(F, 1)));
+    CK(h->rs_pos.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(F, 1)));
+    int64_t T = 0;
+    if (F > 0) {
+        const int g2 = grid_for(F, 256, 1 << 30);
+        resolve_flags_kernel<<<g2, 256, 0, h->stream>>>(ml, mr, d_mask, n, L, expr_prop, return_all, h->rs_flag.as<int32_t>());
+        CK_LAUNCH();
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->rs_flag.as<int32_t>(), h->rs_pos.as<int32_t>(), (int)F, h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        tmp_bytes = h->sort_tmp.cap;
+        CK(cub::DeviceScan::ExclusiveSum(h->sort_tmp.p, tmp_bytes, h->rs_flag.as<int32_t>(), h->rs_pos.as<int32_t>(), (int)F, h->stream));
+        int32_t last_pos = 0, last_flag = 0;
+        CK(cudaMemcpyAsync(&last_pos, h->rs_pos.as<int32_t>() + (F - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&last_flag, h->rs_flag.as<int32_t>() + (F - 1), 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        T = (int64_t)last_pos + last_flag;
+        const RowsLayout lay = rows_layout((size_t)T, sizeof(ST));
+        CK(h->rs_rows.ensure(std::max<size_t>(lay.total, 256)));
+        unsigned char* b = h->rs_rows.as<unsigned char>();
+        if (T > 0) {
+            resolve_scatter_kernel<ST><<<g2, 256, 0, h->stream>>>(
+                h->rs_flag.as<int32_t>(), h->rs_pos.as<int32_t>(), n, L, expr_prop, gl, sl, pl, ml, gr, sr, pr, mr,
+                reinterpret_cast<int32_t*>(b + lay.inter), reinterpret_cast<int32_t*>(b + lay.src), reinterpret_cast<int32_t*>(b + lay.tgt),
+                reinterpret_cast<int32_t*>(b + lay.lg), reinterpret_cast<int32_t*>(b + lay.rg), reinterpret_cast<ST*>(b + lay.ls),
+                reinterpret_cast<ST*>(b + lay.rs), reinterpret_cast<double*>(b + lay.lp), reinterpret_cast<double*>(b + lay.rp), b + lay.keep);
+            CK_LAUNCH();
+        }
+    }
+    h->rs_T = T;
+    h->rs_f64 = sizeof(ST) == 8;
+    if (n_rows) *n_rows = T;
+    return LRPERM_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int lrperm_resolve_triples(lrperm_engine* h, int32_t n_inter, int32_t max_l, int32_t max_r, const int32_t* lig_sub, const int32_t* rec_sub,
+                           const void* stat, int stat_is_f64, const double* props, double expr_prop, const uint8_t* pair_mask,
+                           int first_subunit, int return_all, int64_t* n_rows) {
+    if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("resolve_triples");
+    DeviceGuard guard(h->device);
+    h->rs_T = -1;
+    if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_resolve_triples: set the matrix and labels first");
+    if (n_inter < 0 || max_l <= 0 || max_r <= 0 || (n_inter > 0 && (!lig_sub || !rec_sub)) || !stat || !props)
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_resolve_triples: bad arguments");
+    const int32_t L = h->L, G = (int32_t)h->G;
+    const size_t LG = (size_t)L * G, st_size = stat_is_f64 ? 8 : 4;
+    // inputs (host) -> one device buffer: [props f64][stat][lig_sub][rec_sub][pair_mask]
+    const size_t o_props = 0, o_stat = LG * 8, o_ls = o_stat + ((LG * st_size + 7) & ~(size_t)7);
+    const size_t o_rs = o_ls + (((size_t)n_inter * max_l * 4 + 7) & ~(size_t)7), o_mask = o_rs + (((size_t)n_inter * max_r * 4 + 7) & ~(size_t)7);
+    CK(h->rs_in.ensure(o_mask + (size_t)L * L + 16));
+    unsigned char* b = h->rs_in.as<unsigned char>();
+    CK(cudaMemcpyAsync(b + o_props, props, LG * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(b + o_stat, stat, LG * st_size, cudaMemcpyHostToDevice, h->stream));
+    if (n_inter > 0) {
+        CK(cudaMemcpyAsync(b + o_ls, lig_sub, (size_t)n_inter * max_l * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(b + o_rs, rec_sub, (size_t)n_inter * max_r * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (pair_mask) CK(cudaMemcpyAsync(b + o_mask, pair_mask, (size_t)L * L, cudaMemcpyHostToDevice, h->stream));
+    const uint8_t* d_mask = pair_mask ? b + o_mask : nullptr;
+    if (stat_is_f64)
+        return resolve_impl<double>(h, n_inter, max_l, max_r, reinterpret_cast<int32_t*>(b + o_ls), reinterpret_cast<int32_t*>(b + o_rs),
+                                    reinterpret_cast<double*>(b + o_stat), reinterpret_cast<double*>(b + o_props), expr_prop, d_mask,
+                                    first_subunit, return_all, n_rows);
+    return resolve_impl<float>(h, n_inter, max_l, max_r, reinterpret_cast<int32_t*>(b + o_ls), reinterpret_cast<int32_t*>(b + o_rs),
+                               reinterpret_cast<float*>(b + o_stat), reinterpret_cast<double*>(b + o_props), expr_prop, d_mask,
+                               first_subunit, return_all, n_rows);
+}
+
+int lrperm_fetch_triples(lrperm_engine* h, int32_t* inter, int32_t* src, int32_t* tgt, int32_t* lig_gene, int32_t* rec_gene,
+                         void* lig_stat, void* rec_stat, double* lig_props, double* rec_props, uint8_t* keep) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (h->rs_T < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_fetch_triples: call lrperm_resolve_triples first");
+    const size_t T = (size_t)h->rs_T, st_size = h->rs_f64 ? 8 : 4;
+    if (T == 0) return LRPERM_OK;
+    const RowsLayout lay = rows_layout(T, st_size);
+    const unsigned char* b = h->rs_rows.as<unsigned char>();
+    int rc;
+    if ((rc = download(h, inter, b + lay.inter, 4 * T, 0))) return rc;
+    if ((rc = download(h, src, b + lay.src, 4 * T, 0))) return rc;
+    if ((rc = download(h, tgt, b + lay.tgt, 4 * T, 0))) return rc;
+    if ((rc = download(h, lig_gene, b + lay.lg, 4 * T, 0))) return rc;
+    if ((rc = download(h, rec_gene, b + lay.rg, 4 * T, 0))) return rc;
+    if ((rc = download(h, lig_stat, b + lay.ls, st_size * T, 0))) return rc;
+    if ((rc = download(h, rec_stat, b + lay.rs, st_size * T, 0))) return rc;
+    if ((rc = download(h, lig_props, b + lay.lp, 8 * T, 0))) return rc;
+    if ((rc = download(h, rec_props, b + lay.rp, 8 * T, 0))) return rc;
+    if ((rc = download(h, keep, b + lay.keep, T, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
 }
 
 int lrperm_rank_average(lrperm_engine* h, int64_t n, const double* values, int negate, double* ranks, int on_device) {

@@ -948,6 +948,79 @@ __global__ void build_rows_kernel(const int32_t* __restrict__ lig, const int32_t
 }
 
 // ------------------------------------------------------------------------------------------
+// expr_prop filter + min-subunit resolution of the complexes + name -> index maps
+// (liana/resource/_reassemble_complexes.py:11-101, liana/method/_pipe_utils/_get_mean_perms.py:90-113): the kept
+// (source, target, interaction) rows with their resolved subunit genes and statistics, built from two
+// [n_inter][L] side tables instead of pandas merges over the L^2 x 5,780 exploded rows.
+// ------------------------------------------------------------------------------------------
+// side tables: for (interaction i, cluster c) the subunit with the FIRST minimal statistic in the complex's '_' order
+// (or the first subunit when `first_subunit`: return_all_lrs de-duplicates before the min-subunit step), its
+// statistic / prop, and the minimal prop over all subunits
+template <typename ST>
+__global__ void resolve_side_kernel(const int32_t* __restrict__ sub /*[n][m], -1 padded*/, int32_t n, int32_t m, int32_t L, int32_t G,
+                                    const ST* __restrict__ stat /*[L][G]*/, const double* __restrict__ props /*[L][G]*/, int first_subunit,
+                                    int32_t* __restrict__ gene /*[n][L]*/, ST* __restrict__ statv, double* __restrict__ propv,
+                                    double* __restrict__ pmin) {
+    const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (id >= (int64_t)n * L) return;
+    const int i = (int)(id / L), c = (int)(id % L);
+    int best = 0;
+    ST best_v = (ST)0;
+    double pm = 0.0;
+    bool any = false;
+    for (int k = 0; k < m; ++k) {
+        const int g = sub[(int64_t)i * m + k];
+        if (g < 0) continue;
+        const ST v = stat[(int64_t)c * G + g];
+        const double p = props[(int64_t)c * G + g];
+        if (!any) { best = g; best_v = v; pm = p; any = true; }
+        else {
+            if (!first_subunit && v < best_v) { best = g; best_v = v; }
+            pm = fmin(pm, p);
+        }
+    }
+    gene[id] = best;
+    statv[id] = any ? stat[(int64_t)c * G + best] : (ST)0;
+    propv[id] = any ? props[(int64_t)c * G + best] : 0.0;
+    pmin[id] = any ? pm : 0.0;
+}
+
+// flat row f = (s * L + t) * n + i (the reference concatenates per (source, target) pair, interactions inside)
+__global__ void resolve_flags_kernel(const double* __restrict__ pmin_l, const double* __restrict__ pmin_r, const uint8_t* __restrict__ pair_mask,
+                                     int32_t n, int32_t L, double expr_prop, int return_all, int32_t* __restrict__ flag) {
+    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= (int64_t)L * L * n) return;
+    const int i = (int)(f % n);
+    const int64_t st = f / n;
+    const int s = (int)(st / L), t = (int)(st % L);
+    const bool expressed = pmin_l[(int64_t)i * L + s] >= expr_prop && pmin_r[(int64_t)i * L + t] >= expr_prop;
+    const bool valid = pair_mask ? pair_mask[s * L + t] != 0 : true;
+    flag[f] = (return_all ? valid : (valid && expressed)) ? 1 : 0;
+}
+
+template <typename ST>
+__global__ void resolve_scatter_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int32_t n, int32_t L, double expr_prop,
+                                       const int32_t* __restrict__ gene_l, const ST* __restrict__ stat_l, const double* __restrict__ prop_l,
+                                       const double* __restrict__ pmin_l, const int32_t* __restrict__ gene_r, const ST* __restrict__ stat_r,
+                                       const double* __restrict__ prop_r, const double* __restrict__ pmin_r,
+                                       int32_t* __restrict__ o_inter, int32_t* __restrict__ o_src, int32_t* __restrict__ o_tgt,
+                                       int32_t* __restrict__ o_lg, int32_t* __restrict__ o_rg, ST* __restrict__ o_ls, ST* __restrict__ o_rs,
+                                       double* __restrict__ o_lp, double* __restrict__ o_rp, uint8_t* __restrict__ o_keep) {
+    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= (int64_t)L * L * n || !flag[f]) return;
+    const int i = (int)(f % n);
+    const int64_t st = f / n;
+    const int s = (int)(st / L), t = (int)(st % L);
+    const int64_t a = (int64_t)i * L + s, b = (int64_t)i * L + t;
+    const int32_t r = pos[f];
+    o_inter[r] = i; o_src[r] = s; o_tgt[r] = t;
+    o_lg[r] = gene_l[a]; o_rg[r] = gene_r[b];
+    o_ls[r] = stat_l[a]; o_rs[r] = stat_r[b];
+    o_lp[r] = prop_l[a]; o_rp[r] = prop_r[b];
+    o_keep[r] = (pmin_l[a] >= expr_prop && pmin_r[b] >= expr_prop) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Consensus of method scores (liana/method/_pipe_utils/_aggregate.py:70-181): average-method ranks of a score
 // column (scipy.stats.rankdata(method='average'), :91-98) and the RobustRankAggregate rho of every row (:110-181).
 // ------------------------------------------------------------------------------------------

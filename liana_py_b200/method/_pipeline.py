@@ -94,7 +94,8 @@ class PipelineState:
         key = ("tri", float(expr_prop), bool(return_all_lrs), stat)
         if key not in self._cache:
             by = self.means if stat == "means" else self.trimean()
-            tri = _tables.resolve_triples(self.tables, by, self.props, expr_prop, self.pair_mask, return_all_lrs)
+            tri = _tables.resolve_triples(self.tables, by, self.props, expr_prop, self.pair_mask, return_all_lrs,
+                                          engine=self.engine)
             self._cache[key] = (tri, base_frame(self, tri, stat))
         return self._cache[key]
 

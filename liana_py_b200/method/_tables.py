@@ -101,10 +101,18 @@ class ResolvedTriples:
 
 
 def resolve_triples(tables: ResourceTables, means: np.ndarray, props: np.ndarray, expr_prop: float,
-                    pair_mask: np.ndarray | None = None, return_all_lrs: bool = False) -> ResolvedTriples:
+                    pair_mask: np.ndarray | None = None, return_all_lrs: bool = False, engine=None) -> ResolvedTriples:
     """means [L,G] = the statistic named by the method's `complex_cols` (float32 cluster means; float64 cluster
     trimeans for CellChat), props float64 [L,G], in the gene-subset column space.
-    pair_mask [L,L] bool restricts (source, target) pairs (groupby_pairs)."""
+    pair_mask [L,L] bool restricts (source, target) pairs (groupby_pairs).
+    With an engine (the product path always passes one) the rows are built on the device
+    (`lrperm_resolve_triples`); the NumPy formulation below is the checker of that kernel (CPU tests)."""
+    if engine is not None:
+        r = engine.resolve_triples(tables.lig_sub, tables.rec_sub, means, props, expr_prop, pair_mask,
+                                   first_subunit=return_all_lrs, return_all=return_all_lrs)
+        return ResolvedTriples(inter=r["inter"], src=r["src"], tgt=r["tgt"], lig_gene=r["lig_gene"], rec_gene=r["rec_gene"],
+                               ligand_means=r["lig_stat"], receptor_means=r["rec_stat"], ligand_props=r["lig_props"],
+                               receptor_props=r["rec_props"], keep=r["keep"])
     L = means.shape[0]
     # with return_all_lrs the reference de-duplicates subunit rows BEFORE the min-subunit step
     # (`_reassemble_complexes.py:52-57`), i.e. every complex is represented by its first subunits
