@@ -222,6 +222,9 @@ int lrperm_fetch_triples(lrperm_engine *h, int32_t *inter, int32_t *src, int32_t
  * Host or device pointers (`on_device`), independent of the matrix / label state of the engine.
  */
 int lrperm_rank_average(lrperm_engine *h, int64_t n, const double *values, int negate, double *ranks, int on_device);
+/* order[k] = index of the k-th row when sorting by `values` (stable; descending = largest first): the final
+ * `liana_res.sort_values(magnitude)` of liana_pipe (liana/method/sc/_liana_pipe.py:246-250).  No NaN in `values`. */
+int lrperm_argsort(lrperm_engine *h, int64_t n, const double *values, int descending, int32_t *order, int on_device);
 int lrperm_rra(lrperm_engine *h, int64_t n_rows, int32_t n_cols, const double *rmat, const double *col_max, double *rho, int on_device);
 
 /* Export Philox permutation(s) as index arrays: out[p*N + j] = cell at position j (int32), i.e. the array

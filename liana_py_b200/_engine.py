@@ -27,6 +27,7 @@ ABI_SYMBOLS = (
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
     "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
+    "lrperm_argsort",
 )
 
 _lib = None
@@ -74,6 +75,7 @@ def load_library():
     lib.lrperm_staged_max.argtypes = [vp, vp, vp]
     lib.lrperm_rank_average.argtypes = [vp, i64, vp, C.c_int, vp, C.c_int]
     lib.lrperm_rra.argtypes = [vp, i64, i32, vp, vp, vp, C.c_int]
+    lib.lrperm_argsort.argtypes = [vp, i64, vp, C.c_int, vp, C.c_int]
     lib.lrperm_resolve_triples.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.c_int, vp, C.c_double, vp, C.c_int, C.c_int, vp]
     lib.lrperm_fetch_triples.argtypes = [vp] + [vp] * 10
     _lib = lib
@@ -387,6 +389,14 @@ class Engine:
         out = np.empty(v.shape[0], dtype=np.float64)
         self._check(self._lib.lrperm_rank_average(self._h, int(v.shape[0]), C.c_void_p(v.ctypes.data), int(bool(negate)),
                                                   C.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def argsort(self, values, descending: bool = False) -> np.ndarray:
+        """Stable argsort of a float column on the device (no NaN in `values`)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = np.empty(v.shape[0], dtype=np.int32)
+        self._check(self._lib.lrperm_argsort(self._h, int(v.shape[0]), C.c_void_p(v.ctypes.data), int(bool(descending)),
+                                             C.c_void_p(out.ctypes.data), 0))
         return out
 
     def rra(self, rmat) -> np.ndarray:

@@ -2430,6 +2430,33 @@ int lrperm_rank_average(lrperm_engine* h, int64_t n, const double* values, int n
     return LRPERM_OK;
 }
 
+int lrperm_argsort(lrperm_engine* h, int64_t n, const double* values, int descending, int32_t* order, int on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (n < 0 || n >= 0x7fffffffLL || (n > 0 && (!values || !order))) return h->fail(LRPERM_ERR_INVALID, "lrperm_argsort: bad arguments");
+    if (n == 0) return LRPERM_OK;
+    int rc;
+    const size_t N = (size_t)n;
+    const double* d_vals = values;
+    if (!on_device) { if ((rc = upload(h, h->tmp_a, values, sizeof(double) * N, 0))) return rc; d_vals = h->tmp_a.as<double>(); }
+    CK(h->tmp_b.ensure(sizeof(unsigned long long) * N));
+    CK(h->tmp_c.ensure(sizeof(unsigned long long) * N));
+    CK(h->tmp_d.ensure(sizeof(int32_t) * N * 2));
+    uint32_t* idx = h->tmp_d.as<uint32_t>();
+    uint32_t* idx_sorted = on_device ? reinterpret_cast<uint32_t*>(order) : idx + N;
+    // stable ascending sort of the key of -v puts the largest v first and keeps equal values in their original order
+    rank_keys_kernel<<<grid_for(n, 256, 1 << 30), 256, 0, h->stream>>>(d_vals, n, descending, h->tmp_b.as<unsigned long long>(), idx);
+    CK_LAUNCH();
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->tmp_b.as<unsigned long long>(), h->tmp_c.as<unsigned long long>(), idx, idx_sorted, (int)n, 0, 64, h->stream));
+    CK(h->sort_tmp.ensure(tmp_bytes));
+    tmp_bytes = h->sort_tmp.cap;
+    CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp_bytes, h->tmp_b.as<unsigned long long>(), h->tmp_c.as<unsigned long long>(), idx, idx_sorted, (int)n, 0, 64, h->stream));
+    if (!on_device) CK(cudaMemcpyAsync(order, idx_sorted, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
 int lrperm_rra(lrperm_engine* h, int64_t n_rows, int32_t n_cols, const double* rmat, const double* col_max, double* rho, int on_device) {
     if (!h) return LRPERM_ERR_INVALID;
     DeviceGuard guard(h->device);

@@ -69,4 +69,5 @@ def aggregate(lr_res: pd.DataFrame, consensus, aggregate_method: str = "rra", co
     if "Magnitude" in consensus_opts:
         lr_res[consensus.magnitude] = rank_aggregate_scores(lr_res, consensus.magnitude_specs, aggregate_method, engine)
         order_col = consensus.magnitude
-    return lr_res.sort_values(order_col)
+    from ._pipeline import sort_frame
+    return sort_frame(engine, lr_res, order_col, True)

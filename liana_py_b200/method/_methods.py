@@ -131,7 +131,7 @@ class Method(MethodMeta):
                                perm_source, order, gmean_mode, dist)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
-        liana_res = liana_res.sort_values(by=orderby, ascending=ascending)
+        liana_res = PL.sort_frame(state.engine, liana_res, orderby, ascending)
         if not _names:                          # by_sample across ranks: (code frame, name tables), see by_sample
             return liana_res, PL.name_tables(state)
         liana_res = PL.materialise_names(state, liana_res)

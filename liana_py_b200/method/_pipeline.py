@@ -236,6 +236,16 @@ def materialise_names(state_or_tables, frame: pd.DataFrame) -> pd.DataFrame:
     return frame
 
 
+def sort_frame(engine, frame: pd.DataFrame, by: str, ascending: bool) -> pd.DataFrame:
+    """`liana_res.sort_values(by, ascending)` (`_liana_pipe.py:246-250`) with the argsort on the device; the order among
+    equal values is the original row order (the reference's quicksort leaves it unspecified).  NaN keys go through
+    pandas (NaN last)."""
+    vals = np.asarray(frame[by].values, dtype=np.float64)
+    if engine is None or len(vals) < 4096 or np.isnan(vals).any():
+        return frame.sort_values(by=by, ascending=ascending)
+    return frame.take(engine.argsort(vals, descending=not ascending))
+
+
 def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame: pd.DataFrame, add_cols) -> pd.DataFrame:
     """Method-specific statistic columns of the rows in `tri` (the resolved min-subunit gene of every row
     carries its own statistics through `filter_reassemble_complexes`, `_reassemble_complexes.py:60-66`)."""

@@ -81,7 +81,7 @@ class AggregateClass(MethodMeta):
                            engine=state.engine)
         orderby = self.magnitude if self.magnitude in lr_res.columns else self.specificity
         if orderby in lr_res.columns:
-            lr_res = lr_res.sort_values(by=orderby, ascending=True)   # `_liana_pipe.py:246-250`
+            lr_res = PL.sort_frame(state.engine, lr_res, orderby, True)   # `_liana_pipe.py:246-250`
         if not _names:                          # by_sample across ranks: (code frame, name tables)
             return lr_res, PL.name_tables(state)
         lr_res = PL.materialise_names(state, lr_res)
