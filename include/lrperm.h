@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LRPERM_ABI_VERSION 1
+#define LRPERM_ABI_VERSION 2   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads */
 
 /* status codes */
 #define LRPERM_OK              0
