@@ -172,3 +172,36 @@ def test_cellchat_philox_default_and_no_perms():
     agg = li.mt.AggregateClass(li.mt.aggregate_meta, methods=[li.mt.cellphonedb, li.mt.cellchat])
     out = agg(adata, groupby="cluster", use_raw=False, n_perms=50, inplace=False)
     assert {"lr_means", "cellphone_pvals", "lr_probs", "cellchat_pvals", "magnitude_rank", "specificity_rank"} <= set(out.columns)
+
+
+def test_cellchat_mid_size_properties(engine):
+    """50k cells x 600 genes x 20 clusters, skewed densities: several chunks per gene, two batches of 512, super-batch
+    select.  Cube of the first permutations against the C oracle bit for bit; determinism; permutation shards add up;
+    rows whose observed score is 0 count every permutation; counts equal the oracle's score on the engine's cube."""
+    from liana_py_b200.testing._synth import synthetic_csr
+    N, G, L, P = 50_000, 600, 20, 640
+    X, labels = synthetic_csr(N, G, L, density=0.2, seed_data=5, seed_labels=6)
+    mat_max = np.float32(X.max())
+    engine.set_matrix(X)
+    engine.set_labels(labels, L)
+    rng = np.random.default_rng(2)
+    T = 30_000
+    lig, rec = rng.integers(0, G, T), rng.integers(0, G, T)
+    src, tgt = rng.integers(0, L, T), rng.integers(0, L, T)
+    engine.set_triples(lig, rec, src, tgt)
+    obs_tm = engine.observed_trimean(mat_max)
+    assert np.array_equal(obs_tm, c_oracle.trimean_cube(X, labels, L, None, mat_max)[0])
+    obs = numpy_port.lr_probability((obs_tm[src, lig], obs_tm[tgt, rec]))
+    assert 0.05 < np.mean(obs > 0) < 0.95
+    a = engine.run_trimean(P, mat_max, obs_prob=obs, seed=9)["cellchat"]
+    b = engine.run_trimean(P, mat_max, obs_prob=obs, seed=9)["cellchat"]
+    assert np.array_equal(a, b)                                              # deterministic
+    assert np.all(a[obs == 0] == P)                                          # null score >= 0 always
+    h1 = engine.run_trimean(300, mat_max, obs_prob=obs, seed=9, perm_offset=0)["cellchat"]
+    h2 = engine.run_trimean(P - 300, mat_max, obs_prob=obs, seed=9, perm_offset=300)["cellchat"]
+    assert np.array_equal(h1 + h2, a)                                        # shards by global permutation id add up
+    few = engine.run_trimean(3, mat_max, obs_prob=obs, seed=9, return_cube=True)
+    perms = engine.philox_perms(N, 3, seed=9)
+    ref = c_oracle.trimean_cube(X, labels, L, perms.astype(np.int64), mat_max)
+    assert np.array_equal(few["cube"], ref) and np.mean(ref != 0) > 0.05
+    assert np.array_equal(few["cellchat"].astype(np.int64), numpy_port.counts_cellchat(ref, lig, rec, src, tgt, obs))
