@@ -15,6 +15,8 @@ obs = torch.ones(T, dtype=torch.float32).pin_memory()
 counts = torch.zeros(T, dtype=torch.int32, device="cuda")
 hc = torch.zeros(T, dtype=torch.int32).pin_memory()
 eng = E.Engine(0)
+if len(sys.argv) > 2:
+    eng.set_tuning(0, 0, int(sys.argv[2]))        # MiB of label slab per cell tile (default 64)
 def sync(): torch.cuda.synchronize()
 for it in range(4):
     ts = [time.perf_counter()]
