@@ -151,9 +151,9 @@ struct lrperm_engine {
     cudaStream_t copy_stream = nullptr;   // matrix uploads from pinned host memory (lrperm_set_matrix_csr) run here, unwaited
     cudaEvent_t ev_matrix = nullptr;      // recorded on copy_stream after the upload + packing
     bool matrix_pending = false;          // the engine stream has not waited for ev_matrix yet (validation deferred too)
-    // tile-wise upload: lrperm_set_matrix_csr submits the first cell tile only; the remaining tiles are submitted by
-    // the first call that consumes the matrix (AFTER the small uploads of set_labels / set_triples: the copy engine
-    // serves H2D copies in submission order), each followed on the copy stream by its packing and CSC sort
+    // tile-wise upload: lrperm_set_matrix_csr submits every cell tile to the copy stream, each followed there by its
+    // packing and CSC sort.  The copy engine serves H2D copies of all streams in submission order, so while the
+    // upload is pending the small tables of set_labels / set_triples / the chunk tables go through copy KERNELS
     const void* up_indices = nullptr;
     const void* up_data = nullptr;
     std::vector<int64_t> up_e;            // entry offset at every tile boundary [n_tiles + 1]
@@ -185,6 +185,8 @@ struct lrperm_engine {
     // order and the tile's gene-major copy occupies the same index range), so a tile can be sorted - and its chunks
     // run - while later tiles are still being uploaded
     int32_t csc_tile_cells = 0, n_tiles = 0, tiles_enqueued = 0, tiles_tabled = 0;
+    PinnedBuf up_pin;                     // pinned mirror of small pageable uploads made while a matrix upload is pending
+    size_t up_pin_off = 0;                // bump offset; reset by set_labels / set_triples (which end with a stream sync)
     PinnedBuf hist_pin;                   // pinned host [n_tiles][G] column counts per tile
     PinnedBuf table_pin;                  // pinned host mirror of the chunk table + tile_slot_ptr rows (read by copy_words_kernel)
     DevBuf csc_keys, csc_keys2, csc_payload, tile_hist, tile_slot_ptr;
@@ -323,10 +325,35 @@ int upload_pageable(lrperm_engine* h, void* dst, const void* src, size_t bytes) 
     return LRPERM_OK;
 }
 
+// Host -> device copy that bypasses the copy engine: while a pinned matrix upload is pending its tiles fill the H2D
+// queue (copies of all streams are served in submission order), and the label / triple tables of the calls that
+// follow would arrive only after the last tile.  A kernel reads them over PCIe instead - straight from the caller's
+// buffer when it is pinned, else from a pinned mirror filled here.
+int upload_by_kernel(lrperm_engine* h, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return LRPERM_OK;
+    const unsigned char* from = static_cast<const unsigned char*>(src);
+    if (!is_pinned_host(src) || (reinterpret_cast<uintptr_t>(src) & 3)) {
+        const size_t need = h->up_pin_off + ((bytes + 255) & ~(size_t)255);
+        if (need > h->up_pin.cap) {
+            // a retired block may still be read by queued kernels: PinnedBuf keeps it; start a fresh one
+            CK(h->up_pin.ensure(std::max(need, (size_t)(32u << 20))));
+            h->up_pin_off = 0;
+        }
+        unsigned char* pin = h->up_pin.as<unsigned char>() + h->up_pin_off;
+        memcpy(pin, src, bytes);
+        h->up_pin_off += (bytes + 255) & ~(size_t)255;
+        from = pin;
+    }
+    copy_bytes_kernel<<<grid_for((int64_t)(bytes >> 2) + 1, 256, h->sm_count * 4), 256, 0, st>>>(from, static_cast<unsigned char*>(dst), (int64_t)bytes);
+    CK_LAUNCH();
+    return LRPERM_OK;
+}
+
 // copy `bytes` from a host-or-device source into a device buffer on the engine stream
 int upload(lrperm_engine* h, DevBuf& dst, const void* src, size_t bytes, int on_device) {
     CK(dst.ensure(bytes));
     if (bytes == 0) return LRPERM_OK;
+    if (!on_device && h->matrix_pending && bytes <= (256u << 20)) return upload_by_kernel(h, dst.p, src, bytes, h->stream);
     if (!on_device && bytes >= (32u << 20) && !is_pinned_host(src)) return upload_pageable(h, dst.p, src, bytes);
     CK(cudaMemcpyAsync(dst.p, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     return LRPERM_OK;
@@ -1442,6 +1469,7 @@ void lrperm_destroy(lrperm_engine* h) {
     for (cudaEvent_t ev : h->ev_main_tile) cudaEventDestroy(ev);
     h->hist_pin.release();
     h->table_pin.release();
+    h->up_pin.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1529,10 +1557,9 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     h->N = n_cells; h->G = n_genes; h->nnz = nnz;
 
     if (!on_device && nnz > 0 && is_pinned_host(indptr) && is_pinned_host(indices) && is_pinned_host(data)) {
-        // Pinned host buffers: nothing waits here.  The row pointers and the FIRST cell tile go to the copy stream now,
-        // the other tiles when the matrix is first consumed (submit_pending_tiles); every tile is packed and its CSC
-        // copy sorted on the copy stream right behind its transfer, so lrperm_run can start the first batch on tile 0
-        // while tiles 1.. are still crossing PCIe.  The buffers must stay valid and unchanged until that call returns
+        // Pinned host buffers: nothing waits here.  The row pointers and every cell tile go to the copy stream now; every
+        // tile is packed and its CSC copy sorted on that stream right behind its transfer, so lrperm_run can start the
+        // first batch on tile 0 while tiles 1.. are still crossing PCIe.  The buffers must stay valid and unchanged until that call returns
         // (as with cudaMemcpyAsync).  Column-range validation is reported by the consuming call.
         cudaStream_t sC = h->copy_stream;
         h->staged = false;
@@ -1567,7 +1594,8 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
         CK_LAUNCH();
         h->matrix_pending = true;
         h->have_matrix = true;
-        return submit_tiles(h, 1);                     // the first tile now
+        // all tiles now: the calls that follow do not use the copy engine while this upload is pending (upload_by_kernel)
+        return submit_tiles(h, -1);
     }
 
     CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
@@ -1780,6 +1808,7 @@ int lrperm_set_labels(lrperm_engine* h, const int32_t* labels, int32_t n_cluster
     StageTimer timer("set_labels");
     DeviceGuard guard(h->device);
     h->have_labels = false;
+    h->up_pin_off = 0;
     if (!h->have_matrix) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: call lrperm_set_matrix_csr first");
     if (!labels || n_clusters <= 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_labels: NULL labels or n_clusters <= 0");
     const int64_t N = h->N;
@@ -1871,6 +1900,7 @@ int lrperm_set_triples(lrperm_engine* h, int64_t n_triples, const int32_t* ligan
     StageTimer timer("set_triples");
     DeviceGuard guard(h->device);
     h->have_triples = false;
+    h->up_pin_off = 0;
     if (!h->have_matrix || !h->have_labels) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_triples: set the matrix and labels first");
     if (n_triples < 0) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_triples: n_triples < 0");
     if (n_triples > 0 && (!ligand_idx || !receptor_idx || !source_idx || !target_idx))
@@ -1888,10 +1918,11 @@ int lrperm_set_triples(lrperm_engine* h, int64_t n_triples, const int32_t* ligan
         if (!on_device) {
             CK(h->tmp_a.ensure(sizeof(int32_t) * T * 4));
             int32_t* base = h->tmp_a.as<int32_t>();
-            CK(cudaMemcpyAsync(base, ligand_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemcpyAsync(base + T, receptor_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemcpyAsync(base + 2 * T, source_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemcpyAsync(base + 3 * T, target_idx, 4 * T, cudaMemcpyHostToDevice, h->stream));
+            const int32_t* srcs[4] = {ligand_idx, receptor_idx, source_idx, target_idx};
+            for (int k = 0; k < 4; ++k) {
+                if (h->matrix_pending) { if ((rc = upload_by_kernel(h, base + (size_t)k * T, srcs[k], 4 * T, h->stream))) return rc; }
+                else CK(cudaMemcpyAsync(base + (size_t)k * T, srcs[k], 4 * T, cudaMemcpyHostToDevice, h->stream));
+            }
             dl = base; dr = base + T; dsrc = base + 2 * T; dt = base + 3 * T;
         }
         build_rows_kernel<<<grid_for((int64_t)T, 256, 1 << 30), 256, 0, h->stream>>>(

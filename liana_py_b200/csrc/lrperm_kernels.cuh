@@ -272,6 +272,14 @@ __global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* 
 __global__ void copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
+// the same for any byte count (4-byte aligned pointers): whole words, then the tail bytes
+__global__ void copy_bytes_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int64_t n) {
+    const int64_t words = n >> 2;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[(words << 2) + threadIdx.x] = src[(words << 2) + threadIdx.x];
+}
 
 // stored-entry counts per (cluster, gene): props = count / n_c  (_common.py:41-42)
 __global__ void stored_counts_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs,
