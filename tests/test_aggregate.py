@@ -87,3 +87,21 @@ def test_rra_properties():
     once = rank_aggregate_scores(df, {"A": ("expr_prod", False)}, "mean")
     twice = rank_aggregate_scores(df, {"A": ("expr_prod", False), "B": ("expr_prod", False)}, "mean")
     assert np.array_equal(np.argsort(once), np.argsort(twice)[::-1])
+
+
+def test_method_registry_matches_reference_records():
+    """`li.mt.show_methods()` / `get_method_scores()` (`liana/method/__init__.py:17-32`) and the MethodMeta records of the
+    three permutation methods (`sc/_cellphonedb.py:34-50`, `_geometric_mean.py:27-41`, `_cellchat.py:36-53`)."""
+    import liana_py_b200 as li
+    meta = li.mt.show_methods()
+    assert list(meta["Method Name"]) == ["CellPhoneDB", "Connectome", "log2FC", "NATMI", "SingleCellSignalR",
+                                         "Rank_Aggregate", "Geometric Mean", "CellChat"]
+    scores = li.mt.get_method_scores()
+    assert scores["cellphone_pvals"] is True and scores["lr_means"] is False and scores["cellchat_pvals"] is True
+    assert scores["lr_probs"] is False and scores["magnitude_rank"] is True
+    cc = li.mt.cellchat
+    assert (cc.complex_cols, cc.add_cols, cc.magnitude, cc.specificity, cc.permute, cc._kh) == (
+        ["ligand_trimean", "receptor_trimean"], ["mat_max"], "lr_probs", "cellchat_pvals", True, 0.5)
+    cp = li.mt.cellphonedb
+    assert (cp.complex_cols, cp.add_cols, cp.magnitude, cp.specificity, cp.magnitude_ascending, cp.specificity_ascending) == (
+        ["ligand_means", "receptor_means"], [], "lr_means", "cellphone_pvals", False, True)
