@@ -281,7 +281,7 @@ def run_gpu(args):
         roofline["smem_pipe"] = {"updates_per_clk_per_sm": upd_clk_sm, "wavefronts_per_update_warp": wf_per_update_warp,
                                  "peak_updates_per_clk_per_sm": 32.0 / wf_per_update_warp,
                                  "frac": upd_clk_sm * wf_per_update_warp / 32.0,
-                                 "ncu_l1tex_lsuin_pct": 79.7, "ncu_source": "profiles/r01_ncu_full_c3_fast2.md"}
+                                 "ncu_l1tex_lsuin_pct": 80.8, "ncu_source": "profiles/r01_ncu_full_c3_fast2_final.md"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
