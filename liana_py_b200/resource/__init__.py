@@ -1,9 +1,9 @@
 """Ligand-receptor resources.
 
-Only the `consensus` table is bundled (``consensus.csv``: the `resource == 'consensus'` rows of the
-reference's ``liana/resource/omni_resource.csv`` reduced to gene symbols, derived by
-``scripts/extract_resource.py``).  Other resources are passed as a DataFrame via ``resource=``
-or as ``interactions=[(ligand, receptor), ...]`` - same contract as
+The 17 tables of the reference's ``liana/resource/omni_resource.csv`` (consensus, mouseconsensus, cellphonedb,
+cellchatdb, ...) are bundled as gene-symbol CSVs (data, derived by ``scripts/extract_resource.py`` the way
+``liana/resource/select_resource.py:9-40`` selects them).  Any other resource is passed as a DataFrame via
+``resource=`` or as ``interactions=[(ligand, receptor), ...]`` - same contract as
 ``liana/resource/select_resource.py:57-82``.
 """
 from __future__ import annotations

@@ -105,3 +105,29 @@ def test_method_registry_matches_reference_records():
     cp = li.mt.cellphonedb
     assert (cp.complex_cols, cp.add_cols, cp.magnitude, cp.specificity, cp.magnitude_ascending, cp.specificity_ascending) == (
         ["ligand_means", "receptor_means"], [], "lr_means", "cellphone_pvals", False, True)
+
+
+def test_bundled_resources_match_reference_tables():
+    """Every resource of the reference's `omni_resource.csv` is bundled as a gene-symbol table (data derived by
+    scripts/extract_resource.py) and selected the way `liana/resource/select_resource.py:9-40` selects it
+    (case-insensitive name, ValueError for unknown names).  The row-by-row comparison with the reference's file runs
+    only where /root/reference exists (the build container)."""
+    import os
+    import pandas as pd
+    import pytest
+    import liana_py_b200 as li
+    names = li.rs.show_resources()
+    assert "consensus" in names and "cellphonedb" in names and "mouseconsensus" in names and len(names) == 17
+    assert li.rs.select_resource("Consensus").shape == (4624, 2)
+    with pytest.raises(ValueError, match="not found"):
+        li.rs.select_resource("nope")
+    src = "/root/reference/liana/resource/omni_resource.csv"
+    if os.path.exists(src):
+        omni = pd.read_csv(src, index_col=False)
+        assert sorted(omni["resource"].unique()) == names
+        for name in names:
+            ref = omni[omni["resource"] == name][["source_genesymbol", "target_genesymbol"]]
+            got = li.rs.select_resource(name)
+            assert list(got.columns) == ["ligand", "receptor"]
+            assert (got["ligand"].values == ref["source_genesymbol"].values).all()
+            assert (got["receptor"].values == ref["target_genesymbol"].values).all()

@@ -210,7 +210,7 @@ def test_single_non_permutation_methods_run():
 
 
 # ---- the optional arguments of the call signature, against the reference's frames ---------------------------
-@pytest.mark.parametrize("name", ["pairs", "interactions", "resource", "raw", "layer"])
+@pytest.mark.parametrize("name", ["pairs", "interactions", "resource", "raw", "layer", "resname"])
 def test_call_signature_variants_identical_to_reference(name):
     from variants import variant_inputs
     adata, variants = variant_inputs()

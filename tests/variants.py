@@ -33,6 +33,7 @@ def variant_inputs():
         resource=dict(resource=custom, use_raw=False),
         raw=dict(use_raw=True),
         layer=dict(layer="sqrt", use_raw=False),
+        resname=dict(resource_name="CellPhoneDB", use_raw=False),     # another bundled resource, case-insensitive name
     )
 
 
