@@ -107,6 +107,11 @@ int lrperm_commit_matrix(lrperm_engine *h, const int32_t *col_map, int64_t n_gen
  * in those rows: the inputs of CellChat's `mat_max = adata.X.max()` (liana/method/sc/_liana_pipe.py:143-146;
  * the implicit zeros take part in that maximum, the caller adds them).  Valid between stage and the next stage. */
 int lrperm_staged_max(lrperm_engine *h, float *max_stored, int64_t *n_stored);
+/* Per-cluster sum x and sum x^2 (float64) over ALL stored entries of the staged matrix, every gene: the inputs of
+ * scSeqComm's `_cluster_stats` (cluster mean and standard deviation of the prepared matrix BEFORE the resource gene
+ * subset, liana/method/sc/_liana_pipe.py:157-158, 466-476).  row_label[r] (host, int32, one per staged row) = cluster
+ * of the row, -1 = row not kept.  Valid between stage and the next stage. */
+int lrperm_staged_cluster_stats(lrperm_engine *h, const int32_t *row_label, int32_t n_clusters, double *sum_x, double *sum_sq);
 
 /* Cluster code per cell (codes of obs['@label'] in .cat.categories order, _get_mean_perms.py:47-52). */
 int lrperm_set_labels(lrperm_engine *h, const int32_t *labels, int32_t n_clusters, int on_device);

@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
     "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
-    "lrperm_argsort",
+    "lrperm_argsort", "lrperm_staged_cluster_stats",
 )
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library():
     lib.lrperm_rank_average.argtypes = [vp, i64, vp, C.c_int, vp, C.c_int]
     lib.lrperm_rra.argtypes = [vp, i64, i32, vp, vp, vp, C.c_int]
     lib.lrperm_argsort.argtypes = [vp, i64, vp, C.c_int, vp, C.c_int]
+    lib.lrperm_staged_cluster_stats.argtypes = [vp, vp, i32, vp, vp]
     lib.lrperm_resolve_triples.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.c_int, vp, C.c_double, vp, C.c_int, C.c_int, vp]
     lib.lrperm_fetch_triples.argtypes = [vp] + [vp] * 10
     _lib = lib
@@ -202,6 +203,14 @@ class Engine:
         mx, cnt = C.c_float(0.0), C.c_int64(0)
         self._check(self._lib.lrperm_staged_max(self._h, C.byref(mx), C.byref(cnt)))
         return np.float32(mx.value), int(cnt.value)
+
+    def staged_cluster_stats(self, row_label, n_clusters: int):
+        """(sum_x, sum_sq) float64 [L] over all stored entries of the staged matrix per cluster (row_label -1 = dropped)."""
+        lab = np.ascontiguousarray(row_label, dtype=np.int32)
+        sx, sq = np.zeros(n_clusters, dtype=np.float64), np.zeros(n_clusters, dtype=np.float64)
+        self._check(self._lib.lrperm_staged_cluster_stats(self._h, C.c_void_p(lab.ctypes.data), int(n_clusters),
+                                                          C.c_void_p(sx.ctypes.data), C.c_void_p(sq.ctypes.data)))
+        return sx, sq
 
     def commit_matrix(self, col_map, n_genes_out: int, n_cells_out: int):
         """Make the staged matrix the engine's matrix: rows flagged in row_keep, columns with col_map >= 0."""

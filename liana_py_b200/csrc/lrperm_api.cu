@@ -1721,6 +1721,29 @@ int lrperm_staged_max(lrperm_engine* h, float* max_stored, int64_t* n_stored) {
     return LRPERM_OK;
 }
 
+int lrperm_staged_cluster_stats(lrperm_engine* h, const int32_t* row_label, int32_t n_clusters, double* sum_x, double* sum_sq) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->staged) return h->fail(LRPERM_ERR_INVALID, "lrperm_staged_cluster_stats: call lrperm_stage_matrix_csr first");
+    if (!row_label || n_clusters <= 0 || n_clusters > 2048 || !sum_x || !sum_sq)
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_staged_cluster_stats: bad arguments (at most 2048 clusters)");
+    int rc;
+    const size_t L = (size_t)n_clusters;
+    if ((rc = upload(h, h->tmp_d, row_label, sizeof(int32_t) * (size_t)std::max<int64_t>(h->st_N, 1), 0))) return rc;
+    CK(h->small_b.ensure(sizeof(double) * 2 * L));
+    CK(cudaMemsetAsync(h->small_b.p, 0, sizeof(double) * 2 * L, h->stream));
+    if (h->st_N > 0 && h->st_nnz > 0) {
+        staged_cluster_stats_kernel<<<grid_for(h->st_N * 32, 256, h->sm_count * 8), 256, sizeof(double) * 2 * L, h->stream>>>(
+            h->st_indptr.as<int32_t>(), h->st_data.as<float>(), h->tmp_d.as<int32_t>(), (int32_t)h->st_N, n_clusters,
+            h->small_b.as<double>(), h->small_b.as<double>() + L);
+        CK_LAUNCH();
+    }
+    if ((rc = download(h, sum_x, h->small_b.p, sizeof(double) * L, 0))) return rc;
+    if ((rc = download(h, sum_sq, h->small_b.as<double>() + L, sizeof(double) * L, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
 int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_genes_out) {
     if (!h) return LRPERM_ERR_INVALID;
     StageTimer timer("commit_matrix");

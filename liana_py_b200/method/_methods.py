@@ -126,7 +126,8 @@ class Method(MethodMeta):
         if supp_columns:
             raise NotImplementedError("supp_columns are outside the scope of the permutation engine")
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
-                           use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in self.add_cols)
+                           use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in self.add_cols,
+                           want_cluster_stats="ligand_cdf" in self.add_cols)
         liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
                                perm_source, order, gmean_mode, dist)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \

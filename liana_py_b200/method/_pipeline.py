@@ -99,6 +99,21 @@ class PipelineState:
             self._cache[key] = (tri, base_frame(self, tri, stat))
         return self._cache[key]
 
+    def gene_cdf(self) -> np.ndarray:
+        """scSeqComm's `_gene_cdf` per (cluster, gene), float64 [L,G] (`_liana_pipe.py:479-483`): P(N(cluster mean,
+        cluster std / sqrt(n_c)) <= gene mean), 0 where the gene's cluster mean is 0."""
+        if "cdf" not in self._cache:
+            from scipy.stats import norm
+            if self.prep.cluster_stats is None:
+                raise RuntimeError("the input was prepared without cluster statistics (internal error)")
+            mean, std = self.prep.cluster_stats
+            scale = std / np.sqrt(self.sizes.astype(np.float64))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                p = norm.cdf(self.means, loc=mean[:, None], scale=scale[:, None])
+            p[self.means == 0] = 0
+            self._cache["cdf"] = p
+        return self._cache["cdf"]
+
     def trimean(self) -> np.ndarray:
         """Observed cluster trimeans of X / mat_max, float64 [L,G] (`_liana_pipe.py:307-308, 462-465`)."""
         if "trimean" not in self._cache:
@@ -164,7 +179,7 @@ class PipelineState:
 
 
 def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells, use_raw, layer,
-            verbose, device=0, base=float(np.e), want_max=False) -> PipelineState:
+            verbose, device=0, base=float(np.e), want_max=False, want_cluster_stats=False) -> PipelineState:
     res = handle_resource(interactions=interactions, resource=resource, resource_name=resource_name, verbose=verbose)
     groupby_subset = None
     if groupby_pairs is not None:
@@ -173,7 +188,8 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
         groupby_subset = np.union1d(groupby_pairs[K.SOURCE].unique(), groupby_pairs[K.TARGET].unique())
     eng = get_engine(device)
     prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, engine=eng, groupby_subset=groupby_subset,
-                              use_raw=use_raw, layer=layer, verbose=verbose, want_max=want_max)
+                              use_raw=use_raw, layer=layer, verbose=verbose, want_max=want_max,
+                              want_cluster_stats=want_cluster_stats)
     tables, all_entities = _cached_tables(res, prep.var_names)
     _pre.assert_covered(all_entities, prep.var_names, verbose=verbose)
     # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`): a column map for the
@@ -267,6 +283,10 @@ def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame
             frame[col] = np.float32(state.prep.mat_mean)
         elif col == K.MAT_MAX:
             frame[col] = np.float32(state.prep.mat_max)
+        elif col == "ligand_cdf":
+            frame[col] = state.gene_cdf()[tri.src, tri.lig_gene]
+        elif col == "receptor_cdf":
+            frame[col] = state.gene_cdf()[tri.tgt, tri.rec_gene]
         else:
             raise NotImplementedError(f"column `{col}` is outside the scope of the permutation engine")
     return frame

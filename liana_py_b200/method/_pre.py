@@ -36,6 +36,7 @@ class PreparedInput:
     n_cells: int                  # kept cells
     mat_mean: float = 0.0         # mean over ALL entries of the prepared matrix (SingleCellSignalR, `_liana_pipe.py:139-140`)
     mat_max: np.float32 | None = None   # `adata.X.max()` of the prepared matrix (CellChat, `_liana_pipe.py:143-146`)
+    cluster_stats: tuple | None = None  # (mean [L], std [L]) over ALL entries of a cluster's rows (scSeqComm, `:466-476`)
 
 
 def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False):
@@ -80,7 +81,7 @@ def _make_unique(names: pd.Index) -> pd.Index:
 
 
 def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_raw=False, layer=None,
-                  complex_sep="_", verbose=False, want_max=False) -> PreparedInput:
+                  complex_sep="_", verbose=False, want_max=False, want_cluster_stats=False) -> PreparedInput:
     """Same checks, order and exception types as `prep_check_adata` (`_pre.py:65-169`); the passes over the
     matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU."""
     if hasattr(adata, "mod"):
@@ -157,7 +158,18 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
         # scipy's sparse .max(): the implicit zeros take part (any prepared matrix that is not fully dense has one)
         stored_max, n_stored = engine.staged_max()
         mat_max = stored_max if (n_stored >= n_all and n_stored > 0) else np.float32(max(stored_max, np.float32(0)))
-    return PreparedInput(mat_max=mat_max, var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
+    cluster_stats = None
+    if want_cluster_stats:
+        # `temp.X.mean()` / `np.std(temp.X.toarray())` per label over the prepared matrix (all non-empty genes, zeros
+        # included): from per-cluster sum x, sum x^2 of the staged matrix
+        L = len(kept_categories)
+        row_label = np.full(X.shape[0], -1, dtype=np.int32)
+        row_label[rows] = new_codes
+        sx, sq = engine.staged_cluster_stats(row_label, L)
+        n_entries = np.bincount(new_codes, minlength=L).astype(np.float64) * len(keep_cols)
+        mean = sx / n_entries
+        cluster_stats = (mean, np.sqrt(np.maximum(sq / n_entries - mean ** 2, 0.0)))
+    return PreparedInput(mat_max=mat_max, cluster_stats=cluster_stats, var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
                          labels=new_codes, categories=kept_categories, obs_index=obs.index[rows], n_cells=len(rows),
                          mat_mean=float(stats["kept_total"] / n_all) if n_all else 0.0)
 

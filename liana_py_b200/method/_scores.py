@@ -1,5 +1,6 @@
 """The non-permutation methods the default `li.mt.rank_aggregate` ranks next to CellPhoneDB's
-permutation p-values: Connectome, log2FC, NATMI, SingleCellSignalR.
+permutation p-values: Connectome, log2FC, NATMI, SingleCellSignalR; and scSeqComm's inter-cellular score
+(`liana/method/sc/_scseqcomm.py:4-21`).
 
 Same score formulas, column names and MethodMeta records as the reference
 (`liana/method/sc/_connectome.py:5-22`, `_logfc.py:4-6`, `_natmi.py:4-17`,
@@ -57,7 +58,17 @@ _singlecellsignalr = MethodMeta(method_name="SingleCellSignalR", complex_cols=[_
                                 specificity_ascending=None, permute=False,
                                 reference="Cabello-Aguilar et al., 2020. Nucleic Acids Research 48(10).")
 
+def _inter_score(x):
+    return np.minimum(x["ligand_cdf"].values, x["receptor_cdf"].values), None
+
+
+_scseqcomm = MethodMeta(method_name="scSeqComm", complex_cols=[_LM, _RM], add_cols=["ligand_cdf", "receptor_cdf"],
+                        fun=_inter_score, magnitude="inter_score", magnitude_ascending=False, specificity=None,
+                        specificity_ascending=None, permute=False,
+                        reference="Baruzzo et al., 2022. Bioinformatics 38(7).")
+
 connectome = Method(_method=_connectome)
+scseqcomm = Method(_method=_scseqcomm)
 logfc = Method(_method=_logfc)
 natmi = Method(_method=_natmi)
 singlecellsignalr = Method(_method=_singlecellsignalr)

@@ -171,6 +171,7 @@ def load_reference():
     ns.logfc_mod = importlib.import_module("liana.method.sc._logfc")
     ns.natmi_mod = importlib.import_module("liana.method.sc._natmi")
     ns.sca_mod = importlib.import_module("liana.method.sc._singlecellsignalr")
+    ns.scseqcomm = importlib.import_module("liana.method.sc._scseqcomm").scseqcomm
     ns.cellchat_mod = importlib.import_module("liana.method.sc._cellchat")
     ns.cellchat = ns.cellchat_mod.cellchat
     # the default consensus of `liana/method/__init__.py:13-14` (that __init__ pulls in the spatial stack)

@@ -221,6 +221,17 @@ def save_cellchat(ref):
     save_cellchat_case("ragged90", ragged_case(), "cluster", 16, 5, 0.05, ref)
 
 
+def save_scseqcomm(ref):
+    """li.mt.scseqcomm of the reference (non-permutation: cluster mean / std of the whole prepared matrix, normal cdf
+    of the gene means, `liana/method/sc/_scseqcomm.py`, `_liana_pipe.py:466-499`) on three inputs -> final frames."""
+    cases = {"small300": (make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12), 0.1),
+             "dense700": (dense_case(), 0.1), "ragged90": (ragged_case(), 0.05)}
+    for name, (adata, ep) in cases.items():
+        res = ref.scseqcomm(adata.copy(), groupby="cluster", use_raw=False, expr_prop=ep, inplace=False, verbose=False)
+        res.to_csv(os.path.join(OUT, f"{name}_scseqcomm.csv.gz"), index=False)
+        print(f"{name} scseqcomm: {res.shape}, mean inter_score {res['inter_score'].mean():.6f}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
@@ -230,8 +241,12 @@ def main():
     if "--cellchat-only" in sys.argv:
         save_cellchat(ref)
         return
+    if "--scseqcomm-only" in sys.argv:
+        save_scseqcomm(ref)
+        return
     save_variants(ref)
     save_cellchat(ref)
+    save_scseqcomm(ref)
     save_reference_csv_fixture()
     save_rank_aggregate("toy700", make_synthetic_adata(700, 765, 10, density=0.10), "cluster", 100, 1337, 0.1, ref)
     small = make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12)

@@ -95,7 +95,7 @@ def test_method_registry_matches_reference_records():
     import liana_py_b200 as li
     meta = li.mt.show_methods()
     assert list(meta["Method Name"]) == ["CellPhoneDB", "Connectome", "log2FC", "NATMI", "SingleCellSignalR",
-                                         "Rank_Aggregate", "Geometric Mean", "CellChat"]
+                                         "Rank_Aggregate", "Geometric Mean", "scSeqComm", "CellChat"]
     scores = li.mt.get_method_scores()
     assert scores["cellphone_pvals"] is True and scores["lr_means"] is False and scores["cellchat_pvals"] is True
     assert scores["lr_probs"] is False and scores["magnitude_rank"] is True

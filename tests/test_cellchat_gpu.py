@@ -205,3 +205,24 @@ def test_cellchat_mid_size_properties(engine):
     ref = c_oracle.trimean_cube(X, labels, L, perms.astype(np.int64), mat_max)
     assert np.array_equal(few["cube"], ref) and np.mean(ref != 0) > 0.05
     assert np.array_equal(few["cellchat"].astype(np.int64), numpy_port.counts_cellchat(ref, lig, rec, src, tgt, obs))
+
+
+@pytest.mark.parametrize("name", ["small300", "dense700", "ragged90"])
+def test_scseqcomm_frame_matches_reference(name):
+    """li.mt.scseqcomm (non-permutation; cluster statistics of the whole prepared matrix from the staged upload,
+    `lrperm_staged_cluster_stats`) against the reference's own frame.  The reference computes the cluster mean / std
+    in float32 (`np.std` of the densified float32 rows), here they are float64 sums: the normal cdf agrees to ~1e-5."""
+    adata, _, _, ep = _load_input(name)
+    res = li.mt.scseqcomm(adata, groupby="cluster", use_raw=False, expr_prop=ep, inplace=False)
+    gold = pd.read_csv(os.path.join(GOLDEN, f"{name}_scseqcomm.csv.gz"), float_precision="round_trip")
+    assert list(res.columns) == list(gold.columns)
+    a = res.sort_values(KEY).reset_index(drop=True)
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in KEY + ["ligand", "receptor"]:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+    for c in ["ligand_means", "receptor_means"]:
+        assert np.array_equal(a[c].values, b[c].values.astype(np.float32)), c
+    for c in ["ligand_cdf", "receptor_cdf", "inter_score"]:
+        np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-4, atol=2e-5, err_msg=c)
+    assert np.all(np.diff(res["inter_score"].values) <= 0)
