@@ -1733,9 +1733,13 @@ int lrperm_staged_cluster_stats(lrperm_engine* h, const int32_t* row_label, int3
     CK(h->small_b.ensure(sizeof(double) * 2 * L));
     CK(cudaMemsetAsync(h->small_b.p, 0, sizeof(double) * 2 * L, h->stream));
     if (h->st_N > 0 && h->st_nnz > 0) {
-        staged_cluster_stats_kernel<<<grid_for(h->st_N * 32, 256, h->sm_count * 8), 256, sizeof(double) * 2 * L, h->stream>>>(
-            h->st_indptr.as<int32_t>(), h->st_data.as<float>(), h->tmp_d.as<int32_t>(), (int32_t)h->st_N, n_clusters,
-            h->small_b.as<double>(), h->small_b.as<double>() + L);
+        const int n_blocks = (int)std::min<int64_t>(h->st_N, (int64_t)h->sm_count * 16);
+        CK(h->tmp_a.ensure(sizeof(double) * 2 * L * (size_t)n_blocks));
+        staged_cluster_stats_kernel<<<n_blocks, 32, sizeof(double) * 2 * L, h->stream>>>(
+            h->st_indptr.as<int32_t>(), h->st_data.as<float>(), h->tmp_d.as<int32_t>(), (int32_t)h->st_N, n_clusters, h->tmp_a.as<double>());
+        CK_LAUNCH();
+        staged_cluster_stats_reduce_kernel<<<grid_for((int64_t)(2 * L), 128, 1 << 30), 128, 0, h->stream>>>(
+            h->tmp_a.as<double>(), n_blocks, (int32_t)(2 * L), h->small_b.as<double>());
         CK_LAUNCH();
     }
     if ((rc = download(h, sum_x, h->small_b.p, sizeof(double) * L, 0))) return rc;

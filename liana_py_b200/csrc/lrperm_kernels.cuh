@@ -170,17 +170,17 @@ __global__ void stage_max_kernel(const int32_t* __restrict__ indptr, const float
 
 // Per-cluster sum x and sum x^2 over ALL stored entries of the staged matrix (every gene, before the resource subset):
 // the cluster mean / standard deviation of scSeqComm's `_cluster_stats` (liana/method/sc/_liana_pipe.py:466-476).
-// row_label[r] = cluster of staged row r, -1 = row not kept.  float64, block-private shared accumulators.
-__global__ void staged_cluster_stats_kernel(const int32_t* __restrict__ indptr, const float* __restrict__ data,
-                                            const int32_t* __restrict__ row_label, int32_t N, int32_t L,
-                                            double* __restrict__ sum_x, double* __restrict__ sum_sq) {
+// row_label[r] = cluster of staged row r, -1 = row not kept.  float64 and DETERMINISTIC: one warp per CTA walks its
+// rows in a fixed order into private shared accumulators (no atomics), the per-CTA partials are summed in CTA order.
+__global__ void __launch_bounds__(32)
+staged_cluster_stats_kernel(const int32_t* __restrict__ indptr, const float* __restrict__ data,
+                            const int32_t* __restrict__ row_label, int32_t N, int32_t L,
+                            double* __restrict__ partial /*[gridDim.x][2 L]*/) {
     extern __shared__ double cs_smem[];          // [2][L]
-    for (int c = threadIdx.x; c < 2 * L; c += blockDim.x) cs_smem[c] = 0.0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < N; r += nwarps) {
+    const int lane = threadIdx.x;
+    for (int c = lane; c < 2 * L; c += 32) cs_smem[c] = 0.0;
+    __syncwarp();
+    for (int r = blockIdx.x; r < N; r += gridDim.x) {
         const int c = row_label[r];
         if (c < 0 || c >= L) continue;
         const int s = indptr[r], e = indptr[r + 1];
@@ -188,13 +188,20 @@ __global__ void staged_cluster_stats_kernel(const int32_t* __restrict__ indptr, 
         for (int o = s + lane; o < e; o += 32) { const double x = (double)data[o]; a += x; b += x * x; }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
-        if (lane == 0) { atomicAdd(&cs_smem[c], a); atomicAdd(&cs_smem[L + c], b); }
+        if (lane == 0) { cs_smem[c] += a; cs_smem[L + c] += b; }
+        __syncwarp();
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < L; c += blockDim.x) {
-        if (cs_smem[c] != 0.0) atomicAdd(&sum_x[c], cs_smem[c]);
-        if (cs_smem[L + c] != 0.0) atomicAdd(&sum_sq[c], cs_smem[L + c]);
-    }
+    __syncwarp();
+    for (int c = lane; c < 2 * L; c += 32) partial[(int64_t)blockIdx.x * 2 * L + c] = cs_smem[c];
+}
+
+__global__ void staged_cluster_stats_reduce_kernel(const double* __restrict__ partial, int32_t n_blocks, int32_t L2,
+                                                   double* __restrict__ out /*[2 L]*/) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= L2) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * L2 + c];
+    out[c] = s;
 }
 
 // entries of every KEPT row that survive the column map -> counts[new_row]

@@ -226,3 +226,26 @@ def test_scseqcomm_frame_matches_reference(name):
     for c in ["ligand_cdf", "receptor_cdf", "inter_score"]:
         np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-4, atol=2e-5, err_msg=c)
     assert np.all(np.diff(res["inter_score"].values) <= 0)
+
+
+@pytest.mark.parametrize("method", ["cellchat", "scseqcomm", "rank_aggregate"])
+def test_by_sample_of_other_methods_matches_per_sample_calls(method):
+    """`.by_sample` (`liana/method/sc/_Method.py:92-159`) is inherited by every method: the concatenated frame must be
+    the per-sample calls in sample-category order (CellChat needs mat_max per sample, scSeqComm the per-sample
+    cluster statistics of the staged matrix)."""
+    adata, P, seed, ep = _load_input("dense700")
+    rng = np.random.default_rng(1)
+    adata.obs["sample"] = pd.Categorical(rng.choice(["s1", "s2", "s3"], size=adata.shape[0]))
+    fn = getattr(li.mt, method)
+    kw = dict(groupby="cluster", use_raw=False, expr_prop=ep, n_perms=40, seed=seed)
+    res = fn.by_sample(adata, "sample", inplace=False, **kw)
+    assert res.columns[0] == "sample" and list(dict.fromkeys(res["sample"])) == ["s1", "s2", "s3"]
+    for s in ["s1", "s2", "s3"]:
+        one = fn(adata[np.asarray(adata.obs["sample"] == s)].copy(), inplace=False, **kw)
+        got = res[res["sample"] == s].drop(columns="sample")
+        a = got.sort_values(KEY).reset_index(drop=True)
+        b = one.sort_values(KEY).reset_index(drop=True)
+        assert list(a.columns) == list(b.columns) and len(a) == len(b)
+        for c in a.columns:
+            if a[c].dtype.kind == "f":
+                assert np.array_equal(a[c].values, b[c].values, equal_nan=True), (s, c)
