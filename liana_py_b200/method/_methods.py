@@ -69,8 +69,8 @@ class MethodMeta:
     def by_sample(self, adata, sample_key: str, key_added: str = K.Keys.uns_key, inplace: bool = V.inplace,
                   verbose=V.verbose, **kwargs):
         """Run the method per sample (`_Method.py:92-159`).  Samples are independent; with a
-        DistContext (kwarg `dist`) whole samples are sharded over ranks, longest first, and the
-        per-sample frames are gathered - no data-path collective."""
+        DistContext (kwarg `dist`) contiguous blocks of samples are sharded over ranks and one finished
+        frame per rank is gathered - no data-path collective."""
         if sample_key not in adata.obs:
             raise ValueError(f"{sample_key} was not found in `adata.obs`.")
         if not isinstance(adata.obs[sample_key].dtype, pd.CategoricalDtype):
@@ -85,19 +85,19 @@ class MethodMeta:
         sharded = dist is not None and dist.world_size > 1
         for i in mine:
             temp = adata[sample_col == samples[i]].copy()
-            # across ranks the frames travel with integer code columns + their small name tables (a third of
-            # the bytes of the string frames) and are turned into names after the gather
-            results[samples[i]] = self.__call__(temp, inplace=False, verbose=full_verbose, _names=not sharded, **kwargs)
-        if sharded:
-            merged = {}
-            for part in dist.all_gather_objects(results):
-                merged.update(part)
-            results = {s: PL.materialise_names(tables, frame) for s, (frame, tables) in merged.items()}
+            results[samples[i]] = self.__call__(temp, inplace=False, verbose=full_verbose, **kwargs)
         frames = []
         for s in samples:                      # sample-category order, like the reference's concat
-            df = results[s]
-            df.insert(0, sample_key, s)
-            frames.append(df)
+            if s in results:
+                df = results[s]
+                df.insert(0, sample_key, s)
+                frames.append(df)
+        if sharded:
+            # every rank finishes its own block of samples (names, sample column, local concat: that is where the
+            # time goes - pandas over millions of rows) and ONE frame per rank travels; the blocks are contiguous in
+            # sample order (DistContext.sample_shard), so the rank frames concatenate without re-sorting
+            local = pd.concat(frames, ignore_index=True) if frames else None
+            frames = [p for p in dist.all_gather_objects(local) if p is not None]
         liana_res = pd.concat(frames, ignore_index=True)
         if inplace:
             adata.uns[key_added] = liana_res
