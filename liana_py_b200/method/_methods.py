@@ -78,6 +78,9 @@ class MethodMeta:
         full_verbose = verbose == 'full'
         samples = list(adata.obs[sample_key].cat.categories)
         dist: Optional[DistContext] = kwargs.pop("dist", None)
+        # engine-only option: gather=False leaves every rank with the frame of ITS block of samples (to be written out
+        # per rank); assembling one pandas frame of all samples on every rank costs far more than computing them
+        gather: bool = kwargs.pop("gather", True)
         sample_col = np.asarray(adata.obs[sample_key])
         sizes = [int((sample_col == s).sum()) for s in samples]
         mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
@@ -97,8 +100,8 @@ class MethodMeta:
             # time goes - pandas over millions of rows) and ONE frame per rank travels; the blocks are contiguous in
             # sample order (DistContext.sample_shard), so the rank frames concatenate without re-sorting
             local = pd.concat(frames, ignore_index=True) if frames else None
-            frames = [p for p in dist.all_gather_objects(local) if p is not None]
-        liana_res = pd.concat(frames, ignore_index=True)
+            frames = [p for p in dist.all_gather_objects(local) if p is not None] if gather else ([local] if local is not None else [])
+        liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0]
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res

@@ -51,12 +51,17 @@ else:
     X = sparse.vstack(mats).tocsr()
     obs = pd.DataFrame({"cluster": pd.Categorical([f"c{v:02d}" for v in np.concatenate(labs)]), "sample": pd.Categorical(samp)})
     adata = AnnDataLite(X=X, obs=obs, var=pd.DataFrame(index=pd.Index(genes)))
-    for it in range(2):
-        t0 = time.perf_counter()
-        res = li.mt.cellphonedb.by_sample(adata, sample_key="sample", groupby="cluster", use_raw=False, n_perms=1000,
-                                          inplace=False, device=local, dist=dist)
-        dt = time.perf_counter() - t0
-        if rank == 0:
-            print(f"c5 by_sample {S} samples x {N} cells, world {world}, call {it}: {dt:.2f} s, rows {len(res)}", flush=True)
+    for gather in ((True, False) if world > 1 else (True,)):
+        for it in range(2):
+            if world > 1:
+                td.barrier()
+            t0 = time.perf_counter()
+            res = li.mt.cellphonedb.by_sample(adata, sample_key="sample", groupby="cluster", use_raw=False, n_perms=1000,
+                                              inplace=False, device=local, dist=dist, **({} if world == 1 else {"gather": gather}))
+            if world > 1:
+                td.barrier()
+            dt = time.perf_counter() - t0
+            if rank == 0:
+                print(f"c5 by_sample {S} samples x {N} cells, world {world}, gather={gather}, call {it}: {dt:.2f} s, rows on rank 0 {len(res)}", flush=True)
 if world > 1:
     td.destroy_process_group()
