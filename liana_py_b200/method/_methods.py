@@ -101,7 +101,8 @@ class MethodMeta:
             # sample order (DistContext.sample_shard), so the rank frames concatenate without re-sorting
             local = pd.concat(frames, ignore_index=True) if frames else None
             frames = [p for p in dist.all_gather_objects(local) if p is not None] if gather else ([local] if local is not None else [])
-        liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0]
+        # a fresh RangeIndex like the reference's `concat(...).reset_index()` (`_Method.py:154-155`)
+        liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0].reset_index(drop=True)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
