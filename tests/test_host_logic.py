@@ -1,0 +1,101 @@
+"""CPU: the host logic of the drop-in's input contract (`method/_pre.py`, restating `prep_check_adata`,
+liana/method/_pipe_utils/_pre.py:65-169) with the engine stood in by SciPy (the three matrix statistics the device
+computes from the staged upload), checked against the reference's own `prep_check_adata` where /root/reference exists
+and against first principles everywhere."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy import sparse
+
+from liana_py_b200.method import _pre
+from liana_py_b200.testing._anndata_lite import AnnDataLite
+from liana_py_b200.testing._synth import make_synthetic_adata
+
+
+class SciPyStage:
+    """Stand-in of Engine.stage_matrix / staged_max / staged_cluster_stats (what the CUDA kernels compute)."""
+
+    def stage_matrix(self, X, row_keep=None):
+        self.X, self.keep = X.tocsr(), row_keep
+        rows = np.arange(X.shape[0]) if row_keep is None else np.flatnonzero(row_keep)
+        return dict(col_sums=np.asarray(X.astype(np.float64).sum(axis=0)).ravel(),
+                    kept_total=float(X[rows].astype(np.float64).sum()), n_nonfinite=int((~np.isfinite(X.data)).sum()),
+                    n_empty_rows=int((np.asarray(X.sum(axis=1)).ravel() == 0).sum()))
+
+    def staged_max(self):
+        rows = np.arange(self.X.shape[0]) if self.keep is None else np.flatnonzero(self.keep)
+        sub = self.X[rows]
+        return (np.float32(sub.data.max()) if sub.nnz else np.float32(-np.inf)), int(sub.nnz)
+
+    def staged_cluster_stats(self, row_label, L):
+        sx, sq = np.zeros(L), np.zeros(L)
+        for c in range(L):
+            d = self.X[np.flatnonzero(row_label == c)].data.astype(np.float64)
+            sx[c], sq[c] = d.sum(), (d * d).sum()
+        return sx, sq
+
+
+def _ragged():
+    rng = np.random.default_rng(3)
+    n, g = 120, 40
+    dense = (rng.random((n, g)) < 0.3) * rng.random((n, g))
+    dense[:, 7] = 0                                   # empty gene -> removed
+    dense[11] = 0                                     # empty cell -> kept
+    labels = np.array(["b"] * 50 + ["a"] * 40 + ["tiny"] * 3 + ["c"] * 27)
+    obs = pd.DataFrame({"cluster": pd.Categorical(labels, categories=["c", "a", "b", "tiny", "unused"])})
+    var = pd.DataFrame(index=pd.Index([f"g{(i * 7) % g:02d}" for i in range(g)]))     # unsorted names
+    return AnnDataLite(X=sparse.csr_matrix(dense.astype(np.float32)), obs=obs, var=var)
+
+
+def test_prepare_input_contract():
+    ad = _ragged()
+    prep = _pre.prepare_input(ad, "cluster", min_cells=5, engine=SciPyStage(), want_max=True, want_cluster_stats=True)
+    assert list(prep.categories) == ["c", "a", "b"]                        # category order, 'tiny' (< min_cells) and 'unused' dropped
+    assert prep.n_cells == 117 and len(prep.labels) == 117 and prep.labels.max() == 2
+    assert list(prep.var_names) == sorted(prep.var_names) and ad.var_names[7] not in prep.var_names and len(prep.var_names) == 39
+    kept = np.flatnonzero(np.asarray(ad.obs["cluster"]) != "tiny")
+    X = ad.X[kept]
+    assert np.isclose(prep.mat_mean, X.sum() / (117 * 39))
+    assert prep.mat_max == np.float32(X.max())
+    codes = prep.labels
+    for c in range(3):
+        rows = X[codes == c].toarray()[:, np.asarray(ad.X.sum(axis=0)).ravel() != 0]
+        assert np.isclose(prep.cluster_stats[0][c], rows.mean(), rtol=1e-12)
+        assert np.isclose(prep.cluster_stats[1][c], rows.std(), rtol=1e-9)
+    # groupby_subset keeps only the named clusters
+    sub = _pre.prepare_input(ad, "cluster", min_cells=5, engine=SciPyStage(), groupby_subset=["a", "c"])
+    assert list(sub.categories) == ["c", "a"] and sub.n_cells == 67
+
+
+def test_prepare_input_errors_match_reference_conventions():
+    ad = _ragged()
+    with pytest.raises(AssertionError):
+        _pre.prepare_input(ad, "nope", min_cells=5, engine=SciPyStage())
+    with pytest.raises(ValueError, match="raw"):
+        _pre.prepare_input(ad, "cluster", min_cells=5, engine=SciPyStage(), use_raw=True)
+    with pytest.raises(ValueError, match="layer"):
+        _pre.prepare_input(ad, "cluster", min_cells=5, engine=SciPyStage(), use_raw=True, layer="x")
+    bad = ad.copy()
+    bad.X = bad.X.copy()
+    bad.X.data[3] = np.nan
+    with pytest.raises(ValueError, match="non finite"):
+        _pre.prepare_input(bad, "cluster", min_cells=5, engine=SciPyStage())
+    with pytest.raises(ValueError, match="Too few features"):
+        _pre.assert_covered(np.array(["A", "B", "C"]), np.array(["X", "Y"]))
+    _pre.assert_covered(np.array(["A", "B"]), np.array(["A", "Y"]))       # half missing is allowed (0.98)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/liana"), reason="needs the reference tree (build container)")
+def test_prepare_input_equals_reference_prep_check_adata():
+    from oracle.ref_shim import load_reference
+    ref = load_reference()
+    for ad in (_ragged(), make_synthetic_adata(300, 400, 5, density=0.15, seed_data=11, seed_labels=12)):
+        out = ref.pre.prep_check_adata(adata=ad.copy(), groupby="cluster", min_cells=5, use_raw=False, layer=None, verbose=False)
+        prep = _pre.prepare_input(ad.copy(), "cluster", min_cells=5, engine=SciPyStage())
+        assert list(out.var_names) == list(prep.var_names)
+        assert list(out.obs["@label"].cat.categories) == list(prep.categories)
+        assert np.array_equal(np.asarray(out.obs["@label"].cat.codes), prep.labels)
+        assert out.shape == (prep.n_cells, len(prep.var_names))
+        assert np.isclose(float(np.mean(out.X, dtype="float32")), prep.mat_mean, rtol=1e-5)
