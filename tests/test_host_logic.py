@@ -61,7 +61,7 @@ def test_prepare_input_contract():
     assert prep.mat_max == np.float32(X.max())
     codes = prep.labels
     for c in range(3):
-        rows = X[codes == c].toarray()[:, np.asarray(ad.X.sum(axis=0)).ravel() != 0]
+        rows = X[codes == c].toarray()[:, np.asarray(ad.X.sum(axis=0)).ravel() != 0].astype(np.float64)
         assert np.isclose(prep.cluster_stats[0][c], rows.mean(), rtol=1e-12)
         assert np.isclose(prep.cluster_stats[1][c], rows.std(), rtol=1e-9)
     # groupby_subset keeps only the named clusters
