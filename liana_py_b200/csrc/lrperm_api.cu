@@ -180,6 +180,7 @@ struct lrperm_engine {
     int64_t N = 0, G = 0, nnz = 0;
     DevBuf indptr, csr_pairs, csc_pairs, err_flag;
     bool have_matrix = false, csc_ready = false;
+    bool csr_packed = true;               // false after a pinned upload: csr_pairs is built from the raw arrays on first use
     std::vector<int32_t> h_csc_ptr;   // [G+1] gene pointers of the value-sorted CSC (trimean path)
     // FAST mode: the CSC copy is built cell tile by cell tile (the entries of a tile's rows are contiguous in CSR
     // order and the tile's gene-major copy occupies the same index range), so a tile can be sorted - and its chunks
@@ -425,7 +426,7 @@ int csc_begin(lrperm_engine* h, int32_t tile_cells) {
 
 // queue the CSC build of tile t on `st`: keys + histogram, stable radix sort by column (cells stay ascending inside a
 // gene), histogram to the pinned host buffer, event.  [e0, e1) = the tile's entry range (host-known).
-int csc_enqueue_tile(lrperm_engine* h, int32_t t, int64_t e0, int64_t e1, cudaStream_t st) {
+int csc_enqueue_tile(lrperm_engine* h, int32_t t, int64_t e0, int64_t e1, cudaStream_t st, bool from_raw = false) {
     const int32_t G = (int32_t)h->G;
     const int32_t row0 = (int32_t)std::min<int64_t>((int64_t)t * h->csc_tile_cells, h->N);
     const int32_t row1 = (int32_t)std::min<int64_t>((int64_t)(t + 1) * h->csc_tile_cells, h->N);
@@ -437,8 +438,13 @@ int csc_enqueue_tile(lrperm_engine* h, int32_t t, int64_t e0, int64_t e1, cudaSt
         if (!use_shared) smem = 0;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(csc_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = (int)std::min<int64_t>((int64_t)h->sm_count * 4, std::max<int64_t>(1, ((int64_t)(row1 - row0) * 32 + 511) / 512));
-        csc_keys_kernel<<<grid, 512, smem, st>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), row0, row1, G,
-                                                 h->csc_keys.as<uint32_t>(), h->csc_payload.as<unsigned long long>(), d_hist, use_shared);
+        if (from_raw)       // pinned upload: straight from the staged raw arrays, no packed copy yet
+            csc_keys_kernel<<<grid, 512, smem, st>>>(h->indptr.as<int32_t>(), nullptr, row0, row1, G,
+                                                     h->csc_keys.as<uint32_t>(), h->csc_payload.as<unsigned long long>(), d_hist, use_shared,
+                                                     h->st_indices.as<int32_t>(), h->st_data.as<float>(), h->err_flag_m.as<int>());
+        else
+            csc_keys_kernel<<<grid, 512, smem, st>>>(h->indptr.as<int32_t>(), h->csr_pairs.as<int2>(), row0, row1, G,
+                                                     h->csc_keys.as<uint32_t>(), h->csc_payload.as<unsigned long long>(), d_hist, use_shared);
         CK_LAUNCH();
         int end_bit = 1;
         while ((1 << end_bit) < G && end_bit < 31) ++end_bit;
@@ -466,12 +472,11 @@ int submit_tiles(lrperm_engine* h, int32_t count) {
         if (e1 > e0) {
             CK(cudaMemcpyAsync(h->st_indices.as<int32_t>() + e0, static_cast<const int32_t*>(h->up_indices) + e0, sizeof(int32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, sC));
             CK(cudaMemcpyAsync(h->st_data.as<float>() + e0, static_cast<const float*>(h->up_data) + e0, sizeof(float) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, sC));
-            pack_csr_kernel<<<grid_for((int64_t)(row1 - row0) * 32, 256, h->sm_count * 32), 256, 0, sC>>>(
-                h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), row0, row1, (int32_t)h->G,
-                h->csr_pairs.as<int2>(), h->err_flag_m.as<int>());
-            CK_LAUNCH();
+            // no packing here: FAST mode builds its CSC copy from the raw arrays; the bank-dealt csr_pairs of the
+            // row-gather kernels (EXACT order, observed statistics, moments, trimean) is built on first use (wait_matrix)
         }
-        if ((rc = csc_enqueue_tile(h, t, e0, e1, sC))) return rc;
+        (void)row0; (void)row1;
+        if ((rc = csc_enqueue_tile(h, t, e0, e1, sC, true))) return rc;
         h->tiles_enqueued = t + 1;
     }
     h->up_next_tile = end;
@@ -483,20 +488,32 @@ int submit_tiles(lrperm_engine* h, int32_t count) {
 // without waiting): submit what is left of it, make the engine stream wait, surface the deferred validation result.
 // Everything that reads the whole matrix on the device calls this first; what does not need it (labels, triples,
 // the label slabs of the first batches) proceeds while the upload runs.
-int wait_matrix(lrperm_engine* h) {
-    if (!h->matrix_pending) return LRPERM_OK;
-    int rc;
-    if ((rc = submit_tiles(h, -1))) return rc;
-    h->matrix_pending = false;
-    CK(cudaStreamWaitEvent(h->stream, h->ev_matrix, 0));
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, h->err_flag_m.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (flag) {
-        CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream));
-        h->have_matrix = false;
-        return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr (deferred check): invalid input (flag=%d: 1=column out of range, "
-                       "2=indptr overflow, 4=indptr not monotone)", flag);
+// need_csr: the caller reads csr_pairs (row-gather kernels).  After a pinned upload that copy does not exist yet (FAST
+// mode never needs it): it is packed here, once, from the raw arrays the upload left in the staging buffers.
+int wait_matrix(lrperm_engine* h, bool need_csr = true) {
+    if (h->matrix_pending) {
+        int rc;
+        if ((rc = submit_tiles(h, -1))) return rc;
+        h->matrix_pending = false;
+        CK(cudaStreamWaitEvent(h->stream, h->ev_matrix, 0));
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, h->err_flag_m.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (flag) {
+            CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream));
+            h->have_matrix = false;
+            return h->fail(LRPERM_ERR_INVALID, "lrperm_set_matrix_csr (deferred check): invalid input (flag=%d: 1=column out of range, "
+                           "2=indptr overflow, 4=indptr not monotone)", flag);
+        }
+    }
+    if (need_csr && !h->csr_packed) {
+        if (h->nnz > 0) {
+            pack_csr_kernel<<<grid_for(h->N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
+                h->indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), 0, (int32_t)h->N, (int32_t)h->G,
+                h->csr_pairs.as<int2>(), h->err_flag.as<int>());
+            CK_LAUNCH();
+        }
+        h->csr_packed = true;
     }
     return LRPERM_OK;
 }
@@ -568,6 +585,7 @@ int csc_enqueue_all(lrperm_engine* h, int32_t tile_cells) {
     if (h->csc_ready && h->csc_tile_cells == tile_cells) return LRPERM_OK;
     StageTimer timer("build_csc");
     int rc;
+    if ((rc = wait_matrix(h, true))) return rc;            // a rebuild reads the packed copy
     if ((rc = csc_begin(h, tile_cells))) return rc;
     // entry ranges of the tiles: indptr at the tile boundaries
     std::vector<int32_t> e((size_t)h->n_tiles + 1, 0);
@@ -886,7 +904,7 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         h->tiles_tabled = 0;
         slots_cap = (size_t)(h->nnz / std::max(chunk_nnz, 1)) + (size_t)G * (size_t)h->n_tiles + 1;
     } else {
-        if ((rc = wait_matrix(h))) return rc;
+        if ((rc = wait_matrix(h, false))) return rc;
         if ((rc = ensure_fast_tables(h, chunk_nnz, tile_cells))) return rc;
         slots_cap = (size_t)std::max(h->n_slots, 1);
     }
@@ -1586,6 +1604,7 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
             h->up_e[(size_t)t] = indptr_is_64 ? static_cast<const int64_t*>(indptr)[row] : (int64_t)static_cast<const int32_t*>(indptr)[row];
         }
         h->up_indices = indices; h->up_data = data; h->up_next_tile = 0;
+        h->csr_packed = false;
         CK(cudaMemcpyAsync(h->st_indptr.p, indptr, isz * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, sC));
         if (indptr_is_64)
             narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, sC>>>(h->st_indptr.as<int64_t>(), n_cells + 1, h->indptr.as<int32_t>(), h->err_flag_m.as<int>());
@@ -1631,6 +1650,7 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     int rc = check_err_flag(h, "lrperm_set_matrix_csr");
     if (rc) return rc;
     h->have_matrix = true;
+    h->csr_packed = true;
     // FAST mode is what normally follows: start the CSC copy now, it sorts while the caller prepares labels / triples
     if (h->eager_csc && nnz > 0 && (rc = csc_enqueue_all(h, fast_tile_cells(h)))) return rc;
     return LRPERM_OK;
@@ -1642,7 +1662,12 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
     if (!h) return LRPERM_ERR_INVALID;
     StageTimer timer("stage_matrix_csr");
     DeviceGuard guard(h->device);
-    if (h->matrix_pending) { CK(cudaStreamSynchronize(h->copy_stream)); h->matrix_pending = false; CK(cudaMemsetAsync(h->err_flag_m.p, 0, sizeof(int), h->stream)); }
+    if (h->have_matrix && (h->matrix_pending || !h->csr_packed)) {
+        // the staging buffers hold the raw arrays of the current matrix (pinned upload, not packed yet): finish it first
+        const int rcw = wait_matrix(h, true);
+        if (rcw) { h->have_matrix = false; h->matrix_pending = false; h->csr_packed = true; CK(cudaStreamSynchronize(h->copy_stream)); }
+        CK(cudaStreamSynchronize(h->stream));
+    }
     h->staged = false;
     if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: bad shape or NULL indptr");
     if (n_cells >= 0x7fffffffLL || n_genes >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: n_cells and n_genes must be < 2^31");
@@ -1826,6 +1851,7 @@ int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_gen
     if ((rc = check_err_flag(h, "lrperm_commit_matrix"))) return rc;
     h->N = N_out; h->G = n_genes_out; h->nnz = nnz_out;
     h->have_matrix = true;
+    h->csr_packed = true;
     if (h->eager_csc && nnz_out > 0 && (rc = csc_enqueue_all(h, fast_tile_cells(h)))) return rc;
     return LRPERM_OK;
 }
@@ -2123,7 +2149,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     const int64_t n_batches = (n_perms + PB - 1) / PB;
     const bool pipelined = order_mode == LRPERM_ORDER_FAST && h->overlap && n_batches > 0;
     if (order_mode == LRPERM_ORDER_FAST && !pipelined) {
-        if ((rc = wait_matrix(h))) return rc;
+        if ((rc = wait_matrix(h, false))) return rc;
         if ((rc = ensure_fast_tables(h, fast_chunk, fast_tile))) return rc;
         CK(h->slab.ensure((size_t)N * PB));
         CK(h->partials.ensure(sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB));

@@ -277,9 +277,14 @@ __global__ void narrow_indptr_kernel(const T* __restrict__ in, int64_t n, int32_
 // payload {cell, value bits} packed so that the sorted payload array IS the tile's csc_pairs range; column histogram of
 // the tile privatised in shared memory (one global atomic per (CTA, column) instead of one per entry).  The entries
 // of a tile's rows are contiguous in CSR order, and the tile's CSC occupies the same index range.
+// `pairs` == nullptr: read the raw CSR arrays (raw_idx / raw_val) instead of the packed pairs and validate the column
+// range here (flag `err`, column clamped to 0): the packed copy is only needed by the row-gather kernels and is then
+// built lazily.
 __global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ pairs, int32_t row0, int32_t row1, int32_t G,
                                 uint32_t* __restrict__ keys, unsigned long long* __restrict__ payload,
-                                int32_t* __restrict__ col_count, int use_shared) {
+                                int32_t* __restrict__ col_count, int use_shared,
+                                const int32_t* __restrict__ raw_idx = nullptr, const float* __restrict__ raw_val = nullptr,
+                                int* __restrict__ err = nullptr) {
     extern __shared__ int32_t hist_smem[];
     int32_t* hist = use_shared ? hist_smem : col_count;      // G too large for shared memory: global atomics
     if (use_shared) for (int g = threadIdx.x; g < G; g += blockDim.x) hist[g] = 0;
@@ -290,7 +295,13 @@ __global__ void csc_keys_kernel(const int32_t* __restrict__ indptr, const int2* 
     for (int r = row0 + warp; r < row1; r += nwarps) {
         const int s = indptr[r], e = indptr[r + 1];
         for (int o = s + lane; o < e; o += 32) {
-            const int2 pr = pairs[o];
+            int2 pr;
+            if (pairs) pr = pairs[o];
+            else {
+                pr.x = raw_idx[o];
+                pr.y = __float_as_int(raw_val[o]);
+                if (pr.x < 0 || pr.x >= G) { atomicOr(err, 1); pr.x = 0; }
+            }
             keys[o] = (uint32_t)pr.x;
             payload[o] = ((unsigned long long)(uint32_t)pr.y << 32) | (uint32_t)r;
             atomicAdd(&hist[pr.x], 1);
