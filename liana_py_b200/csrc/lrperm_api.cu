@@ -585,7 +585,8 @@ int csc_enqueue_all(lrperm_engine* h, int32_t tile_cells) {
     if (h->csc_ready && h->csc_tile_cells == tile_cells) return LRPERM_OK;
     StageTimer timer("build_csc");
     int rc;
-    if ((rc = wait_matrix(h, true))) return rc;            // a rebuild reads the packed copy
+    const bool raw = !h->csr_packed;                        // no packed copy yet: sort from the raw arrays in the staging buffers
+    if ((rc = wait_matrix(h, false))) return rc;
     if ((rc = csc_begin(h, tile_cells))) return rc;
     // entry ranges of the tiles: indptr at the tile boundaries
     std::vector<int32_t> e((size_t)h->n_tiles + 1, 0);
@@ -595,7 +596,7 @@ int csc_enqueue_all(lrperm_engine* h, int32_t tile_cells) {
     }
     CK(cudaStreamSynchronize(h->stream));
     for (int32_t t = 0; t < h->n_tiles; ++t)
-        if ((rc = csc_enqueue_tile(h, t, e[(size_t)t], e[(size_t)t + 1], h->stream))) return rc;
+        if ((rc = csc_enqueue_tile(h, t, e[(size_t)t], e[(size_t)t + 1], h->stream, raw))) return rc;
     h->tiles_enqueued = h->n_tiles;
     return LRPERM_OK;
 }
@@ -1632,6 +1633,24 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
         CK_LAUNCH();
     }
     CK(h->csr_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
+    if (nnz > 0 && on_device) {
+        // Device input (e.g. the sharded multi-GPU upload): keep a raw copy in the staging buffers (the caller's
+        // tensors may go away), validate the columns, and leave the packed copy to the first row-gather consumer -
+        // FAST mode sorts its CSC copy straight from the raw arrays.
+        h->staged = false;
+        CK(h->st_indices.ensure(sizeof(int32_t) * (size_t)nnz));
+        CK(h->st_data.ensure(sizeof(float) * (size_t)nnz));
+        CK(cudaMemcpyAsync(h->st_indices.p, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->st_data.p, data, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToDevice, h->stream));
+        validate_columns_kernel<<<grid_for(nnz, 256, h->sm_count * 16), 256, 0, h->stream>>>(h->st_indices.as<int32_t>(), nnz, (int32_t)n_genes, h->err_flag.as<int>());
+        CK_LAUNCH();
+        int rc = check_err_flag(h, "lrperm_set_matrix_csr");
+        if (rc) return rc;
+        h->have_matrix = true;
+        h->csr_packed = false;
+        if (h->eager_csc && (rc = csc_enqueue_all(h, fast_tile_cells(h)))) return rc;
+        return LRPERM_OK;
+    }
     if (nnz > 0) {
         const int32_t* d_idx = indices;
         const float* d_val = data;

@@ -168,6 +168,16 @@ __global__ void stage_max_kernel(const int32_t* __restrict__ indptr, const float
     }
 }
 
+// column range check of raw CSR indices (the packing kernel does it too, but FAST-only flows never pack)
+__global__ void validate_columns_kernel(const int32_t* __restrict__ indices, int64_t nnz, int32_t G, int* __restrict__ err) {
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = indices[i];
+        bad |= c < 0 || c >= G;
+    }
+    if (bad) atomicOr(err, 1);
+}
+
 // Per-cluster sum x and sum x^2 over ALL stored entries of the staged matrix (every gene, before the resource subset):
 // the cluster mean / standard deviation of scSeqComm's `_cluster_stats` (liana/method/sc/_liana_pipe.py:466-476).
 // row_label[r] = cluster of staged row r, -1 = row not kept.  float64 and DETERMINISTIC: one warp per CTA walks its
