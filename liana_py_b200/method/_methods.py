@@ -127,13 +127,14 @@ class Method(MethodMeta):
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
                  *, perm_source: str = "philox", order: Optional[str] = None, gmean_mode: str = "product",
                  device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
-        if supp_columns:
-            raise NotImplementedError("supp_columns are outside the scope of the permutation engine")
+        # supplementary statistic columns ride along with the method's own (`_liana_pipe.py:111-114`)
+        add_cols = PL.method_columns(self.add_cols, supp_columns)
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
-                           use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in self.add_cols,
-                           want_cluster_stats="ligand_cdf" in self.add_cols)
+                           use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in add_cols,
+                           want_cluster_stats=("ligand_cdf" in add_cols) or ("receptor_cdf" in add_cols),
+                           mdata_kwargs=mdata_kwargs)
         liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
-                               perm_source, order, gmean_mode, dist)
+                               perm_source, order, gmean_mode, dist, add_cols=add_cols)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
         liana_res = PL.sort_frame(state.engine, liana_res, orderby, ascending)
@@ -146,15 +147,17 @@ class Method(MethodMeta):
 
 
 def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_lrs, perm_source, order,
-               gmean_mode, dist, aggregate_flag=False, null_cache=None, permuting_methods=None) -> pd.DataFrame:
+               gmean_mode, dist, aggregate_flag=False, null_cache=None, permuting_methods=None,
+               add_cols=None) -> pd.DataFrame:
     """`_run_method` (`_liana_pipe.py:363-452`) for one method on a prepared PipelineState.
 
     In a consensus (`null_cache` given) every permutation method named in `permuting_methods` is counted
     from ONE pass over the permutations, and the counts are cached for the methods that follow."""
     stat = "trimean" if K.LIGAND_TRIMEAN in method.complex_cols else "means"
     tri, lr_res = state.resolved(expr_prop, return_all_lrs, stat)       # shared by the methods of a consensus
-    if method.add_cols:
-        lr_res = PL.add_method_columns(state, tri, lr_res, method.add_cols)
+    add_cols = method.add_cols if add_cols is None else add_cols
+    if add_cols:
+        lr_res = PL.add_method_columns(state, tri, lr_res, add_cols)
         lr_res = lr_res[sorted(lr_res.columns)]            # `np.union1d` of the column sets (`_liana_pipe.py:385`)
     kept = tri.keep
     x = lr_res[kept] if return_all_lrs else lr_res

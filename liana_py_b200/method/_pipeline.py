@@ -179,8 +179,12 @@ class PipelineState:
 
 
 def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells, use_raw, layer,
-            verbose, device=0, base=float(np.e), want_max=False, want_cluster_stats=False) -> PipelineState:
+            verbose, device=0, base=float(np.e), want_max=False, want_cluster_stats=False,
+            mdata_kwargs=None) -> PipelineState:
     res = handle_resource(interactions=interactions, resource=resource, resource_name=resource_name, verbose=verbose)
+    if _pre.is_mudata(adata):                    # `_liana_pipe.py:126-129`
+        adata = _pre.mdata_to_anndata(adata, **(mdata_kwargs or {}), verbose=verbose)
+        use_raw, layer = False, None
     groupby_subset = None
     if groupby_pairs is not None:
         if not (K.SOURCE in groupby_pairs.columns) | (K.TARGET in groupby_pairs.columns):
@@ -287,9 +291,35 @@ def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame
             frame[col] = state.gene_cdf()[tri.src, tri.lig_gene]
         elif col == "receptor_cdf":
             frame[col] = state.gene_cdf()[tri.tgt, tri.rec_gene]
+        elif col in frame.columns:
+            pass                                   # a key / complex / proportion column the frame already carries
+        elif col == K.LIGAND_MEANS:                # only reachable as supplementary columns of CellChat
+            frame[col] = state.means[tri.src, tri.lig_gene]
+        elif col == K.RECEPTOR_MEANS:
+            frame[col] = state.means[tri.tgt, tri.rec_gene]
+        elif col in (K.LIGAND_TRIMEAN, K.RECEPTOR_TRIMEAN):
+            if state.prep.mat_max is None:
+                # `_get_lr` only computes trimeans when `mat_max` is among the requested columns
+                # (`_liana_pipe.py:143-146, 307-308`); the reference then fails selecting the column
+                raise KeyError(f"`{col}` needs `mat_max` among the supp_columns")
+            frame[col] = state.trimean()[tri.src, tri.lig_gene] if col == K.LIGAND_TRIMEAN \
+                else state.trimean()[tri.tgt, tri.rec_gene]
+        elif col in ("ligand_pvals", "receptor_pvals"):
+            raise NotImplementedError(f"`{col}` comes from scanpy's rank_genes_groups (`_liana_pipe.py:279-283`), "
+                                      "which is outside the scope of the permutation engine")
         else:
-            raise NotImplementedError(f"column `{col}` is outside the scope of the permutation engine")
+            raise KeyError(f"`{col}` is not a column of the ligand-receptor statistics")
     return frame
+
+
+def method_columns(method_add_cols, supp_columns) -> list:
+    """`_add_cols + supp_columns` of `liana_pipe` (`_liana_pipe.py:111-114`): the method's own statistic columns
+    followed by the caller's supplementary ones, once each (the reference takes `np.union1d` of them)."""
+    out = list(method_add_cols)
+    for col in (supp_columns or []):
+        if col not in out:
+            out.append(col)
+    return out
 
 
 def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, seed, perm_source, order,

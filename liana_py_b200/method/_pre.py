@@ -61,6 +61,60 @@ def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False):
     return X
 
 
+def is_mudata(obj) -> bool:
+    """MuData (or a look-alike): a `.mod` mapping of modality name -> AnnData (`_liana_pipe.py:126`)."""
+    return hasattr(obj, "mod") and hasattr(obj.mod, "keys")
+
+
+class ModalityPair:
+    """What `mdata_to_anndata` returns, reduced to what the pipeline reads: X (CSR), var_names, obs."""
+    raw = None
+    isbacked = False
+
+    def __init__(self, X, var_names, obs, uns):
+        self.X, self.var_names, self.obs, self.uns, self.layers = X, pd.Index(var_names), obs, uns, {}
+
+    @property
+    def shape(self):
+        return self.X.shape
+
+
+def _handle_mod(mdata, mod, use_raw, layer, transform, verbose):
+    """One modality's matrix and names (`liana/utils/mdata_to_anndata.py:60-75`)."""
+    if mod not in mdata.mod.keys():
+        raise ValueError(f"`{mod}` is not in the mdata!")
+    md = mdata.mod[mod]
+    if use_raw:
+        if getattr(md, "raw", None) is None:
+            raise ValueError("`.raw` is not initialized!")
+        X, names = md.raw.X, md.raw.var_names
+    else:
+        X, names = choose_mtx_rep(md, use_raw=False, layer=layer, verbose=verbose), md.var_names
+    if transform:
+        _logg(f"Transforming {mod} using {getattr(transform, '__name__', transform)}", verbose=verbose)
+        X = transform(X)
+    return sparse.csr_matrix(X), pd.Index(names), pd.Index(md.obs_names)
+
+
+def mdata_to_anndata(mdata, x_mod, y_mod, x_layer=None, y_layer=None, x_use_raw=False, y_use_raw=False,
+                     x_transform=None, y_transform=None, verbose=True) -> ModalityPair:
+    """Two modalities of a MuData side by side as one matrix (`liana/utils/mdata_to_anndata.py:6-58`:
+    `anndata.concat([x, y], axis=1)` = inner join on the cell names, x's order; obs / uns from the MuData)."""
+    if x_mod is None or y_mod is None:
+        raise ValueError("Both `x_mod` and `y_mod` must be provided!")
+    xX, xn, xo = _handle_mod(mdata, x_mod, x_use_raw, x_layer, x_transform, verbose)
+    yX, yn, yo = _handle_mod(mdata, y_mod, y_use_raw, y_layer, y_transform, verbose)
+    if not xo.equals(yo):
+        common = xo.intersection(yo, sort=False)
+        xX, yX = xX[xo.get_indexer(common)], yX[yo.get_indexer(common)]
+        xo = common
+    if xX.shape[0] != mdata.obs.shape[0]:
+        raise ValueError(f"Length of passed value for obs_names is {mdata.obs.shape[0]}, but this AnnData has shape: "
+                         f"({xX.shape[0]}, {xX.shape[1] + yX.shape[1]})")
+    X = sparse.hstack([xX, yX], format="csr")
+    return ModalityPair(X, xn.append(yn), mdata.obs.copy(), dict(mdata.uns))
+
+
 def _make_unique(names: pd.Index) -> pd.Index:
     names = pd.Index(names.astype(str))
     if names.is_unique:
@@ -84,9 +138,8 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
                   complex_sep="_", verbose=False, want_max=False, want_cluster_stats=False) -> PreparedInput:
     """Same checks, order and exception types as `prep_check_adata` (`_pre.py:65-169`); the passes over the
     matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU."""
-    if hasattr(adata, "mod"):
-        raise NotImplementedError("MuData input is outside the scope of the B200 permutation engine; "
-                                  "convert to AnnData first.")
+    if is_mudata(adata):
+        raise ValueError("MuData input: pass `mdata_kwargs` (x_mod, y_mod, ...) through the method call")
     X = choose_mtx_rep(adata, use_raw=use_raw, layer=layer, verbose=verbose)
     if use_raw and layer is None:
         var_names = pd.Index(adata.raw.var_names)

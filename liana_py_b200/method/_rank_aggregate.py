@@ -58,7 +58,7 @@ class AggregateClass(MethodMeta):
             consensus_opts = "Magnitude"                       # `_liana_pipe.py:108-109`
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
                            use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in self.add_cols,
-                           want_cluster_stats="ligand_cdf" in self.add_cols)
+                           want_cluster_stats="ligand_cdf" in self.add_cols, mdata_kwargs=mdata_kwargs)
         null_cache = {}
         lrs = {}
         for method in self.methods:

@@ -177,3 +177,21 @@ class AnnDataLite:
 
     def __repr__(self):
         return f"AnnDataLite with n_obs x n_vars = {self.shape[0]} x {self.shape[1]}"
+
+
+class MuDataLite:
+    """A MuData look-alike: `.mod` (name -> AnnData-like) plus the shared obs / obsp / obsm / uns the
+    reference's `mdata_to_anndata` copies (`liana/utils/mdata_to_anndata.py:53-56`)."""
+
+    def __init__(self, mod: dict, obs=None):
+        self.mod = dict(mod)
+        first = next(iter(self.mod.values()))
+        self.obs = first.obs.copy() if obs is None else obs
+        self.obsp, self.obsm, self.uns = {}, {}, {}
+
+    @property
+    def shape(self):
+        return (self.obs.shape[0], sum(m.shape[1] for m in self.mod.values()))
+
+    def __repr__(self):
+        return f"MuDataLite with {len(self.mod)} modalities, n_obs = {self.obs.shape[0]}"

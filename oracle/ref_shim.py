@@ -23,6 +23,8 @@ import os
 import sys
 import types
 
+import pandas as pd
+
 REFERENCE_ROOT = os.environ.get("LIANA_REFERENCE_ROOT", "/root/reference")
 
 
@@ -69,6 +71,23 @@ def _scanpy_scale(adata, zero_center=True, max_value=None, copy=False, layer=Non
     return out if copy else None
 
 
+def _anndata_concat(adatas, axis=0, label=None, **kwargs):
+    """Restatement of `anndata.concat` (third-party, pinned anndata 0.9.2, not vendored) for the one call the
+    reference makes: `an.concat([xdata, ydata], axis=1, label='modality')` (`liana/utils/mdata_to_anndata.py:51`) -
+    variables side by side, inner join on the cell names in the first object's order, `var[label]` = position."""
+    from scipy import sparse
+    from liana_py_b200.testing._anndata_lite import AnnDataLite
+    assert axis == 1 and len(adatas) == 2
+    x, y = adatas
+    common = x.obs_names.intersection(y.obs_names, sort=False)
+    xi, yi = x.obs_names.get_indexer(common), y.obs_names.get_indexer(common)
+    X = sparse.hstack([sparse.csr_matrix(x.X)[xi], sparse.csr_matrix(y.X)[yi]], format="csr")
+    var = pd.DataFrame(index=x.var_names.append(y.var_names))
+    if label is not None:
+        var[label] = pd.Categorical(["0"] * x.shape[1] + ["1"] * y.shape[1])
+    return AnnDataLite(X=X, obs=pd.DataFrame(index=common), var=var)
+
+
 def _install_pandas_compat():
     """Container drift, not a change of the reference: `_run_method` ends with `lr_res.drop([None], axis=1)`
     (`_liana_pipe.py:449-450`) to remove the column a method without a magnitude / specificity score wrote
@@ -109,7 +128,7 @@ def load_reference():
     repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if repo_root not in sys.path:
         sys.path.insert(0, repo_root)
-    from liana_py_b200.testing._anndata_lite import AnnDataLite
+    from liana_py_b200.testing._anndata_lite import AnnDataLite, MuDataLite
 
     lroot = os.path.join(REFERENCE_ROOT, "liana")
 
@@ -129,6 +148,7 @@ def load_reference():
     # third-party stubs
     an = types.ModuleType("anndata")
     an.AnnData = AnnDataLite
+    an.concat = _anndata_concat
     sys.modules.setdefault("anndata", an)
     sc = types.ModuleType("scanpy")
     sc.AnnData = AnnDataLite
@@ -136,17 +156,15 @@ def load_reference():
     sys.modules.setdefault("scanpy", sc)
     mu = types.ModuleType("mudata")
 
-    class MuData:  # only used in isinstance checks (`_liana_pipe.py:126`)
-        pass
-    mu.MuData = MuData
+    mu.MuData = MuDataLite      # used in isinstance checks (`_liana_pipe.py:126`)
     sys.modules.setdefault("mudata", mu)
     dr = types.ModuleType("docrep")
     dr.DocstringProcessor = _DocstringProcessor
     sys.modules.setdefault("docrep", dr)
 
     # names `_liana_pipe.py` imports from packages whose __init__ we skipped
-    sys.modules["liana.utils"].mdata_to_anndata = lambda *a, **k: (_ for _ in ()).throw(
-        NotImplementedError("MuData input is out of scope"))
+    sys.modules["liana.utils"].mdata_to_anndata = \
+        importlib.import_module("liana.utils.mdata_to_anndata").mdata_to_anndata
     rc = importlib.import_module("liana.resource._reassemble_complexes")
     sys.modules["liana.resource"].explode_complexes = rc.explode_complexes
     sys.modules["liana.resource"].filter_reassemble_complexes = rc.filter_reassemble_complexes

@@ -24,7 +24,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
 from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from variants import variant_inputs  # noqa: E402
+from variants import mdata_inputs, variant_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -212,6 +212,12 @@ def save_variants(ref):
                               verbose=False, **kw)
         res.to_csv(os.path.join(OUT, f"variant_{name}_cellphonedb.csv.gz"), index=False)
         print(f"variant {name}: {res.shape}, mean pval {res['cellphone_pvals'].mean():.4f}")
+    # MuData input: two modalities joined by the reference's own `mdata_to_anndata`
+    mdata, mkw = mdata_inputs()
+    res = ref.cellphonedb(mdata, groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, verbose=False,
+                          use_raw=True, mdata_kwargs=mkw)          # use_raw is overridden for MuData (`_liana_pipe.py:128`)
+    res.to_csv(os.path.join(OUT, "variant_mdata_cellphonedb.csv.gz"), index=False)
+    print(f"variant mdata: {res.shape}, mean pval {res['cellphone_pvals'].mean():.4f}")
 
 
 def save_cellchat(ref):

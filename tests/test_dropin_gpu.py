@@ -220,6 +220,51 @@ def test_call_signature_variants_identical_to_reference(name):
     compare(res, gold, "lr_means", "cellphone_pvals")
 
 
+def test_supp_columns_identical_to_reference():
+    """`supp_columns` (`_liana_pipe.py:111-114`): the statistic columns of the other methods ride along with
+    CellPhoneDB's; same column order (np.union1d = sorted, then the two scores) and values as the reference's frame."""
+    from variants import variant_inputs, SUPP_COLUMNS
+    adata, variants = variant_inputs()
+    res = li.mt.cellphonedb(adata, groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+                            perm_source="reference", **variants["supp"])
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_supp_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")
+    a = res.sort_values(KEY).reset_index(drop=True)
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    for c in ("mat_mean", "mat_max"):
+        assert a[c].dtype == np.float32 and np.array_equal(a[c].values, b[c].values.astype(np.float32)), c
+    for c in ("ligand_trimean", "receptor_trimean"):
+        assert np.array_equal(a[c].values, b[c].values), c                          # exact selection: bit-identical
+    for c in [c for c in SUPP_COLUMNS if c not in ("mat_mean", "mat_max", "ligand_trimean", "receptor_trimean")]:
+        # float32 / float64 statistics accumulated by another route: the reference's own frame tolerance
+        np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-4, atol=2e-6, err_msg=c)
+    with pytest.raises(KeyError):                      # trimeans exist only when mat_max is requested too
+        li.mt.cellphonedb(adata, groupby="cluster", n_perms=None, use_raw=False, inplace=False,
+                          supp_columns=["ligand_trimean"])
+    with pytest.raises(NotImplementedError):
+        li.mt.cellphonedb(adata, groupby="cluster", n_perms=None, use_raw=False, inplace=False,
+                          supp_columns=["ligand_pvals"])
+
+
+def test_mudata_input_identical_to_reference():
+    """A MuData as input (`_liana_pipe.py:126-129`, `liana/utils/mdata_to_anndata.py`): the two modalities named in
+    `mdata_kwargs` side by side, `use_raw` / `layer` overridden, the result written into the MuData's `.uns`."""
+    from variants import mdata_inputs
+    mdata, mkw = mdata_inputs()
+    kw = dict(groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, perm_source="reference", use_raw=True, mdata_kwargs=mkw)
+    res = li.mt.cellphonedb(mdata, inplace=False, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_mdata_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")
+    li.mt.cellphonedb(mdata, **kw)
+    assert mdata.uns["liana_res"].shape == res.shape
+    agg = li.mt.rank_aggregate(mdata, groupby="cluster", n_perms=None, use_raw=False, inplace=False, mdata_kwargs=mkw)
+    assert len(agg) == len(res) and "magnitude_rank" in agg.columns
+    with pytest.raises(ValueError, match="is not in the mdata"):
+        li.mt.cellphonedb(mdata, groupby="cluster", n_perms=2, mdata_kwargs=dict(x_mod="rna", y_mod="nope"))
+    with pytest.raises(TypeError):                    # x_mod / y_mod are required, as in the reference
+        li.mt.cellphonedb(mdata, groupby="cluster", n_perms=2)
+
+
 def test_return_all_lrs_contract():
     """`return_all_lrs=True` (liana/tests/test_sc_methods.py:166-190: every (pair, interaction) row comes back, the
     rows that fail expr_prop get the worst magnitude / specificity of the kept ones).  The reference itself cannot

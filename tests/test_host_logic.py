@@ -99,3 +99,48 @@ def test_prepare_input_equals_reference_prep_check_adata():
         assert np.array_equal(np.asarray(out.obs["@label"].cat.codes), prep.labels)
         assert out.shape == (prep.n_cells, len(prep.var_names))
         assert np.isclose(float(np.mean(out.X, dtype="float32")), prep.mat_mean, rtol=1e-5)
+
+
+# ---- MuData input ------------------------------------------------------------------------------------------
+def test_mdata_to_anndata_matches_reference():
+    """`_pre.mdata_to_anndata` against the reference's `liana/utils/mdata_to_anndata.py` run on the same MuData
+    look-alike (when /root/reference is present), and its error conventions."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from variants import mdata_inputs
+    from liana_py_b200.method import _pre
+    mdata, mkw = mdata_inputs()
+    got = _pre.mdata_to_anndata(mdata, **mkw, verbose=False)
+    x, y = mdata.mod["rna"], mdata.mod["prot"]
+    assert got.X.shape == (x.shape[0], x.shape[1] + y.shape[1]) and sparse.isspmatrix_csr(got.X)
+    assert list(got.var_names) == list(x.var_names) + list(y.var_names)
+    assert np.array_equal(got.X[:, :x.shape[1]].toarray(), x.layers["sqrt"].toarray())
+    assert np.array_equal(got.X[:, x.shape[1]:].toarray(), np.sqrt(y.X.toarray()))
+    assert got.obs.equals(mdata.obs) and got.obs is not mdata.obs
+    from oracle import ref_shim
+    if ref_shim.reference_available():
+        ref_shim.load_reference()
+        import importlib
+        ref_fun = importlib.import_module("liana.utils.mdata_to_anndata").mdata_to_anndata
+        want = ref_fun(mdata, **mkw, verbose=False)
+        assert list(want.var_names) == list(got.var_names)
+        assert (want.X != got.X).nnz == 0 and want.obs.equals(got.obs)
+    # cells in a different order / a subset in one modality: inner join on the names, x's order
+    y2 = y[np.arange(y.shape[0])[::-1][:250]].copy()
+    from liana_py_b200.testing._anndata_lite import MuDataLite
+    x2 = x[np.isin(x.obs_names, y2.obs_names)].copy()
+    md2 = MuDataLite({"rna": x, "prot": y2}, obs=x2.obs.copy())
+    got2 = _pre.mdata_to_anndata(md2, x_mod="rna", y_mod="prot", verbose=False)
+    assert got2.X.shape[0] == 250
+    assert np.array_equal(got2.X[:, x.shape[1]:].toarray(), y[np.isin(y.obs_names, y2.obs_names)].X.toarray())
+    with pytest.raises(ValueError, match="must be provided"):
+        _pre.mdata_to_anndata(mdata, x_mod=None, y_mod="prot")
+    with pytest.raises(ValueError, match="is not in the mdata"):
+        _pre.mdata_to_anndata(mdata, x_mod="rna", y_mod="nope")
+    raw = _pre.mdata_to_anndata(mdata, x_mod="rna", y_mod="prot", y_use_raw=True)      # `.raw` keeps ALL its variables
+    assert raw.X.shape[1] == x.shape[1] + y.raw.X.shape[1]
+    y.raw = None
+    with pytest.raises(ValueError, match="raw"):
+        _pre.mdata_to_anndata(mdata, x_mod="rna", y_mod="prot", y_use_raw=True)
+    with pytest.raises(ValueError):                              # obs of the MuData does not match the joined cells
+        _pre.mdata_to_anndata(MuDataLite({"rna": x, "prot": y2}), x_mod="rna", y_mod="prot")

@@ -10,6 +10,10 @@ from liana_py_b200.testing._synth import make_synthetic_adata
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+SUPP_COLUMNS = ["ligand_means_sums", "receptor_means_sums", "ligand_zscores", "receptor_zscores", "ligand_logfc",
+                "receptor_logfc", "mat_mean", "mat_max", "ligand_trimean", "receptor_trimean", "ligand_cdf", "receptor_cdf"]
+
+
 def variant_inputs():
     """small300 with the optional arguments of the call signature exercised (liana/tests/test_sc_methods.py,
     test_pre.py use the same knobs on pbmc68k): groupby_pairs, interactions=, resource=, .raw, layers."""
@@ -34,6 +38,18 @@ def variant_inputs():
         raw=dict(use_raw=True),
         layer=dict(layer="sqrt", use_raw=False),
         resname=dict(resource_name="CellPhoneDB", use_raw=False),     # another bundled resource, case-insensitive name
+        # every statistic column another method would request, carried along as supplementary columns
+        supp=dict(use_raw=False, supp_columns=SUPP_COLUMNS),
     )
 
 
+
+
+def mdata_inputs():
+    """The variant input split into two modalities of a MuData look-alike (liana/tests/test_sc_methods.py:167-190,
+    test_rank_aggregate.py:72-92 call the methods on a MuData with `mdata_kwargs`): x takes its `sqrt` layer, y is
+    transformed on the way in."""
+    from liana_py_b200.testing._anndata_lite import MuDataLite
+    adata, _ = variant_inputs()
+    mdata = MuDataLite({"rna": adata[:, 0:200].copy(), "prot": adata[:, 200:400].copy()})
+    return mdata, dict(x_mod="rna", y_mod="prot", x_layer="sqrt", y_transform=np.sqrt)
