@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LRPERM_ABI_VERSION 2   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads */
+#define LRPERM_ABI_VERSION 3   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads; 3: dense staging */
 
 /* status codes */
 #define LRPERM_OK              0
@@ -102,6 +102,17 @@ int lrperm_set_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes,
 int lrperm_stage_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes, const void *indptr, int indptr_is_64,
                             const int32_t *indices, const float *data, int on_device, const uint8_t *row_keep,
                             double *col_sums, double *kept_total, int64_t *n_nonfinite, int64_t *n_empty_rows);
+/*
+ * The same staging step for a DENSE row-major matrix (adata.X as a 2-D array): replaces the `csr_matrix(X)` of
+ * _choose_mtx_rep (liana/method/_pipe_utils/_pre.py:259-262) and the float32 cast (:117-119).  values = float32
+ * (values_are_f64 == 0) or float64, n_cells rows of n_genes values, row_stride (in elements, >= n_genes) apart.  The
+ * entries that compare != 0 in their own type become the stored entries (NaN included, -0.0 not), in column order,
+ * rounded to float32.  The dense rows are on the device only for the conversion (host input: the whole matrix is
+ * uploaded next to its CSR copy; LRPERM_ERR_OOM when that does not fit).  Outputs and row_keep as above.
+ */
+int lrperm_stage_matrix_dense(lrperm_engine *h, int64_t n_cells, int64_t n_genes, const void *values, int values_are_f64,
+                              int64_t row_stride, int on_device, const uint8_t *row_keep,
+                              double *col_sums, double *kept_total, int64_t *n_nonfinite, int64_t *n_empty_rows);
 int lrperm_commit_matrix(lrperm_engine *h, const int32_t *col_map, int64_t n_genes_out);
 /* Largest STORED value over the kept rows of the staged matrix (-inf if none) and the number of stored entries
  * in those rows: the inputs of CellChat's `mat_max = adata.X.max()` (liana/method/sc/_liana_pipe.py:143-146;

@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "lrperm_cluster_moments", "lrperm_stage_matrix_csr", "lrperm_commit_matrix",
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
     "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
-    "lrperm_argsort", "lrperm_staged_cluster_stats",
+    "lrperm_argsort", "lrperm_staged_cluster_stats", "lrperm_stage_matrix_dense",
 )
 
 _lib = None
@@ -59,6 +59,7 @@ def load_library():
     lib.lrperm_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.lrperm_cluster_moments.argtypes = [vp, C.c_double, vp, vp, vp, C.c_int]
     lib.lrperm_stage_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.lrperm_stage_matrix_dense.argtypes = [vp, i64, i64, vp, C.c_int, i64, C.c_int, vp, vp, vp, vp, vp]
     lib.lrperm_commit_matrix.argtypes = [vp, vp, i64]
     lib.lrperm_set_matrix_csr.argtypes = [vp, i64, i64, vp, C.c_int, vp, vp, C.c_int]
     lib.lrperm_set_labels.argtypes = [vp, vp, i32, C.c_int]
@@ -195,6 +196,42 @@ class Engine:
             self._h, int(n), int(g), C.c_void_p(indptr.ctypes.data), int(indptr.dtype == np.int64),
             C.c_void_p(indices.ctypes.data), C.c_void_p(data.ctypes.data), 0,
             None if keep is None else C.c_void_p(keep.ctypes.data), C.c_void_p(col_sums.ctypes.data),
+            C.byref(total), C.byref(bad), C.byref(empty)))
+        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+
+    def stage_matrix_dense(self, X, row_keep=None):
+        """`stage_matrix` for a dense 2-D array (NumPy float32 / float64, or a CUDA torch tensor of those types): the
+        CSR conversion (`csr_matrix(X)`: entries != 0, column order) happens on the device."""
+        on_device = _is_torch(X)
+        if on_device:
+            if X.dim() != 2 or str(X.dtype) not in ("torch.float32", "torch.float64") or not X.is_cuda:
+                raise ValueError("dense device input must be a 2-D CUDA tensor of float32 or float64")
+            if X.stride(1) != 1 and X.shape[1] > 1:
+                X = X.contiguous()
+            ptr, stride, is64 = X.data_ptr(), (X.stride(0) if X.shape[0] > 1 else X.shape[1]), X.dtype.itemsize == 8
+            if row_keep is not None:
+                import torch
+                keep = torch.as_tensor(np.ascontiguousarray(row_keep, dtype=np.uint8), device=X.device)
+                keep_ptr = keep.data_ptr()
+        else:
+            X = np.asarray(X)
+            if X.ndim != 2:
+                raise ValueError("dense input must be 2-D")
+            if X.dtype not in (np.float32, np.float64):
+                X = X.astype(np.float32)
+            if not X.flags.c_contiguous:
+                X = np.ascontiguousarray(X)
+            ptr, stride, is64 = X.ctypes.data, X.shape[1], X.dtype == np.float64
+            keep = None if row_keep is None else np.ascontiguousarray(row_keep, dtype=np.uint8)
+            keep_ptr = None if keep is None else keep.ctypes.data
+        if row_keep is None:
+            keep_ptr = None
+        n, g = int(X.shape[0]), int(X.shape[1])
+        col_sums = np.zeros(g, dtype=np.float64)
+        total, bad, empty = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.lrperm_stage_matrix_dense(
+            self._h, n, g, C.c_void_p(ptr), int(is64), int(max(stride, g)), int(on_device),
+            None if keep_ptr is None else C.c_void_p(keep_ptr), C.c_void_p(col_sums.ctypes.data),
             C.byref(total), C.byref(bad), C.byref(empty)))
         return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
 

@@ -1675,42 +1675,22 @@ int lrperm_set_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, co
     return LRPERM_OK;
 }
 
-int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, const void* indptr, int indptr_is_64,
-                            const int32_t* indices, const float* data, int on_device, const uint8_t* row_keep,
-                            double* col_sums, double* kept_total, int64_t* n_nonfinite, int64_t* n_empty_rows) {
-    if (!h) return LRPERM_ERR_INVALID;
-    StageTimer timer("stage_matrix_csr");
-    DeviceGuard guard(h->device);
+namespace {
+// a matrix whose raw arrays still sit in the staging buffers (pinned upload, not packed yet) is finished first
+int stage_begin(lrperm_engine* h) {
     if (h->have_matrix && (h->matrix_pending || !h->csr_packed)) {
-        // the staging buffers hold the raw arrays of the current matrix (pinned upload, not packed yet): finish it first
         const int rcw = wait_matrix(h, true);
         if (rcw) { h->have_matrix = false; h->matrix_pending = false; h->csr_packed = true; CK(cudaStreamSynchronize(h->copy_stream)); }
         CK(cudaStreamSynchronize(h->stream));
     }
     h->staged = false;
-    if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: bad shape or NULL indptr");
-    if (n_cells >= 0x7fffffffLL || n_genes >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: n_cells and n_genes must be < 2^31");
-    int64_t nnz = 0;
-    const size_t isz = indptr_is_64 ? 8 : 4;
-    {
-        unsigned char last[8] = {0};
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(indptr) + isz * (size_t)n_cells;
-        if (on_device) { CK(cudaMemcpyAsync(last, src, isz, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
-        else memcpy(last, src, isz);
-        if (indptr_is_64) { int64_t v; memcpy(&v, last, 8); nnz = v; } else { int32_t v; memcpy(&v, last, 4); nnz = v; }
-    }
-    if (nnz < 0 || nnz >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: nnz=%lld must be in [0, 2^31)", (long long)nnz);
-    if (nnz > 0 && (!indices || !data)) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: NULL indices/data");
+    return LRPERM_OK;
+}
+
+// statistics of the staged CSR arrays (st_indptr / st_indices / st_data hold n_cells rows, nnz entries)
+int stage_finish(lrperm_engine* h, const char* what, int64_t n_cells, int64_t n_genes, int64_t nnz, const uint8_t* row_keep,
+                 int on_device, double* col_sums, double* kept_total, int64_t* n_nonfinite, int64_t* n_empty_rows) {
     int rc;
-    CK(h->st_indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
-    if ((rc = upload(h, h->tmp_a, indptr, isz * (size_t)(n_cells + 1), on_device))) return rc;
-    if (indptr_is_64)
-        narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int64_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
-    else
-        narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int32_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
-    CK_LAUNCH();
-    if ((rc = upload(h, h->st_indices, indices, sizeof(int32_t) * (size_t)nnz, on_device))) return rc;
-    if ((rc = upload(h, h->st_data, data, sizeof(float) * (size_t)nnz, on_device))) return rc;
     h->st_has_keep = row_keep != nullptr;
     if (row_keep && (rc = upload(h, h->st_row_keep, row_keep, (size_t)n_cells, on_device))) return rc;
     // [G doubles col sums][kept_total][n_nonfinite][n_empty_rows]
@@ -1728,7 +1708,7 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
     }
     std::vector<double> host((size_t)n_genes + 3);
     CK(cudaMemcpyAsync(host.data(), d_small, small_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = check_err_flag(h, "lrperm_stage_matrix_csr"))) return rc;     // synchronises the stream
+    if ((rc = check_err_flag(h, what))) return rc;     // synchronises the stream
     if (col_sums) memcpy(col_sums, host.data(), sizeof(double) * (size_t)n_genes);
     if (kept_total) *kept_total = host[(size_t)n_genes];
     unsigned long long u;
@@ -1737,6 +1717,100 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
     h->st_N = n_cells; h->st_G = n_genes; h->st_nnz = nnz;
     h->staged = true;
     return LRPERM_OK;
+}
+}  // namespace
+
+int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, const void* indptr, int indptr_is_64,
+                            const int32_t* indices, const float* data, int on_device, const uint8_t* row_keep,
+                            double* col_sums, double* kept_total, int64_t* n_nonfinite, int64_t* n_empty_rows) {
+    if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("stage_matrix_csr");
+    DeviceGuard guard(h->device);
+    int rc;
+    if ((rc = stage_begin(h))) return rc;
+    if (n_cells < 0 || n_genes <= 0 || !indptr) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: bad shape or NULL indptr");
+    if (n_cells >= 0x7fffffffLL || n_genes >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: n_cells and n_genes must be < 2^31");
+    int64_t nnz = 0;
+    const size_t isz = indptr_is_64 ? 8 : 4;
+    {
+        unsigned char last[8] = {0};
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(indptr) + isz * (size_t)n_cells;
+        if (on_device) { CK(cudaMemcpyAsync(last, src, isz, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+        else memcpy(last, src, isz);
+        if (indptr_is_64) { int64_t v; memcpy(&v, last, 8); nnz = v; } else { int32_t v; memcpy(&v, last, 4); nnz = v; }
+    }
+    if (nnz < 0 || nnz >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: nnz=%lld must be in [0, 2^31)", (long long)nnz);
+    if (nnz > 0 && (!indices || !data)) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: NULL indices/data");
+    CK(h->st_indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    if ((rc = upload(h, h->tmp_a, indptr, isz * (size_t)(n_cells + 1), on_device))) return rc;
+    if (indptr_is_64)
+        narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int64_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
+    else
+        narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int32_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
+    CK_LAUNCH();
+    if ((rc = upload(h, h->st_indices, indices, sizeof(int32_t) * (size_t)nnz, on_device))) return rc;
+    if ((rc = upload(h, h->st_data, data, sizeof(float) * (size_t)nnz, on_device))) return rc;
+    return stage_finish(h, "lrperm_stage_matrix_csr", n_cells, n_genes, nnz, row_keep, on_device, col_sums, kept_total,
+                        n_nonfinite, n_empty_rows);
+}
+
+int lrperm_stage_matrix_dense(lrperm_engine* h, int64_t n_cells, int64_t n_genes, const void* values, int values_are_f64,
+                              int64_t row_stride, int on_device, const uint8_t* row_keep,
+                              double* col_sums, double* kept_total, int64_t* n_nonfinite, int64_t* n_empty_rows) {
+    if (!h) return LRPERM_ERR_INVALID;
+    StageTimer timer("stage_matrix_dense");
+    DeviceGuard guard(h->device);
+    int rc;
+    if ((rc = stage_begin(h))) return rc;
+    if (n_cells < 0 || n_genes <= 0 || (n_cells > 0 && !values) || row_stride < n_genes)
+        return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_dense: bad shape, NULL values or row_stride < n_genes");
+    if (n_cells >= 0x7fffffffLL || n_genes >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_dense: n_cells and n_genes must be < 2^31");
+    const size_t esz = values_are_f64 ? 8 : 4;
+    // the dense rows sit on the device only while they are converted (host input: uploaded whole, released below)
+    DevBuf dense;
+    const void* X = values;
+    if (!on_device && n_cells > 0) {
+        const size_t bytes = esz * ((size_t)(n_cells - 1) * (size_t)row_stride + (size_t)n_genes);
+        if ((rc = upload(h, dense, values, bytes, 0))) { dense.release(); return rc; }
+        X = dense.p;
+    }
+    struct Release { DevBuf& b; cudaStream_t s; ~Release() { if (b.p) { cudaStreamSynchronize(s); b.release(); } } } release{dense, h->stream};
+    CK(h->st_indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    CK(h->tmp_a.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    CK(h->small_b.ensure(16));
+    CK(cudaMemsetAsync(h->small_b.p, 0, 16, h->stream));
+    CK(cudaMemsetAsync(h->tmp_a.p, 0, sizeof(int32_t), h->stream));
+    const int grid = grid_for(std::max<int64_t>(n_cells, 1) * 32, 256, h->sm_count * 32);
+    if (n_cells > 0) {
+        if (values_are_f64)
+            dense_count_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->tmp_a.as<int32_t>(), h->small_b.as<unsigned long long>());
+        else
+            dense_count_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->tmp_a.as<int32_t>(), h->small_b.as<unsigned long long>());
+        CK_LAUNCH();
+    }
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, h->small_b.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (total >= 0x7fffffffULL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_dense: %llu stored entries, must be < 2^31", total);
+    const int64_t nnz = (int64_t)total;
+    {
+        // inclusive scan of counts[1..N] with counts[0] = 0 == exclusive row pointers (total < 2^31: no overflow)
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, h->tmp_a.as<int32_t>(), h->st_indptr.as<int32_t>(), (int)(n_cells + 1), h->stream));
+        CK(h->sort_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::InclusiveSum(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<int32_t>(), h->st_indptr.as<int32_t>(), (int)(n_cells + 1), h->stream));
+    }
+    CK(h->st_indices.ensure(sizeof(int32_t) * (size_t)nnz));
+    CK(h->st_data.ensure(sizeof(float) * (size_t)nnz));
+    if (n_cells > 0 && nnz > 0) {
+        if (values_are_f64)
+            dense_fill_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>());
+        else
+            dense_fill_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>());
+        CK_LAUNCH();
+    }
+    return stage_finish(h, "lrperm_stage_matrix_dense", n_cells, n_genes, nnz, row_keep, on_device, col_sums, kept_total,
+                        n_nonfinite, n_empty_rows);
 }
 
 int lrperm_staged_max(lrperm_engine* h, float* max_stored, int64_t* n_stored) {

@@ -139,6 +139,56 @@ __global__ void stage_stats_kernel(const int32_t* __restrict__ indptr, const int
     }
 }
 
+// Dense row-major input (adata.X as a 2-D array) -> the staged CSR the other kernels read; `csr_matrix(X)` of the
+// reference's `_choose_mtx_rep` (liana/method/_pipe_utils/_pre.py:259-262) keeps the entries that compare != 0 (NaN
+// included, -0.0 not) in column order.  HBM-bound streaming passes, one warp per row, 128 B coalesced loads:
+// pass 1 counts a row's stored entries (-> counts[r + 1], 64-bit total), pass 2 compacts them behind indptr[r] with a
+// ballot prefix so the column order is kept.  T = float or double (rounded to float32 like `astype(np.float32)`).
+template <typename T>
+__global__ void dense_count_kernel(const T* __restrict__ X, int64_t ld, int32_t N, int32_t G, int32_t* __restrict__ counts,
+                                   unsigned long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long mine = 0;
+    for (int r = warp; r < N; r += nwarps) {
+        const T* row = X + (int64_t)r * ld;
+        int n = 0;
+        for (int c = lane; c < G; c += 32) n += (row[c] != (T)0) ? 1 : 0;     // tested in T: a double that underflows float32 stays stored
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+        if (lane == 0) { counts[r + 1] = n; mine += (unsigned long long)n; }
+    }
+    if (lane == 0 && mine) atomicAdd(total, mine);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
+}
+
+template <typename T>
+__global__ void dense_fill_kernel(const T* __restrict__ X, int64_t ld, int32_t N, int32_t G, const int32_t* __restrict__ indptr,
+                                  int32_t* __restrict__ indices, float* __restrict__ data) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t below = (1u << lane) - 1u;
+    for (int r = warp; r < N; r += nwarps) {
+        const T* row = X + (int64_t)r * ld;
+        int base = indptr[r];
+        for (int c0 = 0; c0 < G; c0 += 32) {
+            const int c = c0 + lane;
+            const T t = c < G ? row[c] : (T)0;
+            const float v = (float)t;
+            const bool keep = t != (T)0;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int o = base + __popc(m & below);
+                indices[o] = c;
+                data[o] = v;
+            }
+            base += __popc(m);
+        }
+    }
+}
+
 // largest stored value over the kept rows of the staged matrix (CellChat's `mat_max = adata.X.max()`,
 // liana/method/sc/_liana_pipe.py:143-146), as an order-preserving unsigned key so that atomicMax applies
 __device__ __forceinline__ uint32_t float_order_key(float v) {

@@ -39,8 +39,9 @@ class PreparedInput:
     cluster_stats: tuple | None = None  # (mean [L], std [L]) over ALL entries of a cluster's rows (scSeqComm, `:466-476`)
 
 
-def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False):
-    """Matrix choice (.raw.X | layers[layer] | X) -> CSR; errors as `_pre.py:227-264`."""
+def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False, keep_dense=False):
+    """Matrix choice (.raw.X | layers[layer] | X) -> CSR; errors as `_pre.py:227-264`.  `keep_dense`: a dense 2-D
+    array is handed on as it is (the engine converts it on the device, `Engine.stage_matrix_dense`)."""
     is_layer = layer is not None
     if is_layer and use_raw:
         raise ValueError("Cannot specify `layer` and have `use_raw=True`.")
@@ -57,8 +58,17 @@ def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False):
         X = adata.X
     if not sparse.isspmatrix_csr(X):
         _logg("Converting to sparse csr matrix!", verbose=verbose)
+        if keep_dense and _is_dense(X):
+            return X
         X = sparse.csr_matrix(X)
     return X
+
+
+def _is_dense(X) -> bool:
+    """A plain 2-D NumPy array (not np.matrix) or a 2-D CUDA torch tensor."""
+    if type(X) is np.ndarray:
+        return X.ndim == 2
+    return type(X).__module__.startswith("torch") and hasattr(X, "data_ptr") and X.dim() == 2 and X.is_cuda
 
 
 def is_mudata(obj) -> bool:
@@ -140,16 +150,21 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU."""
     if is_mudata(adata):
         raise ValueError("MuData input: pass `mdata_kwargs` (x_mod, y_mod, ...) through the method call")
-    X = choose_mtx_rep(adata, use_raw=use_raw, layer=layer, verbose=verbose)
+    X = choose_mtx_rep(adata, use_raw=use_raw, layer=layer, verbose=verbose, keep_dense=True)
     if use_raw and layer is None:
         var_names = pd.Index(adata.raw.var_names)
     else:
         var_names = pd.Index(adata.var_names)
-    if X.dtype != np.float32:
-        X = X.astype(np.float32)
-    if not X.has_canonical_format:          # duplicate entries would break "one entry per (cell, gene)"
-        X = X.copy()
-        X.sum_duplicates()
+    dense = _is_dense(X)
+    if dense:
+        if type(X) is np.ndarray and X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float32)
+    else:
+        if X.dtype != np.float32:
+            X = X.astype(np.float32)
+        if not X.has_canonical_format:          # duplicate entries would break "one entry per (cell, gene)"
+            X = X.copy()
+            X.sum_duplicates()
     var_names = _make_unique(var_names)
     obs = adata.obs
 
@@ -183,16 +198,22 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     if len(rows) != X.shape[0]:
         row_keep = keep.astype(np.uint8)
 
-    stats = engine.stage_matrix(X, row_keep)
+    stats = engine.stage_matrix_dense(X, row_keep) if dense else engine.stage_matrix(X, row_keep)
     # empty features are removed (sum == 0 over ALL cells), empty cells only reported (`_pre.py:122-133`)
     empty = stats["col_sums"] == 0
     if empty.any():
         _logg(f"{int(empty.sum())} features of mat are empty, they will be removed.", level="warn", verbose=verbose)
     if stats["n_empty_rows"]:
         _logg(f"{stats['n_empty_rows']} samples of mat are empty, they will be removed.", level="warn", verbose=verbose)
-    head = float(np.sum(X.data[:100]))
-    if head == np.floor(head):
-        _logg("Make sure that normalized counts are passed!", level="warn", verbose=verbose)
+    if verbose:                              # sum of the first 100 stored values (`_pre.py:136-138`)
+        if dense:
+            first = X[:max(1, 100 // max(X.shape[1], 1) + 1) * 8].reshape(-1)
+            first = np.asarray(first.cpu() if hasattr(first, "cpu") else first, dtype=np.float32)
+            head = float(np.sum(first[first != 0][:100]))
+        else:
+            head = float(np.sum(X.data[:100]))
+        if head == np.floor(head):
+            _logg("Make sure that normalized counts are passed!", level="warn", verbose=verbose)
     if stats["n_nonfinite"]:
         raise ValueError("mat contains non finite values (nan or inf), please set them to 0 or remove them.")
     if low:

@@ -265,6 +265,19 @@ def test_mudata_input_identical_to_reference():
         li.mt.cellphonedb(mdata, groupby="cluster", n_perms=2)
 
 
+def test_dense_matrix_input_equals_sparse_input():
+    """`adata.X` as a dense 2-D array (`_choose_mtx_rep` converts it with `csr_matrix(X)`, `_pre.py:259-262`): converted
+    on the device, same frame as for the CSR input - and so as the reference's."""
+    adata, P, seed, ep = load_input("small300")
+    gold = pd.read_csv(os.path.join(GOLDEN, "small300_cellphonedb.csv.gz"), float_precision="round_trip")
+    for dtype in (np.float32, np.float64):
+        dense = AnnDataLite(X=adata.X, obs=adata.obs.copy(), var=adata.var.copy())
+        dense.X = adata.X.toarray().astype(dtype)
+        res = li.mt.cellphonedb(dense, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                                inplace=False, perm_source="reference")
+        compare(res, gold, "lr_means", "cellphone_pvals")
+
+
 def test_return_all_lrs_contract():
     """`return_all_lrs=True` (liana/tests/test_sc_methods.py:166-190: every (pair, interaction) row comes back, the
     rows that fail expr_prop get the worst magnitude / specificity of the kept ones).  The reference itself cannot

@@ -24,6 +24,10 @@ class SciPyStage:
                     kept_total=float(X[rows].astype(np.float64).sum()), n_nonfinite=int((~np.isfinite(X.data)).sum()),
                     n_empty_rows=int((np.asarray(X.sum(axis=1)).ravel() == 0).sum()))
 
+    def stage_matrix_dense(self, X, row_keep=None):
+        self.dense_calls = getattr(self, "dense_calls", 0) + 1
+        return self.stage_matrix(sparse.csr_matrix(X).astype(np.float32), row_keep)
+
     def staged_max(self):
         rows = np.arange(self.X.shape[0]) if self.keep is None else np.flatnonzero(self.keep)
         sub = self.X[rows]
@@ -144,3 +148,20 @@ def test_mdata_to_anndata_matches_reference():
         _pre.mdata_to_anndata(mdata, x_mod="rna", y_mod="prot", y_use_raw=True)
     with pytest.raises(ValueError):                              # obs of the MuData does not match the joined cells
         _pre.mdata_to_anndata(MuDataLite({"rna": x, "prot": y2}), x_mod="rna", y_mod="prot")
+
+
+def test_prepare_input_dense_matrix_goes_to_the_device_conversion():
+    """A dense `adata.X` (2-D array) is not converted on the host: `prepare_input` hands it to
+    `Engine.stage_matrix_dense` and ends with the same prepared input as for its CSR form."""
+    adata = _ragged()
+    want = _pre.prepare_input(adata, "cluster", 5, SciPyStage(), want_max=True, want_cluster_stats=True)
+    for dtype in (np.float32, np.float64, np.int64):
+        d = AnnDataLite(X=sparse.csr_matrix(adata.X), obs=adata.obs.copy(), var=adata.var.copy())
+        d.X = (np.rint(adata.X.toarray()) if dtype == np.int64 else adata.X.toarray()).astype(dtype)
+        stage = SciPyStage()
+        got = _pre.prepare_input(d, "cluster", 5, stage, want_max=True, want_cluster_stats=True, verbose=True)
+        assert stage.dense_calls == 1
+        if dtype != np.int64:
+            assert list(got.var_names) == list(want.var_names) and np.array_equal(got.var_cols, want.var_cols)
+            assert np.array_equal(got.labels, want.labels) and got.mat_max == want.mat_max
+            assert got.mat_mean == want.mat_mean and np.allclose(got.cluster_stats[1], want.cluster_stats[1])
