@@ -91,7 +91,8 @@ int lrperm_set_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes,
  * liana_pipe (liana/method/sc/_liana_pipe.py:161-164), which the reference does with SciPy copies.
  *
  * lrperm_stage_matrix_csr uploads the caller's FULL matrix (n_cells x n_genes, any column order within a
- * row, nnz < 2^31) and returns, over that matrix: col_sums[g] (float64, all rows; a gene is "empty" when
+ * row; it may hold 2^31 stored entries or more - its row pointers are int64 on the device - as long as what
+ * survives lrperm_commit_matrix stays below 2^31) and returns, over that matrix: col_sums[g] (float64, all rows; a gene is "empty" when
  * it is 0), the total over the rows flagged in row_keep (NULL = all rows; for mat_mean), the number of
  * non-finite stored values and of all-zero rows.  The outputs are HOST pointers (any may be NULL);
  * indptr / indices / data / row_keep follow `on_device`.

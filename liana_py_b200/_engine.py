@@ -199,6 +199,27 @@ class Engine:
             C.byref(total), C.byref(bad), C.byref(empty)))
         return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
 
+    def stage_matrix_device(self, indptr, indices, data, shape, row_keep=None):
+        """`stage_matrix` for CSR arrays that already live on the device (CUDA torch tensors: indptr int32 / int64,
+        indices int32, data float32; row_keep uint8 or None).  The staged matrix may hold more than 2^31 entries."""
+        import torch
+        if not (indptr.is_cuda and indices.is_cuda and data.is_cuda):
+            raise ValueError("stage_matrix_device takes CUDA tensors")
+        if indptr.dtype not in (torch.int32, torch.int64) or indices.dtype != torch.int32 or data.dtype != torch.float32:
+            raise ValueError("indptr must be int32 / int64, indices int32, data float32")
+        indptr, indices, data = indptr.contiguous(), indices.contiguous(), data.contiguous()
+        keep = None if row_keep is None else row_keep.to(device=data.device, dtype=torch.uint8).contiguous()
+        n, g = int(shape[0]), int(shape[1])
+        col_sums = np.zeros(g, dtype=np.float64)
+        total, bad, empty = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+        torch.cuda.current_stream().synchronize()            # the engine runs on its own stream
+        self._check(self._lib.lrperm_stage_matrix_csr(
+            self._h, n, g, C.c_void_p(indptr.data_ptr()), int(indptr.dtype == torch.int64),
+            C.c_void_p(indices.data_ptr()), C.c_void_p(data.data_ptr()), 1,
+            None if keep is None else C.c_void_p(keep.data_ptr()), C.c_void_p(col_sums.ctypes.data),
+            C.byref(total), C.byref(bad), C.byref(empty)))
+        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+
     def stage_matrix_dense(self, X, row_keep=None):
         """`stage_matrix` for a dense 2-D array (NumPy float32 / float64, or a CUDA torch tensor of those types): the
         CSR conversion (`csr_matrix(X)`: entries != 0, column order) happens on the device."""
@@ -229,6 +250,9 @@ class Engine:
         n, g = int(X.shape[0]), int(X.shape[1])
         col_sums = np.zeros(g, dtype=np.float64)
         total, bad, empty = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+        if on_device:
+            import torch
+            torch.cuda.current_stream().synchronize()        # the engine runs on its own stream
         self._check(self._lib.lrperm_stage_matrix_dense(
             self._h, n, g, C.c_void_p(ptr), int(is64), int(max(stride, g)), int(on_device),
             None if keep_ptr is None else C.c_void_p(keep_ptr), C.c_void_p(col_sums.ctypes.data),

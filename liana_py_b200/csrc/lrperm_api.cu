@@ -1700,7 +1700,7 @@ int stage_finish(lrperm_engine* h, const char* what, int64_t n_cells, int64_t n_
     double* d_small = h->st_small.as<double>();
     if (n_cells > 0) {
         stage_stats_kernel<<<grid_for(n_cells * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
-            h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(),
+            h->st_indptr.as<int64_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(),
             row_keep ? h->st_row_keep.as<uint8_t>() : nullptr, (int32_t)n_cells, (int32_t)n_genes, d_small,
             d_small + n_genes, reinterpret_cast<unsigned long long*>(d_small + n_genes + 1),
             reinterpret_cast<unsigned long long*>(d_small + n_genes + 2), h->err_flag.as<int>());
@@ -1739,14 +1739,15 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
         else memcpy(last, src, isz);
         if (indptr_is_64) { int64_t v; memcpy(&v, last, 8); nnz = v; } else { int32_t v; memcpy(&v, last, 4); nnz = v; }
     }
-    if (nnz < 0 || nnz >= 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: nnz=%lld must be in [0, 2^31)", (long long)nnz);
+    // the STAGED matrix may hold 2^31 entries or more (int64 row pointers on the device); the committed one may not
+    if (nnz < 0 || nnz >= (1LL << 40)) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_csr: nnz=%lld must be in [0, 2^40)", (long long)nnz);
     if (nnz > 0 && (!indices || !data)) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: NULL indices/data");
-    CK(h->st_indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    CK(h->st_indptr.ensure(sizeof(int64_t) * (size_t)(n_cells + 1)));
     if ((rc = upload(h, h->tmp_a, indptr, isz * (size_t)(n_cells + 1), on_device))) return rc;
     if (indptr_is_64)
-        narrow_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int64_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
+        widen_indptr_kernel<int64_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int64_t>(), n_cells + 1, h->st_indptr.as<int64_t>(), h->err_flag.as<int>());
     else
-        narrow_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int32_t>(), n_cells + 1, h->st_indptr.as<int32_t>(), h->err_flag.as<int>());
+        widen_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int32_t>(), n_cells + 1, h->st_indptr.as<int64_t>(), h->err_flag.as<int>());
     CK_LAUNCH();
     if ((rc = upload(h, h->st_indices, indices, sizeof(int32_t) * (size_t)nnz, on_device))) return rc;
     if ((rc = upload(h, h->st_data, data, sizeof(float) * (size_t)nnz, on_device))) return rc;
@@ -1775,38 +1776,37 @@ int lrperm_stage_matrix_dense(lrperm_engine* h, int64_t n_cells, int64_t n_genes
         X = dense.p;
     }
     struct Release { DevBuf& b; cudaStream_t s; ~Release() { if (b.p) { cudaStreamSynchronize(s); b.release(); } } } release{dense, h->stream};
-    CK(h->st_indptr.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
-    CK(h->tmp_a.ensure(sizeof(int32_t) * (size_t)(n_cells + 1)));
+    CK(h->st_indptr.ensure(sizeof(int64_t) * (size_t)(n_cells + 1)));
+    CK(h->tmp_a.ensure(sizeof(int64_t) * (size_t)(n_cells + 1)));
     CK(h->small_b.ensure(16));
     CK(cudaMemsetAsync(h->small_b.p, 0, 16, h->stream));
-    CK(cudaMemsetAsync(h->tmp_a.p, 0, sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->tmp_a.p, 0, sizeof(int64_t), h->stream));
     const int grid = grid_for(std::max<int64_t>(n_cells, 1) * 32, 256, h->sm_count * 32);
     if (n_cells > 0) {
         if (values_are_f64)
-            dense_count_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->tmp_a.as<int32_t>(), h->small_b.as<unsigned long long>());
+            dense_count_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->tmp_a.as<int64_t>(), h->small_b.as<unsigned long long>());
         else
-            dense_count_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->tmp_a.as<int32_t>(), h->small_b.as<unsigned long long>());
+            dense_count_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->tmp_a.as<int64_t>(), h->small_b.as<unsigned long long>());
         CK_LAUNCH();
     }
     unsigned long long total = 0;
     CK(cudaMemcpyAsync(&total, h->small_b.p, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (total >= 0x7fffffffULL) return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_stage_matrix_dense: %llu stored entries, must be < 2^31", total);
     const int64_t nnz = (int64_t)total;
     {
-        // inclusive scan of counts[1..N] with counts[0] = 0 == exclusive row pointers (total < 2^31: no overflow)
+        // inclusive scan of counts[1..N] with counts[0] = 0 == exclusive row pointers (int64: no 2^31 limit here)
         size_t tmp_bytes = 0;
-        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, h->tmp_a.as<int32_t>(), h->st_indptr.as<int32_t>(), (int)(n_cells + 1), h->stream));
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, h->tmp_a.as<int64_t>(), h->st_indptr.as<int64_t>(), (int)(n_cells + 1), h->stream));
         CK(h->sort_tmp.ensure(tmp_bytes));
-        CK(cub::DeviceScan::InclusiveSum(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<int32_t>(), h->st_indptr.as<int32_t>(), (int)(n_cells + 1), h->stream));
+        CK(cub::DeviceScan::InclusiveSum(h->sort_tmp.p, tmp_bytes, h->tmp_a.as<int64_t>(), h->st_indptr.as<int64_t>(), (int)(n_cells + 1), h->stream));
     }
     CK(h->st_indices.ensure(sizeof(int32_t) * (size_t)nnz));
     CK(h->st_data.ensure(sizeof(float) * (size_t)nnz));
     if (n_cells > 0 && nnz > 0) {
         if (values_are_f64)
-            dense_fill_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>());
+            dense_fill_kernel<double><<<grid, 256, 0, h->stream>>>(static_cast<const double*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->st_indptr.as<int64_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>());
         else
-            dense_fill_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>());
+            dense_fill_kernel<float><<<grid, 256, 0, h->stream>>>(static_cast<const float*>(X), row_stride, (int32_t)n_cells, (int32_t)n_genes, h->st_indptr.as<int64_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>());
         CK_LAUNCH();
     }
     return stage_finish(h, "lrperm_stage_matrix_dense", n_cells, n_genes, nnz, row_keep, on_device, col_sums, kept_total,
@@ -1822,7 +1822,7 @@ int lrperm_staged_max(lrperm_engine* h, float* max_stored, int64_t* n_stored) {
     CK(cudaMemsetAsync(h->small_b.p, 0, 16, h->stream));
     if (h->st_N > 0 && h->st_nnz > 0) {
         stage_max_kernel<<<grid_for(h->st_N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
-            h->st_indptr.as<int32_t>(), h->st_data.as<float>(), h->st_has_keep ? h->st_row_keep.as<uint8_t>() : nullptr,
+            h->st_indptr.as<int64_t>(), h->st_data.as<float>(), h->st_has_keep ? h->st_row_keep.as<uint8_t>() : nullptr,
             (int32_t)h->st_N, h->small_b.as<uint32_t>(), reinterpret_cast<unsigned long long*>(h->small_b.as<unsigned char>() + 8));
         CK_LAUNCH();
     }
@@ -1854,7 +1854,7 @@ int lrperm_staged_cluster_stats(lrperm_engine* h, const int32_t* row_label, int3
         const int n_blocks = (int)std::min<int64_t>(h->st_N, (int64_t)h->sm_count * 16);
         CK(h->tmp_a.ensure(sizeof(double) * 2 * L * (size_t)n_blocks));
         staged_cluster_stats_kernel<<<n_blocks, 32, sizeof(double) * 2 * L, h->stream>>>(
-            h->st_indptr.as<int32_t>(), h->st_data.as<float>(), h->tmp_d.as<int32_t>(), (int32_t)h->st_N, n_clusters, h->tmp_a.as<double>());
+            h->st_indptr.as<int64_t>(), h->st_data.as<float>(), h->tmp_d.as<int32_t>(), (int32_t)h->st_N, n_clusters, h->tmp_a.as<double>());
         CK_LAUNCH();
         staged_cluster_stats_reduce_kernel<<<grid_for((int64_t)(2 * L), 128, 1 << 30), 128, 0, h->stream>>>(
             h->tmp_a.as<double>(), n_blocks, (int32_t)(2 * L), h->small_b.as<double>());
@@ -1915,9 +1915,17 @@ int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_gen
     CK(h->indptr.ensure(sizeof(int32_t) * (size_t)(N_out + 1)));
     int64_t nnz_out = 0;
     if (N > 0) {
+        CK(h->small_b.ensure(16));
+        CK(cudaMemsetAsync(h->small_b.p, 0, 8, h->stream));
         mapped_count_kernel<<<grid_for(N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
-            h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), d_map.as<int32_t>(), d_newrow.as<int32_t>(), (int32_t)N, d_counts.as<int32_t>());
+            h->st_indptr.as<int64_t>(), h->st_indices.as<int32_t>(), d_map.as<int32_t>(), d_newrow.as<int32_t>(), (int32_t)N, d_counts.as<int32_t>(),
+            h->small_b.as<unsigned long long>());
         CK_LAUNCH();
+        unsigned long long kept = 0;
+        CK(cudaMemcpyAsync(&kept, h->small_b.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (kept >= 0x7fffffffULL)
+            return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_commit_matrix: %llu entries survive the row / column filter, must be < 2^31", kept);
     }
     {
         size_t tmp_bytes = 0;
@@ -1934,7 +1942,7 @@ int lrperm_commit_matrix(lrperm_engine* h, const int32_t* col_map, int64_t n_gen
     CK(h->csr_pairs.ensure(sizeof(int2) * (size_t)std::max<int64_t>(nnz_out, 1)));
     if (N > 0 && nnz_out > 0) {
         mapped_scatter_kernel<<<grid_for(N * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(
-            h->st_indptr.as<int32_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), d_map.as<int32_t>(), d_newrow.as<int32_t>(),
+            h->st_indptr.as<int64_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(), d_map.as<int32_t>(), d_newrow.as<int32_t>(),
             (int32_t)N, h->indptr.as<int32_t>(), h->tmp_c.as<int32_t>(), h->tmp_d.as<float>());
         CK_LAUNCH();
         pack_csr_kernel<<<grid_for(N_out * 32, 256, h->sm_count * 32), 256, 0, h->stream>>>(

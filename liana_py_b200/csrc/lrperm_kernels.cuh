@@ -104,7 +104,7 @@ __global__ void pack_csr_kernel(const int32_t* __restrict__ indptr, const int32_
 // One warp per row of the staged matrix: per-column sums over ALL rows (float64 atomics; used only for
 // the "gene is empty" test and the matrix mean), number of non-finite values, number of empty rows,
 // total over the kept rows.
-__global__ void stage_stats_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+__global__ void stage_stats_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                    const float* __restrict__ data, const uint8_t* __restrict__ row_keep, int32_t N, int32_t G,
                                    double* __restrict__ col_sums, double* __restrict__ kept_total,
                                    unsigned long long* __restrict__ n_nonfinite, unsigned long long* __restrict__ n_empty_rows,
@@ -115,9 +115,9 @@ __global__ void stage_stats_kernel(const int32_t* __restrict__ indptr, const int
     double block_total = 0.0;
     unsigned long long bad = 0, empty = 0;
     for (int r = warp; r < N; r += nwarps) {
-        const int s = indptr[r], e = indptr[r + 1];
+        const int64_t s = indptr[r], e = indptr[r + 1];
         double row = 0.0;
-        for (int o = s + lane; o < e; o += 32) {
+        for (int64_t o = s + lane; o < e; o += 32) {
             const int c = indices[o];
             const float v = data[o];
             if (c < 0 || c >= G) { atomicOr(err, 1); continue; }
@@ -145,7 +145,7 @@ __global__ void stage_stats_kernel(const int32_t* __restrict__ indptr, const int
 // pass 1 counts a row's stored entries (-> counts[r + 1], 64-bit total), pass 2 compacts them behind indptr[r] with a
 // ballot prefix so the column order is kept.  T = float or double (rounded to float32 like `astype(np.float32)`).
 template <typename T>
-__global__ void dense_count_kernel(const T* __restrict__ X, int64_t ld, int32_t N, int32_t G, int32_t* __restrict__ counts,
+__global__ void dense_count_kernel(const T* __restrict__ X, int64_t ld, int32_t N, int32_t G, int64_t* __restrict__ counts,
                                    unsigned long long* __restrict__ total) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -164,7 +164,7 @@ __global__ void dense_count_kernel(const T* __restrict__ X, int64_t ld, int32_t 
 }
 
 template <typename T>
-__global__ void dense_fill_kernel(const T* __restrict__ X, int64_t ld, int32_t N, int32_t G, const int32_t* __restrict__ indptr,
+__global__ void dense_fill_kernel(const T* __restrict__ X, int64_t ld, int32_t N, int32_t G, const int64_t* __restrict__ indptr,
                                   int32_t* __restrict__ indices, float* __restrict__ data) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -172,7 +172,7 @@ __global__ void dense_fill_kernel(const T* __restrict__ X, int64_t ld, int32_t N
     const uint32_t below = (1u << lane) - 1u;
     for (int r = warp; r < N; r += nwarps) {
         const T* row = X + (int64_t)r * ld;
-        int base = indptr[r];
+        int64_t base = indptr[r];
         for (int c0 = 0; c0 < G; c0 += 32) {
             const int c = c0 + lane;
             const T t = c < G ? row[c] : (T)0;
@@ -180,7 +180,7 @@ __global__ void dense_fill_kernel(const T* __restrict__ X, int64_t ld, int32_t N
             const bool keep = t != (T)0;
             const uint32_t m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
-                const int o = base + __popc(m & below);
+                const int64_t o = base + __popc(m & below);
                 indices[o] = c;
                 data[o] = v;
             }
@@ -196,7 +196,7 @@ __device__ __forceinline__ uint32_t float_order_key(float v) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__global__ void stage_max_kernel(const int32_t* __restrict__ indptr, const float* __restrict__ data,
+__global__ void stage_max_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ data,
                                  const uint8_t* __restrict__ row_keep, int32_t N, uint32_t* __restrict__ max_key,
                                  unsigned long long* __restrict__ n_stored) {
     const int lane = threadIdx.x & 31;
@@ -206,8 +206,8 @@ __global__ void stage_max_kernel(const int32_t* __restrict__ indptr, const float
     unsigned long long stored = 0;
     for (int r = warp; r < N; r += nwarps) {
         if (row_keep && !row_keep[r]) continue;
-        const int s = indptr[r], e = indptr[r + 1];
-        for (int o = s + lane; o < e; o += 32) best = max(best, float_order_key(data[o]));
+        const int64_t s = indptr[r], e = indptr[r + 1];
+        for (int64_t o = s + lane; o < e; o += 32) best = max(best, float_order_key(data[o]));
         if (lane == 0) stored += (unsigned long long)(e - s);
     }
 #pragma unroll
@@ -233,7 +233,7 @@ __global__ void validate_columns_kernel(const int32_t* __restrict__ indices, int
 // row_label[r] = cluster of staged row r, -1 = row not kept.  float64 and DETERMINISTIC: one warp per CTA walks its
 // rows in a fixed order into private shared accumulators (no atomics), the per-CTA partials are summed in CTA order.
 __global__ void __launch_bounds__(32)
-staged_cluster_stats_kernel(const int32_t* __restrict__ indptr, const float* __restrict__ data,
+staged_cluster_stats_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ data,
                             const int32_t* __restrict__ row_label, int32_t N, int32_t L,
                             double* __restrict__ partial /*[gridDim.x][2 L]*/) {
     extern __shared__ double cs_smem[];          // [2][L]
@@ -243,9 +243,9 @@ staged_cluster_stats_kernel(const int32_t* __restrict__ indptr, const float* __r
     for (int r = blockIdx.x; r < N; r += gridDim.x) {
         const int c = row_label[r];
         if (c < 0 || c >= L) continue;
-        const int s = indptr[r], e = indptr[r + 1];
+        const int64_t s = indptr[r], e = indptr[r + 1];
         double a = 0.0, b = 0.0;
-        for (int o = s + lane; o < e; o += 32) { const double x = (double)data[o]; a += x; b += x * x; }
+        for (int64_t o = s + lane; o < e; o += 32) { const double x = (double)data[o]; a += x; b += x * x; }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
         if (lane == 0) { cs_smem[c] += a; cs_smem[L + c] += b; }
@@ -265,26 +265,28 @@ __global__ void staged_cluster_stats_reduce_kernel(const double* __restrict__ pa
 }
 
 // entries of every KEPT row that survive the column map -> counts[new_row]
-__global__ void mapped_count_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+__global__ void mapped_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                     const int32_t* __restrict__ col_map, const int32_t* __restrict__ new_row /*[N], -1 = dropped*/,
-                                    int32_t N, int32_t* __restrict__ counts) {
+                                    int32_t N, int32_t* __restrict__ counts, unsigned long long* __restrict__ total) {
     const int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long mine = 0;
     for (int r = warp; r < N; r += nwarps) {
         const int nr = new_row[r];
         if (nr < 0) continue;
-        const int s = indptr[r], e = indptr[r + 1];
+        const int64_t s = indptr[r], e = indptr[r + 1];
         int n = 0;
-        for (int o = s + lane; o < e; o += 32) n += col_map[indices[o]] >= 0;
+        for (int64_t o = s + lane; o < e; o += 32) n += col_map[indices[o]] >= 0;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
-        if (lane == 0) counts[nr] = n;
+        if (lane == 0) { counts[nr] = n; mine += (unsigned long long)n; }
     }
+    if (lane == 0 && mine) atomicAdd(total, mine);       // the committed matrix must stay below 2^31 entries
 }
 
 // order-preserving compaction of the kept entries into (out_indices, out_data) at out_indptr[new_row]
-__global__ void mapped_scatter_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+__global__ void mapped_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                       const float* __restrict__ data, const int32_t* __restrict__ col_map,
                                       const int32_t* __restrict__ new_row, int32_t N, const int32_t* __restrict__ out_indptr,
                                       int32_t* __restrict__ out_indices, float* __restrict__ out_data) {
@@ -295,9 +297,9 @@ __global__ void mapped_scatter_kernel(const int32_t* __restrict__ indptr, const 
     for (int r = warp; r < N; r += nwarps) {
         const int nr = new_row[r];
         if (nr < 0) continue;
-        const int s = indptr[r], e = indptr[r + 1];
+        const int64_t s = indptr[r], e = indptr[r + 1];
         int w = out_indptr[nr];
-        for (int o = s; o < e; o += 32) {
+        for (int64_t o = s; o < e; o += 32) {
             const bool in = o + lane < e;
             const int c = in ? col_map[indices[o + lane]] : -1;
             const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
@@ -330,6 +332,19 @@ __global__ void narrow_indptr_kernel(const T* __restrict__ in, int64_t n, int32_
         if (v < 0 || (int64_t)v > 0x7fffffffLL) atomicOr(err, 2);
         if (i > 0 && in[i - 1] > v) atomicOr(err, 4);
         out[i] = (int32_t)v;
+    }
+}
+
+// Row pointers of the STAGED (caller's full) matrix: validated and kept as int64 - the full matrix of an atlas-sized
+// input exceeds 2^31 stored entries long before its resource-gene subset (the engine matrix, int32 offsets) does.
+template <typename T>
+__global__ void widen_indptr_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const T v = in[i];
+        if (v < 0) atomicOr(err, 2);
+        if (i > 0 && in[i - 1] > v) atomicOr(err, 4);
+        out[i] = (int64_t)v;
     }
 }
 
