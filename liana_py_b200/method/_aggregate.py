@@ -57,7 +57,8 @@ def robust_rank_aggregate(rmat: np.ndarray) -> np.ndarray:
     return np.clip(np.min(p, axis=1) * n, a_min=0, a_max=1)
 
 
-def aggregate(lr_res: pd.DataFrame, consensus, aggregate_method: str = "rra", consensus_opts=None, engine=None) -> pd.DataFrame:
+def aggregate(lr_res: pd.DataFrame, consensus, aggregate_method: str = "rra", consensus_opts=None, engine=None,
+              sort: bool = True) -> pd.DataFrame:
     """`_aggregate` (`_aggregate.py:7-67`) on the already-joined frame (key columns + every method's
     score columns).  Adds `consensus.specificity` / `consensus.magnitude` and sorts by the last one."""
     if consensus_opts is None:
@@ -69,5 +70,7 @@ def aggregate(lr_res: pd.DataFrame, consensus, aggregate_method: str = "rra", co
     if "Magnitude" in consensus_opts:
         lr_res[consensus.magnitude] = rank_aggregate_scores(lr_res, consensus.magnitude_specs, aggregate_method, engine)
         order_col = consensus.magnitude
+    if not sort:                                 # the caller orders the frame (once) itself
+        return lr_res
     from ._pipeline import sort_frame
     return sort_frame(engine, lr_res, order_col, True)

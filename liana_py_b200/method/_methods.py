@@ -137,10 +137,9 @@ class Method(MethodMeta):
                                perm_source, order, gmean_mode, dist, add_cols=add_cols)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
-        liana_res = PL.sort_frame(state.engine, liana_res, orderby, ascending)
         if not _names:                          # by_sample across ranks: (code frame, name tables), see by_sample
-            return liana_res, PL.name_tables(state)
-        liana_res = PL.materialise_names(state, liana_res)
+            return PL.sort_frame(state.engine, liana_res, orderby, ascending), PL.name_tables(state)
+        liana_res = PL.finish_frame(state, liana_res, orderby, ascending)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
@@ -187,7 +186,9 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
             null = NullCounts(out[method.engine_score], n_perms)
     magnitude, specificity = method.fun(x, null) if method.permute else method.fun(x)
     spec_name = method.specificity if (not method.permute or n_perms is not None) else None
-    lr_res = (lr_res[K.PRIMARY] if aggregate_flag else lr_res).copy()     # the cached base frame stays untouched
+    # the cached base frame stays untouched: a shallow copy shares its (never written) columns, the score columns
+    # added below are new arrays owned by the copy
+    lr_res = (lr_res[K.PRIMARY] if aggregate_flag else lr_res).copy(deep=False)
     if return_all_lrs:
         lr_res[K.LRS_TO_KEEP] = kept
     if method.magnitude is not None:

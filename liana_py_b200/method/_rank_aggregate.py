@@ -78,14 +78,19 @@ class AggregateClass(MethodMeta):
             for col in f.columns:
                 if col not in lr_res.columns:                   # duplicated score names keep the first (`:47-49`)
                     lr_res[col] = f[col].values
+        # `_aggregate` sorts by its last consensus column and `liana_pipe` by the magnitude (`_aggregate.py:65`,
+        # `_liana_pipe.py:246-250`); sorting a sorted frame again changes nothing, so the frame is ordered once
         lr_res = aggregate(lr_res, consensus=self, aggregate_method=aggregate_method, consensus_opts=consensus_opts,
-                           engine=state.engine)
+                           engine=state.engine, sort=False)
         orderby = self.magnitude if self.magnitude in lr_res.columns else self.specificity
-        if orderby in lr_res.columns:
-            lr_res = PL.sort_frame(state.engine, lr_res, orderby, True)   # `_liana_pipe.py:246-250`
-        if not _names:                          # by_sample across ranks: (code frame, name tables)
+        if orderby not in lr_res.columns:       # no consensus column was asked for: rows stay as they are
+            lr_res = lr_res if not _names else PL.materialise_names(state, lr_res)
+        elif not _names:                        # by_sample across ranks: (code frame, name tables)
+            lr_res = PL.sort_frame(state.engine, lr_res, orderby, True)
+        else:
+            lr_res = PL.finish_frame(state, lr_res, orderby, True)
+        if not _names:
             return lr_res, PL.name_tables(state)
-        lr_res = PL.materialise_names(state, lr_res)
         if inplace:
             adata.uns[key_added] = lr_res
         return None if inplace else lr_res
