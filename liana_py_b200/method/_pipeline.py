@@ -302,7 +302,7 @@ def finish_frame(state: PipelineState, frame: pd.DataFrame, by: str, ascending: 
 def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame: pd.DataFrame, add_cols) -> pd.DataFrame:
     """Method-specific statistic columns of the rows in `tri` (the resolved min-subunit gene of every row
     carries its own statistics through `filter_reassemble_complexes`, `_reassemble_complexes.py:60-66`)."""
-    frame = frame.copy()
+    frame = frame.copy(deep=False)           # new columns only; the cached base frame is not written
     for col in add_cols:
         if col == "ligand_zscores":
             frame[col] = state.zscores()[tri.src, tri.lig_gene]
