@@ -469,10 +469,14 @@ class Engine:
                                              C.c_void_p(out.ctypes.data), 0))
         return out
 
-    def rra(self, rmat) -> np.ndarray:
-        """RobustRankAggregate rho per row of a rank matrix [n_rows, n_cols] (`_aggregate.py:110-181`)."""
+    def rra(self, rmat, col_max=None) -> np.ndarray:
+        """RobustRankAggregate rho per row of a rank matrix [n_rows, n_cols] (`_aggregate.py:110-181`); `col_max` =
+        the column maxima when the caller has them (an axis-0 reduction of a row-major matrix is slow in NumPy)."""
         r = np.ascontiguousarray(rmat, dtype=np.float64)
-        col_max = np.ascontiguousarray(r.max(axis=0)) if r.shape[0] else np.ones(r.shape[1])
+        if col_max is not None:
+            col_max = np.ascontiguousarray(col_max, dtype=np.float64)
+        else:
+            col_max = np.ascontiguousarray(r.max(axis=0)) if r.shape[0] else np.ones(r.shape[1])
         out = np.empty(r.shape[0], dtype=np.float64)
         self._check(self._lib.lrperm_rra(self._h, int(r.shape[0]), int(r.shape[1]), C.c_void_p(r.ctypes.data),
                                          C.c_void_p(col_max.ctypes.data), C.c_void_p(out.ctypes.data), 0))

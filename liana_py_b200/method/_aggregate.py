@@ -42,7 +42,11 @@ def rank_aggregate_scores(lr_res: pd.DataFrame, specs: dict, aggregate_method: s
     # is symmetric, so the order of the columns does not change the result
     rmat = np.stack([ranks[name] for name in ranks], axis=1)
     if aggregate_method == "rra":
-        return robust_rank_aggregate(rmat) if engine is None else engine.rra(rmat)
+        if engine is None:
+            return robust_rank_aggregate(rmat)
+        # column maxima from the contiguous rank vectors (np.max propagates NaN like the axis-0 maximum of the matrix)
+        col_max = [np.max(ranks[name]) if len(ranks[name]) else 1.0 for name in ranks]
+        return engine.rra(rmat, col_max)
     return np.mean(rmat, axis=1) / rmat.shape[0]
 
 

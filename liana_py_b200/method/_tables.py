@@ -32,37 +32,63 @@ class ResourceTables:
     entities: np.ndarray           # sorted gene names used by the kept interactions
 
 
+@dataclass
+class ExplodedResource:
+    """A resource split into subunits ONCE (the Python string work), independent of any dataset."""
+    ligand_complex: np.ndarray     # [n_int] str, resource order
+    receptor_complex: np.ndarray   # [n_int] str
+    lig_all: np.ndarray            # [n_int, max_l] index into `entities`, -1 padded
+    rec_all: np.ndarray            # [n_int, max_r]
+    entities: np.ndarray           # sorted subunit symbols named anywhere in the resource
+
+
+def explode_resource(resource: pd.DataFrame, sep: str = "_") -> ExplodedResource:
+    lig = [str(x) for x in resource["ligand"].astype(str)]
+    rec = [str(x) for x in resource["receptor"].astype(str)]
+    lig_lists, rec_lists = [x.split(sep) for x in lig], [x.split(sep) for x in rec]
+    ents = sorted({g for lst in lig_lists for g in lst} | {g for lst in rec_lists for g in lst})
+    pos = {g: i for i, g in enumerate(ents)}
+    n = len(lig)
+    max_l = max((len(x) for x in lig_lists), default=1)
+    max_r = max((len(x) for x in rec_lists), default=1)
+    lig_all = np.full((n, max_l), -1, dtype=np.int32)
+    rec_all = np.full((n, max_r), -1, dtype=np.int32)
+    for i, (ls, rs) in enumerate(zip(lig_lists, rec_lists)):
+        lig_all[i, :len(ls)] = [pos[g] for g in ls]
+        rec_all[i, :len(rs)] = [pos[g] for g in rs]
+    return ExplodedResource(np.array(lig, dtype=str), np.array(rec, dtype=str), lig_all, rec_all, np.array(ents, dtype=str))
+
+
 def resource_entities(resource: pd.DataFrame, sep: str = "_") -> np.ndarray:
     """All subunit symbols named by the resource (np.union1d of exploded ligand / receptor)."""
-    genes = set()
-    for col in ("ligand", "receptor"):
-        for entry in resource[col].astype(str):
-            genes.update(entry.split(sep))
-    return np.array(sorted(genes), dtype=str)
+    return explode_resource(resource, sep).entities
+
+
+def tables_for_genes(ex: ExplodedResource, var_names: np.ndarray) -> ResourceTables:
+    """Drop interactions with any subunit missing from `var_names` (filter_resource), then index the remaining
+    subunits into the gene-subset column space (sorted intersection of resource entities and var_names,
+    `_liana_pipe.py:161-164`).  Array operations only: `by_sample` calls this once per sample, because every sample
+    has its own set of non-empty genes."""
+    present = pd.Index(np.asarray(var_names, dtype=str)).get_indexer(ex.entities) >= 0 if len(ex.entities) else np.zeros(0, bool)
+    present = np.append(present, True)                           # index -1 (padding) counts as present
+    ok = present[ex.lig_all].all(axis=1) & present[ex.rec_all].all(axis=1)
+    lig_all, rec_all = ex.lig_all[ok], ex.rec_all[ok]
+    used = np.zeros(len(ex.entities) + 1, dtype=bool)
+    used[lig_all.reshape(-1)] = True
+    used[rec_all.reshape(-1)] = True
+    used = used[:-1]                                             # the slot the -1 padding wrote to
+    remap = np.append(np.cumsum(used, dtype=np.int64) - 1, -1).astype(np.int32)   # old entity -> kept entity; -1 stays -1
+    lig_sub, rec_sub = remap[lig_all], remap[rec_all]
+    # trailing all-padding columns go (widths = longest kept complex, as when built from the kept rows only)
+    max_l = max(int((lig_sub >= 0).sum(axis=1).max(initial=1)), 1)
+    max_r = max(int((rec_sub >= 0).sum(axis=1).max(initial=1)), 1)
+    return ResourceTables(ex.ligand_complex[ok], ex.receptor_complex[ok], np.ascontiguousarray(lig_sub[:, :max_l]),
+                          np.ascontiguousarray(rec_sub[:, :max_r]), ex.entities[used])
 
 
 def build_resource_tables(resource: pd.DataFrame, var_names: np.ndarray, sep: str = "_"):
-    """Drop interactions with any subunit missing from `var_names` (filter_resource), then index
-    the remaining subunits into the gene-subset column space (sorted intersection of resource
-    entities and var_names, `_liana_pipe.py:161-164`).  Returns (tables, entities)."""
-    present = set(map(str, var_names))
-    lig_lists, rec_lists, lc, rc = [], [], [], []
-    for lig, rec in zip(resource["ligand"].astype(str), resource["receptor"].astype(str)):
-        ls, rs = lig.split(sep), rec.split(sep)
-        if all(x in present for x in ls) and all(x in present for x in rs):
-            lig_lists.append(ls); rec_lists.append(rs); lc.append(lig); rc.append(rec)
-    ents = sorted({g for lst in lig_lists for g in lst} | {g for lst in rec_lists for g in lst})
-    entities = np.array(ents, dtype=str)
-    pos = {g: i for i, g in enumerate(ents)}
-    n = len(lc)
-    max_l = max((len(x) for x in lig_lists), default=1)
-    max_r = max((len(x) for x in rec_lists), default=1)
-    lig_sub = np.full((n, max_l), -1, dtype=np.int32)
-    rec_sub = np.full((n, max_r), -1, dtype=np.int32)
-    for i, (ls, rs) in enumerate(zip(lig_lists, rec_lists)):
-        lig_sub[i, :len(ls)] = [pos[g] for g in ls]
-        rec_sub[i, :len(rs)] = [pos[g] for g in rs]
-    return ResourceTables(np.array(lc, dtype=str), np.array(rc, dtype=str), lig_sub, rec_sub, entities)
+    """(ResourceTables for `var_names`) from a resource frame; see `explode_resource` / `tables_for_genes`."""
+    return tables_for_genes(explode_resource(resource, sep), var_names)
 
 
 def _resolve_side(sub: np.ndarray, means: np.ndarray, props: np.ndarray, first_subunit: bool):

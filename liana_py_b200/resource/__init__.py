@@ -13,6 +13,7 @@ import os
 import pandas as pd
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
+_PARSED = {}       # resource name -> parsed frame (callers get copies; `by_sample` asks once per sample)
 
 
 def show_resources():
@@ -26,7 +27,9 @@ def select_resource(resource_name: str = "consensus") -> pd.DataFrame:
     if not os.path.exists(path):
         raise ValueError(f"Resource {name} not found. Please choose from {show_resources()} "
                          "or pass a DataFrame via `resource=`.")
-    return pd.read_csv(path, index_col=False)
+    if name not in _PARSED:
+        _PARSED[name] = pd.read_csv(path, index_col=False)
+    return _PARSED[name].copy()
 
 
 def handle_resource(interactions=None, resource=None, resource_name=None, verbose=False) -> pd.DataFrame:

@@ -165,3 +165,46 @@ def test_prepare_input_dense_matrix_goes_to_the_device_conversion():
             assert list(got.var_names) == list(want.var_names) and np.array_equal(got.var_cols, want.var_cols)
             assert np.array_equal(got.labels, want.labels) and got.mat_max == want.mat_max
             assert got.mat_mean == want.mat_mean and np.allclose(got.cluster_stats[1], want.cluster_stats[1])
+
+
+def test_resource_tables_vectorised_equal_plain_restatement():
+    """`_tables.tables_for_genes` (array operations on the once-exploded resource, what `by_sample` runs per sample)
+    against a plain loop over the interactions (`filter_resource`, liana/method/_pipe_utils/_pre.py:188-224, +
+    explode_complexes): kept interactions, their order, subunit indices, padding widths, entities - for several
+    bundled resources and gene sets from complete to empty."""
+    from liana_py_b200.method import _tables
+    from liana_py_b200.resource import select_resource
+
+    def plain(resource, var_names, sep="_"):
+        present = set(map(str, var_names))
+        L, R, lc, rc = [], [], [], []
+        for lig, rec in zip(resource["ligand"].astype(str), resource["receptor"].astype(str)):
+            ls, rs = lig.split(sep), rec.split(sep)
+            if all(x in present for x in ls) and all(x in present for x in rs):
+                L.append(ls); R.append(rs); lc.append(lig); rc.append(rec)
+        ents = sorted({g for l in L for g in l} | {g for l in R for g in l})
+        pos = {g: i for i, g in enumerate(ents)}
+        a = np.full((len(lc), max((len(x) for x in L), default=1)), -1, np.int32)
+        b = np.full((len(lc), max((len(x) for x in R), default=1)), -1, np.int32)
+        for i, (ls, rs) in enumerate(zip(L, R)):
+            a[i, :len(ls)] = [pos[g] for g in ls]
+            b[i, :len(rs)] = [pos[g] for g in rs]
+        return np.array(lc, dtype=str), np.array(rc, dtype=str), a, b, np.array(ents, dtype=str)
+
+    rng = np.random.default_rng(0)
+    for name in ("consensus", "cellphonedb", "cellchatdb", "mouseconsensus", "kirouac2010"):
+        res = select_resource(name)
+        ex = _tables.explode_resource(res)
+        assert np.array_equal(ex.entities, _tables.resource_entities(res)) and len(ex.ligand_complex) == len(res)
+        for frac in (1.0, 0.7, 0.2, 0.0):
+            sub = ex.entities[rng.random(len(ex.entities)) < frac] if frac < 1 else ex.entities
+            names = np.concatenate([sub, np.array(["BG1", "BG2"])])
+            rng.shuffle(names)
+            t, w = _tables.tables_for_genes(ex, names), plain(res, names)
+            assert np.array_equal(t.ligand_complex, w[0]) and np.array_equal(t.receptor_complex, w[1]), (name, frac)
+            assert t.lig_sub.shape == w[2].shape and np.array_equal(t.lig_sub, w[2]), (name, frac)
+            assert t.rec_sub.shape == w[3].shape and np.array_equal(t.rec_sub, w[3]), (name, frac)
+            assert np.array_equal(t.entities, w[4]), (name, frac)
+    # the parsed resource is cached: callers get independent copies
+    a = select_resource("consensus"); a.loc[0, "ligand"] = "changed"
+    assert select_resource("consensus").loc[0, "ligand"] != "changed"
