@@ -154,7 +154,13 @@ __global__ void dense_count_kernel(const T* __restrict__ X, int64_t ld, int32_t 
     for (int r = warp; r < N; r += nwarps) {
         const T* row = X + (int64_t)r * ld;
         int n = 0;
-        for (int c = lane; c < G; c += 32) n += (row[c] != (T)0) ? 1 : 0;     // tested in T: a double that underflows float32 stays stored
+        for (int c0 = lane; c0 < G; c0 += 128) {           // 4 independent 128 B loads in flight per warp
+            T t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = (c0 + 32 * k < G) ? row[c0 + 32 * k] : (T)0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) n += (t[k] != (T)0) ? 1 : 0;   // tested in T: a double that underflows float32 stays stored
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
         if (lane == 0) { counts[r + 1] = n; mine += (unsigned long long)n; }
@@ -173,18 +179,21 @@ __global__ void dense_fill_kernel(const T* __restrict__ X, int64_t ld, int32_t N
     for (int r = warp; r < N; r += nwarps) {
         const T* row = X + (int64_t)r * ld;
         int64_t base = indptr[r];
-        for (int c0 = 0; c0 < G; c0 += 32) {
-            const int c = c0 + lane;
-            const T t = c < G ? row[c] : (T)0;
-            const float v = (float)t;
-            const bool keep = t != (T)0;
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int64_t o = base + __popc(m & below);
-                indices[o] = c;
-                data[o] = v;
+        for (int c0 = 0; c0 < G; c0 += 128) {              // 4 independent 128 B loads in flight per warp
+            T t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = (c0 + 32 * k + lane < G) ? row[c0 + 32 * k + lane] : (T)0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool keep = t[k] != (T)0;
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int64_t o = base + __popc(m & below);
+                    indices[o] = c0 + 32 * k + lane;
+                    data[o] = (float)t[k];
+                }
+                base += __popc(m);
             }
-            base += __popc(m);
         }
     }
 }
