@@ -208,3 +208,28 @@ def test_resource_tables_vectorised_equal_plain_restatement():
     # the parsed resource is cached: callers get independent copies
     a = select_resource("consensus"); a.loc[0, "ligand"] = "changed"
     assert select_resource("consensus").loc[0, "ligand"] != "changed"
+
+
+def test_handle_resource_precedence_and_errors():
+    """Mirrors liana/tests/test_select_resource.py: interactions > resource > resource_name; sizes of the bundled
+    tables; ValueError when nothing is given, for a malformed interactions list and for a frame without the columns."""
+    from liana_py_b200.resource import handle_resource, select_resource, show_resources
+    r = handle_resource(interactions=[("a", "b"), ("c", "d"), ("a", "b")], resource=select_resource("consensus"),
+                        resource_name="consensus")
+    assert r.shape == (2, 2) and list(r.columns) == ["ligand", "receptor"]            # duplicates dropped, others ignored
+    r = handle_resource(interactions=None, resource=select_resource("consensus"), resource_name="ignore me")
+    assert r.shape[0] == 4624 and list(r.columns) == ["ligand", "receptor"]
+    r = handle_resource(interactions=None, resource=None, resource_name="CellChatDB")   # names are case-insensitive
+    assert r.shape[0] == 1912
+    assert "consensus" in show_resources() and len(show_resources()) == 17
+    with pytest.raises(ValueError):
+        handle_resource(interactions=None, resource=None, resource_name=None)
+    with pytest.raises(ValueError):
+        handle_resource(interactions=[("a", "b", "c")])
+    with pytest.raises(ValueError):
+        handle_resource(resource=pd.DataFrame({"x": ["a"], "y": ["b"]}))
+    with pytest.raises(ValueError, match="not found"):
+        select_resource("no_such_resource")
+    # a resource that names none of the data's genes is refused by the coverage check (`_pre.py:15-62`)
+    with pytest.raises(ValueError, match="Too few features"):
+        _pre.assert_covered(np.array(["A", "B", "C", "D"]), np.array(["X1", "X2"]))
