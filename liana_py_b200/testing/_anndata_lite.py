@@ -193,5 +193,21 @@ class MuDataLite:
     def shape(self):
         return (self.obs.shape[0], sum(m.shape[1] for m in self.mod.values()))
 
+    def __getitem__(self, key):
+        """Row subsetting (what `by_sample` does with a MuData): every modality and the shared obs."""
+        rows = AnnDataLite._row_selector(key, self.obs.shape[0])
+        obs = self.obs.iloc[rows].copy()
+        for c in obs.columns:
+            if isinstance(obs[c].dtype, pd.CategoricalDtype):
+                obs[c] = obs[c].cat.remove_unused_categories()
+        out = MuDataLite({k: m[rows] for k, m in self.mod.items()}, obs=obs)
+        out.uns = dict(self.uns)
+        return out
+
+    def copy(self):
+        out = MuDataLite({k: m.copy() for k, m in self.mod.items()}, obs=self.obs.copy())
+        out.obsp, out.obsm, out.uns = dict(self.obsp), dict(self.obsm), dict(self.uns)
+        return out
+
     def __repr__(self):
         return f"MuDataLite with {len(self.mod)} modalities, n_obs = {self.obs.shape[0]}"

@@ -259,6 +259,13 @@ def test_mudata_input_identical_to_reference():
     assert mdata.uns["liana_res"].shape == res.shape
     agg = li.mt.rank_aggregate(mdata, groupby="cluster", n_perms=None, use_raw=False, inplace=False, mdata_kwargs=mkw)
     assert len(agg) == len(res) and "magnitude_rank" in agg.columns
+    # by_sample on a MuData: the samples are row subsets of every modality (`_Method.py:138-152`)
+    rng = np.random.default_rng(1)
+    mdata.obs["sample"] = pd.Categorical(rng.choice(["s1", "s2"], size=mdata.obs.shape[0]))
+    per = li.mt.cellphonedb.by_sample(mdata, "sample", inplace=False, **kw)
+    one = li.mt.cellphonedb(mdata[np.asarray(mdata.obs["sample"] == "s2")].copy(), inplace=False, **kw)
+    got = per[per["sample"] == "s2"].drop(columns="sample").sort_values(KEY).reset_index(drop=True)
+    assert got.equals(one.sort_values(KEY).reset_index(drop=True))
     with pytest.raises(ValueError, match="is not in the mdata"):
         li.mt.cellphonedb(mdata, groupby="cluster", n_perms=2, mdata_kwargs=dict(x_mod="rna", y_mod="nope"))
     with pytest.raises(TypeError):                    # x_mod / y_mod are required, as in the reference
