@@ -85,9 +85,14 @@ class PipelineState:
     the statistics only the non-permutation methods need are computed lazily from the engine's
     float64 per-(cluster, gene) moments (`lrperm_cluster_moments`)."""
 
-    def __init__(self, prep, tables, engine, means, props, sizes, pair_mask, base=float(np.e)):
+    def __init__(self, prep, tables, engine, means, props, sizes, pair_mask, base=float(np.e), sizes_all=None):
         self.prep, self.tables, self.engine = prep, tables, engine
         self.means, self.props, self.sizes, self.pair_mask = means, props, sizes, pair_mask
+        # cells without a label (NaN in `groupby`) stay in the matrix like in the reference: they form one more,
+        # nameless cluster on the engine (last row of every [cluster, gene] table) that no interaction refers to, but
+        # that takes part in the shuffles, in the whole-matrix statistics and in the "rest" of the log fold changes
+        self.sizes_all = sizes if sizes_all is None else sizes_all
+        self.engine_tables = None
         self.base = float(base)
         self._moments = None
         self._cache = {}
@@ -99,9 +104,15 @@ class PipelineState:
         (ligand_means / receptor_means) or 'trimean' (CellChat's complex_cols).  Callers must not mutate the frame."""
         key = ("tri", float(expr_prop), bool(return_all_lrs), stat)
         if key not in self._cache:
-            by = self.means if stat == "means" else self.trimean()
-            tri = _tables.resolve_triples(self.tables, by, self.props, expr_prop, self.pair_mask, return_all_lrs,
-                                          engine=self.engine)
+            by, props, mask = (self.means if stat == "means" else self.trimean()), self.props, self.pair_mask
+            if self.engine_tables is not None:
+                # unlabeled cells: the tables carry the engine's extra cluster, masked out of every (source, target) pair
+                L = len(self.sizes)
+                by = self.engine_tables[0] if stat == "means" else self.trimean(all_rows=True)
+                props = self.engine_tables[1]
+                mask = np.zeros((L + 1, L + 1), dtype=bool)
+                mask[:L, :L] = True if self.pair_mask is None else self.pair_mask
+            tri = _tables.resolve_triples(self.tables, by, props, expr_prop, mask, return_all_lrs, engine=self.engine)
             self._cache[key] = (tri, base_frame(self, tri, stat))
         return self._cache[key]
 
@@ -120,13 +131,14 @@ class PipelineState:
             self._cache["cdf"] = p
         return self._cache["cdf"]
 
-    def trimean(self) -> np.ndarray:
-        """Observed cluster trimeans of X / mat_max, float64 [L,G] (`_liana_pipe.py:307-308, 462-465`)."""
+    def trimean(self, all_rows: bool = False) -> np.ndarray:
+        """Observed cluster trimeans of X / mat_max, float64 [L,G] (`_liana_pipe.py:307-308, 462-465`); `all_rows`
+        keeps the engine's extra row for unlabeled cells."""
         if "trimean" not in self._cache:
             if self.prep.mat_max is None:
                 raise RuntimeError("the input was prepared without mat_max (internal error)")
             self._cache["trimean"] = self.engine.observed_trimean(self.prep.mat_max)
-        return self._cache["trimean"]
+        return self._cache["trimean"] if all_rows else self._cache["trimean"][:len(self.sizes)]
 
     def _get_moments(self):
         if self._moments is None:
@@ -139,12 +151,13 @@ class PipelineState:
         cluster's cells is (cluster mean - mean_g) / std_g)."""
         if "z" not in self._cache:
             sum_x, sum_sq, _ = self._get_moments()
-            n = float(self.sizes.sum())
+            n = float(self.sizes_all.sum())
             mean = sum_x.sum(axis=0) / n
             var = (sum_sq.sum(axis=0) / n - mean ** 2) * (n / (n - 1.0))
             std = np.sqrt(np.maximum(var, 0.0))
             std[std == 0] = 1.0
-            cl_mean = sum_x / self.sizes[:, None].astype(np.float64)
+            L = len(self.sizes)
+            cl_mean = sum_x[:L] / self.sizes[:, None].astype(np.float64)
             self._cache["z"] = ((cl_mean - mean[None, :]) / std[None, :]).astype(np.float32)
         return self._cache["z"]
 
@@ -153,10 +166,12 @@ class PipelineState:
         if "fc" not in self._cache:
             _, _, sum_e = self._get_moments()
             n_c = self.sizes.astype(np.float64)[:, None]
-            n = float(self.sizes.sum())
+            n = float(self.sizes_all.sum())
+            total = sum_e.sum(axis=0)[None, :]                  # unlabeled cells belong to every cluster's "rest"
+            sum_e = sum_e[:len(self.sizes)]
             subj = sum_e / n_c
             with np.errstate(invalid="ignore", divide="ignore"):
-                rest = (sum_e.sum(axis=0)[None, :] - sum_e) / (n - n_c)
+                rest = (total - sum_e) / (n - n_c)
             self._cache["fc"] = (np.log2(subj + 1.0) - np.log2(rest + 1.0)).astype(np.float32)
         return self._cache["fc"]
 
@@ -212,9 +227,13 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
     L = len(prep.categories)
     eng.commit_matrix(col_map, len(tables.entities), prep.n_cells)
     prep.var_names = tables.entities
-    eng.set_labels(prep.labels, L)
-    means, stored, sizes = eng.observed()
-    props = stored / sizes[:, None].astype(np.float64)
+    labels, L_eng = prep.labels, L
+    if len(labels) and labels.min() < 0:          # cells without a label: one more cluster on the engine (see PipelineState)
+        labels, L_eng = np.where(labels < 0, L, labels).astype(np.int32), L + 1
+    eng.set_labels(labels, L_eng)
+    means_all, stored, sizes_all = eng.observed()
+    props_all = stored / sizes_all[:, None].astype(np.float64)
+    means, props, sizes = means_all[:L], props_all[:L], sizes_all[:L]
     pair_mask = None
     if groupby_pairs is not None:
         pos = {c: i for i, c in enumerate(prep.categories)}
@@ -222,7 +241,10 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
         for s, t in zip(groupby_pairs[K.SOURCE], groupby_pairs[K.TARGET]):
             if s in pos and t in pos:
                 pair_mask[pos[s], pos[t]] = True
-    return PipelineState(prep, tables, eng, means, props, sizes, pair_mask, base=base)
+    state = PipelineState(prep, tables, eng, means, props, sizes, pair_mask, base=base, sizes_all=sizes_all)
+    if L_eng != L:
+        state.engine_tables = (means_all, props_all)       # [L + 1, G]: what the engine's row resolution indexes
+    return state
 
 
 def _take_names(names, codes):

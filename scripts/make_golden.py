@@ -24,7 +24,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
 from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from variants import mdata_inputs, variant_inputs  # noqa: E402
+from variants import mdata_inputs, nanlabel_inputs, variant_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -218,6 +218,16 @@ def save_variants(ref):
                           use_raw=True, mdata_kwargs=mkw)          # use_raw is overridden for MuData (`_liana_pipe.py:128`)
     res.to_csv(os.path.join(OUT, "variant_mdata_cellphonedb.csv.gz"), index=False)
     print(f"variant mdata: {res.shape}, mean pval {res['cellphone_pvals'].mean():.4f}")
+    # cells without a cluster label
+    adata = nanlabel_inputs()
+    res = ref.cellphonedb(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, verbose=False,
+                          use_raw=False)
+    res.to_csv(os.path.join(OUT, "variant_nanlabels_cellphonedb.csv.gz"), index=False)
+    print(f"variant nanlabels: {res.shape}, mean pval {res['cellphone_pvals'].mean():.4f}")
+    res = ref.rank_aggregate(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, verbose=False,
+                             use_raw=False)
+    res.to_csv(os.path.join(OUT, "variant_nanlabels_rank_aggregate.csv.gz"), index=False)
+    print(f"variant nanlabels rank_aggregate: {res.shape}")
 
 
 def save_cellchat(ref):

@@ -285,6 +285,25 @@ def test_dense_matrix_input_equals_sparse_input():
         compare(res, gold, "lr_means", "cellphone_pvals")
 
 
+def test_cells_without_a_label_identical_to_reference():
+    """NaN in `groupby`: the reference keeps such cells (`prep_check_adata` filters by category only) - they are
+    shuffled with the others (`_get_mean_perms.py:46-52`: an all-False row of labels_mask), count in mat_mean / the
+    z-score scaling, and are part of the "rest" of every cluster's log fold change (`_liana_pipe.py:341-360`).  Here
+    they are one more, nameless cluster on the engine.  cellphonedb frame and the consensus against the reference's."""
+    from variants import nanlabel_inputs
+    adata = nanlabel_inputs()
+    assert adata.obs["cluster"].isna().sum() > 10
+    kw = dict(groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, perm_source="reference", use_raw=False)
+    res = li.mt.cellphonedb(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_nanlabels_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")
+    agg = li.mt.rank_aggregate(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_nanlabels_rank_aggregate.csv.gz"), float_precision="round_trip")
+    compare_aggregate(agg, gold, ["specificity_rank", "magnitude_rank"])
+    cc = li.mt.cellchat(adata, **kw)                       # the trimean path with the extra cluster: runs, names only real clusters
+    assert set(cc["source"]) <= set(adata.obs["cluster"].cat.categories) and cc["cellchat_pvals"].between(0, 1).all()
+
+
 def test_return_all_lrs_contract():
     """`return_all_lrs=True` (liana/tests/test_sc_methods.py:166-190: every (pair, interaction) row comes back, the
     rows that fail expr_prop get the worst magnitude / specificity of the kept ones).  The reference itself cannot

@@ -53,3 +53,14 @@ def mdata_inputs():
     adata, _ = variant_inputs()
     mdata = MuDataLite({"rna": adata[:, 0:200].copy(), "prot": adata[:, 200:400].copy()})
     return mdata, dict(x_mod="rna", y_mod="prot", x_layer="sqrt", y_transform=np.sqrt)
+
+
+def nanlabel_inputs():
+    """The variant input with every tenth cell (at random) left without a cluster label (NaN in `groupby`): the
+    reference keeps such cells in the matrix - they are shuffled with the others, count in the whole-matrix
+    statistics and in the "rest" of the log fold changes - but they belong to no cluster."""
+    adata, _ = variant_inputs()
+    lab = adata.obs["cluster"].astype(object).copy()
+    lab[np.random.default_rng(3).random(len(lab)) < 0.1] = np.nan
+    adata.obs["cluster"] = pd.Categorical(lab)
+    return adata
