@@ -304,6 +304,33 @@ def test_cells_without_a_label_identical_to_reference():
     assert set(cc["source"]) <= set(adata.obs["cluster"].cat.categories) and cc["cellchat_pvals"].between(0, 1).all()
 
 
+def test_nothing_expressed_gives_an_empty_frame():
+    """`expr_prop` above 1: no interaction survives.  The reference returns an empty frame with the usual columns and
+    dtypes for a single method (its consensus fails inside pandas: 'cannot set a frame with no defined index');
+    here every method - and the consensus - returns the empty frame."""
+    adata, P, seed, ep = load_input("small300")
+    full = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=4, inplace=False)
+    for method in (li.mt.cellphonedb, li.mt.geometric_mean, li.mt.cellchat, li.mt.natmi, li.mt.rank_aggregate):
+        res = method(adata, groupby="cluster", use_raw=False, n_perms=4, expr_prop=1.01, inplace=False)
+        assert len(res) == 0, method.method_name
+        ok = method(adata, groupby="cluster", use_raw=False, n_perms=4, inplace=False)
+        assert list(res.columns) == list(ok.columns), method.method_name
+    res = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=4, expr_prop=1.01, inplace=False)
+    for c in ("ligand_means", "receptor_means", "lr_means"):
+        assert res[c].dtype == np.float32
+    for c in ("ligand_props", "receptor_props", "cellphone_pvals"):
+        assert res[c].dtype == np.float64
+    assert res["source"].dtype == full["source"].dtype and res["ligand"].dtype == full["ligand"].dtype
+    by = li.mt.cellphonedb.by_sample(_with_samples(adata), "sample", groupby="cluster", use_raw=False, n_perms=4,
+                                     expr_prop=1.01, inplace=False)
+    assert len(by) == 0 and by.columns[0] == "sample"
+
+
+def _with_samples(adata):
+    adata.obs["sample"] = pd.Categorical(np.where(np.arange(adata.shape[0]) % 2 == 0, "A", "B"))
+    return adata
+
+
 def test_return_all_lrs_contract():
     """`return_all_lrs=True` (liana/tests/test_sc_methods.py:166-190: every (pair, interaction) row comes back, the
     rows that fail expr_prop get the worst magnitude / specificity of the kept ones).  The reference itself cannot
