@@ -24,7 +24,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
 from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from variants import mdata_inputs, nanlabel_inputs, variant_inputs  # noqa: E402
+from variants import mdata_inputs, nanlabel_inputs, signed_inputs, variant_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -228,6 +228,13 @@ def save_variants(ref):
                              use_raw=False)
     res.to_csv(os.path.join(OUT, "variant_nanlabels_rank_aggregate.csv.gz"), index=False)
     print(f"variant nanlabels rank_aggregate: {res.shape}")
+    # negative values, integer cluster names
+    adata = signed_inputs()
+    for name in ("cellphonedb", "cellchat"):
+        res = getattr(ref, name)(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+                                 verbose=False, use_raw=False)
+        res.to_csv(os.path.join(OUT, f"variant_signed_{name}.csv.gz"), index=False)
+        print(f"variant signed {name}: {res.shape}")
 
 
 def save_cellchat(ref):

@@ -304,6 +304,27 @@ def test_cells_without_a_label_identical_to_reference():
     assert set(cc["source"]) <= set(adata.obs["cluster"].cat.categories) and cc["cellchat_pvals"].between(0, 1).all()
 
 
+def test_signed_values_and_integer_cluster_names_identical_to_reference():
+    """Scaled / centred data (a third of the stored values negative: sums, the zero mask of lr_means and the
+    quartile selection of CellChat all see both signs) and integer cluster names (`source` / `target` are int64
+    columns in the reference's frames)."""
+    from variants import signed_inputs
+    adata = signed_inputs()
+    kw = dict(groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, perm_source="reference", use_raw=False)
+    res = li.mt.cellphonedb(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_signed_cellphonedb.csv.gz"), float_precision="round_trip")
+    assert res["source"].dtype == np.int64 and res["target"].dtype == np.int64
+    compare(res, gold, "lr_means", "cellphone_pvals")
+    cc = li.mt.cellchat(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_signed_cellchat.csv.gz"), float_precision="round_trip")
+    assert list(cc.columns) == list(gold.columns)
+    a = cc.sort_values(KEY).reset_index(drop=True)
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b) and (a[KEY].values == b[KEY].values).all()
+    for c in ("ligand_trimean", "receptor_trimean", "ligand_props", "receptor_props", "lr_probs", "cellchat_pvals"):
+        assert np.array_equal(a[c].values, b[c].values), c
+
+
 def test_nothing_expressed_gives_an_empty_frame():
     """`expr_prop` above 1: no interaction survives.  The reference returns an empty frame with the usual columns and
     dtypes for a single method (its consensus fails inside pandas: 'cannot set a frame with no defined index');

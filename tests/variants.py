@@ -64,3 +64,14 @@ def nanlabel_inputs():
     lab[np.random.default_rng(3).random(len(lab)) < 0.1] = np.nan
     adata.obs["cluster"] = pd.Categorical(lab)
     return adata
+
+
+def signed_inputs():
+    """The variant input shifted so that a third of the stored values are negative (scaled / centred data) and with
+    INTEGER cluster names (1, 4, 7, ...): `source` / `target` come back as int64 columns in the reference."""
+    adata, _ = variant_inputs()
+    X = adata.X.copy()
+    X.data = (X.data - 1.0).astype(np.float32)
+    adata.X = X
+    adata.obs["cluster"] = pd.Categorical(adata.obs["cluster"].cat.codes.astype(int) * 3 + 1)
+    return adata
