@@ -230,7 +230,7 @@ def save_variants(ref):
     print(f"variant nanlabels rank_aggregate: {res.shape}")
     # negative values, integer cluster names
     adata = signed_inputs()
-    for name in ("cellphonedb", "cellchat"):
+    for name in ("cellphonedb", "cellchat", "geometric_mean"):
         res = getattr(ref, name)(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
                                  verbose=False, use_raw=False)
         res.to_csv(os.path.join(OUT, f"variant_signed_{name}.csv.gz"), index=False)

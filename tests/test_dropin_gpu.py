@@ -325,6 +325,27 @@ def test_signed_values_and_integer_cluster_names_identical_to_reference():
         assert np.array_equal(a[c].values, b[c].values), c
 
 
+def test_geometric_mean_of_signed_values_follows_the_reference_nan_rules():
+    """A geometric mean of negative cluster means is NaN in the reference (`scipy.stats.gmean`: log of a negative), a
+    NaN never compares `>=`, so such rows get p-value 0 and null means with a negative factor never count
+    (`_geometric_mean.py:22-23`, `_get_mean_perms.py:133-137`).  Both comparison modes of the engine follow that."""
+    from variants import signed_inputs
+    adata = signed_inputs()
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_signed_geometric_mean.csv.gz"), float_precision="round_trip")
+    b = gold.sort_values(KEY).reset_index(drop=True)
+    assert b["lr_gmeans"].isna().sum() > 50
+    for mode in ("product", "literal"):
+        with np.errstate(invalid="ignore"):
+            res = li.mt.geometric_mean(adata, groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+                                       perm_source="reference", use_raw=False, gmean_mode=mode)
+        assert list(res.columns) == list(gold.columns)
+        a = res.sort_values(KEY).reset_index(drop=True)
+        assert len(a) == len(b) and (a[KEY].values == b[KEY].values).all()
+        assert np.array_equal(a["lr_gmeans"].values, b["lr_gmeans"].values.astype(np.float32), equal_nan=True), mode
+        assert np.array_equal(a["gmean_pvals"].values, b["gmean_pvals"].values), mode
+        assert res["lr_gmeans"].isna().values[-int(b["lr_gmeans"].isna().sum()):].all()       # NaN magnitudes sort last
+
+
 def test_nothing_expressed_gives_an_empty_frame():
     """`expr_prop` above 1: no interaction survives.  The reference returns an empty frame with the usual columns and
     dtypes for a single method (its consensus fails inside pandas: 'cannot set a frame with no defined index');
