@@ -346,6 +346,37 @@ def test_geometric_mean_of_signed_values_follows_the_reference_nan_rules():
         assert res["lr_gmeans"].isna().values[-int(b["lr_gmeans"].isna().sum()):].all()       # NaN magnitudes sort last
 
 
+def test_return_all_lrs_in_the_other_entry_points():
+    """The reference's own `return_all_lrs` tests (liana/tests/test_sc_methods.py:151-164, test_rank_aggregate.py:60-70)
+    restated on the synthetic input: NATMI's fill rule (both of its scores are 'larger is better', so filtered rows get
+    the minimum), `logfc.by_sample`, `rank_aggregate` without permutations (11 columns) and `rank_aggregate.by_sample`
+    (14 columns) - every call returns every (cluster pair, interaction) row."""
+    adata, P, seed, ep = load_input("small300")
+    L = adata.obs["cluster"].nunique()
+    kw = dict(groupby="cluster", use_raw=False, expr_prop=ep, inplace=False)
+    kept = li.mt.natmi(adata, **kw)
+    lr_all = li.mt.natmi(adata, return_all_lrs=True, **kw)
+    n_all = len(lr_all)
+    assert n_all % (L * L) == 0 and n_all > len(kept) and lr_all.shape[1] == kept.shape[1] + 1
+    assert int(lr_all["lrs_to_keep"].sum()) == len(kept)
+    rest = lr_all[~lr_all["lrs_to_keep"]]
+    assert (rest[li.mt.natmi.magnitude] == lr_all[li.mt.natmi.magnitude].min()).all()
+    assert (rest[li.mt.natmi.specificity] == lr_all[li.mt.natmi.specificity].min()).all()
+    res = li.mt.rank_aggregate(adata, return_all_lrs=True, n_perms=None, **kw)
+    assert res.shape == (n_all, 11) and "specificity_rank" not in res.columns
+    res = li.mt.rank_aggregate(adata, return_all_lrs=True, n_perms=8, **kw)
+    assert res.shape == (n_all, 13)
+    assert res["magnitude_rank"].between(0, 1).all() and np.all(np.diff(res["magnitude_rank"].values) >= 0)
+    _with_samples(adata)
+    by = li.mt.logfc.by_sample(adata, "sample", return_all_lrs=True, **kw)
+    assert by.columns[0] == "sample" and set(by["sample"]) == {"A", "B"}
+    for s in ("A", "B"):                                  # per sample: all pairs x the interactions covered by ITS genes
+        assert (by["sample"] == s).sum() % (L * L) == 0
+    by = li.mt.rank_aggregate.by_sample(adata, "sample", return_all_lrs=True, n_perms=8, key_added="liana_by_sample",
+                                        **{k: v for k, v in kw.items() if k != "inplace"})
+    assert by is None and adata.uns["liana_by_sample"].shape[1] == 14 and "sample" in adata.uns["liana_by_sample"].columns
+
+
 def test_nothing_expressed_gives_an_empty_frame():
     """`expr_prop` above 1: no interaction survives.  The reference returns an empty frame with the usual columns and
     dtypes for a single method (its consensus fails inside pandas: 'cannot set a frame with no defined index');
