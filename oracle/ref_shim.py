@@ -104,6 +104,40 @@ def _install_pandas_compat():
         return orig(self, labels, *args, **kwargs)
     drop._lrperm_compat = True
     pd.DataFrame.drop = drop
+    _install_chained_fillna_compat()
+
+
+def _install_chained_fillna_compat():
+    """Container drift again: with `return_all_lrs=True` the reference fills the left-merged flag columns through a
+    CHAINED in-place call, `lr_res['lrs_to_keep'].fillna(value=False, inplace=True)` (`_reassemble_complexes.py:56-57`).
+    Under the pinned pandas 2.0.3 `lr_res[col]` is a cached view, so the call updates the frame, and filling an object
+    column of True / NaN silently downcasts it to bool.  pandas 3 (copy-on-write) makes the same line a no-op, and
+    `~lr_res[lrs_to_keep]` (`_liana_pipe.py:389`) then fails.  Emulated here and only here: a column taken out of a
+    frame remembers where it came from, and an in-place `fillna` on it writes the (downcast) result back."""
+    import weakref
+    import pandas as pd
+    orig_getitem = pd.DataFrame.__getitem__
+    orig_fillna = pd.Series.fillna
+
+    def getitem(self, key):
+        out = orig_getitem(self, key)
+        if isinstance(key, str) and isinstance(out, pd.Series):
+            object.__setattr__(out, "_lrperm_parent", (weakref.ref(self), key))
+        return out
+
+    def fillna(self, value=None, *args, inplace=False, **kwargs):
+        if not inplace:
+            return orig_fillna(self, value, *args, **kwargs)
+        parent = getattr(self, "_lrperm_parent", None)
+        frame = parent[0]() if parent is not None else None
+        filled = orig_fillna(self, value, *args, **kwargs).infer_objects()
+        if frame is not None:
+            frame[parent[1]] = filled
+            return None
+        return orig_fillna(self, value, *args, inplace=True, **kwargs)
+
+    pd.DataFrame.__getitem__ = getitem
+    pd.Series.fillna = fillna
 
 
 def _install_numpy_compat():

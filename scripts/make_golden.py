@@ -228,6 +228,13 @@ def save_variants(ref):
                              use_raw=False)
     res.to_csv(os.path.join(OUT, "variant_nanlabels_rank_aggregate.csv.gz"), index=False)
     print(f"variant nanlabels rank_aggregate: {res.shape}")
+    # return_all_lrs (needs the pinned-pandas emulation of oracle/ref_shim.py::_install_chained_fillna_compat)
+    adata, _ = variant_inputs()
+    for name, fn in (("cellphonedb", ref.cellphonedb), ("natmi", ref.natmi_mod.natmi), ("rank_aggregate", ref.rank_aggregate)):
+        res = fn(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, verbose=False,
+                 use_raw=False, return_all_lrs=True)
+        res.to_csv(os.path.join(OUT, f"variant_allrs_{name}.csv.gz"), index=False)
+        print(f"variant allrs {name}: {res.shape}, kept {int(res['lrs_to_keep'].sum()) if 'lrs_to_keep' in res else '-'}")
     # negative values, integer cluster names
     adata = signed_inputs()
     for name in ("cellphonedb", "cellchat", "geometric_mean"):

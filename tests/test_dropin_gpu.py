@@ -346,6 +346,35 @@ def test_geometric_mean_of_signed_values_follows_the_reference_nan_rules():
         assert res["lr_gmeans"].isna().values[-int(b["lr_gmeans"].isna().sum()):].all()       # NaN magnitudes sort last
 
 
+def test_return_all_lrs_frames_identical_to_reference():
+    """`return_all_lrs=True` against frames of the reference itself (run under the pinned-pandas emulation of
+    oracle/ref_shim.py: its chained in-place `fillna` is a no-op under pandas 3): every (cluster pair, interaction)
+    row, complexes represented by their first subunits (`drop_duplicates` before the min-subunit step,
+    `_reassemble_complexes.py:52-57`), filtered rows filled with the worst kept score (`_liana_pipe.py:433-443`)."""
+    from variants import variant_inputs
+    adata, _ = variant_inputs()
+    kw = dict(groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, perm_source="reference", use_raw=False,
+              return_all_lrs=True)
+    res = li.mt.cellphonedb(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_allrs_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")
+    a, b = res.sort_values(KEY).reset_index(drop=True), gold.sort_values(KEY).reset_index(drop=True)
+    assert a["lrs_to_keep"].dtype == bool and np.array_equal(a["lrs_to_keep"].values, b["lrs_to_keep"].values)
+    res = li.mt.natmi(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_allrs_natmi.csv.gz"), float_precision="round_trip")
+    assert list(res.columns) == list(gold.columns)
+    a, b = res.sort_values(KEY).reset_index(drop=True), gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b) and (a[KEY + ["ligand", "receptor"]].values == b[KEY + ["ligand", "receptor"]].values).all()
+    assert np.array_equal(a["lrs_to_keep"].values, b["lrs_to_keep"].values)
+    for c in ("ligand_means", "receptor_means", "ligand_props", "receptor_props"):
+        assert np.array_equal(a[c].values, b[c].values.astype(a[c].dtype)), c
+    for c in ("ligand_means_sums", "receptor_means_sums", "expr_prod", "spec_weight"):
+        np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-4, atol=2e-6, err_msg=c)
+    res = li.mt.rank_aggregate(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_allrs_rank_aggregate.csv.gz"), float_precision="round_trip")
+    compare_aggregate(res, gold, ["specificity_rank", "magnitude_rank"])
+
+
 def test_return_all_lrs_in_the_other_entry_points():
     """The reference's own `return_all_lrs` tests (liana/tests/test_sc_methods.py:151-164, test_rank_aggregate.py:60-70)
     restated on the synthetic input: NATMI's fill rule (both of its scores are 'larger is better', so filtered rows get
@@ -406,9 +435,8 @@ def _with_samples(adata):
 
 def test_return_all_lrs_contract():
     """`return_all_lrs=True` (liana/tests/test_sc_methods.py:166-190: every (pair, interaction) row comes back, the
-    rows that fail expr_prop get the worst magnitude / specificity of the kept ones).  The reference itself cannot
-    run this option under pandas 3 (chained `fillna(inplace=True)`, `_reassemble_complexes.py:56-57`), so the
-    contract is checked directly."""
+    rows that fail expr_prop get the worst magnitude / specificity of the kept ones): the contract checked directly,
+    next to the frame comparison of `test_return_all_lrs_frames_identical_to_reference`."""
     adata, P, seed, ep = load_input("small300")
     kept = li.mt.cellphonedb(adata, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
                              inplace=False, perm_source="reference")
