@@ -24,7 +24,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
 from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from variants import mdata_inputs, nanlabel_inputs, signed_inputs, variant_inputs  # noqa: E402
+from variants import mdata_inputs, nanlabel_inputs, sample_inputs, signed_inputs, variant_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -235,6 +235,12 @@ def save_variants(ref):
                  use_raw=False, return_all_lrs=True)
         res.to_csv(os.path.join(OUT, f"variant_allrs_{name}.csv.gz"), index=False)
         print(f"variant allrs {name}: {res.shape}, kept {int(res['lrs_to_keep'].sum()) if 'lrs_to_keep' in res else '-'}")
+    # by_sample of the reference (`sc/_Method.py:92-159`)
+    for name, fn in (("cellphonedb", ref.cellphonedb), ("rank_aggregate", ref.rank_aggregate)):
+        res = fn.by_sample(sample_inputs(), sample_key="sample", groupby="cluster", n_perms=16, seed=7, expr_prop=0.1,
+                           inplace=False, verbose=False, use_raw=False)
+        res.to_csv(os.path.join(OUT, f"variant_bysample_{name}.csv.gz"), index=False)
+        print(f"variant bysample {name}: {res.shape}")
     # negative values, integer cluster names
     adata = signed_inputs()
     for name in ("cellphonedb", "cellchat", "geometric_mean"):

@@ -346,6 +346,28 @@ def test_geometric_mean_of_signed_values_follows_the_reference_nan_rules():
         assert res["lr_gmeans"].isna().values[-int(b["lr_gmeans"].isna().sum()):].all()       # NaN magnitudes sort last
 
 
+def test_by_sample_frames_identical_to_reference():
+    """`Method.by_sample` / `AggregateClass.by_sample` against the frames of the reference's own by_sample
+    (`sc/_Method.py:92-159`): `sample` first, samples stacked in category order under a fresh RangeIndex, every
+    sample's block equal to the reference's block."""
+    from variants import sample_inputs
+    kw = dict(sample_key="sample", groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+              perm_source="reference", use_raw=False)
+    res = li.mt.cellphonedb.by_sample(sample_inputs(), **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_bysample_cellphonedb.csv.gz"), float_precision="round_trip")
+    assert list(res.columns) == list(gold.columns) and len(res) == len(gold)
+    assert isinstance(res.index, pd.RangeIndex) and list(dict.fromkeys(res["sample"])) == list(dict.fromkeys(gold["sample"]))
+    for s_name in ("s1", "s2"):
+        compare(res[res["sample"] == s_name].drop(columns="sample"), gold[gold["sample"] == s_name].drop(columns="sample"),
+                "lr_means", "cellphone_pvals")
+    agg = li.mt.rank_aggregate.by_sample(sample_inputs(), **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_bysample_rank_aggregate.csv.gz"), float_precision="round_trip")
+    assert list(agg.columns) == list(gold.columns) and len(agg) == len(gold)
+    for s_name in ("s1", "s2"):
+        compare_aggregate(agg[agg["sample"] == s_name].drop(columns="sample"),
+                          gold[gold["sample"] == s_name].drop(columns="sample"), ["specificity_rank", "magnitude_rank"])
+
+
 def test_return_all_lrs_frames_identical_to_reference():
     """`return_all_lrs=True` against frames of the reference itself (run under the pinned-pandas emulation of
     oracle/ref_shim.py: its chained in-place `fillna` is a no-op under pandas 3): every (cluster pair, interaction)

@@ -75,3 +75,11 @@ def signed_inputs():
     adata.X = X
     adata.obs["cluster"] = pd.Categorical(adata.obs["cluster"].cat.codes.astype(int) * 3 + 1)
     return adata
+
+
+def sample_inputs():
+    """The variant input with a plain-string `sample` column (two unequal samples): `by_sample` converts it to a
+    categorical, runs every sample on its own rows and stacks the frames in category order."""
+    adata, _ = variant_inputs()
+    adata.obs["sample"] = np.where(np.arange(adata.shape[0]) % 3 == 0, "s2", "s1")
+    return adata
