@@ -241,6 +241,13 @@ def save_variants(ref):
                            inplace=False, verbose=False, use_raw=False)
         res.to_csv(os.path.join(OUT, f"variant_bysample_{name}.csv.gz"), index=False)
         print(f"variant bysample {name}: {res.shape}")
+    # consensus with a non-default log base and no expression filter (every row scored); magnitude-only consensus
+    adata, _ = variant_inputs()
+    for tag, kw in (("base2_all", dict(base=2.0, expr_prop=0.0)), ("magnitude_only", dict(consensus_opts=["Magnitude"], expr_prop=0.1))):
+        res = ref.rank_aggregate(adata.copy(), groupby="cluster", n_perms=16, seed=3, inplace=False, verbose=False,
+                                 use_raw=False, **kw)
+        res.to_csv(os.path.join(OUT, f"variant_{tag}_rank_aggregate.csv.gz"), index=False)
+        print(f"variant {tag} rank_aggregate: {res.shape}")
     # negative values, integer cluster names
     adata = signed_inputs()
     for name in ("cellphonedb", "cellchat", "geometric_mean"):
