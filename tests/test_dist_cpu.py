@@ -63,6 +63,39 @@ def _worker(rank, world, port, out_dir):
         assert merged == {i: s * 2 for i, s in enumerate(sizes)}
         loads = [sum(sizes[i] for i in q) for q in (ctx.all_gather_objects(mine))]
         assert max(loads) - min(loads) <= max(sizes)
+        # the drop-in methods themselves under the 2-rank context (the engine stood in by the oracle, tests/_oracle_engine.py):
+        # permutations sharded by global id + integer all-reduce -> the reference's frame on every rank; by_sample with
+        # whole samples per rank, gathered (every rank holds all samples) or not (every rank keeps its own block)
+        import pandas as pd
+        import liana_py_b200 as li
+        from liana_py_b200.method import _pipeline as PL
+        from _oracle_engine import OracleEngine
+        import test_dropin_gpu as G
+        PL._ENGINES[0] = OracleEngine()
+        adata, Pn, seed, ep = G.load_input("small300")
+        kw = dict(groupby="cluster", use_raw=False, n_perms=Pn, seed=seed, expr_prop=ep, inplace=False, perm_source="reference")
+        res = li.mt.cellphonedb(adata, dist=ctx, **kw)
+        gold = pd.read_csv(os.path.join(G.GOLDEN, "small300_cellphonedb.csv.gz"), float_precision="round_trip")
+        G.compare(res, gold, "lr_means", "cellphone_pvals")
+        cc = li.mt.cellchat(adata, dist=ctx, **kw)
+        goldc = pd.read_csv(os.path.join(G.GOLDEN, "small300_cellchat.csv.gz"), float_precision="round_trip")
+        a, b = cc.sort_values(G.KEY).reset_index(drop=True), goldc.sort_values(G.KEY).reset_index(drop=True)
+        assert np.array_equal(a["cellchat_pvals"].values, b["cellchat_pvals"].values)
+        from variants import sample_inputs
+        kws = dict(sample_key="sample", groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False,
+                   perm_source="reference", use_raw=False)
+        golds = pd.read_csv(os.path.join(G.GOLDEN, "variant_bysample_cellphonedb.csv.gz"), float_precision="round_trip")
+        full = li.mt.cellphonedb.by_sample(sample_inputs(), dist=ctx, **kws)
+        assert len(full) == len(golds) and list(dict.fromkeys(full["sample"])) == ["s1", "s2"]
+        for s_name in ("s1", "s2"):
+            G.compare(full[full["sample"] == s_name].drop(columns="sample"),
+                      golds[golds["sample"] == s_name].drop(columns="sample"), "lr_means", "cellphone_pvals")
+        own = li.mt.cellphonedb.by_sample(sample_inputs(), dist=ctx, gather=False, **kws)
+        mine_s = set(own["sample"])
+        assert len(mine_s) == 1                                     # two samples, two ranks: one whole sample each
+        assert set().union(*ctx.all_gather_objects(mine_s)) == {"s1", "s2"}
+        G.compare(own.drop(columns="sample"), golds[golds["sample"] == next(iter(mine_s))].drop(columns="sample"),
+                  "lr_means", "cellphone_pvals")
         t = torch.full((4,), rank + 1, dtype=torch.int32)
         ctx.all_reduce_sum_(t)
         assert t.tolist() == [sum(range(1, world + 1))] * 4
