@@ -24,7 +24,7 @@ from oracle.ref_shim import load_reference  # noqa: E402
 from liana_py_b200.testing._synth import make_synthetic_adata  # noqa: E402
 from liana_py_b200.testing._anndata_lite import AnnDataLite  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from variants import mdata_inputs, nanlabel_inputs, sample_inputs, signed_inputs, variant_inputs  # noqa: E402
+from variants import mdata_inputs, nanlabel_inputs, sample_inputs, signed_inputs, ties_inputs, variant_inputs  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -248,6 +248,12 @@ def save_variants(ref):
                                  use_raw=False, **kw)
         res.to_csv(os.path.join(OUT, f"variant_{tag}_rank_aggregate.csv.gz"), index=False)
         print(f"variant {tag} rank_aggregate: {res.shape}")
+    # tied subunits: the reference's tie rule decides which subunit represents a complex
+    adata, n_tied = ties_inputs()
+    for name, fn in (("cellphonedb", ref.cellphonedb), ("cellchat", ref.cellchat)):
+        res = fn(adata.copy(), groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, verbose=False, use_raw=False)
+        res.to_csv(os.path.join(OUT, f"variant_ties_{name}.csv.gz"), index=False)
+        print(f"variant ties {name}: {res.shape} ({n_tied} complexes with copied subunits)")
     # negative values, integer cluster names
     adata = signed_inputs()
     for name in ("cellphonedb", "cellchat", "geometric_mean"):

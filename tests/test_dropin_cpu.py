@@ -93,3 +93,7 @@ def test_cellchat_and_scseqcomm_frames(name):
 @pytest.mark.parametrize("method", ["cellchat", "scseqcomm", "rank_aggregate"])
 def test_by_sample_of_other_methods(method):
     GC.test_by_sample_of_other_methods_matches_per_sample_calls(method)
+
+
+def test_tied_subunits():
+    G.test_tied_subunits_resolved_like_the_reference()

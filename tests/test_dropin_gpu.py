@@ -346,6 +346,28 @@ def test_geometric_mean_of_signed_values_follows_the_reference_nan_rules():
         assert res["lr_gmeans"].isna().values[-int(b["lr_gmeans"].isna().sum()):].all()       # NaN magnitudes sort last
 
 
+def test_tied_subunits_resolved_like_the_reference():
+    """Complexes whose subunits have EQUAL cluster means (copied expression): which subunit represents the complex
+    is decided by the tie rule alone - the reference keeps every minimal row and then the first per key
+    (`_reduce_complexes` + `drop_duplicates(keep='first')`, `_reassemble_complexes.py:60-101`), i.e. the first minimal
+    subunit in the complex's own order; for CellChat the same on the trimeans."""
+    from variants import ties_inputs
+    adata, n_tied = ties_inputs()
+    assert n_tied >= 20
+    kw = dict(groupby="cluster", n_perms=16, seed=7, expr_prop=0.1, inplace=False, perm_source="reference", use_raw=False)
+    res = li.mt.cellphonedb(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_ties_cellphonedb.csv.gz"), float_precision="round_trip")
+    compare(res, gold, "lr_means", "cellphone_pvals")                # includes the `ligand` / `receptor` columns
+    cc = li.mt.cellchat(adata, **kw)
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_ties_cellchat.csv.gz"), float_precision="round_trip")
+    a, b = cc.sort_values(KEY).reset_index(drop=True), gold.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in KEY + ["ligand", "receptor"]:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+    for c in ("ligand_trimean", "receptor_trimean", "lr_probs", "cellchat_pvals"):
+        assert np.array_equal(a[c].values, b[c].values), c
+
+
 def test_consensus_options_identical_to_reference():
     """`base=2` (the log fold changes undo a log2 instead of a natural log, `_liana_pipe.py:266-273`) with
     `expr_prop=0` (every (pair, interaction) row is scored: T = T_max of this input) and another seed; and a

@@ -83,3 +83,30 @@ def sample_inputs():
     adata, _ = variant_inputs()
     adata.obs["sample"] = np.where(np.arange(adata.shape[0]) % 3 == 0, "s2", "s1")
     return adata
+
+
+def ties_inputs():
+    """The variant input with TIED subunits: for every complex of the consensus resource whose subunits are all
+    present, the first subunit's expression is copied into the others (equal cluster means and proportions in every
+    cluster: which subunit represents the complex is decided by the reference's tie rule alone); for every second such
+    complex the copy is then zeroed in the cells of the first cluster, so the tie holds in some clusters only."""
+    adata, _ = variant_inputs()
+    res = pd.read_csv(os.path.join(ROOT, "liana_py_b200", "resource", "consensus.csv"))
+    names = list(adata.var_names)
+    pos = {g: i for i, g in enumerate(names)}
+    X = adata.X.tolil(copy=True)
+    first = np.flatnonzero(np.asarray(adata.obs["cluster"].cat.codes) == 0)
+    seen, k = set(), 0
+    for entry in list(res["ligand"]) + list(res["receptor"]):
+        subs = entry.split("_")
+        if len(subs) < 2 or entry in seen or not all(g in pos for g in subs):
+            continue
+        seen.add(entry)
+        for g in subs[1:]:
+            X[:, pos[g]] = X[:, pos[subs[0]]]
+            if k % 2:
+                X[first, pos[g]] = 0
+        k += 1
+    adata.X = X.tocsr().astype(np.float32)
+    adata.X.eliminate_zeros()
+    return adata, k
