@@ -6,7 +6,6 @@ resolution, score functions, consensus, frame assembly, by_sample, MuData, suppl
 machine without a GPU, and `tests/test_dropin_cpu.py` compares its frames with the frames the reference produced
 (tests/golden).  The GPU suite runs the very same comparisons through the CUDA library."""
 import numpy as np
-from scipy import sparse
 from scipy.stats import rankdata
 
 from liana_py_b200 import _engine as E

@@ -3,7 +3,6 @@ the SAME frame comparisons against the reference's frames as tests/test_dropin_g
 B200, executed here through the oracle - so the host logic (input contract, tables, row resolution, scores, consensus,
 frame assembly, by_sample, MuData, supplementary columns, unlabeled cells, return_all_lrs) is checked on every
 machine, and a difference on the GPU box can only come from the device code."""
-import numpy as np
 import pytest
 
 from liana_py_b200.method import _pipeline as PL
