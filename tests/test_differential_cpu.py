@@ -1,0 +1,87 @@
+"""CPU, differential: random small inputs and call options through the reference's own code (oracle/ref_shim.py, needs
+/root/reference: skipped elsewhere) and through the drop-in layer with the oracle-backed engine stand-in
+(tests/_oracle_engine.py).  Frames must agree exactly for the permutation methods (cellphonedb, geometric_mean,
+cellchat) and to the reference's own tolerance for a non-permutation score - a fuzz test of the host logic (input
+contract, cluster filtering, resource tables, complex resolution, score functions, frame assembly)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="needs the reference tree")
+
+from liana_py_b200.method import _pipeline as PL          # noqa: E402
+from liana_py_b200.testing._synth import make_synthetic_adata      # noqa: E402
+from _oracle_engine import OracleEngine                   # noqa: E402
+import liana_py_b200 as li                                # noqa: E402
+
+KEY = ["source", "target", "ligand_complex", "receptor_complex"]
+
+
+@pytest.fixture(autouse=True)
+def oracle_engine(monkeypatch):
+    monkeypatch.setitem(PL._ENGINES, 0, OracleEngine())
+    yield
+
+
+def _case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n, g, L = int(rng.integers(60, 260)), int(rng.integers(150, 700)), int(rng.integers(2, 7))
+    adata = make_synthetic_adata(n, g, L, density=float(rng.uniform(0.05, 0.3)), seed_data=seed, seed_labels=seed + 50)
+    kw = dict(expr_prop=float(rng.choice([0.0, 0.05, 0.1, 0.3])), min_cells=int(rng.choice([1, 5, 12])),
+              n_perms=int(rng.integers(3, 12)), seed=int(rng.integers(0, 10 ** 6)))
+    if rng.random() < 0.4:                            # unbalanced clusters: some fall below min_cells
+        codes = np.asarray(adata.obs["cluster"].cat.codes)
+        drop = np.flatnonzero((codes == 0) & (rng.random(n) < 0.85))
+        keep = np.setdiff1d(np.arange(n), drop)
+        adata = adata[keep].copy()
+    if rng.random() < 0.3:
+        cats = list(adata.obs["cluster"].cat.categories)
+        k = min(len(cats), 3)
+        kw["groupby_pairs"] = pd.DataFrame({"source": rng.choice(cats, k), "target": rng.choice(cats, k)}).drop_duplicates()
+    if rng.random() < 0.3:
+        kw["resource_name"] = str(rng.choice(["cellphonedb", "cellchatdb", "connectomedb2020", "mouseconsensus"]))
+    if rng.random() < 0.25:                           # unlabeled cells
+        lab = adata.obs["cluster"].astype(object).copy()
+        lab[rng.random(len(lab)) < 0.08] = np.nan
+        adata.obs["cluster"] = pd.Categorical(lab)
+    return adata, kw
+
+
+def _same(a, b, exact, close=()):
+    assert list(a.columns) == list(b.columns)
+    a, b = a.sort_values(KEY).reset_index(drop=True), b.sort_values(KEY).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in KEY + ["ligand", "receptor"]:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+    for c in exact:
+        assert np.array_equal(a[c].values, b[c].values.astype(a[c].dtype), equal_nan=True), c
+    for c in close:
+        np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-4, atol=2e-6, err_msg=c)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_inputs_agree_with_the_reference(seed):
+    ref = ref_shim.load_reference()
+    adata, kw = _case(seed)
+    common = dict(groupby="cluster", use_raw=False, inplace=False, verbose=False, **kw)
+    try:
+        want = ref.cellphonedb(adata.copy(), **common)
+    except Exception as e:                             # e.g. too few resource genes in a tiny input: same refusal here
+        with pytest.raises(type(e)):
+            li.mt.cellphonedb(adata.copy(), perm_source="reference", **common)
+        return
+    got = li.mt.cellphonedb(adata.copy(), perm_source="reference", **common)
+    stats = ["ligand_means", "receptor_means", "ligand_props", "receptor_props"]
+    _same(got, want, stats + ["lr_means", "cellphone_pvals"])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = ref.geometric_mean_mod.geometric_mean(adata.copy(), **common)
+        got = li.mt.geometric_mean(adata.copy(), perm_source="reference", **common)
+    _same(got, want, stats + ["lr_gmeans", "gmean_pvals"])
+    want = ref.cellchat(adata.copy(), **common)
+    got = li.mt.cellchat(adata.copy(), perm_source="reference", **common)
+    _same(got, want, ["ligand_trimean", "receptor_trimean", "ligand_props", "receptor_props", "lr_probs", "cellchat_pvals"])
+    want = ref.natmi_mod.natmi(adata.copy(), **common)
+    got = li.mt.natmi(adata.copy(), **common)
+    _same(got, want, stats, close=["expr_prod", "spec_weight"])
