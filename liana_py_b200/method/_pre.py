@@ -240,7 +240,7 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
         row_label = np.full(X.shape[0], -1, dtype=np.int32)
         row_label[rows] = new_codes
         sx, sq = engine.staged_cluster_stats(row_label, L)
-        n_entries = np.bincount(new_codes, minlength=L).astype(np.float64) * len(keep_cols)
+        n_entries = np.bincount(new_codes[new_codes >= 0], minlength=L).astype(np.float64) * len(keep_cols)   # unlabeled cells: no cluster
         mean = sx / n_entries
         cluster_stats = (mean, np.sqrt(np.maximum(sq / n_entries - mean ** 2, 0.0)))
     return PreparedInput(mat_max=mat_max, cluster_stats=cluster_stats, var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],

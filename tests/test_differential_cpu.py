@@ -85,3 +85,29 @@ def test_random_inputs_agree_with_the_reference(seed):
     want = ref.natmi_mod.natmi(adata.copy(), **common)
     got = li.mt.natmi(adata.copy(), **common)
     _same(got, want, stats, close=["expr_prod", "spec_weight"])
+
+
+@pytest.mark.parametrize("seed", range(20, 26))
+def test_random_inputs_non_permutation_scores(seed):
+    """Connectome, log2FC, SingleCellSignalR, scSeqComm on random inputs (a random log base for the fold changes): key
+    columns and resolved subunits identical, scores within the reference's own frame tolerance (`float32` statistics
+    accumulated by another route), scSeqComm's normal cdf to 1e-5 (its cluster std is a float32 `np.std` there)."""
+    ref = ref_shim.load_reference()
+    adata, kw = _case(seed)
+    kw.pop("n_perms"); kw.pop("seed")
+    base = float(np.random.default_rng(seed).choice([np.e, 2.0, 10.0]))
+    common = dict(groupby="cluster", use_raw=False, inplace=False, verbose=False, base=base, **kw)
+    try:
+        ref.natmi_mod.natmi(adata.copy(), **common)
+    except ValueError:
+        pytest.skip("input refused by the reference (covered by the other test)")
+    for want_fn, got_fn, close, tol in (
+            (ref.connectome_mod.connectome, li.mt.connectome, ["expr_prod", "scaled_weight"], None),
+            (ref.logfc_mod.logfc, li.mt.logfc, ["lr_logfc"], None),
+            (ref.sca_mod.singlecellsignalr, li.mt.singlecellsignalr, ["lrscore"], None),
+            (ref.scseqcomm, li.mt.scseqcomm, [], 1e-5)):
+        want, got = want_fn(adata.copy(), **common), got_fn(adata.copy(), **common)
+        _same(got, want, [], close=close)
+        if tol is not None:
+            a, b = got.sort_values(KEY).reset_index(drop=True), want.sort_values(KEY).reset_index(drop=True)
+            np.testing.assert_allclose(a["inter_score"].values, b["inter_score"].values, rtol=0, atol=tol)
