@@ -111,3 +111,76 @@ def test_random_inputs_non_permutation_scores(seed):
         if tol is not None:
             a, b = got.sort_values(KEY).reset_index(drop=True), want.sort_values(KEY).reset_index(drop=True)
             np.testing.assert_allclose(a["inter_score"].values, b["inter_score"].values, rtol=0, atol=tol)
+
+
+MODES = ["return_all_lrs", "supp_columns", "dense", "interactions", "by_sample", "raw_layer"]
+
+
+@pytest.mark.parametrize("seed", range(40, 52))
+def test_random_inputs_call_options(seed):
+    """One optional feature of the call signature per case, on a random input, cellphonedb on both sides: every
+    (pair, interaction) row (`return_all_lrs`), supplementary columns, a dense matrix, a hand-picked interaction list,
+    `by_sample`, `.raw` / a layer."""
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(seed)
+    adata, kw = _case(seed)
+    kw.pop("groupby_pairs", None)
+    mode = MODES[seed % len(MODES)]
+    common = dict(groupby="cluster", inplace=False, verbose=False, **kw)
+    use = dict(use_raw=False)
+    by_sample = False
+    close = []
+    if mode == "return_all_lrs":
+        common["return_all_lrs"] = True
+    elif mode == "supp_columns":
+        pool = ["ligand_means_sums", "receptor_means_sums", "ligand_zscores", "receptor_zscores", "ligand_logfc", "receptor_logfc",
+                "mat_mean", "ligand_cdf", "receptor_cdf"]
+        common["supp_columns"] = close = list(rng.choice(pool, size=int(rng.integers(1, 5)), replace=False))
+    elif mode == "dense":
+        adata.X = adata.X.toarray().astype(rng.choice([np.float32, np.float64]))
+    elif mode == "interactions":
+        from liana_py_b200.resource import select_resource
+        res = select_resource(common.pop("resource_name", "consensus"))
+        present = set(adata.var_names)
+        ok = res[[all(x in present for x in (l + "_" + r).split("_")) for l, r in zip(res["ligand"], res["receptor"])]]
+        if len(ok) < 5:
+            pytest.skip("too few covered interactions in this random input")
+        pick = ok.iloc[rng.choice(len(ok), size=min(len(ok), 25), replace=False)]
+        common["interactions"] = list(zip(pick["ligand"], pick["receptor"]))
+    elif mode == "by_sample":
+        by_sample = True
+        adata.obs["sample"] = rng.choice(["a", "b", "c"], size=adata.shape[0])
+    elif mode == "raw_layer":
+        X = adata.X.tocsr()
+        other = X.copy(); other.data = np.sqrt(other.data).astype(np.float32)
+        if rng.random() < 0.5:
+            adata.raw = type("Raw", (), {"X": other, "var_names": adata.var_names, "var": adata.var})()
+            use = dict(use_raw=True)
+        else:
+            adata.layers["alt"] = other
+            use = dict(use_raw=False, layer="alt")
+    common.update(use)
+
+    def call(method, a, **extra):
+        return method.by_sample(a, "sample", **common, **extra) if by_sample else method(a, **common, **extra)
+
+    try:
+        want = call(ref.cellphonedb, adata.copy())
+    except ValueError:
+        with pytest.raises(ValueError):
+            call(li.mt.cellphonedb, adata.copy(), perm_source="reference")
+        return
+    got = call(li.mt.cellphonedb, adata.copy(), perm_source="reference")
+    key = (["sample"] if by_sample else []) + KEY
+    assert list(got.columns) == list(want.columns)
+    a, b = got.sort_values(key).reset_index(drop=True), want.sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b)
+    for c in key + ["ligand", "receptor"]:
+        assert (a[c].astype(str).values == b[c].astype(str).values).all(), (mode, c)
+    for c in ["ligand_means", "receptor_means", "ligand_props", "receptor_props", "lr_means", "cellphone_pvals"]:
+        assert np.array_equal(a[c].values, b[c].values.astype(a[c].dtype)), (mode, c)
+    if "lrs_to_keep" in b:
+        assert np.array_equal(a["lrs_to_keep"].values, b["lrs_to_keep"].values)
+    for c in close:
+        tol = dict(rtol=0, atol=1e-5) if c.endswith("_cdf") else dict(rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(a[c].values.astype(np.float64), b[c].values.astype(np.float64), err_msg=f"{mode} {c}", **tol)
