@@ -194,6 +194,10 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     kept_codes = codes[rows]
     new_codes = np.where(kept_codes >= 0, remap[np.maximum(kept_codes, 0)], -1).astype(np.int32)
     kept_categories = np.asarray(cats[used])
+    if len(kept_categories) == 0:
+        # the reference fails later with an IndexError on its empty category list; say what happened instead
+        raise ValueError(f"No cells left: every identity in `{groupby}` was excluded (min_cells={min_cells}"
+                         + (", groupby_pairs" if groupby_subset is not None else "") + ").")
     row_keep = None
     if len(rows) != X.shape[0]:
         row_keep = keep.astype(np.uint8)

@@ -233,3 +233,9 @@ def test_handle_resource_precedence_and_errors():
     # a resource that names none of the data's genes is refused by the coverage check (`_pre.py:15-62`)
     with pytest.raises(ValueError, match="Too few features"):
         _pre.assert_covered(np.array(["A", "B", "C", "D"]), np.array(["X1", "X2"]))
+
+
+def test_prepare_input_refuses_an_input_without_clusters():
+    adata = _ragged()
+    with pytest.raises(ValueError, match="No cells left"):
+        _pre.prepare_input(adata, "cluster", 10 ** 6, SciPyStage())
