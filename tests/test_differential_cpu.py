@@ -216,3 +216,59 @@ def test_random_inputs_consensus(seed):
         if ok.any():
             d = np.abs(x[ok] - y[ok])
             assert (d <= 1e-4 * np.maximum(np.abs(y[ok]), 1e-12)).mean() >= 0.95 and d.max() <= 5e-3, (c, float(d.max()))
+
+
+def test_degenerate_inputs_and_error_conventions_agree():
+    """Degenerate inputs and wrong arguments: both sides return the same frame, or refuse with the same exception type
+    (and, for the reference's own messages, the same text)."""
+    ref = ref_shim.load_reference()
+
+    def base():
+        return make_synthetic_adata(150, 400, 4, density=0.15, seed_data=5, seed_labels=6)
+
+    def both(adata, ref_fn=None, our_fn=None, **kw):
+        ref_fn, our_fn = ref_fn or ref.cellphonedb, our_fn or li.mt.cellphonedb
+        common = dict(groupby="cluster", inplace=False, verbose=False, **kw)
+        extra = dict(perm_source="reference") if our_fn in (li.mt.cellphonedb, li.mt.geometric_mean, li.mt.cellchat) else {}
+        try:
+            want = ref_fn(adata.copy(), **common)
+        except Exception as e:
+            with pytest.raises(type(e)) as info:
+                our_fn(adata.copy(), **common, **extra)
+            return str(e), str(info.value)
+        got = our_fn(adata.copy(), **common, **extra)
+        assert list(got.columns) == list(want.columns) and len(got) == len(want)
+        a, b = got.sort_values(KEY).reset_index(drop=True), want.sort_values(KEY).reset_index(drop=True)
+        for c in a.columns:
+            if a[c].dtype.kind == "f":
+                np.testing.assert_allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=1e-4, atol=2e-6, err_msg=c)
+            else:
+                assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+        return None
+
+    a = base(); a.obs["cluster"] = pd.Categorical(["only"] * 150)
+    both(a, use_raw=False, n_perms=4)                                                        # a single cluster
+    both(base(), use_raw=False, n_perms=4, groupby_pairs=pd.DataFrame({"source": ["c00", "zzz"], "target": ["c01", "c00"]}))
+    a = base(); a.obs["cluster"] = np.asarray(a.obs["cluster"].cat.codes)
+    both(a, use_raw=False, n_perms=4)                                                        # integer, non-categorical labels
+    a = base(); names = np.array(a.var_names, dtype=object); names[5] = names[6]; a.var_names = list(names)
+    both(a, use_raw=False, n_perms=4)                                                        # duplicated gene name
+    both(base(), use_raw=False, n_perms=4, expr_prop=1.0)
+    a = base(); a.X = a.X.tocsc()
+    both(a, use_raw=False, n_perms=4)
+    a = base(); a.X = a.X.astype(np.float64)
+    both(a, use_raw=False, n_perms=4)
+    a = base(); X = a.X.tolil(); X[3] = 0; X[:, 7] = 0; a.X = X.tocsr()
+    both(a, use_raw=False, n_perms=4)                                                        # an empty cell, an empty gene
+    both(base(), ref.connectome_mod.connectome, li.mt.connectome, use_raw=False, n_perms=4)
+    both(base(), ref.logfc_mod.logfc, li.mt.logfc, use_raw=False, base=10)
+    both(base(), ref.scseqcomm, li.mt.scseqcomm, use_raw=False, expr_prop=0)
+    both(base(), ref.cellchat, li.mt.cellchat, use_raw=False, n_perms=None)
+    both(base(), ref.geometric_mean, li.mt.geometric_mean, use_raw=False, n_perms=None)
+    # refusals: same type, same words
+    a = base(); X = a.X.copy(); X.data[5] = np.nan; a.X = X
+    for msgs in (both(a, use_raw=False, n_perms=2), both(base(), n_perms=2), both(base(), n_perms=2, layer="x", use_raw=True),
+                 both(base(), use_raw=False, n_perms=2, interactions=[("a", "b", "c")]),
+                 both(base(), use_raw=False, n_perms=2, groupby_pairs=pd.DataFrame({"x": [1]}))):
+        assert msgs is not None and msgs[0] == msgs[1], msgs
+    assert both(base(), use_raw=False, n_perms=2, layer="x") is not None                     # KeyError: unknown layer
