@@ -151,3 +151,29 @@ def test_philox_label_mixing_matches_hypergeometric():
                 var = m * (K / n) * (1 - K / n) * (n - m) / (n - 1)
                 assert abs(x.mean() - mean) < 5 * np.sqrt(var / P), (n, a, b, x.mean(), mean)
                 assert 0.85 < x.var() / var < 1.18, (n, a, b, x.var(), var)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_c_restatement_equals_literal_numpy_port_on_random_inputs(seed):
+    """The two oracles against each other beyond the fixtures: the C restatement (sequential float32 sums; exact
+    quartile selection) and the literal NumPy/SciPy port (the reference's own calls) on random shapes - ragged
+    clusters, explicit zeros, negative values, dense and very sparse matrices - bit for bit."""
+    from scipy import sparse
+    rng = np.random.default_rng(seed)
+    N, G, L = int(rng.integers(20, 160)), int(rng.integers(3, 40)), int(rng.integers(1, 7))
+    dens = float(rng.choice([0.02, 0.2, 0.7, 1.0]))
+    X = sparse.random(N, G, density=dens, format="csr", dtype=np.float32, random_state=seed,
+                      data_rvs=lambda k: (rng.gamma(1.5, 2.0, k) - (1.0 if seed % 2 else 0.0)).astype(np.float32))
+    if X.nnz:
+        X.data[::7] = 0.0                                   # explicit stored zeros
+    labels = rng.integers(0, L, N).astype(np.int32)
+    labels[:L] = np.arange(L)                               # no empty cluster: SciPy's mean divides by the row count
+    P = 5
+    perm_idx = numpy_port.perm_indices(N, P, 100 + seed)
+    want = numpy_port.get_means_perms(X, labels, L, P, 100 + seed)
+    assert np.array_equal(c_oracle.cube(X, labels, L, perm_idx), want.astype(np.float32))
+    if X.nnz:
+        mat_max = np.float32(max(X.max(), 0.5))
+        want_t = numpy_port.get_trimean_perms(X, labels, L, P, 100 + seed, mat_max)
+        assert np.array_equal(c_oracle.trimean_cube(X, labels, L, perm_idx, mat_max), want_t)
+        assert np.array_equal(c_oracle.trimean_cube(X, labels, L, None, mat_max)[0], numpy_port.observed_trimean(X, labels, L, mat_max))
