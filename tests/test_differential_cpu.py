@@ -272,3 +272,33 @@ def test_degenerate_inputs_and_error_conventions_agree():
                  both(base(), use_raw=False, n_perms=2, groupby_pairs=pd.DataFrame({"x": [1]}))):
         assert msgs is not None and msgs[0] == msgs[1], msgs
     assert both(base(), use_raw=False, n_perms=2, layer="x") is not None                     # KeyError: unknown layer
+
+
+@pytest.mark.parametrize("combo", ["cpdb+gmean+natmi", "gmean+sca+scseqcomm", "connectome+logfc"])
+def test_custom_consensus_agrees(combo):
+    """`AggregateClass(aggregate_meta, methods=[...])` with method lists other than the default (two permutation nulls
+    counted in one pass; a consensus without any permutation method): columns, scores and both rank columns."""
+    ref = ref_shim.load_reference()
+    RA = ref.rank_aggregate_mod
+    rm, om = {
+        "cpdb+gmean+natmi": ([ref.cellphonedb, ref.geometric_mean, ref.natmi_mod.natmi], [li.mt.cellphonedb, li.mt.geometric_mean, li.mt.natmi]),
+        "gmean+sca+scseqcomm": ([ref.geometric_mean, ref.sca_mod.singlecellsignalr, ref.scseqcomm],
+                                [li.mt.geometric_mean, li.mt.singlecellsignalr, li.mt.scseqcomm]),
+        "connectome+logfc": ([ref.connectome_mod.connectome, ref.logfc_mod.logfc], [li.mt.connectome, li.mt.logfc]),
+    }[combo]
+    adata = make_synthetic_adata(150, 400, 4, density=0.15, seed_data=5, seed_labels=6)
+    kw = dict(groupby="cluster", use_raw=False, inplace=False, verbose=False, n_perms=6, seed=2)
+    want = RA.AggregateClass(RA._rank_aggregate_meta, methods=rm)(adata.copy(), **kw)
+    got = li.mt.AggregateClass(li.mt.aggregate_meta, methods=om)(adata.copy(), perm_source="reference", **kw)
+    assert list(got.columns) == list(want.columns) and len(got) == len(want)
+    a, b = got.sort_values(KEY).reset_index(drop=True), want.sort_values(KEY).reset_index(drop=True)
+    assert (a[KEY].astype(str).values == b[KEY].astype(str).values).all()
+    for c in want.columns[4:]:
+        tol = dict(rtol=0, atol=1e-5) if c == "inter_score" else dict(rtol=1e-4, atol=2e-6)
+        if c.endswith("_pvals"):
+            assert np.array_equal(a[c].values, b[c].values), c
+        elif c.endswith("_rank"):
+            d = np.abs(a[c].values - b[c].values)
+            assert (d <= 1e-4 * np.maximum(np.abs(b[c].values), 1e-12)).mean() >= 0.95 and d.max() <= 5e-3, (c, float(d.max()))
+        else:
+            np.testing.assert_allclose(a[c].values.astype(float), b[c].values.astype(float), err_msg=c, **tol)
