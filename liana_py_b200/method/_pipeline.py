@@ -63,7 +63,8 @@ def _cached_tables(res: pd.DataFrame, var_names: np.ndarray):
     """(ResourceTables, all resource entities).  Two levels: the resource split into subunits (Python string work over
     4.6 k interactions, ~50 ms) is memoised on the resource's content; the tables for one gene set (array operations,
     < 1 ms) on (resource, gene names) - every sample of `by_sample` has its own set of non-empty genes."""
-    rkey = int(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).sum())
+    # row hashes as bytes: sensitive to the ORDER of the interactions too (a plain sum would not be)
+    rkey = hash(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).values.tobytes())
     ex = _EXPLODED_CACHE.get(rkey)
     if ex is None:
         if len(_EXPLODED_CACHE) >= 8:
