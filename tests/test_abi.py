@@ -31,3 +31,27 @@ def test_create_fails_loudly_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(_engine.EngineError, match="lrperm_create failed"):
         _engine.Engine(0)
+
+
+def test_product_never_imports_the_oracle():
+    """`oracle/` and the tests' engine stand-in are checkers: nothing under the package may import them, and the
+    engine has no CPU path (creating one without the CUDA library / a device raises)."""
+    import ast
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent / "liana_py_b200"
+    for path in root.rglob("*.py"):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for n in names:
+                assert not (n == "oracle" or n.startswith("oracle.") or n.startswith("_oracle_engine")), (str(path), n)
+    import torch
+    if not torch.cuda.is_available():
+        import pytest
+        from liana_py_b200 import _engine
+        with pytest.raises(_engine.EngineError):
+            _engine.Engine(0)
