@@ -302,3 +302,38 @@ def test_custom_consensus_agrees(combo):
             assert (d <= 1e-4 * np.maximum(np.abs(b[c].values), 1e-12)).mean() >= 0.95 and d.max() <= 5e-3, (c, float(d.max()))
         else:
             np.testing.assert_allclose(a[c].values.astype(float), b[c].values.astype(float), err_msg=c, **tol)
+
+
+@pytest.mark.parametrize("seed", range(90, 94))
+def test_random_mudata_inputs(seed):
+    """A random input split into two modalities at a random column, with a random choice of `x_layer` / `y_use_raw` /
+    transforms: the reference's `mdata_to_anndata` + pipeline against `mdata_kwargs` here."""
+    from liana_py_b200.testing._anndata_lite import MuDataLite
+    ref = ref_shim.load_reference()
+    rng = np.random.default_rng(seed)
+    adata, kw = _case(seed)
+    kw.pop("groupby_pairs", None)
+    cut = int(rng.integers(adata.shape[1] // 4, 3 * adata.shape[1] // 4))
+    x, y = adata[:, :cut].copy(), adata[:, cut:].copy()
+    mkw = dict(x_mod="left", y_mod="right")
+    if rng.random() < 0.5:
+        lay = x.X.copy(); lay.data = np.log1p(lay.data).astype(np.float32)
+        x.layers["log"] = lay
+        mkw["x_layer"] = "log"
+    if rng.random() < 0.5:
+        mkw["y_transform"] = np.sqrt
+    if rng.random() < 0.5:
+        raw = y.X.copy(); raw.data = (raw.data * 2).astype(np.float32)
+        y.raw = type("Raw", (), {"X": raw, "var_names": y.var_names, "var": y.var,
+                                 "to_adata": lambda self=None, _y=y, _r=raw: type(_y)(X=_r, obs=_y.obs.copy(), var=_y.var.copy())})()
+        mkw["y_use_raw"] = True
+    mdata = MuDataLite({"left": x, "right": y}, obs=adata.obs.copy())
+    common = dict(groupby="cluster", inplace=False, verbose=False, mdata_kwargs=mkw, **kw)
+    try:
+        want = ref.cellphonedb(mdata, **common)
+    except ValueError:
+        with pytest.raises(ValueError):
+            li.mt.cellphonedb(mdata, perm_source="reference", **common)
+        return
+    got = li.mt.cellphonedb(mdata, perm_source="reference", **common)
+    _same(got, want, ["ligand_means", "receptor_means", "ligand_props", "receptor_props", "lr_means", "cellphone_pvals"])
