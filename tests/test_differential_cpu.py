@@ -337,3 +337,36 @@ def test_random_mudata_inputs(seed):
         return
     got = li.mt.cellphonedb(mdata, perm_source="reference", **common)
     _same(got, want, ["ligand_means", "receptor_means", "ligand_props", "receptor_props", "lr_means", "cellphone_pvals"])
+
+
+@pytest.mark.parametrize("name,supp", [
+    ("cellchat", ["ligand_means", "receptor_means", "mat_mean"]),
+    ("natmi", ["ligand_zscores", "receptor_logfc", "mat_max", "ligand_trimean"]),
+    ("scseqcomm", ["ligand_means_sums", "mat_mean"]),
+    ("logfc", ["ligand_cdf", "receptor_cdf", "ligand_props"]),
+    ("cellphonedb", ["nonsense"]),                      # KeyError on both sides
+    ("cellphonedb", ["ligand_trimean"]),                # trimeans exist only with mat_max: KeyError on both sides
+])
+def test_supp_columns_of_every_method_agree(name, supp):
+    ref = ref_shim.load_reference()
+    ref_fn = {"cellchat": ref.cellchat, "natmi": ref.natmi_mod.natmi, "scseqcomm": ref.scseqcomm, "logfc": ref.logfc_mod.logfc,
+              "cellphonedb": ref.cellphonedb}[name]
+    our_fn = getattr(li.mt, name)
+    adata = make_synthetic_adata(150, 400, 4, density=0.15, seed_data=5, seed_labels=6)
+    kw = dict(groupby="cluster", use_raw=False, inplace=False, verbose=False, supp_columns=supp)
+    perm = dict(n_perms=4, seed=3) if name in ("cellchat", "cellphonedb") else {}
+    extra = dict(perm_source="reference") if perm else {}
+    try:
+        want = ref_fn(adata.copy(), **kw, **perm)
+    except KeyError:
+        with pytest.raises(KeyError):
+            our_fn(adata.copy(), **kw, **perm, **extra)
+        return
+    got = our_fn(adata.copy(), **kw, **perm, **extra)
+    assert list(got.columns) == list(want.columns) and len(got) == len(want)
+    a, b = got.sort_values(KEY).reset_index(drop=True), want.sort_values(KEY).reset_index(drop=True)
+    for c in want.columns:
+        if a[c].dtype.kind == "f":
+            np.testing.assert_allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=1e-4, atol=1e-5, err_msg=c)
+        else:
+            assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
