@@ -55,3 +55,38 @@ def test_product_never_imports_the_oracle():
         from liana_py_b200 import _engine
         with pytest.raises(_engine.EngineError):
             _engine.Engine(0)
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/lrperm.h against the `argtypes` the ctypes binding declares: same number of
+    parameters, pointers where the header has pointers, 64-bit integers where it has int64_t / uint64_t, doubles and
+    floats where it has them - a binding that drifts from the header corrupts memory silently."""
+    import ctypes as C
+    import re
+    from liana_py_b200 import _engine
+    lib = _engine.load_library()
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "lrperm.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|void|const\s+char\s*\*)\s*(lrperm_\w+)\s*\(([^;{}]*?)\)\s*;", header)
+    assert {p[0] for p in protos} == set(_engine.ABI_SYMBOLS)
+    checked = 0
+    for name, params in protos:
+        fn = getattr(lib, name)
+        plist = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]
+        if fn.argtypes is None:
+            assert name in ("lrperm_abi_version",) or not plist, f"{name}: no argtypes declared"
+            continue
+        assert len(fn.argtypes) == len(plist), (name, len(fn.argtypes), plist)
+        for at, p in zip(fn.argtypes, plist):
+            if "*" in p:
+                assert at in (C.c_void_p, C.c_char_p) or issubclass(at, C._Pointer), (name, p, at)
+            elif re.search(r"\b(u?int64_t)\b", p):
+                assert C.sizeof(at) == 8 and at not in (C.c_double, C.c_void_p), (name, p, at)
+            elif re.search(r"\bdouble\b", p):
+                assert at is C.c_double, (name, p, at)
+            elif re.search(r"\bfloat\b", p):
+                assert at is C.c_float, (name, p, at)
+            else:                                   # int / int32_t / enums
+                assert C.sizeof(at) == 4 and at not in (C.c_float,), (name, p, at)
+        checked += 1
+    assert checked >= 25
