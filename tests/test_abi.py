@@ -90,3 +90,13 @@ def test_ctypes_signatures_match_the_header():
                 assert C.sizeof(at) == 4 and at not in (C.c_float,), (name, p, at)
         checked += 1
     assert checked >= 25
+    # return types: status codes are int, the error text a C string, destroy returns nothing
+    rets = {v: k for k, v in re.findall(r"\b(int|void|const\s+char\s*\*)\s*(lrperm_\w+)\s*\(", header)}
+    for name, ret in rets.items():
+        rt = getattr(lib, name).restype
+        if ret == "void":
+            assert rt is None, name
+        elif ret.startswith("const"):
+            assert rt is C.c_char_p, name
+        else:
+            assert rt is C.c_int, name
