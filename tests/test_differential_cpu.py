@@ -22,7 +22,14 @@ KEY = ["source", "target", "ligand_complex", "receptor_complex"]
 @pytest.fixture(autouse=True)
 def oracle_engine(monkeypatch):
     monkeypatch.setitem(PL._ENGINES, 0, OracleEngine())
+    # the reference switches `specificity` of its shared method objects off for good after an `n_perms=None` call
+    # (`_liana_pipe.py:420-422`); keep one test's calls from changing what the next one gets
+    ref = ref_shim.load_reference()
+    methods = [getattr(m, "_method", m) for m in (ref.cellphonedb, ref.geometric_mean, ref.cellchat)]   # the records that get mutated
+    saved = [m.specificity for m in methods]
     yield
+    for m, spec in zip(methods, saved):
+        m.specificity = spec
 
 
 def _case(seed):
