@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LRPERM_ABI_VERSION 3   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads; 3: dense staging */
+#define LRPERM_ABI_VERSION 4   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads; 3: dense staging; 4: run statistics, matrix export */
 
 /* status codes */
 #define LRPERM_OK              0
@@ -259,6 +259,21 @@ int lrperm_philox_perms(lrperm_engine *h, int64_t n_cells, int64_t n_perms, int6
  * (summed over batches), out[6] its launch count, out[7] permutations per batch. */
 int lrperm_last_timings(lrperm_engine *h, float *out8);
 
+/* Work statistics of the last lrperm_run in FAST order: out[0] genes accumulated, out[1] stored entries of those genes,
+ * out[2] (gene, cell tile) chunks launched per permutation group, out[3] stored entries of the whole matrix.  With the
+ * option "skip_unreferenced" (default 1) a run that exports no cube accumulates only the genes some triple of
+ * lrperm_set_triples reads (the reference computes every gene of the subset matrix, _get_mean_perms.py:61-64, and then
+ * gathers only those, _liana_pipe.py:416-419); the counts are identical either way. */
+int lrperm_run_stats(lrperm_engine *h, int64_t *out4);
+
+/* Shape of the engine's matrix: out[0] cells, out[1] genes, out[2] stored entries. */
+int lrperm_matrix_info(lrperm_engine *h, int64_t *out3);
+/* Copy the engine's matrix (after lrperm_set_matrix_csr / lrperm_commit_matrix) out as CSR: indptr int32 [N+1], indices
+ * int32 [nnz], data float32 [nnz]; the order of the entries inside a row is unspecified.  out_on_device != 0: device
+ * pointers, which may belong to ANOTHER CUDA device (unified addressing: the copy then goes peer to peer over NVLink) -
+ * this is how a committed matrix is replicated to the engines of other GPUs without crossing PCIe again. */
+int lrperm_export_matrix_csr(lrperm_engine *h, int32_t *indptr, int32_t *indices, float *data, int out_on_device);
+
 /* Tuning knobs of FAST mode (0 = engine default): permutations per batch (multiple of 128), stored
  * entries per gene chunk, and MiB of label slab one cell tile may span (kept L2 resident). */
 int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_chunk_nnz, int32_t fast_tile_mib);
@@ -271,7 +286,8 @@ int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_ch
  *   "slab0_by_tile"       1 (default) = the first batch's label slab is generated and consumed cell tile by cell tile
  *   "fast_first_batch"    permutations of a short first batch of the pipelined FAST path (0 = none, default)
  *   "trimean_chunk_nnz"   stored entries per chunk of the trimean path (0 = auto; multiple of 1024)
- *   "trimean_perm_batch"  permutations per batch of the trimean path (0 = auto; multiple of 128)  */
+ *   "trimean_perm_batch"  permutations per batch of the trimean path (0 = auto; multiple of 128)
+ *   "skip_unreferenced"   1 (default) = runs that export no cube skip the genes no triple reads (see lrperm_run_stats)  */
 int lrperm_set_option(lrperm_engine *h, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -28,6 +28,7 @@ ABI_SYMBOLS = (
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
     "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
     "lrperm_argsort", "lrperm_staged_cluster_stats", "lrperm_stage_matrix_dense",
+    "lrperm_run_stats", "lrperm_matrix_info", "lrperm_export_matrix_csr",
 )
 
 _lib = None
@@ -80,6 +81,9 @@ def load_library():
     lib.lrperm_staged_cluster_stats.argtypes = [vp, vp, i32, vp, vp]
     lib.lrperm_resolve_triples.argtypes = [vp, i32, i32, i32, vp, vp, vp, C.c_int, vp, C.c_double, vp, C.c_int, C.c_int, vp]
     lib.lrperm_fetch_triples.argtypes = [vp] + [vp] * 10
+    lib.lrperm_run_stats.argtypes = [vp, vp]
+    lib.lrperm_matrix_info.argtypes = [vp, vp]
+    lib.lrperm_export_matrix_csr.argtypes = [vp, vp, vp, vp, C.c_int]
     _lib = lib
     return lib
 
@@ -487,6 +491,37 @@ class Engine:
         self._check(self._lib.lrperm_philox_perms(self._h, int(n_cells), int(n_perms), int(perm_offset),
                                                   C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_void_p(out.ctypes.data), 0))
         return out
+
+    def run_stats(self) -> dict:
+        """Work of the last FAST run: genes / stored entries actually accumulated (include/lrperm.h)."""
+        buf = (C.c_int64 * 4)()
+        self._check(self._lib.lrperm_run_stats(self._h, C.cast(buf, C.c_void_p)))
+        return {"genes_scored": int(buf[0]), "nnz_scored": int(buf[1]), "chunks_run": int(buf[2]), "nnz": int(buf[3])}
+
+    def matrix_info(self):
+        """(cells, genes, stored entries) of the engine's matrix."""
+        buf = (C.c_int64 * 3)()
+        self._check(self._lib.lrperm_matrix_info(self._h, C.cast(buf, C.c_void_p)))
+        return int(buf[0]), int(buf[1]), int(buf[2])
+
+    def export_matrix_csr(self, device=None):
+        """The engine's matrix as CSR.  device=None: NumPy arrays (indptr, indices, data); a torch CUDA device (possibly
+        another GPU than the engine's): torch tensors there, copied device to device (peer copy over NVLink)."""
+        n, g, nnz = self.matrix_info()
+        if device is None:
+            indptr = np.empty(n + 1, dtype=np.int32)
+            indices, data = np.empty(nnz, dtype=np.int32), np.empty(nnz, dtype=np.float32)
+            self._check(self._lib.lrperm_export_matrix_csr(self._h, C.c_void_p(indptr.ctypes.data), C.c_void_p(indices.ctypes.data),
+                                                           C.c_void_p(data.ctypes.data), 0))
+            return indptr, indices, data
+        import torch
+        indptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+        indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)[:nnz]
+        data = torch.empty(max(nnz, 1), dtype=torch.float32, device=device)[:nnz]
+        torch.cuda.synchronize(device)
+        self._check(self._lib.lrperm_export_matrix_csr(self._h, C.c_void_p(indptr.data_ptr()), C.c_void_p(indices.data_ptr()),
+                                                       C.c_void_p(data.data_ptr()), 1))
+        return indptr, indices, data
 
     def timings(self) -> dict:
         buf = (C.c_float * 8)()

@@ -226,6 +226,21 @@ struct lrperm_engine {
     int32_t fast_first_batch = 0;                       // permutations of a short first batch (0 = none; A/B only)
     int32_t n_chunks = 0, n_slots = 0;
     DevBuf chunks;
+    // Genes no triple reads are not accumulated when no cube is exported (option "skip_unreferenced"): the chunk
+    // table keeps ALL chunks and their slot numbers (so the summation order of every referenced gene, and with it every
+    // result, is unchanged), `chunks_f` lists the chunks of the referenced genes only, tile-major like `chunks`.
+    int32_t skip_unref = 1;
+    std::vector<uint8_t> h_needed;                      // [G] 1 = some triple reads the gene (from lrperm_set_triples)
+    DevBuf needed_dev;
+    bool needed_valid = false;
+    int64_t needed_version = 0, chunk_table_id = 0;
+    int64_t chunks_f_needed = -1, chunks_f_table = -1;  // versions the filtered list was built for
+    int32_t chunks_f_tiles = 0;
+    DevBuf chunks_f;
+    std::vector<FastChunk> h_chunks_f;
+    std::vector<int32_t> h_tile_chunk_ptr_f;
+    bool filter_tables = false;                         // chunks_append_tile maintains the filtered list too (set by the run)
+    int64_t stat_genes_scored = 0, stat_nnz_scored = 0, stat_chunks_run = 0;   // of the last lrperm_run
 
     // work buffers
     DevBuf slab2, partials2;              // second halves of the double buffers of the pipelined FAST path
@@ -243,6 +258,7 @@ struct lrperm_engine {
     bool vsc_ready = false, tm_tables_ready = false;
     int32_t tm_chunk_nnz = 0, tm_perm_batch = 0;        // tuning (0 = auto)
     int32_t tm_table_nnz = -1;                           // chunk size the trimean chunk table was built for
+    int64_t tm_table_needed = 0;                         // needed_version it was filtered by (0 = all genes)
     int32_t tm_n_chunks = 0, tm_n_slots = 0, tm_n_regions = 0;
     float tm_ms[5] = {0, 0, 0, 0, 0};                    // count, prefix, select, finalize, select-warps-that-walked (n/a)
 
@@ -529,12 +545,17 @@ int chunks_append_tile(lrperm_engine* h, int32_t t, int32_t chunk_nnz, cudaStrea
         h->h_tile_slot_ptr.assign((size_t)h->n_tiles * ((size_t)G + 1), 0);
         h->h_tile_entry0.assign(1, 0);
         h->n_slots = 0;
+        ++h->chunk_table_id;
+        h->h_chunks_f.clear();
+        h->h_tile_chunk_ptr_f.assign(1, 0);
+        h->chunks_f_tiles = 0;
         // device tables sized for any tiling of this matrix
         const size_t max_chunks = (size_t)(h->nnz / std::max(chunk_nnz, 1)) + (size_t)G * (size_t)h->n_tiles + 1;
         CK(h->chunks.ensure(sizeof(FastChunk) * max_chunks));
         CK(h->tile_slot_ptr.ensure(sizeof(int32_t) * h->h_tile_slot_ptr.size()));
-        const size_t words = max_chunks * (sizeof(FastChunk) / 4) + h->h_tile_slot_ptr.size();
+        const size_t words = 2 * max_chunks * (sizeof(FastChunk) / 4) + h->h_tile_slot_ptr.size();
         CK(h->table_pin.ensure(sizeof(uint32_t) * words));      // an outgrown mirror is retired, not freed: nothing in flight loses it
+        CK(h->chunks_f.ensure(sizeof(FastChunk) * max_chunks));
     }
     const int32_t* hist = h->hist_pin.as<int32_t>() + (size_t)t * G;
     int32_t pos = h->h_tile_entry0[(size_t)t];
@@ -575,8 +596,59 @@ int chunks_append_tile(lrperm_engine* h, int32_t t, int32_t chunk_nnz, cudaStrea
         copy_words_kernel<<<grid_for((int64_t)G + 1, 256, 64), 256, 0, st>>>(pin, reinterpret_cast<uint32_t*>(h->tile_slot_ptr.as<int32_t>() + (size_t)t * ((size_t)G + 1)), (int64_t)G + 1);
         CK_LAUNCH();
     }
+    if (h->filter_tables && h->chunks_f_tiles == t) {
+        // the tile's chunks of referenced genes, same order; third region of the pinned mirror
+        const size_t first_f = h->h_chunks_f.size();
+        for (size_t i = first; i < h->h_chunks.size(); ++i)
+            if (h->h_needed[(size_t)h->h_chunks[i].gene]) h->h_chunks_f.push_back(h->h_chunks[i]);
+        h->h_tile_chunk_ptr_f.push_back((int32_t)h->h_chunks_f.size());
+        const size_t n_f = h->h_chunks_f.size() - first_f;
+        if (n_f) {
+            uint32_t* pin = h->table_pin.as<uint32_t>() + max_chunks * cw + h->h_tile_slot_ptr.size() + first_f * cw;
+            memcpy(pin, h->h_chunks_f.data() + first_f, sizeof(FastChunk) * n_f);
+            copy_words_kernel<<<grid_for((int64_t)(n_f * cw), 256, 256), 256, 0, st>>>(pin, reinterpret_cast<uint32_t*>(h->chunks_f.as<FastChunk>() + first_f), (int64_t)(n_f * cw));
+            CK_LAUNCH();
+        }
+        h->chunks_f_tiles = t + 1;
+        h->chunks_f_needed = h->needed_version;
+        h->chunks_f_table = h->chunk_table_id;
+    }
     h->tiles_tabled = t + 1;
     return LRPERM_OK;
+}
+
+// filtered chunk list (referenced genes only) of a chunk table that is complete on the host
+int ensure_filtered_chunks(lrperm_engine* h) {
+    if (h->chunks_f_table == h->chunk_table_id && h->chunks_f_needed == h->needed_version && h->chunks_f_tiles == h->n_tiles) return LRPERM_OK;
+    h->h_chunks_f.clear();
+    h->h_tile_chunk_ptr_f.assign(1, 0);
+    for (int32_t t = 0; t < h->n_tiles; ++t) {
+        for (int32_t i = h->h_tile_chunk_ptr[(size_t)t]; i < h->h_tile_chunk_ptr[(size_t)t + 1]; ++i)
+            if (h->h_needed[(size_t)h->h_chunks[(size_t)i].gene]) h->h_chunks_f.push_back(h->h_chunks[(size_t)i]);
+        h->h_tile_chunk_ptr_f.push_back((int32_t)h->h_chunks_f.size());
+    }
+    CK(h->chunks_f.ensure(sizeof(FastChunk) * std::max<size_t>(h->h_chunks_f.size(), 1)));
+    if (!h->h_chunks_f.empty())     // pageable source: the call returns once the data has been staged
+        CK(cudaMemcpyAsync(h->chunks_f.p, h->h_chunks_f.data(), sizeof(FastChunk) * h->h_chunks_f.size(), cudaMemcpyHostToDevice, h->stream));
+    h->chunks_f_table = h->chunk_table_id;
+    h->chunks_f_needed = h->needed_version;
+    h->chunks_f_tiles = h->n_tiles;
+    return LRPERM_OK;
+}
+
+// work statistics of a FAST run: genes / stored entries / chunk warps actually accumulated
+void fast_run_stats(lrperm_engine* h, bool filt) {
+    const int32_t G = (int32_t)h->G;
+    int64_t genes = 0, nnz = 0;
+    const int32_t* hist = h->hist_pin.as<int32_t>();
+    for (int32_t g = 0; g < G; ++g) {
+        if (filt && !h->h_needed[(size_t)g]) continue;
+        ++genes;
+        if (hist) for (int32_t t = 0; t < h->n_tiles; ++t) nnz += hist[(size_t)t * G + g];
+    }
+    h->stat_genes_scored = genes;
+    h->stat_nnz_scored = nnz;
+    h->stat_chunks_run = filt ? (int64_t)h->h_chunks_f.size() : (int64_t)h->h_chunks.size();
 }
 
 // everything at once (matrix resident): CSC of all tiles, then all chunk tables
@@ -663,7 +735,7 @@ int launch_exact(lrperm_engine* h, const PermSource& ps, int32_t pb, float* cube
 }
 
 template <int Q>
-int launch_fast_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, int32_t c0, int32_t cn) {
+int launch_fast_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, const FastChunk* table, int32_t c0, int32_t cn) {
     const int32_t L = h->L;
     const size_t smem = (size_t)kFastWarps * L * Q * 32 * sizeof(float);
     CK(cudaFuncSetAttribute(fast_means_kernel<Q, kFastWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -672,14 +744,14 @@ int launch_fast_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* part
     const int64_t grid = (items + kFastWarps - 1) / kFastWarps;
     if (grid > 0) {
         fast_means_kernel<Q, kFastWarps><<<(unsigned)grid, kFastWarps * 32, smem, h->stream>>>(
-            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>() + c0, cn, slab, PB, L, groups, partials);
+            h->csc_pairs.as<int2>(), table + c0, cn, slab, PB, L, groups, partials);
         CK_LAUNCH();
     }
     return LRPERM_OK;
 }
 
 template <int Q, int B>
-int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, int32_t c0, int32_t cn) {
+int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, const FastChunk* table, int32_t c0, int32_t cn) {
     const int32_t L = h->L;
     const size_t smem = (size_t)L * Q * 128 + 16 * B;
     CK(cudaFuncSetAttribute(fast2_means_kernel<Q, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -688,7 +760,7 @@ int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* par
     if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: too many chunks (%lld CTAs)", (long long)grid);
     if (grid > 0) {
         fast2_means_kernel<Q, B><<<(unsigned)grid, 32, smem, h->stream>>>(
-            h->csc_pairs.as<int2>(), h->chunks.as<FastChunk>() + c0, cn, slab, PB, L, groups, partials);
+            h->csc_pairs.as<int2>(), table + c0, cn, slab, PB, L, groups, partials);
         CK_LAUNCH();
     }
     return LRPERM_OK;
@@ -750,17 +822,24 @@ int launch_score_t(lrperm_engine* h, int scores, const float* cube, int32_t PP, 
 }
 
 
-// chunks [c0, c0 + cn) of the table (cn < 0: all)
-int launch_fast_any(lrperm_engine* h, int Q, int32_t PB, const uint8_t* slab, float* partials, int32_t c0 = 0, int32_t cn = -1) {
-    if (cn < 0) cn = h->n_chunks - c0;
+// chunks [c0, c0 + cn) of the full table, or of the filtered one (referenced genes only) when `filt`; cn < 0: all
+int launch_fast_any(lrperm_engine* h, int Q, int32_t PB, const uint8_t* slab, float* partials, bool filt, int32_t c0 = 0, int32_t cn = -1) {
+    const FastChunk* table = filt ? h->chunks_f.as<FastChunk>() : h->chunks.as<FastChunk>();
+    if (cn < 0) cn = (filt ? (int32_t)h->h_chunks_f.size() : h->n_chunks) - c0;
     if (h->fast_variant == 2) {
-        if (Q == 8) return launch_fast2_q<8, 16>(h, PB, slab, partials, c0, cn);
-        if (Q == 4) return launch_fast2_q<4, 32>(h, PB, slab, partials, c0, cn);
-        return launch_fast2_q<2, 32>(h, PB, slab, partials, c0, cn);
+        if (Q == 8) return launch_fast2_q<8, 16>(h, PB, slab, partials, table, c0, cn);
+        if (Q == 4) return launch_fast2_q<4, 32>(h, PB, slab, partials, table, c0, cn);
+        return launch_fast2_q<2, 32>(h, PB, slab, partials, table, c0, cn);
     }
-    if (Q == 4) return launch_fast_q<4>(h, PB, slab, partials, c0, cn);
-    if (Q == 2) return launch_fast_q<2>(h, PB, slab, partials, c0, cn);
-    return launch_fast_q<1>(h, PB, slab, partials, c0, cn);
+    if (Q == 4) return launch_fast_q<4>(h, PB, slab, partials, table, c0, cn);
+    if (Q == 2) return launch_fast_q<2>(h, PB, slab, partials, table, c0, cn);
+    return launch_fast_q<1>(h, PB, slab, partials, table, c0, cn);
+}
+
+// FAST mode accumulates only the genes some triple reads when nothing else consumes the cube
+bool fast_filter_on(const lrperm_engine* h, int scores, const float* cube_out) {
+    return h->skip_unref && scores != 0 && cube_out == nullptr && h->have_triples && h->needed_valid &&
+           (int64_t)h->h_needed.size() == h->G;
 }
 
 struct RunArgs {
@@ -898,6 +977,8 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     // transfer (chunks are scheduled tile-major anyway): the host waits for tile t's CSC sort, builds its chunk
     // table, launches the tile's chunk warps; tiles t+1.. keep crossing PCIe and being sorted on the copy stream.
     const bool gated = h->matrix_pending && h->csc_tile_cells == tile_cells;
+    const bool filt = fast_filter_on(h, a.scores, a.cube_out);
+    h->filter_tables = filt;
     size_t slots_cap;
     if (gated) {
         if ((rc = submit_tiles(h, -1))) return rc;           // behind the label / triple uploads in the copy engine's queue
@@ -907,8 +988,10 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     } else {
         if ((rc = wait_matrix(h, false))) return rc;
         if ((rc = ensure_fast_tables(h, chunk_nnz, tile_cells))) return rc;
+        if (filt && (rc = ensure_filtered_chunks(h))) return rc;
         slots_cap = (size_t)std::max(h->n_slots, 1);
     }
+    const uint8_t* d_needed = filt ? h->needed_dev.as<uint8_t>() : nullptr;
     const size_t part_max = sizeof(float) * slots_cap * L * pb_max;
     CK(h->partials.ensure(part_max));
     if (dbl) CK(h->partials2.ensure(part_max));
@@ -927,10 +1010,11 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
             for (int32_t t = 0; t < h->n_tiles; ++t) {
                 if (gated && (rc = chunks_append_tile(h, t, chunk_nnz, sA))) return rc;      // host waits for tile t's CSC
                 if (by_tile) CK(cudaStreamWaitEvent(sA, h->ev_slab_tile[(size_t)t], 0));   // the tile's slab rows exist
-                const int32_t c0 = h->h_tile_chunk_ptr[(size_t)t], c1 = h->h_tile_chunk_ptr[(size_t)t + 1];
+                const std::vector<int32_t>& tcp = filt ? h->h_tile_chunk_ptr_f : h->h_tile_chunk_ptr;
+                const int32_t c0 = tcp[(size_t)t], c1 = tcp[(size_t)t + 1];
                 // kernel time of the tile alone (the waits above - slab rows, CSC of an arriving tile - are not kernel time)
                 CK(cudaEventRecord(h->ev_main_tile[2 * (size_t)t], sA));
-                if (c1 > c0 && (rc = launch_fast_any(h, Q, PBb, slabs[0], parts[0], c0, c1 - c0))) return rc;
+                if (c1 > c0 && (rc = launch_fast_any(h, Q, PBb, slabs[0], parts[0], filt, c0, c1 - c0))) return rc;
                 CK(cudaEventRecord(h->ev_main_tile[2 * (size_t)t + 1], sA));
             }
             h->main_tiles_timed = h->n_tiles;
@@ -941,13 +1025,13 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
                 CK(cudaStreamWaitEvent(sA, h->ev_matrix, 0));
                 h->check_matrix_flag = true;
             }
-        } else if ((rc = launch_fast_any(h, Q, PBb, slabs[b & 1], parts[b & 1]))) return rc;
+        } else if ((rc = launch_fast_any(h, Q, PBb, slabs[b & 1], parts[b & 1], filt))) return rc;
         CK(cudaEventRecord(EV(b, 3), sA));
         // ---- B: finalize + score (+ optional cube export) ----
         CK(cudaStreamWaitEvent(sB, EV(b, 3), 0));
         CK(cudaEventRecord(EV(b, 4), sB));
         fast_finalize_kernel<<<grid_for((int64_t)G * L * PBb, 256, h->sm_count * 8), 256, 0, sB>>>(
-            parts[b & 1], h->tile_slot_ptr.as<int32_t>(), h->n_tiles, h->inv_n.as<float>(), G, L, PBb, h->cube.as<float>(), PBb, 0);
+            parts[b & 1], h->tile_slot_ptr.as<int32_t>(), h->n_tiles, h->inv_n.as<float>(), G, L, PBb, h->cube.as<float>(), PBb, 0, d_needed);
         CK_LAUNCH();
         CK(cudaEventRecord(EV(b, 5), sB));
         if (a.scores) {
@@ -975,6 +1059,8 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     // join: A continues (result copies) after the last score on B
     CK(cudaStreamWaitEvent(sA, EV(n_batches - 1, 6), 0));
     CK(cudaEventRecord(h->events[1], sA));
+    h->filter_tables = false;
+    fast_run_stats(h, filt);
     return LRPERM_OK;
 }
 
@@ -1044,8 +1130,11 @@ int build_vsc(lrperm_engine* h) {
 
 // chunk table of the trimean path: every gene's positive region and negative region (the explicit zeros between
 // them need no walk), cut every chunk_nnz entries; slots are consecutive inside a region; longest chunks first
-int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz) {
-    if (h->tm_table_nnz == chunk_nnz) return LRPERM_OK;
+int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz, bool filt) {
+    // filt: only the genes some triple reads get chunks (their regions are independent of each other, so nothing else
+    // changes); the table is then tied to the triple set it was built for
+    const int64_t want_needed = filt ? h->needed_version : 0;
+    if (h->tm_table_nnz == chunk_nnz && h->tm_table_needed == want_needed) return LRPERM_OK;
     StageTimer timer("build_tm_chunks");
     const int32_t G = (int32_t)h->G;
     std::vector<int32_t> pos_end((size_t)G), neg_begin((size_t)G);
@@ -1066,6 +1155,7 @@ int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz) {
     std::vector<uint8_t> region_dir;
     int32_t slot = 0;
     for (int32_t g = 0; g < G; ++g) {
+        if (filt && !h->h_needed[(size_t)g]) continue;
         const int32_t b[2] = {h->h_csc_ptr[(size_t)g], neg_begin[(size_t)g]};
         const int32_t e[2] = {pos_end[(size_t)g], h->h_csc_ptr[(size_t)g + 1]};
         for (int dir = 0; dir < 2; ++dir) {
@@ -1096,6 +1186,7 @@ int build_tm_chunks(lrperm_engine* h, int32_t chunk_nnz) {
     CK(cudaMemcpyAsync(h->tm_region_ptr.p, region_ptr.data(), sizeof(int32_t) * region_ptr.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->tm_table_nnz = chunk_nnz;
+    h->tm_table_needed = want_needed;
     return LRPERM_OK;
 }
 
@@ -1226,7 +1317,8 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
     if ((rc = build_vsc(h))) return rc;
     // entries per chunk: the select pass re-walks whole chunks, so they are shorter than FAST mode's
     const int32_t chunk_nnz = h->tm_chunk_nnz ? h->tm_chunk_nnz : 8192;
-    if ((rc = build_tm_chunks(h, chunk_nnz))) return rc;
+    const bool filt = a.score && a.cube_out == nullptr && h->skip_unref && h->have_triples && h->needed_valid && (int64_t)h->h_needed.size() == h->G;
+    if ((rc = build_tm_chunks(h, chunk_nnz, filt))) return rc;
     if ((rc = build_tm_tables(h))) return rc;
     // permutations per batch: the walk visits cells in VALUE order, so the whole label slab of a batch (N x PB
     // bytes) should sit in L2: <= 64 MiB
@@ -1480,7 +1572,7 @@ void lrperm_destroy(lrperm_engine* h) {
                       &h->tmp_a, &h->tmp_b, &h->tmp_c, &h->tmp_d, &h->stage_out, &h->small_a, &h->small_b,
                       &h->vsc_pairs, &h->tm_chunks, &h->tm_region_ptr, &h->tm_counts, &h->tm_prefix, &h->tm_planes, &h->tm_cube,
                       &h->tm_tgt, &h->tm_roles, &h->thr_d, &h->counts_t, &h->tm_diag, &h->tm_chunk_of_slot, &h->tm_region_dir,
-                      &h->tm_walk_flag, &h->tm_walk_list, &h->rs_side, &h->rs_flag, &h->rs_pos, &h->rs_rows, &h->rs_in})
+                      &h->tm_walk_flag, &h->tm_walk_list, &h->rs_side, &h->rs_flag, &h->rs_pos, &h->rs_rows, &h->rs_in, &h->needed_dev, &h->chunks_f})
         b->release();
     for (cudaEvent_t ev : h->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_tile) cudaEventDestroy(ev);
@@ -1541,6 +1633,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "fast_first_batch") {
         if (value < 0 || value > 4096) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_first_batch must be in [0, 4096]");
         h->fast_first_batch = (int32_t)value;
+    } else if (key == "skip_unreferenced") {
+        if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: skip_unreferenced must be 0 or 1");
+        h->skip_unref = (int32_t)value;
     } else if (key == "fast_q") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_q must be 0, 1, 2, 4 or 8");
         h->fast_q = (int32_t)value;
@@ -2082,11 +2177,22 @@ int lrperm_set_triples(lrperm_engine* h, int64_t n_triples, const int32_t* ligan
         build_rows_kernel<<<grid_for((int64_t)T, 256, 1 << 30), 256, 0, h->stream>>>(
             dl, dr, dsrc, dt, (int64_t)T, (int32_t)h->G, h->L, h->rowA.as<int32_t>(), h->rowB.as<int32_t>(), h->err_flag.as<int>());
         CK_LAUNCH();
+        // genes some triple reads (FAST mode skips the others when no cube is exported)
+        CK(h->needed_dev.ensure((size_t)h->G));
+        CK(cudaMemsetAsync(h->needed_dev.p, 0, (size_t)h->G, h->stream));
+        mark_genes_kernel<<<grid_for((int64_t)T, 256, h->sm_count * 8), 256, 0, h->stream>>>(dl, dr, (int64_t)T, (int32_t)h->G, h->needed_dev.as<uint8_t>());
+        CK_LAUNCH();
+        h->h_needed.assign((size_t)h->G, 0);
+        CK(cudaMemcpyAsync(h->h_needed.data(), h->needed_dev.p, (size_t)h->G, cudaMemcpyDeviceToHost, h->stream));
         if (obs_cpdb && (rc = upload(h, h->thr_c, obs_cpdb, sizeof(float) * T, on_device))) return rc;
         if (obs_gmean && (rc = upload(h, h->thr_g, obs_gmean, sizeof(float) * T, on_device))) return rc;
     }
-    rc = check_err_flag(h, "lrperm_set_triples");
+    h->needed_valid = false;
+    rc = check_err_flag(h, "lrperm_set_triples");      // synchronises the stream: h_needed has arrived
     if (rc) return rc;
+    if (T == 0) { CK(h->needed_dev.ensure((size_t)h->G)); CK(cudaMemsetAsync(h->needed_dev.p, 0, (size_t)h->G, h->stream)); h->h_needed.assign((size_t)h->G, 0); }
+    h->needed_valid = true;
+    ++h->needed_version;
     h->T = n_triples;
     h->have_thr_c = obs_cpdb != nullptr;
     h->have_thr_g = obs_gmean != nullptr;
@@ -2249,9 +2355,12 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     CK(h->cube.ensure(sizeof(float) * (size_t)G * L * PP));
     const int64_t n_batches = (n_perms + PB - 1) / PB;
     const bool pipelined = order_mode == LRPERM_ORDER_FAST && h->overlap && n_batches > 0;
+    const bool filt_serial = order_mode == LRPERM_ORDER_FAST && !pipelined && fast_filter_on(h, scores, cube_out);
     if (order_mode == LRPERM_ORDER_FAST && !pipelined) {
         if ((rc = wait_matrix(h, false))) return rc;
         if ((rc = ensure_fast_tables(h, fast_chunk, fast_tile))) return rc;
+        if (filt_serial && (rc = ensure_filtered_chunks(h))) return rc;
+        fast_run_stats(h, filt_serial);
         CK(h->slab.ensure((size_t)N * PB));
         CK(h->partials.ensure(sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB));
     }
@@ -2336,11 +2445,12 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         CK(cudaEventRecord(h->events[evi++], h->stream));
         // ---- stage 2: per-(gene, cluster, permutation) means ----
         if (order_mode == LRPERM_ORDER_FAST) {
-            rc = launch_fast_any(h, Q, PB, h->slab.as<uint8_t>(), h->partials.as<float>());
+            rc = launch_fast_any(h, Q, PB, h->slab.as<uint8_t>(), h->partials.as<float>(), filt_serial);
             if (rc) return rc;
             CK(cudaEventRecord(h->events[evi++], h->stream));   // main kernel done
             fast_finalize_kernel<<<grid_for((int64_t)G * L * PB, 256, h->sm_count * 8), 256, 0, h->stream>>>(
-                h->partials.as<float>(), h->tile_slot_ptr.as<int32_t>(), h->n_tiles, h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0);
+                h->partials.as<float>(), h->tile_slot_ptr.as<int32_t>(), h->n_tiles, h->inv_n.as<float>(), G, L, PB, h->cube.as<float>(), PP, 0,
+                filt_serial ? h->needed_dev.as<uint8_t>() : nullptr);
             CK_LAUNCH();
         } else {
             if ((rc = launch_exact(h, ps, pb, h->cube.as<float>(), PP))) return rc;
@@ -2661,6 +2771,47 @@ int lrperm_rra(lrperm_engine* h, int64_t n_rows, int32_t n_cols, const double* r
     rra_kernel<<<grid_for(n_rows, 128, 1 << 30), 128, 0, h->stream>>>(d_r, d_m, n_rows, n_cols, d_out);
     CK_LAUNCH();
     if (!on_device) CK(cudaMemcpyAsync(rho, d_out, sizeof(double) * (size_t)n_rows, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LRPERM_OK;
+}
+
+int lrperm_run_stats(lrperm_engine* h, int64_t* out4) {
+    if (!h || !out4) return LRPERM_ERR_INVALID;
+    out4[0] = h->stat_genes_scored; out4[1] = h->stat_nnz_scored; out4[2] = h->stat_chunks_run; out4[3] = h->nnz;
+    return LRPERM_OK;
+}
+
+int lrperm_matrix_info(lrperm_engine* h, int64_t* out3) {
+    if (!h || !out3) return LRPERM_ERR_INVALID;
+    if (!h->have_matrix) return h->fail(LRPERM_ERR_INVALID, "lrperm_matrix_info: no matrix set");
+    out3[0] = h->N; out3[1] = h->G; out3[2] = h->nnz;
+    return LRPERM_OK;
+}
+
+int lrperm_export_matrix_csr(lrperm_engine* h, int32_t* indptr, int32_t* indices, float* data, int out_on_device) {
+    if (!h) return LRPERM_ERR_INVALID;
+    DeviceGuard guard(h->device);
+    if (!h->have_matrix) return h->fail(LRPERM_ERR_INVALID, "lrperm_export_matrix_csr: no matrix set");
+    if (!indptr || (h->nnz > 0 && (!indices || !data))) return h->fail(LRPERM_ERR_INVALID, "lrperm_export_matrix_csr: NULL output");
+    int rc;
+    if ((rc = wait_matrix(h, false))) return rc;
+    // cudaMemcpyDefault: with unified addressing the destination may be a buffer of ANOTHER device (peer copy over NVLink)
+    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDefault : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpyAsync(indptr, h->indptr.p, sizeof(int32_t) * (size_t)(h->N + 1), kind, h->stream));
+    if (h->nnz > 0) {
+        const size_t n = (size_t)h->nnz;
+        const int32_t* src_i; const float* src_v;
+        if (!h->csr_packed) { src_i = h->st_indices.as<int32_t>(); src_v = h->st_data.as<float>(); }     // raw arrays of the upload
+        else {
+            CK(h->tmp_c.ensure(sizeof(int32_t) * n));
+            CK(h->tmp_d.ensure(sizeof(float) * n));
+            unpack_pairs_kernel<<<grid_for((int64_t)n, 256, h->sm_count * 16), 256, 0, h->stream>>>(h->csr_pairs.as<int2>(), (int64_t)n, h->tmp_c.as<int32_t>(), h->tmp_d.as<float>());
+            CK_LAUNCH();
+            src_i = h->tmp_c.as<int32_t>(); src_v = h->tmp_d.as<float>();
+        }
+        CK(cudaMemcpyAsync(indices, src_i, sizeof(int32_t) * n, kind, h->stream));
+        CK(cudaMemcpyAsync(data, src_v, sizeof(float) * n, kind, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return LRPERM_OK;
 }

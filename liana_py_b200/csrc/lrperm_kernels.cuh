@@ -227,6 +227,15 @@ __global__ void stage_max_kernel(const int64_t* __restrict__ indptr, const float
     }
 }
 
+// packed {column, value bits} pairs -> separate index / value arrays (lrperm_export_matrix_csr)
+__global__ void unpack_pairs_kernel(const int2* __restrict__ pairs, int64_t n, int32_t* __restrict__ indices, float* __restrict__ data) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 pr = pairs[i];
+        indices[i] = pr.x;
+        data[i] = __int_as_float(pr.y);
+    }
+}
+
 // column range check of raw CSR indices (the packing kernel does it too, but FAST-only flows never pack)
 __global__ void validate_columns_kernel(const int32_t* __restrict__ indices, int64_t nnz, int32_t G, int* __restrict__ err) {
     bool bad = false;
@@ -954,9 +963,11 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
 // FAST mode, step 3: combine a gene's chunk partials in fixed order (cell tiles ascending, chunks ascending inside a
 // tile: slots are numbered tile by tile, tile_slot_ptr[t][g] .. [t][g+1] are gene g's slots in tile t), scale by
 // 1/n_c, write cube.
+// `needed` (or nullptr): genes some kept triple reads; the others were not accumulated (their chunk warps never ran) and
+// their cube rows are left as they are - nothing reads them.
 __global__ void fast_finalize_kernel(const float* __restrict__ partials, const int32_t* __restrict__ tile_slot_ptr /*[n_tiles][G+1]*/,
                                      int32_t n_tiles, const float* __restrict__ inv_n, int32_t G, int32_t L, int32_t PB,
-                                     float* __restrict__ cube, int32_t PP, int32_t p_off) {
+                                     float* __restrict__ cube, int32_t PP, int32_t p_off, const uint8_t* __restrict__ needed = nullptr) {
     // thread per (g, c, p) with p fastest
     const int64_t total = (int64_t)G * L * PB;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -964,6 +975,7 @@ __global__ void fast_finalize_kernel(const float* __restrict__ partials, const i
         const int64_t gc = i / PB;
         const int c = (int)(gc % L);
         const int g = (int)(gc / L);
+        if (needed && !needed[g]) continue;
         float s = 0.0f;
         for (int t = 0; t < n_tiles; ++t) {
             const int s0 = tile_slot_ptr[(int64_t)t * (G + 1) + g], s1 = tile_slot_ptr[(int64_t)t * (G + 1) + g + 1];
@@ -1070,6 +1082,17 @@ __global__ void cube_export_kernel(const float* __restrict__ cube, int32_t G, in
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int p = p0 + r, g = g0 + threadIdx.x;
         if (g < G && p < n_perms_batch) out[((int64_t)p * L + c) * G + g] = tile[threadIdx.x][r];
+    }
+}
+
+// needed[g] = 1 for every gene column some triple reads (ligand or receptor side): FAST mode accumulates only those
+// when no cube is exported
+__global__ void mark_genes_kernel(const int32_t* __restrict__ lig, const int32_t* __restrict__ rec, int64_t T, int32_t G,
+                                  uint8_t* __restrict__ needed) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = lig[i], r = rec[i];
+        if (l >= 0 && l < G) needed[l] = 1;
+        if (r >= 0 && r < G) needed[r] = 1;
     }
 }
 

@@ -1,9 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY - loads the *unmodified* reference modules from /root/reference.
-
-Only usable in the build container (``/root/reference`` does not exist on the GPU box).
-It is used by ``scripts/make_golden.py`` to generate the committed fixtures under
-``tests/golden/`` and by container-only differential tests.  Nothing in the product
-package imports this file.
+"""TEST INFRASTRUCTURE ONLY - loads the *unmodified* reference modules from /root/reference (build container) or from
+the byte-for-byte copy ``oracle/make_ref.py`` leaves under ``oracle/_ref/`` (git-ignored; it travels to the GPU box
+with the snapshot, where ``/root/reference`` does not exist).
+It is used by ``scripts/make_golden.py`` to generate the committed fixtures under ``tests/golden/``, by the
+container-only differential tests, and by ``bench.py`` to TIME the reference's own hot path on the box's host cores
+(``--impl reference`` and ``cpu_baseline``, ``kind: "reference"``).  Nothing in the product package imports this file.
 
 Recipe: the heavy package ``__init__`` files pull in scanpy /
 plotnine / mudata, which are not installed.  We pre-register bare package modules whose
@@ -25,7 +25,22 @@ import types
 
 import pandas as pd
 
-REFERENCE_ROOT = os.environ.get("LIANA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference_root() -> str:
+    """/root/reference in the build container; on the GPU box (where that tree does not exist) the unmodified copy that
+    `oracle/make_ref.py` left under `oracle/_ref/` (git-ignored, shipped with the snapshot)."""
+    env = os.environ.get("LIANA_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "liana", "method", "sc")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
