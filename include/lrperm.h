@@ -217,7 +217,8 @@ int lrperm_trimean_timings(lrperm_engine *h, float *out6);
  *   first_subunit          1 = every complex is represented by its first subunit (return_all_lrs de-duplicates before
  *                          the min-subunit step, :52-57), else the FIRST subunit with the minimal statistic
  *   return_all             1 = rows that fail expr_prop are emitted too (keep = 0)
- * Rows come out in the reference's order (source-major, then target, then interaction).  lrperm_resolve_triples returns
+ * Rows come out in the reference's order (per (source, target) pair with the source varying fastest - target-major,
+ * `np.meshgrid(labels, labels).reshape(2, L*L).T`, _liana_pipe.py:310-312 - then interaction).  lrperm_resolve_triples returns
  * the row count; lrperm_fetch_triples copies the columns to host arrays of that length (all required): interaction index, source / target cluster, resolved ligand / receptor gene column, their
  * statistic (float32 or float64 like `stat`) and props, and the expr_prop flag.
  */

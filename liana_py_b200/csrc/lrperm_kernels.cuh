@@ -1147,14 +1147,15 @@ __global__ void resolve_side_kernel(const int32_t* __restrict__ sub /*[n][m], -1
     pmin[id] = any ? pm : 0.0;
 }
 
-// flat row f = (s * L + t) * n + i (the reference concatenates per (source, target) pair, interactions inside)
+// flat row f = (t * L + s) * n + i: the reference concatenates per (source, target) pair with the SOURCE varying
+// fastest (`np.meshgrid(labels, labels).reshape(2, L*L).T`, liana/method/sc/_liana_pipe.py:310-312), interactions inside
 __global__ void resolve_flags_kernel(const double* __restrict__ pmin_l, const double* __restrict__ pmin_r, const uint8_t* __restrict__ pair_mask,
                                      int32_t n, int32_t L, double expr_prop, int return_all, int32_t* __restrict__ flag) {
     const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (f >= (int64_t)L * L * n) return;
     const int i = (int)(f % n);
     const int64_t st = f / n;
-    const int s = (int)(st / L), t = (int)(st % L);
+    const int t = (int)(st / L), s = (int)(st % L);
     const bool expressed = pmin_l[(int64_t)i * L + s] >= expr_prop && pmin_r[(int64_t)i * L + t] >= expr_prop;
     const bool valid = pair_mask ? pair_mask[s * L + t] != 0 : true;
     flag[f] = (return_all ? valid : (valid && expressed)) ? 1 : 0;
@@ -1172,7 +1173,7 @@ __global__ void resolve_scatter_kernel(const int32_t* __restrict__ flag, const i
     if (f >= (int64_t)L * L * n || !flag[f]) return;
     const int i = (int)(f % n);
     const int64_t st = f / n;
-    const int s = (int)(st / L), t = (int)(st % L);
+    const int t = (int)(st / L), s = (int)(st % L);
     const int64_t a = (int64_t)i * L + s, b = (int64_t)i * L + t;
     const int32_t r = pos[f];
     o_inter[r] = i; o_src[r] = s; o_tgt[r] = t;

@@ -4,8 +4,10 @@ Same call signatures, defaults, result columns, dtypes and sort order as the ref
 `Method.__call__` / `MethodMeta.by_sample` (`liana/method/sc/_Method.py:92-267`).  Engine-only
 options are keyword-only with defaults:
 
-  perm_source  'philox'    (default) permutations generated on device from (seed, perm id)
+  perm_source  'philox'    (default) permutations generated on device from (seed, perm id): p-values statistically
+                           equivalent to liana's, NOT the same numbers for the same seed
                'reference' the reference's own NumPy PCG64 draws -> results identical to liana
+               None        = the environment variable LIANA_B200_PERM_SOURCE, else 'philox'
   order        None (auto: 'exact' with perm_source='reference', 'fast' with 'philox') | 'exact' | 'fast'
   gmean_mode   'product' (exact comparison) | 'literal' (float64 exp/log like scipy.stats.gmean)
   device       CUDA device index;  dist: a DistContext to shard permutations / samples over ranks
@@ -69,8 +71,8 @@ class MethodMeta:
     def by_sample(self, adata, sample_key: str, key_added: str = K.Keys.uns_key, inplace: bool = V.inplace,
                   verbose=V.verbose, **kwargs):
         """Run the method per sample (`_Method.py:92-159`).  Samples are independent; with a
-        DistContext (kwarg `dist`) contiguous blocks of samples are sharded over ranks and one finished
-        frame per rank is gathered - no data-path collective."""
+        DistContext (kwarg `dist`) contiguous blocks of samples are sharded over ranks and the numeric result
+        columns are all-gathered (`_by_sample_sharded`) - no data-path collective."""
         if sample_key not in adata.obs:
             raise ValueError(f"{sample_key} was not found in `adata.obs`.")
         if not isinstance(adata.obs[sample_key].dtype, pd.CategoricalDtype):
@@ -84,28 +86,57 @@ class MethodMeta:
         sample_col = np.asarray(adata.obs[sample_key])
         sizes = [int((sample_col == s).sum()) for s in samples]
         mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
-        results = {}
         sharded = dist is not None and dist.world_size > 1
-        for i in mine:
-            temp = adata[sample_col == samples[i]].copy()
-            results[samples[i]] = self.__call__(temp, inplace=False, verbose=full_verbose, **kwargs)
-        frames = []
-        for s in samples:                      # sample-category order, like the reference's concat
-            if s in results:
-                df = results[s]
-                df.insert(0, sample_key, s)
+        if not sharded:
+            frames = []
+            for i in mine:                         # sample-category order, like the reference's concat
+                temp = adata[sample_col == samples[i]].copy()
+                df = self.__call__(temp, inplace=False, verbose=full_verbose, **kwargs)
+                df.insert(0, sample_key, samples[i])
                 frames.append(df)
-        if sharded:
-            # every rank finishes its own block of samples (names, sample column, local concat: that is where the
-            # time goes - pandas over millions of rows) and ONE frame per rank travels; the blocks are contiguous in
-            # sample order (DistContext.sample_shard), so the rank frames concatenate without re-sorting
-            local = pd.concat(frames, ignore_index=True) if frames else None
-            frames = [p for p in dist.all_gather_objects(local) if p is not None] if gather else ([local] if local is not None else [])
-        # a fresh RangeIndex like the reference's `concat(...).reset_index()` (`_Method.py:154-155`)
-        liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0].reset_index(drop=True)
+            # a fresh RangeIndex like the reference's `concat(...).reset_index()` (`_Method.py:154-155`)
+            liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0].reset_index(drop=True)
+        else:
+            liana_res = self._by_sample_sharded(adata, sample_key, samples, sample_col, list(mine), dist, gather,
+                                                full_verbose, kwargs)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
+
+    def _by_sample_sharded(self, adata, sample_key, samples, sample_col, mine, dist, gather, verbose, kwargs):
+        """Samples sharded over ranks (contiguous blocks of the sample order, `DistContext.sample_shard`).  Every rank
+        scores its own samples and keeps the result as NUMBERS: the name columns are codes into tables that are the
+        same on every rank (the resource's genes / complexes, the clusters of the whole object, the sample list).  The
+        numeric columns are concatenated over ranks with one all-gather per column (NVLink), and only then - once, on
+        the consumer - the string columns are built.  No DataFrame is pickled."""
+        from ..resource import handle_resource
+        if "groupby" not in kwargs:
+            raise TypeError("by_sample: pass `groupby` as a keyword argument")
+        lab = adata.obs[kwargs["groupby"]]
+        cats = lab.cat.categories if isinstance(lab.dtype, pd.CategoricalDtype) else pd.Categorical(lab).categories
+        res = handle_resource(interactions=kwargs.get("interactions"), resource=kwargs.get("resource"),
+                              resource_name=kwargs.get("resource_name", V.resource_name), verbose=False)
+        g_tables = PL.global_name_tables(res, cats)
+        parts, columns = [], None
+        for i in mine:
+            temp = adata[sample_col == samples[i]].copy()
+            frame, l_tables = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **kwargs)
+            cols = PL.to_global_codes(frame, l_tables, g_tables)
+            cols = {sample_key: np.full(len(frame), i, dtype=np.int32), **cols}
+            parts.append(cols)
+            columns = list(cols)
+        # column names / dtypes of a rank without samples come from the others (tiny object exchange)
+        spec = [(c, parts[0][c].dtype.str) for c in columns] if parts else None
+        if gather:                                  # a collective: every rank takes part
+            spec = next((s for s in dist.all_gather_objects(spec) if s is not None), None)
+        if spec is None:                            # no sample on this rank (gather=False) or anywhere
+            return pd.DataFrame({sample_key: pd.Series([], dtype=object)})
+        local = {c: (np.concatenate([p[c] for p in parts]) if parts else np.zeros(0, dtype=np.dtype(dt))) for c, dt in spec}
+        if gather:
+            local = dist.all_gather_rows(local)
+        g_tables = dict(g_tables)
+        g_tables[sample_key] = pd.Index(samples)
+        return PL.frame_from_codes(local, g_tables)
 
 
 class Method(MethodMeta):
@@ -125,7 +156,7 @@ class Method(MethodMeta):
                  n_perms: Optional[int] = V.n_perms, seed: int = V.seed, n_jobs: int = 1,
                  resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
-                 *, perm_source: str = "philox", order: Optional[str] = None, gmean_mode: str = "product",
+                 *, perm_source: Optional[str] = None, order: Optional[str] = None, gmean_mode: str = "product",
                  device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
         # supplementary statistic columns ride along with the method's own (`_liana_pipe.py:111-114`)
         add_cols = PL.method_columns(self.add_cols, supp_columns)

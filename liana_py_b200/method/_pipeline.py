@@ -47,16 +47,52 @@ def observed_gmean(ligand_means: np.ndarray, receptor_means: np.ndarray) -> np.n
 def reference_perm_indices(n_cells: int, n_perms: int, seed: int) -> np.ndarray:
     """The reference's own draws: ONE default_rng(seed), `rng.permutation(arange(N))` P times in
     order (`_get_mean_perms.py:69-72,79`).  Used when perm_source='reference' (validation mode)."""
+    chunks = [c for _, c in reference_perm_chunks(n_cells, n_perms, seed, 0, n_perms, max_bytes=1 << 62)]
+    return chunks[0] if chunks else np.empty((0, n_cells), dtype=np.int32)
+
+
+def reference_perm_chunks(n_cells: int, n_perms: int, seed: int, lo: int, hi: int, max_bytes: int = 256 << 20):
+    """Draws [lo, hi) of the reference's permutation stream as (first draw, index array) chunks of at most `max_bytes`:
+    the P x N index array of a large run never exists at once (500k cells x 1000 permutations would be 2 GB).  The
+    stream is sequential (one PCG64 generator), so the draws before `lo` are generated and dropped."""
     rng = np.random.default_rng(seed=seed)
     idx = np.arange(n_cells)
-    out = np.empty((n_perms, n_cells), dtype=np.int32 if n_cells < 2 ** 31 else np.int64)
-    for p in range(n_perms):
-        out[p] = rng.permutation(idx)
-    return out
+    dtype = np.int32 if n_cells < 2 ** 31 else np.int64
+    for _ in range(lo):
+        rng.permutation(idx)
+    per = max(1, int(max_bytes // max(n_cells * np.dtype(dtype).itemsize, 1)))
+    for p0 in range(lo, hi, per):
+        p1 = min(hi, p0 + per)
+        out = np.empty((p1 - p0, n_cells), dtype=dtype)
+        for p in range(p1 - p0):
+            out[p] = rng.permutation(idx)
+        yield p0, out
+
+
+def default_perm_source() -> str:
+    """Where the label shuffles come from when a call does not say: 'philox' (device, the production default) unless the
+    environment variable LIANA_B200_PERM_SOURCE says 'reference' (the reference's own NumPy draws -> p-values identical
+    to liana's for the same seed; validation runs)."""
+    import os
+    v = os.environ.get("LIANA_B200_PERM_SOURCE", "philox").strip().lower()
+    if v not in ("philox", "reference"):
+        raise ValueError("LIANA_B200_PERM_SOURCE must be 'philox' or 'reference'")
+    return v
 
 
 _TABLE_CACHE = {}
 _EXPLODED_CACHE = {}
+
+
+def exploded(res: pd.DataFrame):
+    """The resource split into subunits (memoised on its content, see `_cached_tables`)."""
+    rkey = hash(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).values.tobytes())
+    ex = _EXPLODED_CACHE.get(rkey)
+    if ex is None:
+        if len(_EXPLODED_CACHE) >= 8:
+            _EXPLODED_CACHE.pop(next(iter(_EXPLODED_CACHE)))
+        ex = _EXPLODED_CACHE[rkey] = _tables.explode_resource(res)
+    return rkey, ex
 
 
 def _cached_tables(res: pd.DataFrame, var_names: np.ndarray):
@@ -64,12 +100,7 @@ def _cached_tables(res: pd.DataFrame, var_names: np.ndarray):
     4.6 k interactions, ~50 ms) is memoised on the resource's content; the tables for one gene set (array operations,
     < 1 ms) on (resource, gene names) - every sample of `by_sample` has its own set of non-empty genes."""
     # row hashes as bytes: sensitive to the ORDER of the interactions too (a plain sum would not be)
-    rkey = hash(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).values.tobytes())
-    ex = _EXPLODED_CACHE.get(rkey)
-    if ex is None:
-        if len(_EXPLODED_CACHE) >= 8:
-            _EXPLODED_CACHE.pop(next(iter(_EXPLODED_CACHE)))
-        ex = _EXPLODED_CACHE[rkey] = _tables.explode_resource(res)
+    rkey, ex = exploded(res)
     key = (rkey, len(var_names), hash(np.asarray(var_names, dtype=str).tobytes()))
     hit = _TABLE_CACHE.get(key)
     if hit is None:
@@ -276,6 +307,44 @@ def name_tables(state: PipelineState) -> dict:
             K.RECEPTOR_COMPLEX: tb.receptor_complex, K.SOURCE: cats, K.TARGET: cats}
 
 
+def global_name_tables(res: pd.DataFrame, categories) -> dict:
+    """Name tables that do not depend on the sample / rank: every gene and complex the RESOURCE names, every cluster
+    of the whole object.  `by_sample` over ranks exchanges frames whose name columns hold codes into these tables
+    (integers travel over NCCL; the strings are built once, on the consumer)."""
+    _, ex = exploded(res)
+    genes = pd.Index(ex.entities)
+    return {K.LIGAND: genes, K.RECEPTOR: genes, K.LIGAND_COMPLEX: pd.Index(pd.unique(ex.ligand_complex)),
+            K.RECEPTOR_COMPLEX: pd.Index(pd.unique(ex.receptor_complex)), K.SOURCE: pd.Index(categories),
+            K.TARGET: pd.Index(categories)}
+
+
+def to_global_codes(frame: pd.DataFrame, local_tables: dict, global_tables: dict) -> dict:
+    """Columns of a code frame as 1-D arrays, the name columns re-coded from the sample's own tables (`name_tables`)
+    into `global_name_tables`."""
+    out = {}
+    for col in frame.columns:
+        v = frame[col].values
+        if col in local_tables:
+            remap = global_tables[col].get_indexer(pd.Index(np.asarray(local_tables[col])))
+            if (remap < 0).any():
+                raise RuntimeError(f"`{col}`: a name of the sample is missing from the global table (internal error)")
+            v = remap.astype(np.int32)[v]
+        out[col] = np.ascontiguousarray(v)
+    return out
+
+
+def frame_from_codes(columns: dict, global_tables: dict) -> pd.DataFrame:
+    """The result frame from gathered columns: code columns -> names (one vectorised take each, in the thread pool)."""
+    cols = list(columns)
+
+    def build(c):
+        v = columns[c]
+        return _take_names(global_tables[c], v) if c in global_tables else v
+
+    done = list(_frame_pool().map(build, cols))
+    return pd.DataFrame(dict(zip(cols, done)), copy=False)
+
+
 def materialise_names(state_or_tables, frame: pd.DataFrame) -> pd.DataFrame:
     """Replace the code columns of `base_frame` by the gene / complex / cluster names (in place, same order)."""
     lookup = state_or_tables if isinstance(state_or_tables, dict) else name_tables(state_or_tables)
@@ -395,21 +464,25 @@ def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, 
     rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
     lo = (n_perms * rank) // world
     hi = (n_perms * (rank + 1)) // world
-    if perm_source == "reference":
-        perm_idx = reference_perm_indices(state.prep.n_cells, n_perms, seed)[lo:hi]
-        if order is None:
-            order = "exact"
-    elif perm_source == "philox":
-        perm_idx = None
-        if order is None:
-            order = "fast"
-    else:
+    perm_source = default_perm_source() if perm_source is None else perm_source
+    if perm_source not in ("philox", "reference"):
         raise ValueError("perm_source must be 'philox' or 'reference'")
+    if order is None:
+        order = "exact" if perm_source == "reference" else "fast"
     if order not in ("exact", "fast"):
         raise ValueError("order must be 'exact', 'fast' or None")
-    out = eng.run(hi - lo, seed=seed, perm_offset=lo, perm_idx=perm_idx,
-                  order=E.ORDER_EXACT if order == "exact" else E.ORDER_FAST, scores=scores,
-                  gmean_mode=E.GMEAN_LITERAL if gmean_mode == "literal" else E.GMEAN_PRODUCT)
+    kw = dict(order=E.ORDER_EXACT if order == "exact" else E.ORDER_FAST, scores=scores,
+              gmean_mode=E.GMEAN_LITERAL if gmean_mode == "literal" else E.GMEAN_PRODUCT)
+    if perm_source == "philox":
+        out = eng.run(hi - lo, seed=seed, perm_offset=lo, **kw)
+    else:
+        # the reference's draws, a bounded chunk of the index array at a time; integer counts add up
+        out = None
+        for _, idx in reference_perm_chunks(state.prep.n_cells, n_perms, seed, lo, hi):
+            part = eng.run(len(idx), seed=seed, perm_idx=idx, **kw)
+            out = part if out is None else {k: out[k] + part[k] for k in out}
+        if out is None:
+            out = eng.run(0, seed=seed, **kw)
     if dist is not None and world > 1:
         out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
     return out
@@ -434,13 +507,18 @@ def permutation_counts_trimean(state: PipelineState, tri, obs_prob, n_perms, see
     rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
     lo = (n_perms * rank) // world
     hi = (n_perms * (rank + 1)) // world
-    if perm_source == "reference":
-        perm_idx = reference_perm_indices(state.prep.n_cells, n_perms, seed)[lo:hi]
-    elif perm_source == "philox":
-        perm_idx = None
+    perm_source = default_perm_source() if perm_source is None else perm_source
+    if perm_source == "philox":
+        out = eng.run_trimean(hi - lo, state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_offset=lo)
+    elif perm_source == "reference":
+        out = None
+        for _, idx in reference_perm_chunks(state.prep.n_cells, n_perms, seed, lo, hi):
+            part = eng.run_trimean(len(idx), state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_idx=idx)
+            out = part if out is None else {k: out[k] + part[k] for k in out}
+        if out is None:
+            out = eng.run_trimean(0, state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed)
     else:
         raise ValueError("perm_source must be 'philox' or 'reference'")
-    out = eng.run_trimean(hi - lo, state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_offset=lo, perm_idx=perm_idx)
     if dist is not None and world > 1:
         out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
     return out

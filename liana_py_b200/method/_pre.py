@@ -174,8 +174,9 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     lab = obs[groupby]
     if not isinstance(lab.dtype, pd.CategoricalDtype):
         _logg(f"Converting `{groupby}` to categorical!", level="warn", verbose=verbose)
+        # a local Series only: the reference converts inside the copy `prep_check_adata` made of `obs`
+        # (`_pre.py:112-119, 269-271`), the caller's column keeps its dtype
         lab = lab.astype("category")
-        obs[groupby] = lab       # the reference converts in place too (`_pre.py:269-271`)
     # on the category CODES (one bincount) instead of pandas categorical ops over every cell
     codes = np.asarray(lab.cat.codes, dtype=np.int64)
     cats = lab.cat.categories

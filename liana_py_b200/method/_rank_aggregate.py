@@ -52,7 +52,7 @@ class AggregateClass(MethodMeta):
                  n_perms: Optional[int] = V.n_perms, seed: int = V.seed, n_jobs: int = 1,
                  resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
-                 *, perm_source: str = "philox", order: Optional[str] = None, gmean_mode: str = "product",
+                 *, perm_source: Optional[str] = None, order: Optional[str] = None, gmean_mode: str = "product",
                  device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
         if n_perms is None:
             consensus_opts = "Magnitude"                       # `_liana_pipe.py:108-109`

@@ -146,19 +146,21 @@ def resolve_triples(tables: ResourceTables, means: np.ndarray, props: np.ndarray
     rg, rm, rp, rpmin = _resolve_side(tables.rec_sub, means, props, first_subunit=return_all_lrs)
     n = lg.shape[0]
     # min(all subunit props) >= expr_prop  <=>  both sides pass: two [n, L] masks instead of an [n, L, L] float cube;
-    # the row order (source-major, then target, then interaction: the reference concatenates per pair) is the
-    # C order of an [L, L, n] mask, so one flatnonzero gives the rows already in place
+    # the row order (per (source, target) pair with the source varying fastest, then interaction: the reference
+    # concatenates per pair of `np.meshgrid(labels, labels).reshape(2, L*L).T`, `_liana_pipe.py:310-312`) is the
+    # C order of a [target, source, interaction] mask, so one flatnonzero gives the rows already in place
     l_ok = np.ascontiguousarray((lpmin >= expr_prop).T)                   # [s, i]
     r_ok = np.ascontiguousarray((rpmin >= expr_prop).T)                   # [t, i]
-    expressed = l_ok[:, None, :] & r_ok[None, :, :]                       # [s, t, i]
+    expressed = r_ok[:, None, :] & l_ok[None, :, :]                       # [t, s, i]
+    mask_ts = None if pair_mask is None else np.ascontiguousarray(np.asarray(pair_mask, dtype=bool).T)   # [t, s]
     if return_all_lrs:
-        sel = np.ones((L, L, n), dtype=bool) if pair_mask is None else np.broadcast_to(pair_mask[:, :, None], (L, L, n))
+        sel = np.ones((L, L, n), dtype=bool) if mask_ts is None else np.broadcast_to(mask_ts[:, :, None], (L, L, n))
     else:
-        sel = expressed if pair_mask is None else expressed & pair_mask[:, :, None]
+        sel = expressed if mask_ts is None else expressed & mask_ts[:, :, None]
     flat = np.flatnonzero(sel)
     keep = expressed.ravel()[flat] if return_all_lrs else np.ones(flat.shape[0], dtype=bool)
     st, i_idx = np.divmod(flat, n)
-    s_idx, t_idx = np.divmod(st, L)
+    t_idx, s_idx = np.divmod(st, L)
     li, ri = i_idx * L + s_idx, i_idx * L + t_idx                         # flat positions in the [n, L] side tables
 
     def side(a, pos, dtype):

@@ -377,3 +377,26 @@ def test_supp_columns_of_every_method_agree(name, supp):
             np.testing.assert_allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=1e-4, atol=1e-5, err_msg=c)
         else:
             assert (a[c].astype(str).values == b[c].astype(str).values).all(), c
+
+
+@pytest.mark.parametrize("seed", [3, 5, 11])
+def test_unsorted_row_order_is_the_references(seed):
+    """Per-method frames of a consensus returned as they are (`consensus_opts=False`, `_liana_pipe.py:220-221`): the rows
+    come out in the reference's own order - per (source, target) pair of `np.meshgrid(labels, labels).reshape(2, L*L).T`
+    (`:310-312`, the SOURCE varies fastest), interactions inside - not merely the same set of rows."""
+    ref = ref_shim.load_reference()
+    adata, kw = _case(seed)
+    kw.pop("groupby_pairs", None)
+    agg_ref = ref.rank_aggregate_mod.AggregateClass(ref.rank_aggregate_mod._rank_aggregate_meta,
+                                                    methods=[ref.cellphonedb, ref.geometric_mean])
+    want = agg_ref(adata.copy(), groupby="cluster", use_raw=False, consensus_opts=False, inplace=False, **kw)
+    agg = li.mt.AggregateClass(li.mt.aggregate_meta, methods=[li.mt.cellphonedb, li.mt.geometric_mean])
+    got = agg(adata.copy(), groupby="cluster", use_raw=False, consensus_opts=False, inplace=False, perm_source="reference", **kw)
+    assert list(got) == list(want)
+    for name in got:
+        a, b = got[name].reset_index(drop=True), want[name].reset_index(drop=True)
+        assert len(a) == len(b) > 0
+        assert (a[KEY].values == b[KEY].values).all()
+        for col in b.columns:
+            if col not in KEY:
+                np.testing.assert_array_equal(a[col].values, b[col].values)

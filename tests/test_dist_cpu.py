@@ -112,6 +112,51 @@ def test_two_rank_gloo(tmp_path):
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
 
+def _worker_by_sample(rank, world, port, out_dir):
+    """3 ranks, 2 samples: one rank owns no sample.  The frame gathered from numeric columns must equal the frame one
+    process builds (same rows, order, column dtypes and values)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pandas as pd
+        import liana_py_b200 as li
+        from liana_py_b200.method import _pipeline as PL
+        from _oracle_engine import OracleEngine
+        from variants import sample_inputs
+        PL._ENGINES[0] = OracleEngine()
+        ctx = DistContext.from_torch()
+        for method, extra in ((li.mt.cellphonedb, {}), (li.mt.rank_aggregate, {}), (li.mt.cellphonedb, {"return_all_lrs": True})):
+            kws = dict(sample_key="sample", groupby="cluster", n_perms=8, seed=7, expr_prop=0.1, inplace=False,
+                       perm_source="reference", use_raw=False, **extra)
+            single = method.by_sample(sample_inputs(), **kws)
+            full = method.by_sample(sample_inputs(), dist=ctx, **kws)
+            pd.testing.assert_frame_equal(full, single)
+            own = method.by_sample(sample_inputs(), dist=ctx, gather=False, **kws)
+            n_own = ctx.all_gather_objects(len(own))
+            assert sum(n_own) == len(single) and min(n_own) == 0          # a rank without samples returns an empty frame
+            if len(own):
+                ref = single[single["sample"].isin(set(own["sample"]))].reset_index(drop=True)
+                pd.testing.assert_frame_equal(own, ref)
+        # all_gather_rows: ragged, empty and bool columns
+        cols = {"a": np.arange(rank * 3, dtype=np.int32), "b": np.linspace(0, 1, rank * 3), "c": np.arange(rank * 3) % 2 == 0}
+        got = ctx.all_gather_rows(cols)
+        want_a = np.concatenate([np.arange(r * 3, dtype=np.int32) for r in range(world)])
+        assert np.array_equal(got["a"], want_a) and got["a"].dtype == np.int32
+        assert got["b"].dtype == np.float64 and got["c"].dtype == np.bool_ and len(got["c"]) == len(want_a)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_three_rank_by_sample_numeric_gather(tmp_path):
+    world = 3
+    here = os.path.dirname(os.path.abspath(__file__))
+    os.environ["PYTHONPATH"] = here + os.pathsep + os.path.dirname(here) + os.pathsep + os.environ.get("PYTHONPATH", "")
+    mp.spawn(_worker_by_sample, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
 def test_perm_ranges_partition():
     for P in (1, 7, 1000, 1001):
         for W in (1, 2, 3, 8):
