@@ -168,9 +168,11 @@ struct lrperm_engine {
     DevBuf err_flag_m;                    // validation flags of the pending matrix
     // pageable uploads: two pinned staging pieces filled by a few host threads while the other one is in flight
     ParallelCopier* copier = nullptr;
-    void* pin[2] = {nullptr, nullptr};
-    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
-    static constexpr size_t kPinPiece = 16u << 20;
+    static constexpr int kMaxPin = 4;
+    void* pin[kMaxPin] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pin_ev[kMaxPin] = {nullptr, nullptr, nullptr, nullptr};
+    int n_pin = 2;                        // staging pieces in rotation  (LRPERM_PIN_PIECES, 2..4)
+    size_t pin_piece = 16u << 20;         // bytes per piece             (LRPERM_PIN_PIECE_MB)
     int32_t overlap = 1;
     std::string err;
     int sm_count = 148;
@@ -319,26 +321,32 @@ bool is_pinned_host(const void* p) {
 int upload_pageable(lrperm_engine* h, void* dst, const void* src, size_t bytes) {
     if (!h->copier) {
         const unsigned hw = std::thread::hardware_concurrency();
-        h->copier = new (std::nothrow) ParallelCopier((int)std::max(2u, std::min(6u, hw ? hw / 2 : 2u)));
+        // host threads that fill the staging pieces: measured on the 16-core B200 host (scripts/upload_probe.py)
+        unsigned n_threads = std::max(2u, std::min(8u, hw ? hw / 2 : 2u));
+        if (const char* e = std::getenv("LRPERM_COPY_THREADS")) n_threads = (unsigned)std::max(1, std::min(64, atoi(e)));
+        if (const char* e = std::getenv("LRPERM_PIN_PIECES")) h->n_pin = std::max(2, std::min((int)lrperm_engine::kMaxPin, atoi(e)));
+        if (const char* e = std::getenv("LRPERM_PIN_PIECE_MB")) h->pin_piece = (size_t)std::max(1, std::min(1024, atoi(e))) << 20;
+        h->copier = new (std::nothrow) ParallelCopier((int)n_threads);
         if (!h->copier) return h->fail(LRPERM_ERR_OOM, "host allocation failed");
-        for (int i = 0; i < 2; ++i) {
-            CK(cudaHostAlloc(&h->pin[i], lrperm_engine::kPinPiece, cudaHostAllocDefault));
+        for (int i = 0; i < h->n_pin; ++i) {
+            CK(cudaHostAlloc(&h->pin[i], h->pin_piece, cudaHostAllocDefault));
             CK(cudaEventCreateWithFlags(&h->pin_ev[i], cudaEventDisableTiming));
         }
     }
     const unsigned char* s = static_cast<const unsigned char*>(src);
     unsigned char* d = static_cast<unsigned char*>(dst);
+    const int np = h->n_pin;
     int k = 0;
-    for (size_t o = 0; o < bytes; o += lrperm_engine::kPinPiece, ++k) {
-        const size_t n = std::min(lrperm_engine::kPinPiece, bytes - o);
-        const int b = k & 1;
-        if (k >= 2) CK(cudaEventSynchronize(h->pin_ev[b]));      // the DMA that read this piece two rounds ago is done
+    for (size_t o = 0; o < bytes; o += h->pin_piece, ++k) {
+        const size_t n = std::min(h->pin_piece, bytes - o);
+        const int b = k % np;
+        if (k >= np) CK(cudaEventSynchronize(h->pin_ev[b]));     // the DMA that read this piece one rotation ago is done
         h->copier->copy(h->pin[b], s + o, n);
         CK(cudaMemcpyAsync(d + o, h->pin[b], n, cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(h->pin_ev[b], h->stream));
     }
     // the staging pieces are reused by the next upload: leave none in flight
-    for (int b = 0; b < 2 && b < k; ++b) CK(cudaEventSynchronize(h->pin_ev[b]));
+    for (int b = 0; b < np && b < k; ++b) CK(cudaEventSynchronize(h->pin_ev[b]));
     return LRPERM_OK;
 }
 
@@ -1586,7 +1594,7 @@ void lrperm_destroy(lrperm_engine* h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_matrix) cudaEventDestroy(h->ev_matrix);
     delete h->copier;
-    for (int i = 0; i < 2; ++i) { if (h->pin[i]) cudaFreeHost(h->pin[i]); if (h->pin_ev[i]) cudaEventDestroy(h->pin_ev[i]); }
+    for (int i = 0; i < lrperm_engine::kMaxPin; ++i) { if (h->pin[i]) cudaFreeHost(h->pin[i]); if (h->pin_ev[i]) cudaEventDestroy(h->pin_ev[i]); }
     delete h;
 }
 

@@ -99,6 +99,68 @@ class DistContext:
             torch.cuda.current_stream(dev).synchronize()
         return d_indptr, outs[0], outs[1]
 
+    def all_reduce_np(self, arr: np.ndarray, op: str = "sum") -> np.ndarray:
+        """Element-wise sum / max of a small host array (float64 or int64) over ranks."""
+        if self.world_size == 1:
+            return arr
+        import torch
+        import torch.distributed as dist
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a.copy()).to(self.device if self.device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
+        return t.cpu().numpy().reshape(a.shape)
+
+    def row_block(self, n_rows: int, indptr=None):
+        """Contiguous block of rows [r0, r1) of a replicated host matrix this rank stages: cut where the running number
+        of stored entries crosses k/world of the total (CSR `indptr` given), else by rows."""
+        w, r = self.world_size, self.rank
+        if indptr is None or n_rows == 0:
+            return (n_rows * r) // w, (n_rows * (r + 1)) // w
+        total = int(indptr[n_rows])
+        cuts = [int(np.searchsorted(indptr, total * k // w, side="left")) for k in range(w + 1)]
+        cuts[0], cuts[-1] = 0, n_rows
+        cuts = [min(max(c, 0), n_rows) for c in cuts]
+        for k in range(1, w + 1):
+            cuts[k] = max(cuts[k], cuts[k - 1])
+        return cuts[r], cuts[r + 1]
+
+    def all_gather_csr(self, engine):
+        """Every rank's engine holds the committed matrix of ITS block of cells (same genes): rebuild the whole
+        committed matrix on every rank - blocks in rank order - from one padded all-gather per array over NVLink.
+        Returns torch tensors (indptr int32 [N+1], indices int32, data float32) on this rank's device, to hand to
+        `Engine.set_matrix_csr`."""
+        import torch
+        import torch.distributed as dist
+        dev = self.device if self.device is not None else torch.device("cpu")
+        ip, ix, dt = engine.export_matrix_csr(dev)
+        n_local, nnz_local = int(ip.numel()) - 1, int(ix.numel())
+        meta = self.all_reduce_np(np.array([[n_local, nnz_local] if r == self.rank else [0, 0] for r in range(self.world_size)],
+                                           dtype=np.int64))
+        rows, nnzs = [int(v) for v in meta[:, 0]], [int(v) for v in meta[:, 1]]
+
+        def gather(local, sizes):
+            n_max = max(max(sizes), 1)
+            pad = torch.zeros(n_max, dtype=local.dtype, device=dev)
+            pad[:local.numel()].copy_(local)
+            if dist.get_backend(self.group) == "nccl":
+                full = torch.empty(n_max * self.world_size, dtype=local.dtype, device=dev)
+                dist.all_gather_into_tensor(full, pad, group=self.group)
+                parts = [full[r * n_max:r * n_max + sizes[r]] for r in range(self.world_size)]
+            else:
+                bufs = [torch.empty_like(pad) for _ in range(self.world_size)]
+                dist.all_gather(bufs, pad, group=self.group)
+                parts = [bufs[r][:sizes[r]] for r in range(self.world_size)]
+            return parts
+
+        ix_all = torch.cat(gather(ix, nnzs))
+        dt_all = torch.cat(gather(dt, nnzs))
+        counts = torch.cat(gather(torch.diff(ip.to(torch.int64)).to(torch.int32) if n_local else ip[:0], rows))
+        indptr = torch.zeros(sum(rows) + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(counts.to(torch.int64), 0)
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()     # the engine works on its own stream
+        return indptr.to(torch.int32), ix_all, dt_all
+
     def all_gather_rows(self, columns: dict) -> dict:
         """Concatenate, in rank order, the per-rank NumPy columns of a table (same column names and dtypes on every
         rank, any number of rows per rank - also zero): one size exchange, then one padded all-gather per column

@@ -10,7 +10,11 @@ options are keyword-only with defaults:
                None        = the environment variable LIANA_B200_PERM_SOURCE, else 'philox'
   order        None (auto: 'exact' with perm_source='reference', 'fast' with 'philox') | 'exact' | 'fast'
   gmean_mode   'product' (exact comparison) | 'literal' (float64 exp/log like scipy.stats.gmean)
-  device       CUDA device index;  dist: a DistContext to shard permutations / samples over ranks
+  device       CUDA device index;  dist: a DistContext to shard permutations / samples over ranks (torchrun,
+               one process per GPU)
+  devices      list of CUDA device indices: ONE call, one process, several GPUs - the input is prepared on
+               devices[0], the committed matrix is copied to the others over NVLink, the permutations (or the
+               samples of `by_sample`) are split over them by threads; results are identical to one GPU's
 `n_jobs` is accepted and ignored (parallelism is on the GPU).
 """
 from __future__ import annotations
@@ -83,11 +87,33 @@ class MethodMeta:
         # engine-only option: gather=False leaves every rank with the frame of ITS block of samples (to be written out
         # per rank); assembling one pandas frame of all samples on every rank costs far more than computing them
         gather: bool = kwargs.pop("gather", True)
+        devices = kwargs.pop("devices", None)
         sample_col = np.asarray(adata.obs[sample_key])
         sizes = [int((sample_col == s).sum()) for s in samples]
         mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
         sharded = dist is not None and dist.world_size > 1
-        if not sharded:
+        if devices is not None and len(devices) > 1:
+            # one process, several GPUs: contiguous blocks of samples per device, one thread each (the C ABI calls -
+            # uploads, statistics, permutations - release the GIL; the pandas parts take turns)
+            if sharded:
+                raise ValueError("pass either `dist` (one process per GPU) or `devices` (one process, several GPUs)")
+            from concurrent.futures import ThreadPoolExecutor
+            kwargs.pop("device", None)
+            blocks = [DistContext(k, len(devices)).sample_shard(sizes) for k in range(len(devices))]
+
+            def work(k):
+                out = []
+                for i in blocks[k]:
+                    temp = adata[sample_col == samples[i]].copy()
+                    df = self.__call__(temp, inplace=False, verbose=full_verbose, device=int(devices[k]), **kwargs)
+                    df.insert(0, sample_key, samples[i])
+                    out.append(df)
+                return out
+
+            with ThreadPoolExecutor(len(devices)) as pool:
+                frames = [df for part in pool.map(work, range(len(devices))) for df in part]
+            liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0].reset_index(drop=True)
+        elif not sharded:
             frames = []
             for i in mine:                         # sample-category order, like the reference's concat
                 temp = adata[sample_col == samples[i]].copy()
@@ -157,15 +183,17 @@ class Method(MethodMeta):
                  resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
                  *, perm_source: Optional[str] = None, order: Optional[str] = None, gmean_mode: str = "product",
-                 device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
+                 device: int = 0, dist: Optional[DistContext] = None, devices: Optional[list] = None,
+                 _names: bool = True):
+        device, devices = PL.resolve_devices(device, devices)
         # supplementary statistic columns ride along with the method's own (`_liana_pipe.py:111-114`)
         add_cols = PL.method_columns(self.add_cols, supp_columns)
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
                            use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in add_cols,
                            want_cluster_stats=("ligand_cdf" in add_cols) or ("receptor_cdf" in add_cols),
-                           mdata_kwargs=mdata_kwargs)
+                           mdata_kwargs=mdata_kwargs, dist=dist)
         liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
-                               perm_source, order, gmean_mode, dist, add_cols=add_cols)
+                               perm_source, order, gmean_mode, dist, add_cols=add_cols, devices=devices)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
         if not _names:                          # by_sample across ranks: (code frame, name tables), see by_sample
@@ -178,7 +206,7 @@ class Method(MethodMeta):
 
 def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_lrs, perm_source, order,
                gmean_mode, dist, aggregate_flag=False, null_cache=None, permuting_methods=None,
-               add_cols=None) -> pd.DataFrame:
+               add_cols=None, devices=None) -> pd.DataFrame:
     """`_run_method` (`_liana_pipe.py:363-452`) for one method on a prepared PipelineState.
 
     In a consensus (`null_cache` given) every permutation method named in `permuting_methods` is counted
@@ -199,7 +227,7 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
             null = null_cache[key]
         elif method.engine_score == "cellchat":
             obs = PL.observed_cellchat(sub.ligand_means, sub.receptor_means, cellchat._kh)
-            out = PL.permutation_counts_trimean(state, sub, obs, n_perms, seed, perm_source, cellchat._kh, dist)
+            out = PL.permutation_counts_trimean(state, sub, obs, n_perms, seed, perm_source, cellchat._kh, dist, devices)
             null = NullCounts(out["cellchat"], n_perms)
             if null_cache is not None:
                 null_cache[key] = null
@@ -209,7 +237,7 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
                 wanted |= {m.engine_score for m in permuting_methods if m.permute and m.engine_score in ("cpdb", "gmean")}
             oc = PL.observed_cpdb(sub.ligand_means, sub.receptor_means) if "cpdb" in wanted else None
             og = PL.observed_gmean(sub.ligand_means, sub.receptor_means) if "gmean" in wanted else None
-            out = PL.permutation_counts(state, sub, oc, og, n_perms, seed, perm_source, order, gmean_mode, dist)
+            out = PL.permutation_counts(state, sub, oc, og, n_perms, seed, perm_source, order, gmean_mode, dist, devices)
             if null_cache is not None:
                 for name in ("cpdb", "gmean"):
                     if name in out:

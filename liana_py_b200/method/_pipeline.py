@@ -29,6 +29,16 @@ def get_engine(device: int = 0) -> E.Engine:
     return eng
 
 
+def resolve_devices(device, devices):
+    """(`device` the input is prepared on, list of devices the null is split over or None)."""
+    if devices is None:
+        return int(device), None
+    devices = [int(d) for d in devices]
+    if not devices:
+        raise ValueError("devices must name at least one CUDA device")
+    return devices[0], (devices if len(devices) > 1 else None)
+
+
 def observed_cpdb(ligand_means: np.ndarray, receptor_means: np.ndarray) -> np.ndarray:
     """float32 mean of the pair, zero where either side is zero (`_cellphonedb.py:25-27`)."""
     zero = (ligand_means == 0) | (receptor_means == 0)
@@ -125,9 +135,43 @@ class PipelineState:
         # that takes part in the shuffles, in the whole-matrix statistics and in the "rest" of the log fold changes
         self.sizes_all = sizes if sizes_all is None else sizes_all
         self.engine_tables = None
+        self.engine_labels = None            # (labels int32 [N], n_clusters) as set on the engine (`prepare`)
         self.base = float(base)
         self._moments = None
         self._cache = {}
+        self._replicas = {}
+
+    def replicas(self, devices) -> list:
+        """Engines of `devices` (CUDA indices) that hold this state's matrix and labels; the first entry is the state's
+        own engine.  The committed matrix is exported once on its device and copied to the others device to device
+        (peer copies over NVLink - nothing crosses PCIe again), each device then builds its own tables; all of that
+        runs in one thread per device."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        devices = [int(d) for d in devices]
+        if devices[0] != self.engine.device:
+            raise ValueError("devices[0] must be the device the input was prepared on")
+        if len(set(devices)) != len(devices):
+            raise ValueError("devices must be distinct")
+        missing = [d for d in devices[1:] if d not in self._replicas]
+        if missing:
+            n, g, _ = self.engine.matrix_info()
+            src = self.engine.export_matrix_csr(torch.device("cuda", devices[0]))
+            labels, L = self.engine_labels
+
+            def make(d):
+                dev = torch.device("cuda", d)
+                with torch.cuda.device(dev):
+                    ip, ix, dt = (t.to(dev, non_blocking=False) for t in src)
+                    eng = get_engine(d)
+                    eng.set_matrix_csr(ip, ix, dt, n, g)
+                    eng.set_labels(labels, L)
+                return d, eng
+
+            with ThreadPoolExecutor(len(missing)) as pool:
+                for d, eng in pool.map(make, missing):
+                    self._replicas[d] = eng
+        return [self.engine] + [self._replicas[d] for d in devices[1:]]
 
     def resolved(self, expr_prop, return_all_lrs, stat="means"):
         """(ResolvedTriples, base lr_res frame) for one filter setting; the methods of a consensus that share
@@ -233,7 +277,7 @@ class PipelineState:
 
 def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells, use_raw, layer,
             verbose, device=0, base=float(np.e), want_max=False, want_cluster_stats=False,
-            mdata_kwargs=None) -> PipelineState:
+            mdata_kwargs=None, dist: DistContext | None = None) -> PipelineState:
     res = handle_resource(interactions=interactions, resource=resource, resource_name=resource_name, verbose=verbose)
     if _pre.is_mudata(adata):                    # `_liana_pipe.py:126-129`
         adata = _pre.mdata_to_anndata(adata, **(mdata_kwargs or {}), verbose=verbose)
@@ -246,7 +290,7 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
     eng = get_engine(device)
     prep = _pre.prepare_input(adata, groupby=groupby, min_cells=min_cells, engine=eng, groupby_subset=groupby_subset,
                               use_raw=use_raw, layer=layer, verbose=verbose, want_max=want_max,
-                              want_cluster_stats=want_cluster_stats)
+                              want_cluster_stats=want_cluster_stats, dist=dist)
     tables, all_entities = _cached_tables(res, prep.var_names)
     _pre.assert_covered(all_entities, prep.var_names, verbose=verbose)
     # subset to the resource's genes (sorted intersection, `_liana_pipe.py:161-164`): a column map for the
@@ -257,12 +301,20 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
     if verbose:
         print(f"Generating ligand-receptor stats for {prep.n_cells} samples and {len(tables.entities)} features")
     L = len(prep.categories)
-    eng.commit_matrix(col_map, len(tables.entities), prep.n_cells)
+    if prep.n_cells_local is None:
+        eng.commit_matrix(col_map, len(tables.entities), prep.n_cells)
+    else:
+        # every rank committed the cells of its own row block: the committed blocks (resource genes only, ~6 % of the
+        # staged bytes) are all-gathered over NVLink and become every rank's matrix
+        eng.commit_matrix(col_map, len(tables.entities), prep.n_cells_local)
+        d_ip, d_ix, d_dt = dist.all_gather_csr(eng)
+        eng.set_matrix_csr(d_ip, d_ix, d_dt, prep.n_cells, len(tables.entities))
     prep.var_names = tables.entities
     labels, L_eng = prep.labels, L
     if len(labels) and labels.min() < 0:          # cells without a label: one more cluster on the engine (see PipelineState)
         labels, L_eng = np.where(labels < 0, L, labels).astype(np.int32), L + 1
     eng.set_labels(labels, L_eng)
+    engine_labels = (np.ascontiguousarray(labels, dtype=np.int32), L_eng)
     means_all, stored, sizes_all = eng.observed()
     props_all = stored / sizes_all[:, None].astype(np.float64)
     means, props, sizes = means_all[:L], props_all[:L], sizes_all[:L]
@@ -274,6 +326,7 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
             if s in pos and t in pos:
                 pair_mask[pos[s], pos[t]] = True
     state = PipelineState(prep, tables, eng, means, props, sizes, pair_mask, base=base, sizes_all=sizes_all)
+    state.engine_labels = engine_labels
     if L_eng != L:
         state.engine_tables = (means_all, props_all)       # [L + 1, G]: what the engine's row resolution indexes
     return state
@@ -453,17 +506,41 @@ def method_columns(method_add_cols, supp_columns) -> list:
     return out
 
 
-def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, seed, perm_source, order,
-                       gmean_mode, dist: DistContext | None = None):
-    """Exceedance counts for the kept rows.  Permutations are sharded over ranks when a
-    DistContext with world_size > 1 is given; the uint32 count vectors are summed with one
-    all-reduce (integer -> identical for any GPU count)."""
-    eng = state.engine
-    scores = (E.SCORE_CPDB if obs_cpdb is not None else 0) | (E.SCORE_GMEAN if obs_gmean is not None else 0)
-    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs_cpdb, obs_gmean)
+def _shard_runner(state, dist, devices, n_perms, setup, run_range):
+    """Shared plumbing of the two null entry points.  One engine: permutations [lo, hi) of this rank.  `devices`
+    (several CUDA indices, one process): the permutation range is split over the devices' engines, one thread each
+    (the C ABI calls release the GIL), and the integer counts are added on the host.  Ranks (`dist`): the uint32
+    count vectors are summed with one all-reduce - identical results for any number of GPUs either way."""
+    if devices is not None and len(devices) > 1:
+        if dist is not None and dist.world_size > 1:
+            raise ValueError("pass either `dist` (one process per GPU) or `devices` (one process, several GPUs)")
+        from concurrent.futures import ThreadPoolExecutor
+        engines = state.replicas(devices)
+        n = len(engines)
+
+        def work(k):
+            import torch
+            with torch.cuda.device(engines[k].device):
+                setup(engines[k])
+                return run_range(engines[k], (n_perms * k) // n, (n_perms * (k + 1)) // n)
+
+        with ThreadPoolExecutor(n) as pool:
+            parts = list(pool.map(work, range(n)))
+        return {k: sum((p[k].astype(np.uint32) for p in parts[1:]), parts[0][k].astype(np.uint32)) for k in parts[0]}
     rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
-    lo = (n_perms * rank) // world
-    hi = (n_perms * (rank + 1)) // world
+    setup(state.engine)
+    out = run_range(state.engine, (n_perms * rank) // world, (n_perms * (rank + 1)) // world)
+    if dist is not None and world > 1:
+        out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
+    return out
+
+
+def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, seed, perm_source, order,
+                       gmean_mode, dist: DistContext | None = None, devices=None):
+    """Exceedance counts for the kept rows.  Permutations are sharded by global id over ranks (`dist`) or over the
+    devices of one process (`devices`); only the uint32 count vectors are combined (integer -> identical for any
+    GPU count)."""
+    scores = (E.SCORE_CPDB if obs_cpdb is not None else 0) | (E.SCORE_GMEAN if obs_gmean is not None else 0)
     perm_source = default_perm_source() if perm_source is None else perm_source
     if perm_source not in ("philox", "reference"):
         raise ValueError("perm_source must be 'philox' or 'reference'")
@@ -473,19 +550,21 @@ def permutation_counts(state: PipelineState, tri, obs_cpdb, obs_gmean, n_perms, 
         raise ValueError("order must be 'exact', 'fast' or None")
     kw = dict(order=E.ORDER_EXACT if order == "exact" else E.ORDER_FAST, scores=scores,
               gmean_mode=E.GMEAN_LITERAL if gmean_mode == "literal" else E.GMEAN_PRODUCT)
-    if perm_source == "philox":
-        out = eng.run(hi - lo, seed=seed, perm_offset=lo, **kw)
-    else:
+
+    def setup(eng):
+        eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs_cpdb, obs_gmean)
+
+    def run_range(eng, lo, hi):
+        if perm_source == "philox":
+            return eng.run(hi - lo, seed=seed, perm_offset=lo, **kw)
         # the reference's draws, a bounded chunk of the index array at a time; integer counts add up
         out = None
         for _, idx in reference_perm_chunks(state.prep.n_cells, n_perms, seed, lo, hi):
             part = eng.run(len(idx), seed=seed, perm_idx=idx, **kw)
             out = part if out is None else {k: out[k] + part[k] for k in out}
-        if out is None:
-            out = eng.run(0, seed=seed, **kw)
-    if dist is not None and world > 1:
-        out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
-    return out
+        return out if out is not None else eng.run(0, seed=seed, **kw)
+
+    return _shard_runner(state, dist, devices, n_perms, setup, run_range)
 
 
 KH = 0.5          # `cellchat._kh` (`liana/method/sc/_cellchat.py:53`)
@@ -499,26 +578,24 @@ def observed_cellchat(ligand_trimean: np.ndarray, receptor_trimean: np.ndarray, 
 
 
 def permutation_counts_trimean(state: PipelineState, tri, obs_prob, n_perms, seed, perm_source, kh=KH,
-                               dist: DistContext | None = None):
+                               dist: DistContext | None = None, devices=None):
     """CellChat exceedance counts for the kept rows (selection, not summation: no `order` applies).  Sharded over
-    ranks like `permutation_counts`."""
-    eng = state.engine
-    eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt)
-    rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
-    lo = (n_perms * rank) // world
-    hi = (n_perms * (rank + 1)) // world
+    ranks / devices like `permutation_counts`."""
     perm_source = default_perm_source() if perm_source is None else perm_source
-    if perm_source == "philox":
-        out = eng.run_trimean(hi - lo, state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_offset=lo)
-    elif perm_source == "reference":
+    if perm_source not in ("philox", "reference"):
+        raise ValueError("perm_source must be 'philox' or 'reference'")
+    mat_max = state.prep.mat_max
+
+    def setup(eng):
+        eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt)
+
+    def run_range(eng, lo, hi):
+        if perm_source == "philox":
+            return eng.run_trimean(hi - lo, mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_offset=lo)
         out = None
         for _, idx in reference_perm_chunks(state.prep.n_cells, n_perms, seed, lo, hi):
-            part = eng.run_trimean(len(idx), state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_idx=idx)
+            part = eng.run_trimean(len(idx), mat_max, obs_prob=obs_prob, kh=kh, seed=seed, perm_idx=idx)
             out = part if out is None else {k: out[k] + part[k] for k in out}
-        if out is None:
-            out = eng.run_trimean(0, state.prep.mat_max, obs_prob=obs_prob, kh=kh, seed=seed)
-    else:
-        raise ValueError("perm_source must be 'philox' or 'reference'")
-    if dist is not None and world > 1:
-        out = {k: dist.all_reduce_sum_u32(v) for k, v in out.items()}
-    return out
+        return out if out is not None else eng.run_trimean(0, mat_max, obs_prob=obs_prob, kh=kh, seed=seed)
+
+    return _shard_runner(state, dist, devices, n_perms, setup, run_range)

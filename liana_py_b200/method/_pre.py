@@ -37,6 +37,7 @@ class PreparedInput:
     mat_mean: float = 0.0         # mean over ALL entries of the prepared matrix (SingleCellSignalR, `_liana_pipe.py:139-140`)
     mat_max: np.float32 | None = None   # `adata.X.max()` of the prepared matrix (CellChat, `_liana_pipe.py:143-146`)
     cluster_stats: tuple | None = None  # (mean [L], std [L]) over ALL entries of a cluster's rows (scSeqComm, `:466-476`)
+    n_cells_local: int | None = None    # multi-rank staging: kept cells of the row block THIS rank staged (None = all)
 
 
 def choose_mtx_rep(adata, use_raw=False, layer=None, verbose=False, keep_dense=False):
@@ -144,10 +145,23 @@ def _make_unique(names: pd.Index) -> pd.Index:
     return pd.Index(out)
 
 
+def _row_block(X, dense, r0, r1):
+    """Rows [r0, r1) of the caller's matrix WITHOUT copying its entries (views of the CSR arrays / of the dense rows)."""
+    if dense:
+        return X[r0:r1]
+    e0, e1 = int(X.indptr[r0]), int(X.indptr[r1])
+    return sparse.csr_matrix((X.data[e0:e1], X.indices[e0:e1], X.indptr[r0:r1 + 1] - X.indptr[r0]),
+                             shape=(r1 - r0, X.shape[1]), copy=False)
+
+
 def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_raw=False, layer=None,
-                  complex_sep="_", verbose=False, want_max=False, want_cluster_stats=False) -> PreparedInput:
+                  complex_sep="_", verbose=False, want_max=False, want_cluster_stats=False, dist=None) -> PreparedInput:
     """Same checks, order and exception types as `prep_check_adata` (`_pre.py:65-169`); the passes over the
-    matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU."""
+    matrix (feature sums, sample sums, finiteness, later the row / column subset) run on the GPU.
+
+    `dist` (a DistContext with several ranks, every rank holding the same host object): each rank stages only ITS
+    contiguous block of rows - 1/world of the bytes crosses each PCIe link - and the statistics are summed over ranks;
+    `_pipeline.prepare` then commits the blocks and all-gathers the (small) committed matrix over NVLink."""
     if is_mudata(adata):
         raise ValueError("MuData input: pass `mdata_kwargs` (x_mod, y_mod, ...) through the method call")
     X = choose_mtx_rep(adata, use_raw=use_raw, layer=layer, verbose=verbose, keep_dense=True)
@@ -203,7 +217,18 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     if len(rows) != X.shape[0]:
         row_keep = keep.astype(np.uint8)
 
-    stats = engine.stage_matrix_dense(X, row_keep) if dense else engine.stage_matrix(X, row_keep)
+    sharded = dist is not None and dist.world_size > 1
+    r0, r1 = 0, X.shape[0]
+    Xs, keep_s = X, row_keep
+    if sharded:
+        r0, r1 = dist.row_block(X.shape[0], None if dense else X.indptr)
+        Xs = _row_block(X, dense, r0, r1)
+        keep_s = None if row_keep is None else row_keep[r0:r1]
+    stats = engine.stage_matrix_dense(Xs, keep_s) if dense else engine.stage_matrix(Xs, keep_s)
+    if sharded:
+        packed = dist.all_reduce_np(np.concatenate([stats["col_sums"], [stats["kept_total"], float(stats["n_nonfinite"]),
+                                                                        float(stats["n_empty_rows"])]]))
+        stats = dict(col_sums=packed[:-3], kept_total=float(packed[-3]), n_nonfinite=int(packed[-2]), n_empty_rows=int(packed[-1]))
     # empty features are removed (sum == 0 over ALL cells), empty cells only reported (`_pre.py:122-133`)
     empty = stats["col_sums"] == 0
     if empty.any():
@@ -236,6 +261,9 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     if want_max:
         # scipy's sparse .max(): the implicit zeros take part (any prepared matrix that is not fully dense has one)
         stored_max, n_stored = engine.staged_max()
+        if sharded:
+            stored_max = np.float32(dist.all_reduce_np(np.array([float(stored_max)]), "max")[0])
+            n_stored = int(dist.all_reduce_np(np.array([n_stored], dtype=np.int64))[0])
         mat_max = stored_max if (n_stored >= n_all and n_stored > 0) else np.float32(max(stored_max, np.float32(0)))
     cluster_stats = None
     if want_cluster_stats:
@@ -244,12 +272,16 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
         L = len(kept_categories)
         row_label = np.full(X.shape[0], -1, dtype=np.int32)
         row_label[rows] = new_codes
-        sx, sq = engine.staged_cluster_stats(row_label, L)
+        sx, sq = engine.staged_cluster_stats(row_label[r0:r1], L)
+        if sharded:
+            both = dist.all_reduce_np(np.concatenate([sx, sq]))
+            sx, sq = both[:L], both[L:]
         n_entries = np.bincount(new_codes[new_codes >= 0], minlength=L).astype(np.float64) * len(keep_cols)   # unlabeled cells: no cluster
         mean = sx / n_entries
         cluster_stats = (mean, np.sqrt(np.maximum(sq / n_entries - mean ** 2, 0.0)))
     return PreparedInput(mat_max=mat_max, cluster_stats=cluster_stats, var_names=names[order], var_cols=keep_cols[order].astype(np.int64), n_genes_in=X.shape[1],
                          labels=new_codes, categories=kept_categories, obs_index=obs.index[rows], n_cells=len(rows),
+                         n_cells_local=int(keep[r0:r1].sum()) if sharded else None,
                          mat_mean=float(stats["kept_total"] / n_all) if n_all else 0.0)
 
 

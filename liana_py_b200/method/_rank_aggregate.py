@@ -53,12 +53,14 @@ class AggregateClass(MethodMeta):
                  resource: Optional[pd.DataFrame] = V.resource, interactions: Optional[list] = V.interactions,
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
                  *, perm_source: Optional[str] = None, order: Optional[str] = None, gmean_mode: str = "product",
-                 device: int = 0, dist: Optional[DistContext] = None, _names: bool = True):
+                 device: int = 0, dist: Optional[DistContext] = None, devices: Optional[list] = None,
+                 _names: bool = True):
+        device, devices = PL.resolve_devices(device, devices)
         if n_perms is None:
             consensus_opts = "Magnitude"                       # `_liana_pipe.py:108-109`
         state = PL.prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs, min_cells,
                            use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in self.add_cols,
-                           want_cluster_stats="ligand_cdf" in self.add_cols, mdata_kwargs=mdata_kwargs)
+                           want_cluster_stats="ligand_cdf" in self.add_cols, mdata_kwargs=mdata_kwargs, dist=dist)
         null_cache = {}
         lrs = {}
         for method in self.methods:
@@ -67,7 +69,8 @@ class AggregateClass(MethodMeta):
             meta = getattr(method, "_method", method)
             lrs[method.method_name] = run_method(state, meta, expr_prop, n_perms, seed, return_all_lrs, perm_source,
                                                  order, gmean_mode, dist, aggregate_flag=True, null_cache=null_cache,
-                                                 permuting_methods=[getattr(m, "_method", m) for m in self.methods])
+                                                 permuting_methods=[getattr(m, "_method", m) for m in self.methods],
+                                                 devices=devices)
         if consensus_opts is False:                             # per-method results as they are (`:220-221`)
             return {k: PL.materialise_names(state, v) for k, v in lrs.items()}
         # the reference outer-merges the per-method frames on the key columns (`_aggregate.py:39-49`);

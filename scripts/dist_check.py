@@ -37,10 +37,20 @@ for name in ("cellphonedb", "geometric_mean", "cellchat", "rank_aggregate"):
     if ctx.rank == 0:
         print(f"{name}: {ctx.world_size} ranks == 1 rank ({len(one)} rows, {time.time() - t0:.2f} s)", flush=True)
 sk = [c for c in adata.obs.columns if c != "cluster"][0]
-one = li.mt.cellphonedb.by_sample(adata, sk, **kw)
-many = li.mt.cellphonedb.by_sample(adata, sk, dist=ctx, **kw)
-same(one, many)
+for name in ("cellphonedb", "rank_aggregate"):
+    fn = getattr(li.mt, name)
+    one = fn.by_sample(adata, sk, **kw)
+    many = fn.by_sample(adata, sk, dist=ctx, **kw)          # numeric columns all-gathered, names built on the consumer
+    pd.testing.assert_frame_equal(many, one)                 # same rows, same ORDER, same dtypes
+    own = fn.by_sample(adata, sk, dist=ctx, gather=False, **kw)
+    assert sum(ctx.all_gather_objects(len(own))) == len(one)
+    if ctx.rank == 0:
+        print(f"{name}.by_sample over {adata.obs[sk].nunique()} samples: {ctx.world_size} ranks == 1 rank ({len(one)} rows)", flush=True)
+# dense input and a min_cells filter through the sharded staging
+dense = make_synthetic_adata(3000, 400, 6, density=0.3, seed_data=7, seed_labels=8)
+dense.X = np.asarray(dense.X.todense(), dtype=np.float32)
+same(li.mt.cellphonedb(dense, min_cells=400, **kw), li.mt.cellphonedb(dense, min_cells=400, dist=ctx, **kw))
 if ctx.rank == 0:
-    print(f"by_sample over {adata.obs[sk].nunique()} samples: {ctx.world_size} ranks == 1 rank ({len(one)} rows)", flush=True)
+    print("dense input + min_cells through the sharded staging: ok", flush=True)
 dist.barrier()
 dist.destroy_process_group()

@@ -32,6 +32,20 @@ class OracleEngine(SciPyStage):
         self.Xc, self.N, self.G = Xc, int(n_cells_out), int(n_genes_out)
         assert Xc.shape == (self.N, self.G)
 
+    def export_matrix_csr(self, device=None):
+        ip, ix, dt = self.Xc.indptr.astype(np.int32), self.Xc.indices.astype(np.int32), self.Xc.data.astype(np.float32)
+        if device is None:
+            return ip, ix, dt
+        import torch
+        return torch.from_numpy(ip), torch.from_numpy(ix), torch.from_numpy(dt)
+
+    def set_matrix_csr(self, indptr, indices, data, n_cells, n_genes):
+        from scipy import sparse
+        to_np = lambda a: a.numpy() if hasattr(a, "numpy") else np.asarray(a)      # noqa: E731
+        Xc = sparse.csr_matrix((to_np(data), to_np(indices), to_np(indptr)), shape=(int(n_cells), int(n_genes)))
+        Xc.sort_indices()
+        self.Xc, self.N, self.G = Xc, int(n_cells), int(n_genes)
+
     def set_labels(self, labels, n_clusters):
         self.labels, self.L = np.ascontiguousarray(labels, dtype=np.int32), int(n_clusters)
 

@@ -523,3 +523,19 @@ def test_return_all_lrs_contract():
     simple = ~(m["ligand_complex"].str.contains("_") | m["receptor_complex"].str.contains("_"))
     assert np.array_equal(m.loc[simple, "cellphone_pvals"].values, m.loc[simple, "cellphone_pvals_all"].values)
     assert np.array_equal(m.loc[simple, "lr_means"].values, m.loc[simple, "lr_means_all"].values)
+
+
+def test_devices_kwarg_equals_single_gpu():
+    """Single-call multi-GPU: `devices=[0, 1, ...]` splits the permutations (or the samples of `by_sample`) over the GPUs
+    of ONE process - the committed matrix is copied device to device - and must return exactly the one-GPU frame."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from liana_py_b200.testing._synth import make_synthetic_adata
+    devices = list(range(min(torch.cuda.device_count(), 4)))
+    adata = make_synthetic_adata(8000, 1200, 7, density=0.2, seed_data=15, seed_labels=16, n_samples=4)
+    kw = dict(groupby="cluster", use_raw=False, n_perms=333, seed=5, inplace=False)
+    for fn in (li.mt.cellphonedb, li.mt.cellchat, li.mt.rank_aggregate):
+        pd.testing.assert_frame_equal(fn(adata, devices=devices, **kw), fn(adata, **kw))
+    pd.testing.assert_frame_equal(li.mt.cellphonedb.by_sample(adata, "sample", devices=devices, **kw),
+                                  li.mt.cellphonedb.by_sample(adata, "sample", **kw))
