@@ -76,7 +76,7 @@ class MethodMeta:
                   verbose=V.verbose, **kwargs):
         """Run the method per sample (`_Method.py:92-159`).  Samples are independent; with a
         DistContext (kwarg `dist`) contiguous blocks of samples are sharded over ranks and the numeric result
-        columns are all-gathered (`_by_sample_sharded`) - no data-path collective."""
+        columns are all-gathered (`_by_sample_blocks`) - no data-path collective."""
         if sample_key not in adata.obs:
             raise ValueError(f"{sample_key} was not found in `adata.obs`.")
         if not isinstance(adata.obs[sample_key].dtype, pd.CategoricalDtype):
@@ -92,49 +92,24 @@ class MethodMeta:
         sizes = [int((sample_col == s).sum()) for s in samples]
         mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
         sharded = dist is not None and dist.world_size > 1
-        if devices is not None and len(devices) > 1:
-            # one process, several GPUs: contiguous blocks of samples per device, one thread each (the C ABI calls -
-            # uploads, statistics, permutations - release the GIL; the pandas parts take turns)
-            if sharded:
-                raise ValueError("pass either `dist` (one process per GPU) or `devices` (one process, several GPUs)")
-            from concurrent.futures import ThreadPoolExecutor
-            kwargs.pop("device", None)
-            blocks = [DistContext(k, len(devices)).sample_shard(sizes) for k in range(len(devices))]
-
-            def work(k):
-                out = []
-                for i in blocks[k]:
-                    temp = adata[sample_col == samples[i]].copy()
-                    df = self.__call__(temp, inplace=False, verbose=full_verbose, device=int(devices[k]), **kwargs)
-                    df.insert(0, sample_key, samples[i])
-                    out.append(df)
-                return out
-
-            with ThreadPoolExecutor(len(devices)) as pool:
-                frames = [df for part in pool.map(work, range(len(devices))) for df in part]
-            liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0].reset_index(drop=True)
-        elif not sharded:
-            frames = []
-            for i in mine:                         # sample-category order, like the reference's concat
-                temp = adata[sample_col == samples[i]].copy()
-                df = self.__call__(temp, inplace=False, verbose=full_verbose, **kwargs)
-                df.insert(0, sample_key, samples[i])
-                frames.append(df)
-            # a fresh RangeIndex like the reference's `concat(...).reset_index()` (`_Method.py:154-155`)
-            liana_res = pd.concat(frames, ignore_index=True) if len(frames) != 1 else frames[0].reset_index(drop=True)
-        else:
-            liana_res = self._by_sample_sharded(adata, sample_key, samples, sample_col, list(mine), dist, gather,
-                                                full_verbose, kwargs)
+        if devices is not None and len(devices) > 1 and sharded:
+            raise ValueError("pass either `dist` (one process per GPU) or `devices` (one process, several GPUs)")
+        liana_res = self._by_sample_blocks(adata, sample_key, samples, sample_col, sizes, list(mine), dist if sharded else None,
+                                           gather, full_verbose, kwargs, devices)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
 
-    def _by_sample_sharded(self, adata, sample_key, samples, sample_col, mine, dist, gather, verbose, kwargs):
-        """Samples sharded over ranks (contiguous blocks of the sample order, `DistContext.sample_shard`).  Every rank
-        scores its own samples and keeps the result as NUMBERS: the name columns are codes into tables that are the
-        same on every rank (the resource's genes / complexes, the clusters of the whole object, the sample list).  The
-        numeric columns are concatenated over ranks with one all-gather per column (NVLink), and only then - once, on
-        the consumer - the string columns are built.  No DataFrame is pickled."""
+    def _by_sample_blocks(self, adata, sample_key, samples, sample_col, sizes, mine, dist, gather, verbose, kwargs, devices):
+        """Every sample is scored into a frame of NUMBERS: the name columns are codes into tables that do not depend
+        on the sample (the resource's genes / complexes, the clusters of the whole object, the sample list), so the
+        per-sample results concatenate as arrays and the string columns are built ONCE at the end (in row chunks on a
+        thread pool) instead of once per sample plus a pandas concat of string columns.
+          ranks (`dist`)     contiguous blocks of the sample order per rank (`DistContext.sample_shard`); the numeric
+                             columns are concatenated over ranks with one all-gather per column over NVLink - no
+                             DataFrame is pickled
+          `devices`          one process, several GPUs: contiguous blocks of samples per device, one thread each (the C
+                             ABI calls - uploads, statistics, permutations - release the GIL; the pandas parts take turns)"""
         from ..resource import handle_resource
         if "groupby" not in kwargs:
             raise TypeError("by_sample: pass `groupby` as a keyword argument")
@@ -143,22 +118,29 @@ class MethodMeta:
         res = handle_resource(interactions=kwargs.get("interactions"), resource=kwargs.get("resource"),
                               resource_name=kwargs.get("resource_name", V.resource_name), verbose=False)
         g_tables = PL.global_name_tables(res, cats)
-        parts, columns = [], None
-        for i in mine:
+
+        def score(i, **extra):
             temp = adata[sample_col == samples[i]].copy()
-            frame, l_tables = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **kwargs)
+            frame, l_tables = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **{**kwargs, **extra})
             cols = PL.to_global_codes(frame, l_tables, g_tables)
-            cols = {sample_key: np.full(len(frame), i, dtype=np.int32), **cols}
-            parts.append(cols)
-            columns = list(cols)
+            return {sample_key: np.full(len(frame), i, dtype=np.int32), **cols}
+
+        if devices is not None and len(devices) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            blocks = [[i for i in DistContext(k, len(devices)).sample_shard(sizes) if i in set(mine)] for k in range(len(devices))]
+            with ThreadPoolExecutor(len(devices)) as pool:
+                parts = [p for part in pool.map(lambda k: [score(i, device=int(devices[k])) for i in blocks[k]], range(len(devices)))
+                         for p in part]
+        else:
+            parts = [score(i) for i in mine]
         # column names / dtypes of a rank without samples come from the others (tiny object exchange)
-        spec = [(c, parts[0][c].dtype.str) for c in columns] if parts else None
-        if gather:                                  # a collective: every rank takes part
+        spec = [(c, parts[0][c].dtype.str) for c in parts[0]] if parts else None
+        if dist is not None and gather:             # a collective: every rank takes part
             spec = next((s for s in dist.all_gather_objects(spec) if s is not None), None)
         if spec is None:                            # no sample on this rank (gather=False) or anywhere
             return pd.DataFrame({sample_key: pd.Series([], dtype=object)})
         local = {c: (np.concatenate([p[c] for p in parts]) if parts else np.zeros(0, dtype=np.dtype(dt))) for c, dt in spec}
-        if gather:
+        if dist is not None and gather:
             local = dist.all_gather_rows(local)
         g_tables = dict(g_tables)
         g_tables[sample_key] = pd.Index(samples)

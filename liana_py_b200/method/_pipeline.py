@@ -332,11 +332,39 @@ def prepare(adata, groupby, resource_name, resource, interactions, groupby_pairs
     return state
 
 
+_CHUNK_POOL = None
+
+
+def _chunk_pool():
+    """Second small pool for the row chunks of `_take_names` (which itself runs inside `_frame_pool` tasks)."""
+    global _CHUNK_POOL
+    if _CHUNK_POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _CHUNK_POOL = ThreadPoolExecutor(max_workers=max(1, min(16, os.cpu_count() or 1)), thread_name_prefix="lrperm-take")
+    return _CHUNK_POOL
+
+
 def _take_names(names, codes):
     """names[codes] as a pandas string array: one vectorised take on the Index's backing array (10x faster
-    than fancy-indexing a NumPy unicode array and letting pandas re-infer every string)."""
+    than fancy-indexing a NumPy unicode array and letting pandas re-infer every string).  Millions of rows (the frame
+    of `by_sample`) are taken in row chunks on a thread pool - Arrow's take releases the GIL - and stay chunked: a
+    pandas Arrow string column is a ChunkedArray anyway (1 s -> 0.2 s per column at 28 M rows on 8 threads)."""
     idx = names if isinstance(names, pd.Index) else pd.Index(np.asarray(names))
-    return idx.array.take(np.asarray(codes, dtype=np.int64))
+    arr = idx.array
+    codes = np.asarray(codes)
+    if len(codes) >= (1 << 21) and isinstance(arr, pd.arrays.ArrowStringArray) and hasattr(arr, "_pa_array"):
+        try:
+            import pyarrow as pa
+            import pyarrow.compute as pc
+            table = arr._pa_array
+            table = table.combine_chunks() if isinstance(table, pa.ChunkedArray) else table
+            parts = np.array_split(codes, max(1, min(64, len(codes) >> 20)))
+            outs = list(_chunk_pool().map(lambda c: pc.take(table, pa.array(c)), parts))
+            return type(arr)(pa.chunked_array(outs), dtype=arr.dtype)
+        except Exception:        # an Arrow / pandas build without these entry points: the plain take below
+            pass
+    return arr.take(codes.astype(np.int64, copy=False))
 
 
 def base_frame(state: PipelineState, tri: _tables.ResolvedTriples, stat: str = "means") -> pd.DataFrame:

@@ -145,13 +145,24 @@ def _make_unique(names: pd.Index) -> pd.Index:
     return pd.Index(out)
 
 
+class CSRBlock:
+    """Rows [r0, r1) of a CSR matrix as VIEWS of its arrays (what `Engine.stage_matrix` reads: indptr / indices / data /
+    shape).  Not a SciPy matrix on purpose: SciPy's constructor copies a view that is much smaller than its base array
+    (`_prune_array`), i.e. every rank but the first would copy its whole block on the host."""
+
+    def __init__(self, X, r0, r1):
+        e0, e1 = int(X.indptr[r0]), int(X.indptr[r1])
+        self.indptr = X.indptr[r0:r1 + 1] - X.indptr[r0]
+        self.indices, self.data = X.indices[e0:e1], X.data[e0:e1]
+        self.shape = (r1 - r0, X.shape[1])
+
+    def tocsr(self):
+        return sparse.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape)
+
+
 def _row_block(X, dense, r0, r1):
     """Rows [r0, r1) of the caller's matrix WITHOUT copying its entries (views of the CSR arrays / of the dense rows)."""
-    if dense:
-        return X[r0:r1]
-    e0, e1 = int(X.indptr[r0]), int(X.indptr[r1])
-    return sparse.csr_matrix((X.data[e0:e1], X.indices[e0:e1], X.indptr[r0:r1 + 1] - X.indptr[r0]),
-                             shape=(r1 - r0, X.shape[1]), copy=False)
+    return X[r0:r1] if dense else CSRBlock(X, r0, r1)
 
 
 def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_raw=False, layer=None,

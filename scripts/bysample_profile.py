@@ -8,15 +8,10 @@ from liana_py_b200.testing._anndata_lite import AnnDataLite
 from liana_py_b200.testing._synth import consensus_genes
 from liana_py_b200.testing._synth_gpu import synthetic_csr_torch
 
+import torch
+import bench
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-genes = consensus_genes(); G = len(genes); N, L = 10_000, 30
-mats, labs, samp = [], [], []
-for s in range(S):
-    indptr, indices, data, labels = synthetic_csr_torch(N, G, L, 0.08, seed_data=1337 + 2 * s, seed_labels=1338 + 2 * s)
-    mats.append(sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(N, G)))
-    labs.append(labels.cpu().numpy()); samp += [f"s{s:02d}"] * N
-obs = pd.DataFrame({"cluster": pd.Categorical([f"c{v:02d}" for v in np.concatenate(labs)]), "sample": pd.Categorical(samp)})
-adata = AnnDataLite(X=sparse.vstack(mats).tocsr(), obs=obs, var=pd.DataFrame(index=pd.Index(genes)))
+adata, _ = bench.by_sample_adata(torch.device("cuda", 0), n_samples=S)       # the bench's configs[4] input: 10k cells x 5k genes x 30 clusters per sample
 kw = dict(sample_key="sample", groupby="cluster", use_raw=False, n_perms=1000, inplace=False)
 for _ in range(2):
     t0 = time.perf_counter(); res = li.mt.cellphonedb.by_sample(adata, **kw)

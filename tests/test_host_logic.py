@@ -18,7 +18,8 @@ class SciPyStage:
     """Stand-in of Engine.stage_matrix / staged_max / staged_cluster_stats (what the CUDA kernels compute)."""
 
     def stage_matrix(self, X, row_keep=None):
-        self.X, self.keep = X.tocsr(), row_keep
+        X = X.tocsr()                 # a SciPy matrix, or the row-block view of multi-rank staging (`_pre.CSRBlock`)
+        self.X, self.keep = X, row_keep
         rows = np.arange(X.shape[0]) if row_keep is None else np.flatnonzero(row_keep)
         return dict(col_sums=np.asarray(X.astype(np.float64).sum(axis=0)).ravel(),
                     kept_total=float(X[rows].astype(np.float64).sum()), n_nonfinite=int((~np.isfinite(X.data)).sum()),
