@@ -120,10 +120,13 @@ class MethodMeta:
         g_tables = PL.global_name_tables(res, cats)
 
         def score(i, **extra):
-            temp = adata[sample_col == samples[i]].copy()
-            frame, l_tables = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **{**kwargs, **extra})
-            cols = PL.to_global_codes(frame, l_tables, g_tables)
-            return {sample_key: np.full(len(frame), i, dtype=np.int32), **cols}
+            temp = adata[sample_col == samples[i]]
+            if getattr(temp, "is_view", True):      # anndata hands out views; a stand-in that already copied is not copied again
+                temp = temp.copy()
+            cols, state = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **{**kwargs, **extra})
+            cols = PL.to_global_codes(cols, PL.global_code_maps(state, g_tables))
+            n_rows = len(next(iter(cols.values()))) if cols else 0
+            return {sample_key: np.full(n_rows, i, dtype=np.int32), **cols}
 
         if devices is not None and len(devices) > 1:
             from concurrent.futures import ThreadPoolExecutor
@@ -178,8 +181,8 @@ class Method(MethodMeta):
                                perm_source, order, gmean_mode, dist, add_cols=add_cols, devices=devices)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
-        if not _names:                          # by_sample across ranks: (code frame, name tables), see by_sample
-            return PL.sort_frame(state.engine, liana_res, orderby, ascending), PL.name_tables(state)
+        if not _names:                          # by_sample: (sorted numeric columns, prepared state), see `_by_sample_blocks`
+            return PL.sorted_code_columns(state.engine, liana_res, orderby, ascending), state
         liana_res = PL.finish_frame(state, liana_res, orderby, ascending)
         if inplace:
             adata.uns[key_added] = liana_res

@@ -96,7 +96,11 @@ _EXPLODED_CACHE = {}
 
 def exploded(res: pd.DataFrame):
     """The resource split into subunits (memoised on its content, see `_cached_tables`)."""
-    rkey = hash(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).values.tobytes())
+    hint = res.attrs.get("lrperm_resource_key")
+    if hint is not None and hint[2] == len(res) and list(res.columns[:2]) == ["ligand", "receptor"]:
+        rkey = hint                                   # a bundled table as `select_resource` handed it out
+    else:
+        rkey = hash(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).values.tobytes())
     ex = _EXPLODED_CACHE.get(rkey)
     if ex is None:
         if len(_EXPLODED_CACHE) >= 8:
@@ -389,29 +393,42 @@ def name_tables(state: PipelineState) -> dict:
 
 
 def global_name_tables(res: pd.DataFrame, categories) -> dict:
-    """Name tables that do not depend on the sample / rank: every gene and complex the RESOURCE names, every cluster
-    of the whole object.  `by_sample` over ranks exchanges frames whose name columns hold codes into these tables
-    (integers travel over NCCL; the strings are built once, on the consumer)."""
+    """Name tables that do not depend on the sample / rank: every gene the RESOURCE names, the ligand / receptor
+    complex of every interaction of the resource, every cluster of the whole object.  `by_sample` exchanges frames
+    whose name columns hold codes into these tables (integers travel over NCCL; the strings are built once, on the
+    consumer)."""
     _, ex = exploded(res)
     genes = pd.Index(ex.entities)
-    return {K.LIGAND: genes, K.RECEPTOR: genes, K.LIGAND_COMPLEX: pd.Index(pd.unique(ex.ligand_complex)),
-            K.RECEPTOR_COMPLEX: pd.Index(pd.unique(ex.receptor_complex)), K.SOURCE: pd.Index(categories),
+    return {K.LIGAND: genes, K.RECEPTOR: genes, K.LIGAND_COMPLEX: pd.Index(ex.ligand_complex),
+            K.RECEPTOR_COMPLEX: pd.Index(ex.receptor_complex), K.SOURCE: pd.Index(categories),
             K.TARGET: pd.Index(categories)}
 
 
-def to_global_codes(frame: pd.DataFrame, local_tables: dict, global_tables: dict) -> dict:
-    """Columns of a code frame as 1-D arrays, the name columns re-coded from the sample's own tables (`name_tables`)
-    into `global_name_tables`."""
-    out = {}
-    for col in frame.columns:
-        v = frame[col].values
-        if col in local_tables:
-            remap = global_tables[col].get_indexer(pd.Index(np.asarray(local_tables[col])))
-            if (remap < 0).any():
-                raise RuntimeError(f"`{col}`: a name of the sample is missing from the global table (internal error)")
-            v = remap.astype(np.int32)[v]
-        out[col] = np.ascontiguousarray(v)
-    return out
+def global_code_maps(state: PipelineState, global_tables: dict) -> dict:
+    """local code -> global code per name column: genes and interactions through the indices the resource tables
+    carry (`ResourceTables.entity_index / inter_index`, no string is touched), clusters through one small lookup."""
+    tb = state.tables
+    cats = global_tables[K.SOURCE].get_indexer(pd.Index(np.asarray(state.prep.categories))).astype(np.int32)
+    if (cats < 0).any():
+        raise RuntimeError("a cluster of the sample is missing from the object's categories (internal error)")
+    return {K.LIGAND: tb.entity_index, K.RECEPTOR: tb.entity_index, K.LIGAND_COMPLEX: tb.inter_index,
+            K.RECEPTOR_COMPLEX: tb.inter_index, K.SOURCE: cats, K.TARGET: cats}
+
+
+def to_global_codes(columns: dict, maps: dict) -> dict:
+    """Columns of a code frame (1-D arrays), the name columns re-coded into `global_name_tables`."""
+    return {c: (maps[c][v] if c in maps else np.ascontiguousarray(v)) for c, v in columns.items()}
+
+
+def sorted_code_columns(engine, frame: pd.DataFrame, by: str, ascending: bool) -> dict:
+    """`sort_frame` for a frame that stays numeric: every column gathered once as a 1-D array (no pandas take over
+    consolidated blocks)."""
+    vals = np.asarray(frame[by].values, dtype=np.float64)
+    if engine is None or len(vals) < 4096 or np.isnan(vals).any():
+        frame = frame.sort_values(by=by, ascending=ascending)
+        return {c: frame[c].values for c in frame.columns}
+    order = engine.argsort(vals, descending=not ascending)
+    return {c: frame[c].values.take(order) for c in frame.columns}
 
 
 def frame_from_codes(columns: dict, global_tables: dict) -> pd.DataFrame:

@@ -86,14 +86,14 @@ class AggregateClass(MethodMeta):
         lr_res = aggregate(lr_res, consensus=self, aggregate_method=aggregate_method, consensus_opts=consensus_opts,
                            engine=state.engine, sort=False)
         orderby = self.magnitude if self.magnitude in lr_res.columns else self.specificity
+        if not _names:                          # by_sample: (sorted numeric columns, prepared state)
+            if orderby not in lr_res.columns:
+                return {c: lr_res[c].values for c in lr_res.columns}, state
+            return PL.sorted_code_columns(state.engine, lr_res, orderby, True), state
         if orderby not in lr_res.columns:       # no consensus column was asked for: rows stay as they are
-            lr_res = lr_res if not _names else PL.materialise_names(state, lr_res)
-        elif not _names:                        # by_sample across ranks: (code frame, name tables)
-            lr_res = PL.sort_frame(state.engine, lr_res, orderby, True)
+            lr_res = PL.materialise_names(state, lr_res)
         else:
             lr_res = PL.finish_frame(state, lr_res, orderby, True)
-        if not _names:
-            return lr_res, PL.name_tables(state)
         if inplace:
             adata.uns[key_added] = lr_res
         return None if inplace else lr_res

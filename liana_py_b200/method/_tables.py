@@ -30,6 +30,8 @@ class ResourceTables:
     lig_sub: np.ndarray            # [n_int, max_l] gene index, -1 padded
     rec_sub: np.ndarray            # [n_int, max_r]
     entities: np.ndarray           # sorted gene names used by the kept interactions
+    entity_index: np.ndarray = None    # [n_entities] int32: position of every kept gene in the resource's own entity list
+    inter_index: np.ndarray = None     # [n_int] int32: position of every kept interaction in the resource
 
 
 @dataclass
@@ -83,7 +85,8 @@ def tables_for_genes(ex: ExplodedResource, var_names: np.ndarray) -> ResourceTab
     max_l = max(int((lig_sub >= 0).sum(axis=1).max(initial=1)), 1)
     max_r = max(int((rec_sub >= 0).sum(axis=1).max(initial=1)), 1)
     return ResourceTables(ex.ligand_complex[ok], ex.receptor_complex[ok], np.ascontiguousarray(lig_sub[:, :max_l]),
-                          np.ascontiguousarray(rec_sub[:, :max_r]), ex.entities[used])
+                          np.ascontiguousarray(rec_sub[:, :max_r]), ex.entities[used],
+                          np.flatnonzero(used).astype(np.int32), np.flatnonzero(ok).astype(np.int32))
 
 
 def build_resource_tables(resource: pd.DataFrame, var_names: np.ndarray, sep: str = "_"):

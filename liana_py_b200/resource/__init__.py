@@ -29,6 +29,8 @@ def select_resource(resource_name: str = "consensus") -> pd.DataFrame:
                          "or pass a DataFrame via `resource=`.")
     if name not in _PARSED:
         _PARSED[name] = pd.read_csv(path, index_col=False)
+        # identity of an UNMODIFIED bundled table (attrs survive .copy()): lets the table caches skip hashing the content
+        _PARSED[name].attrs["lrperm_resource_key"] = ("bundled", name, len(_PARSED[name]))
     return _PARSED[name].copy()
 
 

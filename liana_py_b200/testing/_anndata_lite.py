@@ -51,6 +51,7 @@ class AnnDataLite:
         self.layers = {} if layers is None else layers
         self.raw = raw
         self.isbacked = False
+        self.is_view = False                 # subsetting copies (anndata hands out views)
 
     # -- names / shape -----------------------------------------------------------------
     @property
