@@ -163,49 +163,62 @@ class DistContext:
 
     def all_gather_rows(self, columns: dict) -> dict:
         """Concatenate, in rank order, the per-rank NumPy columns of a table (same column names and dtypes on every
-        rank, any number of rows per rank - also zero): one size exchange, then one padded all-gather per column
-        (NCCL `all_gather_into_tensor` over NVLink; gloo in the CPU tests).  No pickling, no strings."""
+        rank, any number of rows per rank - also zero).  The columns of a rank travel as ONE byte buffer: one size
+        exchange, one H2D copy, one padded `all_gather_into_tensor` over NVLink (gloo in the CPU tests), one D2H copy
+        into a pinned buffer that is kept for the next call.  No pickling, no strings."""
         if self.world_size == 1:
             return columns
         import torch
         import torch.distributed as dist
         names = list(columns)
-        n_local = int(len(columns[names[0]])) if names else 0
+        if not names:
+            return columns
+        n_local = int(len(columns[names[0]]))
         dev = self.device if self.device is not None else torch.device("cpu")
-        sizes = torch.zeros(self.world_size, dtype=torch.int64, device=dev)
-        mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_gather_into_tensor(sizes, mine, group=self.group)
-        else:
-            parts = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world_size)]
-            dist.all_gather(parts, mine, group=self.group)
-            sizes = torch.cat(parts)
-        sizes = [int(v) for v in sizes.cpu()]
-        n_max = max(sizes) if sizes else 0
-        out = {}
-        for c in names:
-            a = np.ascontiguousarray(columns[c])
-            if a.dtype == np.bool_:
-                a = a.view(np.uint8)
-            was_bool = columns[c].dtype == np.bool_
-            if n_max == 0:
-                out[c] = columns[c][:0]
-                continue
-            local = torch.zeros(n_max, dtype=torch.from_numpy(a[:0]).dtype, device=dev)
+        nccl = dist.get_backend(self.group) == "nccl"
+        sizes = self.all_reduce_np(np.array([n_local if r == self.rank else 0 for r in range(self.world_size)], dtype=np.int64))
+        sizes = [int(v) for v in sizes]
+        dtypes = [np.dtype(columns[c].dtype) for c in names]
+        row_bytes = [d.itemsize for d in dtypes]
+        n_max = max(sizes)
+        if n_max == 0:
+            return {c: columns[c][:0] for c in names}
+        # local buffer: column after column, every column padded to n_max rows (8-byte aligned starts)
+        col_off, off = [], 0
+        for rb in row_bytes:
+            col_off.append(off)
+            off += (n_max * rb + 7) & ~7
+        stride = off
+        send = torch.zeros(stride, dtype=torch.uint8, device=dev)
+        for c, o, rb in zip(names, col_off, row_bytes):
             if n_local:
-                local[:n_local].copy_(torch.from_numpy(a), non_blocking=False)
-            if dist.get_backend(self.group) == "nccl":
-                full = torch.empty(n_max * self.world_size, dtype=local.dtype, device=dev)
-                dist.all_gather_into_tensor(full, local, group=self.group)
-                full = full.view(self.world_size, n_max)
-                parts = [full[r, :sizes[r]] for r in range(self.world_size)]
-            else:
-                bufs = [torch.empty_like(local) for _ in range(self.world_size)]
-                dist.all_gather(bufs, local, group=self.group)
-                parts = [bufs[r][:sizes[r]] for r in range(self.world_size)]
-            host = torch.cat(parts).cpu().numpy()
-            out[c] = host.view(np.bool_) if was_bool else host
-        return out
+                a = np.ascontiguousarray(columns[c]).view(np.uint8).reshape(-1)
+                send[o:o + n_local * rb].copy_(torch.from_numpy(a), non_blocking=True)
+        if nccl:
+            full = torch.empty(stride * self.world_size, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(full, send, group=self.group)
+            host = self._pinned(stride * self.world_size)
+            host.copy_(full, non_blocking=False)
+            buf = host.numpy()
+        else:
+            bufs = [torch.empty_like(send) for _ in range(self.world_size)]
+            dist.all_gather(bufs, send, group=self.group)
+            buf = torch.cat(bufs).numpy()
+        def own(args):                               # owns its memory: the pinned buffer is reused by the next call
+            o, d = args
+            return np.concatenate([buf[r * stride + o:r * stride + o + sizes[r] * d.itemsize].view(d) for r in range(self.world_size)])
+
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(min(8, len(names))) as pool:       # memcpy releases the GIL
+            return dict(zip(names, pool.map(own, zip(col_off, dtypes))))
+
+    def _pinned(self, n_bytes: int):
+        """Grow-only pinned host buffer (page-locking is the expensive part of a device -> host copy of gigabytes)."""
+        import torch
+        cur = getattr(self, "_pin_buf", None)
+        if cur is None or cur.numel() < n_bytes:
+            self._pin_buf = cur = torch.empty(int(n_bytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        return cur[:n_bytes]
 
     def all_gather_objects(self, obj):
         if self.world_size == 1:

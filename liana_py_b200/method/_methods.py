@@ -88,8 +88,9 @@ class MethodMeta:
         # per rank); assembling one pandas frame of all samples on every rank costs far more than computing them
         gather: bool = kwargs.pop("gather", True)
         devices = kwargs.pop("devices", None)
-        sample_col = np.asarray(adata.obs[sample_key])
-        sizes = [int((sample_col == s).sum()) for s in samples]
+        # category CODES, not the names: `obs[sample_key] == name` over an object array costs ~10 ns per cell and sample
+        sample_col = np.asarray(adata.obs[sample_key].cat.codes)
+        sizes = np.bincount(sample_col[sample_col >= 0], minlength=len(samples)).tolist()
         mine = range(len(samples)) if dist is None or dist.world_size == 1 else dist.sample_shard(sizes)
         sharded = dist is not None and dist.world_size > 1
         if devices is not None and len(devices) > 1 and sharded:
@@ -120,7 +121,7 @@ class MethodMeta:
         g_tables = PL.global_name_tables(res, cats)
 
         def score(i, **extra):
-            temp = adata[sample_col == samples[i]]
+            temp = adata[sample_col == i]
             if getattr(temp, "is_view", True):      # anndata hands out views; a stand-in that already copied is not copied again
                 temp = temp.copy()
             cols, state = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **{**kwargs, **extra})
@@ -128,6 +129,15 @@ class MethodMeta:
             n_rows = len(next(iter(cols.values()))) if cols else 0
             return {sample_key: np.full(n_rows, i, dtype=np.int32), **cols}
 
+        import os
+        import time
+        tlog = [] if os.environ.get("LRPERM_DEBUG_TIMING") else None
+
+        def mark(what, t0):
+            if tlog is not None:
+                tlog.append(f"{what} {1e3 * (time.perf_counter() - t0):.1f} ms")
+
+        t_all = time.perf_counter()
         if devices is not None and len(devices) > 1:
             from concurrent.futures import ThreadPoolExecutor
             blocks = [[i for i in DistContext(k, len(devices)).sample_shard(sizes) if i in set(mine)] for k in range(len(devices))]
@@ -136,18 +146,29 @@ class MethodMeta:
                          for p in part]
         else:
             parts = [score(i) for i in mine]
+        mark(f"score {len(parts)} samples", t_all)
         # column names / dtypes of a rank without samples come from the others (tiny object exchange)
+        t0 = time.perf_counter()
         spec = [(c, parts[0][c].dtype.str) for c in parts[0]] if parts else None
         if dist is not None and gather:             # a collective: every rank takes part
             spec = next((s for s in dist.all_gather_objects(spec) if s is not None), None)
         if spec is None:                            # no sample on this rank (gather=False) or anywhere
             return pd.DataFrame({sample_key: pd.Series([], dtype=object)})
         local = {c: (np.concatenate([p[c] for p in parts]) if parts else np.zeros(0, dtype=np.dtype(dt))) for c, dt in spec}
+        mark("concatenate", t0)
         if dist is not None and gather:
+            t0 = time.perf_counter()
             local = dist.all_gather_rows(local)
+            mark("all_gather_rows", t0)
         g_tables = dict(g_tables)
         g_tables[sample_key] = pd.Index(samples)
-        return PL.frame_from_codes(local, g_tables)
+        t0 = time.perf_counter()
+        out = PL.frame_from_codes(local, g_tables)
+        mark("frame_from_codes", t0)
+        if tlog is not None:
+            import sys
+            print(f"[by_sample rank {dist.rank if dist is not None else 0}] " + " | ".join(tlog), file=sys.stderr, flush=True)
+        return out
 
 
 class Method(MethodMeta):
