@@ -161,11 +161,13 @@ class DistContext:
             torch.cuda.current_stream(dev).synchronize()     # the engine works on its own stream
         return indptr.to(torch.int32), ix_all, dt_all
 
-    def all_gather_rows(self, columns: dict) -> dict:
+    def all_gather_rows(self, columns: dict, dst=None):
         """Concatenate, in rank order, the per-rank NumPy columns of a table (same column names and dtypes on every
         rank, any number of rows per rank - also zero).  The columns of a rank travel as ONE byte buffer: one size
-        exchange, one H2D copy, one padded `all_gather_into_tensor` over NVLink (gloo in the CPU tests), one D2H copy
-        into a pinned buffer that is kept for the next call.  No pickling, no strings."""
+        exchange, one H2D copy, one padded collective over NVLink (gloo in the CPU tests), one D2H copy.  No pickling,
+        no strings.  dst=None: every rank gets the table (`all_gather_into_tensor`); dst=r: only rank r does (`gather`,
+        the others return None) - the device -> host copy and everything the caller builds from the table then run on
+        one rank with the whole host to itself instead of `world` times side by side."""
         if self.world_size == 1:
             return columns
         import torch
@@ -182,7 +184,7 @@ class DistContext:
         row_bytes = [d.itemsize for d in dtypes]
         n_max = max(sizes)
         if n_max == 0:
-            return {c: columns[c][:0] for c in names}
+            return {c: columns[c][:0] for c in names} if dst is None or dst == self.rank else None
         # local buffer: column after column, every column padded to n_max rows (8-byte aligned starts)
         col_off, off = [], 0
         for rb in row_bytes:
@@ -194,31 +196,27 @@ class DistContext:
             if n_local:
                 a = np.ascontiguousarray(columns[c]).view(np.uint8).reshape(-1)
                 send[o:o + n_local * rb].copy_(torch.from_numpy(a), non_blocking=True)
-        if nccl:
+        mine = dst is None or dst == self.rank
+        if nccl and dst is None:
             full = torch.empty(stride * self.world_size, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(full, send, group=self.group)
-            host = self._pinned(stride * self.world_size)
-            host.copy_(full, non_blocking=False)
-            buf = host.numpy()
-        else:
+        elif dst is None:
             bufs = [torch.empty_like(send) for _ in range(self.world_size)]
             dist.all_gather(bufs, send, group=self.group)
-            buf = torch.cat(bufs).numpy()
-        def own(args):                               # owns its memory: the pinned buffer is reused by the next call
-            o, d = args
-            return np.concatenate([buf[r * stride + o:r * stride + o + sizes[r] * d.itemsize].view(d) for r in range(self.world_size)])
-
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(min(8, len(names))) as pool:       # memcpy releases the GIL
-            return dict(zip(names, pool.map(own, zip(col_off, dtypes))))
-
-    def _pinned(self, n_bytes: int):
-        """Grow-only pinned host buffer (page-locking is the expensive part of a device -> host copy of gigabytes)."""
-        import torch
-        cur = getattr(self, "_pin_buf", None)
-        if cur is None or cur.numel() < n_bytes:
-            self._pin_buf = cur = torch.empty(int(n_bytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
-        return cur[:n_bytes]
+            full = torch.cat(bufs)
+        else:
+            bufs = [torch.empty_like(send) for _ in range(self.world_size)] if mine else None
+            dist.gather(send, bufs, dst=dst, group=self.group)
+            full = torch.cat(bufs) if mine else None
+        if not mine:
+            return None
+        # compact on the device (rank after rank inside every column), then ONE device -> host copy per column straight
+        # into the arrays the caller keeps (pageable: page-locking gigabytes for a one-off copy costs more than it saves)
+        out = {}
+        for c, o, d in zip(names, col_off, dtypes):
+            parts = [full[r * stride + o:r * stride + o + sizes[r] * d.itemsize] for r in range(self.world_size)]
+            out[c] = torch.cat(parts).cpu().numpy().view(d)
+        return out
 
     def all_gather_objects(self, obj):
         if self.world_size == 1:

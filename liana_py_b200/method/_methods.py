@@ -84,9 +84,11 @@ class MethodMeta:
         full_verbose = verbose == 'full'
         samples = list(adata.obs[sample_key].cat.categories)
         dist: Optional[DistContext] = kwargs.pop("dist", None)
-        # engine-only option: gather=False leaves every rank with the frame of ITS block of samples (to be written out
-        # per rank); assembling one pandas frame of all samples on every rank costs far more than computing them
-        gather: bool = kwargs.pop("gather", True)
+        # engine-only option (ranks): gather=True - every rank returns the frame of ALL samples; gather=<rank> (an int) -
+        # only that rank does, the others return None: the 28 M-row frame of 96 samples is then assembled once, with the
+        # whole host to itself, instead of `world` times side by side; gather=False - every rank keeps the frame of ITS
+        # block of samples (to be written out per rank)
+        gather = kwargs.pop("gather", True)
         devices = kwargs.pop("devices", None)
         # category CODES, not the names: `obs[sample_key] == name` over an object array costs ~10 ns per cell and sample
         sample_col = np.asarray(adata.obs[sample_key].cat.codes)
@@ -149,17 +151,20 @@ class MethodMeta:
         mark(f"score {len(parts)} samples", t_all)
         # column names / dtypes of a rank without samples come from the others (tiny object exchange)
         t0 = time.perf_counter()
+        collect = dist is not None and gather is not False
         spec = [(c, parts[0][c].dtype.str) for c in parts[0]] if parts else None
-        if dist is not None and gather:             # a collective: every rank takes part
+        if collect:                                 # a collective: every rank takes part
             spec = next((s for s in dist.all_gather_objects(spec) if s is not None), None)
         if spec is None:                            # no sample on this rank (gather=False) or anywhere
             return pd.DataFrame({sample_key: pd.Series([], dtype=object)})
         local = {c: (np.concatenate([p[c] for p in parts]) if parts else np.zeros(0, dtype=np.dtype(dt))) for c, dt in spec}
         mark("concatenate", t0)
-        if dist is not None and gather:
+        if collect:
             t0 = time.perf_counter()
-            local = dist.all_gather_rows(local)
+            local = dist.all_gather_rows(local, dst=None if gather is True else int(gather))
             mark("all_gather_rows", t0)
+            if local is None:                       # gather=<another rank>
+                return None
         g_tables = dict(g_tables)
         g_tables[sample_key] = pd.Index(samples)
         t0 = time.perf_counter()

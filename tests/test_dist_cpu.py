@@ -132,6 +132,10 @@ def _worker_by_sample(rank, world, port, out_dir):
             single = method.by_sample(sample_inputs(), **kws)
             full = method.by_sample(sample_inputs(), dist=ctx, **kws)
             pd.testing.assert_frame_equal(full, single)
+            at0 = method.by_sample(sample_inputs(), dist=ctx, gather=0, **kws)       # only rank 0 assembles the frame
+            assert (at0 is None) == (rank != 0)
+            if rank == 0:
+                pd.testing.assert_frame_equal(at0, single)
             own = method.by_sample(sample_inputs(), dist=ctx, gather=False, **kws)
             n_own = ctx.all_gather_objects(len(own))
             assert sum(n_own) == len(single) and min(n_own) == 0          # a rank without samples returns an empty frame
