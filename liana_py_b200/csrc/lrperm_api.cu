@@ -922,7 +922,11 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
     // as ITS rows exist (the chunk schedule is tile-major); later batches' slabs are hidden behind the previous batch.
     const int32_t tile_rows = std::max(tile_cells, 1);
     const int32_t n_tiles_run = (int32_t)std::max<int64_t>(1, (N + tile_rows - 1) / tile_rows);
-    const bool slab0_tiled = a.perm_source == LRPERM_PERMS_PHILOX && n_tiles_run > 1 && h->slab0_by_tile;
+    // (measured, scripts/small_shard_ab.py: with <= 256 permutations - one rank's share on 8 GPUs - the tile-wise launches
+    // cost more in partial waves than the hidden slab rows save: 3.94 vs 3.78 ms at 125 permutations; a run that is gated
+    // by a pending upload is tile-wise anyway)
+    const bool slab0_tiled = a.perm_source == LRPERM_PERMS_PHILOX && n_tiles_run > 1 && h->slab0_by_tile &&
+                             (a.n_perms > 256 || h->matrix_pending);
     while (h->ev_slab_tile.size() < (size_t)n_tiles_run) {
         cudaEvent_t ev;
         CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -2343,7 +2347,9 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         // still hold ~16 waves of (chunk x permutation group) warps; 4096 for configs[1], 16384 for configs[2]
         int32_t chunk_nnz = h->fast_chunk_nnz;
         if (!chunk_nnz) {
-            const int64_t groups = 512 / (32 * Q);
+            // (for the nominal 4 permutations per lane whatever Q runs: the chunk table defines the summation order, and
+            // FAST results must not depend on tuning knobs or on the number of GPUs)
+            const int64_t groups = 512 / (32 * 4);
             const int64_t target_items = (int64_t)h->sm_count * 8 * 16;
             int64_t c = h->nnz * groups / std::max<int64_t>(target_items, 1);
             c = std::min<int64_t>(std::max<int64_t>(c, 4096), 16384);

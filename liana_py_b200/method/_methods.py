@@ -217,7 +217,7 @@ class Method(MethodMeta):
 
 def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_lrs, perm_source, order,
                gmean_mode, dist, aggregate_flag=False, null_cache=None, permuting_methods=None,
-               add_cols=None, devices=None) -> pd.DataFrame:
+               add_cols=None, devices=None, reference_quirks=False) -> pd.DataFrame:
     """`_run_method` (`_liana_pipe.py:363-452`) for one method on a prepared PipelineState.
 
     In a consensus (`null_cache` given) every permutation method named in `permuting_methods` is counted
@@ -242,9 +242,14 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
             null = NullCounts(out["cellchat"], n_perms)
             if null_cache is not None:
                 null_cache[key] = null
+            if reference_quirks and aggregate_flag:
+                # the reference's in-place `adata.X /= norm_factor` stays in effect for the methods that follow
+                state.scale_matrix_like_reference(state.prep.mat_max)
         else:
             wanted = {method.engine_score}
-            if null_cache is not None and permuting_methods:
+            # (one pass for all mean-based nulls of a consensus - unless the reference's matrix carry-over is being
+            # reproduced: then every method must see the matrix as it is when ITS turn comes)
+            if null_cache is not None and permuting_methods and not reference_quirks:
                 wanted |= {m.engine_score for m in permuting_methods if m.permute and m.engine_score in ("cpdb", "gmean")}
             oc = PL.observed_cpdb(sub.ligand_means, sub.receptor_means) if "cpdb" in wanted else None
             og = PL.observed_gmean(sub.ligand_means, sub.receptor_means) if "gmean" in wanted else None

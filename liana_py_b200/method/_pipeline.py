@@ -145,6 +145,20 @@ class PipelineState:
         self._cache = {}
         self._replicas = {}
 
+    def scale_matrix_like_reference(self, mat_max):
+        """Reference quirk, reproduced only on request (`reference_quirks=True` of a consensus): CellChat's null divides
+        the SHARED matrix in place, `adata.X /= norm_factor` (`_get_mean_perms.py:43-44`), so every permutation method
+        that runs after CellChat in the same consensus shuffles the scaled matrix (while its observed scores, computed
+        before, stay unscaled).  SciPy evaluates the division as a float32 multiply by the reciprocal; so does this."""
+        recip32, _ = E.Engine.trimean_reciprocals(mat_max)
+        eng = self.engine
+        n, g = eng.N, eng.G
+        ip, ix, dt = eng.export_matrix_csr()
+        eng.set_matrix_csr(ip, ix, (np.asarray(dt, dtype=np.float32) * np.float32(recip32)).astype(np.float32), n, g)
+        eng.set_labels(*self.engine_labels)
+        self._replicas = {}
+        self.matrix_scaled_by = np.float32(recip32)
+
     def replicas(self, devices) -> list:
         """Engines of `devices` (CUDA indices) that hold this state's matrix and labels; the first entry is the state's
         own engine.  The committed matrix is exported once on its device and copied to the others device to device

@@ -54,7 +54,12 @@ class AggregateClass(MethodMeta):
                  mdata_kwargs: dict = dict(), inplace: bool = V.inplace, verbose: Optional[bool] = V.verbose,
                  *, perm_source: Optional[str] = None, order: Optional[str] = None, gmean_mode: str = "product",
                  device: int = 0, dist: Optional[DistContext] = None, devices: Optional[list] = None,
-                 _names: bool = True):
+                 reference_quirks: bool = False, _names: bool = True):
+        """`reference_quirks=True` (engine-only, validation): reproduce the one known side effect of the reference's
+        consensus - CellChat's null scales the shared matrix in place (`_get_mean_perms.py:43-44`), so the permutation
+        methods that run AFTER CellChat in `methods` shuffle `X / mat_max` against unscaled observed scores.  Default
+        False: every method's null is computed on the matrix the caller passed (what the reference does for any
+        consensus without CellChat, e.g. the default `rank_aggregate`)."""
         device, devices = PL.resolve_devices(device, devices)
         if n_perms is None:
             consensus_opts = "Magnitude"                       # `_liana_pipe.py:108-109`
@@ -70,7 +75,7 @@ class AggregateClass(MethodMeta):
             lrs[method.method_name] = run_method(state, meta, expr_prop, n_perms, seed, return_all_lrs, perm_source,
                                                  order, gmean_mode, dist, aggregate_flag=True, null_cache=null_cache,
                                                  permuting_methods=[getattr(m, "_method", m) for m in self.methods],
-                                                 devices=devices)
+                                                 devices=devices, reference_quirks=reference_quirks)
         if consensus_opts is False:                             # per-method results as they are (`:220-221`)
             return {k: PL.materialise_names(state, v) for k, v in lrs.items()}
         # the reference outer-merges the per-method frames on the key columns (`_aggregate.py:39-49`);

@@ -248,6 +248,14 @@ def save_variants(ref):
                                  use_raw=False, **kw)
         res.to_csv(os.path.join(OUT, f"variant_{tag}_rank_aggregate.csv.gz"), index=False)
         print(f"variant {tag} rank_aggregate: {res.shape}")
+    # a custom consensus that contains CellChat: its null scales the shared matrix in place (`_get_mean_perms.py:43-44`),
+    # so geometric_mean - which runs after it - is shuffled on X / mat_max (the drop-in's `reference_quirks=True`)
+    adata, _ = variant_inputs()
+    RA = ref.rank_aggregate_mod
+    agg = RA.AggregateClass(RA._rank_aggregate_meta, methods=[ref.cellphonedb, ref.cellchat, ref.geometric_mean])
+    res = agg(adata.copy(), groupby="cluster", n_perms=16, seed=3, inplace=False, verbose=False, use_raw=False)
+    res.to_csv(os.path.join(OUT, "variant_cellchat_consensus_rank_aggregate.csv.gz"), index=False)
+    print(f"variant cellchat consensus: {res.shape}, mean gmean pval {res['gmean_pvals'].mean():.4f}")
     # tied subunits: the reference's tie rule decides which subunit represents a complex
     adata, n_tied = ties_inputs()
     for name, fn in (("cellphonedb", ref.cellphonedb), ("cellchat", ref.cellchat)):

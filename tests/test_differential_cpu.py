@@ -400,3 +400,30 @@ def test_unsorted_row_order_is_the_references(seed):
         for col in b.columns:
             if col not in KEY:
                 np.testing.assert_array_equal(a[col].values, b[col].values)
+
+
+def test_cellchat_in_a_consensus_matrix_carry_over():
+    """The reference's CellChat null divides the shared matrix in place (`adata.X /= norm_factor`,
+    `_get_mean_perms.py:43-44`): in a consensus, the permutation methods that run AFTER CellChat shuffle X / mat_max
+    against their unscaled observed scores.  The drop-in computes every null on the matrix the caller passed (default,
+    pinned here: p-values equal the stand-alone method's) and reproduces the reference's behaviour with
+    `reference_quirks=True` (p-values identical to the reference's consensus)."""
+    ref = ref_shim.load_reference()
+    RA = ref.rank_aggregate_mod
+    adata = make_synthetic_adata(160, 420, 4, density=0.2, seed_data=15, seed_labels=16)
+    kw = dict(groupby="cluster", use_raw=False, inplace=False, verbose=False, n_perms=8, seed=3)
+    ref_methods = [ref.cellphonedb, ref.cellchat, ref.geometric_mean]
+    own_methods = [li.mt.cellphonedb, li.mt.cellchat, li.mt.geometric_mean]
+    want = RA.AggregateClass(RA._rank_aggregate_meta, methods=ref_methods)(adata.copy(), **kw).sort_values(KEY).reset_index(drop=True)
+    agg = li.mt.AggregateClass(li.mt.aggregate_meta, methods=own_methods)
+    quirk = agg(adata.copy(), perm_source="reference", reference_quirks=True, **kw).sort_values(KEY).reset_index(drop=True)
+    plain = agg(adata.copy(), perm_source="reference", **kw).sort_values(KEY).reset_index(drop=True)
+    alone = li.mt.geometric_mean(adata.copy(), perm_source="reference", **kw).sort_values(KEY).reset_index(drop=True)
+    assert list(quirk.columns) == list(want.columns) and len(quirk) == len(want)
+    for c in ("cellphone_pvals", "cellchat_pvals", "gmean_pvals"):
+        assert np.array_equal(quirk[c].values, want[c].values), c            # the reference's consensus, reproduced
+    # before CellChat nothing differs; after it the reference's null is computed on the scaled matrix
+    assert np.array_equal(plain["cellphone_pvals"].values, want["cellphone_pvals"].values)
+    assert np.array_equal(plain["cellchat_pvals"].values, want["cellchat_pvals"].values)
+    assert np.array_equal(plain["gmean_pvals"].values, alone["gmean_pvals"].values)   # default: the stand-alone method's p-values
+    assert not np.array_equal(plain["gmean_pvals"].values, want["gmean_pvals"].values)

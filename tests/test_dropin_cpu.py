@@ -74,6 +74,10 @@ def test_consensus_options():
     G.test_consensus_options_identical_to_reference()
 
 
+def test_consensus_containing_cellchat():
+    G.test_consensus_containing_cellchat_reference_quirk()
+
+
 def test_error_conventions_and_empty_result():
     G.test_error_conventions()
     G.test_nothing_expressed_gives_an_empty_frame()

@@ -539,3 +539,27 @@ def test_devices_kwarg_equals_single_gpu():
         pd.testing.assert_frame_equal(fn(adata, devices=devices, **kw), fn(adata, **kw))
     pd.testing.assert_frame_equal(li.mt.cellphonedb.by_sample(adata, "sample", devices=devices, **kw),
                                   li.mt.cellphonedb.by_sample(adata, "sample", **kw))
+
+
+def test_consensus_containing_cellchat_reference_quirk():
+    """A custom consensus [cellphonedb, cellchat, geometric_mean]: the reference's CellChat null scales the shared matrix
+    in place (`_get_mean_perms.py:43-44`), so geometric_mean - which runs after it - is shuffled on X / mat_max against
+    its unscaled observed scores.  `reference_quirks=True` reproduces the reference's frame (fixture from its own code);
+    the default computes every null on the caller's matrix: geometric_mean's p-values are the stand-alone method's."""
+    from variants import variant_inputs
+    adata, _ = variant_inputs()
+    kw = dict(groupby="cluster", n_perms=16, seed=3, inplace=False, perm_source="reference", use_raw=False)
+    agg = li.mt.AggregateClass(li.mt.aggregate_meta, methods=[li.mt.cellphonedb, li.mt.cellchat, li.mt.geometric_mean])
+    gold = pd.read_csv(os.path.join(GOLDEN, "variant_cellchat_consensus_rank_aggregate.csv.gz"), float_precision="round_trip")
+    quirk = agg(adata, reference_quirks=True, **kw)
+    assert list(quirk.columns) == list(gold.columns) and len(quirk) == len(gold)
+    a, b = quirk.sort_values(KEY).reset_index(drop=True), gold.sort_values(KEY).reset_index(drop=True)
+    for c in ("cellphone_pvals", "cellchat_pvals", "gmean_pvals"):
+        assert np.array_equal(a[c].values, b[c].values), c
+    for c in ("lr_means", "lr_probs", "lr_gmeans"):
+        np.testing.assert_allclose(a[c].values, b[c].values, rtol=1e-6, atol=0)
+    plain = agg(adata, **kw).sort_values(KEY).reset_index(drop=True)
+    alone = li.mt.geometric_mean(adata, **kw).sort_values(KEY).reset_index(drop=True)
+    assert np.array_equal(plain["cellphone_pvals"].values, b["cellphone_pvals"].values)
+    assert np.array_equal(plain["gmean_pvals"].values, alone["gmean_pvals"].values)
+    assert not np.array_equal(plain["gmean_pvals"].values, b["gmean_pvals"].values)
