@@ -427,7 +427,9 @@ int csc_begin(lrperm_engine* h, int32_t tile_cells) {
     CK(h->csc_keys.ensure(sizeof(uint32_t) * n1));                // column keys
     CK(h->csc_keys2.ensure(sizeof(uint32_t) * n1));               // sorted keys (discarded)
     CK(h->csc_payload.ensure(sizeof(unsigned long long) * n1));   // payload {cell, value bits}
-    CK(h->csc_pairs.ensure(sizeof(int2) * n1));
+    // + 64 zero entries behind the last one: fast3_means_kernel (bulk copies of whole 32-entry blocks) may read past the end
+    CK(h->csc_pairs.ensure(sizeof(int2) * (n1 + 64)));
+    CK(cudaMemsetAsync(h->csc_pairs.as<int2>() + n1, 0, sizeof(int2) * 64, h->stream));
     const size_t hist_elems = (size_t)h->n_tiles * (size_t)G;
     CK(h->tile_hist.ensure(sizeof(int32_t) * hist_elems));
     CK(h->hist_pin.ensure(sizeof(int32_t) * hist_elems));
@@ -774,6 +776,22 @@ int launch_fast2_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* par
     return LRPERM_OK;
 }
 
+template <int Q, int R>
+int launch_fast3_q(lrperm_engine* h, int32_t PB, const uint8_t* slab, float* partials, const FastChunk* table, int32_t c0, int32_t cn) {
+    const int32_t L = h->L;
+    const size_t smem = (size_t)L * Q * 128 + (size_t)R * 32 * sizeof(int2) + (size_t)R * 8;
+    CK(cudaFuncSetAttribute(fast3_means_kernel<Q, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int32_t groups = PB / (32 * Q);
+    const int64_t grid = (int64_t)cn * groups;
+    if (grid > 0x7fffffffLL) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: too many chunks (%lld CTAs)", (long long)grid);
+    if (grid > 0) {
+        fast3_means_kernel<Q, R><<<(unsigned)grid, 32, smem, h->stream>>>(
+            h->csc_pairs.as<int2>(), table + c0, cn, slab, PB, L, groups, partials);
+        CK_LAUNCH();
+    }
+    return LRPERM_OK;
+}
+
 // v2 kernel: permutations per lane.  The slab byte is label*Q/2 (must fit 8 bits) and the bins take
 // L*Q*128 B of shared memory per warp; more, smaller CTAs hide the LDS->FADD->STS chain better.
 int pick_q2(const lrperm_engine* h) {
@@ -834,7 +852,8 @@ int launch_score_t(lrperm_engine* h, int scores, const float* cube, int32_t PP, 
 int launch_fast_any(lrperm_engine* h, int Q, int32_t PB, const uint8_t* slab, float* partials, bool filt, int32_t c0 = 0, int32_t cn = -1) {
     const FastChunk* table = filt ? h->chunks_f.as<FastChunk>() : h->chunks.as<FastChunk>();
     if (cn < 0) cn = (filt ? (int32_t)h->h_chunks_f.size() : h->n_chunks) - c0;
-    if (h->fast_variant == 2) {
+    if (h->fast_variant == 3 && Q == 4) return launch_fast3_q<4, 4>(h, PB, slab, partials, table, c0, cn);
+    if (h->fast_variant >= 2) {
         if (Q == 8) return launch_fast2_q<8, 16>(h, PB, slab, partials, table, c0, cn);
         if (Q == 4) return launch_fast2_q<4, 32>(h, PB, slab, partials, table, c0, cn);
         return launch_fast2_q<2, 32>(h, PB, slab, partials, table, c0, cn);
@@ -881,7 +900,7 @@ std::vector<int32_t> batch_schedule(int64_t n_perms, int32_t PB, int32_t gran, i
 int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, const uint8_t* slab_labels,
                        int32_t chunk_nnz, int32_t tile_cells) {
     const int64_t N = h->N;
-    const int32_t label_scale = h->fast_variant == 2 ? Q / 2 : 1;
+    const int32_t label_scale = h->fast_variant >= 2 ? Q / 2 : 1;
     const int32_t G = (int32_t)h->G, L = h->L;
     const int32_t gran = std::max(128, 32 * Q);
     // option "fast_first_batch": a short first batch would shorten the slab prologue that nothing overlaps.  Measured
@@ -1622,7 +1641,7 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     if (!h || !name) return LRPERM_ERR_INVALID;
     const std::string key(name);
     if (key == "fast_variant") {
-        if (value != 1 && value != 2) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_variant must be 1 or 2");
+        if (value != 1 && value != 2 && value != 3) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_variant must be 1, 2 or 3");
         h->fast_variant = (int32_t)value;
     } else if (key == "overlap") {
         if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: overlap must be 0 or 1");
@@ -2336,7 +2355,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     int32_t fast_chunk = 0, fast_tile = 0;
     if (order_mode == LRPERM_ORDER_FAST) {
         if (L > 255) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode supports at most 255 clusters (got %d); use EXACT", L);
-        Q = h->fast_variant == 2 ? pick_q2(h) : pick_q(h);
+        Q = h->fast_variant >= 2 ? pick_q2(h) : pick_q(h);
         if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: %d clusters do not fit the shared-memory bins", L);
         PB = h->fast_perm_batch ? h->fast_perm_batch : 512;
         const int32_t gran = std::max(128, 32 * Q);        // a warp covers 32*Q permutations
@@ -2382,8 +2401,8 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
     if (scores & LRPERM_SCORE_GMEAN) CK(cudaMemsetAsync(h->counts_g.p, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(T, 1), h->stream));
 
     const uint8_t* slab_labels = h->labels8.as<uint8_t>();
-    const int32_t label_scale = (order_mode == LRPERM_ORDER_FAST && h->fast_variant == 2) ? Q / 2 : 1;
-    if (order_mode == LRPERM_ORDER_FAST && h->fast_variant == 2) {
+    const int32_t label_scale = (order_mode == LRPERM_ORDER_FAST && h->fast_variant >= 2) ? Q / 2 : 1;
+    if (order_mode == LRPERM_ORDER_FAST && h->fast_variant >= 2) {
         const int32_t scale = Q / 2;
         if (h->labels8s_scale != scale) {
             CK(h->labels8s.ensure((size_t)std::max<int64_t>(N, 1)));

@@ -960,6 +960,125 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// FAST mode, step 2 (v3, EXPERIMENT - option "fast_variant" = 3): fast2_means_kernel with the {cell, value} entries
+// brought into shared memory by the bulk-copy engine instead of the LSU.  One elected lane issues
+// `cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes` (1-D TMA, SASS: UBLKCP) for a ring of R blocks of
+// B = 32 entries (256 B each); an mbarrier per ring slot counts the arriving bytes, the warp waits on its phase bit,
+// reads the block back as 128-bit broadcasts ({cell, value} x 2 per load) and re-arms the slot for block j + R.  Against
+// v2 this takes the entry LDG (2 wavefronts per block) and the STS staging (2 wavefronts + 2 __syncwarp) off the
+// LSU / shared-memory path; the bin read-modify-write (256 wavefronts per block) and the label words (32) stay.
+// Bulk copies need 16-byte aligned addresses: the chunk is walked from its even-aligned start, and the (at most 1 + 31)
+// entries outside [begin, end) that the first / last block carries get the value +0.0f (their cells are valid cells of
+// the neighbouring chunks, or the zero padding behind the last entry, so the label loads stay in bounds).
+// Same summation order as v2 -> bit-identical results (scripts/fast_ab.py, tests).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr_u32(dst)), "l"(src), "r"(bytes), "r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int Q, int R>
+__global__ void __launch_bounds__(32)
+fast3_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restrict__ chunks, int32_t n_chunks,
+                   const uint8_t* __restrict__ slab, int32_t PB, int32_t L, int32_t groups_per_batch,
+                   float* __restrict__ partials /*[slot][L][PB]*/) {
+    extern __shared__ __align__(16) unsigned char smem2[];
+    using LV = typename LabelVec<Q>::type;
+    constexpr int B = 32;
+    const int lane = threadIdx.x;
+    const int chunk_id = (int)(blockIdx.x / (unsigned)groups_per_batch);
+    const int group = (int)(blockIdx.x - (unsigned)chunk_id * (unsigned)groups_per_batch);
+    const FastChunk ch = chunks[chunk_id];
+    const int bins_bytes = L * Q * 128;
+    unsigned char* bins = smem2;
+    int2* ring = reinterpret_cast<int2*>(smem2 + bins_bytes);                               // [R][B]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem2 + bins_bytes + R * B * (int)sizeof(int2));   // [R]
+    {
+        float4* z = reinterpret_cast<float4*>(bins);
+        for (int i = lane; i < L * Q * 8; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int ka = ch.begin & ~1;                                   // 16-byte aligned start of the walk
+    const int nblk = (ch.end - ka + B - 1) / B;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) mbar_init(&mbar[r], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r < nblk) {
+                mbar_expect_tx(&mbar[r], B * (uint32_t)sizeof(int2));
+                bulk_copy_g2s(ring + r * B, csc_pairs + ka + r * B, B * (uint32_t)sizeof(int2), &mbar[r]);
+            }
+    }
+    __syncwarp();
+    const LV* __restrict__ slab_w = reinterpret_cast<const LV*>(slab) + (group * 32 + lane);
+    const int64_t row_words = PB / Q;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+
+    auto fetch = [&](int j, LV (&lw)[B], float (&vv)[B]) {
+        const int slot = j % R;
+        mbar_wait(&mbar[slot], (uint32_t)((j / R) & 1));
+        if (j == 0 || j == nblk - 1) {                              // entries outside [begin, end): value +0.0f
+            const int idx = ka + j * B + lane;
+            if (idx < ch.begin || idx >= ch.end) ring[slot * B + lane].y = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int u = 0; u < B; u += 2) {
+            const int4 c4 = *reinterpret_cast<const int4*>(ring + slot * B + u);
+            lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
+            lw[u + 1] = __ldg(slab_w + (int64_t)c4.z * row_words);
+            vv[u + 0] = __int_as_float(c4.y);
+            vv[u + 1] = __int_as_float(c4.w);
+        }
+        __syncwarp();                                               // every lane has read the slot: re-arm it
+        if (lane == 0 && j + R < nblk) {
+            mbar_expect_tx(&mbar[slot], B * (uint32_t)sizeof(int2));
+            bulk_copy_g2s(ring + slot * B, csc_pairs + ka + (j + R) * B, B * (uint32_t)sizeof(int2), &mbar[slot]);
+        }
+    };
+    auto update = [&](const LV (&lw)[B], const float (&vv)[B]) {
+#pragma unroll
+        for (int u = 0; u < B; ++u) fast2_update<Q>(bins, lane4, lw[u], vv[u]);
+    };
+
+    LV lwA[B], lwB[B];
+    float vA[B], vB[B];
+    fetch(0, lwA, vA);
+    for (int j = 0; j < nblk; j += 2) {
+        const bool more1 = j + 1 < nblk;
+        if (more1) fetch(j + 1, lwB, vB);
+        update(lwA, vA);
+        if (!more1) break;
+        if (j + 2 < nblk) fetch(j + 2, lwA, vA);
+        update(lwB, vB);
+    }
+    __syncwarp();
+    const float* mybins = reinterpret_cast<const float*>(bins) + lane;
+    float* out = partials + (int64_t)ch.slot * L * PB + group * 32 * Q + lane * Q;
+    for (int c = 0; c < L; ++c) {
+        float vals[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) vals[q] = mybins[(c * Q + q) * 32];
+        float* dst = out + (int64_t)c * PB;
+#pragma unroll
+        for (int q = 0; q < Q; q += 4)
+            __stcs(reinterpret_cast<float4*>(dst + q), make_float4(vals[q], vals[(q + 1) % Q], vals[(q + 2) % Q], vals[(q + 3) % Q]));
+    }
+}
+
 // FAST mode, step 3: combine a gene's chunk partials in fixed order (cell tiles ascending, chunks ascending inside a
 // tile: slots are numbered tile by tile, tile_slot_ptr[t][g] .. [t][g+1] are gene g's slots in tile t), scale by
 // 1/n_c, write cube.

@@ -8,8 +8,9 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
 N, G, L = {"c2": (50000, 1877, 20), "c3": (500000, 1877, 50), "c4": (200000, 1877, 40)}[cfg]
 Pf = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 Pe = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+variant = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 indptr, indices, data, labels = synthetic_csr_torch(N, G, L, 0.08)
-eng = E.Engine(0); eng.set_matrix_csr(indptr, indices, data, N, G); eng.set_labels(labels, L)
+eng = E.Engine(0); eng.set_option("fast_variant", variant); eng.set_matrix_csr(indptr, indices, data, N, G); eng.set_labels(labels, L)
 rng = np.random.default_rng(0); T = 1_000_000
 lig, rec, src, tgt = rng.integers(0, G, T), rng.integers(0, G, T), rng.integers(0, L, T), rng.integers(0, L, T)
 eng.set_triples(lig, rec, src, tgt, np.ones(T, np.float32), None)
