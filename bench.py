@@ -750,14 +750,14 @@ def run_reference(args):
               L=full["L"], nnz=int(X.nnz), T=int(len(obs)), T_max=int(tables.lig_sub.shape[0]) * full["L"] ** 2, tri=tri, obs=obs)
     P, T = args.n_perms, wl["T"]
     n_jobs = max(1, min(os.cpu_count() or 1, 32))
-    budget = max(5.0, min(args.cpu_budget, 60.0))
+    # every step is a bounded sample of the workload; the whole `--steps K --warmup W` run is sized to ~2 minutes of sampling
+    n_iter = max(1, args.warmup + args.steps)
+    budget = max(2.0, min(args.cpu_budget, 120.0 / n_iter))
     vals, last = [], None
-    for i in range(args.warmup + args.steps):
+    for i in range(n_iter):
         last = cpu_baseline((X, labels, genes), wl, P, n_jobs=n_jobs, budget_s=budget)
         if i >= args.warmup:
             vals.append(last["value"])
-        if i == 0 and args.warmup + args.steps > 2:
-            budget = max(5.0, budget / 2)
     value = float(np.mean(vals))
     last["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
