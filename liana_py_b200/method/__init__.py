@@ -3,7 +3,7 @@ non-permutation methods the default consensus ranks (connectome, logfc, natmi, s
 from ._methods import Method, MethodMeta, NullCounts, cellphonedb, geometric_mean, cellchat  # noqa: F401
 from ._scores import connectome, logfc, natmi, singlecellsignalr, scseqcomm  # noqa: F401
 from ._rank_aggregate import AggregateClass, aggregate_meta, rank_aggregate  # noqa: F401
-from ._dist import DistContext  # noqa: F401
+from ._dist import DistContext, bind_to_gpu_numa  # noqa: F401
 
 
 def show_methods():

@@ -10,6 +10,29 @@ from __future__ import annotations
 import numpy as np
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Restrict this process (and the threads it starts later: the engine's upload threads) to the CPU cores NVML
+    reports as local to the GPU.  With one process per GPU on a two-socket host, the pageable -> pinned staging copies
+    of an upload then stay on the socket the GPU hangs off instead of crossing the inter-socket link.  Call it before
+    the big host arrays are allocated (first touch puts them on the local node).  Returns False when NVML or
+    `sched_setaffinity` is not available; nothing else changes then."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return False
+        os.sched_setaffinity(0, allowed)
+        return True
+    except Exception:
+        return False
+
+
 class DistContext:
     def __init__(self, rank: int = 0, world_size: int = 1, device=None, group=None):
         self.rank, self.world_size, self.device, self.group = rank, world_size, device, group

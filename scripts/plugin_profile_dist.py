@@ -11,6 +11,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
+print("numa bound:", li.mt.bind_to_gpu_numa(local) if os.environ.get("BIND_NUMA", "1") == "1" else "off", file=sys.stderr)
 dist.init_process_group("nccl", device_id=dev)
 ctx = li.mt.DistContext.from_torch()
 adata = bench.host_adata(bench.gen_full(name, dev))
