@@ -203,16 +203,57 @@ class Method(MethodMeta):
                            use_raw, layer, verbose, device=device, base=base, want_max=K.MAT_MAX in add_cols,
                            want_cluster_stats=("ligand_cdf" in add_cols) or ("receptor_cdf" in add_cols),
                            mdata_kwargs=mdata_kwargs, dist=dist)
-        liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
-                               perm_source, order, gmean_mode, dist, add_cols=add_cols, devices=devices)
         orderby, ascending = (self.magnitude, self.magnitude_ascending) if self.magnitude is not None \
             else (self.specificity, self.specificity_ascending)             # `_liana_pipe.py:246-250`
+        if (_names and self.permute and n_perms is not None and self.magnitude is not None and not return_all_lrs
+                and (dist is None or dist.world_size == 1) and devices is None):
+            liana_res = _call_overlapped(state, self._method, expr_prop, n_perms, seed, perm_source, order, gmean_mode, add_cols)
+            if liana_res is not None:
+                if inplace:
+                    adata.uns[key_added] = liana_res
+                return None if inplace else liana_res
+        liana_res = run_method(state, self._method, expr_prop, n_perms, seed, return_all_lrs,
+                               perm_source, order, gmean_mode, dist, add_cols=add_cols, devices=devices)
         if not _names:                          # by_sample: (sorted numeric columns, prepared state), see `_by_sample_blocks`
             return PL.sorted_code_columns(state.engine, liana_res, orderby, ascending), state
         liana_res = PL.finish_frame(state, liana_res, orderby, ascending)
         if inplace:
             adata.uns[key_added] = liana_res
         return None if inplace else liana_res
+
+
+_NULL_POOL = None
+
+
+def _call_overlapped(state, method, expr_prop, n_perms, seed, perm_source, order, gmean_mode, add_cols):
+    """One permutation method, result frame assembled WHILE the permutations run.  The frame is sorted by the magnitude
+    (`_liana_pipe.py:246-250`), which does not depend on the null: the row order is taken first (device argsort), the
+    null is started on a worker thread (the C ABI call releases the GIL; nothing else touches the engine until it
+    returns), the main thread gathers every column in that order and builds the name columns, and the p-values join
+    at the end.  Same frame as `run_method` + `finish_frame`; None when the shortcut does not apply (few rows, NaN keys)."""
+    global _NULL_POOL
+    stat = "trimean" if K.LIGAND_TRIMEAN in method.complex_cols else "means"
+    tri, lr_res = state.resolved(expr_prop, False, stat)
+    if add_cols:
+        lr_res = PL.add_method_columns(state, tri, lr_res, add_cols)
+        lr_res = lr_res[sorted(lr_res.columns)]
+    magnitude = method.fun(lr_res, None)[0]
+    vals = np.asarray(magnitude, dtype=np.float64)
+    if state.engine is None or len(vals) < 4096 or np.isnan(vals).any():
+        return None
+    row_order = state.engine.argsort(vals, descending=not method.magnitude_ascending)
+    if _NULL_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _NULL_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="lrperm-null")
+    fut = _NULL_POOL.submit(_compute_null, state, method, tri, tri.keep, expr_prop, n_perms, seed, False, perm_source, order,
+                            gmean_mode, None)
+    try:
+        cols = PL.gather_columns(state, lr_res, row_order)
+        cols[method.magnitude] = np.asarray(magnitude).take(row_order)
+    finally:
+        null = fut.result()                      # the engine is free again (also when the gather failed)
+    cols[method.specificity] = null.pvals().take(row_order)
+    return pd.DataFrame(cols, index=pd.Index(row_order), copy=False)
 
 
 def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_lrs, perm_source, order,
@@ -230,6 +271,35 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
         lr_res = lr_res[sorted(lr_res.columns)]            # `np.union1d` of the column sets (`_liana_pipe.py:385`)
     kept = tri.keep
     x = lr_res[kept] if return_all_lrs else lr_res
+    null = _compute_null(state, method, tri, kept, expr_prop, n_perms, seed, return_all_lrs, perm_source, order, gmean_mode,
+                         dist, aggregate_flag, null_cache, permuting_methods, devices, reference_quirks)
+    magnitude, specificity = method.fun(x, null) if method.permute else method.fun(x)
+    spec_name = method.specificity if (not method.permute or n_perms is not None) else None
+    # the cached base frame stays untouched: a shallow copy shares its (never written) columns, the score columns
+    # added below are new arrays owned by the copy
+    lr_res = (lr_res[K.PRIMARY] if aggregate_flag else lr_res).copy(deep=False)
+    if return_all_lrs:
+        lr_res[K.LRS_TO_KEEP] = kept
+    if method.magnitude is not None:
+        lr_res[method.magnitude] = _scatter(magnitude, kept, return_all_lrs)
+    if spec_name is not None:
+        lr_res[spec_name] = _scatter(specificity, kept, return_all_lrs)
+    if return_all_lrs:
+        # rows that failed expr_prop get the worst kept value (`_liana_pipe.py:433-443`)
+        for col, asc in ((method.magnitude, method.magnitude_ascending), (spec_name, method.specificity_ascending)):
+            if col is not None:
+                vals = lr_res[col]
+                lr_res.loc[~kept, col] = vals.max() if asc else vals.min()
+    if aggregate_flag:
+        cols = K.PRIMARY + [c for c in (method.magnitude, spec_name) if c is not None]
+        lr_res = lr_res[cols]
+    return lr_res
+
+
+def _compute_null(state, method, tri, kept, expr_prop, n_perms, seed, return_all_lrs, perm_source, order, gmean_mode,
+                  dist, aggregate_flag=False, null_cache=None, permuting_methods=None, devices=None, reference_quirks=False):
+    """The permutation null of one method (`_liana_pipe.py:402-419`): exceedance counts from the engine, or None for a
+    method without permutations / `n_perms=None`."""
     null = None
     if method.permute and n_perms is not None:
         sub = tri if not return_all_lrs else _subset(tri, kept)
@@ -259,27 +329,7 @@ def run_method(state, method: MethodMeta, expr_prop, n_perms, seed, return_all_l
                     if name in out:
                         null_cache[(name,) + key[1:]] = NullCounts(out[name], n_perms)
             null = NullCounts(out[method.engine_score], n_perms)
-    magnitude, specificity = method.fun(x, null) if method.permute else method.fun(x)
-    spec_name = method.specificity if (not method.permute or n_perms is not None) else None
-    # the cached base frame stays untouched: a shallow copy shares its (never written) columns, the score columns
-    # added below are new arrays owned by the copy
-    lr_res = (lr_res[K.PRIMARY] if aggregate_flag else lr_res).copy(deep=False)
-    if return_all_lrs:
-        lr_res[K.LRS_TO_KEEP] = kept
-    if method.magnitude is not None:
-        lr_res[method.magnitude] = _scatter(magnitude, kept, return_all_lrs)
-    if spec_name is not None:
-        lr_res[spec_name] = _scatter(specificity, kept, return_all_lrs)
-    if return_all_lrs:
-        # rows that failed expr_prop get the worst kept value (`_liana_pipe.py:433-443`)
-        for col, asc in ((method.magnitude, method.magnitude_ascending), (spec_name, method.specificity_ascending)):
-            if col is not None:
-                vals = lr_res[col]
-                lr_res.loc[~kept, col] = vals.max() if asc else vals.min()
-    if aggregate_flag:
-        cols = K.PRIMARY + [c for c in (method.magnitude, spec_name) if c is not None]
-        lr_res = lr_res[cols]
-    return lr_res
+    return null
 
 
 def _scatter(values, kept, return_all_lrs):

@@ -509,6 +509,20 @@ def finish_frame(state: PipelineState, frame: pd.DataFrame, by: str, ascending: 
     return pd.DataFrame(dict(zip(cols, done)), index=pd.Index(order), copy=False)
 
 
+def gather_columns(state: PipelineState, frame: pd.DataFrame, order: np.ndarray) -> dict:
+    """Every column of a code frame gathered in `order` as a finished 1-D array (name columns materialised), through the
+    thread pool - the column loop of `finish_frame`, usable while the engine is busy (it touches no device)."""
+    lookup = name_tables(state)
+    cols = list(frame.columns)
+    arrays = [frame[c].values for c in cols]
+
+    def gather(i):
+        v = arrays[i].take(order)
+        return _take_names(lookup[cols[i]], v) if cols[i] in lookup else v
+
+    return dict(zip(cols, _frame_pool().map(gather, range(len(cols)))))
+
+
 def add_method_columns(state: PipelineState, tri: _tables.ResolvedTriples, frame: pd.DataFrame, add_cols) -> pd.DataFrame:
     """Method-specific statistic columns of the rows in `tri` (the resolved min-subunit gene of every row
     carries its own statistics through `filter_reassemble_complexes`, `_reassemble_complexes.py:60-66`)."""

@@ -100,3 +100,7 @@ def test_by_sample_of_other_methods(method):
 
 def test_tied_subunits():
     G.test_tied_subunits_resolved_like_the_reference()
+
+
+def test_overlapped_frame_assembly():
+    G.test_overlapped_frame_assembly_equals_plain_path()

@@ -563,3 +563,21 @@ def test_consensus_containing_cellchat_reference_quirk():
     assert np.array_equal(plain["cellphone_pvals"].values, b["cellphone_pvals"].values)
     assert np.array_equal(plain["gmean_pvals"].values, alone["gmean_pvals"].values)
     assert not np.array_equal(plain["gmean_pvals"].values, b["gmean_pvals"].values)
+
+
+def test_overlapped_frame_assembly_equals_plain_path():
+    """`Method.__call__` assembles the sorted frame while the permutations run (>= 4096 rows): same frame as
+    `run_method` + `finish_frame`, column for column, index included."""
+    from liana_py_b200.method import _methods as M, _pipeline as PL
+    from liana_py_b200.testing._synth import make_synthetic_adata
+    adata = make_synthetic_adata(400, 900, 6, density=0.3, seed_data=3, seed_labels=4)
+    for fn in (li.mt.cellphonedb, li.mt.geometric_mean, li.mt.cellchat):
+        kw = dict(groupby="cluster", use_raw=False, n_perms=5, seed=1, inplace=False)
+        got = fn(adata, **kw)
+        assert len(got) >= 4096
+        add_cols = PL.method_columns(fn.add_cols, None)
+        state = PL.prepare(adata, "cluster", "consensus", None, None, None, 5, False, None, False,
+                           want_max="mat_max" in add_cols)
+        plain = M.run_method(state, fn._method, 0.1, 5, 1, False, None, None, "product", None, add_cols=add_cols)
+        plain = PL.finish_frame(state, plain, fn.magnitude, fn.magnitude_ascending)
+        pd.testing.assert_frame_equal(got, plain)
