@@ -288,7 +288,9 @@ int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_ch
  *   "fast_first_batch"    permutations of a short first batch of the pipelined FAST path (0 = none, default)
  *   "trimean_chunk_nnz"   stored entries per chunk of the trimean path (0 = auto; multiple of 1024)
  *   "trimean_perm_batch"  permutations per batch of the trimean path (0 = auto; multiple of 128)
- *   "skip_unreferenced"   1 (default) = runs that export no cube skip the genes no triple reads (see lrperm_run_stats)  */
+ *   "skip_unreferenced"   1 (default) = runs that export no cube skip the genes no triple reads (see lrperm_run_stats)
+ *   "narrow_indices"      1 (default) = lrperm_stage_matrix_csr sends the column indices of a large pageable upload as 16 bits
+ *                         (n_genes <= 65536): less host memory traffic and PCIe volume; same staged matrix  */
 int lrperm_set_option(lrperm_engine *h, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -103,16 +103,29 @@ public:
         cv_.notify_all();
         for (auto& t : workers_) t.join();
     }
-    void copy(void* dst, const void* src, size_t bytes) {
-        if (bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    // narrow = false: memcpy of `bytes`.  narrow = true: `bytes` OUTPUT bytes of uint16 written from bytes / 2 int32 inputs
+    // (column indices < 65536 travel over PCIe at half their size); returns the OR of the inputs' high halves, i.e.
+    // non-zero when an index was negative or >= 65536 (it would not survive the narrowing).
+    uint32_t copy(void* dst, const void* src, size_t bytes, bool narrow = false) {
+        if (bytes < (1u << 20)) {
+            if (!narrow) { memcpy(dst, src, bytes); return 0; }
+            return narrow_slice(static_cast<uint16_t*>(dst), static_cast<const int32_t*>(src), bytes / 2);
+        }
         {
             std::lock_guard<std::mutex> lk(m_);
             dst_ = static_cast<unsigned char*>(dst); src_ = static_cast<const unsigned char*>(src); bytes_ = bytes;
+            narrow_ = narrow; bad_ = 0;
             pending_ = n_; ++gen_;
         }
         cv_.notify_all();
         std::unique_lock<std::mutex> lk(m_);
         done_.wait(lk, [this] { return pending_ == 0; });
+        return bad_;
+    }
+    static uint32_t narrow_slice(uint16_t* d, const int32_t* s, size_t n) {
+        uint32_t bad = 0;
+        for (size_t i = 0; i < n; ++i) { const uint32_t v = (uint32_t)s[i]; bad |= v >> 16; d[i] = (uint16_t)v; }
+        return bad;
     }
 private:
     void loop(int i) {
@@ -125,9 +138,15 @@ private:
             const size_t slice = ((bytes_ + n_ - 1) / n_ + 63) & ~(size_t)63;
             const size_t b = std::min(bytes_, slice * i), e = std::min(bytes_, slice * (i + 1));
             unsigned char* d = dst_; const unsigned char* s = src_;
+            const bool narrow = narrow_;
             lk.unlock();
-            if (e > b) memcpy(d + b, s + b, e - b);
+            uint32_t bad = 0;
+            if (e > b) {
+                if (!narrow) memcpy(d + b, s + b, e - b);
+                else bad = narrow_slice(reinterpret_cast<uint16_t*>(d + b), reinterpret_cast<const int32_t*>(s + 2 * b), (e - b) / 2);
+            }
             lk.lock();
+            bad_ |= bad;
             if (--pending_ == 0) done_.notify_one();
         }
     }
@@ -138,6 +157,8 @@ private:
     unsigned long long gen_ = 0;
     bool stop_ = false;
     unsigned char* dst_ = nullptr; const unsigned char* src_ = nullptr; size_t bytes_ = 0;
+    bool narrow_ = false;
+    uint32_t bad_ = 0;
     int pending_ = 0;
 };
 
@@ -231,6 +252,7 @@ struct lrperm_engine {
     // Genes no triple reads are not accumulated when no cube is exported (option "skip_unreferenced"): the chunk
     // table keeps ALL chunks and their slot numbers (so the summation order of every referenced gene, and with it every
     // result, is unchanged), `chunks_f` lists the chunks of the referenced genes only, tile-major like `chunks`.
+    int32_t narrow_idx = 1;               // option "narrow_indices": 16-bit column indices on the wire for large pageable stage uploads
     int32_t skip_unref = 1;
     std::vector<uint8_t> h_needed;                      // [G] 1 = some triple reads the gene (from lrperm_set_triples)
     DevBuf needed_dev;
@@ -318,7 +340,7 @@ bool is_pinned_host(const void* p) {
 
 // Large upload from PAGEABLE host memory (a NumPy array): the driver's own staging moves ~10 GB/s; here host threads
 // fill one pinned piece while the previous one is on the wire.
-int upload_pageable(lrperm_engine* h, void* dst, const void* src, size_t bytes) {
+int upload_pageable(lrperm_engine* h, void* dst, const void* src, size_t bytes, bool narrow = false, uint32_t* bad_out = nullptr) {
     if (!h->copier) {
         const unsigned hw = std::thread::hardware_concurrency();
         // host threads that fill the staging pieces: measured on the 16-core B200 host (scripts/upload_probe.py)
@@ -333,20 +355,23 @@ int upload_pageable(lrperm_engine* h, void* dst, const void* src, size_t bytes) 
             CK(cudaEventCreateWithFlags(&h->pin_ev[i], cudaEventDisableTiming));
         }
     }
+    // narrow: `bytes` counts the uint16 OUTPUT; the int32 source is read at twice the offset
     const unsigned char* s = static_cast<const unsigned char*>(src);
     unsigned char* d = static_cast<unsigned char*>(dst);
     const int np = h->n_pin;
+    uint32_t bad = 0;
     int k = 0;
     for (size_t o = 0; o < bytes; o += h->pin_piece, ++k) {
         const size_t n = std::min(h->pin_piece, bytes - o);
         const int b = k % np;
         if (k >= np) CK(cudaEventSynchronize(h->pin_ev[b]));     // the DMA that read this piece one rotation ago is done
-        h->copier->copy(h->pin[b], s + o, n);
+        bad |= h->copier->copy(h->pin[b], s + (narrow ? 2 * o : o), n, narrow);
         CK(cudaMemcpyAsync(d + o, h->pin[b], n, cudaMemcpyHostToDevice, h->stream));
         CK(cudaEventRecord(h->pin_ev[b], h->stream));
     }
     // the staging pieces are reused by the next upload: leave none in flight
     for (int b = 0; b < np && b < k; ++b) CK(cudaEventSynchronize(h->pin_ev[b]));
+    if (bad_out) *bad_out = bad;
     return LRPERM_OK;
 }
 
@@ -1664,6 +1689,9 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "fast_first_batch") {
         if (value < 0 || value > 4096) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_first_batch must be in [0, 4096]");
         h->fast_first_batch = (int32_t)value;
+    } else if (key == "narrow_indices") {
+        if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: narrow_indices must be 0 or 1");
+        h->narrow_idx = (int32_t)value;
     } else if (key == "skip_unreferenced") {
         if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: skip_unreferenced must be 0 or 1");
         h->skip_unref = (int32_t)value;
@@ -1875,7 +1903,20 @@ int lrperm_stage_matrix_csr(lrperm_engine* h, int64_t n_cells, int64_t n_genes, 
     else
         widen_indptr_kernel<int32_t><<<grid_for(n_cells + 1, 256, 1 << 30), 256, 0, h->stream>>>(h->tmp_a.as<int32_t>(), n_cells + 1, h->st_indptr.as<int64_t>(), h->err_flag.as<int>());
     CK_LAUNCH();
-    if ((rc = upload(h, h->st_indices, indices, sizeof(int32_t) * (size_t)nnz, on_device))) return rc;
+    // Column indices of a large pageable upload travel as 16 bits when they fit (n_genes <= 65536): the host threads that fill the
+    // pinned staging pieces narrow them on the way (the transfer is bound by host memory traffic: read + staging write + DMA read),
+    // a kernel widens them again on the device.  An index that would not survive (negative or >= 65536) is an invalid column.
+    const bool narrow = !on_device && h->narrow_idx && n_genes <= 65536 && nnz >= (4LL << 20) && !is_pinned_host(indices);
+    if (narrow) {
+        CK(h->st_indices.ensure(sizeof(int32_t) * (size_t)nnz));
+        CK(h->tmp_b.ensure(sizeof(uint16_t) * (size_t)nnz));
+        uint32_t bad = 0;
+        if ((rc = upload_pageable(h, h->tmp_b.p, indices, sizeof(uint16_t) * (size_t)nnz, true, &bad))) return rc;
+        if (bad) return h->fail(LRPERM_ERR_INVALID, "lrperm_stage_matrix_csr: invalid input (flag=1: 1=column out of range, 2=indptr overflow, "
+                                "4=indptr not monotone, 8=triple index out of range)");
+        widen_u16_kernel<<<grid_for(nnz, 256, h->sm_count * 16), 256, 0, h->stream>>>(h->tmp_b.as<uint16_t>(), nnz, h->st_indices.as<int32_t>());
+        CK_LAUNCH();
+    } else if ((rc = upload(h, h->st_indices, indices, sizeof(int32_t) * (size_t)nnz, on_device))) return rc;
     if ((rc = upload(h, h->st_data, data, sizeof(float) * (size_t)nnz, on_device))) return rc;
     return stage_finish(h, "lrperm_stage_matrix_csr", n_cells, n_genes, nnz, row_keep, on_device, col_sums, kept_total,
                         n_nonfinite, n_empty_rows);

@@ -236,6 +236,11 @@ __global__ void unpack_pairs_kernel(const int2* __restrict__ pairs, int64_t n, i
     }
 }
 
+// 16-bit column indices of a narrowed stage upload -> int32
+__global__ void widen_u16_kernel(const uint16_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
 // column range check of raw CSR indices (the packing kernel does it too, but FAST-only flows never pack)
 __global__ void validate_columns_kernel(const int32_t* __restrict__ indices, int64_t nnz, int32_t G, int* __restrict__ err) {
     bool bad = false;
