@@ -267,6 +267,13 @@ int lrperm_last_timings(lrperm_engine *h, float *out8);
  * gathers only those, _liana_pipe.py:416-419); the counts are identical either way. */
 int lrperm_run_stats(lrperm_engine *h, int64_t *out4);
 
+/* Debug build only (-DLRPERM_BOUNDS_CHECK, `python -m liana_py_b200.build --debug` -> liblrperm_debug.so; the production library
+ * answers LRPERM_ERR_UNSUPPORTED): the hot kernels test every index they compute - shared-memory bin offsets, accumulator columns,
+ * cells, chunk ranges, partial-sum slots, cube rows - against the engine's extents.  Returns and clears the violation bits since
+ * the last call (0 = none; 1 bin offset, 2 cell, 4 chunk range, 8 slot, 16 column, 32 row extent, 64 cube row, 128 trimean plane) and,
+ * in first2 (may be NULL), the bit and the value of the first violation.  Stands in for compute-sanitizer where that tool is closed. */
+int lrperm_debug_bounds(lrperm_engine *h, uint32_t *flags, int64_t *first2);
+
 /* Shape of the engine's matrix: out[0] cells, out[1] genes, out[2] stored entries. */
 int lrperm_matrix_info(lrperm_engine *h, int64_t *out3);
 /* Copy the engine's matrix (after lrperm_set_matrix_csr / lrperm_commit_matrix) out as CSR: indptr int32 [N+1], indices

@@ -12,7 +12,8 @@ from typing import Optional
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "_lib", "liblrperm.so")
+# LRPERM_LIB: another build of the same ABI (e.g. the bounds-checking debug build, `python -m liana_py_b200.build --debug`)
+LIB_PATH = os.environ.get("LRPERM_LIB") or os.path.join(_PKG_DIR, "_lib", "liblrperm.so")
 
 PERMS_INDEX, PERMS_PHILOX = 0, 1
 ORDER_EXACT, ORDER_FAST = 0, 1
@@ -28,7 +29,7 @@ ABI_SYMBOLS = (
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
     "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
     "lrperm_argsort", "lrperm_staged_cluster_stats", "lrperm_stage_matrix_dense",
-    "lrperm_run_stats", "lrperm_matrix_info", "lrperm_export_matrix_csr",
+    "lrperm_run_stats", "lrperm_matrix_info", "lrperm_export_matrix_csr", "lrperm_debug_bounds",
 )
 
 _lib = None
@@ -84,6 +85,7 @@ def load_library():
     lib.lrperm_run_stats.argtypes = [vp, vp]
     lib.lrperm_matrix_info.argtypes = [vp, vp]
     lib.lrperm_export_matrix_csr.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.lrperm_debug_bounds.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 
@@ -491,6 +493,13 @@ class Engine:
         self._check(self._lib.lrperm_philox_perms(self._h, int(n_cells), int(n_perms), int(perm_offset),
                                                   C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_void_p(out.ctypes.data), 0))
         return out
+
+    def debug_bounds(self):
+        """(violation bits, (first bit, first value)) of the kernels' own bounds checks since the last call - debug build
+        only (`LRPERM_LIB=.../liblrperm_debug.so`); the production library raises EngineError."""
+        flags, first = C.c_uint32(0), (C.c_int64 * 2)()
+        self._check(self._lib.lrperm_debug_bounds(self._h, C.byref(flags), C.cast(first, C.c_void_p)))
+        return int(flags.value), (int(first[0]), int(first[1]))
 
     def run_stats(self) -> dict:
         """Work of the last FAST run: genes / stored entries actually accumulated (include/lrperm.h)."""

@@ -18,6 +18,7 @@ HEADERS = [os.path.join(_PKG, "csrc", "lrperm_kernels.cuh"), os.path.join(_PKG, 
            os.path.join(_ROOT, "include", "lrperm.h"),
            os.path.join(_ROOT, "include", "lrperm_philox.h")]
 OUT = os.path.join(_PKG, "_lib", "liblrperm.so")
+OUT_DEBUG = os.path.join(_PKG, "_lib", "liblrperm_debug.so")      # same ABI + the kernels' own bounds checks (--debug)
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
@@ -30,26 +31,27 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC or add /usr/local/cuda/bin to PATH)")
 
 
-def is_stale() -> bool:
-    if not os.path.exists(OUT):
+def is_stale(out: str = OUT) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"),
-           *SOURCES, "-o", OUT]
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    out = OUT_DEBUG if debug else OUT
+    if not force and not is_stale(out):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [find_nvcc(), *NVCC_FLAGS, *(["-DLRPERM_BOUNDS_CHECK"] if debug else []),
+           "-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_PKG, "csrc"), *SOURCES, "-o", out]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -325,6 +325,17 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// extents for the kernels' own bounds checks (debug build only: -DLRPERM_BOUNDS_CHECK); queued on the engine stream
+int dbg_set_dims(lrperm_engine* h, int64_t n_slots, int64_t PB) {
+#ifdef LRPERM_BOUNDS_CHECK
+    DebugDims d{(long long)h->N, (long long)h->G, (long long)h->L, (long long)h->nnz, (long long)n_slots, (long long)PB, (long long)h->T};
+    CK(cudaMemcpyToSymbolAsync(g_dbg_dims, &d, sizeof(d), 0, cudaMemcpyHostToDevice, h->stream));
+#else
+    (void)h; (void)n_slots; (void)PB;
+#endif
+    return LRPERM_OK;
+}
+
 int grid_for(int64_t n, int threads, int cap = 148 * 16) {
     int64_t g = (n + threads - 1) / threads;
     if (g < 1) g = 1;
@@ -1048,6 +1059,7 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
         slots_cap = (size_t)std::max(h->n_slots, 1);
     }
     const uint8_t* d_needed = filt ? h->needed_dev.as<uint8_t>() : nullptr;
+    if ((rc = dbg_set_dims(h, (int64_t)slots_cap, pb_max))) return rc;
     const size_t part_max = sizeof(float) * slots_cap * L * pb_max;
     CK(h->partials.ensure(part_max));
     if (dbl) CK(h->partials2.ensure(part_max));
@@ -1376,6 +1388,7 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
     const bool filt = a.score && a.cube_out == nullptr && h->skip_unref && h->have_triples && h->needed_valid && (int64_t)h->h_needed.size() == h->G;
     if ((rc = build_tm_chunks(h, chunk_nnz, filt))) return rc;
     if ((rc = build_tm_tables(h))) return rc;
+    if ((rc = dbg_set_dims(h, std::max(h->tm_n_slots, 1), 0))) return rc;
     // permutations per batch: the walk visits cells in VALUE order, so the whole label slab of a batch (N x PB
     // bytes) should sit in L2: <= 64 MiB
     int32_t PB = h->tm_perm_batch;
@@ -2285,6 +2298,7 @@ int lrperm_observed(lrperm_engine* h, float* means, int32_t* stored_counts, int3
         CK(h->cube.ensure(sizeof(float) * LG));
         CK(h->stage_out.ensure(sizeof(float) * LG));
         PermSource ps{}; ps.identity = 1;
+        if ((rc = dbg_set_dims(h, 1, 0))) return rc;
         if ((rc = launch_exact(h, ps, 1, h->cube.as<float>(), 1))) return rc;
         dim3 blk(32, 8), grd((G + 31) / 32, 1, L);
         cube_export_kernel<<<grd, blk, 0, h->stream>>>(h->cube.as<float>(), G, L, 1, 1, h->stage_out.as<float>());
@@ -2419,6 +2433,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         fast_tile = tile_cells;
     } else {
         if ((rc = wait_matrix(h))) return rc;
+        if ((rc = dbg_set_dims(h, 1, 0))) return rc;
         // enough (perm, cluster) warps for several waves, cube batch <= ~256 MB
         PB = 512;
         while (PB > 128 && (int64_t)PB * L * G * 4 > (256LL << 20)) PB >>= 1;
@@ -2435,6 +2450,7 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         if ((rc = ensure_fast_tables(h, fast_chunk, fast_tile))) return rc;
         if (filt_serial && (rc = ensure_filtered_chunks(h))) return rc;
         fast_run_stats(h, filt_serial);
+        if ((rc = dbg_set_dims(h, std::max(h->n_slots, 1), PB))) return rc;
         CK(h->slab.ensure((size_t)N * PB));
         CK(h->partials.ensure(sizeof(float) * (size_t)std::max(h->n_slots, 1) * L * PB));
     }
@@ -2847,6 +2863,26 @@ int lrperm_rra(lrperm_engine* h, int64_t n_rows, int32_t n_cols, const double* r
     if (!on_device) CK(cudaMemcpyAsync(rho, d_out, sizeof(double) * (size_t)n_rows, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return LRPERM_OK;
+}
+
+int lrperm_debug_bounds(lrperm_engine* h, uint32_t* flags, int64_t* first2) {
+    if (!h || !flags) return LRPERM_ERR_INVALID;
+#ifdef LRPERM_BOUNDS_CHECK
+    DeviceGuard guard(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned int f = 0;
+    long long first[2] = {0, 0};
+    CK(cudaMemcpyFromSymbol(&f, g_dbg_flags, sizeof(f)));
+    CK(cudaMemcpyFromSymbol(first, g_dbg_first, sizeof(first)));
+    const unsigned int zero = 0;
+    CK(cudaMemcpyToSymbol(g_dbg_flags, &zero, sizeof(zero)));
+    *flags = f;
+    if (first2) { first2[0] = first[0]; first2[1] = first[1]; }
+    return LRPERM_OK;
+#else
+    (void)first2;
+    return h->fail(LRPERM_ERR_UNSUPPORTED, "lrperm_debug_bounds: this library was built without -DLRPERM_BOUNDS_CHECK (python -m liana_py_b200.build --debug)");
+#endif
 }
 
 int lrperm_run_stats(lrperm_engine* h, int64_t* out4) {

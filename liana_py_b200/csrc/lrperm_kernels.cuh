@@ -20,6 +20,29 @@
 
 namespace lrperm {
 
+// ------------------------------------------------------------------------------------------
+// Bounds checks of our own (compute-sanitizer is closed on the B200 pool): compiled in only with
+// -DLRPERM_BOUNDS_CHECK (`python -m liana_py_b200.build --debug` -> liblrperm_debug.so).  Every index the
+// hot kernels compute - shared-memory bin offsets, accumulator columns, cells, chunk ranges, partial-sum slots,
+// cube rows - is tested against the extents the host stored in `g_dbg_dims` before the run; a violation sets a
+// bit in `g_dbg_flags` (and remembers the first offending value) instead of trapping, `lrperm_debug_bounds`
+// returns and clears it.  The production library contains none of this.
+// ------------------------------------------------------------------------------------------
+struct DebugDims { long long N, G, L, nnz, n_slots, PB, T; };
+#ifdef LRPERM_BOUNDS_CHECK
+__device__ DebugDims g_dbg_dims;
+__device__ unsigned int g_dbg_flags;
+__device__ long long g_dbg_first[2];
+__device__ __forceinline__ void dbg_fail(unsigned int bit, long long value) {
+    if (atomicOr(&g_dbg_flags, bit) == 0u) { g_dbg_first[0] = (long long)bit; g_dbg_first[1] = value; }
+}
+#define LRPERM_CHECK(cond, bit, value) do { if (!(cond)) dbg_fail((bit), (long long)(value)); } while (0)
+#else
+#define LRPERM_CHECK(cond, bit, value) do { } while (0)
+#endif
+// bits: 1 bin offset, 2 cell index, 4 chunk range, 8 partial-sum slot, 16 accumulator column, 32 row extent, 64 cube row, 128 plane / cluster of the trimean select
+constexpr unsigned int kDbgBin = 1, kDbgCell = 2, kDbgChunk = 4, kDbgSlot = 8, kDbgColumn = 16, kDbgRow = 32, kDbgCubeRow = 64, kDbgPlane = 128;
+
 constexpr int kExactWarps = 8;       // warps per CTA in the exact-order kernel
 constexpr int kFastWarps = 8;        // warps per CTA in the fast kernel
 constexpr int kScoreThreads = 256;   // threads per CTA in the score kernel
@@ -594,8 +617,10 @@ exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ 
                 const int j = order[k];
                 cell = ps.identity ? j : perm_lookup(ps, p, N, j);
             }
+            LRPERM_CHECK((unsigned)cell < (unsigned long long)g_dbg_dims.N, kDbgCell, cell);
             rs = indptr[cell];
             re = indptr[cell + 1];
+            LRPERM_CHECK(rs >= 0 && rs <= re && re <= g_dbg_dims.nnz, kDbgRow, rs);
         }
     };
 
@@ -619,7 +644,10 @@ exact_means_kernel(const int32_t* __restrict__ indptr, const int2* __restrict__ 
         float x[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (u * 32 < n) x[u] = lds(acc_s + (uint32_t)q[u].x * 4u);
+            if (u * 32 < n) {
+                LRPERM_CHECK((unsigned)q[u].x < (unsigned)Gpad, kDbgColumn, q[u].x);
+                x[u] = lds(acc_s + (uint32_t)q[u].x * 4u);
+            }
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (u * 32 < n) x[u] = __fadd_rn(x[u], __fmul_rn(__int_as_float(q[u].y), inv));
@@ -859,6 +887,7 @@ __device__ __forceinline__ void fast2_update(unsigned char* bins, uint32_t lane4
     for (int q = 0; q < Q; ++q) {
         // {byte1 = label byte q, byte0 = lane*4}: offset of bin [label][q=0][lane]
         const uint32_t off = __byte_perm(label_word<Q>(lw, q), lane4, 0x5504u | ((uint32_t)(q & 3) << 4));
+        LRPERM_CHECK((long long)off + q * 128 + 4 <= g_dbg_dims.L * Q * 128, kDbgBin, off);
         b[q] = reinterpret_cast<float*>(bins + off + q * 128);
     }
 #pragma unroll
@@ -892,6 +921,8 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
     const LV* __restrict__ slab_w = reinterpret_cast<const LV*>(slab) + (group * 32 + lane);
     const int64_t row_words = PB / Q;              // label words per slab row
     const uint32_t lane4 = (uint32_t)lane * 4u;
+    LRPERM_CHECK(ch.begin >= 0 && ch.begin < ch.end && ch.end <= g_dbg_dims.nnz, kDbgChunk, ch.begin);
+    LRPERM_CHECK(ch.slot >= 0 && ch.slot < g_dbg_dims.n_slots && ch.gene >= 0, kDbgSlot, ch.slot);
     const int first_cell = __ldg(&csc_pairs[ch.begin]).x;
 
     auto load_pair = [&](int k) -> int2 {          // tail entries add +0.0f to a valid bin
@@ -910,6 +941,8 @@ fast2_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
 #pragma unroll
         for (int u = 0; u < B; u += 4) {
             const int4 c4 = *reinterpret_cast<const int4*>(st_cell + buf * B + u);
+            LRPERM_CHECK((unsigned)c4.x < (unsigned long long)g_dbg_dims.N && (unsigned)c4.y < (unsigned long long)g_dbg_dims.N &&
+                         (unsigned)c4.z < (unsigned long long)g_dbg_dims.N && (unsigned)c4.w < (unsigned long long)g_dbg_dims.N, kDbgCell, c4.x);
             lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
             lw[u + 1] = __ldg(slab_w + (int64_t)c4.y * row_words);
             lw[u + 2] = __ldg(slab_w + (int64_t)c4.z * row_words);
@@ -1043,6 +1076,7 @@ fast3_means_kernel(const int2* __restrict__ csc_pairs, const FastChunk* __restri
 #pragma unroll
         for (int u = 0; u < B; u += 2) {
             const int4 c4 = *reinterpret_cast<const int4*>(ring + slot * B + u);
+            LRPERM_CHECK((unsigned)c4.x < (unsigned long long)g_dbg_dims.N && (unsigned)c4.z < (unsigned long long)g_dbg_dims.N, kDbgCell, c4.x);
             lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
             lw[u + 1] = __ldg(slab_w + (int64_t)c4.z * row_words);
             vv[u + 0] = __int_as_float(c4.y);
@@ -1103,6 +1137,7 @@ __global__ void fast_finalize_kernel(const float* __restrict__ partials, const i
         float s = 0.0f;
         for (int t = 0; t < n_tiles; ++t) {
             const int s0 = tile_slot_ptr[(int64_t)t * (G + 1) + g], s1 = tile_slot_ptr[(int64_t)t * (G + 1) + g + 1];
+            LRPERM_CHECK(s0 >= 0 && s0 <= s1 && s1 <= g_dbg_dims.n_slots, kDbgSlot, s1);
             for (int sl = s0; sl < s1; ++sl) s = __fadd_rn(s, __ldcs(&partials[((int64_t)sl * L + c) * PB + p]));
         }
         cube[((int64_t)g * L + c) * PP + p_off + p] = __fmul_rn(s, inv_n[c]);
@@ -1157,6 +1192,8 @@ score_count_kernel(const float* __restrict__ cube, int32_t PP, int32_t n_perms_b
             const int tn = min(32, nt - tb);
             for (int u = 0; u < tn; ++u) {
                 const int t = tb + u;
+                LRPERM_CHECK((unsigned)s_ra[t] < (unsigned long long)(g_dbg_dims.G * g_dbg_dims.L) &&
+                             (unsigned)s_rb[t] < (unsigned long long)(g_dbg_dims.G * g_dbg_dims.L), kDbgCubeRow, s_ra[t]);
                 const float a = __ldg(&cube[(int64_t)s_ra[t] * PP + p]);
                 const float b = __ldg(&cube[(int64_t)s_rb[t] * PP + p]);
                 if (CPDB) {

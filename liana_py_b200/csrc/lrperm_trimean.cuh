@@ -145,6 +145,7 @@ __device__ __noinline__ void tm_hit(unsigned char* bins, const int32_t* tgt_s, f
             const int4 t4 = *reinterpret_cast<const int4*>(tgt_s + c * 8 + (k & 4));      // ranks k&4 .. k&4+3
             const int m = tgt_s[c * 8 + 6];
             const int plane = dir ? k : m - 1 - k;
+            LRPERM_CHECK(plane >= 0 && plane < kTmPlanes && c >= 0 && c < g_dbg_dims.L, kDbgPlane, plane);
             out_base[(int64_t)plane * plane_stride + (int64_t)c * PB + q] = v;
             const int cur = (k & 3) == 0 ? t4.x : (k & 3) == 1 ? t4.y : (k & 3) == 2 ? t4.z : t4.w;
             const int nxt = (k & 3) == 0 ? t4.y : (k & 3) == 1 ? t4.z : (k & 3) == 2 ? t4.w : tgt_s[c * 8 + 4];
@@ -249,6 +250,8 @@ tm_select_kernel(const int2* __restrict__ vsc_pairs, const FastChunk* __restrict
 #pragma unroll
             for (int u = 0; u < B; u += 4) {
                 const int4 c4 = *reinterpret_cast<const int4*>(st_cell + buf * B + u);
+                LRPERM_CHECK((unsigned)c4.x < (unsigned long long)g_dbg_dims.N && (unsigned)c4.y < (unsigned long long)g_dbg_dims.N &&
+                             (unsigned)c4.z < (unsigned long long)g_dbg_dims.N && (unsigned)c4.w < (unsigned long long)g_dbg_dims.N, kDbgCell, c4.x);
                 lw[u + 0] = __ldg(slab_w + (int64_t)c4.x * row_words);
                 lw[u + 1] = __ldg(slab_w + (int64_t)c4.y * row_words);
                 lw[u + 2] = __ldg(slab_w + (int64_t)c4.z * row_words);
@@ -262,6 +265,7 @@ tm_select_kernel(const int2* __restrict__ vsc_pairs, const FastChunk* __restrict
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const uint32_t off = __byte_perm(label_word<Q>(lw, q), lane4, 0x5504u | ((uint32_t)(q & 3) << 4));
+                LRPERM_CHECK((long long)off + q * 128 + 4 <= g_dbg_dims.L * Q * 128, kDbgBin, off);
                 b[q] = reinterpret_cast<uint32_t*>(bins + off + q * 128);
             }
 #pragma unroll
