@@ -731,14 +731,21 @@ __global__ void slab_philox_kernel(PermSource ps, const int32_t* __restrict__ cl
     const int p = blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = p < n_perms_batch;
     lrperm_bij_t bij = lrperm_bij_init(ps.seed, (uint64_t)(ps.perm_id0 + (active ? p : 0)), (uint32_t)N);
-    const int i0 = cell0 + blockIdx.x * cells_per_block;
-    const int i1 = min(min(N, cell1), i0 + cells_per_block);
     if (!active) return;
-    for (int i = i0; i < i1; ++i) {
-        const int k = (int)lrperm_bij_inverse(&bij, (uint32_t)i);
-        int c = s_bucket[k >> bucket_shift];                              // cluster of the bucket's first position
-        while (k >= s_start[c + 1]) ++c;                                  // a bucket rarely spans a boundary
-        slab[(int64_t)i * PB + p] = (uint8_t)(c * label_scale);
+    // blocks of cells_per_block cells, strided over gridDim.x: the grid may be as large as the number of blocks (one block
+    // each) or a small PERSISTENT one.  The pipelined FAST path uses the latter: this kernel is ALU-bound and runs next to the
+    // shared-memory-bound main kernel on a high-priority stream; launched with one CTA per block it floods every SM with up to
+    // 56 always-ready warps against the main kernel's 8, and the main kernel loses 18 % (scripts/overlap_ab.py); a few
+    // resident warps per scheduler keep the integer pipe just as busy.
+    const int end = min(N, cell1);
+    for (int64_t i0 = (int64_t)cell0 + (int64_t)blockIdx.x * cells_per_block; i0 < end; i0 += (int64_t)gridDim.x * cells_per_block) {
+        const int i1 = (int)min((int64_t)end, i0 + cells_per_block);
+        for (int i = (int)i0; i < i1; ++i) {
+            const int k = (int)lrperm_bij_inverse(&bij, (uint32_t)i);
+            int c = s_bucket[k >> bucket_shift];                          // cluster of the bucket's first position
+            while (k >= s_start[c + 1]) ++c;                              // a bucket rarely spans a boundary
+            slab[(int64_t)i * PB + p] = (uint8_t)(c * label_scale);
+        }
     }
 }
 
