@@ -296,8 +296,10 @@ int lrperm_set_tuning(lrperm_engine *h, int32_t fast_perm_batch, int32_t fast_ch
  *   "trimean_chunk_nnz"   stored entries per chunk of the trimean path (0 = auto; multiple of 1024)
  *   "trimean_perm_batch"  permutations per batch of the trimean path (0 = auto; multiple of 128)
  *   "skip_unreferenced"   1 (default) = runs that export no cube skip the genes no triple reads (see lrperm_run_stats)
- *   "slab_ctas_per_sm"    CTAs per SM of the (persistent) label-slab kernel of the pipelined FAST path (default 2; 0 = one CTA per
- *                         block of cells): it runs next to the main kernel and must not flood the warp schedulers
+ *   "slab_ctas_per_sm"    CTAs per SM of the (persistent) label-slab kernel of the pipelined FAST path (0 = auto, default: a quarter of
+ *                         the main kernel's resident CTAs): it runs next to the main kernel and must not flood the warp schedulers
+ *   "slab_mode"           which label-slab launches use that persistent grid: 2 (default) all but the very first tile of a run,
+ *                         1 all, 3 batches >= 1 only, 0 none (one CTA per block of cells, round 1's behaviour)
  *   "narrow_indices"      1 (default) = lrperm_stage_matrix_csr sends the column indices of a large pageable upload as 16 bits
  *                         (n_genes <= 65536): less host memory traffic and PCIe volume; same staged matrix  */
 int lrperm_set_option(lrperm_engine *h, const char *name, int64_t value);

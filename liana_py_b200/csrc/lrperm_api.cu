@@ -252,7 +252,8 @@ struct lrperm_engine {
     // Genes no triple reads are not accumulated when no cube is exported (option "skip_unreferenced"): the chunk
     // table keeps ALL chunks and their slot numbers (so the summation order of every referenced gene, and with it every
     // result, is unchanged), `chunks_f` lists the chunks of the referenced genes only, tile-major like `chunks`.
-    int32_t slab_ctas_per_sm = 2;         // option: resident CTAs per SM of the label-slab kernel in the pipelined FAST path (0 = full grid)
+    int32_t slab_mode = 2;                // option (A/B): which slab launches use the persistent grid: 1 all, 2 all but batch 0 / tile 0, 3 batches >= 1, 0 none
+    int32_t slab_ctas_per_sm = 0;         // option: resident CTAs per SM of the label-slab kernel in the pipelined FAST path (0 = full grid)
     int32_t narrow_idx = 1;               // option "narrow_indices": 16-bit column indices on the wire for large pageable stage uploads
     int32_t skip_unref = 1;
     std::vector<uint8_t> h_needed;                      // [G] 1 = some triple reads the gene (from lrperm_set_triples)
@@ -1014,12 +1015,23 @@ int run_fast_pipelined(lrperm_engine* h, const RunArgs& a, int Q, int32_t PB, co
                 const int64_t c0 = nt == 1 ? 0 : (int64_t)t * tile_rows, c1 = nt == 1 ? N : std::min<int64_t>(N, c0 + tile_rows);
                 // persistent grid: `slab_ctas_per_sm` CTAs of 4 warps per SM in total (see slab_philox_kernel); 0 = one CTA per block
                 const unsigned n_blocks = (unsigned)((c1 - c0 + cells_per_block - 1) / cells_per_block), n_grp = (unsigned)((pb + 127) / 128);
-                // (a run of ONE batch has nothing to run next to and its slab is on the critical path: full grid.  Measured,
-                // scripts/overlap_ab.py, configs[2]: 1000 permutations 25.9 -> 24.1 ms with 2 CTAs per SM for EVERY batch - batch 0
-                // included, although its slab then takes longer: its tiles release the main kernel's tile launches one by one
-                // and the second batch's slab no longer floods the first batch's main kernel; 125 permutations 3.80 vs 4.28 ms)
+                // (a run of ONE batch has nothing to run next to and its slab is on the critical path: full grid, like the very first
+                // tile of a longer run.  Measured, scripts/overlap_ab.py, configs[2], 1000 permutations: 25.9 ms full grid everywhere,
+                // 24.0 persistent everywhere, 23.5 persistent everywhere but the first tile; 125 permutations 3.80 vs 4.28 ms)
                 unsigned gx = n_blocks;
-                if (h->slab_ctas_per_sm > 0 && n_batches > 1) gx = std::min(n_blocks, std::max(1u, (unsigned)(h->slab_ctas_per_sm * h->sm_count) / n_grp));
+                const bool first_alone = (b == 0 && t == 0);              // nothing runs next to the very first slab rows
+                const bool persist = h->slab_mode == 1 ? true : h->slab_mode == 2 ? !first_alone : h->slab_mode == 3 ? b > 0 : false;
+                // CTAs per SM: a quarter of what the main kernel keeps resident (its one-warp CTAs are limited by their bins: 8 per
+                // SM at 50 clusters, 19 at 20) - measured best at configs[2] (2: 25.9 -> 23.5 ms), the configs[3] shape (3: 11.9 ->
+                // 11.4 ms) and neutral at configs[1] (5: 3.03 ms), where the main kernel's many warps are not starved anyway
+                int32_t sc = h->slab_ctas_per_sm;
+                if (sc == 0) {
+                    const size_t per_cta = (size_t)L * Q * 128 + 512 + 1024;
+                    const int32_t main_ctas = (int32_t)std::min<size_t>(32, (228u << 10) / per_cta);
+                    sc = main_ctas >= 16 ? -1 : std::max(2, (main_ctas + 3) / 4);      // many small main CTAs: nothing to protect
+                }
+                // (a single batch gains nothing, tile-wise or not: 13.49 vs 13.37 ms at 500 permutations)
+                if (sc > 0 && n_batches > 1 && persist) gx = std::min(n_blocks, std::max(1u, (unsigned)(sc * h->sm_count) / n_grp));
                 dim3 grd(gx, n_grp);
                 slab_philox_kernel<<<grd, 128, tab_smem, sB>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
                                                                h->bucket_shift, L, label_scale, (int32_t)N, pb, slab, PBb, cells_per_block,
@@ -1481,7 +1493,11 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
                     // later batches' slabs run next to the count kernel of an earlier batch: persistent small grid (see slab_philox_kernel)
                     const unsigned n_blocks = (unsigned)((N + cells_per_block - 1) / cells_per_block), n_grp = (unsigned)((pb + 127) / 128);
                     unsigned gx = n_blocks;
-                    if (h->slab_ctas_per_sm > 0 && b > 0 && sS != sM) gx = std::min(n_blocks, std::max(1u, (unsigned)(h->slab_ctas_per_sm * h->sm_count) / n_grp));
+                    {
+                        int32_t sc = h->slab_ctas_per_sm;
+                        if (sc == 0) sc = std::max(2, ((int32_t)std::min<size_t>(32, (228u << 10) / ((size_t)L * Q * 128 + 512 + 1024)) + 3) / 4);
+                        if (h->slab_mode > 0 && b > 0 && sS != sM) gx = std::min(n_blocks, std::max(1u, (unsigned)(sc * h->sm_count) / n_grp));
+                    }
                     dim3 grd(gx, n_grp);
                     const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
                     slab_philox_kernel<<<grd, 128, tab_smem, sS>>>(ps, h->cl_start.as<int32_t>(), h->bucket_cluster.as<uint8_t>(), h->n_buckets,
@@ -1715,8 +1731,11 @@ int lrperm_set_option(lrperm_engine* h, const char* name, int64_t value) {
     } else if (key == "fast_first_batch") {
         if (value < 0 || value > 4096) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: fast_first_batch must be in [0, 4096]");
         h->fast_first_batch = (int32_t)value;
+    } else if (key == "slab_mode") {
+        if (value < 0 || value > 3) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: slab_mode must be in [0, 3]");
+        h->slab_mode = (int32_t)value;
     } else if (key == "slab_ctas_per_sm") {
-        if (value < 0 || value > 16) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: slab_ctas_per_sm must be in [0, 16]");
+        if (value < 0 || value > 32) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: slab_ctas_per_sm must be in [0, 32] (0 = auto)");
         h->slab_ctas_per_sm = (int32_t)value;
     } else if (key == "narrow_indices") {
         if (value != 0 && value != 1) return h->fail(LRPERM_ERR_INVALID, "lrperm_set_option: narrow_indices must be 0 or 1");

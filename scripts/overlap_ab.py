@@ -9,7 +9,7 @@ from liana_py_b200.method import _pipeline as PL, _tables
 from liana_py_b200.resource import select_resource
 from liana_py_b200.testing._synth import consensus_genes
 from liana_py_b200.testing._synth_gpu import synthetic_csr_torch
-N, L = 500_000, 50
+N, L = {"c3": (500_000, 50), "c2": (50_000, 20), "c4": (200_000, 40)}[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 genes = consensus_genes(); G = len(genes)
 indptr, indices, data, labels = synthetic_csr_torch(N, G, L, 0.08)
 eng = E.Engine(0); eng.set_matrix_csr(indptr, indices, data, N, G); eng.set_labels(labels, L)
@@ -20,9 +20,9 @@ eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
 counts = torch.zeros(len(obs), dtype=torch.int32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ref = None
-for P in (1000,):
-    for overlap, pb, sc in ((1, 0, 2), (1, 0, 3), (1, 0, 2), (1, 0, 3), (1, 0, 2), (1, 0, 3), (1, 0, 0)):
-        eng.set_option("overlap", overlap); eng.set_tuning(pb, 0, 0); eng.set_option("slab_ctas_per_sm", sc)
+for P in (1000, 500, 250):
+    for overlap, pb, sc, mode in ((1, 0, 0, 0), (1, 0, 0, 2)):
+        eng.set_option("overlap", overlap); eng.set_tuning(pb, 0, 0); eng.set_option("slab_ctas_per_sm", sc); eng.set_option("slab_mode", mode)
         ts = []
         for it in range(12):
             flush.fill_(1); torch.cuda.synchronize()
@@ -33,5 +33,5 @@ for P in (1000,):
         if ref is None: ref = c
         tm = eng.timings(); st = eng.run_stats()
         upd = st["nnz_scored"] * P / (tm["main_kernel_ms"] * 1e-3) / 148 / 1.965e9
-        print(f"P={P} overlap={overlap} batch={pb or 512} slab_ctas_per_sm={sc}: {np.median(ts[2:]):.3f} ms (setup {tm['setup_ms']:.2f} main {tm['main_kernel_ms']:.2f} means {tm['means_ms']:.2f} "
+        print(f"P={P} overlap={overlap} batch={pb or 512} slab_ctas_per_sm={sc} slab_mode={mode}: {np.median(ts[2:]):.3f} ms (setup {tm['setup_ms']:.2f} main {tm['main_kernel_ms']:.2f} means {tm['means_ms']:.2f} "
               f"score {tm['score_ms']:.2f}; main kernel {upd:.2f} updates/clk/SM) same={np.array_equal(c, ref) if P == 1000 else '-'}", flush=True)
