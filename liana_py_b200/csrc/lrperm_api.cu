@@ -1495,8 +1495,11 @@ int run_trimean_batches(lrperm_engine* h, const TrimeanArgs& a) {
                     unsigned gx = n_blocks;
                     {
                         int32_t sc = h->slab_ctas_per_sm;
-                        if (sc == 0) sc = std::max(2, ((int32_t)std::min<size_t>(32, (228u << 10) / ((size_t)L * Q * 128 + 512 + 1024)) + 3) / 4);
-                        if (h->slab_mode > 0 && b > 0 && sS != sM) gx = std::min(n_blocks, std::max(1u, (unsigned)(sc * h->sm_count) / n_grp));
+                        if (sc == 0) {
+                            const int32_t main_ctas = (int32_t)std::min<size_t>(32, (228u << 10) / ((size_t)L * Q * 128 + 512 + 1024));
+                            sc = main_ctas >= 16 ? -1 : std::max(2, (main_ctas + 3) / 4);
+                        }
+                        if (sc > 0 && h->slab_mode > 0 && b > 0 && sS != sM) gx = std::min(n_blocks, std::max(1u, (unsigned)(sc * h->sm_count) / n_grp));
                     }
                     dim3 grd(gx, n_grp);
                     const size_t tab_smem = sizeof(int32_t) * (size_t)(L + 1) + (size_t)h->n_buckets;
