@@ -2452,10 +2452,9 @@ int lrperm_run(lrperm_engine* h, int64_t n_perms, int64_t perm_offset, uint64_t 
         if (Q == 0) return h->fail(LRPERM_ERR_UNSUPPORTED, "FAST mode: %d clusters do not fit the shared-memory bins", L);
         PB = h->fast_perm_batch ? h->fast_perm_batch : 512;
         const int32_t gran = std::max(128, 32 * Q);        // a warp covers 32*Q permutations
-        // A run that would be ONE batch (one rank's share of 1000 permutations on 2-4 GPUs) is cut in two, so that the second half's label
-        // slab and the first half's finalize + score are hidden behind a main kernel (scripts/overlap_ab.py, configs[2]: 500 permutations
-        // 13.38 -> 12.86 ms, 250: 7.02 -> 6.80 ms; the configs[3] shape 6.40 -> 6.00 / 3.30 -> 3.10 ms).  Results do not depend on the schedule.
-        if (!h->fast_perm_batch && n_perms > gran && n_perms <= 512) PB = (int32_t)(((n_perms + 1) / 2 + gran - 1) / gran * gran);
+        // (cutting a run that would be ONE batch - one rank's share on 2-4 GPUs - in two, so that the second half's slab hides behind the
+        // first half's main kernel, was measured and NOT adopted: 500 permutations 13.4 -> 12.4-12.9 ms in most runs but 14.3-14.7 ms in
+        // others, depending on what ran before - scripts/overlap_ab.py; `lrperm_set_tuning(256, ...)` asks for it explicitly)
         if (n_perms < PB) PB = (int32_t)std::max<int64_t>(gran, ((n_perms + gran - 1) / gran) * gran);
         PB = ((PB + gran - 1) / gran) * gran;
         const int32_t tile_cells = fast_tile_cells(h);

@@ -20,8 +20,8 @@ eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)
 counts = torch.zeros(len(obs), dtype=torch.int32, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ref = None
-for P in (1000, 500, 250, 125):
-    for overlap, pb, sc, mode in ((1, 0, 0, 2), (1, 512, 0, 2), (1, 0, 0, 0), (0, 0, 0, 0)):
+for P in (500, 250):
+    for overlap, pb, sc, mode in ((1, 0, 0, 2), (1, 256, 0, 2), (1, 512, 0, 2), (1, 0, 0, 2), (1, 256, 0, 2), (1, 128, 0, 2), (1, 512, 0, 2)):
         eng.set_option("overlap", overlap); eng.set_tuning(pb, 0, 0); eng.set_option("slab_ctas_per_sm", sc); eng.set_option("slab_mode", mode)
         ts = []
         for it in range(12):
