@@ -240,3 +240,68 @@ def test_prepare_input_refuses_an_input_without_clusters():
     adata = _ragged()
     with pytest.raises(ValueError, match="No cells left"):
         _pre.prepare_input(adata, "cluster", 10 ** 6, SciPyStage())
+
+
+def test_reference_perm_chunks_equal_the_whole_stream():
+    """Chunked draws of the reference's permutation stream (bounded memory, any [lo, hi) range of a rank / device) are the
+    same numbers as the whole P x N array drawn at once (`_get_mean_perms.py:69-72, 79`)."""
+    from liana_py_b200.method import _pipeline as PL
+    n, P, seed = 37, 23, 99
+    whole = PL.reference_perm_indices(n, P, seed)
+    rng = np.random.default_rng(seed)
+    want = np.stack([rng.permutation(np.arange(n)) for _ in range(P)])
+    assert np.array_equal(whole, want) and whole.dtype == np.int32
+    for lo, hi in ((0, P), (5, 17), (22, 23), (7, 7)):
+        parts = list(PL.reference_perm_chunks(n, P, seed, lo, hi, max_bytes=3 * n * 4))       # 3 draws per chunk
+        assert [p0 for p0, _ in parts] == list(range(lo, hi, 3))
+        got = np.concatenate([c for _, c in parts]) if parts else np.zeros((0, n), np.int32)
+        assert np.array_equal(got, want[lo:hi])
+
+
+def test_default_perm_source_switch(monkeypatch):
+    from liana_py_b200.method import _pipeline as PL
+    monkeypatch.delenv("LIANA_B200_PERM_SOURCE", raising=False)
+    assert PL.default_perm_source() == "philox"
+    monkeypatch.setenv("LIANA_B200_PERM_SOURCE", "Reference")
+    assert PL.default_perm_source() == "reference"
+    monkeypatch.setenv("LIANA_B200_PERM_SOURCE", "numpy")
+    with pytest.raises(ValueError):
+        PL.default_perm_source()
+
+
+def test_row_blocks_partition_the_matrix_without_copies():
+    """Multi-rank staging: contiguous row blocks balanced by stored entries, handed to the engine as VIEWS of the caller's
+    arrays (a SciPy matrix built from such views would copy them: `_prune_array`)."""
+    from liana_py_b200.method._dist import DistContext
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 50, 1000)
+    counts[100:200] = 0
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    X = sparse.csr_matrix((rng.random(indptr[-1]).astype(np.float32), rng.integers(0, 30, indptr[-1]).astype(np.int32), indptr),
+                          shape=(1000, 30))
+    for world in (1, 2, 3, 8):
+        cuts = [DistContext(r, world).row_block(1000, X.indptr) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        loads = [int(X.indptr[b] - X.indptr[a]) for a, b in cuts]
+        assert max(loads) - min(loads) <= 2 * 50 + indptr[-1] // (world * 50)
+        for a, b in cuts:
+            blk = _pre.CSRBlock(X, a, b)
+            assert blk.shape == (b - a, 30) and np.shares_memory(blk.data, X.data) and np.shares_memory(blk.indices, X.indices)
+            assert (blk.tocsr() != X[a:b]).nnz == 0
+    assert DistContext(1, 4).row_block(10) == (2, 5)            # no row pointers (dense input): by rows
+
+
+def test_global_code_tables_cover_every_sample():
+    """`by_sample` keeps its result numeric: a sample's gene / interaction / cluster codes are re-coded through integer
+    maps into tables that do not depend on the sample."""
+    from liana_py_b200.method import _pipeline as PL, _tables
+    from liana_py_b200.resource import select_resource
+    res = select_resource("consensus")
+    _, ex = PL.exploded(res)
+    g = PL.global_name_tables(res, ["a", "b", "c"])
+    assert len(g["ligand_complex"]) == len(res) and len(g["ligand"]) == len(ex.entities)
+    some = np.sort(np.random.default_rng(1).choice(ex.entities, 600, replace=False))
+    tb = _tables.tables_for_genes(ex, some)
+    assert np.array_equal(ex.entities[tb.entity_index], tb.entities)
+    assert np.array_equal(ex.ligand_complex[tb.inter_index], tb.ligand_complex)
+    assert np.array_equal(np.asarray(g["receptor_complex"])[tb.inter_index], tb.receptor_complex)
