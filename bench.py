@@ -361,8 +361,8 @@ def run_gpu(args):
         n_rows_plugin = int(len(res))
         adata = res = None
         keep.clear()
-        extra["configs3_rank_aggregate"] = configs3_rank_aggregate(device, local, dctx, world, P)
-        extra["configs4_by_sample"] = configs4_by_sample(device, local, dctx, world, P)
+        extra["configs3_rank_aggregate"] = _guarded("configs3_rank_aggregate", lambda: configs3_rank_aggregate(device, local, dctx, world, P))
+        extra["configs4_by_sample"] = _guarded("configs4_by_sample", lambda: configs4_by_sample(device, local, dctx, world, P))
         if world == 1:      # the engine holds another matrix now: put the main workload back for the sections below
             adata = host_adata(gen_full(args.workload, device))
             state = PL.prepare(adata, "cluster", "consensus", None, None, None, 5, False, None, False, device=local)
@@ -438,27 +438,41 @@ def run_gpu(args):
     }
     restore = lambda: eng.set_triples(tri.lig_gene, tri.rec_gene, tri.src, tri.tgt, obs, None)    # noqa: E731
     if world == 1 and not args.no_stress:
-        line["stress_expr_prop0"] = stress_variant(state, P, order, counts, timed)
+        line["stress_expr_prop0"] = _guarded("stress_expr_prop0", lambda: stress_variant(state, P, order, counts, timed))
         restore()
     if world == 1 and not args.no_cellchat:
-        line["cellchat_null"] = cellchat_null(state, adata, wl, P, timed, cpu=not args.no_cpu)
+        line["cellchat_null"] = _guarded("cellchat_null", lambda: cellchat_null(state, adata, wl, P, timed, cpu=not args.no_cpu))
         restore()
     if world == 1 and args.order == "fast" and not args.no_exact:
-        ex_ms, _, ex_kern, ex_n, _ = timed(lambda: eng.run(P, seed=1337, order=E.ORDER_EXACT, scores=E.SCORE_CPDB,
-                                                         counts_out=(counts, None)), 2, 1)
-        ex_ms /= 2
-        ex_static = load_static_profile(f"{args.workload}_exact")
-        line["exact_order_mode"] = {"ms_per_step": ex_ms, "value": P * T / (ex_ms * 1e-3), "kernel": "exact_means_kernel",
-                                    "roofline": {"bound": "hbm", "frac": per_perm_bytes * P / (ex_kern / 2 * 1e-3) / 1e9 / peak_gbs,
-                                                 "peak": peak_gbs, "traffic_detail": ex_static},
-                                    "note": "bit-identical-to-reference summation order (validation mode); every gene is computed"}
+        def exact_section():
+            ex_ms, _, ex_kern, ex_n, _ = timed(lambda: eng.run(P, seed=1337, order=E.ORDER_EXACT, scores=E.SCORE_CPDB,
+                                                             counts_out=(counts, None)), 2, 1)
+            ex_ms /= 2
+            ex_static = load_static_profile(f"{args.workload}_exact")
+            return {"ms_per_step": ex_ms, "value": P * T / (ex_ms * 1e-3), "kernel": "exact_means_kernel",
+                    "roofline": {"bound": "hbm", "frac": per_perm_bytes * P / (ex_kern / 2 * 1e-3) / 1e9 / peak_gbs,
+                                 "peak": peak_gbs, "traffic_detail": ex_static},
+                    "note": "bit-identical-to-reference summation order (validation mode); every gene is computed"}
+        line["exact_order_mode"] = _guarded("exact_order_mode", exact_section)
     if world == 1 and not args.no_dropin:
-        line["dropin_call_subset"] = dropin_subset(eng, state, wl, P, local)
+        line["dropin_call_subset"] = _guarded("dropin_call_subset", lambda: dropin_subset(eng, state, wl, P, local))
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(subset_inputs(eng, state), wl, P, n_jobs=1, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = _guarded("cpu_baseline", lambda: cpu_baseline(subset_inputs(eng, state), wl, P, n_jobs=1,
+                                                                            budget_s=args.cpu_budget))
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _guarded(section, fn):
+    """A secondary section must not cost the line its primary numbers: an exception is printed to stderr and recorded
+    as {"error": ...} under the section's key (all sections run on every rank that takes part, so ranks fail alike)."""
+    try:
+        return fn()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"section": section, "error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def _wall_max(fn, world, device, repeats=1):
