@@ -100,6 +100,7 @@ def exploded(res: pd.DataFrame):
     if hint is not None and hint[2] == len(res) and list(res.columns[:2]) == ["ligand", "receptor"]:
         rkey = hint                                   # a bundled table as `select_resource` handed it out
     else:
+        # row hashes as bytes: sensitive to the ORDER of the interactions too (a plain sum would not be)
         rkey = hash(pd.util.hash_pandas_object(res[["ligand", "receptor"]], index=False).values.tobytes())
     ex = _EXPLODED_CACHE.get(rkey)
     if ex is None:
@@ -113,7 +114,6 @@ def _cached_tables(res: pd.DataFrame, var_names: np.ndarray):
     """(ResourceTables, all resource entities).  Two levels: the resource split into subunits (Python string work over
     4.6 k interactions, ~50 ms) is memoised on the resource's content; the tables for one gene set (array operations,
     < 1 ms) on (resource, gene names) - every sample of `by_sample` has its own set of non-empty genes."""
-    # row hashes as bytes: sensitive to the ORDER of the interactions too (a plain sum would not be)
     rkey, ex = exploded(res)
     key = (rkey, len(var_names), hash(np.asarray(var_names, dtype=str).tobytes()))
     hit = _TABLE_CACHE.get(key)
@@ -497,16 +497,7 @@ def finish_frame(state: PipelineState, frame: pd.DataFrame, by: str, ascending: 
     if state.engine is None or len(vals) < 4096 or np.isnan(vals).any():
         return materialise_names(state, sort_frame(state.engine, frame, by, ascending))
     order = state.engine.argsort(vals, descending=not ascending)
-    lookup = name_tables(state)
-    cols = list(frame.columns)
-    arrays = [frame[c].values for c in cols]
-
-    def gather(i):
-        v = arrays[i].take(order)
-        return _take_names(lookup[cols[i]], v) if cols[i] in lookup else v
-
-    done = list(_frame_pool().map(gather, range(len(cols))))
-    return pd.DataFrame(dict(zip(cols, done)), index=pd.Index(order), copy=False)
+    return pd.DataFrame(gather_columns(state, frame, order), index=pd.Index(order), copy=False)
 
 
 def gather_columns(state: PipelineState, frame: pd.DataFrame, order: np.ndarray) -> dict:
