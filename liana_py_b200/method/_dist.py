@@ -3,7 +3,9 @@
 The permutation null shards naturally: rank r runs permutations
 [P*r/R, P*(r+1)/R) against replicated inputs and only the uint32 exceedance counters are
 combined - one integer all-reduce, so results are bit-identical for any number of GPUs.
-`by_sample` shards whole samples and needs no collective (results are gathered as objects).
+`by_sample` shards whole samples: no data-path collective; the per-rank result columns (numbers and
+integer codes, never strings or pickled frames) are concatenated with one packed all-gather.
+Row-sharded staging of a replicated host matrix: `row_block` + `all_gather_csr`.
 """
 from __future__ import annotations
 

@@ -129,7 +129,7 @@ class MethodMeta:
             cols, state = self.__call__(temp, inplace=False, verbose=verbose, _names=False, **{**kwargs, **extra})
             cols = PL.to_global_codes(cols, PL.global_code_maps(state, g_tables))
             n_rows = len(next(iter(cols.values()))) if cols else 0
-            return {sample_key: np.full(n_rows, i, dtype=np.int32), **cols}
+            return {sample_key: np.full(n_rows, i, dtype=PL.code_dtype(len(samples))), **cols}
 
         import os
         import time

@@ -305,3 +305,26 @@ def test_global_code_tables_cover_every_sample():
     assert np.array_equal(ex.entities[tb.entity_index], tb.entities)
     assert np.array_equal(ex.ligand_complex[tb.inter_index], tb.ligand_complex)
     assert np.array_equal(np.asarray(g["receptor_complex"])[tb.inter_index], tb.receptor_complex)
+
+
+def test_global_codes_travel_in_the_narrowest_type_their_table_allows():
+    """`by_sample` exchanges code columns between ranks: 8 bits for clusters, 16 for the genes / interactions of a resource."""
+    from types import SimpleNamespace
+    from liana_py_b200.method import _pipeline as PL, _tables
+    from liana_py_b200.resource import select_resource
+    assert PL.code_dtype(256) is np.uint8 and PL.code_dtype(257) is np.uint16
+    assert PL.code_dtype(65536) is np.uint16 and PL.code_dtype(65537) is np.int32
+    res = select_resource("consensus")
+    _, ex = PL.exploded(res)
+    cats = [f"c{i}" for i in range(30)]
+    g = PL.global_name_tables(res, cats)
+    some = np.sort(np.random.default_rng(2).choice(ex.entities, 500, replace=False))
+    tb = _tables.tables_for_genes(ex, some)
+    state = SimpleNamespace(tables=tb, prep=SimpleNamespace(categories=np.array(cats[3:20])))
+    maps = PL.global_code_maps(state, g)
+    assert maps["source"].dtype == np.uint8 and maps["ligand"].dtype == np.uint16 and maps["ligand_complex"].dtype == np.uint16
+    assert np.array_equal(maps["source"], np.arange(3, 20)) and np.array_equal(maps["ligand"], tb.entity_index)
+    cols = PL.to_global_codes({"source": np.array([0, 16, 5]), "lr_means": np.array([1.0, 2.0, 3.0])}, maps)
+    assert cols["source"].dtype == np.uint8 and cols["source"].tolist() == [3, 19, 8]
+    frame = PL.frame_from_codes(cols, g)
+    assert frame["source"].tolist() == ["c3", "c19", "c8"] and frame["lr_means"].tolist() == [1.0, 2.0, 3.0]
