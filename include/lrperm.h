@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LRPERM_ABI_VERSION 4   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads; 3: dense staging; 4: run statistics, matrix export */
+#define LRPERM_ABI_VERSION 5   /* 2: trimean (CellChat), staged max, consensus / resolve / argsort entry points, async pinned uploads; 3: dense staging; 4: run statistics, matrix export; 5: staged info */
 
 /* status codes */
 #define LRPERM_OK              0
@@ -103,6 +103,16 @@ int lrperm_set_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes,
 int lrperm_stage_matrix_csr(lrperm_engine *h, int64_t n_cells, int64_t n_genes, const void *indptr, int indptr_is_64,
                             const int32_t *indices, const float *data, int on_device, const uint8_t *row_keep,
                             double *col_sums, double *kept_total, int64_t *n_nonfinite, int64_t *n_empty_rows);
+/*
+ * Shape of the staged matrix and n_unordered: the number of its stored entries whose column index is not greater than
+ * its predecessor's in the same row, counted by the staging pass.  0 = every row strictly increasing, i.e. SciPy's
+ * "canonical format" (sorted, no duplicate entries) - the property the reference's SciPy arithmetic relies on when it
+ * sums a (cell, gene) entry once (`X[perm_idx]`, `.sum(0)`: liana/method/sc/_get_mean_perms.py:62-63).  The engine
+ * itself accepts any column order but not duplicates: a caller that sees n_unordered > 0 sorts / sums duplicates on
+ * its side (`csr_matrix.sum_duplicates`) and stages again - and does not need a pass of its own over every index
+ * (SciPy's `has_canonical_format`: 0.5 ms per million entries) when it is 0.  Any output may be NULL.
+ */
+int lrperm_staged_info(lrperm_engine *h, int64_t *n_cells, int64_t *n_genes, int64_t *nnz, int64_t *n_unordered);
 /*
  * The same staging step for a DENSE row-major matrix (adata.X as a 2-D array): replaces the `csr_matrix(X)` of
  * _choose_mtx_rep (liana/method/_pipe_utils/_pre.py:259-262) and the float32 cast (:117-119).  values = float32

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "lrperm_run_trimean", "lrperm_observed_trimean", "lrperm_trimean_timings", "lrperm_staged_max",
     "lrperm_rank_average", "lrperm_rra", "lrperm_resolve_triples", "lrperm_fetch_triples",
     "lrperm_argsort", "lrperm_staged_cluster_stats", "lrperm_stage_matrix_dense",
-    "lrperm_run_stats", "lrperm_matrix_info", "lrperm_export_matrix_csr", "lrperm_debug_bounds",
+    "lrperm_run_stats", "lrperm_matrix_info", "lrperm_export_matrix_csr", "lrperm_debug_bounds", "lrperm_staged_info",
 )
 
 _lib = None
@@ -86,6 +86,7 @@ def load_library():
     lib.lrperm_matrix_info.argtypes = [vp, vp]
     lib.lrperm_export_matrix_csr.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.lrperm_debug_bounds.argtypes = [vp, vp, vp]
+    lib.lrperm_staged_info.argtypes = [vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -188,7 +189,9 @@ class Engine:
 
     def stage_matrix(self, X, row_keep=None):
         """Upload the caller's FULL SciPy CSR matrix (float32) and return its statistics:
-        dict(col_sums float64 [G], kept_total, n_nonfinite, n_empty_rows).  Follow with commit_matrix."""
+        dict(col_sums float64 [G], kept_total, n_nonfinite, n_empty_rows, n_unordered).  n_unordered > 0: some row is not
+        strictly increasing in its column indices (unsorted or duplicate entries) - canonicalise (`sum_duplicates`) and
+        stage again.  Follow with commit_matrix."""
         indptr = np.ascontiguousarray(X.indptr)
         if indptr.dtype not in (np.int32, np.int64):
             indptr = indptr.astype(np.int64)
@@ -203,7 +206,8 @@ class Engine:
             C.c_void_p(indices.ctypes.data), C.c_void_p(data.ctypes.data), 0,
             None if keep is None else C.c_void_p(keep.ctypes.data), C.c_void_p(col_sums.ctypes.data),
             C.byref(total), C.byref(bad), C.byref(empty)))
-        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value,
+                    n_unordered=self.staged_info()["n_unordered"])
 
     def stage_matrix_device(self, indptr, indices, data, shape, row_keep=None):
         """`stage_matrix` for CSR arrays that already live on the device (CUDA torch tensors: indptr int32 / int64,
@@ -224,7 +228,8 @@ class Engine:
             C.c_void_p(indices.data_ptr()), C.c_void_p(data.data_ptr()), 1,
             None if keep is None else C.c_void_p(keep.data_ptr()), C.c_void_p(col_sums.ctypes.data),
             C.byref(total), C.byref(bad), C.byref(empty)))
-        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value,
+                    n_unordered=self.staged_info()["n_unordered"])
 
     def stage_matrix_dense(self, X, row_keep=None):
         """`stage_matrix` for a dense 2-D array (NumPy float32 / float64, or a CUDA torch tensor of those types): the
@@ -263,7 +268,14 @@ class Engine:
             self._h, n, g, C.c_void_p(ptr), int(is64), int(max(stride, g)), int(on_device),
             None if keep_ptr is None else C.c_void_p(keep_ptr), C.c_void_p(col_sums.ctypes.data),
             C.byref(total), C.byref(bad), C.byref(empty)))
-        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value)
+        return dict(col_sums=col_sums, kept_total=total.value, n_nonfinite=bad.value, n_empty_rows=empty.value,
+                    n_unordered=self.staged_info()["n_unordered"])
+
+    def staged_info(self) -> dict:
+        """dict(n_cells, n_genes, nnz, n_unordered) of the staged matrix (`lrperm_staged_info`)."""
+        vals = [C.c_int64(0) for _ in range(4)]
+        self._check(self._lib.lrperm_staged_info(self._h, *[C.byref(v) for v in vals]))
+        return dict(zip(("n_cells", "n_genes", "nnz", "n_unordered"), (int(v.value) for v in vals)))
 
     def staged_max(self):
         """(largest stored value over the kept rows of the staged matrix as np.float32, stored entries in them)."""

@@ -222,7 +222,7 @@ struct lrperm_engine {
 
     // staged (caller's full) matrix, between lrperm_stage_matrix_csr and lrperm_commit_matrix
     bool staged = false;
-    int64_t st_N = 0, st_G = 0, st_nnz = 0;
+    int64_t st_N = 0, st_G = 0, st_nnz = 0, st_unordered = 0;
     bool st_has_keep = false;
     DevBuf st_indptr, st_indices, st_data, st_row_keep, st_small;
 
@@ -1898,8 +1898,8 @@ int stage_finish(lrperm_engine* h, const char* what, int64_t n_cells, int64_t n_
     int rc;
     h->st_has_keep = row_keep != nullptr;
     if (row_keep && (rc = upload(h, h->st_row_keep, row_keep, (size_t)n_cells, on_device))) return rc;
-    // [G doubles col sums][kept_total][n_nonfinite][n_empty_rows]
-    const size_t small_bytes = sizeof(double) * ((size_t)n_genes + 3);
+    // [G doubles col sums][kept_total][n_nonfinite][n_empty_rows][n_unordered]
+    const size_t small_bytes = sizeof(double) * ((size_t)n_genes + 4);
     CK(h->st_small.ensure(small_bytes));
     CK(cudaMemsetAsync(h->st_small.p, 0, small_bytes, h->stream));
     double* d_small = h->st_small.as<double>();
@@ -1908,10 +1908,11 @@ int stage_finish(lrperm_engine* h, const char* what, int64_t n_cells, int64_t n_
             h->st_indptr.as<int64_t>(), h->st_indices.as<int32_t>(), h->st_data.as<float>(),
             row_keep ? h->st_row_keep.as<uint8_t>() : nullptr, (int32_t)n_cells, (int32_t)n_genes, d_small,
             d_small + n_genes, reinterpret_cast<unsigned long long*>(d_small + n_genes + 1),
-            reinterpret_cast<unsigned long long*>(d_small + n_genes + 2), h->err_flag.as<int>());
+            reinterpret_cast<unsigned long long*>(d_small + n_genes + 2),
+            reinterpret_cast<unsigned long long*>(d_small + n_genes + 3), h->err_flag.as<int>());
         CK_LAUNCH();
     }
-    std::vector<double> host((size_t)n_genes + 3);
+    std::vector<double> host((size_t)n_genes + 4);
     CK(cudaMemcpyAsync(host.data(), d_small, small_bytes, cudaMemcpyDeviceToHost, h->stream));
     if ((rc = check_err_flag(h, what))) return rc;     // synchronises the stream
     if (col_sums) memcpy(col_sums, host.data(), sizeof(double) * (size_t)n_genes);
@@ -1919,6 +1920,7 @@ int stage_finish(lrperm_engine* h, const char* what, int64_t n_cells, int64_t n_
     unsigned long long u;
     memcpy(&u, &host[(size_t)n_genes + 1], 8); if (n_nonfinite) *n_nonfinite = (int64_t)u;
     memcpy(&u, &host[(size_t)n_genes + 2], 8); if (n_empty_rows) *n_empty_rows = (int64_t)u;
+    memcpy(&u, &host[(size_t)n_genes + 3], 8); h->st_unordered = (int64_t)u;
     h->st_N = n_cells; h->st_G = n_genes; h->st_nnz = nnz;
     h->staged = true;
     return LRPERM_OK;
@@ -2029,6 +2031,16 @@ int lrperm_stage_matrix_dense(lrperm_engine* h, int64_t n_cells, int64_t n_genes
     }
     return stage_finish(h, "lrperm_stage_matrix_dense", n_cells, n_genes, nnz, row_keep, on_device, col_sums, kept_total,
                         n_nonfinite, n_empty_rows);
+}
+
+int lrperm_staged_info(lrperm_engine* h, int64_t* n_cells, int64_t* n_genes, int64_t* nnz, int64_t* n_unordered) {
+    if (!h) return LRPERM_ERR_INVALID;
+    if (!h->staged) return h->fail(LRPERM_ERR_INVALID, "lrperm_staged_info: call lrperm_stage_matrix_csr first");
+    if (n_cells) *n_cells = h->st_N;
+    if (n_genes) *n_genes = h->st_G;
+    if (nnz) *nnz = h->st_nnz;
+    if (n_unordered) *n_unordered = h->st_unordered;
+    return LRPERM_OK;
 }
 
 int lrperm_staged_max(lrperm_engine* h, float* max_stored, int64_t* n_stored) {

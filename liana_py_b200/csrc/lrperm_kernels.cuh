@@ -126,23 +126,26 @@ __global__ void pack_csr_kernel(const int32_t* __restrict__ indptr, const int32_
 // ------------------------------------------------------------------------------------------
 // One warp per row of the staged matrix: per-column sums over ALL rows (float64 atomics; used only for
 // the "gene is empty" test and the matrix mean), number of non-finite values, number of empty rows,
-// total over the kept rows.
+// total over the kept rows, and the number of stored entries whose column is not greater than its predecessor's in
+// the same row (0 = every row strictly increasing = SciPy's canonical format: sorted, no duplicates - what the host
+// would otherwise establish with a pass of its own over every index, `has_canonical_format`).
 __global__ void stage_stats_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                    const float* __restrict__ data, const uint8_t* __restrict__ row_keep, int32_t N, int32_t G,
                                    double* __restrict__ col_sums, double* __restrict__ kept_total,
                                    unsigned long long* __restrict__ n_nonfinite, unsigned long long* __restrict__ n_empty_rows,
-                                   int* __restrict__ err) {
+                                   unsigned long long* __restrict__ n_unordered, int* __restrict__ err) {
     const int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     double block_total = 0.0;
-    unsigned long long bad = 0, empty = 0;
+    unsigned long long bad = 0, empty = 0, unordered = 0;
     for (int r = warp; r < N; r += nwarps) {
         const int64_t s = indptr[r], e = indptr[r + 1];
         double row = 0.0;
         for (int64_t o = s + lane; o < e; o += 32) {
             const int c = indices[o];
             const float v = data[o];
+            if (o > s && indices[o - 1] >= c) ++unordered;      // the neighbour's load: same or previous cache line
             if (c < 0 || c >= G) { atomicOr(err, 1); continue; }
             if (!isfinite(v)) { ++bad; continue; }
             if (v != 0.0f) atomicAdd(&col_sums[c], (double)v);
@@ -156,6 +159,7 @@ __global__ void stage_stats_kernel(const int64_t* __restrict__ indptr, const int
         }
     }
     if (bad) atomicAdd(n_nonfinite, bad);
+    if (unordered) atomicAdd(n_unordered, unordered);
     if (lane == 0) {
         if (empty) atomicAdd(n_empty_rows, empty);
         if (block_total != 0.0) atomicAdd(kept_total, block_total);

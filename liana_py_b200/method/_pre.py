@@ -160,6 +160,16 @@ class CSRBlock:
         return sparse.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape)
 
 
+def _canonical_copy(X):
+    """A copy of a SciPy CSR matrix in canonical format (indices sorted within a row, duplicate entries summed); the
+    cached format flags of the copy are dropped first, so a stale "is canonical" cannot turn `sum_duplicates` into a no-op."""
+    X = X.copy()
+    for flag in ("_has_canonical_format", "_has_sorted_indices"):
+        X.__dict__.pop(flag, None)
+    X.sum_duplicates()
+    return X
+
+
 def _row_block(X, dense, r0, r1):
     """Rows [r0, r1) of the caller's matrix WITHOUT copying its entries (views of the CSR arrays / of the dense rows)."""
     return X[r0:r1] if dense else CSRBlock(X, r0, r1)
@@ -187,9 +197,11 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
     else:
         if X.dtype != np.float32:
             X = X.astype(np.float32)
-        if not X.has_canonical_format:          # duplicate entries would break "one entry per (cell, gene)"
-            X = X.copy()
-            X.sum_duplicates()
+        # duplicate entries would break "one entry per (cell, gene)".  SciPy answers `has_canonical_format` with a pass
+        # over every index (0.5 ms per million entries) unless the matrix carries a cached answer; only a cached "no" is
+        # acted on here - otherwise the staging pass counts the out-of-order entries on the device (`n_unordered`, below)
+        if getattr(X, "_has_canonical_format", None) is False or getattr(X, "_has_sorted_indices", None) is False:
+            X = _canonical_copy(X)
     var_names = _make_unique(var_names)
     obs = adata.obs
 
@@ -229,17 +241,27 @@ def prepare_input(adata, groupby, min_cells, engine, groupby_subset=None, use_ra
         row_keep = keep.astype(np.uint8)
 
     sharded = dist is not None and dist.world_size > 1
-    r0, r1 = 0, X.shape[0]
-    Xs, keep_s = X, row_keep
-    if sharded:
-        r0, r1 = dist.row_block(X.shape[0], None if dense else X.indptr)
-        Xs = _row_block(X, dense, r0, r1)
+
+    def stage(X):
+        """Stage this rank's rows [r0, r1) of X (all of them with one rank); statistics summed over the ranks."""
+        r0, r1 = dist.row_block(X.shape[0], None if dense else X.indptr) if sharded else (0, X.shape[0])
+        Xs = _row_block(X, dense, r0, r1) if sharded else X
         keep_s = None if row_keep is None else row_keep[r0:r1]
-    stats = engine.stage_matrix_dense(Xs, keep_s) if dense else engine.stage_matrix(Xs, keep_s)
-    if sharded:
-        packed = dist.all_reduce_np(np.concatenate([stats["col_sums"], [stats["kept_total"], float(stats["n_nonfinite"]),
-                                                                        float(stats["n_empty_rows"])]]))
-        stats = dict(col_sums=packed[:-3], kept_total=float(packed[-3]), n_nonfinite=int(packed[-2]), n_empty_rows=int(packed[-1]))
+        stats = engine.stage_matrix_dense(Xs, keep_s) if dense else engine.stage_matrix(Xs, keep_s)
+        if sharded:
+            packed = dist.all_reduce_np(np.concatenate([stats["col_sums"], [stats["kept_total"], float(stats["n_nonfinite"]),
+                                                                            float(stats["n_empty_rows"]), float(stats["n_unordered"])]]))
+            stats = dict(col_sums=packed[:-4], kept_total=float(packed[-4]), n_nonfinite=int(packed[-3]),
+                         n_empty_rows=int(packed[-2]), n_unordered=int(packed[-1]))
+        return stats, r0, r1
+
+    stats, r0, r1 = stage(X)
+    if not dense and stats["n_unordered"]:
+        # some row is not strictly increasing (unsorted indices or duplicate entries; the count is summed over the ranks, so
+        # every rank takes this branch): SciPy's canonical form - duplicates summed, which is how the reference's SciPy
+        # arithmetic treats them - staged again
+        X = _canonical_copy(X)
+        stats, r0, r1 = stage(X)
     # empty features are removed (sum == 0 over ALL cells), empty cells only reported (`_pre.py:122-133`)
     empty = stats["col_sums"] == 0
     if empty.any():

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/lrperm.h but not exported"
     assert sorted(_engine.ABI_SYMBOLS) == declared
-    assert lib.lrperm_abi_version() == 4
+    assert lib.lrperm_abi_version() == 5
 
 
 def test_create_fails_loudly_without_gpu():

@@ -50,6 +50,10 @@ def test_dense_matrix_input():
     G.test_dense_matrix_input_equals_sparse_input()
 
 
+def test_non_canonical_matrix():
+    G.test_non_canonical_matrix_gives_the_frame_of_its_canonical_form()
+
+
 def test_cells_without_a_label():
     G.test_cells_without_a_label_identical_to_reference()
 

@@ -285,6 +285,41 @@ def test_dense_matrix_input_equals_sparse_input():
         compare(res, gold, "lr_means", "cellphone_pvals")
 
 
+def test_non_canonical_matrix_gives_the_frame_of_its_canonical_form():
+    """A CSR matrix whose rows are not sorted, or that stores a (cell, gene) entry in two pieces: SciPy - and so the
+    reference - computes with the matrix they add up to.  The staging pass counts the out-of-order entries
+    (`n_unordered`); only then does the host canonicalise (`sum_duplicates`) and stage again - with no pass of its own
+    over every index.  Both ways in: a fresh matrix (no cached SciPy flag: the device finds out) and one whose flag says no."""
+    adata, P, seed, ep = load_input("small300")
+    gold = pd.read_csv(os.path.join(GOLDEN, "small300_cellphonedb.csv.gz"), float_precision="round_trip")
+    X = adata.X.tocsr()
+    rng = np.random.default_rng(5)
+
+    def shuffled():
+        ix, dt = X.indices.copy(), X.data.copy()
+        for r in range(X.shape[0]):
+            s, e = X.indptr[r], X.indptr[r + 1]
+            p = rng.permutation(e - s)
+            ix[s:e], dt[s:e] = ix[s:e][p], dt[s:e][p]
+        return sparse.csr_matrix((dt, ix, X.indptr.copy()), shape=X.shape)
+
+    def split():                                         # every entry as two halves (exact in float32)
+        rep = np.repeat(np.arange(X.nnz), 2)
+        return sparse.csr_matrix((X.data[rep] * np.float32(0.5), X.indices[rep], X.indptr * 2), shape=X.shape)
+
+    for make in (shuffled, split):
+        for ask_scipy_first in (False, True):
+            Xn = make()
+            assert "_has_canonical_format" not in Xn.__dict__
+            if ask_scipy_first:
+                assert not Xn.has_canonical_format
+            other = AnnDataLite(X=Xn, obs=adata.obs.copy(), var=adata.var.copy())
+            res = li.mt.cellphonedb(other, groupby="cluster", use_raw=False, n_perms=P, seed=seed, expr_prop=ep,
+                                    inplace=False, perm_source="reference")
+            compare(res, gold, "lr_means", "cellphone_pvals")
+            assert other.X is Xn and Xn.nnz == (X.nnz if make is shuffled else 2 * X.nnz)      # the caller's matrix is not touched
+
+
 def test_cells_without_a_label_identical_to_reference():
     """NaN in `groupby`: the reference keeps such cells (`prep_check_adata` filters by category only) - they are
     shuffled with the others (`_get_mean_perms.py:46-52`: an all-False row of labels_mask), count in mat_mean / the

@@ -14,6 +14,17 @@ from liana_py_b200.testing._anndata_lite import AnnDataLite
 from liana_py_b200.testing._synth import make_synthetic_adata
 
 
+def count_unordered(X) -> int:
+    """Stored entries whose column is not greater than its predecessor's in the same row (what `stage_stats_kernel` counts)."""
+    ix, ip = np.asarray(X.indices, dtype=np.int64), np.asarray(X.indptr, dtype=np.int64)
+    if len(ix) < 2:
+        return 0
+    bad = np.diff(ix) <= 0                                   # bad[o - 1]: entry o against entry o - 1
+    starts = ip[:-1][(ip[:-1] > 0) & (ip[:-1] < len(ix)) & (np.diff(ip) > 0)]
+    bad[starts - 1] = False                                  # the first entry of a row has no predecessor
+    return int(bad.sum())
+
+
 class SciPyStage:
     """Stand-in of Engine.stage_matrix / staged_max / staged_cluster_stats (what the CUDA kernels compute)."""
 
@@ -23,7 +34,7 @@ class SciPyStage:
         rows = np.arange(X.shape[0]) if row_keep is None else np.flatnonzero(row_keep)
         return dict(col_sums=np.asarray(X.astype(np.float64).sum(axis=0)).ravel(),
                     kept_total=float(X[rows].astype(np.float64).sum()), n_nonfinite=int((~np.isfinite(X.data)).sum()),
-                    n_empty_rows=int((np.asarray(X.sum(axis=1)).ravel() == 0).sum()))
+                    n_empty_rows=int((np.asarray(X.sum(axis=1)).ravel() == 0).sum()), n_unordered=count_unordered(X))
 
     def stage_matrix_dense(self, X, row_keep=None):
         self.dense_calls = getattr(self, "dense_calls", 0) + 1
@@ -328,3 +339,39 @@ def test_global_codes_travel_in_the_narrowest_type_their_table_allows():
     assert cols["source"].dtype == np.uint8 and cols["source"].tolist() == [3, 19, 8]
     frame = PL.frame_from_codes(cols, g)
     assert frame["source"].tolist() == ["c3", "c19", "c8"] and frame["lr_means"].tolist() == [1.0, 2.0, 3.0]
+
+
+def test_out_of_order_rows_are_canonicalised_only_after_the_staging_pass_says_so():
+    """`prepare_input` does not ask SciPy whether the matrix is canonical (a pass over every index): the staging pass
+    reports `n_unordered`; only a non-zero count - or a cached SciPy flag that already says no - costs a canonical copy."""
+    class Counting(SciPyStage):
+        def __init__(self):
+            self.seen = []
+
+        def stage_matrix(self, X, row_keep=None):
+            out = super().stage_matrix(X, row_keep)
+            self.seen.append((int(X.nnz), out["n_unordered"]))
+            return out
+
+    ad = _ragged()
+    X = ad.X
+    rep = np.repeat(np.arange(X.nnz), 2)
+    split = sparse.csr_matrix((X.data[rep] * np.float32(0.5), X.indices[rep], X.indptr * 2), shape=X.shape)
+    rev = sparse.csr_matrix((np.concatenate([X.data[s:e][::-1] for s, e in zip(X.indptr[:-1], X.indptr[1:])]),
+                             np.concatenate([X.indices[s:e][::-1] for s, e in zip(X.indptr[:-1], X.indptr[1:])]),
+                             X.indptr.copy()), shape=X.shape)
+    want = _pre.prepare_input(ad, "cluster", min_cells=5, engine=SciPyStage(), want_max=True)
+    eng = Counting()
+    _pre.prepare_input(ad, "cluster", min_cells=5, engine=eng)
+    assert eng.seen == [(X.nnz, 0)] and "_has_canonical_format" not in X.__dict__            # canonical: one staging, SciPy not asked
+    for Xn in (split, rev):
+        eng = Counting()
+        other = AnnDataLite(X=Xn, obs=ad.obs.copy(), var=ad.var.copy())
+        got = _pre.prepare_input(other, "cluster", min_cells=5, engine=eng, want_max=True)
+        assert [n for n, _ in eng.seen] == [Xn.nnz, X.nnz] and eng.seen[0][1] > 0 and eng.seen[1][1] == 0
+        assert np.array_equal(got.var_names, want.var_names) and got.mat_max == want.mat_max and got.mat_mean == pytest.approx(want.mat_mean)
+        assert (eng.X != X).nnz == 0 and other.X is Xn and Xn.nnz == len(Xn.data)               # staged: the canonical form; input untouched
+        assert not Xn.has_canonical_format                                                    # now SciPy knows, and says no:
+        eng = Counting()
+        _pre.prepare_input(other, "cluster", min_cells=5, engine=eng)
+        assert eng.seen == [(X.nnz, 0)]                                                       # canonicalised before the first staging
