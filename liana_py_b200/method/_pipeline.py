@@ -41,9 +41,15 @@ def resolve_devices(device, devices):
 
 def observed_cpdb(ligand_means: np.ndarray, receptor_means: np.ndarray) -> np.ndarray:
     """float32 mean of the pair, zero where either side is zero (`_cellphonedb.py:25-27`)."""
-    zero = (ligand_means == 0) | (receptor_means == 0)
-    out = np.mean((ligand_means, receptor_means), axis=0)
-    out[zero] = 0
+    # `np.mean((a, b), axis=0)` of two float32 arrays is the float32 sum halved - written out, it skips the 2 x T copy
+    # NumPy makes of the tuple (halving is exact, so the bits are the same)
+    a, b = np.asarray(ligand_means), np.asarray(receptor_means)
+    if a.dtype != np.float32 or b.dtype != np.float32:
+        out = np.mean((a, b), axis=0)
+    else:
+        out = a + b
+        out *= np.float32(0.5)
+    out[(a == 0) | (b == 0)] = 0
     return out
 
 
@@ -438,8 +444,17 @@ def code_dtype(n_names: int):
 
 
 def to_global_codes(columns: dict, maps: dict) -> dict:
-    """Columns of a code frame (1-D arrays), the name columns re-coded into `global_name_tables`."""
-    return {c: (maps[c][v] if c in maps else np.ascontiguousarray(v)) for c, v in columns.items()}
+    """Columns of a code frame (1-D arrays), the name columns re-coded into `global_name_tables` (a take per column from
+    a table of a few thousand entries; NumPy releases the GIL for it, so the columns go through the thread pool)."""
+    names = list(columns)
+
+    def recode(c):
+        v = columns[c]
+        return maps[c].take(v) if c in maps else np.ascontiguousarray(v)
+
+    if len(names) < 2 or len(columns[names[0]]) < 65536:
+        return {c: recode(c) for c in names}
+    return dict(zip(names, _frame_pool().map(recode, names)))
 
 
 def sorted_code_columns(engine, frame: pd.DataFrame, by: str, ascending: bool) -> dict:
@@ -450,7 +465,9 @@ def sorted_code_columns(engine, frame: pd.DataFrame, by: str, ascending: bool) -
         frame = frame.sort_values(by=by, ascending=ascending)
         return {c: frame[c].values for c in frame.columns}
     order = engine.argsort(vals, descending=not ascending)
-    return {c: frame[c].values.take(order) for c in frame.columns}
+    cols = list(frame.columns)
+    arrays = [frame[c].values for c in cols]
+    return dict(zip(cols, _frame_pool().map(lambda a: a.take(order), arrays)))
 
 
 def frame_from_codes(columns: dict, global_tables: dict) -> pd.DataFrame:
