@@ -46,6 +46,18 @@ for name in ("cellphonedb", "rank_aggregate"):
     assert sum(ctx.all_gather_objects(len(own))) == len(one)
     if ctx.rank == 0:
         print(f"{name}.by_sample over {adata.obs[sk].nunique()} samples: {ctx.world_size} ranks == 1 rank ({len(one)} rows)", flush=True)
+# the same gather with every column going through the chunked pinned device -> host copy (gigabyte-sized frames take it by default)
+from liana_py_b200.method import _dist as _D
+_D.D2H_CHUNKED_MIN_BYTES = 1
+for g in (True, 0):
+    many = li.mt.cellphonedb.by_sample(adata, sk, dist=ctx, gather=g, **kw)
+    if many is not None:
+        pd.testing.assert_frame_equal(many, li.mt.cellphonedb.by_sample(adata, sk, **kw))
+    else:
+        li.mt.cellphonedb.by_sample(adata, sk, **kw)
+if ctx.rank == 0:
+    print("by_sample gather through the chunked device -> host copy: ok", flush=True)
+_D.D2H_CHUNKED_MIN_BYTES = 8 << 20
 # dense input and a min_cells filter through the sharded staging
 dense = make_synthetic_adata(3000, 400, 6, density=0.3, seed_data=7, seed_labels=8)
 dense.X = np.asarray(dense.X.todense(), dtype=np.float32)
