@@ -32,3 +32,17 @@ def test_reference_arm_prints_one_contract_line():
     for k in ("cells", "genes", "genes_in_resource", "clusters", "nnz", "nnz_full", "n_perms", "triples_kept"):
         assert k in d["config"], k
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_a_failing_secondary_section_does_not_cost_the_line():
+    """`bench._guarded`: the sections beside the primary numbers (configs[3] / [4], stress, CellChat, ...) record an
+    exception under their key instead of aborting the run before the JSON line is printed."""
+    import bench
+    assert bench._guarded("ok", lambda: {"value": 1}) == {"value": 1}
+
+    def boom():
+        raise RuntimeError("x" * 1000)
+
+    out = bench._guarded("stress_expr_prop0", boom)
+    assert out["section"] == "stress_expr_prop0" and out["error"].startswith("RuntimeError: xxx") and len(out["error"]) <= 300
+    json.dumps(out)
